@@ -1,0 +1,727 @@
+// sm_100a kernels + C ABI of the SMEM-seeding engine.
+//
+// Work decomposition (B200: 148 SMs, 126 MB L2, HBM3e):
+//   * a rank query is one aligned 64-byte bucket; four lanes ("quad") fetch it with one 128-bit
+//     load each, so one warp-wide load instruction moves eight buckets = eight independent
+//     FM chains.  The path is random-access and latency-bound: no TMA, no tensor cores.
+//   * k_sweep:  persistent grid, one quad per read (8 reads in flight per warp, dynamic read
+//     queue), bidirectional FM extension enumerating every maximal exact match of the read.
+//     All quads of a warp execute ONE uniform load/popcount section per iteration, so the
+//     eight chains' bucket fetches are always in flight together.
+//   * k_select: one thread per read, integer selection of the reference's records from the
+//     match list (BWA / LUT / RMI semantics), LUT gather and RMI predict + last-mile search
+//     fused in.
+//   * k_scan_* / k_gather_records: counts -> offsets -> records in (read, emission) order.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/genie_smem.h"
+#include "host_common.hpp"
+#include "select_logic.cuh"
+
+namespace gsm {
+
+#define GSM_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return fail(GSM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+constexpr int SWEEP_THREADS = 128;
+constexpr int SWEEP_CAP = 32;        // candidates kept in shared memory per quad
+constexpr int SELECT_THREADS = 128;
+
+__device__ __forceinline__ U4 ldg_u4(const uint4* p) {
+    uint4 v = __ldg(p);
+    return U4{v.x, v.y, v.z, v.w};
+}
+
+// One FM extension step executed by all quads of a warp together.  Every lane passes its quad's
+// operands; `active` quads get their result, inactive ones issue no loads.
+__device__ __forceinline__ StepOut quad_step(const uint4* __restrict__ bk, uint32_t P0, uint32_t P1, uint32_t ch,
+                                             uint32_t Cc, uint32_t primary, uint32_t ql, bool active) {
+    uint32_t b0, r0, b1, r1;
+    split192(P0, b0, r0);
+    split192(P1, b1, r1);
+    U4 v0 = U4{0, 0, 0, 0}, v1;
+    if (active) v0 = ldg_u4(bk + (size_t)b0 * 4 + ql);
+    v1 = v0;
+    if (active && b1 != b0) v1 = ldg_u4(bk + (size_t)b1 * 4 + ql);
+    uint32_t packed = part_counts(v0, r0, ch, ql) | (part_counts(v1, r1, ch, ql) << 16);
+    packed += __shfl_xor_sync(FULL, packed, 1);
+    packed += __shfl_xor_sync(FULL, packed, 2);
+    uint32_t he0, hl0, he1, hl1;
+    header_counts(v0, ch, he0, hl0);
+    header_counts(v1, ch, he1, hl1);
+    const uint32_t A = __shfl_sync(FULL, he0, 0, 4);
+    const uint32_t B = __shfl_sync(FULL, he1, 0, 4);
+    const uint32_t D = __shfl_sync(FULL, hl1 - hl0, 0, 4);
+    const uint32_t eq0 = A + (packed & 0xFFu);
+    const uint32_t eq1 = B + ((packed >> 16) & 0xFFu);
+    const uint32_t ltd = D + ((packed >> 24) & 0xFFu) - ((packed >> 8) & 0xFFu);
+    return finish_step(eq0, 0u, eq1, ltd, P0, P1, ch, Cc, primary);
+}
+
+// ===================================================================================== sweep
+struct SweepArgs {
+    const uint4* fwd;
+    const uint4* rev;
+    IndexMeta meta;
+    const uint4* reads;
+    const uint32_t* chunk_off;
+    const uint32_t* len;
+    uint32_t n_reads;
+    uint32_t max_chunks;     // 16-byte chunks of the longest read
+    uint32_t max_len;
+    uint4* mem_pool;
+    unsigned long long mem_cap;
+    uint32_t* mem_off;
+    uint32_t* mem_cnt;
+    uint4* scratch;          // per quad: [0, max_len) match staging, [max_len, 2 max_len) candidate spill
+    unsigned long long* counters;
+};
+
+struct DevSweepCtx {
+    const SweepArgs& a;
+    uint32_t* words;      // shared: packed read
+    uint32_t* cj;         // shared: candidate arrays
+    uint32_t* clo;
+    uint32_t* ccnt;
+    uint4* stage;         // global: match staging of this quad
+    uint4* spill;         // global: candidate spill of this quad
+    uint32_t ql, qmask, qbase;
+
+    __device__ __forceinline__ bool fetch(uint32_t& rid, uint32_t& L) {
+        unsigned long long r = 0;
+        if (ql == 0) r = atomicAdd(&a.counters[3], 1ull);
+        r = __shfl_sync(qmask, r, qbase);
+        if (r >= a.n_reads) return false;
+        rid = (uint32_t)r;
+        L = __ldg(a.len + rid);
+        const uint32_t off = __ldg(a.chunk_off + rid);
+        const uint32_t nch = (L + 63u) >> 6;
+        __syncwarp(qmask);                       // everyone is done with the previous read's words
+        for (uint32_t c = ql; c < nch; c += 4) {
+            uint4 v = __ldg(a.reads + (size_t)off + c);
+            reinterpret_cast<uint4*>(words)[c] = v;
+        }
+        __syncwarp(qmask);
+        return true;
+    }
+    __device__ __forceinline__ uint32_t base(uint32_t pos) const { return base_msb(words, pos); }
+    __device__ __forceinline__ void cand_put(uint32_t i, uint32_t j, uint32_t lo, uint32_t cnt) {
+        if (i < SWEEP_CAP) { cj[i] = j; clo[i] = lo; ccnt[i] = cnt; }      // same value from all 4 lanes
+        else if (ql == 0) __stcg(spill + (i - SWEEP_CAP), make_uint4(j, lo, cnt, 0u));
+    }
+    __device__ __forceinline__ void cand_get(uint32_t i, uint32_t& j, uint32_t& lo, uint32_t& cnt) const {
+        if (i < SWEEP_CAP) { j = cj[i]; lo = clo[i]; cnt = ccnt[i]; }
+        else { uint4 v = __ldcg(spill + (i - SWEEP_CAP)); j = v.x; lo = v.y; cnt = v.z; }
+    }
+    __device__ __forceinline__ void cand_sync() { __syncwarp(qmask); }
+    __device__ __forceinline__ void emit(uint32_t idx, MemEntry e) {
+        if (ql == 0) __stcg(stage + idx, make_uint4(e.se, e.lo, e.cnt, e.sweep));
+    }
+    __device__ __forceinline__ void finish(uint32_t rid, uint32_t n) {
+        __syncwarp(qmask);
+        unsigned long long off = 0;
+        if (ql == 0) off = atomicAdd(&a.counters[0], (unsigned long long)n);
+        off = __shfl_sync(qmask, off, qbase);
+        if (off + n > a.mem_cap) {
+            if (ql == 0) { atomicOr(&a.counters[2], 1ull); a.mem_off[rid] = 0; a.mem_cnt[rid] = 0; }
+            return;
+        }
+        for (uint32_t k = ql; k < n; k += 4) a.mem_pool[off + k] = __ldcg(stage + k);
+        if (ql == 0) { a.mem_off[rid] = (uint32_t)off; a.mem_cnt[rid] = n; }
+    }
+};
+
+__global__ void __launch_bounds__(SWEEP_THREADS, 8) k_sweep(const SweepArgs a) {
+    extern __shared__ uint4 smem4[];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ql = lane & 3u;
+    const uint32_t quad_in_block = threadIdx.x >> 2;
+    const uint32_t quad_words = a.max_chunks * 4u + 3u * SWEEP_CAP;     // uint32 per quad
+    uint32_t* qs = reinterpret_cast<uint32_t*>(smem4) + (size_t)quad_in_block * quad_words;
+    const size_t gq = (size_t)blockIdx.x * (SWEEP_THREADS / 4) + quad_in_block;
+    DevSweepCtx ctx{a,
+                    qs,
+                    qs + a.max_chunks * 4u,
+                    qs + a.max_chunks * 4u + SWEEP_CAP,
+                    qs + a.max_chunks * 4u + 2 * SWEEP_CAP,
+                    a.scratch + gq * 2 * a.max_len,
+                    a.scratch + gq * 2 * a.max_len + a.max_len,
+                    ql,
+                    0xFu << (lane & ~3u),
+                    lane & ~3u};
+    Sweeper<DevSweepCtx> sw;
+    for (;;) {
+        uint32_t P0 = 0, P1 = 0, ch = 0;
+        bool rev = false;
+        const bool need = sw.prepare(ctx, a.meta, P0, P1, ch, rev);
+        if (!__any_sync(FULL, need)) break;
+        const StepOut r = quad_step(rev ? a.rev : a.fwd, P0, P1, ch, a.meta.C[ch], rev ? a.meta.prim_r : a.meta.prim_f, ql, need);
+        if (need) sw.consume(ctx, a.meta, r);
+    }
+}
+
+// ===================================================================================== select
+struct SelectArgs {
+    const uint4* fwd;
+    IndexMeta meta;
+    uint64_t n_bases;
+    const uint32_t* sa;
+    const uint32_t* text;
+    const uint32_t* reads;      // as words
+    const uint32_t* chunk_off;
+    const uint32_t* len;
+    uint32_t n_reads;
+    uint32_t max_len;
+    uint32_t read_id_base;
+    uint32_t min_len;
+    uint32_t K;
+    const uint2* lut;
+    RmiModel rmi;
+    uint4* mem_pool;
+    const uint32_t* mem_off;
+    const uint32_t* mem_cnt;
+    uint4* stage;               // per thread: max_len records
+    uint4* rec_tmp;
+    unsigned long long rec_cap;
+    uint32_t* rec_tmp_off;
+    uint32_t* rec_cnt;
+    uint8_t* read_status;
+    unsigned long long* counters;
+};
+
+template <int METHOD>
+struct DevSelCtx {
+    const SelectArgs& a;
+    const uint32_t* words;
+    uint4* mems;
+    uint4* stage;
+    uint32_t L, K, n_mems, min_len, rid, n_rec;
+    bool raised;
+
+    __device__ __forceinline__ MemEntry mem(uint32_t k) const {
+        uint4 v = mems[k];
+        return MemEntry{v.x, v.y, v.z, v.w};
+    }
+    __device__ __forceinline__ uint32_t base(uint32_t pos) const { return (__ldg(words + (pos >> 4)) >> (30u - 2u * (pos & 15u))) & 3u; }
+    __device__ __forceinline__ bool failed() const { return raised; }
+
+    __device__ void interval(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt) {
+        lo = 0; cnt = a.meta.n_rows;
+        const uint4* fwd = a.fwd;
+        auto load = [fwd](uint64_t idx) { return ldg_u4(fwd + idx); };
+        for (uint32_t p = j; p > i; --p) {
+            const uint32_t c = base(p - 1);
+            StepOut r = step_single(load, lo, lo + cnt, c, a.meta.C[c], a.meta.prim_f);
+            lo = r.lo_new; cnt = r.cnt_new;
+            if (cnt == 0) return;
+        }
+    }
+
+    __device__ bool seed(uint32_t c, int64_t& lo, int64_t& hi) {
+        const uint32_t* w = words;
+        auto rd = [w](uint64_t i) { return __ldg(w + i); };
+        const uint64_t code = kmer_code(rd, c, K);
+        if (METHOD == GSM_METHOD_LUT) {
+            const uint2 e = __ldg(a.lut + code);
+            lo = e.x; hi = (int64_t)e.x + e.y - 1;
+            return e.y != 0;
+        }
+        const uint32_t* sa = a.sa;
+        const uint32_t* tx = a.text;
+        auto sal = [sa](uint64_t r) { return __ldg(sa + r); };
+        auto txl = [tx](uint64_t i) { return __ldg(tx + i); };
+        RmiTable<decltype(sal), decltype(txl)> t{sal, txl, (int64_t)a.meta.n_rows, (int64_t)a.n_bases, K, false};
+        double pred;
+        t.lookup(a.rmi, code, pred, lo, hi);
+        if (t.raised) { raised = true; return false; }
+        return hi >= lo;
+    }
+
+    __device__ bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi) {
+        if (METHOD == GSM_METHOD_LUT) {
+            // check_sequential (SMEM.py:196-202) on two TRUE k-mer intervals: some occurrence of
+            // q[c:c+K] is followed one base later by q[pc:pc+K]  <=>  the k-mers overlap
+            // consistently and q[c] + q[pc:pc+K] occurs (one backward step on the second seed).
+            for (uint32_t t = 1; t < K; ++t)
+                if (base(c + t) != base(pc + t - 1)) return false;
+            const uint32_t ch = base(c);
+            const uint4* fwd = a.fwd;
+            auto load = [fwd](uint64_t idx) { return ldg_u4(fwd + idx); };
+            StepOut r = step_single(load, (uint32_t)plo, (uint32_t)phi + 1u, ch, a.meta.C[ch], a.meta.prim_f);
+            return r.cnt_new != 0;
+        }
+        // RMI: literal check on the RETURNED intervals (SMEM.py:262-265), which may be wrong
+        const int64_t n = (int64_t)a.meta.n_rows;
+        for (int64_t x = clo; x <= chi; ++x) {
+            const uint32_t px = __ldg(a.sa + (x < 0 ? x + n : x));
+            for (int64_t y = plo; y <= phi; ++y)
+                if (px + 1u == __ldg(a.sa + (y < 0 ? y + n : y))) return true;
+        }
+        return false;
+    }
+
+    __device__ __forceinline__ void emit(uint32_t i, uint32_t j, int64_t lo, int64_t hi) {
+        stage[n_rec++] = make_uint4(a.read_id_base + rid, i | (j << 16), (uint32_t)lo, (uint32_t)hi);
+    }
+};
+
+template <int METHOD>
+__global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    for (size_t rid = gtid; rid < a.n_reads; rid += nthreads) {
+        DevSelCtx<METHOD> c{a,
+                            a.reads + (size_t)__ldg(a.chunk_off + rid) * 4,
+                            a.mem_pool + a.mem_off[rid],
+                            a.stage + gtid * a.max_len,
+                            __ldg(a.len + rid), a.K, a.mem_cnt[rid], a.min_len, (uint32_t)rid, 0u, false};
+        // the sweep emits each sweep's matches longest-end first: put every segment in ascending order
+        for (uint32_t s0 = 0; s0 < c.n_mems;) {
+            uint32_t s1 = s0 + 1;
+            const uint32_t id = c.mems[s0].w;
+            while (s1 < c.n_mems && c.mems[s1].w == id) ++s1;
+            for (uint32_t x = s0, y = s1 - 1; x < y; ++x, --y) {
+                uint4 t = c.mems[x]; c.mems[x] = c.mems[y]; c.mems[y] = t;
+            }
+            s0 = s1;
+        }
+        uint8_t status = GSM_READ_OK;
+        if (METHOD == GSM_METHOD_BWA) Selector<DevSelCtx<METHOD>>::run_bwa(c);
+        else if (c.L < c.K) status = GSM_READ_TOO_SHORT;
+        else Selector<DevSelCtx<METHOD>>::run_seeded(c);
+        if (c.raised) { status = GSM_READ_REF_RAISES; c.n_rec = 0; }
+        unsigned long long off = atomicAdd(&a.counters[1], (unsigned long long)c.n_rec);
+        if (off + c.n_rec > a.rec_cap) {
+            atomicOr(&a.counters[2], 2ull);
+            a.rec_tmp_off[rid] = 0; a.rec_cnt[rid] = 0;
+        } else {
+            for (uint32_t k = 0; k < c.n_rec; ++k) a.rec_tmp[off + k] = c.stage[k];
+            a.rec_tmp_off[rid] = (uint32_t)off; a.rec_cnt[rid] = c.n_rec;
+        }
+        a.read_status[rid] = status;
+    }
+}
+
+// ===================================================================================== scan + gather
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* total) {
+    __shared__ unsigned long long warp_sums[SCAN_THREADS / 32];
+    __shared__ unsigned long long tot;
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    unsigned long long x = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long y = __shfl_up_sync(FULL, x, d);
+        if (lane >= (uint32_t)d) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long s = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0ull;
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long y = __shfl_up_sync(FULL, s, d);
+            if (lane >= (uint32_t)d) s += y;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;
+        if (lane == SCAN_THREADS / 32 - 1) tot = s;
+    }
+    __syncthreads();
+    unsigned long long base = wid ? warp_sums[wid - 1] : 0ull;
+    *total = tot;
+    unsigned long long r = base + x - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* cnt, uint64_t n, unsigned long long* off, unsigned long long* tile_sums) {
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    unsigned long long v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? cnt[base + i] : 0u;
+        sum += v[i];
+    }
+    unsigned long long total;
+    unsigned long long ex = block_exclusive_scan(sum, &total);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) off[base + i] = ex;
+        ex += v[i];
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_top(unsigned long long* tile_sums, uint64_t n_tiles, unsigned long long* grand_total) {
+    unsigned long long carry = 0;
+    for (uint64_t b = 0; b < n_tiles; b += SCAN_THREADS) {
+        unsigned long long v = (b + threadIdx.x < n_tiles) ? tile_sums[b + threadIdx.x] : 0ull;
+        unsigned long long total;
+        unsigned long long ex = block_exclusive_scan(v, &total);
+        if (b + threadIdx.x < n_tiles) tile_sums[b + threadIdx.x] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(unsigned long long* off, uint64_t n, const unsigned long long* tile_sums, const unsigned long long* grand_total) {
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    const unsigned long long add = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+        if (base + i < n) off[base + i] += add;
+    if (blockIdx.x == 0 && threadIdx.x == 0) off[n] = *grand_total;
+}
+
+__global__ void k_gather_records(const uint4* rec_tmp, const uint32_t* tmp_off, const uint32_t* cnt, const unsigned long long* off,
+                                 uint64_t n_reads, uint4* out, unsigned long long out_cap, unsigned long long* counters) {
+    // one quad per read: records are 16 bytes, a read has a handful of them
+    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const uint32_t ql = threadIdx.x & 3u;
+    if (q >= n_reads) return;
+    const uint32_t n = cnt[q];
+    const unsigned long long dst = off[q];
+    if (dst + n > out_cap) { if (ql == 0 && n) atomicOr(&counters[2], 4ull); return; }
+    const uint32_t src = tmp_off[q];
+    for (uint32_t k = ql; k < n; k += 4) out[dst + k] = rec_tmp[(size_t)src + k];
+}
+
+// ===================================================================================== batched primitives
+struct BackArgs {
+    const uint4* fwd;
+    IndexMeta meta;
+    const uint32_t* reads;
+    const uint32_t* chunk_off;
+    const uint32_t* len;
+    uint64_t n_reads;
+    uint32_t* lo;
+    uint32_t* cnt;
+};
+
+// exact_match_back_prop (reference SMEM/ExactMatch.py:132-151): one quad per read.
+__global__ void __launch_bounds__(128) k_backsearch(const BackArgs a) {
+    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const uint32_t ql = threadIdx.x & 3u;
+    const bool valid = q < a.n_reads;
+    uint32_t L = 0;
+    const uint32_t* w = a.reads;
+    if (valid) { L = __ldg(a.len + q); w = a.reads + (size_t)__ldg(a.chunk_off + q) * 4; }
+    uint32_t lo = 0, cnt = a.meta.n_rows;
+    int32_t p = (int32_t)L - 1;
+    for (;;) {
+        const bool act = valid && p >= 0 && cnt != 0;
+        if (!__any_sync(FULL, act)) break;
+        uint32_t ch = 0;
+        if (act) ch = (__ldg(w + (p >> 4)) >> (30u - 2u * ((uint32_t)p & 15u))) & 3u;
+        StepOut r = quad_step(a.fwd, lo, lo + cnt, ch, a.meta.C[ch], a.meta.prim_f, ql, act);
+        if (act) { lo = r.lo_new; cnt = r.cnt_new; --p; }
+    }
+    if (valid && ql == 0) { a.lo[q] = lo; a.cnt[q] = cnt; }
+}
+
+// exact_match_back_prop_add_one (reference SMEM/ExactMatch.py:155-171)
+__global__ void __launch_bounds__(128) k_add_one(const uint4* fwd, IndexMeta meta, uint64_t n, const uint8_t* base, uint32_t* lo, uint32_t* cnt) {
+    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const uint32_t ql = threadIdx.x & 3u;
+    const bool act = q < n && cnt[q] != 0;
+    uint32_t l = 0, c = 0, ch = 0;
+    if (act) { l = lo[q]; c = cnt[q]; ch = base[q] & 3u; }
+    StepOut r = quad_step(fwd, l, l + c, ch, meta.C[ch], meta.prim_f, ql, act);
+    if (act && ql == 0) { lo[q] = r.lo_new; cnt[q] = r.cnt_new; }
+}
+
+// get_position(s) (reference SMEM/ExactMatch.py:191-199)
+__global__ void k_sa_lookup(const uint32_t* sa, uint64_t n_rows, uint64_t n, const uint32_t* rows, uint32_t* pos) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pos[i] = rows[i] < n_rows ? __ldg(sa + rows[i]) : 0u;
+}
+
+// LUT.generate_lut (reference SMEM/LUT.py:15-35) as a dense table: one thread per k-mer code.
+__global__ void k_lut_build(const uint4* fwd, IndexMeta meta, uint32_t K, uint64_t n_codes, uint2* table) {
+    const uint64_t code = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (code >= n_codes) return;
+    auto load = [fwd](uint64_t idx) { return ldg_u4(fwd + idx); };
+    uint32_t lo = 0, cnt = meta.n_rows;
+    for (uint32_t t = 0; t < K && cnt; ++t) {
+        const uint32_t c = (uint32_t)(code >> (2 * t)) & 3u;      // backward search: last base first
+        StepOut r = step_single(load, lo, lo + cnt, c, meta.C[c], meta.prim_f);
+        lo = r.lo_new; cnt = r.cnt_new;
+    }
+    table[code] = make_uint2(lo, cnt);
+}
+
+// RMI_LUT.get_suffix_rmi (reference SMEM/RMI_LUT.py:67-78) for a batch of codes
+__global__ void k_rmi_lookup(const uint32_t* sa, const uint32_t* text, uint64_t n_rows, uint64_t n_bases, RmiModel m, uint64_t n,
+                             const uint64_t* codes, double* pred, int64_t* lo, int64_t* hi, uint8_t* status) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto sal = [sa](uint64_t r) { return __ldg(sa + r); };
+    auto txl = [text](uint64_t w) { return __ldg(text + w); };
+    RmiTable<decltype(sal), decltype(txl)> t{sal, txl, (int64_t)n_rows, (int64_t)n_bases, m.K, false};
+    double p; int64_t l, h;
+    t.lookup(m, codes[i], p, l, h);
+    pred[i] = p; lo[i] = l; hi[i] = h;
+    status[i] = t.raised ? GSM_READ_REF_RAISES : GSM_READ_OK;
+}
+
+// Random aligned 64-byte gather with the rank kernels' access shape (quad = 4 x 16 B).
+// dependent != 0: each quad runs a pointer chase (latency-bound, like one FM chain);
+// dependent == 0: independent fetches (the bandwidth ceiling for 64-byte random access).
+__global__ void __launch_bounds__(128) k_gather_probe(const uint4* buf, uint64_t n_buckets, uint32_t iters, uint32_t dependent, unsigned long long* sink) {
+    const uint64_t gq = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const uint32_t ql = threadIdx.x & 3u;
+    uint64_t state = gq * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    uint32_t acc = 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+        state = state * 6364136223846793005ull + 1442695040888963407ull;
+        uint64_t idx = (state >> 17) % n_buckets;
+        uint4 v = __ldg(buf + idx * 4 + ql);
+        uint32_t x = v.x ^ v.y ^ v.z ^ v.w;
+        acc += x;
+        if (dependent) {
+            x ^= __shfl_xor_sync(FULL, x, 1);
+            x ^= __shfl_xor_sync(FULL, x, 2);
+            state ^= x;
+        }
+    }
+    if (acc == 0x7FFFFFFFu) atomicAdd(sink, 1ull);
+}
+
+}  // namespace gsm
+
+// ===================================================================================== C ABI
+using namespace gsm;
+
+namespace {
+
+IndexMeta make_meta(const gsm_dev_index* ix) {
+    IndexMeta m;
+    for (int c = 0; c < 4; ++c) { m.C[c] = ix->C[c]; m.cnt[c] = ix->C[c + 1] - ix->C[c]; }
+    m.prim_f = ix->primary_fwd; m.prim_r = ix->primary_rev; m.n_rows = (uint32_t)ix->n_rows;
+    return m;
+}
+
+int device_ready() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(GSM_E_NODEVICE, "no CUDA device visible: libgenie_smem has no CPU fallback");
+    }
+    return GSM_OK;
+}
+
+size_t sweep_smem_bytes(uint32_t max_len) {
+    const uint32_t max_chunks = (max_len + 63u) / 64u;
+    return (size_t)(SWEEP_THREADS / 4) * (max_chunks * 4u + 3u * SWEEP_CAP) * sizeof(uint32_t);
+}
+
+int sweep_grid(uint32_t max_len, int* blocks) {
+    int dev = 0, sms = 0, per_sm = 0;
+    GSM_CUDA(cudaGetDevice(&dev));
+    GSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const size_t smem = sweep_smem_bytes(max_len);
+    if (smem > 48 * 1024) GSM_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep, SWEEP_THREADS, smem));
+    if (per_sm < 1) return fail(GSM_E_CAPACITY, "read length too large for the sweep kernel's shared memory");
+    *blocks = sms * per_sm;
+    return GSM_OK;
+}
+
+int select_grid(int* blocks) {
+    int dev = 0, sms = 0;
+    GSM_CUDA(cudaGetDevice(&dev));
+    GSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    *blocks = sms * 8;
+    return GSM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gsm_smem_workspace_info(uint64_t n_reads, uint32_t max_len, gsm_workspace_info* out) {
+    if (!out || max_len == 0 || max_len > 65535) return fail(GSM_E_INVALID, "gsm_smem_workspace_info: max_len must be in 1..65535");
+    int st = device_ready();
+    if (st) return st;
+    int sb = 0, lb = 0;
+    if ((st = sweep_grid(max_len, &sb))) return st;
+    if ((st = select_grid(&lb))) return st;
+    const uint64_t sweep_bytes = (uint64_t)sb * (SWEEP_THREADS / 4) * 2ull * max_len * 16ull;
+    const uint64_t sel_bytes = (uint64_t)lb * SELECT_THREADS * (uint64_t)max_len * 16ull;
+    out->quad_scratch_bytes = sweep_bytes > sel_bytes ? sweep_bytes : sel_bytes;
+    out->scan_tmp_bytes = ((n_reads + SCAN_TILE - 1) / SCAN_TILE + 2) * 8ull;
+    out->grid_blocks = (uint32_t)sb;
+    out->block_threads = SWEEP_THREADS;
+    return GSM_OK;
+}
+
+int gsm_backsearch_batch(const gsm_dev_index* ix, const gsm_dev_reads* rd, uint32_t* lo, uint32_t* cnt, void* stream) {
+    if (!ix || !rd || !lo || !cnt) return fail(GSM_E_INVALID, "null");
+    int st = device_ready();
+    if (st) return st;
+    if (rd->n_reads == 0) return GSM_OK;
+    BackArgs a{(const uint4*)ix->fwd_buckets, make_meta(ix), (const uint32_t*)rd->packed, rd->chunk_off, rd->len, rd->n_reads, lo, cnt};
+    const uint64_t threads = rd->n_reads * 4;
+    k_backsearch<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_backsearch_add_one_batch(const gsm_dev_index* ix, uint64_t n, const uint8_t* base, uint32_t* lo, uint32_t* cnt, void* stream) {
+    if (!ix || !base || !lo || !cnt) return fail(GSM_E_INVALID, "null");
+    int st = device_ready();
+    if (st) return st;
+    if (n == 0) return GSM_OK;
+    k_add_one<<<(unsigned)((n * 4 + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const uint4*)ix->fwd_buckets, make_meta(ix), n, base, lo, cnt);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_sa_lookup_batch(const gsm_dev_index* ix, uint64_t n, const uint32_t* rows, uint32_t* pos, void* stream) {
+    if (!ix || !ix->sa || !rows || !pos) return fail(GSM_E_INVALID, "gsm_sa_lookup_batch needs the suffix array on the device");
+    int st = device_ready();
+    if (st) return st;
+    if (n == 0) return GSM_OK;
+    k_sa_lookup<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ix->sa, ix->n_rows, n, rows, pos);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_lut_build(const gsm_dev_index* ix, uint32_t K, uint32_t* table, void* stream) {
+    if (!ix || !table || K < 1 || K > 16) return fail(GSM_E_INVALID, "gsm_lut_build: K must be in 1..16");
+    int st = device_ready();
+    if (st) return st;
+    const uint64_t n_codes = 1ull << (2 * K);
+    k_lut_build<<<(unsigned)((n_codes + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)ix->fwd_buckets, make_meta(ix), K, n_codes, (uint2*)table);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+static int fill_rmi(const gsm_dev_rmi* rmi, RmiModel* m) {
+    memset(m, 0, sizeof(*m));
+    if (!rmi || !rmi->level_sizes || !rmi->coef || !rmi->intercept) return fail(GSM_E_INVALID, "RMI parameters missing");
+    if (rmi->n_levels < 1 || rmi->n_levels > 8 || rmi->K < 1 || rmi->K > 32) return fail(GSM_E_INVALID, "RMI: 1..8 levels, K in 1..32");
+    m->K = rmi->K; m->n_levels = rmi->n_levels; m->coef = rmi->coef; m->intercept = rmi->intercept;
+    uint32_t off = 0;
+    for (uint32_t l = 0; l < rmi->n_levels; ++l) { m->level_size[l] = rmi->level_sizes[l]; m->level_off[l] = off; off += rmi->level_sizes[l]; }
+    return GSM_OK;
+}
+
+int gsm_rmi_lookup_batch(const gsm_dev_index* ix, const gsm_dev_rmi* rmi, uint64_t n, const uint64_t* codes, double* pred,
+                         int64_t* lo, int64_t* hi, uint8_t* status, void* stream) {
+    if (!ix || !ix->sa || !ix->text2bit || !codes || !pred || !lo || !hi || !status) return fail(GSM_E_INVALID, "gsm_rmi_lookup_batch: null argument (needs sa + text on the device)");
+    int st = device_ready();
+    if (st) return st;
+    RmiModel m;
+    if ((st = fill_rmi(rmi, &m))) return st;
+    if (n == 0) return GSM_OK;
+    k_rmi_lookup<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(ix->sa, ix->text2bit, ix->n_rows, ix->n_rows - 1, m, n, codes, pred, lo, hi, status);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_smem_batch(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd, uint32_t min_len, uint32_t K, const uint32_t* lut,
+                   const gsm_dev_rmi* rmi, gsm_workspace* ws, void* stream_) {
+    if (!ix || !rd || !ws) return fail(GSM_E_INVALID, "null");
+    if (!ix->fwd_buckets || !ix->rev_buckets) return fail(GSM_E_INVALID, "gsm_smem_batch needs both BWT directions on the device");
+    if (rd->max_len == 0 || rd->max_len > 65535) return fail(GSM_E_INVALID, "max_len must be in 1..65535");
+    if (rd->n_reads >= (1ull << 32)) return fail(GSM_E_INVALID, "at most 2^32-1 reads per batch");
+    if (ws->mem_cap >= (1ull << 32) || ws->rec_cap >= (1ull << 32)) return fail(GSM_E_INVALID, "pool capacities must be < 2^32 entries");
+    if (method == GSM_METHOD_LUT && (!lut || K < 1 || K > 16)) return fail(GSM_E_INVALID, "LUT method needs a table and K in 1..16");
+    RmiModel rm;
+    memset(&rm, 0, sizeof(rm));
+    if (method == GSM_METHOD_RMI) {
+        int st = fill_rmi(rmi, &rm);
+        if (st) return st;
+        if (!ix->sa || !ix->text2bit) return fail(GSM_E_INVALID, "RMI method needs the suffix array and packed text on the device");
+        K = rmi->K;
+    }
+    if (method < 0 || method > 2) return fail(GSM_E_INVALID, "unknown method");
+    int st = device_ready();
+    if (st) return st;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int sb = 0, lb = 0;
+    if ((st = sweep_grid(rd->max_len, &sb))) return st;
+    if ((st = select_grid(&lb))) return st;
+    const uint64_t need_sweep = (uint64_t)sb * (SWEEP_THREADS / 4) * 2ull * rd->max_len * 16ull;
+    const uint64_t need_sel = (uint64_t)lb * SELECT_THREADS * (uint64_t)rd->max_len * 16ull;
+    if (ws->quad_scratch_bytes < need_sweep || ws->quad_scratch_bytes < need_sel) return fail(GSM_E_CAPACITY, "quad_scratch too small (see gsm_smem_workspace_info)");
+    const uint64_t n_tiles = (rd->n_reads + SCAN_TILE - 1) / SCAN_TILE;
+    if (ws->scan_tmp_bytes < (n_tiles + 2) * 8) return fail(GSM_E_CAPACITY, "scan_tmp too small");
+    GSM_CUDA(cudaMemsetAsync(ws->counters, 0, 8 * sizeof(uint64_t), stream));
+    if (rd->n_reads == 0) {
+        GSM_CUDA(cudaMemsetAsync(ws->rec_off, 0, sizeof(uint64_t), stream));
+        return GSM_OK;
+    }
+    const IndexMeta meta = make_meta(ix);
+    SweepArgs sa;
+    sa.fwd = (const uint4*)ix->fwd_buckets; sa.rev = (const uint4*)ix->rev_buckets; sa.meta = meta;
+    sa.reads = (const uint4*)rd->packed; sa.chunk_off = rd->chunk_off; sa.len = rd->len; sa.n_reads = (uint32_t)rd->n_reads;
+    sa.max_chunks = (rd->max_len + 63u) / 64u; sa.max_len = rd->max_len;
+    sa.mem_pool = (uint4*)ws->mem_pool; sa.mem_cap = ws->mem_cap; sa.mem_off = ws->mem_off; sa.mem_cnt = ws->mem_cnt;
+    sa.scratch = (uint4*)ws->quad_scratch; sa.counters = (unsigned long long*)ws->counters;
+    k_sweep<<<sb, SWEEP_THREADS, sweep_smem_bytes(rd->max_len), stream>>>(sa);
+    GSM_CUDA(cudaGetLastError());
+
+    SelectArgs se;
+    se.fwd = (const uint4*)ix->fwd_buckets; se.meta = meta; se.n_bases = ix->n_rows - 1; se.sa = ix->sa; se.text = ix->text2bit;
+    se.reads = (const uint32_t*)rd->packed; se.chunk_off = rd->chunk_off; se.len = rd->len; se.n_reads = (uint32_t)rd->n_reads;
+    se.max_len = rd->max_len; se.read_id_base = rd->read_id_base; se.min_len = min_len; se.K = K; se.lut = (const uint2*)lut; se.rmi = rm;
+    se.mem_pool = (uint4*)ws->mem_pool; se.mem_off = ws->mem_off; se.mem_cnt = ws->mem_cnt; se.stage = (uint4*)ws->quad_scratch;
+    se.rec_tmp = (uint4*)ws->rec_tmp; se.rec_cap = ws->rec_cap; se.rec_tmp_off = ws->rec_tmp_off; se.rec_cnt = ws->rec_cnt;
+    se.read_status = ws->read_status; se.counters = (unsigned long long*)ws->counters;
+    if (method == GSM_METHOD_BWA) k_select<GSM_METHOD_BWA><<<lb, SELECT_THREADS, 0, stream>>>(se);
+    else if (method == GSM_METHOD_LUT) k_select<GSM_METHOD_LUT><<<lb, SELECT_THREADS, 0, stream>>>(se);
+    else k_select<GSM_METHOD_RMI><<<lb, SELECT_THREADS, 0, stream>>>(se);
+    GSM_CUDA(cudaGetLastError());
+
+    unsigned long long* tiles = (unsigned long long*)ws->scan_tmp;
+    k_scan_tiles<<<(unsigned)n_tiles, SCAN_THREADS, 0, stream>>>(ws->rec_cnt, rd->n_reads, (unsigned long long*)ws->rec_off, tiles);
+    k_scan_top<<<1, SCAN_THREADS, 0, stream>>>(tiles, n_tiles, tiles + n_tiles);
+    k_scan_add<<<(unsigned)n_tiles, SCAN_THREADS, 0, stream>>>((unsigned long long*)ws->rec_off, rd->n_reads, tiles, tiles + n_tiles);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_smem_collect(const gsm_dev_reads* rd, gsm_workspace* ws, gsm_record* out, uint64_t out_cap, void* stream) {
+    if (!rd || !ws || (!out && out_cap)) return fail(GSM_E_INVALID, "null");
+    int st = device_ready();
+    if (st) return st;
+    if (rd->n_reads == 0) return GSM_OK;
+    const uint64_t threads = rd->n_reads * 4;
+    k_gather_records<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)ws->rec_tmp, ws->rec_tmp_off, ws->rec_cnt, (const unsigned long long*)ws->rec_off, rd->n_reads, (uint4*)out, out_cap,
+        (unsigned long long*)ws->counters);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_gather_probe(const void* buf, uint64_t bytes, uint64_t n_fetch, uint32_t dependent, uint64_t* sink, uint64_t* n_done, void* stream) {
+    if (!buf || !sink || bytes < 64) return fail(GSM_E_INVALID, "null");
+    int st = device_ready();
+    if (st) return st;
+    int dev = 0, sms = 0;
+    GSM_CUDA(cudaGetDevice(&dev));
+    GSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const uint64_t quads = (uint64_t)sms * 16 * 32;      // 16 blocks x 128 threads per SM
+    uint32_t iters = (uint32_t)((n_fetch + quads - 1) / quads);
+    if (iters == 0) iters = 1;
+    k_gather_probe<<<sms * 16, 128, 0, (cudaStream_t)stream>>>((const uint4*)buf, bytes / 64, iters, dependent, (unsigned long long*)sink);
+    GSM_CUDA(cudaGetLastError());
+    if (n_done) *n_done = quads * iters;
+    return GSM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,390 @@
+"""Batched device engine: torch owns the buffers, libgenie_smem (ctypes) does the work.
+
+This is the layer the reference-shaped classes in surface.py sit on; bench.py and the parity
+tests also call it directly.  Every search goes through the C ABI of include/genie_smem.h and
+therefore through the CUDA kernels; nothing here computes a search result in Python.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+
+RECORD_DTYPE = np.dtype([("read_id", "<u4"), ("qstart", "<u2"), ("qend", "<u2"), ("sa_lo", "<u4"), ("sa_hi", "<u4")])
+_BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+class BaseError(KeyError, ValueError):
+    """A read or reference holds a character outside ACGT (the reference raises KeyError there,
+    SMEM/ExactMatch.py:139; SURVEY 8b asks for ValueError up front -- this is both)."""
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise capi.GsmError(capi.E_NODEVICE, "no CUDA device visible: genie_smem_b200 has no CPU fallback")
+
+
+class HostIndex:
+    """Host-side FM index handle (gsm_index).  Replaces ExactMatch.create_fm_index /
+    load_fm_index (reference SMEM/ExactMatch.py:22-41)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self.info = capi.IndexInfo()
+        capi.check(capi.lib.gsm_index_info_get(self._h, C.byref(self.info)))
+
+    @classmethod
+    def build(cls, text, reverse=True):
+        data = text if isinstance(text, (bytes, bytearray)) else text.encode()
+        h = C.c_void_p()
+        try:
+            capi.check(capi.lib.gsm_index_build(bytes(data), len(data), 1 if reverse else 0, C.byref(h)))
+        except ValueError as e:
+            raise BaseError(str(e)) from None
+        return cls(h)
+
+    @classmethod
+    def from_arrays(cls, text, suffix_array_1based, reverse=True):
+        data = text if isinstance(text, (bytes, bytearray)) else text.encode()
+        sa = np.ascontiguousarray(suffix_array_1based, dtype=np.uint32)
+        if sa.shape[0] != len(data) + 1:
+            raise ValueError("suffix_array must have len(text)+1 entries")
+        h = C.c_void_p()
+        try:
+            capi.check(capi.lib.gsm_index_from_arrays(bytes(data), len(data), sa.ctypes.data, 1 if reverse else 0, C.byref(h)))
+        except ValueError as e:
+            if "ACGT" in str(e):
+                raise BaseError(str(e)) from None
+            raise
+        return cls(h)
+
+    @property
+    def n_rows(self):
+        return int(self.info.n_rows)
+
+    @property
+    def n_bases(self):
+        return int(self.info.n_bases)
+
+    def export(self):
+        """-> (suffix_array uint32[n] 1-based, bwt bytes) in the reference's schema (ExactMatch.py:29-30)."""
+        sa = np.zeros(self.n_rows, np.uint32)
+        bwt = np.zeros(self.n_rows, np.uint8)
+        capi.check(capi.lib.gsm_index_export(self._h, sa.ctypes.data, bwt.ctypes.data))
+        return sa, bwt.tobytes()
+
+    def count_dic(self):
+        """fm_index["count_dic"] of the reference (ExactMatch.py:92-101)."""
+        i = self.info
+        return {"": int(i.n_rows), "$": 0, "A": int(i.C[0]), "C": int(i.C[1]), "G": int(i.C[2]), "T": int(i.C[3])}
+
+    def pack(self, with_sa=True, with_text=True):
+        i = self.info
+        fwd = np.zeros(i.n_buckets * 16, np.uint32)
+        rev = np.zeros(i.n_buckets * 16, np.uint32) if i.has_reverse else None
+        sa = np.zeros(i.n_rows, np.uint32) if with_sa else None
+        text = np.zeros(i.text_words + 2, np.uint32) if with_text else None
+        capi.check(capi.lib.gsm_index_pack(self._h, fwd.ctypes.data, rev.ctypes.data if rev is not None else None,
+                                           sa.ctypes.data if sa is not None else None, text.ctypes.data if text is not None else None))
+        return fwd, rev, sa, text
+
+    def close(self):
+        if self._h is not None:
+            capi.lib.gsm_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _to_dev(a, device):
+    if a is None:
+        return None
+    t = torch.from_numpy(a.view(np.int32))
+    return t.to(device, non_blocking=False)
+
+
+class DeviceIndex:
+    """The index resident in HBM: two bucket arrays (text / reversed text), optionally the full
+    suffix array and the 2-bit text (needed by RMI and by position lookups)."""
+
+    def __init__(self, host: HostIndex, device="cuda", with_sa=True, with_text=True):
+        require_cuda()
+        self.device = torch.device(device)
+        self.info = host.info
+        fwd, rev, sa, text = host.pack(with_sa, with_text)
+        self.fwd = _to_dev(fwd, self.device)
+        self.rev = _to_dev(rev, self.device)
+        self.sa = _to_dev(sa, self.device)
+        self.text = _to_dev(text, self.device)
+        d = capi.DevIndex()
+        d.n_rows, d.n_buckets = host.info.n_rows, host.info.n_buckets
+        d.fwd_buckets, d.rev_buckets = self.fwd.data_ptr(), (self.rev.data_ptr() if self.rev is not None else None)
+        d.sa = self.sa.data_ptr() if self.sa is not None else None
+        d.text2bit = self.text.data_ptr() if self.text is not None else None
+        for c in range(5):
+            d.C[c] = host.info.C[c]
+        d.primary_fwd, d.primary_rev = host.info.primary_fwd, host.info.primary_rev
+        self.c = d
+        self.n_rows = int(host.info.n_rows)
+        self.n_bases = int(host.info.n_bases)
+        self.all_bases_present = all(int(host.info.count[c]) > 0 for c in range(4))
+
+    def bytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.fwd, self.rev, self.sa, self.text) if t is not None)
+
+
+class ReadBatch:
+    """Reads packed 2 bits/base, MSB-first, 16-byte aligned per read (include/genie_smem.h)."""
+
+    def __init__(self, packed_u8, chunk_off, lens, max_len, read_id_base=0):
+        self.packed_host, self.chunk_off_host, self.len_host = packed_u8, chunk_off, lens
+        self.n = int(lens.shape[0])
+        self.max_len = int(max_len)
+        self.read_id_base = int(read_id_base)
+        self.packed = self.chunk_off = self.len = None
+
+    @classmethod
+    def from_strings(cls, reads, read_id_base=0, pin=False):
+        lens = np.asarray([len(r) for r in reads], np.uint32)
+        joined = "".join(reads).encode()
+        return cls._pack(joined, lens, read_id_base, pin)
+
+    @classmethod
+    def from_codes(cls, codes_u8, read_len, read_id_base=0, pin=False):
+        """codes_u8: (n, read_len) array of base codes 0..3 (synthetic batches)."""
+        n = codes_u8.shape[0]
+        lens = np.full(n, read_len, np.uint32)
+        joined = _BASES[np.ascontiguousarray(codes_u8).reshape(-1)].tobytes()
+        return cls._pack(joined, lens, read_id_base, pin)
+
+    @classmethod
+    def _pack(cls, joined, lens, read_id_base, pin):
+        n = int(lens.shape[0])
+        off = np.zeros(n + 1, np.uint32)
+        try:
+            capi.check(capi.lib.gsm_pack_reads(joined, lens.ctypes.data, n, off.ctypes.data, None))
+            nbytes = int(off[n]) * 16 + 16          # one readable pad chunk
+            if pin and torch.cuda.is_available():
+                packed_t = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+                packed = packed_t.numpy()
+            else:
+                packed = np.zeros(nbytes, np.uint8)
+            capi.check(capi.lib.gsm_pack_reads(joined, lens.ctypes.data, n, off.ctypes.data, packed.ctypes.data))
+        except ValueError as e:
+            raise BaseError(str(e)) from None
+        return cls(packed, off, lens, int(lens.max()) if n else 0, read_id_base)
+
+    def to(self, device, non_blocking=False):
+        self.packed = torch.from_numpy(self.packed_host).to(device, non_blocking=non_blocking)
+        self.chunk_off = torch.from_numpy(self.chunk_off_host.view(np.int32)).to(device, non_blocking=non_blocking)
+        self.len = torch.from_numpy(self.len_host.view(np.int32)).to(device, non_blocking=non_blocking)
+        return self
+
+    def h2d_bytes(self):
+        return self.packed_host.nbytes + self.chunk_off_host.nbytes + self.len_host.nbytes
+
+    def cstruct(self):
+        r = capi.DevReads()
+        r.n_reads = self.n
+        r.packed, r.chunk_off, r.len = self.packed.data_ptr(), self.chunk_off.data_ptr(), self.len.data_ptr()
+        r.max_len, r.read_id_base = self.max_len, self.read_id_base
+        return r
+
+
+class RmiParams:
+    """(coef, intercept) per linear model of an RMI (reference SMEM/RMI.py), on the device."""
+
+    def __init__(self, K, level_sizes, coef, intercept, device="cuda"):
+        self.K = int(K)
+        self.level_sizes = np.asarray(level_sizes, np.uint32)
+        self.coef_host = np.ascontiguousarray(coef, np.float64)
+        self.intercept_host = np.ascontiguousarray(intercept, np.float64)
+        assert self.coef_host.shape[0] == int(self.level_sizes.sum()) == self.intercept_host.shape[0]
+        self.coef = torch.from_numpy(self.coef_host).to(device)
+        self.intercept = torch.from_numpy(self.intercept_host).to(device)
+        s = capi.DevRmi()
+        s.K, s.n_levels = self.K, len(self.level_sizes)
+        s.level_sizes = self.level_sizes.ctypes.data_as(capi.u32p)
+        s.coef, s.intercept = self.coef.data_ptr(), self.intercept.data_ptr()
+        self.c = s
+
+
+class SmemResult:
+    """Records of one batch in (read, emission) order + CSR offsets per read."""
+
+    def __init__(self, records, offsets, status, n_mems):
+        self.records, self.offsets, self.status, self.n_mems = records, offsets, status, n_mems
+
+    def for_read(self, i):
+        return self.records[self.offsets[i]:self.offsets[i + 1]]
+
+
+class Engine:
+    """Owns the workspace for batches of up to `max_reads` reads of up to `max_len` bases."""
+
+    def __init__(self, index: DeviceIndex, max_reads, max_len, mems_per_read=24, recs_per_read=16):
+        require_cuda()
+        self.index = index
+        self.device = index.device
+        self.max_reads, self.max_len = int(max_reads), int(max_len)
+        wi = capi.WorkspaceInfo()
+        capi.check(capi.lib.gsm_smem_workspace_info(self.max_reads, self.max_len, C.byref(wi)))
+        self.grid = (int(wi.grid_blocks), int(wi.block_threads))
+        dev = self.device
+        n = max(self.max_reads, 1)
+        self.mem_cap = min(max(n * mems_per_read, 4096), (1 << 32) - 1)
+        self.rec_cap = min(max(n * recs_per_read, 4096), (1 << 32) - 1)
+        self.mem_pool = torch.empty(self.mem_cap * 16, dtype=torch.uint8, device=dev)
+        self.scratch = torch.empty(int(wi.quad_scratch_bytes), dtype=torch.uint8, device=dev)
+        self.mem_off = torch.empty(n, dtype=torch.int32, device=dev)
+        self.mem_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        self.rec_tmp = torch.empty(self.rec_cap * 16, dtype=torch.uint8, device=dev)
+        self.rec_tmp_off = torch.empty(n, dtype=torch.int32, device=dev)
+        self.rec_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        self.rec_off = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        self.read_status = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.scan_tmp = torch.empty(int(wi.scan_tmp_bytes), dtype=torch.uint8, device=dev)
+        self.records = torch.empty(self.rec_cap * 16, dtype=torch.uint8, device=dev)
+        w = capi.Workspace()
+        w.mem_pool, w.mem_cap = self.mem_pool.data_ptr(), self.mem_cap
+        w.quad_scratch, w.quad_scratch_bytes = self.scratch.data_ptr(), self.scratch.numel()
+        w.mem_off, w.mem_cnt = self.mem_off.data_ptr(), self.mem_cnt.data_ptr()
+        w.rec_tmp, w.rec_cap = self.rec_tmp.data_ptr(), self.rec_cap
+        w.rec_tmp_off, w.rec_cnt, w.rec_off = self.rec_tmp_off.data_ptr(), self.rec_cnt.data_ptr(), self.rec_off.data_ptr()
+        w.read_status, w.counters = self.read_status.data_ptr(), self.counters.data_ptr()
+        w.scan_tmp, w.scan_tmp_bytes = self.scan_tmp.data_ptr(), self.scan_tmp.numel()
+        self.ws = w
+        self.kernel_launches = 0
+
+    # -- device-resident step: kernels only (what bench.py times as `value`)
+    def launch(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None):
+        if reads.n > self.max_reads or reads.max_len > self.max_len:
+            raise ValueError("batch exceeds the engine's workspace")
+        r = reads.cstruct()
+        self._reads_c = r
+        capi.check(capi.lib.gsm_smem_batch(method, C.byref(self.index.c), C.byref(r), int(min_len), int(K), _ptr(lut),
+                                           C.byref(rmi.c) if rmi is not None else None, C.byref(self.ws), _stream()))
+        capi.check(capi.lib.gsm_smem_collect(C.byref(r), C.byref(self.ws), _ptr(self.records), self.rec_cap, _stream()))
+        self.kernel_launches += 6 if reads.n else 0    # sweep, select, 3 scan kernels, gather
+
+    def check_overflow(self):
+        c = self.counters.cpu().numpy()
+        if c[2] != 0:
+            raise capi.GsmError(capi.E_CAPACITY, f"workspace overflow (flags {int(c[2])}): mems {int(c[0])}/{self.mem_cap}, "
+                                                 f"records {int(c[1])}/{self.rec_cap}")
+        return int(c[0]), int(c[1])
+
+    # -- end-to-end step: host reads in, host records out
+    def run(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None, grow=True):
+        reads.to(self.device)
+        while True:
+            self.launch(method, reads, min_len, K, lut, rmi)
+            try:
+                n_mems, n_rec = self.check_overflow()
+                break
+            except capi.GsmError as e:
+                if e.code != capi.E_CAPACITY or not grow:
+                    raise
+                self._grow()
+        recs = self.records[: n_rec * 16].cpu().numpy().view(RECORD_DTYPE)
+        offs = self.rec_off[: reads.n + 1].cpu().numpy().astype(np.int64)
+        status = self.read_status[: reads.n].cpu().numpy()
+        return SmemResult(recs, offs, status, n_mems)
+
+    def _grow(self):
+        dev = self.device
+        self.mem_cap = min(self.mem_cap * 4, (1 << 32) - 1)
+        self.rec_cap = min(self.rec_cap * 4, (1 << 32) - 1)
+        self.mem_pool = torch.empty(self.mem_cap * 16, dtype=torch.uint8, device=dev)
+        self.rec_tmp = torch.empty(self.rec_cap * 16, dtype=torch.uint8, device=dev)
+        self.records = torch.empty(self.rec_cap * 16, dtype=torch.uint8, device=dev)
+        self.ws.mem_pool, self.ws.mem_cap = self.mem_pool.data_ptr(), self.mem_cap
+        self.ws.rec_tmp, self.ws.rec_cap = self.rec_tmp.data_ptr(), self.rec_cap
+
+
+# ---------------------------------------------------------------------------- batched primitives
+def backsearch_batch(index: DeviceIndex, reads: ReadBatch):
+    """exact_match_back_prop for every read -> (lo, cnt) uint32 arrays; cnt == 0 <=> reference -1."""
+    require_cuda()
+    reads.to(index.device)
+    lo = torch.empty(max(reads.n, 1), dtype=torch.int32, device=index.device)
+    cnt = torch.empty(max(reads.n, 1), dtype=torch.int32, device=index.device)
+    r = reads.cstruct()
+    capi.check(capi.lib.gsm_backsearch_batch(C.byref(index.c), C.byref(r), _ptr(lo), _ptr(cnt), _stream()))
+    return lo[: reads.n].cpu().numpy().view(np.uint32), cnt[: reads.n].cpu().numpy().view(np.uint32)
+
+
+def add_one_batch(index: DeviceIndex, bases, lo, cnt):
+    """exact_match_back_prop_add_one for a batch of (base code, interval)."""
+    require_cuda()
+    n = len(bases)
+    b = torch.from_numpy(np.ascontiguousarray(bases, np.uint8)).to(index.device)
+    lo_t = torch.from_numpy(np.ascontiguousarray(lo, np.uint32).view(np.int32)).to(index.device)
+    cnt_t = torch.from_numpy(np.ascontiguousarray(cnt, np.uint32).view(np.int32)).to(index.device)
+    capi.check(capi.lib.gsm_backsearch_add_one_batch(C.byref(index.c), n, _ptr(b), _ptr(lo_t), _ptr(cnt_t), _stream()))
+    return lo_t.cpu().numpy().view(np.uint32), cnt_t.cpu().numpy().view(np.uint32)
+
+
+def sa_lookup(index: DeviceIndex, rows):
+    """suffix-array rows -> 1-based text positions (ExactMatch.get_positions)."""
+    require_cuda()
+    rows = np.ascontiguousarray(rows, np.uint32)
+    if rows.size == 0:
+        return np.zeros(0, np.uint32)
+    r = torch.from_numpy(rows.view(np.int32)).to(index.device)
+    out = torch.empty_like(r)
+    capi.check(capi.lib.gsm_sa_lookup_batch(C.byref(index.c), rows.size, _ptr(r), _ptr(out), _stream()))
+    return out.cpu().numpy().view(np.uint32)
+
+
+def lut_build(index: DeviceIndex, K):
+    """Dense device table (4^K x {lo, cnt}); replaces LUT.generate_lut (reference SMEM/LUT.py:15-35)."""
+    require_cuda()
+    t = torch.empty((1 << (2 * K)) * 2, dtype=torch.int32, device=index.device)
+    capi.check(capi.lib.gsm_lut_build(C.byref(index.c), int(K), _ptr(t), _stream()))
+    return t
+
+
+def rmi_lookup_batch(index: DeviceIndex, rmi: RmiParams, codes):
+    """get_suffix_rmi for a batch of k-mer codes -> (pred f64, lo i64, hi i64, status u8)."""
+    require_cuda()
+    codes = np.ascontiguousarray(codes, np.uint64)
+    n = codes.size
+    dev = index.device
+    c = torch.from_numpy(codes.view(np.int64)).to(dev)
+    pred = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    lo = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    hi = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    st = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    capi.check(capi.lib.gsm_rmi_lookup_batch(C.byref(index.c), C.byref(rmi.c), n, _ptr(c), _ptr(pred), _ptr(lo), _ptr(hi), _ptr(st), _stream()))
+    return pred[:n].cpu().numpy(), lo[:n].cpu().numpy(), hi[:n].cpu().numpy(), st[:n].cpu().numpy()
+
+
+def gather_probe(buf: torch.Tensor, n_fetch, dependent):
+    """Random aligned 64-byte gather over `buf`; returns (#fetches, seconds) timed with CUDA events."""
+    require_cuda()
+    sink = torch.zeros(1, dtype=torch.int64, device=buf.device)
+    done = C.c_uint64()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nbytes = buf.numel() * buf.element_size()
+    capi.check(capi.lib.gsm_gather_probe(_ptr(buf), nbytes, max(n_fetch // 8, 1), int(dependent), _ptr(sink), C.byref(done), _stream()))
+    torch.cuda.synchronize()
+    e0.record()
+    capi.check(capi.lib.gsm_gather_probe(_ptr(buf), nbytes, int(n_fetch), int(dependent), _ptr(sink), C.byref(done), _stream()))
+    e1.record()
+    torch.cuda.synchronize()
+    return int(done.value), e0.elapsed_time(e1) * 1e-3

@@ -1,0 +1,229 @@
+/*
+ * genie_smem.h -- C ABI of the B200-native SMEM-seeding engine (libgenie_smem.so).
+ *
+ * This is the drop-in boundary for GENIE-SMEM's search path.  The reference is pure Python
+ * (no FFI of its own), so each entry point cites the reference routine (file:line under
+ * /root/reference/SMEM/) it replaces; INTEGRATION.md shows the ctypes stub a maintainer
+ * would add to the reference classes.
+ *
+ * Conventions
+ *   - every function returns int status: 0 ok, <0 error (GSM_E_*); nothing throws across
+ *     the boundary; gsm_last_error() gives the text of the last failure on this thread;
+ *   - plain pointers and sizes only; the caller (torch tensors / numpy arrays) owns every
+ *     buffer, the library never allocates device memory;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - rows are 0-based suffix-array rows over n = n_bases + 1 rows (row 0 is the '$'
+ *     suffix); an SA interval is reported as (lo, cnt) with cnt == 0 meaning "no match"
+ *     (the reference's int -1, ExactMatch.py:149); suffix-array VALUES are 1-based text
+ *     positions exactly as ExactMatch.py:66 stores them;
+ *   - bases are codes A=0 C=1 G=2 T=3 (LUT.py:39-43); sequences are 2-bit packed MSB-first:
+ *     base i sits in bits [30-2*(i%16), 32-2*(i%16)) of 32-bit word i/16, so the top 2K bits of
+ *     a window are the k-mer code of LUT.convert_seq_to_num (LUT.py:37-48); every read starts
+ *     on a 16-byte boundary of the packed buffer, and packed buffers (reads and text) must be
+ *     readable 16 bytes past their last word.
+ */
+#ifndef GENIE_SMEM_H
+#define GENIE_SMEM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSM_OK 0
+#define GSM_E_INVALID (-1)   /* bad argument (non-ACGT base, null pointer, size mismatch) */
+#define GSM_E_NOMEM (-2)     /* host allocation failed */
+#define GSM_E_CUDA (-3)      /* CUDA runtime error (text in gsm_last_error) */
+#define GSM_E_CAPACITY (-4)  /* a caller-provided buffer is too small */
+#define GSM_E_NODEVICE (-5)  /* no CUDA device: there is NO CPU fallback */
+
+#define GSM_METHOD_BWA 0 /* SMEM.get_SMEMS      (SMEM.py:456-467) */
+#define GSM_METHOD_LUT 1 /* SMEM.get_smems_lut  (SMEM.py:20-192)  */
+#define GSM_METHOD_RMI 2 /* SMEM.get_smems_rmi  (SMEM.py:206-384) */
+
+/* per-read status bits written by the SMEM kernels */
+#define GSM_READ_OK 0u
+#define GSM_READ_REF_RAISES 1u /* the reference raises on this read (RMI last-mile search leaves
+                                  the table: RecursionError / IndexError, RMI_LUT.py:136-184) */
+#define GSM_READ_TOO_SHORT 2u  /* len < K for LUT/RMI (the reference's behaviour is undefined) */
+
+#define GSM_BUCKET_BYTES 64
+#define GSM_BUCKET_SYMS 192
+
+/* ------------------------------------------------------------------ host-side index */
+typedef struct gsm_index gsm_index; /* opaque, immutable after build */
+
+typedef struct {
+    uint64_t n_bases;
+    uint64_t n_rows;       /* n_bases + 1                         (fm_index["ref_size"]) */
+    uint64_t n_buckets;    /* 64-byte rank buckets per direction                        */
+    uint64_t bucket_bytes; /* n_buckets * 64                                            */
+    uint64_t text_words;   /* 32-bit words of the 2-bit packed text incl. 2 pad words    */
+    uint32_t count[4];     /* occurrences of A,C,G,T in the text                        */
+    uint32_t C[5];         /* first row whose suffix starts with A,C,G,T; C[4]=n_rows
+                              (fm_index["count_dic"], ExactMatch.py:92-101)             */
+    uint32_t primary_fwd;  /* row of the forward BWT holding '$'                        */
+    uint32_t primary_rev;  /* same for the BWT of the reversed text                     */
+    uint32_t has_reverse;  /* 1 if the reverse-text BWT was built                       */
+    uint32_t reserved;
+} gsm_index_info;
+
+/* Build BWT / SA / C of text+'$' with an O(n) suffix sorter.
+ * Replaces ExactMatch.create_fm_index (ExactMatch.py:22-33, 52-101: n^2 rotation sort).
+ * bases: n_bases ASCII chars from {A,C,G,T}.  flags: bit0 = also build the BWT of the
+ * reversed text (needed by the SMEM kernels' forward extension). */
+int gsm_index_build(const char* bases, uint64_t n_bases, uint32_t flags, gsm_index** out);
+
+/* Import reference-built arrays (fm_index["suffix_array"], 1-based) instead of sorting:
+ * the "same index arrays" clause.  Replaces ExactMatch.load_fm_index (ExactMatch.py:35-41). */
+int gsm_index_from_arrays(const char* bases, uint64_t n_bases, const uint32_t* suffix_array_1based,
+                          uint32_t flags, gsm_index** out);
+
+int gsm_index_info_get(const gsm_index* idx, gsm_index_info* out);
+
+/* Export in the reference's schema (ExactMatch.py:29-30): suffix_array (1-based, n_rows
+ * entries) and bwt (n_rows chars, '$' at the primary row).  Either pointer may be NULL. */
+int gsm_index_export(const gsm_index* idx, uint32_t* suffix_array_1based, char* bwt);
+
+/* Fill caller-allocated HOST buffers with the device layouts (the caller then copies them
+ * to the GPU).  Any pointer may be NULL to skip that array.
+ *   fwd_buckets / rev_buckets : n_buckets * 64 bytes each
+ *   sa                        : n_rows uint32 (1-based values, as exported)
+ *   text2bit                  : text_words uint32 */
+int gsm_index_pack(const gsm_index* idx, void* fwd_buckets, void* rev_buckets, uint32_t* sa,
+                   uint32_t* text2bit);
+
+void gsm_index_free(gsm_index* idx);
+
+/* Pack ASCII reads into the device read format.  lens[i] bases each, concatenated in
+ * `bases`.  chunk_off (n_reads+1 entries) receives each read's offset in 16-byte chunks;
+ * packed must hold chunk_off[n_reads]*16 bytes -- call with packed == NULL to size it.
+ * Returns GSM_E_INVALID on a non-ACGT base (the reference raises KeyError there). */
+int gsm_pack_reads(const char* bases, const uint32_t* lens, uint64_t n_reads, uint32_t* chunk_off,
+                   void* packed);
+
+/* ------------------------------------------------------------------ device-side views */
+typedef struct {
+    uint64_t n_rows;
+    uint64_t n_buckets;
+    const void* fwd_buckets; /* device */
+    const void* rev_buckets; /* device, may be NULL for gsm_backsearch_batch / gsm_lut_build */
+    const uint32_t* sa;      /* device, 1-based values; needed by RMI and gsm_sa_lookup */
+    const uint32_t* text2bit; /* device; needed by RMI */
+    uint32_t C[5];
+    uint32_t primary_fwd;
+    uint32_t primary_rev;
+    uint32_t reserved;
+} gsm_dev_index;
+
+typedef struct {
+    uint64_t n_reads;
+    const void* packed;        /* device, 2-bit packed reads */
+    const uint32_t* chunk_off; /* device, n_reads + 1 */
+    const uint32_t* len;       /* device, n_reads */
+    uint32_t max_len;          /* max over len[] */
+    uint32_t read_id_base;     /* added to the read index in emitted records (rank sharding) */
+} gsm_dev_reads;
+
+/* One emitted SMEM, before the reference's dict collapses duplicate strings.  16 bytes. */
+typedef struct {
+    uint32_t read_id;
+    uint16_t qstart; /* SMEM = read[qstart:qend] */
+    uint16_t qend;
+    uint32_t sa_lo; /* inclusive rows, the reference's tuple (lo, hi) */
+    uint32_t sa_hi;
+} gsm_record;
+
+/* RMI parameters (RMI.py:52-69): level_sizes[l] models at level l (level 0 has 1), flattened
+ * coef/intercept in level order; prediction = fl(fl(x*coef)+intercept) per level. */
+typedef struct {
+    uint32_t K;             /* RMI_LUT.prediction_size */
+    uint32_t n_levels;
+    const uint32_t* level_sizes; /* HOST pointer, n_levels entries */
+    const double* coef;          /* device */
+    const double* intercept;     /* device */
+} gsm_dev_rmi;
+
+/* Scratch + output buffers for one SMEM batch; all device memory, all caller-allocated.
+ * gsm_smem_workspace_bytes() says how large each must be. */
+typedef struct {
+    void* mem_pool;        /* classical-SMEM pool, mem_cap entries of 16 bytes */
+    uint64_t mem_cap;
+    void* quad_scratch;    /* per-resident-quad staging */
+    uint64_t quad_scratch_bytes;
+    uint32_t* mem_off;     /* n_reads */
+    uint32_t* mem_cnt;     /* n_reads */
+    gsm_record* rec_tmp;   /* unordered record pool, rec_cap entries */
+    uint64_t rec_cap;
+    uint32_t* rec_tmp_off; /* n_reads */
+    uint32_t* rec_cnt;     /* n_reads: records per read (phase-1 result) */
+    uint64_t* rec_off;     /* n_reads + 1: exclusive scan of rec_cnt */
+    uint8_t* read_status;  /* n_reads: GSM_READ_* */
+    uint64_t* counters;    /* 8 x uint64: [0] mems used, [1] records, [2] status bits, [3] next read */
+    void* scan_tmp;        /* scan scratch */
+    uint64_t scan_tmp_bytes;
+} gsm_workspace;
+
+typedef struct {
+    uint64_t quad_scratch_bytes;
+    uint64_t scan_tmp_bytes;
+    uint32_t grid_blocks;   /* persistent grid used by the sweep kernel on this device */
+    uint32_t block_threads;
+} gsm_workspace_info;
+
+int gsm_smem_workspace_info(uint64_t n_reads, uint32_t max_len, gsm_workspace_info* out);
+
+/* ------------------------------------------------------------------ device search */
+/* Batched backward search: ExactMatch.exact_match_back_prop (ExactMatch.py:132-151) for every
+ * read.  lo[i], cnt[i]: rows [lo, lo+cnt); cnt == 0 <=> the reference returns -1. */
+int gsm_backsearch_batch(const gsm_dev_index* idx, const gsm_dev_reads* reads, uint32_t* lo,
+                         uint32_t* cnt, void* stream);
+
+/* One backward-search step for a batch of (char, interval) pairs:
+ * ExactMatch.exact_match_back_prop_add_one (ExactMatch.py:155-171). In place on lo/cnt. */
+int gsm_backsearch_add_one_batch(const gsm_dev_index* idx, uint64_t n, const uint8_t* base,
+                                 uint32_t* lo, uint32_t* cnt, void* stream);
+
+/* rows -> 1-based text positions: ExactMatch.get_position(s) (ExactMatch.py:191-199). */
+int gsm_sa_lookup_batch(const gsm_dev_index* idx, uint64_t n, const uint32_t* rows, uint32_t* pos,
+                        void* stream);
+
+/* Dense k-mer table: entry[code] = {lo, cnt} for every 4^K code, cnt == 0 for absent k-mers.
+ * Replaces LUT.generate_lut (LUT.py:15-35); table: 4^K * 8 bytes of device memory. */
+int gsm_lut_build(const gsm_dev_index* idx, uint32_t K, uint32_t* table, void* stream);
+
+/* The three SMEM entry points.  Phase 1 (this call) runs the kernels and leaves per-read
+ * record counts in ws->rec_cnt, their exclusive scan in ws->rec_off and the total in
+ * ws->counters[1]; phase 2 (gsm_smem_collect) writes the records in (read, emission) order.
+ *   BWA: SMEM.get_SMEMS(query, min_len)            (SMEM.py:456-484, 389-443)
+ *   LUT: SMEM.get_smems_lut(query), K = lut_size    (SMEM.py:20-192), lut = gsm_lut_build table
+ *   RMI: SMEM.get_smems_rmi(query)                  (SMEM.py:206-384, RMI_LUT.py:53-184) */
+int gsm_smem_batch(int method, const gsm_dev_index* idx, const gsm_dev_reads* reads, uint32_t min_len,
+                   uint32_t K, const uint32_t* lut, const gsm_dev_rmi* rmi, gsm_workspace* ws,
+                   void* stream);
+
+int gsm_smem_collect(const gsm_dev_reads* reads, gsm_workspace* ws, gsm_record* out, uint64_t out_cap,
+                     void* stream);
+
+/* RMI_LUT.get_suffix_rmi (RMI_LUT.py:67-78) for a batch of K-mer codes: predict + exponential
+ * + binary last-mile search.  pred receives the float64 prediction, lo/hi the returned pair
+ * (hit <=> hi >= lo as int64), status GSM_READ_REF_RAISES where the reference would raise. */
+int gsm_rmi_lookup_batch(const gsm_dev_index* idx, const gsm_dev_rmi* rmi, uint64_t n,
+                         const uint64_t* codes, double* pred, int64_t* lo, int64_t* hi,
+                         uint8_t* status, void* stream);
+
+/* Random aligned 64-byte gather over `bytes` of device memory with the rank kernels' access
+ * shape (4 lanes x 16 B): the measured ceiling the rank kernels are compared with.
+ * At least n_fetch buckets are fetched; *n_done receives the exact number.  dependent != 0:
+ * every quad chases pointers (one FM chain each); 0: independent fetches.  sink: device u64. */
+int gsm_gather_probe(const void* buf, uint64_t bytes, uint64_t n_fetch, uint32_t dependent,
+                     uint64_t* sink, uint64_t* n_done, void* stream);
+
+const char* gsm_last_error(void);
+int gsm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENIE_SMEM_H */

