@@ -65,6 +65,9 @@ EXPORTS = {
     "gsm_lut_build": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p]),
     "gsm_smem_batch": (C.c_int, [C.c_int, C.POINTER(DevIndex), C.POINTER(DevReads), C.c_uint32, C.c_uint32, C.c_void_p,
                                  C.POINTER(DevRmi), C.POINTER(Workspace), C.c_void_p]),
+    "gsm_smem_sweep": (C.c_int, [C.POINTER(DevIndex), C.POINTER(DevReads), C.POINTER(Workspace), C.c_void_p]),
+    "gsm_smem_select": (C.c_int, [C.c_int, C.POINTER(DevIndex), C.POINTER(DevReads), C.c_uint32, C.c_uint32, C.c_void_p,
+                                  C.POINTER(DevRmi), C.POINTER(Workspace), C.c_void_p]),
     "gsm_smem_collect": (C.c_int, [C.POINTER(DevReads), C.POINTER(Workspace), C.c_void_p, C.c_uint64, C.c_void_p]),
     "gsm_rmi_lookup_batch": (C.c_int, [C.POINTER(DevIndex), C.POINTER(DevRmi), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),

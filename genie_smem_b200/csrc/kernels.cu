@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
             uint32_t s1 = s0 + 1;
             const uint32_t id = c.mems[s0].w;
             while (s1 < c.n_mems && c.mems[s1].w == id) ++s1;
-            for (uint32_t x = s0, y = s1 - 1; x < y; ++x, --y) {
+            // (idempotent: a second selection pass over the same sweep finds the segment ascending)
+            const bool descending = (c.mems[s0].x >> 16) > (c.mems[s1 - 1].x >> 16);
+            for (uint32_t x = s0, y = s1 - 1; descending && x < y; ++x, --y) {
                 uint4 t = c.mems[x]; c.mems[x] = c.mems[y]; c.mems[y] = t;
             }
             s0 = s1;
@@ -632,67 +634,87 @@ int gsm_rmi_lookup_batch(const gsm_dev_index* ix, const gsm_dev_rmi* rmi, uint64
     return GSM_OK;
 }
 
-int gsm_smem_batch(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd, uint32_t min_len, uint32_t K, const uint32_t* lut,
-                   const gsm_dev_rmi* rmi, gsm_workspace* ws, void* stream_) {
+static int smem_check(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_workspace* ws, int* sb, int* lb) {
     if (!ix || !rd || !ws) return fail(GSM_E_INVALID, "null");
-    if (!ix->fwd_buckets || !ix->rev_buckets) return fail(GSM_E_INVALID, "gsm_smem_batch needs both BWT directions on the device");
+    if (!ix->fwd_buckets || !ix->rev_buckets) return fail(GSM_E_INVALID, "the SMEM kernels need both BWT directions on the device");
     if (rd->max_len == 0 || rd->max_len > 65535) return fail(GSM_E_INVALID, "max_len must be in 1..65535");
     if (rd->n_reads >= (1ull << 32)) return fail(GSM_E_INVALID, "at most 2^32-1 reads per batch");
     if (ws->mem_cap >= (1ull << 32) || ws->rec_cap >= (1ull << 32)) return fail(GSM_E_INVALID, "pool capacities must be < 2^32 entries");
-    if (method == GSM_METHOD_LUT && (!lut || K < 1 || K > 16)) return fail(GSM_E_INVALID, "LUT method needs a table and K in 1..16");
-    RmiModel rm;
-    memset(&rm, 0, sizeof(rm));
-    if (method == GSM_METHOD_RMI) {
-        int st = fill_rmi(rmi, &rm);
-        if (st) return st;
-        if (!ix->sa || !ix->text2bit) return fail(GSM_E_INVALID, "RMI method needs the suffix array and packed text on the device");
-        K = rmi->K;
-    }
-    if (method < 0 || method > 2) return fail(GSM_E_INVALID, "unknown method");
     int st = device_ready();
     if (st) return st;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    int sb = 0, lb = 0;
-    if ((st = sweep_grid(rd->max_len, &sb))) return st;
-    if ((st = select_grid(&lb))) return st;
-    const uint64_t need_sweep = (uint64_t)sb * (SWEEP_THREADS / 4) * 2ull * rd->max_len * 16ull;
-    const uint64_t need_sel = (uint64_t)lb * SELECT_THREADS * (uint64_t)rd->max_len * 16ull;
+    if ((st = sweep_grid(rd->max_len, sb))) return st;
+    if ((st = select_grid(lb))) return st;
+    const uint64_t need_sweep = (uint64_t)*sb * (SWEEP_THREADS / 4) * 2ull * rd->max_len * 16ull;
+    const uint64_t need_sel = (uint64_t)*lb * SELECT_THREADS * (uint64_t)rd->max_len * 16ull;
     if (ws->quad_scratch_bytes < need_sweep || ws->quad_scratch_bytes < need_sel) return fail(GSM_E_CAPACITY, "quad_scratch too small (see gsm_smem_workspace_info)");
     const uint64_t n_tiles = (rd->n_reads + SCAN_TILE - 1) / SCAN_TILE;
     if (ws->scan_tmp_bytes < (n_tiles + 2) * 8) return fail(GSM_E_CAPACITY, "scan_tmp too small");
+    return GSM_OK;
+}
+
+int gsm_smem_sweep(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_workspace* ws, void* stream_) {
+    int sb = 0, lb = 0;
+    int st = smem_check(ix, rd, ws, &sb, &lb);
+    if (st) return st;
+    cudaStream_t stream = (cudaStream_t)stream_;
     GSM_CUDA(cudaMemsetAsync(ws->counters, 0, 8 * sizeof(uint64_t), stream));
-    if (rd->n_reads == 0) {
-        GSM_CUDA(cudaMemsetAsync(ws->rec_off, 0, sizeof(uint64_t), stream));
-        return GSM_OK;
-    }
-    const IndexMeta meta = make_meta(ix);
+    if (rd->n_reads == 0) return GSM_OK;
     SweepArgs sa;
-    sa.fwd = (const uint4*)ix->fwd_buckets; sa.rev = (const uint4*)ix->rev_buckets; sa.meta = meta;
+    sa.fwd = (const uint4*)ix->fwd_buckets; sa.rev = (const uint4*)ix->rev_buckets; sa.meta = make_meta(ix);
     sa.reads = (const uint4*)rd->packed; sa.chunk_off = rd->chunk_off; sa.len = rd->len; sa.n_reads = (uint32_t)rd->n_reads;
     sa.max_chunks = (rd->max_len + 63u) / 64u; sa.max_len = rd->max_len;
     sa.mem_pool = (uint4*)ws->mem_pool; sa.mem_cap = ws->mem_cap; sa.mem_off = ws->mem_off; sa.mem_cnt = ws->mem_cnt;
     sa.scratch = (uint4*)ws->quad_scratch; sa.counters = (unsigned long long*)ws->counters;
     k_sweep<<<sb, SWEEP_THREADS, sweep_smem_bytes(rd->max_len), stream>>>(sa);
     GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
 
+int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd, uint32_t min_len, uint32_t K, const uint32_t* lut,
+                    const gsm_dev_rmi* rmi, gsm_workspace* ws, void* stream_) {
+    int sb = 0, lb = 0;
+    int st = smem_check(ix, rd, ws, &sb, &lb);
+    if (st) return st;
+    if (method < 0 || method > 2) return fail(GSM_E_INVALID, "unknown method");
+    if (method == GSM_METHOD_LUT && (!lut || K < 1 || K > 16)) return fail(GSM_E_INVALID, "LUT method needs a table and K in 1..16");
+    RmiModel rm;
+    memset(&rm, 0, sizeof(rm));
+    if (method == GSM_METHOD_RMI) {
+        if ((st = fill_rmi(rmi, &rm))) return st;
+        if (!ix->sa || !ix->text2bit) return fail(GSM_E_INVALID, "RMI method needs the suffix array and packed text on the device");
+        K = rmi->K;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (rd->n_reads == 0) {
+        GSM_CUDA(cudaMemsetAsync(ws->rec_off, 0, sizeof(uint64_t), stream));
+        return GSM_OK;
+    }
     SelectArgs se;
-    se.fwd = (const uint4*)ix->fwd_buckets; se.meta = meta; se.n_bases = ix->n_rows - 1; se.sa = ix->sa; se.text = ix->text2bit;
+    se.fwd = (const uint4*)ix->fwd_buckets; se.meta = make_meta(ix); se.n_bases = ix->n_rows - 1; se.sa = ix->sa; se.text = ix->text2bit;
     se.reads = (const uint32_t*)rd->packed; se.chunk_off = rd->chunk_off; se.len = rd->len; se.n_reads = (uint32_t)rd->n_reads;
     se.max_len = rd->max_len; se.read_id_base = rd->read_id_base; se.min_len = min_len; se.K = K; se.lut = (const uint2*)lut; se.rmi = rm;
     se.mem_pool = (uint4*)ws->mem_pool; se.mem_off = ws->mem_off; se.mem_cnt = ws->mem_cnt; se.stage = (uint4*)ws->quad_scratch;
     se.rec_tmp = (uint4*)ws->rec_tmp; se.rec_cap = ws->rec_cap; se.rec_tmp_off = ws->rec_tmp_off; se.rec_cnt = ws->rec_cnt;
     se.read_status = ws->read_status; se.counters = (unsigned long long*)ws->counters;
+    GSM_CUDA(cudaMemsetAsync((unsigned long long*)ws->counters + 1, 0, sizeof(uint64_t), stream));
     if (method == GSM_METHOD_BWA) k_select<GSM_METHOD_BWA><<<lb, SELECT_THREADS, 0, stream>>>(se);
     else if (method == GSM_METHOD_LUT) k_select<GSM_METHOD_LUT><<<lb, SELECT_THREADS, 0, stream>>>(se);
     else k_select<GSM_METHOD_RMI><<<lb, SELECT_THREADS, 0, stream>>>(se);
     GSM_CUDA(cudaGetLastError());
-
+    const uint64_t n_tiles = (rd->n_reads + SCAN_TILE - 1) / SCAN_TILE;
     unsigned long long* tiles = (unsigned long long*)ws->scan_tmp;
     k_scan_tiles<<<(unsigned)n_tiles, SCAN_THREADS, 0, stream>>>(ws->rec_cnt, rd->n_reads, (unsigned long long*)ws->rec_off, tiles);
     k_scan_top<<<1, SCAN_THREADS, 0, stream>>>(tiles, n_tiles, tiles + n_tiles);
     k_scan_add<<<(unsigned)n_tiles, SCAN_THREADS, 0, stream>>>((unsigned long long*)ws->rec_off, rd->n_reads, tiles, tiles + n_tiles);
     GSM_CUDA(cudaGetLastError());
     return GSM_OK;
+}
+
+int gsm_smem_batch(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd, uint32_t min_len, uint32_t K, const uint32_t* lut,
+                   const gsm_dev_rmi* rmi, gsm_workspace* ws, void* stream) {
+    int st = gsm_smem_sweep(ix, rd, ws, stream);
+    if (st) return st;
+    return gsm_smem_select(method, ix, rd, min_len, K, lut, rmi, ws, stream);
 }
 
 int gsm_smem_collect(const gsm_dev_reads* rd, gsm_workspace* ws, gsm_record* out, uint64_t out_cap, void* stream) {

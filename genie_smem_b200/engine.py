@@ -269,17 +269,33 @@ class Engine:
         w.scan_tmp, w.scan_tmp_bytes = self.scan_tmp.data_ptr(), self.scan_tmp.numel()
         self.ws = w
         self.kernel_launches = 0
+        self._pin = {}
+        self.last_d2h_bytes = 0
 
-    # -- device-resident step: kernels only (what bench.py times as `value`)
-    def launch(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None):
+    # -- device-resident phases: kernels only (bench.py times these as `value`)
+    def _check_batch(self, reads):
         if reads.n > self.max_reads or reads.max_len > self.max_len:
             raise ValueError("batch exceeds the engine's workspace")
-        r = reads.cstruct()
-        self._reads_c = r
-        capi.check(capi.lib.gsm_smem_batch(method, C.byref(self.index.c), C.byref(r), int(min_len), int(K), _ptr(lut),
-                                           C.byref(rmi.c) if rmi is not None else None, C.byref(self.ws), _stream()))
+        self._reads_c = reads.cstruct()
+        return self._reads_c
+
+    def sweep(self, reads: ReadBatch):
+        """k_sweep: every maximal exact match of every read (method-independent FM walk)."""
+        r = self._check_batch(reads)
+        capi.check(capi.lib.gsm_smem_sweep(C.byref(self.index.c), C.byref(r), C.byref(self.ws), _stream()))
+        self.kernel_launches += 1 if reads.n else 0
+
+    def select(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None):
+        """k_select + scan + gather: the reference's records for one method, in (read, emission) order."""
+        r = self._check_batch(reads)
+        capi.check(capi.lib.gsm_smem_select(method, C.byref(self.index.c), C.byref(r), int(min_len), int(K), _ptr(lut),
+                                            C.byref(rmi.c) if rmi is not None else None, C.byref(self.ws), _stream()))
         capi.check(capi.lib.gsm_smem_collect(C.byref(r), C.byref(self.ws), _ptr(self.records), self.rec_cap, _stream()))
-        self.kernel_launches += 6 if reads.n else 0    # sweep, select, 3 scan kernels, gather
+        self.kernel_launches += 5 if reads.n else 0    # select, 3 scan kernels, gather
+
+    def launch(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None):
+        self.sweep(reads)
+        self.select(method, reads, min_len, K, lut, rmi)
 
     def check_overflow(self):
         c = self.counters.cpu().numpy()
@@ -288,9 +304,16 @@ class Engine:
                                                  f"records {int(c[1])}/{self.rec_cap}")
         return int(c[0]), int(c[1])
 
-    # -- end-to-end step: host reads in, host records out
+    def _pinned(self, name, nbytes):
+        buf = self._pin.get(name)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+            self._pin[name] = buf
+        return buf
+
+    # -- end-to-end step: host reads in (H2D), host records out (D2H)
     def run(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None, grow=True):
-        reads.to(self.device)
+        reads.to(self.device, non_blocking=True)
         while True:
             self.launch(method, reads, min_len, K, lut, rmi)
             try:
@@ -300,10 +323,18 @@ class Engine:
                 if e.code != capi.E_CAPACITY or not grow:
                     raise
                 self._grow()
-        recs = self.records[: n_rec * 16].cpu().numpy().view(RECORD_DTYPE)
-        offs = self.rec_off[: reads.n + 1].cpu().numpy().astype(np.int64)
-        status = self.read_status[: reads.n].cpu().numpy()
-        return SmemResult(recs, offs, status, n_mems)
+        n = reads.n
+        hrec = self._pinned("rec", n_rec * 16)
+        hoff = self._pinned("off", (n + 1) * 8)
+        hst = self._pinned("st", max(n, 1))
+        hrec[: n_rec * 16].copy_(self.records[: n_rec * 16], non_blocking=True)
+        hoff[: (n + 1) * 8].copy_(self.rec_off[: n + 1].view(torch.uint8), non_blocking=True)
+        hst[:n].copy_(self.read_status[:n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.last_d2h_bytes = n_rec * 16 + (n + 1) * 8 + n + 64
+        recs = hrec.numpy()[: n_rec * 16].view(RECORD_DTYPE)
+        offs = hoff.numpy()[: (n + 1) * 8].view(np.int64)
+        return SmemResult(recs, offs, hst.numpy()[:n], n_mems)
 
     def _grow(self):
         dev = self.device

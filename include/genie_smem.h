@@ -203,6 +203,15 @@ int gsm_smem_batch(int method, const gsm_dev_index* idx, const gsm_dev_reads* re
                    uint32_t K, const uint32_t* lut, const gsm_dev_rmi* rmi, gsm_workspace* ws,
                    void* stream);
 
+/* The two halves of gsm_smem_batch, callable separately (bench.py times them separately).
+ * gsm_smem_sweep: every maximal exact match of every read (the FM-index walk, method-independent)
+ * into ws->mem_pool / mem_off / mem_cnt.  gsm_smem_select: the reference's record selection for
+ * one method over that match list; it may be called several times after one sweep. */
+int gsm_smem_sweep(const gsm_dev_index* idx, const gsm_dev_reads* reads, gsm_workspace* ws, void* stream);
+int gsm_smem_select(int method, const gsm_dev_index* idx, const gsm_dev_reads* reads, uint32_t min_len,
+                    uint32_t K, const uint32_t* lut, const gsm_dev_rmi* rmi, gsm_workspace* ws,
+                    void* stream);
+
 int gsm_smem_collect(const gsm_dev_reads* reads, gsm_workspace* ws, gsm_record* out, uint64_t out_cap,
                      void* stream);
 

@@ -1,0 +1,69 @@
+"""Pin oracle/smem_oracle.c (the C restatement used as CPU baseline and bulk checker) against the
+golden fixtures frozen from the live reference."""
+import numpy as np
+import pytest
+
+from oracle.c_oracle import COracle
+from tests import golden_util as gu
+
+
+@pytest.fixture(scope="module")
+def orcs():
+    out = {}
+    for name in ("small_data", "medium_data", "big_data"):
+        g = gu.load_index(name)
+        out[name] = (g, COracle(g["text"], g["suffix_array"]))
+    return out
+
+
+def test_backsearch_matches_python_port(orcs):
+    from oracle import ref_port as rp
+    g, o = orcs["medium_data"]
+    idx = rp.RefIndex(g["text"], g["suffix_array"])
+    rng = np.random.default_rng(3)
+    reads = []
+    for _ in range(300):
+        L = int(rng.integers(1, 60))
+        p = int(rng.integers(0, len(g["text"]) - L))
+        reads.append(g["text"][p:p + L])
+        reads.append("".join("ACGT"[c] for c in rng.integers(0, 4, L)))
+    lo, hi = o.backsearch(reads)
+    for q, l, h in zip(reads, lo, hi):
+        e = idx.exact_match_back_prop(q)
+        assert (-1 if h < l else (int(l), int(h))) == e
+
+
+@pytest.mark.parametrize("tag,name", [("medium_data_k6", "medium_data"), ("big_data_k12", "big_data"), ("big_data_k15", "big_data")])
+def test_rmi_lookups(orcs, tag, name):
+    _, o = orcs[name]
+    p = gu.load_rmi(tag)
+    for q, pred, lo, hi in gu.load_json(f"rmi_lookups_{tag}.json.gz"):
+        code = 0
+        for ch in q:
+            code = code << 2 | "ACGT".index(ch)
+        st, gp, glo, ghi = o.rmi_lookup(p, code)
+        if pred is None:
+            assert st == -1
+        else:
+            assert st == 0 and gp == pred and (glo, ghi) == (lo, hi)
+
+
+@pytest.mark.parametrize("fname", ["smems_c1_big_exact101.json.gz", "smems_c2_big_mixed101.json.gz", "smems_big_sub151.json.gz",
+                                   "smems_medium_fuzz.json.gz"])
+def test_smem_sets(orcs, fname):
+    g = gu.load_json(fname)
+    _, o = orcs[g["ref"]]
+    reads = g["reads"]
+    for ml, exp in g["bwa"].items():
+        assert o.smem_dicts(0, reads, min_len=int(ml)) == exp
+    sel = [i for i, e in enumerate(g["lut"]) if e is not None]
+    assert o.smem_dicts(1, [reads[i] for i in sel], K=g["K_lut"]) == [g["lut"][i] for i in sel]
+    for tag, exp in g["rmi"].items():
+        p = gu.load_rmi(tag)
+        sel = [i for i, e in enumerate(exp) if e is not None]
+        got = o.smem_dicts(2, [reads[i] for i in sel], rmi=p)
+        for k, i in enumerate(sel):
+            if isinstance(exp[i], dict):
+                assert got[k] == "raises"
+            else:
+                assert got[k] == exp[i]
