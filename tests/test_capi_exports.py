@@ -1,0 +1,104 @@
+"""The C-ABI library loads and exports every symbol include/genie_smem.h declares; host-side entry
+points work without a GPU; device entry points refuse (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests import golden_util as gu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "genie_smem.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from genie_smem_b200 import _capi as capi
+    names = declared_functions()
+    assert len(names) >= 18
+    lib = C.CDLL(capi.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/genie_smem.h but not exported"
+    assert set(capi.EXPORTS) == set(names), "ctypes bindings out of sync with the header"
+    assert capi.lib.gsm_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    from genie_smem_b200 import _capi as capi
+    assert C.sizeof(capi.IndexInfo) == 96      # 92 bytes of fields, 8-byte aligned
+    assert C.sizeof(capi.DevIndex) == 2 * 8 + 4 * 8 + 5 * 4 + 3 * 4
+    assert C.sizeof(capi.DevReads) == 8 + 3 * 8 + 2 * 4
+    assert C.sizeof(capi.Workspace) == 15 * 8
+    from genie_smem_b200.engine import RECORD_DTYPE
+    assert RECORD_DTYPE.itemsize == 16
+
+
+@pytest.mark.parametrize("name", ["small_data", "medium_data", "big_data"])
+def test_host_builder_reproduces_reference_arrays(name):
+    import genie_smem_b200 as g
+    gi = gu.load_index(name)
+    h = g.HostIndex.build(gi["text"])
+    sa, bwt = h.export()
+    assert np.array_equal(sa, gi["suffix_array"])
+    assert bwt.decode() == gi["bwt"]
+    assert h.count_dic() == gu.meta()[name]["count_dic"]
+    # importer ("same index arrays"): identical device layouts from reference-built SA
+    h2 = g.HostIndex.from_arrays(gi["text"], gi["suffix_array"])
+    for a, b in zip(h.pack(), h2.pack()):
+        assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        g.HostIndex.from_arrays(gi["text"], gi["suffix_array"][::-1].copy() * 0 + 1)
+
+
+def test_host_builder_on_repetitive_and_tiny_texts():
+    import genie_smem_b200 as g
+    from oracle import ref_port as rp
+    rng = np.random.default_rng(0)
+    texts = ["A", "AC", "ACGT", "AAAAAAAA", "ACACACACACAC", "TAACCC" * 50, "GATTACA" * 9 + "T"]
+    texts += ["".join("ACGT"[c] for c in rng.integers(0, 4, int(n))) for n in rng.integers(1, 400, 20)]
+    texts += ["".join("AC"[c] for c in rng.integers(0, 2, 300))]
+    for t in texts:
+        sa, bwt = g.HostIndex.build(t).export()
+        o = rp.RefIndex(t)
+        assert np.array_equal(sa.astype(np.int64), o.suffix_array), t
+        assert bwt.decode() == o.bwt
+
+
+def test_non_acgt_is_rejected():
+    import genie_smem_b200 as g
+    with pytest.raises(KeyError):
+        g.HostIndex.build("ACGTN")
+    with pytest.raises(ValueError):
+        g.ReadBatch.from_strings(["ACGT", "acgt"])
+
+
+def test_read_packing_roundtrip():
+    import genie_smem_b200 as g
+    reads = ["ACGT", "T" * 65, "", "GATTACA" * 30]
+    b = g.ReadBatch.from_strings(reads)
+    assert list(b.chunk_off_host) == [0, 1, 3, 3, 7]
+    words = b.packed_host.view(np.uint32)
+    for i, r in enumerate(reads):
+        w = words[b.chunk_off_host[i] * 4:]
+        got = "".join("ACGT"[(int(w[p >> 4]) >> (30 - 2 * (p & 15))) & 3] for p in range(len(r)))
+        assert got == r
+
+
+def test_device_entry_points_refuse_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import genie_smem_b200 as g
+    from genie_smem_b200 import _capi as capi
+    with pytest.raises(g.GsmError) as e:
+        g.DeviceIndex(g.HostIndex.build("ACGTACGT"))
+    assert e.value.code == capi.E_NODEVICE
+    wi = capi.WorkspaceInfo()
+    assert capi.lib.gsm_smem_workspace_info(10, 100, C.byref(wi)) == capi.E_NODEVICE
+    assert b"no CPU fallback" in capi.lib.gsm_last_error()

@@ -1,0 +1,131 @@
+"""Host build of the kernels' per-read logic (tests/emu: the SAME sweep_logic.cuh / select_logic.cuh
+/ fm_core.cuh the CUDA kernels compile) against the golden fixtures and the oracle.  This is what
+keeps the control flow honest in the GPU-less container; the GPU runs the same headers in
+tests/test_gpu_parity.py."""
+import random
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import ref_port as rp
+from tests import golden_util as gu
+from tests.emu.harness import Emu, records_to_dict
+
+
+@pytest.fixture(scope="module")
+def emus():
+    out = {}
+    for name in ("small_data", "medium_data", "big_data"):
+        g = gu.load_index(name)
+        out[name] = (g, Emu(g["text"]))
+    return out
+
+
+def test_device_layout_lut_equals_reference_table(emus):
+    _, em = emus["medium_data"]
+    g = gu.load_lut("medium_data_k6")
+    t = em.lut(6).reshape(-1, 2)
+    keys = np.nonzero(t[:, 1])[0]
+    assert np.array_equal(keys.astype(np.uint32), g["keys"])
+    assert np.array_equal(t[keys, 0], g["lo"])
+    assert np.array_equal(t[keys, 0] + t[keys, 1] - 1, g["hi"])
+
+
+@pytest.mark.parametrize("tag,name", [("medium_data_k6", "medium_data"), ("big_data_k15", "big_data")])
+def test_rmi_lookup_logic(emus, tag, name):
+    _, em = emus[name]
+    p = gu.load_rmi(tag)
+    for q, pred, lo, hi in gu.load_json(f"rmi_lookups_{tag}.json.gz")[::3]:
+        code = 0
+        for ch in q:
+            code = code << 2 | "ACGT".index(ch)
+        s, gp, glo, ghi = em.rmi_lookup(p, code)
+        if pred is None:
+            assert s == -1
+        else:
+            assert s == 0 and gp == pred and (glo, ghi) == (lo, hi)
+
+
+@pytest.mark.parametrize("fname,stride", [("smems_c1_big_exact101.json.gz", 7), ("smems_c2_big_mixed101.json.gz", 3),
+                                          ("smems_big_sub151.json.gz", 2), ("smems_medium_fuzz.json.gz", 2)])
+def test_sweep_and_select_logic_vs_reference(emus, fname, stride):
+    g = gu.load_json(fname)
+    _, em = emus[g["ref"]]
+    reads = g["reads"]
+    for ml, exp in g["bwa"].items():
+        for q, e in list(zip(reads, exp))[::stride]:
+            assert records_to_dict(q, em.smem(0, q, int(ml))) == e
+    for q, e in list(zip(reads, g["lut"]))[::stride]:
+        if e is not None:
+            assert records_to_dict(q, em.smem(1, q, 1, g["K_lut"])) == e
+    for tag, exp in g["rmi"].items():
+        p = gu.load_rmi(tag)
+        for q, e in list(zip(reads, exp))[::stride]:
+            if e is None:
+                continue
+            r = em.smem(2, q, 1, 0, p)
+            if isinstance(e, dict):
+                assert r == "raises"
+            else:
+                assert records_to_dict(q, r) == e
+
+
+def test_maximal_matches_are_exactly_the_right_maximal_LS_pairs(emus):
+    """sweep output == {(LS[j], j) : j == L or LS[j+1] > LS[j]} with true SA intervals."""
+    g, em = emus["medium_data"]
+    idx = rp.RefIndex(g["text"], g["suffix_array"])
+    rng = random.Random(5)
+    for _ in range(150):
+        L = rng.randint(1, 90)
+        if rng.random() < 0.5:
+            p = rng.randrange(0, len(g["text"]) - L)
+            q = list(g["text"][p:p + L])
+            for k in range(L):
+                if rng.random() < 0.05:
+                    q[k] = rng.choice("ACGT")
+            q = "".join(q)
+        else:
+            q = "".join(rng.choice("ACGT") for _ in range(L))
+        LS = [0] * (L + 2)
+        for j in range(1, L + 1):
+            i = j - 1
+            while i > 0 and idx.exact_match_back_prop(q[i - 1:j]) != -1:
+                i -= 1
+            LS[j] = i
+        exp = []
+        for j in range(1, L + 1):
+            if j == L or LS[j + 1] > LS[j]:
+                lo, hi = idx.exact_match_back_prop(q[LS[j]:j])
+                exp.append((LS[j], j, lo, hi - lo + 1))
+        got, steps = em.sweep(q)
+        assert got == exp
+        assert steps <= 6 * L + 40
+
+
+ACGT = st.text(alphabet="ACGT", min_size=1, max_size=60)
+
+
+@settings(max_examples=60, deadline=None)
+@given(text=st.one_of(st.text(alphabet="ACGT", min_size=8, max_size=200),
+                      st.builds(lambda u, k: (u * k)[:200], st.text(alphabet="ACGT", min_size=1, max_size=7), st.integers(2, 40))),
+       reads=st.lists(ACGT, min_size=1, max_size=6), K=st.integers(2, 5))
+def test_property_random_and_repetitive_references(text, reads, K):
+    if len(set(text)) < 4:
+        text = text + "ACGT"           # parity domain: all four bases occur
+    em = Emu(text)
+    idx = rp.RefIndex(text)
+    o = rp.RefSMEM(idx, lut=rp.RefLUT(idx, K))
+    for q in reads:
+        assert records_to_dict(q, em.smem(0, q, 1)) == gu.norm(o.get_SMEMS(q, 1))
+        if len(q) >= K:
+            assert records_to_dict(q, em.smem(1, q, 1, K)) == gu.norm(o.get_smems_lut(q))
+
+
+def test_long_low_complexity_read_overflows_candidate_cache(emus):
+    """> 32 occurrence-count changes in one forward extension: exercises the candidate spill path."""
+    text = "A" * 300 + "C" + "A" * 120 + "G" + "ACGT" * 5 + "T" * 80
+    em = Emu(text)
+    o = rp.RefSMEM(rp.RefIndex(text))
+    for q in ["A" * 151, "A" * 100 + "C" + "A" * 50, "T" * 70 + "A" * 81, "A" * 40 + "G" + "ACGT" * 3 + "T" * 60]:
+        assert records_to_dict(q, em.smem(0, q, 1)) == gu.norm(o.get_SMEMS(q, 1))
