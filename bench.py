@@ -193,7 +193,7 @@ def main():
     reads_codes = make_reads_host(ref, args.reads, READ_LEN, seed=101 + rank)
     batch = g.ReadBatch.from_codes(reads_codes, READ_LEN, read_id_base=0, pin=True)
     batch.to(dev)
-    engine = g.Engine(index, args.reads, READ_LEN, mems_per_read=10, recs_per_read=8)
+    engine = g.Engine(index, args.reads, READ_LEN, mems_per_read=24, recs_per_read=8)
     lut = g.lut_build(index, LUT_K)
     # RMI: trained on the host from this index (any (coef, intercept) set is valid input; the
     # oracle is given the same parameters)
@@ -307,7 +307,7 @@ def main():
 
     # ---- CPU baseline on the host cores, rank 0 at N=1 only
     cpu_baseline = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.cpu_seconds > 0:
         sa1, _ = host.export()
         v, n_s, thr = cpu_arm(text, sa1, reads_codes, 0, 0, args.cpu_seconds)
         cpu_baseline = {"value": round(v, 1), "unit": "reads/s", "cores": thr, "kind": "port",

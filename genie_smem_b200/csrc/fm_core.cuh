@@ -1,13 +1,14 @@
 // FM-index rank arithmetic shared by every kernel (and by the host-compiled logic test).
 //
-// One rank bucket = 64 bytes = 16 words:
-//   w[0..3]           raw counts of A,C,G,T in rows [0, 192*b)   ('$' slot counted as A)
-//   w[4k], w[4k+1]    low-bit  plane of symbols 64(k-1) .. 64(k-1)+63     (k = 1..3)
-//   w[4k+2], w[4k+3]  high-bit plane of the same symbols
-// so a rank query is ONE aligned 64-byte fetch: four lanes ("a quad") load 16 bytes each with
-// a single 128-bit load; lane 0 holds the checkpoint, lanes 1..3 popcount 64 symbols each.
-// This replaces the reference's n x 5 inclusive occurrence matrix (ExactMatch.py:70-90) and the
-// two list reads per step of exact_match_back_prop (ExactMatch.py:140-145).
+// One rank bucket = 64 bytes = two 32-byte halves; half g (g = 0, 1) holds
+//   w[0], w[1]        raw counts of symbols 2g and 2g+1 in rows [0, 192*b)   ('$' slot counted as A)
+//   w[2..4]           low-bit  plane of symbols 96g .. 96g+95 of the bucket (bit t of word m = symbol 96g+32m+t)
+//   w[5..7]           high-bit plane of the same symbols
+// so a rank query is ONE aligned 64-byte fetch: two lanes ("a pair") load one half each with a
+// single 256-bit load, popcount at most 96 symbols each, and add their two checkpoint words; both
+// lanes do the same amount of useful work.  This replaces the reference's n x 5 inclusive occurrence
+// matrix (ExactMatch.py:70-90) and the two list reads per step of exact_match_back_prop
+// (ExactMatch.py:140-145).
 #pragma once
 #include <stdint.h>
 
@@ -21,6 +22,13 @@ namespace gsm {
 
 struct U4 {
     uint32_t x, y, z, w;
+};
+
+// one 32-byte half of a bucket
+struct Half {
+    uint32_t c0, c1;        // checkpoint counts of symbols 2g, 2g+1
+    uint32_t l0, l1, l2;    // low-bit plane
+    uint32_t h0, h1, h2;    // high-bit plane
 };
 
 GSM_HD uint32_t popc32(uint32_t v) {
@@ -41,32 +49,57 @@ GSM_HD void split192(uint32_t p, uint32_t& bucket, uint32_t& r) {
     r = p - bucket * 192u;
 }
 
-// Per-lane contribution of one 16-byte part of a bucket to a rank query at in-bucket offset r:
-// returns (#symbols == c) | (#symbols < c) << 8 among the first r symbols, counting only the 64
-// symbols this part (ql = 1..3) holds.  ql == 0 (the checkpoint part) contributes 0.
-GSM_HD uint32_t part_counts(const U4& v, uint32_t r, uint32_t c, uint32_t ql) {
-    int nsym = (int)r - 64 * ((int)ql - 1);
-    if (ql == 0 || nsym <= 0) return 0u;
-    uint32_t m0, m1;
-    if (nsym >= 64) { m0 = 0xFFFFFFFFu; m1 = 0xFFFFFFFFu; }
-    else if (nsym >= 32) { m0 = 0xFFFFFFFFu; m1 = (nsym == 32) ? 0u : ((1u << (nsym - 32)) - 1u); }
-    else { m0 = (1u << nsym) - 1u; m1 = 0u; }
-    const uint32_t fl = (c & 1u) ? 0u : 0xFFFFFFFFu;   // flip so that "bit == c's bit" reads as 1
-    const uint32_t fh = (c & 2u) ? 0u : 0xFFFFFFFFu;
-    const uint32_t X = (c >= 2u) ? 0xFFFFFFFFu : 0u;
-    const uint32_t Y = (c == 3u) ? 0xFFFFFFFFu : 0u;
-    const uint32_t Z = (c != 0u) ? 0xFFFFFFFFu : 0u;
-    const uint32_t L0 = v.x, L1 = v.y, H0 = v.z, H1 = v.w;
-    uint32_t eq = popc32((L0 ^ fl) & (H0 ^ fh) & m0) + popc32((L1 ^ fl) & (H1 ^ fh) & m1);
-    // symbols < c:  c=1: ~H&~L   c=2: ~H   c=3: ~H|~L   c=0: none
-    uint32_t lt = popc32(((~H0 & (~L0 | X)) | (~L0 & Y)) & m0 & Z) + popc32(((~H1 & (~L1 | X)) | (~L1 & Y)) & m1 & Z);
+// n low bits set, n in 0..32
+GSM_HD uint32_t mask_low(uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    uint32_t m;
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(0u), "r"(n));
+    return m;
+#else
+    return n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u);
+#endif
+}
+
+GSM_HD uint32_t clamp32(int v) { return (uint32_t)(v < 0 ? 0 : (v > 32 ? 32 : v)); }
+
+// Per-symbol constants of a rank query, computed once per step.
+struct SymK {
+    uint32_t fl, fh;    // plane flips so that "bit == c's bit" reads as 1
+    uint32_t X, Y;      // lt selector:  c=1: ~H&~L   c=2: ~H   c=3: ~H|~L
+    uint32_t nz;        // all ones unless c == 0 (nothing is smaller than A)
+};
+
+GSM_HD SymK sym_consts(uint32_t c) {
+    SymK k;
+    k.fl = 0u - ((c & 1u) ^ 1u);
+    k.fh = 0u - (((c >> 1) & 1u) ^ 1u);
+    k.X = 0u - (c >> 1);
+    k.Y = 0u - (c & (c >> 1));
+    k.nz = 0u - (uint32_t)(c != 0u);
+    return k;
+}
+
+// In-bucket contribution of half g to a rank query at in-bucket offset r (0..191):
+// (#symbols == c) | (#symbols < c) << 8 among the symbols of this half that lie below r.
+GSM_HD uint32_t half_counts(const Half& v, uint32_t r, const SymK& k, uint32_t g) {
+    const int n = (int)r - 96 * (int)g;             // symbols of this half below r (may be <0 or >96)
+    const uint32_t m0 = mask_low(clamp32(n)), m1 = mask_low(clamp32(n - 32)), m2 = mask_low(clamp32(n - 64));
+    const uint32_t eq = popc32((v.l0 ^ k.fl) & (v.h0 ^ k.fh) & m0) + popc32((v.l1 ^ k.fl) & (v.h1 ^ k.fh) & m1) +
+                        popc32((v.l2 ^ k.fl) & (v.h2 ^ k.fh) & m2);
+    const uint32_t lt = popc32(((~v.h0 & (~v.l0 | k.X)) | (~v.l0 & k.Y)) & m0 & k.nz) +
+                        popc32(((~v.h1 & (~v.l1 | k.X)) | (~v.l1 & k.Y)) & m1 & k.nz) +
+                        popc32(((~v.h2 & (~v.l2 | k.X)) | (~v.l2 & k.Y)) & m2 & k.nz);
     return eq | (lt << 8);
 }
 
-// Checkpoint part: counts of c and of symbols < c before the bucket.
-GSM_HD void header_counts(const U4& v, uint32_t c, uint32_t& h_eq, uint32_t& h_lt) {
-    h_eq = c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
-    h_lt = c == 0 ? 0u : c == 1 ? v.x : c == 2 ? v.x + v.y : v.x + v.y + v.z;
+// Checkpoint contribution of half g: its share of count(c) and of count(symbols < c) before the bucket.
+GSM_HD void half_header(const Half& v, uint32_t c, uint32_t g, uint32_t& h_eq, uint32_t& h_lt) {
+    const uint32_t mine = (c >> 1) == g ? ((c & 1u) ? v.c1 : v.c0) : 0u;
+    // half 0 holds A,C: A < c for c >= 1, C < c for c >= 2; half 1 holds G,T: G < c only for c == 3
+    const uint32_t lt0 = (c >= 1u ? v.c0 : 0u) + (c >= 2u ? v.c1 : 0u);
+    const uint32_t lt1 = c == 3u ? v.c0 : 0u;
+    h_eq = mine;
+    h_lt = g == 0u ? lt0 : lt1;
 }
 
 // Result of one extension step on an index with rows [P0, P1) and symbol c:
@@ -79,46 +112,42 @@ struct StepOut {
 };
 
 // Combine raw totals (checkpoint + in-bucket, '$' still counted as A) into a step result.
-GSM_HD StepOut finish_step(uint32_t eq0, uint32_t lt0, uint32_t eq1, uint32_t lt1, uint32_t P0, uint32_t P1,
-                           uint32_t c, uint32_t Cc, uint32_t primary) {
+// eq0/eq1 = raw count(c) below P0/P1, ltd = raw count(< c) in [P0, P1).
+GSM_HD StepOut finish_step(uint32_t eq0, uint32_t eq1, uint32_t ltd, uint32_t P0, uint32_t P1, uint32_t c, uint32_t Cc,
+                           uint32_t primary) {
     const uint32_t a0 = P0 > primary ? 1u : 0u;   // the fake A of the '$' slot lies below P0
     const uint32_t a1 = P1 > primary ? 1u : 0u;
     const uint32_t inrange = a1 - a0;
+    const uint32_t isA = c == 0u ? 1u : 0u;
     StepOut o;
-    if (c == 0) {
-        o.lo_new = Cc + eq0 - a0;
-        o.cnt_new = (eq1 - eq0) - inrange;
-        o.lt_add = inrange;
-    } else {
-        o.lo_new = Cc + eq0;
-        o.cnt_new = eq1 - eq0;
-        o.lt_add = lt1 - lt0;   // raw lt counts include the fake A exactly when '$' is in range
-    }
+    o.lo_new = Cc + eq0 - (isA & a0);
+    o.cnt_new = (eq1 - eq0) - (isA & inrange);
+    o.lt_add = isA ? inrange : ltd;   // raw lt counts include the fake A exactly when '$' is in range
     return o;
 }
 
-// Whole-bucket rank by ONE thread (used by the selection kernels' rare paths, the LUT builder
-// and the host-compiled logic test).  bk = bucket array as 16-byte parts.
-template <typename LoadU4>
-GSM_HD StepOut step_single(LoadU4 load, uint32_t P0, uint32_t P1, uint32_t c, uint32_t Cc, uint32_t primary) {
-    uint32_t tot[2][2];
+// Whole-bucket rank by ONE thread (selection kernels' rare paths, LUT builder, host logic test).
+// load(i) returns the i-th 32-byte half of the bucket array.
+template <typename LoadHalf>
+GSM_HD StepOut step_single(LoadHalf load, uint32_t P0, uint32_t P1, uint32_t c, uint32_t Cc, uint32_t primary) {
+    const SymK k = sym_consts(c);
+    uint32_t eq[2], lt[2];
     const uint32_t P[2] = {P0, P1};
     for (int e = 0; e < 2; ++e) {
         uint32_t b, r;
         split192(P[e], b, r);
-        uint32_t h_eq, h_lt;
-        U4 h = load((uint64_t)b * 4);
-        header_counts(h, c, h_eq, h_lt);
-        uint32_t acc = 0;
-        for (uint32_t ql = 1; ql <= 3; ++ql) {
-            if ((int)r - 64 * ((int)ql - 1) <= 0) break;
-            U4 v = load((uint64_t)b * 4 + ql);
-            acc += part_counts(v, r, c, ql);
+        uint32_t acc = 0, he = 0, hl = 0;
+        for (uint32_t g = 0; g < 2; ++g) {
+            const Half v = load((uint64_t)b * 2 + g);
+            uint32_t a, l;
+            half_header(v, c, g, a, l);
+            he += a; hl += l;
+            acc += half_counts(v, r, k, g);
         }
-        tot[e][0] = h_eq + (acc & 0xFFu);
-        tot[e][1] = h_lt + ((acc >> 8) & 0xFFu);
+        eq[e] = he + (acc & 0xFFu);
+        lt[e] = hl + ((acc >> 8) & 0xFFu);
     }
-    return finish_step(tot[0][0], tot[0][1], tot[1][0], tot[1][1], P0, P1, c, Cc, primary);
+    return finish_step(eq[0], eq[1], lt[1] - lt[0], P0, P1, c, Cc, primary);
 }
 
 // Packed sequences (reads and text) are MSB-first: base i lives in bits [30-2(i%16), 32-2(i%16))

@@ -8,7 +8,7 @@
 //   bwt_array    (last column)                    ExactMatch.py:64
 //   count_dic    (first row per leading char)     ExactMatch.py:92-101
 // The inclusive occurrence matrix (ExactMatch.py:70-90) is not materialised: it is replaced by
-// 64-byte rank buckets {u32 occ[4]; 192 two-bit symbols as bit planes} (see fm_device.cuh).
+// 64-byte rank buckets (two 32-byte halves of {u32 occ[2]; 96 two-bit symbols as bit planes}, fm_core.cuh).
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -146,33 +146,32 @@ void suffix_sort(const uint8_t* sym, int32_t* SA, int32_t n) {
 }
 
 // ---------------------------------------------------------------------------------- buckets
-// bwt: n symbols in 0..3 ('$' stored as 0 at the primary row).  Layout per 64-byte bucket b
-// (rows [192b, 192b+192)): w[0..3] = raw counts of A,C,G,T in rows [0,192b) (the '$' slot
-// counts as A; rank(A, p) is corrected by (p > primary) on the device); for part k = 1..3:
-// w[4k], w[4k+1] = low-bit plane of symbols 64(k-1)..64(k-1)+63, w[4k+2], w[4k+3] = high-bit plane.
+// bwt: n symbols in 0..3 ('$' stored as 0 at the primary row).  Layout per 64-byte bucket b (rows
+// [192b, 192b+192)), two 32-byte halves g = 0, 1 (fm_core.cuh): w[8g], w[8g+1] = raw counts of symbols
+// 2g, 2g+1 in rows [0,192b) (the '$' slot counts as A; rank(A, p) is corrected by (p > primary) on the
+// device); w[8g+2..8g+4] = low-bit plane of symbols 96g..96g+95, w[8g+5..8g+7] = high-bit plane.
 void pack_buckets(const uint8_t* bwt, uint64_t n, std::vector<uint32_t>& out) {
     uint64_t nb = n / GSM_BUCKET_SYMS + 1;
     out.assign(nb * 16, 0);
     uint32_t run[4] = {0, 0, 0, 0};
     for (uint64_t b = 0; b < nb; ++b) {
         uint32_t* w = &out[b * 16];
-        w[0] = run[0]; w[1] = run[1]; w[2] = run[2]; w[3] = run[3];
+        w[0] = run[0]; w[1] = run[1]; w[8] = run[2]; w[9] = run[3];
         uint64_t base = b * GSM_BUCKET_SYMS;
-        for (int k = 1; k <= 3; ++k) {
-            uint64_t lo = 0, hi = 0;
-            for (int t = 0; t < 64; ++t) {
-                uint64_t r = base + 64 * (k - 1) + t;
-                if (r >= n) break;
-                uint32_t c = bwt[r];
-                run[c]++;
-                lo |= (uint64_t)(c & 1u) << t;
-                hi |= (uint64_t)(c >> 1) << t;
+        for (int g = 0; g < 2; ++g)
+            for (int m = 0; m < 3; ++m) {
+                uint32_t lo = 0, hi = 0;
+                for (int t = 0; t < 32; ++t) {
+                    uint64_t r = base + 96 * g + 32 * m + t;
+                    if (r >= n) break;
+                    uint32_t c = bwt[r];
+                    run[c]++;
+                    lo |= (c & 1u) << t;
+                    hi |= (c >> 1) << t;
+                }
+                w[8 * g + 2 + m] = lo;
+                w[8 * g + 5 + m] = hi;
             }
-            w[4 * k + 0] = (uint32_t)lo;
-            w[4 * k + 1] = (uint32_t)(lo >> 32);
-            w[4 * k + 2] = (uint32_t)hi;
-            w[4 * k + 3] = (uint32_t)(hi >> 32);
-        }
     }
 }
 

@@ -22,6 +22,8 @@
 #include "../../include/genie_smem.h"
 #include "host_common.hpp"
 #include "select_logic.cuh"
+#include "sweep_device.cuh"
+
 
 namespace gsm {
 
@@ -33,142 +35,7 @@ namespace gsm {
     } while (0)
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
-constexpr int SWEEP_THREADS = 128;
-constexpr int SWEEP_CAP = 32;        // candidates kept in shared memory per quad
 constexpr int SELECT_THREADS = 128;
-
-__device__ __forceinline__ U4 ldg_u4(const uint4* p) {
-    uint4 v = __ldg(p);
-    return U4{v.x, v.y, v.z, v.w};
-}
-
-// One FM extension step executed by all quads of a warp together.  Every lane passes its quad's
-// operands; `active` quads get their result, inactive ones issue no loads.
-__device__ __forceinline__ StepOut quad_step(const uint4* __restrict__ bk, uint32_t P0, uint32_t P1, uint32_t ch,
-                                             uint32_t Cc, uint32_t primary, uint32_t ql, bool active) {
-    uint32_t b0, r0, b1, r1;
-    split192(P0, b0, r0);
-    split192(P1, b1, r1);
-    U4 v0 = U4{0, 0, 0, 0}, v1;
-    if (active) v0 = ldg_u4(bk + (size_t)b0 * 4 + ql);
-    v1 = v0;
-    if (active && b1 != b0) v1 = ldg_u4(bk + (size_t)b1 * 4 + ql);
-    uint32_t packed = part_counts(v0, r0, ch, ql) | (part_counts(v1, r1, ch, ql) << 16);
-    packed += __shfl_xor_sync(FULL, packed, 1);
-    packed += __shfl_xor_sync(FULL, packed, 2);
-    uint32_t he0, hl0, he1, hl1;
-    header_counts(v0, ch, he0, hl0);
-    header_counts(v1, ch, he1, hl1);
-    const uint32_t A = __shfl_sync(FULL, he0, 0, 4);
-    const uint32_t B = __shfl_sync(FULL, he1, 0, 4);
-    const uint32_t D = __shfl_sync(FULL, hl1 - hl0, 0, 4);
-    const uint32_t eq0 = A + (packed & 0xFFu);
-    const uint32_t eq1 = B + ((packed >> 16) & 0xFFu);
-    const uint32_t ltd = D + ((packed >> 24) & 0xFFu) - ((packed >> 8) & 0xFFu);
-    return finish_step(eq0, 0u, eq1, ltd, P0, P1, ch, Cc, primary);
-}
-
-// ===================================================================================== sweep
-struct SweepArgs {
-    const uint4* fwd;
-    const uint4* rev;
-    IndexMeta meta;
-    const uint4* reads;
-    const uint32_t* chunk_off;
-    const uint32_t* len;
-    uint32_t n_reads;
-    uint32_t max_chunks;     // 16-byte chunks of the longest read
-    uint32_t max_len;
-    uint4* mem_pool;
-    unsigned long long mem_cap;
-    uint32_t* mem_off;
-    uint32_t* mem_cnt;
-    uint4* scratch;          // per quad: [0, max_len) match staging, [max_len, 2 max_len) candidate spill
-    unsigned long long* counters;
-};
-
-struct DevSweepCtx {
-    const SweepArgs& a;
-    uint32_t* words;      // shared: packed read
-    uint32_t* cj;         // shared: candidate arrays
-    uint32_t* clo;
-    uint32_t* ccnt;
-    uint4* stage;         // global: match staging of this quad
-    uint4* spill;         // global: candidate spill of this quad
-    uint32_t ql, qmask, qbase;
-
-    __device__ __forceinline__ bool fetch(uint32_t& rid, uint32_t& L) {
-        unsigned long long r = 0;
-        if (ql == 0) r = atomicAdd(&a.counters[3], 1ull);
-        r = __shfl_sync(qmask, r, qbase);
-        if (r >= a.n_reads) return false;
-        rid = (uint32_t)r;
-        L = __ldg(a.len + rid);
-        const uint32_t off = __ldg(a.chunk_off + rid);
-        const uint32_t nch = (L + 63u) >> 6;
-        __syncwarp(qmask);                       // everyone is done with the previous read's words
-        for (uint32_t c = ql; c < nch; c += 4) {
-            uint4 v = __ldg(a.reads + (size_t)off + c);
-            reinterpret_cast<uint4*>(words)[c] = v;
-        }
-        __syncwarp(qmask);
-        return true;
-    }
-    __device__ __forceinline__ uint32_t base(uint32_t pos) const { return base_msb(words, pos); }
-    __device__ __forceinline__ void cand_put(uint32_t i, uint32_t j, uint32_t lo, uint32_t cnt) {
-        if (i < SWEEP_CAP) { cj[i] = j; clo[i] = lo; ccnt[i] = cnt; }      // same value from all 4 lanes
-        else if (ql == 0) __stcg(spill + (i - SWEEP_CAP), make_uint4(j, lo, cnt, 0u));
-    }
-    __device__ __forceinline__ void cand_get(uint32_t i, uint32_t& j, uint32_t& lo, uint32_t& cnt) const {
-        if (i < SWEEP_CAP) { j = cj[i]; lo = clo[i]; cnt = ccnt[i]; }
-        else { uint4 v = __ldcg(spill + (i - SWEEP_CAP)); j = v.x; lo = v.y; cnt = v.z; }
-    }
-    __device__ __forceinline__ void cand_sync() { __syncwarp(qmask); }
-    __device__ __forceinline__ void emit(uint32_t idx, MemEntry e) {
-        if (ql == 0) __stcg(stage + idx, make_uint4(e.se, e.lo, e.cnt, e.sweep));
-    }
-    __device__ __forceinline__ void finish(uint32_t rid, uint32_t n) {
-        __syncwarp(qmask);
-        unsigned long long off = 0;
-        if (ql == 0) off = atomicAdd(&a.counters[0], (unsigned long long)n);
-        off = __shfl_sync(qmask, off, qbase);
-        if (off + n > a.mem_cap) {
-            if (ql == 0) { atomicOr(&a.counters[2], 1ull); a.mem_off[rid] = 0; a.mem_cnt[rid] = 0; }
-            return;
-        }
-        for (uint32_t k = ql; k < n; k += 4) a.mem_pool[off + k] = __ldcg(stage + k);
-        if (ql == 0) { a.mem_off[rid] = (uint32_t)off; a.mem_cnt[rid] = n; }
-    }
-};
-
-__global__ void __launch_bounds__(SWEEP_THREADS, 8) k_sweep(const SweepArgs a) {
-    extern __shared__ uint4 smem4[];
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t ql = lane & 3u;
-    const uint32_t quad_in_block = threadIdx.x >> 2;
-    const uint32_t quad_words = a.max_chunks * 4u + 3u * SWEEP_CAP;     // uint32 per quad
-    uint32_t* qs = reinterpret_cast<uint32_t*>(smem4) + (size_t)quad_in_block * quad_words;
-    const size_t gq = (size_t)blockIdx.x * (SWEEP_THREADS / 4) + quad_in_block;
-    DevSweepCtx ctx{a,
-                    qs,
-                    qs + a.max_chunks * 4u,
-                    qs + a.max_chunks * 4u + SWEEP_CAP,
-                    qs + a.max_chunks * 4u + 2 * SWEEP_CAP,
-                    a.scratch + gq * 2 * a.max_len,
-                    a.scratch + gq * 2 * a.max_len + a.max_len,
-                    ql,
-                    0xFu << (lane & ~3u),
-                    lane & ~3u};
-    Sweeper<DevSweepCtx> sw;
-    for (;;) {
-        uint32_t P0 = 0, P1 = 0, ch = 0;
-        bool rev = false;
-        const bool need = sw.prepare(ctx, a.meta, P0, P1, ch, rev);
-        if (!__any_sync(FULL, need)) break;
-        const StepOut r = quad_step(rev ? a.rev : a.fwd, P0, P1, ch, a.meta.C[ch], rev ? a.meta.prim_r : a.meta.prim_f, ql, need);
-        if (need) sw.consume(ctx, a.meta, r);
-    }
-}
 
 // ===================================================================================== select
 struct SelectArgs {
@@ -218,7 +85,7 @@ struct DevSelCtx {
     __device__ void interval(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt) {
         lo = 0; cnt = a.meta.n_rows;
         const uint4* fwd = a.fwd;
-        auto load = [fwd](uint64_t idx) { return ldg_u4(fwd + idx); };
+        auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
         for (uint32_t p = j; p > i; --p) {
             const uint32_t c = base(p - 1);
             StepOut r = step_single(load, lo, lo + cnt, c, a.meta.C[c], a.meta.prim_f);
@@ -256,7 +123,7 @@ struct DevSelCtx {
                 if (base(c + t) != base(pc + t - 1)) return false;
             const uint32_t ch = base(c);
             const uint4* fwd = a.fwd;
-            auto load = [fwd](uint64_t idx) { return ldg_u4(fwd + idx); };
+            auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
             StepOut r = step_single(load, (uint32_t)plo, (uint32_t)phi + 1u, ch, a.meta.C[ch], a.meta.prim_f);
             return r.cnt_new != 0;
         }
@@ -388,7 +255,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(unsigned long long* o
 
 __global__ void k_gather_records(const uint4* rec_tmp, const uint32_t* tmp_off, const uint32_t* cnt, const unsigned long long* off,
                                  uint64_t n_reads, uint4* out, unsigned long long out_cap, unsigned long long* counters) {
-    // one quad per read: records are 16 bytes, a read has a handful of them
+    // four lanes per read: records are 16 bytes, a read has a handful of them
     const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const uint32_t ql = threadIdx.x & 3u;
     if (q >= n_reads) return;
@@ -411,10 +278,10 @@ struct BackArgs {
     uint32_t* cnt;
 };
 
-// exact_match_back_prop (reference SMEM/ExactMatch.py:132-151): one quad per read.
+// exact_match_back_prop (reference SMEM/ExactMatch.py:132-151): one lane pair per read.
 __global__ void __launch_bounds__(128) k_backsearch(const BackArgs a) {
-    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    const uint32_t ql = threadIdx.x & 3u;
+    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const uint32_t ql = threadIdx.x & 1u;
     const bool valid = q < a.n_reads;
     uint32_t L = 0;
     const uint32_t* w = a.reads;
@@ -426,7 +293,7 @@ __global__ void __launch_bounds__(128) k_backsearch(const BackArgs a) {
         if (!__any_sync(FULL, act)) break;
         uint32_t ch = 0;
         if (act) ch = (__ldg(w + (p >> 4)) >> (30u - 2u * ((uint32_t)p & 15u))) & 3u;
-        StepOut r = quad_step(a.fwd, lo, lo + cnt, ch, a.meta.C[ch], a.meta.prim_f, ql, act);
+        StepOut r = pair_step(a.fwd, lo, lo + cnt, ch, a.meta.C[ch], a.meta.prim_f, ql, act);
         if (act) { lo = r.lo_new; cnt = r.cnt_new; --p; }
     }
     if (valid && ql == 0) { a.lo[q] = lo; a.cnt[q] = cnt; }
@@ -434,12 +301,12 @@ __global__ void __launch_bounds__(128) k_backsearch(const BackArgs a) {
 
 // exact_match_back_prop_add_one (reference SMEM/ExactMatch.py:155-171)
 __global__ void __launch_bounds__(128) k_add_one(const uint4* fwd, IndexMeta meta, uint64_t n, const uint8_t* base, uint32_t* lo, uint32_t* cnt) {
-    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    const uint32_t ql = threadIdx.x & 3u;
+    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const uint32_t ql = threadIdx.x & 1u;
     const bool act = q < n && cnt[q] != 0;
     uint32_t l = 0, c = 0, ch = 0;
     if (act) { l = lo[q]; c = cnt[q]; ch = base[q] & 3u; }
-    StepOut r = quad_step(fwd, l, l + c, ch, meta.C[ch], meta.prim_f, ql, act);
+    StepOut r = pair_step(fwd, l, l + c, ch, meta.C[ch], meta.prim_f, ql, act);
     if (act && ql == 0) { lo[q] = r.lo_new; cnt[q] = r.cnt_new; }
 }
 
@@ -453,7 +320,7 @@ __global__ void k_sa_lookup(const uint32_t* sa, uint64_t n_rows, uint64_t n, con
 __global__ void k_lut_build(const uint4* fwd, IndexMeta meta, uint32_t K, uint64_t n_codes, uint2* table) {
     const uint64_t code = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (code >= n_codes) return;
-    auto load = [fwd](uint64_t idx) { return ldg_u4(fwd + idx); };
+    auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
     uint32_t lo = 0, cnt = meta.n_rows;
     for (uint32_t t = 0; t < K && cnt; ++t) {
         const uint32_t c = (uint32_t)(code >> (2 * t)) & 3u;      // backward search: last base first
@@ -477,23 +344,22 @@ __global__ void k_rmi_lookup(const uint32_t* sa, const uint32_t* text, uint64_t 
     status[i] = t.raised ? GSM_READ_REF_RAISES : GSM_READ_OK;
 }
 
-// Random aligned 64-byte gather with the rank kernels' access shape (quad = 4 x 16 B).
-// dependent != 0: each quad runs a pointer chase (latency-bound, like one FM chain);
+// Random aligned 64-byte gather with the rank kernels' access shape (lane pair = 2 x 32 B).
+// dependent != 0: each pair runs a pointer chase (latency-bound, like one FM chain);
 // dependent == 0: independent fetches (the bandwidth ceiling for 64-byte random access).
 __global__ void __launch_bounds__(128) k_gather_probe(const uint4* buf, uint64_t n_buckets, uint32_t iters, uint32_t dependent, unsigned long long* sink) {
-    const uint64_t gq = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
-    const uint32_t ql = threadIdx.x & 3u;
+    const uint64_t gq = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    const uint32_t g = threadIdx.x & 1u;
     uint64_t state = gq * 0x9E3779B97F4A7C15ull + 0x1234567ull;
     uint32_t acc = 0;
     for (uint32_t it = 0; it < iters; ++it) {
         state = state * 6364136223846793005ull + 1442695040888963407ull;
         uint64_t idx = (state >> 17) % n_buckets;
-        uint4 v = __ldg(buf + idx * 4 + ql);
-        uint32_t x = v.x ^ v.y ^ v.z ^ v.w;
+        Half v = ldg_half(buf, idx * 2 + g);
+        uint32_t x = v.c0 ^ v.c1 ^ v.l0 ^ v.l1 ^ v.l2 ^ v.h0 ^ v.h1 ^ v.h2;
         acc += x;
         if (dependent) {
             x ^= __shfl_xor_sync(FULL, x, 1);
-            x ^= __shfl_xor_sync(FULL, x, 2);
             state ^= x;
         }
     }
@@ -524,21 +390,20 @@ int device_ready() {
     return GSM_OK;
 }
 
-size_t sweep_smem_bytes(uint32_t max_len) {
-    const uint32_t max_chunks = (max_len + 63u) / 64u;
-    return (size_t)(SWEEP_THREADS / 4) * (max_chunks * 4u + 3u * SWEEP_CAP) * sizeof(uint32_t);
-}
-
 int sweep_grid(uint32_t max_len, int* blocks) {
     int dev = 0, sms = 0, per_sm = 0;
     GSM_CUDA(cudaGetDevice(&dev));
     GSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t smem = sweep_smem_bytes(max_len);
-    if (smem > 48 * 1024) GSM_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSM_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep, SWEEP_THREADS, smem));
     if (per_sm < 1) return fail(GSM_E_CAPACITY, "read length too large for the sweep kernel's shared memory");
     *blocks = sms * per_sm;
     return GSM_OK;
+}
+
+uint64_t sweep_scratch_bytes(int blocks, uint32_t max_len) {
+    return (uint64_t)blocks * SWEEP_GROUPS * 2ull * max_len * 16ull;
 }
 
 int select_grid(int* blocks) {
@@ -560,7 +425,7 @@ int gsm_smem_workspace_info(uint64_t n_reads, uint32_t max_len, gsm_workspace_in
     int sb = 0, lb = 0;
     if ((st = sweep_grid(max_len, &sb))) return st;
     if ((st = select_grid(&lb))) return st;
-    const uint64_t sweep_bytes = (uint64_t)sb * (SWEEP_THREADS / 4) * 2ull * max_len * 16ull;
+    const uint64_t sweep_bytes = sweep_scratch_bytes(sb, max_len);
     const uint64_t sel_bytes = (uint64_t)lb * SELECT_THREADS * (uint64_t)max_len * 16ull;
     out->quad_scratch_bytes = sweep_bytes > sel_bytes ? sweep_bytes : sel_bytes;
     out->scan_tmp_bytes = ((n_reads + SCAN_TILE - 1) / SCAN_TILE + 2) * 8ull;
@@ -575,7 +440,7 @@ int gsm_backsearch_batch(const gsm_dev_index* ix, const gsm_dev_reads* rd, uint3
     if (st) return st;
     if (rd->n_reads == 0) return GSM_OK;
     BackArgs a{(const uint4*)ix->fwd_buckets, make_meta(ix), (const uint32_t*)rd->packed, rd->chunk_off, rd->len, rd->n_reads, lo, cnt};
-    const uint64_t threads = rd->n_reads * 4;
+    const uint64_t threads = rd->n_reads * 2;
     k_backsearch<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
     GSM_CUDA(cudaGetLastError());
     return GSM_OK;
@@ -586,7 +451,7 @@ int gsm_backsearch_add_one_batch(const gsm_dev_index* ix, uint64_t n, const uint
     int st = device_ready();
     if (st) return st;
     if (n == 0) return GSM_OK;
-    k_add_one<<<(unsigned)((n * 4 + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const uint4*)ix->fwd_buckets, make_meta(ix), n, base, lo, cnt);
+    k_add_one<<<(unsigned)((n * 2 + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const uint4*)ix->fwd_buckets, make_meta(ix), n, base, lo, cnt);
     GSM_CUDA(cudaGetLastError());
     return GSM_OK;
 }
@@ -644,7 +509,7 @@ static int smem_check(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_work
     if (st) return st;
     if ((st = sweep_grid(rd->max_len, sb))) return st;
     if ((st = select_grid(lb))) return st;
-    const uint64_t need_sweep = (uint64_t)*sb * (SWEEP_THREADS / 4) * 2ull * rd->max_len * 16ull;
+    const uint64_t need_sweep = sweep_scratch_bytes(*sb, rd->max_len);
     const uint64_t need_sel = (uint64_t)*lb * SELECT_THREADS * (uint64_t)rd->max_len * 16ull;
     if (ws->quad_scratch_bytes < need_sweep || ws->quad_scratch_bytes < need_sel) return fail(GSM_E_CAPACITY, "quad_scratch too small (see gsm_smem_workspace_info)");
     const uint64_t n_tiles = (rd->n_reads + SCAN_TILE - 1) / SCAN_TILE;
@@ -662,7 +527,7 @@ int gsm_smem_sweep(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_workspa
     SweepArgs sa;
     sa.fwd = (const uint4*)ix->fwd_buckets; sa.rev = (const uint4*)ix->rev_buckets; sa.meta = make_meta(ix);
     sa.reads = (const uint4*)rd->packed; sa.chunk_off = rd->chunk_off; sa.len = rd->len; sa.n_reads = (uint32_t)rd->n_reads;
-    sa.max_chunks = (rd->max_len + 63u) / 64u; sa.max_len = rd->max_len;
+    sa.read_u4 = sweep_read_u4(rd->max_len); sa.max_len = rd->max_len;
     sa.mem_pool = (uint4*)ws->mem_pool; sa.mem_cap = ws->mem_cap; sa.mem_off = ws->mem_off; sa.mem_cnt = ws->mem_cnt;
     sa.scratch = (uint4*)ws->quad_scratch; sa.counters = (unsigned long long*)ws->counters;
     k_sweep<<<sb, SWEEP_THREADS, sweep_smem_bytes(rd->max_len), stream>>>(sa);
@@ -737,7 +602,7 @@ int gsm_gather_probe(const void* buf, uint64_t bytes, uint64_t n_fetch, uint32_t
     int dev = 0, sms = 0;
     GSM_CUDA(cudaGetDevice(&dev));
     GSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const uint64_t quads = (uint64_t)sms * 16 * 32;      // 16 blocks x 128 threads per SM
+    const uint64_t quads = (uint64_t)sms * 16 * 64;      // 16 blocks x 128 threads per SM, one chain per lane pair
     uint32_t iters = (uint32_t)((n_fetch + quads - 1) / quads);
     if (iters == 0) iters = 1;
     k_gather_probe<<<sms * 16, 128, 0, (cudaStream_t)stream>>>((const uint4*)buf, bytes / 64, iters, dependent, (unsigned long long*)sink);

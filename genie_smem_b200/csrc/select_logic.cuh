@@ -226,13 +226,25 @@ struct Selector {
         return f;
     }
 
+    // True SA interval of q[i:j): read it off the match list when (i, j) is itself a maximal match
+    // (the usual case), otherwise one backward search from j down to i.
+    GSM_HD static void true_iv(Ctx& c, uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt) {
+        for (uint32_t k = 0; k < c.n_mems; ++k) {
+            MemEntry m = c.mem(k);
+            if (e_of(m) < j) continue;
+            if (e_of(m) == j && s_of(m) == i) { lo = m.lo; cnt = m.cnt; return; }
+            break;
+        }
+        c.interval(i, j, lo, cnt);
+    }
+
     // forward_extension(query, pc+K, kmer, seed) (SMEM.py:425-443): longest key and its value
     GSM_HD static void fwd_only(Ctx& c, uint32_t pc, int64_t slo, int64_t shi, uint32_t& end, int64_t& lo, int64_t& hi) {
         uint32_t f = F_of(c, pc);
         if (f <= pc + c.K) { end = pc + c.K; lo = slo; hi = shi; return; }   // the seed key itself
         end = f;
         uint32_t l, n;
-        c.interval(pc, f, l, n);
+        true_iv(c, pc, f, l, n);
         lo = (int64_t)l; hi = (int64_t)l + n - 1;
     }
 
@@ -267,11 +279,11 @@ struct Selector {
         if (!have || (fend - pc) > (bj - bi)) {
             out.valid = true; out.i = pc; out.j = fend;
             if (fend == pc + K) { out.lo = slo; out.hi = shi; }
-            else { uint32_t l, n; c.interval(pc, fend, l, n); out.lo = (int64_t)l; out.hi = (int64_t)l + n - 1; }
+            else { uint32_t l, n; true_iv(c, pc, fend, l, n); out.lo = (int64_t)l; out.hi = (int64_t)l + n - 1; }
             return;
         }
         out.valid = true; out.i = bi; out.j = bj;
-        if (!b_from_mem) c.interval(bi, bj, blo, bcnt);
+        if (!b_from_mem) true_iv(c, bi, bj, blo, bcnt);
         out.lo = (int64_t)blo; out.hi = (int64_t)blo + bcnt - 1;
     }
 
@@ -304,7 +316,7 @@ struct Selector {
                     if (hit) fwd_only(c, 0, lo, hi, end, flo, fhi);
                     else {
                         end = F_of(c, 0);
-                        uint32_t l, n; c.interval(0, end, l, n); flo = (int64_t)l; fhi = (int64_t)l + n - 1;
+                        uint32_t l, n; true_iv(c, 0, end, l, n); flo = (int64_t)l; fhi = (int64_t)l + n - 1;
                     }
                     c.emit(0, end, flo, fhi);
                     e = end; plen = end;

@@ -14,8 +14,8 @@ using namespace gsm;
 namespace {
 
 struct HostIndex {
-    const U4* fwd;
-    const U4* rev;
+    const Half* fwd;
+    const Half* rev;
     const uint32_t* sa;
     const uint32_t* text;
     IndexMeta meta;
@@ -141,18 +141,18 @@ struct EmuIndex {
 // Maximal exact matches of one read: out gets 4 x u32 per match (start, end, lo, cnt), sorted by
 // end.  Returns the number of matches.
 int emu_sweep(const EmuIndex* ei, const uint32_t* words, uint32_t L, uint32_t* out, uint32_t cap, uint64_t* n_steps) {
-    HostIndex ix{(const U4*)ei->fwd, (const U4*)ei->rev, ei->sa, ei->text, {}, ei->n_bases};
+    HostIndex ix{(const Half*)ei->fwd, (const Half*)ei->rev, ei->sa, ei->text, {}, ei->n_bases};
     for (int c = 0; c < 4; ++c) { ix.meta.C[c] = ei->C[c]; ix.meta.cnt[c] = ei->cnt[c]; }
     ix.meta.prim_f = ei->prim_f; ix.meta.prim_r = ei->prim_r; ix.meta.n_rows = ei->n_rows;
     SweepCtx ctx; ctx.words = words; ctx.L = L;
     Sweeper<SweepCtx> sw;
     uint64_t steps = 0;
     for (;;) {
-        uint32_t P0, P1, ch; bool rev;
-        if (!sw.prepare(ctx, ix.meta, P0, P1, ch, rev)) break;
-        const U4* bk = rev ? ix.rev : ix.fwd;
+        if (!sw.next(ctx, ix.meta)) break;
+        const bool rev = sw.on_reverse();
+        const Half* bk = rev ? ix.rev : ix.fwd;
         auto load = [&](uint64_t idx) { return bk[idx]; };
-        StepOut r = step_single(load, P0, P1, ch, ix.meta.C[ch], rev ? ix.meta.prim_r : ix.meta.prim_f);
+        StepOut r = step_single(load, sw.P0, sw.P0 + sw.cnt, sw.ch, ix.meta.C[sw.ch], rev ? ix.meta.prim_r : ix.meta.prim_f);
         sw.consume(ctx, ix.meta, r);
         ++steps;
     }
@@ -171,18 +171,18 @@ int emu_sweep(const EmuIndex* ei, const uint32_t* words, uint32_t L, uint32_t* o
 int emu_smem(const EmuIndex* ei, int method, const uint32_t* words, uint32_t L, uint32_t min_len, uint32_t K,
              const uint32_t* lut, uint32_t n_levels, const uint32_t* level_sizes, const double* coef,
              const double* intercept, uint32_t* out, uint32_t cap) {
-    HostIndex ix{(const U4*)ei->fwd, (const U4*)ei->rev, ei->sa, ei->text, {}, ei->n_bases};
+    HostIndex ix{(const Half*)ei->fwd, (const Half*)ei->rev, ei->sa, ei->text, {}, ei->n_bases};
     for (int c = 0; c < 4; ++c) { ix.meta.C[c] = ei->C[c]; ix.meta.cnt[c] = ei->cnt[c]; }
     ix.meta.prim_f = ei->prim_f; ix.meta.prim_r = ei->prim_r; ix.meta.n_rows = ei->n_rows;
     if (method != 0 && L < K) return -2;
     SweepCtx ctx; ctx.words = words; ctx.L = L;
     Sweeper<SweepCtx> sw;
     for (;;) {
-        uint32_t P0, P1, ch; bool rev;
-        if (!sw.prepare(ctx, ix.meta, P0, P1, ch, rev)) break;
-        const U4* bk = rev ? ix.rev : ix.fwd;
+        if (!sw.next(ctx, ix.meta)) break;
+        const bool rev = sw.on_reverse();
+        const Half* bk = rev ? ix.rev : ix.fwd;
         auto load = [&](uint64_t idx) { return bk[idx]; };
-        StepOut r = step_single(load, P0, P1, ch, ix.meta.C[ch], rev ? ix.meta.prim_r : ix.meta.prim_f);
+        StepOut r = step_single(load, sw.P0, sw.P0 + sw.cnt, sw.ch, ix.meta.C[sw.ch], rev ? ix.meta.prim_r : ix.meta.prim_f);
         sw.consume(ctx, ix.meta, r);
     }
     sort_mems(ctx.mems);
@@ -206,7 +206,7 @@ int emu_smem(const EmuIndex* ei, int method, const uint32_t* words, uint32_t L, 
 
 // Dense LUT exactly as the device builder computes it: backward search per code.
 void emu_lut_build(const EmuIndex* ei, uint32_t K, uint32_t* table) {
-    const U4* fwd = (const U4*)ei->fwd;
+    const Half* fwd = (const Half*)ei->fwd;
     auto load = [&](uint64_t idx) { return fwd[idx]; };
     uint64_t ncodes = 1ull << (2 * K);
     for (uint64_t code = 0; code < ncodes; ++code) {

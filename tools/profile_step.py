@@ -26,7 +26,7 @@ def main():
     index = g.DeviceIndex(host, "cuda")
     reads = bench.make_reads_host(ref, a.reads, bench.READ_LEN, seed=101)
     batch = g.ReadBatch.from_codes(reads, bench.READ_LEN).to("cuda")
-    eng = g.Engine(index, a.reads, bench.READ_LEN, mems_per_read=10, recs_per_read=8)
+    eng = g.Engine(index, a.reads, bench.READ_LEN, mems_per_read=24, recs_per_read=8)
     kw = {}
     method = g.METHOD_BWA
     if a.method == "lut":
