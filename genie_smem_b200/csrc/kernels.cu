@@ -81,12 +81,21 @@ struct DevSelCtx {
     }
     __device__ __forceinline__ uint32_t base(uint32_t pos) const { return (__ldg(words + (pos >> 4)) >> (30u - 2u * (pos & 15u))) & 3u; }
     __device__ __forceinline__ bool failed() const { return raised; }
+    __device__ __forceinline__ bool seeds_are_true() const { return METHOD == GSM_METHOD_LUT; }
 
     __device__ void interval(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt) {
         lo = 0; cnt = a.meta.n_rows;
         const uint4* fwd = a.fwd;
         auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
-        for (uint32_t p = j; p > i; --p) {
+        uint32_t p = j;
+        if (METHOD == GSM_METHOD_LUT && j - i >= K) {      // the table replaces the first K backward steps
+            const uint32_t* w = words;
+            auto rd = [w](uint64_t x) { return __ldg(w + x); };
+            const uint2 e = __ldg(a.lut + kmer_code(rd, j - K, K));
+            lo = e.x; cnt = e.y; p = j - K;
+            if (cnt == 0) return;
+        }
+        for (; p > i; --p) {
             const uint32_t c = base(p - 1);
             StepOut r = step_single(load, lo, lo + cnt, c, a.meta.C[c], a.meta.prim_f);
             lo = r.lo_new; cnt = r.cnt_new;

@@ -173,6 +173,7 @@ struct RmiTable {
 //   void interval(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt)   true SA interval of q[i:j]
 //   void emit(uint32_t i, uint32_t j, int64_t lo, int64_t hi)
 //   bool failed()                             the reference raised inside seed()
+//   bool seeds_are_true()                     seed() returns exact SA intervals (LUT), not RMI guesses
 template <typename Ctx>
 struct Selector {
     GSM_HD static uint32_t s_of(const MemEntry& e) { return e.se & 0xFFFFu; }
@@ -326,7 +327,11 @@ struct Selector {
                     if (fstate == 0) { fstate = 2; pc = cpos; pfw = true; plo = lo; phi = hi; }          // :70
                     else if (fstate == 1) { fstate = 2; pc = cpos; pfw = false; plo = lo; phi = hi; }    // :73
                     else {
-                        if (c.sequential(cpos, lo, hi, pc, plo, phi)) {                                   // Case 1
+                        // check_sequential of two TRUE k-mer intervals at adjacent windows is just
+                        // "q[cpos : cpos+K+1) occurs" (SURVEY A13): read it off the match list
+                        const bool seq = (c.seeds_are_true() && pc == cpos + 1) ? (F_of(c, cpos) >= cpos + K + 1)
+                                                                               : c.sequential(cpos, lo, hi, pc, plo, phi);
+                        if (seq) {                                                                        // Case 1
                             if (pfw) { Cand b; bext(c, pc, plo, phi, true, b); upd(cd, b.i, b.j, b.lo, b.hi); }
                             else {
                                 if (cd.valid && (pc - pstart) + K < (cd.j - cd.i)) continue;              // :94-95

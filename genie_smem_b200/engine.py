@@ -419,3 +419,133 @@ def gather_probe(buf: torch.Tensor, n_fetch, dependent):
     e1.record()
     torch.cuda.synchronize()
     return int(done.value), e0.elapsed_time(e1) * 1e-3
+
+
+# ---------------------------------------------------------------------------- pipelined end-to-end path
+class _ReadView:
+    """Reads [lo, hi) of a ReadBatch whose buffers are (being) copied to the device."""
+
+    def __init__(self, parent, lo, hi):
+        self.p, self.lo, self.hi = parent, lo, hi
+        self.n = hi - lo
+        self.max_len = parent.max_len
+        self.read_id_base = parent.read_id_base + lo
+
+    def cstruct(self):
+        r = capi.DevReads()
+        r.n_reads = self.n
+        r.packed = self.p.packed.data_ptr()
+        r.chunk_off = self.p.chunk_off.data_ptr() + 4 * self.lo
+        r.len = self.p.len.data_ptr() + 4 * self.lo
+        r.max_len, r.read_id_base = self.max_len, self.read_id_base
+        return r
+
+
+class PipelinedEngine:
+    """Host reads in, host records out, with the PCIe copies hidden behind the kernels: the batch
+    is cut into chunks that alternate between two workspaces on two CUDA streams, so chunk i+1's
+    H2D and chunk i-1's D2H overlap chunk i's sweep/select kernels.  Inputs must be pinned."""
+
+    def __init__(self, index: DeviceIndex, max_reads, max_len, n_chunks=8, mems_per_read=24, recs_per_read=16):
+        require_cuda()
+        self.index, self.device = index, index.device
+        self.n_chunks = max(2, int(n_chunks))
+        self.chunk_reads = (int(max_reads) + self.n_chunks - 1) // self.n_chunks
+        self.engines = [Engine(index, self.chunk_reads, max_len, mems_per_read, recs_per_read) for _ in range(2)]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        self.max_reads, self.max_len = int(max_reads), int(max_len)
+        self._dev = {}
+        self._pin = {}
+        self._cnt_pin = [torch.zeros(8, dtype=torch.int64).pin_memory() for _ in range(2)]
+        self.last_d2h_bytes = 0
+        self.kernel_launches = 0
+
+    def _buf(self, store, name, nbytes, pinned):
+        b = store.get(name)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device="cpu" if pinned else self.device)
+            if pinned:
+                b = b.pin_memory()
+            store[name] = b
+        return b
+
+    def run(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None):
+        n = reads.n
+        if n > self.max_reads or reads.max_len > self.max_len:
+            raise ValueError("batch exceeds the engine's workspace")
+        hp = torch.from_numpy(reads.packed_host)
+        hco = torch.from_numpy(reads.chunk_off_host.view(np.int32))
+        hln = torch.from_numpy(reads.len_host.view(np.int32))
+        reads.packed = self._buf(self._dev, "packed", hp.numel(), False)[: hp.numel()]
+        reads.chunk_off = self._buf(self._dev, "coff", hco.numel() * 4, False)[: hco.numel() * 4].view(torch.int32)
+        reads.len = self._buf(self._dev, "len", max(hln.numel(), 1) * 4, False)[: hln.numel() * 4].view(torch.int32)
+        co = reads.chunk_off_host
+        bounds = [min(n, i * self.chunk_reads) for i in range(self.n_chunks + 1)]
+        bounds = sorted(set(bounds))
+        est = self.engines[0].rec_cap * 16
+        out_rec = self._buf(self._pin, "rec", max(est, 1 << 20), True)
+        out_off = self._buf(self._pin, "off", (n + 1) * 8, True)
+        out_st = self._buf(self._pin, "st", max(n, 1), True)
+        main = torch.cuda.current_stream()
+        start_ev = torch.cuda.Event()
+        start_ev.record(main)
+        pending = []      # (engine idx, lo, hi, event)
+        rec_total = 0
+        mems_total = 0
+        chunk_rec = []
+
+        def drain(item):
+            nonlocal rec_total, mems_total, out_rec
+            e, lo, hi, ev = item
+            ev.synchronize()
+            c = self._cnt_pin[e].numpy()
+            if c[2] != 0:
+                raise capi.GsmError(capi.E_CAPACITY, f"workspace overflow in chunk [{lo},{hi}): mems {int(c[0])}, records {int(c[1])}; "
+                                                     "raise mems_per_read / recs_per_read")
+            n_rec = int(c[1])
+            mems_total += int(c[0])
+            if (rec_total + n_rec) * 16 > out_rec.numel():
+                grown = torch.empty(max((rec_total + n_rec) * 32, out_rec.numel() * 2), dtype=torch.uint8).pin_memory()
+                torch.cuda.synchronize()
+                grown[: rec_total * 16] = out_rec[: rec_total * 16]
+                out_rec = grown
+                self._pin["rec"] = grown
+            eng = self.engines[e]
+            with torch.cuda.stream(self.streams[e]):
+                out_rec[rec_total * 16:(rec_total + n_rec) * 16].copy_(eng.records[: n_rec * 16], non_blocking=True)
+                out_off[lo * 8:hi * 8].copy_(eng.rec_off[: hi - lo].view(torch.uint8), non_blocking=True)
+                out_st[lo:hi].copy_(eng.read_status[: hi - lo], non_blocking=True)
+            chunk_rec.append((lo, hi, rec_total, n_rec))
+            rec_total += n_rec
+
+        for i in range(len(bounds) - 1):
+            lo, hi = bounds[i], bounds[i + 1]
+            e = i % 2
+            if len(pending) == 2:                 # this workspace's previous chunk must be fully drained first
+                drain(pending.pop(0))
+            s = self.streams[e]
+            eng = self.engines[e]
+            with torch.cuda.stream(s):
+                s.wait_event(start_ev)
+                b0, b1 = int(co[lo]) * 16, int(co[hi]) * 16 + 16
+                reads.packed[b0:b1].copy_(hp[b0:b1], non_blocking=True)
+                reads.chunk_off[lo:hi + 1].copy_(hco[lo:hi + 1], non_blocking=True)
+                reads.len[lo:hi].copy_(hln[lo:hi], non_blocking=True)
+                eng.launch(method, _ReadView(reads, lo, hi), min_len, K, lut, rmi)
+                self._cnt_pin[e].copy_(eng.counters, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s)
+            pending.append((e, lo, hi, ev))
+        while pending:
+            drain(pending.pop(0))
+        for s in self.streams:
+            s.synchronize()
+        # chunk-local offsets -> global offsets (host, n+1 int64 adds)
+        offs = out_off.numpy()[: (n + 1) * 8].view(np.int64)
+        for lo, hi, base, n_rec in chunk_rec:
+            offs[lo:hi] += base
+        offs[n] = rec_total
+        self.kernel_launches = sum(e.kernel_launches for e in self.engines)
+        self.last_d2h_bytes = rec_total * 16 + (n + 1) * 8 + n + 64 * len(chunk_rec)
+        recs = out_rec.numpy()[: rec_total * 16].view(RECORD_DTYPE)
+        return SmemResult(recs, offs, out_st.numpy()[:n], mems_total)

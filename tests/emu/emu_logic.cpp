@@ -13,6 +13,8 @@ using namespace gsm;
 
 namespace {
 
+uint64_t g_cnt[8];   // [0] seed lookups [1] interval() calls [2] interval() FM steps [3] sequential() calls [4] reads
+
 struct HostIndex {
     const Half* fwd;
     const Half* rev;
@@ -69,11 +71,20 @@ struct SelCtx {
     MemEntry mem(uint32_t k) const { return mems[k]; }
     uint32_t base(uint32_t pos) const { return base_msb(words, pos); }
     bool failed() const { return raised; }
+    bool seeds_are_true() const { return method == GSM_METHOD_LUT_; }
 
     void interval(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt) {
+        g_cnt[1]++; g_cnt[2] += j - i;
         lo = 0; cnt = ix->meta.n_rows;
         auto load = [&](uint64_t idx) { return ix->fwd[idx]; };
-        for (uint32_t p = j; p > i; --p) {
+        uint32_t p = j;
+        if (method == GSM_METHOD_LUT_ && j - i >= K) {
+            auto rd = [&](uint64_t w) { return words[w]; };
+            uint64_t code = kmer_code(rd, j - K, K);
+            lo = lut[2 * code]; cnt = lut[2 * code + 1]; p = j - K;
+            if (cnt == 0) return;
+        }
+        for (; p > i; --p) {
             uint32_t c = base(p - 1);
             StepOut r = step_single(load, lo, lo + cnt, c, ix->meta.C[c], ix->meta.prim_f);
             lo = r.lo_new; cnt = r.cnt_new;
@@ -82,6 +93,7 @@ struct SelCtx {
     }
 
     bool seed(uint32_t c, int64_t& lo, int64_t& hi) {
+        g_cnt[0]++;
         auto rd = [&](uint64_t w) { return words[w]; };
         uint64_t code = kmer_code(rd, c, K);
         if (method == GSM_METHOD_LUT_) {
@@ -99,6 +111,7 @@ struct SelCtx {
     }
 
     bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi) {
+        g_cnt[3]++;
         if (method == GSM_METHOD_LUT_) {
             // closed form of check_sequential on two TRUE k-mer intervals
             for (uint32_t t = 1; t < K; ++t)
@@ -132,6 +145,8 @@ struct SelCtx {
 }  // namespace
 
 extern "C" {
+
+void emu_counters(uint64_t* out, int reset) { for (int i = 0; i < 8; ++i) { out[i] = g_cnt[i]; if (reset) g_cnt[i] = 0; } }
 
 struct EmuIndex {
     const void* fwd; const void* rev; const uint32_t* sa; const uint32_t* text;

@@ -241,3 +241,31 @@ def test_properties_at_scale(gs):
         for r in res.for_read(i):
             d[q[int(r["qstart"]):int(r["qend"])]] = (int(r["sa_lo"]), int(r["sa_hi"]))
         assert d == o.get_SMEMS(q, 1)
+
+
+def test_pipelined_engine_equals_engine(gs):
+    """The overlapped end-to-end path returns exactly the records of the plain one, ragged lengths included."""
+    rng = np.random.default_rng(9)
+    ref = rng.integers(0, 4, 300_000, dtype=np.uint8)
+    text = np.frombuffer(b"ACGT", np.uint8)[ref].tobytes().decode()
+    m = gs.ExactMatch.from_text(text)
+    reads = []
+    for _ in range(5003):
+        L = int(rng.integers(12, 152))
+        p = int(rng.integers(0, len(text) - L))
+        q = list(text[p:p + L])
+        for k in np.nonzero(rng.random(L) < 0.02)[0]:
+            q[k] = "ACGT"[int(rng.integers(0, 4))]
+        reads.append("".join(q))
+    batch = gs.ReadBatch.from_strings(reads, pin=True)
+    idx = m.device_index
+    lut = gs.lut_build(idx, 8)
+    plain = gs.Engine(idx, len(reads), 160, mems_per_read=48, recs_per_read=48)
+    pipe = gs.PipelinedEngine(idx, len(reads), 160, n_chunks=5, mems_per_read=48, recs_per_read=48)
+    for method, kw in ((gs.METHOD_BWA, {"min_len": 1}), (gs.METHOD_LUT, {"K": 8, "lut": lut})):
+        a = plain.run(method, batch, **kw)
+        ra, oa, sa = a.records.copy(), a.offsets.copy(), a.status.copy()
+        b = pipe.run(method, batch, **kw)
+        assert np.array_equal(oa, b.offsets)
+        assert np.array_equal(ra, b.records)
+        assert np.array_equal(sa, b.status)
