@@ -148,6 +148,24 @@ struct RmiTable {
         }
         if (!have_lower) lower = 0;
         if (!have_upper) upper = n_rows - 1;
+        // The two binary searches of RMI_LUT.py:183-184 start from the same bracket and take the same
+        // branch as long as the probed k-mer differs from q and no None row touches `lower`: walk that
+        // shared prefix once (same probes, same order), then finish each search on its own.
+        for (int depth = 0; depth < 400 && upper - lower > 1; ++depth) {
+            const int64_t sum = lower + upper;
+            int64_t mid = (sum >= 0) ? sum / 2 : -((-sum + 1) / 2);
+            uint64_t mc;
+            bool mok = ref_seq(mid, mc);
+            bool at_lower = false;
+            while (!mok && mid > lower && !raised) {
+                mid -= 1;
+                mok = ref_seq(mid, mc);
+                if (mid == lower) { at_lower = true; break; }
+            }
+            if (raised) return;
+            if (at_lower || !mok || mc == q) break;       // the searches part ways here
+            if (mc < q) lower = mid; else upper = mid;
+        }
         out_lo = binary_search(q, lower, upper, false);
         if (raised) return;
         out_hi = binary_search(q, lower, upper, true);

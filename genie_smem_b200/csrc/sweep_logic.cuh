@@ -147,30 +147,30 @@ struct Sweeper {
         return mode != M_DONE;
     }
 
+    // The walked candidate (cur_j, P0, cnt) cannot be extended beyond `start`.
+    GSM_HD void walk_end(Ctx& c, uint32_t start) {
+        if (start < last_start) emit_match(c, start, cur_j, P0, cnt);
+        if (first_walk && start != lb && ncand != 0) start_lock(c);
+        else end_sweep(c);
+    }
+
     GSM_HD void consume(Ctx& c, const IndexMeta& m, const StepOut& r) {
         (void)m;
-        if (mode == M_FWD) {
-            if (r.cnt_new != cnt) c.cand_put(ncand++, pos, k, cnt);
+        if (mode != M_LOCK) {
+            // FWD (append q[pos] to q[x:pos)) and WALK (prepend q[pos] to q[pos+1:cur_j)) share one hot path:
+            // take the new interval, move one base, fetch it.  Only the ends of an extension branch.
+            const bool fwd = mode == M_FWD;
+            if (fwd && r.cnt_new != cnt) c.cand_put(ncand++, pos, k, cnt);     // count about to change: q[x:pos) is a candidate
             if (r.cnt_new != 0) {
-                k += r.lt_add; P0 = r.lo_new; cnt = r.cnt_new; pos++;
-                if (pos < L) { ch = c.base(pos); return; }
-                c.cand_put(ncand++, pos, k, cnt);
+                k += r.lt_add; P0 = r.lo_new; cnt = r.cnt_new;
+                const uint32_t last = fwd ? L - 1u : 0u;
+                if (pos != last) { pos += fwd ? 1u : 0xFFFFFFFFu; ch = c.base(pos); return; }
+                if (fwd) { pos++; c.cand_put(ncand++, pos, k, cnt); start_bwd(c); return; }    // ran off the right end
+                walk_end(c, 0u);                                                               // ran off the left end
+                return;
             }
-            start_bwd(c);
-            return;
-        }
-        if (mode == M_WALK) {
-            uint32_t start;
-            if (r.cnt_new != 0) {
-                P0 = r.lo_new; cnt = r.cnt_new;
-                if (pos != 0) { pos--; ch = c.base(pos); return; }
-                start = 0;
-            } else {
-                start = pos + 1;
-            }
-            if (start < last_start) emit_match(c, start, cur_j, P0, cnt);
-            if (first_walk && start != lb && ncand != 0) start_lock(c);
-            else end_sweep(c);
+            if (fwd) start_bwd(c);
+            else walk_end(c, pos + 1u);
             return;
         }
         // M_LOCK: candidate t-1 = (cur_j, P0, cnt) was extended with q[pos]

@@ -185,6 +185,10 @@ class ReadBatch:
             capi.check(capi.lib.gsm_pack_reads(joined, lens.ctypes.data, n, off.ctypes.data, packed.ctypes.data))
         except ValueError as e:
             raise BaseError(str(e)) from None
+        if pin and torch.cuda.is_available():          # offsets and lengths travel with every batch too
+            off_t = torch.from_numpy(off.view(np.int32)).pin_memory()
+            len_t = torch.from_numpy(np.ascontiguousarray(lens).view(np.int32)).pin_memory()
+            off, lens = off_t.numpy().view(np.uint32), len_t.numpy().view(np.uint32)
         return cls(packed, off, lens, int(lens.max()) if n else 0, read_id_base)
 
     def to(self, device, non_blocking=False):
