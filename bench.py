@@ -300,12 +300,21 @@ def main():
 
     # ---- multi-GPU: the one collective of the path -- gather of per-rank record counts to rank 0
     total_records = n_rec
+    gather = None
     if world > 1:
-        t = torch.tensor([n_rec], device=dev, dtype=torch.int64)
-        gl = [torch.zeros_like(t) for _ in range(world)] if rank == 0 else None
-        dist.gather(t, gl, dst=0)
+        from genie_smem_b200 import sharding
+        # the final gather of per-rank SMEM records to rank 0 over NCCL (device buffers, NVLink)
+        rec_dev = engine.records[: n_rec * 16]
+        cnt_dev = engine.rec_cnt[: args.reads].to(torch.int64)
+        barrier()
+        t0 = time.perf_counter()
+        g_recs, g_cnts = sharding.gather_records(rec_dev, cnt_dev, dst=0, device=dev)
+        torch.cuda.synchronize()
+        dtg = time.perf_counter() - t0
         if rank == 0:
-            total_records = int(sum(int(x.item()) for x in gl))
+            total_records = int(len(g_recs))
+            gather = {"ms": round(dtg * 1e3, 2), "bytes_received": int(len(g_recs)) * 16, "backend": "nccl",
+                      "note": "includes the device-to-host read of the gathered array on rank 0; outside the timed steps"}
 
     # ---- CPU baseline on the host cores, rank 0 at N=1 only
     cpu_baseline = None
@@ -326,7 +335,8 @@ def main():
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_bwa, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload,
                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(gpu_launches),
-               "clocks": clocks, "methods": methods, "records_total": total_records, "maximal_matches_per_read": round(n_mems / args.reads, 3)}
+               "clocks": clocks, "methods": methods, "records_total": total_records, "maximal_matches_per_read": round(n_mems / args.reads, 3),
+               "record_gather": gather}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
