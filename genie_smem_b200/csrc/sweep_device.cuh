@@ -16,8 +16,8 @@ namespace gsm {
 constexpr int SWEEP_THREADS = 128;
 constexpr int SWEEP_LPR = 2;                              // lanes per read
 constexpr int SWEEP_GROUPS = SWEEP_THREADS / SWEEP_LPR;   // reads in flight per block
-constexpr int SWEEP_CAP = 16;                             // candidates kept in shared memory per read
-constexpr int SWEEP_MIN_BLOCKS = 7;
+constexpr int SWEEP_CAP = 15;                             // candidates kept in shared memory per read
+constexpr int SWEEP_MIN_BLOCKS = 8;
 
 struct SweepArgs {
     const uint4* fwd;
@@ -95,6 +95,7 @@ struct DevSweepCtx {
         L = __ldg(a.len + rid);
         const uint32_t off = __ldg(a.chunk_off + rid);
         const uint32_t nch = (L + 63u) >> 6;
+        const uint32_t nwords = (L + 3u) >> 2;      // four bases per unpacked word
         const uint32_t* spread = reinterpret_cast<const uint32_t*>(g_sweep_smem);
         uint32_t* dst = reinterpret_cast<uint32_t*>(g_sweep_smem) + (bytes0 >> 2);
         __syncwarp(gmask);                       // both lanes are done with the previous read's bases
@@ -104,7 +105,8 @@ struct DevSweepCtx {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) dst[c * 16 + k * 4 + q] = spread[(w[k] >> (24 - 8 * q)) & 0xFFu];
+                for (int q = 0; q < 4; ++q)
+                    if (c * 16 + k * 4 + q < nwords) dst[c * 16 + k * 4 + q] = spread[(w[k] >> (24 - 8 * q)) & 0xFFu];
         }
         __syncwarp(gmask);
         return true;
@@ -140,8 +142,8 @@ struct DevSweepCtx {
     }
 };
 
-// whole 64-base chunks are unpacked, one byte per base
-__host__ __device__ inline uint32_t sweep_read_u4(uint32_t max_len) { return ((max_len + 63u) / 64u) * 4u; }
+// one byte per base, rounded up to 16 bytes
+__host__ __device__ inline uint32_t sweep_read_u4(uint32_t max_len) { return (max_len + 15u) / 16u; }
 
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS) k_sweep(const SweepArgs a) {
     // spread table: byte of four 2-bit bases (MSB first) -> four bytes, first base at the lowest address
