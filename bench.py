@@ -31,7 +31,7 @@ READ_LEN = 151
 SUB_RATE = 0.01
 LUT_K = 12
 RMI_K = 15
-RMI_EXPERTS = (256, 16384)
+RMI_EXPERTS = (512, 131072)      # ~1 leaf per 760 keys, the reference's [10,100] ratio on its 100 kb text
 _B = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
@@ -201,6 +201,7 @@ def main():
     if not args.skip_rmi:
         t0 = time.time()
         rmi = train_rmi(host, ref, RMI_K, RMI_EXPERTS, dev)
+        rmi.build_probe_table(index)      # 16-byte {SA, 32-mer} probe records: one fetch per last-mile probe
         log(f"[rank {rank}] RMI trained in {time.time()-t0:.1f}s")
     torch.cuda.synchronize()
     log(f"[rank {rank}] setup {time.time()-t_setup:.1f}s, index {index.bytes()/1e6:.0f} MB on device")

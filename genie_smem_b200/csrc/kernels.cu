@@ -44,6 +44,7 @@ struct SelectArgs {
     uint64_t n_bases;
     const uint32_t* sa;
     const uint32_t* text;
+    const uint4* probe;         // optional {sa, 32-mer code} records (gsm_rmi_probe_build), else NULL
     const uint32_t* reads;      // as words
     const uint32_t* chunk_off;
     const uint32_t* len;
@@ -64,6 +65,16 @@ struct SelectArgs {
     uint32_t* rec_cnt;
     uint8_t* read_status;
     unsigned long long* counters;
+};
+
+// 16-byte probe record {s, code64 hi, code64 lo, 0}: one fetch per get_ref_seq (RMI_LUT.py:89-92)
+struct TableProbe {
+    const uint4* t;
+    __device__ __forceinline__ void operator()(uint64_t row, int64_t& s, uint64_t& code64) const {
+        const uint4 v = __ldg(t + row);
+        s = (int64_t)v.x;
+        code64 = ((uint64_t)v.y << 32) | (uint64_t)v.z;
+    }
 };
 
 template <int METHOD>
@@ -112,14 +123,24 @@ struct DevSelCtx {
             lo = e.x; hi = (int64_t)e.x + e.y - 1;
             return e.y != 0;
         }
-        const uint32_t* sa = a.sa;
-        const uint32_t* tx = a.text;
-        auto sal = [sa](uint64_t r) { return __ldg(sa + r); };
-        auto txl = [tx](uint64_t i) { return __ldg(tx + i); };
-        RmiTable<decltype(sal), decltype(txl)> t{sal, txl, (int64_t)a.meta.n_rows, (int64_t)a.n_bases, K, false};
         double pred;
-        t.lookup(a.rmi, code, pred, lo, hi);
-        if (t.raised) { raised = true; return false; }
+        bool r;
+        if (a.probe) {                                       // one 16-byte fetch per probe
+            TableProbe pr{a.probe};
+            RmiTable<TableProbe> t{pr, (int64_t)a.meta.n_rows, (int64_t)a.n_bases, K, false};
+            t.lookup(a.rmi, code, pred, lo, hi);
+            r = t.raised;
+        } else {                                             // suffix array, then packed text
+            const uint32_t* sa = a.sa;
+            const uint32_t* tx = a.text;
+            auto sal = [sa](uint64_t x) { return __ldg(sa + x); };
+            auto txl = [tx](uint64_t i) { return __ldg(tx + i); };
+            SaTextProbe<decltype(sal), decltype(txl)> pr{sal, txl};
+            RmiTable<decltype(pr)> t{pr, (int64_t)a.meta.n_rows, (int64_t)a.n_bases, K, false};
+            t.lookup(a.rmi, code, pred, lo, hi);
+            r = t.raised;
+        }
+        if (r) { raised = true; return false; }
         return hi >= lo;
     }
 
@@ -346,11 +367,22 @@ __global__ void k_rmi_lookup(const uint32_t* sa, const uint32_t* text, uint64_t 
     if (i >= n) return;
     auto sal = [sa](uint64_t r) { return __ldg(sa + r); };
     auto txl = [text](uint64_t w) { return __ldg(text + w); };
-    RmiTable<decltype(sal), decltype(txl)> t{sal, txl, (int64_t)n_rows, (int64_t)n_bases, m.K, false};
+    SaTextProbe<decltype(sal), decltype(txl)> pr{sal, txl};
+    RmiTable<decltype(pr)> t{pr, (int64_t)n_rows, (int64_t)n_bases, m.K, false};
     double p; int64_t l, h;
     t.lookup(m, codes[i], p, l, h);
     pred[i] = p; lo[i] = l; hi[i] = h;
     status[i] = t.raised ? GSM_READ_REF_RAISES : GSM_READ_OK;
+}
+
+// {suffix_array[row], code of the 32 bases at that suffix}: makes RMI_LUT.get_ref_seq one 16-byte fetch.
+__global__ void k_rmi_probe_build(const uint32_t* sa, const uint32_t* text, uint64_t n_rows, uint4* out) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint32_t s = __ldg(sa + row);
+    auto txl = [text](uint64_t w) { return __ldg(text + w); };
+    const uint64_t code = kmer_code(txl, (uint64_t)(s - 1), 32);
+    out[row] = make_uint4(s, (uint32_t)(code >> 32), (uint32_t)code, 0u);
 }
 
 // Random aligned 64-byte gather with the rank kernels' access shape (lane pair = 2 x 32 B).
@@ -495,6 +527,15 @@ static int fill_rmi(const gsm_dev_rmi* rmi, RmiModel* m) {
     return GSM_OK;
 }
 
+int gsm_rmi_probe_build(const gsm_dev_index* ix, void* probe, void* stream) {
+    if (!ix || !ix->sa || !ix->text2bit || !probe) return fail(GSM_E_INVALID, "gsm_rmi_probe_build needs sa + text on the device");
+    int st = device_ready();
+    if (st) return st;
+    k_rmi_probe_build<<<(unsigned)((ix->n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ix->sa, ix->text2bit, ix->n_rows, (uint4*)probe);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
 int gsm_rmi_lookup_batch(const gsm_dev_index* ix, const gsm_dev_rmi* rmi, uint64_t n, const uint64_t* codes, double* pred,
                          int64_t* lo, int64_t* hi, uint8_t* status, void* stream) {
     if (!ix || !ix->sa || !ix->text2bit || !codes || !pred || !lo || !hi || !status) return fail(GSM_E_INVALID, "gsm_rmi_lookup_batch: null argument (needs sa + text on the device)");
@@ -564,7 +605,7 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
         return GSM_OK;
     }
     SelectArgs se;
-    se.fwd = (const uint4*)ix->fwd_buckets; se.meta = make_meta(ix); se.n_bases = ix->n_rows - 1; se.sa = ix->sa; se.text = ix->text2bit;
+    se.fwd = (const uint4*)ix->fwd_buckets; se.meta = make_meta(ix); se.n_bases = ix->n_rows - 1; se.sa = ix->sa; se.text = ix->text2bit; se.probe = (method == GSM_METHOD_RMI && rmi) ? (const uint4*)rmi->probe : nullptr;
     se.reads = (const uint32_t*)rd->packed; se.chunk_off = rd->chunk_off; se.len = rd->len; se.n_reads = (uint32_t)rd->n_reads;
     se.max_len = rd->max_len; se.read_id_base = rd->read_id_base; se.min_len = min_len; se.K = K; se.lut = (const uint2*)lut; se.rmi = rm;
     se.mem_pool = (uint4*)ws->mem_pool; se.mem_off = ws->mem_off; se.mem_cnt = ws->mem_cnt; se.stage = (uint4*)ws->quad_scratch;

@@ -54,11 +54,23 @@ GSM_HD double rmi_predict(const RmiModel& m, uint64_t code) {
     return p;
 }
 
-// Table access for the last-mile search.  SaLoad(row) -> 1-based position; TextLoad(word) -> u32.
+// Table access for the last-mile search.  Probe(row, s, code64): s = suffix_array[row] (1-based) and
+// code64 = the MSB-first code of the 32 bases at text position s-1 (zero-padded past the end), either
+// from the suffix array + packed text (two dependent fetches) or from a precomputed 16-byte probe
+// record {s, code64} (one fetch, gsm_rmi_probe_build).
 template <typename SaLoad, typename TextLoad>
-struct RmiTable {
+struct SaTextProbe {
     SaLoad sa;
     TextLoad text;
+    GSM_HD void operator()(uint64_t row, int64_t& s, uint64_t& code64) const {
+        s = (int64_t)sa(row);
+        code64 = kmer_code(text, (uint64_t)(s - 1), 32);
+    }
+};
+
+template <typename Probe>
+struct RmiTable {
+    Probe probe;
     int64_t n_rows;     // len(suffix_array)
     int64_t n_bases;    // ref_seq_size
     uint32_t K;
@@ -70,9 +82,11 @@ struct RmiTable {
         code = 0;
         if (ind < -n_rows || ind >= n_rows) { raised = true; return false; }
         if (ind < 0) ind += n_rows;
-        const int64_t s = (int64_t)sa((uint64_t)ind);
+        int64_t s;
+        uint64_t code64;
+        probe((uint64_t)ind, s, code64);
         if (s - 1 + (int64_t)K > n_bases) return false;
-        code = kmer_code(text, (uint64_t)(s - 1), K);
+        code = code64 >> (64u - 2u * K);
         return true;
     }
 

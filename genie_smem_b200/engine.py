@@ -223,7 +223,16 @@ class RmiParams:
         s.K, s.n_levels = self.K, len(self.level_sizes)
         s.level_sizes = self.level_sizes.ctypes.data_as(capi.u32p)
         s.coef, s.intercept = self.coef.data_ptr(), self.intercept.data_ptr()
+        s.probe = None
         self.c = s
+        self.probe = None
+
+    def build_probe_table(self, index):
+        """16-byte {SA value, 32-mer code} record per row: one fetch per last-mile probe (n_rows x 16 B of HBM)."""
+        self.probe = torch.empty(index.n_rows * 16, dtype=torch.uint8, device=index.device)
+        capi.check(capi.lib.gsm_rmi_probe_build(C.byref(index.c), _ptr(self.probe), _stream()))
+        self.c.probe = self.probe.data_ptr()
+        return self
 
 
 class SmemResult:

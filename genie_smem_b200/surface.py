@@ -386,7 +386,7 @@ class RMI_LUT:
     def params(self):
         if self._params is None:
             self._params = eng.RmiParams(self.prediction_size, self.rmi.level_sizes, self.rmi.coef, self.rmi.intercept,
-                                         self.matcher.device_index.device)
+                                         self.matcher.device_index.device).build_probe_table(self.matcher.device_index)
         return self._params
 
     def _encode(self, query, encoded):

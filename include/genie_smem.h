@@ -143,6 +143,7 @@ typedef struct {
     const uint32_t* level_sizes; /* HOST pointer, n_levels entries */
     const double* coef;          /* device */
     const double* intercept;     /* device */
+    const void* probe;           /* device, optional: n_rows x 16 B from gsm_rmi_probe_build, else NULL */
 } gsm_dev_rmi;
 
 /* Scratch + output buffers for one SMEM batch; all device memory, all caller-allocated.
@@ -214,6 +215,11 @@ int gsm_smem_select(int method, const gsm_dev_index* idx, const gsm_dev_reads* r
 
 int gsm_smem_collect(const gsm_dev_reads* reads, gsm_workspace* ws, gsm_record* out, uint64_t out_cap,
                      void* stream);
+
+/* Optional accelerator for the RMI last-mile search: probe[row] = {suffix_array[row], code of the 32
+ * bases at that suffix} (16 bytes), so RMI_LUT.get_ref_seq (RMI_LUT.py:89-92) is ONE fetch instead of
+ * a suffix-array read followed by a text read.  probe: n_rows * 16 bytes of device memory. */
+int gsm_rmi_probe_build(const gsm_dev_index* idx, void* probe, void* stream);
 
 /* RMI_LUT.get_suffix_rmi (RMI_LUT.py:67-78) for a batch of K-mer codes: predict + exponential
  * + binary last-mile search.  pred receives the float64 prediction, lo/hi the returned pair

@@ -103,7 +103,8 @@ struct SelCtx {
         }
         auto sa = [&](uint64_t r) { return ix->sa[r]; };
         auto tx = [&](uint64_t w) { return ix->text[w]; };
-        RmiTable<decltype(sa), decltype(tx)> t{sa, tx, (int64_t)ix->meta.n_rows, (int64_t)ix->n_bases, K, false};
+        SaTextProbe<decltype(sa), decltype(tx)> pr{sa, tx};
+        RmiTable<decltype(pr)> t{pr, (int64_t)ix->meta.n_rows, (int64_t)ix->n_bases, K, false};
         double pred;
         t.lookup(rmi, code, pred, lo, hi);
         if (t.raised) { raised = true; return false; }
@@ -244,7 +245,8 @@ int emu_rmi_lookup(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint
     for (uint32_t l = 0; l < n_levels; ++l) { m.level_size[l] = level_sizes[l]; m.level_off[l] = off; off += level_sizes[l]; }
     auto sa = [&](uint64_t r) { return ei->sa[r]; };
     auto tx = [&](uint64_t w) { return ei->text[w]; };
-    RmiTable<decltype(sa), decltype(tx)> t{sa, tx, (int64_t)ei->n_rows, (int64_t)ei->n_bases, K, false};
+    SaTextProbe<decltype(sa), decltype(tx)> pr{sa, tx};
+    RmiTable<decltype(pr)> t{pr, (int64_t)ei->n_rows, (int64_t)ei->n_bases, K, false};
     t.lookup(m, code, *pred, *lo, *hi);
     return t.raised ? -1 : 0;
 }

@@ -269,3 +269,22 @@ def test_pipelined_engine_equals_engine(gs):
         assert np.array_equal(oa, b.offsets)
         assert np.array_equal(ra, b.records)
         assert np.array_equal(sa, b.status)
+
+
+def test_rmi_probe_table_changes_nothing(gs, matchers):
+    """The 16-byte probe records are a layout optimisation: records with and without them are identical."""
+    g = gu.load_json("smems_c2_big_mixed101.json.gz")
+    _, m = matchers["big_data"]
+    p = gu.load_rmi("big_data_k15")
+    idx = m.device_index
+    reads = g["reads"][:600]
+    batch = gs.ReadBatch.from_strings(reads)
+    e = gs.Engine(idx, len(reads), 160, mems_per_read=64, recs_per_read=64)
+    plain = gs.RmiParams(p["K"], p["level_sizes"], p["coef"], p["intercept"])
+    a = e.run(gs.METHOD_RMI, batch, rmi=plain)
+    ra, oa = a.records.copy(), a.offsets.copy()
+    fast = gs.RmiParams(p["K"], p["level_sizes"], p["coef"], p["intercept"]).build_probe_table(idx)
+    b = e.run(gs.METHOD_RMI, batch, rmi=fast)
+    assert np.array_equal(oa, b.offsets) and np.array_equal(ra, b.records)
+    got = _dicts(reads, b)
+    assert got == g["rmi"]["big_data_k15"][:600]
