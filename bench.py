@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--ref-bases", type=int, default=100_000_000)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget per method")
     ap.add_argument("--skip-rmi", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the pipelined end-to-end path")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -285,7 +286,7 @@ def main():
         engine.check_overflow()
 
     # ---- end to end through the public API: pinned host reads in, host records out
-    pipe = g.PipelinedEngine(index, args.reads, READ_LEN, n_chunks=8, mems_per_read=24, recs_per_read=8)
+    pipe = g.PipelinedEngine(index, args.reads, READ_LEN, n_chunks=args.e2e_chunks, mems_per_read=24, recs_per_read=8)
 
     def e2e_step():
         return pipe.run(g.METHOD_BWA, batch, min_len=1)      # pinned host reads in, host records out
@@ -304,7 +305,7 @@ def main():
         dt = float(t.item())
     e2e = {"value": world * args.reads * args.steps / dt, "unit": "reads/s", "h2d_bytes_per_step": batch.h2d_bytes(),
            "d2h_bytes_per_step": pipe.last_d2h_bytes, "method": "bwa", "records_last_step": int(len(res.records)),
-           "api": "PipelinedEngine.run (8 chunks, 2 streams: H2D / kernels / D2H overlapped)"}
+           "api": f"PipelinedEngine.run ({args.e2e_chunks} chunks, 2 streams: H2D / kernels / D2H overlapped)"}
 
     # ---- multi-GPU: the one collective of the path -- gather of per-rank record counts to rank 0
     total_records = n_rec
@@ -354,7 +355,7 @@ def train_rmi(host, ref_codes, K, experts, dev):
     """Host-side RMI training on the k-mer -> row keys of this index (reference RMI_LUT.py:36-50);
     every `stride`-th key to keep setup short -- model quality only changes the last-mile length."""
     import genie_smem_b200 as g
-    sa1, _ = host.export()
+    sa1 = host.export()[0] if hasattr(host, "export") else np.asarray(host)     # a HostIndex, or the 1-based suffix array itself
     n_bases = len(ref_codes)
     stride = max(1, len(sa1) // 4_000_000)
     rows = np.arange(0, len(sa1), stride, dtype=np.int64)

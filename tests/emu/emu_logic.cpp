@@ -169,6 +169,8 @@ int emu_sweep(const EmuIndex* ei, const uint32_t* words, uint32_t L, uint32_t* o
         const Half* bk = rev ? ix.rev : ix.fwd;
         auto load = [&](uint64_t idx) { return bk[idx]; };
         StepOut r = step_single(load, sw.P0, sw.P0 + sw.cnt, sw.ch, ix.meta.C[sw.ch], rev ? ix.meta.prim_r : ix.meta.prim_f);
+        g_cnt[4 + (sw.mode == M_FWD ? 0 : sw.mode == M_WALK ? 1 : 2)]++;      // [4] FWD [5] WALK [6] LOCK steps
+        { uint32_t b0, r0, b1, r1; split192(sw.P0, b0, r0); split192(sw.P0 + sw.cnt, b1, r1); g_cnt[7] += (b0 != b1); }   // [7] steps touching two buckets
         sw.consume(ctx, ix.meta, r);
         ++steps;
     }

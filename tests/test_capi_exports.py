@@ -70,6 +70,22 @@ def test_host_builder_on_repetitive_and_tiny_texts():
         assert bwt.decode() == o.bwt
 
 
+def test_packed_index_round_trip(tmp_path):
+    """The binary on-disk index (replacement of <ref>-FM.json) reloads to identical device layouts."""
+    import genie_smem_b200 as g
+    gi = gu.load_index("medium_data")
+    h = g.HostIndex.build(gi["text"])
+    p = g.PackedIndex.from_host(h)
+    p.save(str(tmp_path / "idx"))
+    for mmap in (False, True):
+        q = g.PackedIndex.load(str(tmp_path / "idx"), mmap=mmap)
+        for name in ("fwd", "rev", "sa", "text"):
+            assert np.array_equal(getattr(p, name), getattr(q, name))
+        assert [int(x) for x in q.info.C] == [int(x) for x in h.info.C]
+        assert (q.info.n_rows, q.info.primary_fwd, q.info.primary_rev) == (h.info.n_rows, h.info.primary_fwd, h.info.primary_rev)
+    assert np.array_equal(p.sa, gi["suffix_array"])
+
+
 def test_non_acgt_is_rejected():
     import genie_smem_b200 as g
     with pytest.raises(KeyError):
