@@ -247,7 +247,7 @@ class ReadBatch:
             off_t = torch.from_numpy(off.view(np.int32)).pin_memory()
             len_t = torch.from_numpy(np.ascontiguousarray(lens).view(np.int32)).pin_memory()
             off, lens = off_t.numpy().view(np.uint32), len_t.numpy().view(np.uint32)
-        return cls(packed, off, lens, int(lens.max()) if n else 0, read_id_base)
+        return cls(packed, off, lens, max(1, int(lens.max())) if n else 1, read_id_base)
 
     def to(self, device, non_blocking=False):
         self.packed = torch.from_numpy(self.packed_host).to(device, non_blocking=non_blocking)

@@ -436,6 +436,8 @@ class SMEM:
         queries = list(queries)
         for q in queries:
             _check_bases(q)
+        if not queries:
+            return eng.SmemResult(np.zeros(0, eng.RECORD_DTYPE), np.zeros(1, np.int64), np.zeros(0, np.uint8), 0)
         idx = self.matcher.device_index
         if not idx.all_bases_present:
             raise ValueError("the reference text must contain all of A, C, G, T (SURVEY 8c parity domain)")

@@ -288,3 +288,51 @@ def test_rmi_probe_table_changes_nothing(gs, matchers):
     assert np.array_equal(oa, b.offsets) and np.array_equal(ra, b.records)
     got = _dicts(reads, b)
     assert got == g["rmi"]["big_data_k15"][:600]
+
+
+def _oracle_dicts(text, sa, method, reads, **kw):
+    from oracle.c_oracle import COracle
+    return COracle(text, sa).smem_dicts(method, reads, **kw)
+
+
+def test_long_reads_and_edge_lengths_vs_oracle(gs, matchers):
+    """Reference-style long queries (SMEM.py:517 uses 2,000 bp), length-1 reads, reads shorter than K."""
+    gidx, m = matchers["big_data"]
+    text = gidx["text"]
+    rng = random.Random(21)
+    reads = []
+    for L in (1, 2, 5, 11, 12, 13, 64, 65, 255, 256, 257, 700, 1500, 2000):
+        p = rng.randrange(0, len(text) - L)
+        q = list(text[p:p + L])
+        for k in range(L):
+            if rng.random() < 0.03:
+                q[k] = rng.choice("ACGT")
+        reads.append("".join(q))
+    reads += [gs.create_query_from_ref(text, 2000), gs.create_random_query(300)]
+    s = gs.SMEM(m)
+    s.lut.generate_lut(12)
+    exp = _oracle_dicts(text, gidx["suffix_array"], 0, reads, min_len=1)
+    assert _dicts(reads, s.get_SMEMS_batch(reads, 1)) == exp
+    res = s.get_smems_lut_batch(reads)
+    exp = _oracle_dicts(text, gidx["suffix_array"], 1, reads, K=12)
+    got = _dicts(reads, res)
+    for k, q in enumerate(reads):
+        if len(q) < 12:
+            assert res.status[k] == gs.READ_TOO_SHORT and exp[k] == "short"
+        else:
+            assert got[k] == exp[k], len(q)
+    # an empty batch is legal
+    empty = s.get_SMEMS_batch([], 1)
+    assert len(empty.records) == 0 and list(empty.offsets) == [0]
+
+
+def test_low_complexity_reads_spill_the_candidate_cache(gs):
+    """More occurrence-count changes in one forward extension than shared-memory candidate slots."""
+    text = "A" * 300 + "C" + "A" * 120 + "G" + "ACGT" * 5 + "T" * 80 + "GATTACA" * 20
+    m = gs.ExactMatch.from_text(text)
+    sa, _ = m._host.export()
+    reads = ["A" * 151, "A" * 100 + "C" + "A" * 50, "T" * 70 + "A" * 81, "A" * 40 + "G" + "ACGT" * 3 + "T" * 60, "GATTACA" * 15 + "A" * 40]
+    s = gs.SMEM(m)
+    assert _dicts(reads, s.get_SMEMS_batch(reads, 1)) == _oracle_dicts(text, sa, 0, reads, min_len=1)
+    s.lut.generate_lut(4)
+    assert _dicts(reads, s.get_smems_lut_batch(reads)) == _oracle_dicts(text, sa, 1, reads, K=4)
