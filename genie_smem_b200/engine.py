@@ -187,18 +187,86 @@ class DeviceIndex:
         self.rev = _to_dev(rev, self.device)
         self.sa = _to_dev(sa, self.device)
         self.text = _to_dev(text, self.device)
+        self.build_stats = None
+        self._bind()
+
+    def _bind(self):
+        info = self.info
         d = capi.DevIndex()
-        d.n_rows, d.n_buckets = host.info.n_rows, host.info.n_buckets
+        d.n_rows, d.n_buckets = info.n_rows, info.n_buckets
         d.fwd_buckets, d.rev_buckets = self.fwd.data_ptr(), (self.rev.data_ptr() if self.rev is not None else None)
         d.sa = self.sa.data_ptr() if self.sa is not None else None
         d.text2bit = self.text.data_ptr() if self.text is not None else None
         for c in range(5):
-            d.C[c] = host.info.C[c]
-        d.primary_fwd, d.primary_rev = host.info.primary_fwd, host.info.primary_rev
+            d.C[c] = info.C[c]
+        d.primary_fwd, d.primary_rev = info.primary_fwd, info.primary_rev
         self.c = d
-        self.n_rows = int(host.info.n_rows)
-        self.n_bases = int(host.info.n_bases)
-        self.all_bases_present = all(int(host.info.count[c]) > 0 for c in range(4))
+        self.n_rows = int(info.n_rows)
+        self.n_bases = int(info.n_bases)
+        self.all_bases_present = all(int(info.count[c]) > 0 for c in range(4))
+
+    @classmethod
+    def build_on_device(cls, text, device="cuda", reverse=True):
+        """Construct the whole index ON THE GPU (gsm_index_build_device: radix sort of 32-mer keys + prefix
+        doubling, BWT planes, checkpoints) -- the large-reference replacement of ExactMatch.create_fm_index
+        (reference SMEM/ExactMatch.py:22-33).  text: str / bytes of ACGT, or a uint8 array of codes 0..3
+        (numpy or torch).  Arrays are bit-identical to HostIndex.build's."""
+        require_cuda()
+        self = cls.__new__(cls)
+        self.device = dev = torch.device(device)
+        if isinstance(text, str):
+            text = text.encode()
+        if isinstance(text, (bytes, bytearray)):
+            src, ascii_ = torch.frombuffer(bytearray(text), dtype=torch.uint8), 1
+        elif isinstance(text, np.ndarray):
+            src, ascii_ = torch.from_numpy(np.ascontiguousarray(text, np.uint8)), 0
+        else:
+            src, ascii_ = text.contiguous(), 0
+        n_bases = int(src.numel())
+        if n_bases == 0:
+            raise ValueError("empty reference")
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        with torch.cuda.device(dev):
+            src = src.to(dev)
+            words = (n_bases + 15) // 16 + 2
+            self.text = torch.zeros(words + 2, dtype=torch.int32, device=dev)
+            scratch = torch.zeros(1, dtype=torch.int64, device=dev)
+            e0.record()
+            try:
+                capi.check(capi.lib.gsm_text_pack_device(_ptr(src), n_bases, ascii_, _ptr(self.text), _ptr(scratch), _stream()))
+            except ValueError as e:
+                raise BaseError(str(e)) from None
+            del src
+            n_rows = n_bases + 1
+            nb = n_rows // 192 + 1
+            flags = 1 if reverse else 0
+            need = C.c_uint64()
+            capi.check(capi.lib.gsm_index_build_device_workspace(n_bases, flags, C.byref(need)))
+            self.sa = torch.empty(n_rows, dtype=torch.int32, device=dev)
+            self.fwd = torch.empty(nb * 16, dtype=torch.int32, device=dev)
+            self.rev = torch.empty(nb * 16, dtype=torch.int32, device=dev) if reverse else None
+            ws = torch.empty(int(need.value), dtype=torch.uint8, device=dev)
+            self.info = capi.IndexInfo()
+            e1.record()
+            capi.check(capi.lib.gsm_index_build_device(_ptr(self.text), n_bases, flags, _ptr(self.sa), _ptr(self.fwd), _ptr(self.rev),
+                                                       _ptr(ws), int(need.value), C.byref(self.info), _stream()))
+            e2.record()
+            torch.cuda.synchronize(dev)
+            del ws
+            torch.cuda.empty_cache()
+        self.build_stats = {"pack_ms": e0.elapsed_time(e1), "build_ms": e1.elapsed_time(e2), "workspace_bytes": int(need.value),
+                            "doubling_rounds": int(self.info.reserved)}
+        self.info.reserved = 0
+        self._bind()
+        return self
+
+    def suffix_array_host(self):
+        """fm_index["suffix_array"] (1-based values, ExactMatch.py:66) copied back from the device."""
+        return self.sa.cpu().numpy().view(np.uint32)
+
+    def count_dic(self):
+        i = self.info
+        return {"": int(i.n_rows), "$": 0, "A": int(i.C[0]), "C": int(i.C[1]), "G": int(i.C[2]), "T": int(i.C[3])}
 
     def bytes(self):
         return sum(t.numel() * t.element_size() for t in (self.fwd, self.rev, self.sa, self.text) if t is not None)

@@ -103,6 +103,26 @@ void gsm_index_free(gsm_index* idx);
 int gsm_pack_reads(const char* bases, const uint32_t* lens, uint64_t n_reads, uint32_t* chunk_off,
                    void* packed);
 
+/* ------------------------------------------------------------------ device-side index build */
+/* The same index as gsm_index_build, constructed ON THE GPU (radix sort of 32-mer keys + prefix doubling
+ * over the rows that are still tied; BWT planes by ballot; checkpoints by scan) -- seconds at 10^9 bases.
+ * Replaces ExactMatch.create_fm_index (ExactMatch.py:22-33, 52-101) for large references; bit-identical
+ * arrays to the host builder.  All pointers below are DEVICE memory owned by the caller.
+ *
+ * gsm_text_pack_device: bases (n_bases bytes: ASCII ACGT if ascii != 0, else codes 0..3) -> text2bit
+ *   ((n_bases+15)/16 + 2 words, MSB-first, pad words zeroed).  scratch8: 8 bytes of device scratch.
+ *   GSM_E_INVALID on a non-ACGT base (the reference raises KeyError, ExactMatch.py:139).
+ * gsm_index_build_device_workspace: bytes of scratch gsm_index_build_device needs (about 36 bytes per base).
+ * gsm_index_build_device: text2bit -> sa (n_rows uint32, 1-based values), fwd_buckets and (flags bit0)
+ *   rev_buckets (n_buckets * 64 bytes each); *info (HOST) receives sizes, count[], C[], primary rows;
+ *   info->reserved = prefix-doubling rounds used.  Synchronises the stream. */
+int gsm_text_pack_device(const void* bases, uint64_t n_bases, uint32_t ascii, uint32_t* text2bit, uint64_t* scratch8,
+                         void* stream);
+int gsm_index_build_device_workspace(uint64_t n_bases, uint32_t flags, uint64_t* bytes);
+int gsm_index_build_device(const uint32_t* text2bit, uint64_t n_bases, uint32_t flags, uint32_t* sa, void* fwd_buckets,
+                           void* rev_buckets, void* workspace, uint64_t workspace_bytes, gsm_index_info* info,
+                           void* stream);
+
 /* ------------------------------------------------------------------ device-side views */
 typedef struct {
     uint64_t n_rows;

@@ -1,0 +1,91 @@
+"""GPU index builder (gsm_index_build_device) against the host SA-IS builder, which is itself pinned to the
+reference's own index arrays (test_gpu_parity.py::test_index_builder_matches_reference_arrays, tests/golden).
+Bit-exact: suffix array, both bucket arrays, C, primary rows."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tests import golden_util as gu  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def gs():
+    import genie_smem_b200 as g
+    return g
+
+
+def _texts():
+    rng = np.random.default_rng(5)
+    rnd = lambda n: "".join("ACGT"[c] for c in rng.integers(0, 4, n))  # noqa: E731
+    unit = rnd(700)
+    out = {
+        "one_base": "G",
+        "two_bases": "AA",
+        "five": "ACGTA",
+        "poly_a_33": "A" * 33,
+        "poly_a": "A" * 5000,                              # every suffix ties on every key: log2(n/32) doubling rounds
+        "poly_t_then_a": "T" * 100 + "A" * 100,
+        "tandem": "ACGT" * 3000,
+        "tail_a_run": rnd(3000) + "A" * 70,                # short suffixes tie with genuine A-runs: the virtual ranks
+        "tail_equals_head": "C" + "A" * 40 + rnd(500) + "C" + "A" * 40,
+        "random_200k": rnd(200_000),
+        "repeats": unit * 5 + rnd(1000) + unit[:400] * 3 + "A" * 300 + unit,
+        "two_letter": "".join("AC"[c] for c in rng.integers(0, 2, 20000)),
+    }
+    return out
+
+
+@pytest.mark.parametrize("name", list(_texts().keys()))
+def test_device_build_equals_host_build(gs, name):
+    text = _texts()[name]
+    host = gs.HostIndex.build(text)
+    fwd, rev, sa, _ = host.pack(with_sa=True, with_text=False)
+    dev = gs.DeviceIndex.build_on_device(text)
+    assert np.array_equal(dev.sa.cpu().numpy().view(np.uint32), sa), "suffix array"
+    assert np.array_equal(dev.fwd.cpu().numpy().view(np.uint32), fwd), "forward buckets"
+    assert np.array_equal(dev.rev.cpu().numpy().view(np.uint32), rev), "reverse buckets"
+    for f in ("n_bases", "n_rows", "n_buckets", "bucket_bytes", "primary_fwd", "primary_rev", "has_reverse"):
+        assert int(getattr(dev.info, f)) == int(getattr(host.info, f)), f
+    assert list(dev.info.count) == list(host.info.count)
+    assert list(dev.info.C) == list(host.info.C)
+    _, _, _, text_host = host.pack(with_sa=False, with_text=True)
+    assert np.array_equal(dev.text.cpu().numpy().view(np.uint32)[: len(text_host)], text_host), "packed text"
+
+
+@pytest.mark.parametrize("name", ["small_data", "medium_data", "big_data"])
+def test_device_build_equals_reference_arrays(gs, name):
+    """The arrays the reference's own create_fm_index produced (frozen in tests/golden)."""
+    gidx = gu.load_index(name)
+    dev = gs.DeviceIndex.build_on_device(gidx["text"])
+    assert np.array_equal(dev.suffix_array_host(), gidx["suffix_array"])
+    assert dev.count_dic() == gu.meta()[name]["count_dic"]
+
+
+def test_device_build_from_codes_and_searches(gs):
+    """codes input (no ASCII round trip); the built index drives the search kernels like a host-built one."""
+    rng = np.random.default_rng(9)
+    codes = rng.integers(0, 4, 300_000, dtype=np.uint8)
+    text = "".join("ACGT"[c] for c in codes)
+    dev = gs.DeviceIndex.build_on_device(codes)
+    ref = gs.DeviceIndex(gs.HostIndex.build(text))
+    reads = []
+    for _ in range(2000):
+        p = int(rng.integers(0, len(text) - 151))
+        q = list(text[p:p + 151])
+        for k in np.nonzero(rng.random(151) < 0.02)[0]:
+            q[k] = "ACGT"[("ACGT".index(q[k]) + 1) % 4]
+        reads.append("".join(q))
+    out = []
+    for idx in (dev, ref):
+        e = gs.Engine(idx, len(reads), 151)
+        r = e.run(gs.METHOD_BWA, gs.ReadBatch.from_strings(reads), min_len=1)
+        out.append((r.records.copy(), r.offsets.copy()))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+def test_device_build_rejects_non_acgt(gs):
+    with pytest.raises(ValueError):
+        gs.DeviceIndex.build_on_device("ACGTNACGT")
+    with pytest.raises(KeyError):
+        gs.DeviceIndex.build_on_device("ACGTNACGT")
