@@ -1,18 +1,19 @@
 #!/usr/bin/env python3
 """bench.py -- SMEM reads/s on B200 (BASELINE.json metric) for the B200-native engine.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--ref-bases B] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c4|c3] [--reads R] [--ref-bases B] [--impl reference]
 
-Workload at N=1 = BASELINE.json configs[2]: synthetic 100 Mbp random ACGT reference
-(numpy PCG64(100)), 10 M reads of 151 bp (exact substrings with i.i.d. 1 % substitutions,
-SURVEY 8d), all three SMEM methods on one B200.  Under torchrun (N>1) every rank holds a replica
-of the index and its own 10 M-read shard (weak scaling); the only collective is the final gather
-of per-rank record counts (NCCL), as north_star prescribes.
+Workload at N=1 = BASELINE.json configs[3], the configuration the metric ("reads/s at 1/2/4/8 B200 + achieved HBM GB/s")
+is quoted on: synthetic 1 Gbp random ACGT reference (numpy PCG64(1000)), 50 M reads of 151 bp (exact substrings with
+i.i.d. 1 % substitutions), all three SMEM methods.  The index (suffix array, both BWT bucket arrays) is built
+ON THE GPU in well under a second (gsm_index_build_device), so the 1 Gbp configuration fits the default run; `--config c3`
+selects configs[2] (100 Mbp, 10 M reads; rank buckets L2-resident).  Under torchrun (N>1) every rank holds a replica of the
+index and its own read shard (weak scaling); the only collective is the final gather of per-rank records (NCCL).
 
-A "step" is one pass of the hot path over one read batch.  `value` = BWA-SMEM reads/s with the
-packed reads already resident in HBM (kernels only: sweep + select + scan + gather); `e2e` = the
-same through the public API with HOST buffers (pinned H2D of the packed reads, D2H of records and
-offsets inside the timed region).  LUT- and RMI-SMEM throughputs are reported under "methods".
+A "step" is one pass of the hot path over one read batch.  `value` = BWA-SMEM reads/s with the packed reads already
+resident in HBM (kernels only: sweep + select + scan + gather); `e2e` = the same through the public API starting from RAW
+read bytes in pinned host memory (1 byte/base H2D, 2-bit packing on the GPU, records + offsets D2H, all inside the timed
+region).  LUT- and RMI-SMEM throughputs are reported under "methods".
 """
 import argparse
 import json
@@ -31,7 +32,6 @@ READ_LEN = 151
 SUB_RATE = 0.01
 LUT_K = 12
 RMI_K = 15
-RMI_EXPERTS = (512, 131072)      # ~1 leaf per 760 keys, the reference's [10,100] ratio on its 100 kb text
 _B = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
@@ -144,35 +144,77 @@ def rmi_dict(params):
 
 
 # ------------------------------------------------------------------------------------------ main
-def main():
+CONFIGS = {"c4": dict(ref_bases=1_000_000_000, reads=50_000_000, seed=1000, experts=(2048, 1048576), name="BASELINE.json configs[3]"),
+           "c3": dict(ref_bases=100_000_000, reads=10_000_000, seed=100, experts=(512, 131072), name="BASELINE.json configs[2]")}
+HOST_READS = 600_000      # the first reads of every batch come from numpy so the CPU arms can regenerate exactly them
+
+
+def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
-    ap.add_argument("--ref-bases", type=int, default=100_000_000)
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (default: the config's)")
+    ap.add_argument("--ref-bases", type=int, default=0, help="reference size (default: the config's)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget per method")
     ap.add_argument("--skip-rmi", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the pipelined end-to-end path")
+    ap.add_argument("--seed-k", type=int, default=-1, help="K of the sweep kernel's seed table (-1 = auto, 0 = none)")
     args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.ref_bases:
+        cfg["ref_bases"] = args.ref_bases
+        cfg["name"] = "custom size"
+        if args.ref_bases < 500_000_000:
+            cfg["experts"] = CONFIGS["c3"]["experts"]
+    if args.reads:
+        cfg["reads"] = args.reads
+        if cfg["name"] != "custom size":
+            cfg["name"] += f" shape, {args.reads/1e6:g} M reads"
+    args.ref_bases, args.reads, args.seed, args.experts, args.cfg_name = cfg["ref_bases"], cfg["reads"], cfg["seed"], cfg["experts"], cfg["name"]
+    return args
 
+
+def workload_dict(args, world):
+    bucket_mb = 2 * (args.ref_bases // 192 + 1) * 64 / 1e6
+    return {"workload": f"synthetic {args.ref_bases/1e6:g} Mbp random ACGT reference (PCG64 seed {args.seed}), "
+                        f"{args.reads/1e6:g} M reads x {READ_LEN} bp per GPU, exact substrings + {SUB_RATE:.0%} substitutions ({args.cfg_name})",
+            "ref_bases": args.ref_bases, "reads_per_gpu": args.reads, "read_len": READ_LEN, "sub_rate": SUB_RATE,
+            "lut_K": LUT_K, "rmi_K": RMI_K, "rmi_experts": list(args.experts), "min_len": 1, "sweep_seed_table_K": args.seed_k,
+            "parallelism": f"reads sharded x{world}, index replicated",
+            "l2_policy": f"inputs larger than L2: packed read batch {args.reads * 48 / 1e6:.0f} MB, rank buckets {bucket_mb:.0f} MB, outputs "
+                         f"> 1 GB vs 126 MB L2 (at --config c3 the 67 MB of buckets are L2-resident by design; see DESIGN.md)"}
+
+
+def host_reads(ref_codes, n, seed):
+    return make_reads_host(ref_codes, n, READ_LEN, seed=seed)
+
+
+def device_reads(ref_dev, n, L, seed, out, sub_rate=SUB_RATE, chunk=2_000_000):
+    """Fill out[(n, L) uint8, device] with synthetic reads: exact substrings + i.i.d. substitutions (torch RNG on the
+    device; workload generation only)."""
+    import torch
+    gen = torch.Generator(device=ref_dev.device)
+    gen.manual_seed(seed)
+    ar = torch.arange(L, device=ref_dev.device, dtype=torch.int64)[None, :]
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        starts = torch.randint(0, ref_dev.numel() - L + 1, (b - a, 1), generator=gen, device=ref_dev.device, dtype=torch.int64)
+        r = ref_dev[(starts + ar).view(-1)].view(b - a, L)
+        mut = torch.rand(r.shape, generator=gen, device=ref_dev.device) < sub_rate
+        add = torch.randint(1, 4, r.shape, generator=gen, device=ref_dev.device, dtype=torch.uint8)
+        out[a:b] = torch.where(mut, (r + add) & 3, r)
+    return out
+
+
+def main():
+    args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    global RMI_EXPERTS
-    if args.ref_bases >= 500_000_000:           # keep ~1 leaf per 760-950 keys as the reference grows
-        RMI_EXPERTS = (2048, 1048576)
-    cfg_name = "BASELINE.json configs[2]" if args.ref_bases == 100_000_000 else \
-        ("BASELINE.json configs[3] shape, full suffix array in HBM" if args.ref_bases == 1_000_000_000 else "custom size")
-    workload = {"workload": f"synthetic {args.ref_bases/1e6:g} Mbp random ACGT reference (PCG64 seed 100), "
-                            f"{args.reads/1e6:g} M reads x {READ_LEN} bp per GPU, exact substrings + {SUB_RATE:.0%} substitutions "
-                            f"({cfg_name})",
-                "ref_bases": args.ref_bases, "reads_per_gpu": args.reads, "read_len": READ_LEN, "sub_rate": SUB_RATE,
-                "lut_K": LUT_K, "rmi_K": RMI_K, "rmi_experts": list(RMI_EXPERTS), "min_len": 1,
-                "parallelism": f"reads sharded x{world}, index replicated", "l2_policy": f"packed read batch ({args.reads * 48 / 1e6:.0f} MB) and outputs exceed "
-                f"L2; the rank buckets are {2 * (args.ref_bases // 192 + 1) * 64 / 1e6:.0f} MB (126 MB L2: resident at 100 Mbp, "
-                "HBM-resident at 1 Gbp; see DESIGN.md)"}
+    workload = workload_dict(args, world)
 
     if args.impl == "reference":
         if rank != 0:
@@ -183,7 +225,6 @@ def main():
     import torch
     import torch.distributed as dist
     import genie_smem_b200 as g
-    from genie_smem_b200 import engine as eng
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -191,25 +232,38 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # ---- setup: reference, index (built on the GPU), reads, LUT, RMI
     t_setup = time.time()
-    ref = make_reference(args.ref_bases)
-    text = _B[ref].tobytes()
-    host = g.HostIndex.build(text)
-    log(f"[rank {rank}] index built in {time.time()-t_setup:.1f}s")
-    index = g.DeviceIndex(host, dev)
-    reads_codes = make_reads_host(ref, args.reads, READ_LEN, seed=101 + rank)
-    batch = g.ReadBatch.from_codes(reads_codes, READ_LEN, read_id_base=0, pin=True)
-    batch.to(dev)
+    ref = make_reference(args.ref_bases, args.seed)
+    ref_dev = torch.from_numpy(ref).to(dev)
+    t0 = time.time()
+    index = g.DeviceIndex.build_on_device(ref_dev, dev)
+    log(f"[rank {rank}] reference generated in {t0-t_setup:.1f}s; index built on the GPU in {index.build_stats['build_ms']:.0f} ms "
+        f"(workspace {index.build_stats['workspace_bytes']/1e9:.1f} GB, {index.build_stats['doubling_rounds']} doubling rounds)")
+    if args.seed_k != 0:
+        index.build_seed_table(None if args.seed_k < 0 else args.seed_k)
+    n_host = min(HOST_READS, args.reads)
+    reads_head = host_reads(ref, n_host, seed=args.seed + 1 + rank)          # numpy: the CPU arms regenerate exactly these
+    codes_dev = torch.empty((args.reads, READ_LEN), dtype=torch.uint8, device=dev)
+    codes_dev[:n_host] = torch.from_numpy(reads_head).to(dev)
+    if args.reads > n_host:
+        device_reads(ref_dev, args.reads - n_host, READ_LEN, args.seed + 1 + rank, codes_dev[n_host:])
+    batch = g.ReadBatch.from_device_bases(codes_dev, READ_LEN, read_id_base=rank * args.reads)
+    # raw read bytes in pinned host memory: what the end-to-end path starts from (1 byte/base)
+    ascii_lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    ascii_host = torch.empty((args.reads, READ_LEN), dtype=torch.uint8, pin_memory=True)
+    for a in range(0, args.reads, 5_000_000):
+        b = min(args.reads, a + 5_000_000)
+        ascii_host[a:b].copy_(ascii_lut[codes_dev[a:b].long()])
+    del codes_dev, ref_dev
+    torch.cuda.empty_cache()
     engine = g.Engine(index, args.reads, READ_LEN, mems_per_read=24, recs_per_read=8)
     lut = g.lut_build(index, LUT_K)
-    # RMI: trained on the host from this index (any (coef, intercept) set is valid input; the
-    # oracle is given the same parameters)
     rmi = None
     if not args.skip_rmi:
         t0 = time.time()
-        rmi = train_rmi(host, ref, RMI_K, RMI_EXPERTS, dev)
-        rmi.build_probe_table(index)      # 16-byte {SA, 32-mer} probe records: one fetch per last-mile probe
-        log(f"[rank {rank}] RMI trained in {time.time()-t0:.1f}s")
+        rmi = train_rmi(index, RMI_K, args.experts, dev)
+        log(f"[rank {rank}] RMI probe table + training in {time.time()-t0:.1f}s")
     torch.cuda.synchronize()
     log(f"[rank {rank}] setup {time.time()-t_setup:.1f}s, index {index.bytes()/1e6:.0f} MB on device")
 
@@ -251,26 +305,31 @@ def main():
     engine.sweep(batch)
     ms_sel_bwa = timed(lambda: engine.select(g.METHOD_BWA, batch, min_len=1), args.steps, 1)
     recs = engine.records[: n_rec * 16].view(torch.int32).view(-1, 4)
-    qs = (recs[:, 1] & 0xFFFF).to(torch.int64)
-    qe = ((recs[:, 1] >> 16) & 0xFFFF).to(torch.int64)
-    steps_alg = int(((qe - qs) + (qs > 0).to(torch.int64)).sum().item())
+    steps_alg = 0
+    for a in range(0, n_rec, 50_000_000):
+        w = recs[a:a + 50_000_000, 1]
+        qs = (w & 0xFFFF).to(torch.int64)
+        qe = ((w >> 16) & 0xFFFF).to(torch.int64)
+        steps_alg += int(((qe - qs) + (qs > 0).to(torch.int64)).sum().item())
     alg_bytes = 128 * steps_alg + args.reads * ((READ_LEN + 3) // 4) + 16 * n_rec
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (ms_sweep * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_sweep_dram_bytes.json")
-    if os.path.exists(tpath) and args.ref_bases == 100_000_000:      # the ncu capture was taken on this config
+    traffic, traffic_src = None, None
+    tname = {1_000_000_000: "r01_1gbp_sweep_dram_bytes.json", 100_000_000: "r01_sweep_dram_bytes.json"}.get(args.ref_bases)
+    if tname and os.path.exists(os.path.join(ROOT, "profiles", tname)):        # ncu --set full capture of k_sweep on this reference size
         try:
-            tj = json.load(open(tpath))
+            tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
             traffic = tj["dram_bytes_per_read"] * args.reads
+            traffic_src = f"profiles/{tname}: {tj['dram_bytes_per_read']:.0f} DRAM bytes/read (ncu dram__bytes_read+write of k_sweep) x reads per launch"
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_sweep", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_read": round(alg_bytes / args.reads, 1), "fm_steps_per_read_min": round(steps_alg / args.reads, 2),
                 "records_per_read": round(n_rec / args.reads, 3), "ms_sweep": round(ms_sweep, 3), "ms_select_scan_gather": round(ms_sel_bwa, 3),
-                "note": (f"rank buckets = {2 * (args.ref_bases // 192 + 1) * 64 / 1e6:.0f} MB; below ~100 MB they stay in the 126 MB L2 and the "
-                         "HBM fraction is a statement about necessary bytes, not a DRAM utilisation (see traffic)")}
+                "note": "achieved = algorithmic bytes (SURVEY 8d: 128 B per necessary FM step + read + records) / k_sweep time; the access "
+                        "pattern is dependent random 64-byte fetches, whose measured ceiling on this GPU is ~50 G fetches/s = 3.2 TB/s at this "
+                        "index size (profiles/r01_probe.jsonl), not the streaming peak"}
 
     # ---- the other two methods (device-resident)
     methods = {"bwa": {"reads_per_s": world * args.reads / (ms_bwa * 1e-3), "ms_per_step": ms_bwa}}
@@ -280,44 +339,52 @@ def main():
     if rmi is not None:
         ms_rmi = timed(lambda: engine.launch(g.METHOD_RMI, batch, rmi=rmi), 2, 1)
         methods["rmi"] = {"reads_per_s": world * args.reads / (ms_rmi * 1e-3), "ms_per_step": ms_rmi, "K": RMI_K,
-                          "experts": list(RMI_EXPERTS)}
+                          "experts": list(args.experts)}
         st = engine.read_status[: args.reads]
         methods["rmi"]["reads_where_reference_raises"] = int((st == g.READ_REF_RAISES).sum().item())
         engine.check_overflow()
+    # the device-resident engine's pools are no longer needed: release them before the pipelined path allocates its own
+    total_records_dev = engine.records[: n_rec * 16]
+    rec_cnt_dev = engine.rec_cnt[: args.reads]
 
-    # ---- end to end through the public API: pinned host reads in, host records out
+    # ---- end to end through the public API: raw read bytes (pinned host) in, host records out
     pipe = g.PipelinedEngine(index, args.reads, READ_LEN, n_chunks=args.e2e_chunks, mems_per_read=24, recs_per_read=8)
 
-    def e2e_step():
-        return pipe.run(g.METHOD_BWA, batch, min_len=1)      # pinned host reads in, host records out
+    def e2e_time(step):
+        for _ in range(2):
+            step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * args.reads * args.steps / dt, res
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = e2e_step()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e = {"value": world * args.reads * args.steps / dt, "unit": "reads/s", "h2d_bytes_per_step": batch.h2d_bytes(),
-           "d2h_bytes_per_step": pipe.last_d2h_bytes, "method": "bwa", "records_last_step": int(len(res.records)),
-           "api": f"PipelinedEngine.run ({args.e2e_chunks} chunks, 2 streams: H2D / kernels / D2H overlapped)"}
+    v_ascii, res = e2e_time(lambda: pipe.run_ascii(g.METHOD_BWA, ascii_host, READ_LEN, min_len=1))
+    e2e = {"value": v_ascii, "unit": "reads/s", "h2d_bytes_per_step": pipe.last_h2d_bytes, "d2h_bytes_per_step": pipe.last_d2h_bytes,
+           "method": "bwa", "records_last_step": int(len(res.records)),
+           "api": f"PipelinedEngine.run_ascii ({args.e2e_chunks} chunks, 2 streams: raw ASCII reads H2D, GPU 2-bit packing, sweep/select, "
+                  "records D2H, all overlapped)"}
+    assert len(res.records) == n_rec, "end-to-end path and device-resident path disagree on the number of records"
+    batch.to_host(pin=True)
+    v_packed, _ = e2e_time(lambda: pipe.run(g.METHOD_BWA, batch, min_len=1))
+    e2e["packed_input"] = {"value": v_packed, "h2d_bytes_per_step": batch.h2d_bytes(),
+                           "api": "PipelinedEngine.run (reads already 2-bit packed on the host)"}
 
-    # ---- multi-GPU: the one collective of the path -- gather of per-rank record counts to rank 0
+    # ---- multi-GPU: the one collective of the path -- gather of per-rank records to rank 0
     total_records = n_rec
     gather = None
     if world > 1:
         from genie_smem_b200 import sharding
-        # the final gather of per-rank SMEM records to rank 0 over NCCL (device buffers, NVLink)
-        rec_dev = engine.records[: n_rec * 16]
-        cnt_dev = engine.rec_cnt[: args.reads].to(torch.int64)
+        cnt_dev = rec_cnt_dev.to(torch.int64)
         barrier()
         t0 = time.perf_counter()
-        g_recs, g_cnts = sharding.gather_records(rec_dev, cnt_dev, dst=0, device=dev)
+        g_recs, g_cnts = sharding.gather_records(total_records_dev, cnt_dev, dst=0, device=dev)
         torch.cuda.synchronize()
         dtg = time.perf_counter() - t0
         if rank == 0:
@@ -328,15 +395,16 @@ def main():
     # ---- CPU baseline on the host cores, rank 0 at N=1 only
     cpu_baseline = None
     if rank == 0 and world == 1 and args.cpu_seconds > 0:
-        sa1, _ = host.export()
-        v, n_s, thr = cpu_arm(text, sa1, reads_codes, 0, 0, args.cpu_seconds)
+        text = _B[ref].tobytes()
+        sa1 = index.suffix_array_host()
+        v, n_s, thr = cpu_arm(text, sa1, reads_head, 0, 0, args.cpu_seconds)
         cpu_baseline = {"value": round(v, 1), "unit": "reads/s", "cores": thr, "kind": "port",
                         "sample": f"first {n_s} reads of the same batch, BWA-SMEM, oracle/smem_oracle.c (reference algorithm, "
                                   f"O(L^2) restarts included) on {thr} pthreads"}
-        v2, n2, _ = cpu_arm(text, sa1, reads_codes, 1, 0, args.cpu_seconds / 2, K=LUT_K)
+        v2, n2, _ = cpu_arm(text, sa1, reads_head, 1, 0, args.cpu_seconds / 2, K=LUT_K)
         cpu_baseline["lut_reads_per_s"] = round(v2, 1)
         if rmi is not None:
-            v3, n3, _ = cpu_arm(text, sa1, reads_codes, 2, 0, args.cpu_seconds / 2, rmi=rmi_dict(rmi))
+            v3, n3, _ = cpu_arm(text, sa1, reads_head, 2, 0, args.cpu_seconds / 2, rmi=rmi_dict(rmi))
             cpu_baseline["rmi_reads_per_s"] = round(v3, 1)
 
     if rank == 0:
@@ -345,44 +413,62 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload,
                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(gpu_launches),
                "clocks": clocks, "methods": methods, "records_total": total_records, "maximal_matches_per_read": round(n_mems / args.reads, 3),
-               "record_gather": gather}
+               "record_gather": gather, "index_build": index.build_stats}
+        out["config"]["sweep_seed_table_K"] = int(index.c.seed_K)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def train_rmi(host, ref_codes, K, experts, dev):
-    """Host-side RMI training on the k-mer -> row keys of this index (reference RMI_LUT.py:36-50);
-    every `stride`-th key to keep setup short -- model quality only changes the last-mile length."""
+def train_rmi(index, K, experts, dev, max_keys=8_000_000):
+    """RMI over the k-mer -> row keys of this index (reference RMI_LUT.py:36-50).  The {SA value, 32-mer} probe table is
+    built on the device (it also serves the last-mile search); a strided sample of its rows is the training set --
+    model quality only changes the last-mile length, never the result -- and the fit is the vectorised host trainer."""
+    import torch
     import genie_smem_b200 as g
-    sa1 = host.export()[0] if hasattr(host, "export") else np.asarray(host)     # a HostIndex, or the 1-based suffix array itself
-    n_bases = len(ref_codes)
-    stride = max(1, len(sa1) // 4_000_000)
-    rows = np.arange(0, len(sa1), stride, dtype=np.int64)
-    start = sa1[rows].astype(np.int64) - 1
-    ok = start + K <= n_bases
-    rows, start = rows[ok], start[ok]
-    key = np.zeros(len(rows), np.int64)
-    for j in range(K):
-        key = (key << 2) | ref_codes[start + j]
-    m = g.RMI(list(experts)).fit(key, rows)
-    return g.RmiParams(K, m.level_sizes, m.coef, m.intercept, dev)
+    rmi = g.RmiParams(K, [1] + list(experts), np.zeros(1 + sum(experts)), np.zeros(1 + sum(experts)), dev)
+    rmi.build_probe_table(index)
+    n_rows = index.n_rows
+    stride = max(1, n_rows // max_keys)
+    tab = rmi.probe.view(torch.int32).view(-1, 4)[::stride].cpu().numpy().view(np.uint32)
+    rows = np.arange(0, n_rows, stride, dtype=np.int64)
+    start = tab[:, 0].astype(np.int64) - 1
+    code = (tab[:, 1].astype(np.uint64) << np.uint64(32)) | tab[:, 2].astype(np.uint64)
+    ok = start + K <= index.n_bases
+    key = (code[ok] >> np.uint64(64 - 2 * K)).astype(np.int64)
+    m = g.RMI(list(experts)).fit(key, rows[ok])
+    out = g.RmiParams(K, m.level_sizes, m.coef, m.intercept, dev)
+    out.probe = rmi.probe
+    out.c.probe = rmi.probe.data_ptr()
+    return out
 
 
 def reference_arm(args, workload):
-    """--impl reference: the reference's CPU path (oracle port in C, all host threads) on bounded
-    samples of the same workload.  No GPU, none of the engine's kernels."""
-    import genie_smem_b200 as g        # host-side index builder only (SA-IS); search is the oracle's
-    ref = make_reference(args.ref_bases)
+    """--impl reference: the reference's CPU path (oracle port in C, all host threads) on bounded samples of the same
+    workload.  The suffix array both arms search is an INPUT of the path: it is built by whichever builder is available
+    (the GPU builder when a device is visible, else host SA-IS) before the timed region; the timed search runs on the
+    host cores only, through oracle/smem_oracle.c, with none of the engine's kernels."""
+    import genie_smem_b200 as g
+    ref = make_reference(args.ref_bases, args.seed)
     text = _B[ref].tobytes()
-    host = g.HostIndex.build(text, reverse=False)
-    sa1, _ = host.export()
-    reads_codes = make_reads_host(ref, min(args.reads, 200_000), READ_LEN, seed=101)
+    sa1 = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            idx = g.DeviceIndex.build_on_device(ref, "cuda:0", reverse=False)
+            sa1 = idx.suffix_array_host()
+            del idx
+            torch.cuda.empty_cache()
+    except Exception as e:          # no usable device: fall through to the host builder
+        log(f"reference arm: GPU index build unavailable ({e}); using host SA-IS")
+    if sa1 is None:
+        sa1, _ = g.HostIndex.build(text, reverse=False).export()
+    reads_codes = host_reads(ref, min(args.reads, HOST_READS), seed=args.seed + 1)
     from oracle.c_oracle import COracle
     o = COracle(text, sa1)
     thr = o.max_threads
     L = READ_LEN
-    # size one step to ~10 s
+    # size one step to ~8 s
     n0 = 32 * thr
     joined = _B[reads_codes[:n0].reshape(-1)].tobytes()
     t0 = time.perf_counter()

@@ -26,7 +26,7 @@ class IndexInfo(C.Structure):
 class DevIndex(C.Structure):
     _fields_ = [("n_rows", C.c_uint64), ("n_buckets", C.c_uint64), ("fwd_buckets", C.c_void_p), ("rev_buckets", C.c_void_p),
                 ("sa", C.c_void_p), ("text2bit", C.c_void_p), ("C", C.c_uint32 * 5), ("primary_fwd", C.c_uint32),
-                ("primary_rev", C.c_uint32), ("reserved", C.c_uint32)]
+                ("primary_rev", C.c_uint32), ("seed_K", C.c_uint32), ("seed_table", C.c_void_p)]
 
 
 class DevReads(C.Structure):
@@ -62,11 +62,15 @@ EXPORTS = {
     "gsm_index_build_device_workspace": (C.c_int, [C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "gsm_index_build_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                          C.POINTER(IndexInfo), C.c_void_p]),
+    "gsm_pack_reads_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
+    "gsm_pack_reads_device_check": (C.c_int, [C.c_void_p, C.c_void_p]),
     "gsm_smem_workspace_info": (C.c_int, [C.c_uint64, C.c_uint32, C.POINTER(WorkspaceInfo)]),
     "gsm_backsearch_batch": (C.c_int, [C.POINTER(DevIndex), C.POINTER(DevReads), C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_backsearch_add_one_batch": (C.c_int, [C.POINTER(DevIndex), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_sa_lookup_batch": (C.c_int, [C.POINTER(DevIndex), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_lut_build": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p]),
+    "gsm_seed_table_build": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p]),
     "gsm_smem_batch": (C.c_int, [C.c_int, C.POINTER(DevIndex), C.POINTER(DevReads), C.c_uint32, C.c_uint32, C.c_void_p,
                                  C.POINTER(DevRmi), C.POINTER(Workspace), C.c_void_p]),
     "gsm_smem_sweep": (C.c_int, [C.POINTER(DevIndex), C.POINTER(DevReads), C.POINTER(Workspace), C.c_void_p]),

@@ -1,0 +1,97 @@
+// Read ingest on the device: ASCII (or code) reads -> the 2-bit packed, 16-byte aligned batch
+// layout of include/genie_smem.h.  The reference takes one Python string per call (ExactMatch.load_query,
+// SMEM/ExactMatch.py:104-108; SMEM.get_SMEMS(query, ...), SMEM/SMEM.py:456); a pipeline hands over raw read
+// bytes, which cross PCIe once (1 byte/base) and are packed here at HBM speed instead of by a host loop.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <string>
+
+#include "../../include/genie_smem.h"
+#include "host_common.hpp"
+
+namespace gsm {
+
+#define GSM_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return fail(GSM_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+namespace {
+
+// One warp per read, one lane per 16-base output word (grid-stride over reads).  The pad words of a read's last
+// 16-byte chunk are zeroed.  A non-ACGT byte records the smallest offending read index in *bad.
+__global__ void __launch_bounds__(256) k_pack_reads(const uint8_t* bases, const unsigned long long* base_off, uint32_t fixed_len,
+                                                    const uint32_t* chunk_off, uint64_t n_reads, int ascii, uint32_t* packed,
+                                                    uint32_t* len_out, unsigned long long* bad) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp0; r < n_reads; r += n_warps) {
+        uint64_t b0;
+        uint32_t L;
+        if (base_off) {
+            b0 = base_off[r];
+            L = (uint32_t)(base_off[r + 1] - b0);
+        } else {
+            b0 = r * (uint64_t)fixed_len;
+            L = fixed_len;
+        }
+        uint32_t* dst = packed + (uint64_t)chunk_off[r] * 4u;
+        const uint32_t n_words = ((L + 63u) / 64u) * 4u;
+        if (len_out && lane == 0) len_out[r] = L;
+        for (uint32_t w = lane; w < n_words; w += 32u) {
+            uint32_t v = 0;
+            const uint32_t t0 = w * 16u;
+            for (uint32_t t = 0; t < 16u && t0 + t < L; ++t) {
+                uint32_t c = bases[b0 + t0 + t];
+                if (ascii) c = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+                if (c > 3u) {
+                    atomicMin(bad, (unsigned long long)r);
+                    c = 0;
+                }
+                v |= c << (30u - 2u * t);
+            }
+            dst[w] = v;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace gsm
+
+using namespace gsm;
+
+extern "C" {
+
+int gsm_pack_reads_device(const void* bases, const uint64_t* base_off, uint32_t fixed_len, const uint32_t* chunk_off, uint64_t n_reads,
+                          uint32_t ascii, void* packed, uint32_t* len_out, uint64_t* scratch8, void* stream) {
+    if (!bases || !chunk_off || !packed || !scratch8) return fail(GSM_E_INVALID, "gsm_pack_reads_device: null");
+    if (!base_off && fixed_len == 0) return fail(GSM_E_INVALID, "gsm_pack_reads_device: base_off is NULL and fixed_len is 0");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(GSM_E_NODEVICE, "no CUDA device");
+    if (n_reads == 0) return GSM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    GSM_CUDA(cudaMemsetAsync(scratch8, 0xFF, 8, st));
+    const uint64_t warps = n_reads;
+    const unsigned grid = (unsigned)std::min<uint64_t>((warps + 7) / 8, 148ull * 32);
+    k_pack_reads<<<grid, 256, 0, st>>>((const uint8_t*)bases, (const unsigned long long*)base_off, fixed_len, chunk_off, n_reads, (int)ascii,
+                                       (uint32_t*)packed, len_out, (unsigned long long*)scratch8);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+/* Result of the validity check of the last gsm_pack_reads_device on this scratch word: GSM_OK, or GSM_E_INVALID
+ * naming the first read that holds a non-ACGT byte.  Synchronises the stream. */
+int gsm_pack_reads_device_check(const uint64_t* scratch8, void* stream) {
+    unsigned long long bad = 0;
+    GSM_CUDA(cudaMemcpyAsync(&bad, scratch8, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GSM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (bad != ~0ull) return fail(GSM_E_INVALID, "non-ACGT base in read " + std::to_string(bad));
+    return GSM_OK;
+}
+
+}  // extern "C"

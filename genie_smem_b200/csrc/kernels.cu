@@ -361,6 +361,27 @@ __global__ void k_lut_build(const uint4* fwd, IndexMeta meta, uint32_t K, uint64
 }
 
 // RMI_LUT.get_suffix_rmi (reference SMEM/RMI_LUT.py:67-78) for a batch of codes
+// Seed table of the sweep kernel: per K-mer code the rows of the k-mer on the text index, its count, and the rows
+// of the reversed k-mer on the reversed-text index -- the state (k, P0, cnt) a forward extension has after K steps.
+__global__ void k_seed_build(const uint4* fwd, const uint4* rev, IndexMeta meta, uint32_t K, uint64_t n_codes, uint4* table) {
+    const uint64_t code = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (code >= n_codes) return;
+    auto lf = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
+    auto lr = [rev](uint64_t idx) { return ldg_half(rev, idx); };
+    uint32_t lo = 0, cnt = meta.n_rows, rlo = 0, rcnt = meta.n_rows;
+    for (uint32_t t = 0; t < K && cnt; ++t) {
+        const uint32_t c = (uint32_t)(code >> (2 * t)) & 3u;                  // last base first
+        const StepOut r = step_single(lf, lo, lo + cnt, c, meta.C[c], meta.prim_f);
+        lo = r.lo_new; cnt = r.cnt_new;
+    }
+    for (uint32_t t = 0; t < K && rcnt && cnt; ++t) {
+        const uint32_t c = (uint32_t)(code >> (2 * (K - 1 - t))) & 3u;        // first base first
+        const StepOut r = step_single(lr, rlo, rlo + rcnt, c, meta.C[c], meta.prim_r);
+        rlo = r.lo_new; rcnt = r.cnt_new;
+    }
+    table[code] = make_uint4(lo, cnt, cnt ? rlo : 0u, 0u);
+}
+
 __global__ void k_rmi_lookup(const uint32_t* sa, const uint32_t* text, uint64_t n_rows, uint64_t n_bases, RmiModel m, uint64_t n,
                              const uint64_t* codes, double* pred, int64_t* lo, int64_t* hi, uint8_t* status) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -517,6 +538,18 @@ int gsm_lut_build(const gsm_dev_index* ix, uint32_t K, uint32_t* table, void* st
     return GSM_OK;
 }
 
+int gsm_seed_table_build(const gsm_dev_index* ix, uint32_t K, void* table, void* stream) {
+    if (!ix || !table || !ix->fwd_buckets || !ix->rev_buckets) return fail(GSM_E_INVALID, "gsm_seed_table_build: needs both bucket arrays");
+    if (K < 1 || K > 14) return fail(GSM_E_INVALID, "gsm_seed_table_build: K must be in 1..14");
+    int st = device_ready();
+    if (st) return st;
+    const uint64_t n_codes = 1ull << (2 * K);
+    k_seed_build<<<(unsigned)((n_codes + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const uint4*)ix->fwd_buckets, (const uint4*)ix->rev_buckets,
+                                                                                    make_meta(ix), K, n_codes, (uint4*)table);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
 static int fill_rmi(const gsm_dev_rmi* rmi, RmiModel* m) {
     memset(m, 0, sizeof(*m));
     if (!rmi || !rmi->level_sizes || !rmi->coef || !rmi->intercept) return fail(GSM_E_INVALID, "RMI parameters missing");
@@ -577,7 +610,9 @@ int gsm_smem_sweep(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_workspa
     SweepArgs sa;
     sa.fwd = (const uint4*)ix->fwd_buckets; sa.rev = (const uint4*)ix->rev_buckets; sa.meta = make_meta(ix);
     sa.reads = (const uint4*)rd->packed; sa.chunk_off = rd->chunk_off; sa.len = rd->len; sa.n_reads = (uint32_t)rd->n_reads;
-    sa.read_u4 = sweep_read_u4(rd->max_len); sa.max_len = rd->max_len;
+    sa.read_u4 = sweep_read_u4(rd->max_len); sa.pack_u4 = sweep_pack_u4(rd->max_len); sa.max_len = rd->max_len;
+    sa.seed_tab = (const uint4*)ix->seed_table; sa.seed_K = ix->seed_table ? ix->seed_K : 0u;
+    if (sa.seed_tab && (sa.seed_K < 1 || sa.seed_K > 16)) return fail(GSM_E_INVALID, "seed table K must be in 1..16");
     sa.mem_pool = (uint4*)ws->mem_pool; sa.mem_cap = ws->mem_cap; sa.mem_off = ws->mem_off; sa.mem_cnt = ws->mem_cnt;
     sa.scratch = (uint4*)ws->quad_scratch; sa.counters = (unsigned long long*)ws->counters;
     k_sweep<<<sb, SWEEP_THREADS, sweep_smem_bytes(rd->max_len), stream>>>(sa);

@@ -16,7 +16,7 @@ namespace gsm {
 constexpr int SWEEP_THREADS = 128;
 constexpr int SWEEP_LPR = 2;                              // lanes per read
 constexpr int SWEEP_GROUPS = SWEEP_THREADS / SWEEP_LPR;   // reads in flight per block
-constexpr int SWEEP_CAP = 15;                             // candidates kept in shared memory per read
+constexpr int SWEEP_CAP = 12;                             // candidates kept in shared memory per read
 constexpr int SWEEP_MIN_BLOCKS = 8;
 
 struct SweepArgs {
@@ -28,7 +28,10 @@ struct SweepArgs {
     const uint32_t* len;
     uint32_t n_reads;
     uint32_t read_u4;        // uint4 slots of shared memory per read for its unpacked bases
+    uint32_t pack_u4;        // uint4 slots per read for its packed words (k-mer codes of the seed table)
     uint32_t max_len;
+    const uint4* seed_tab;   // optional 4^seed_K x {fwd lo, count, rev lo, 0} (gsm_seed_table_build), else NULL
+    uint32_t seed_K;
     uint4* mem_pool;
     unsigned long long mem_cap;
     uint32_t* mem_off;
@@ -38,7 +41,8 @@ struct SweepArgs {
 };
 
 // Shared memory: [256 x u32 spread table][per pair: SWEEP_CAP candidates of 16 B {end, lo, cnt, -}, then
-// the read's bases one per byte].  Indexed through one extern array so that the compiler emits LDS/STS.
+// the read's bases one per byte, then its packed words][16 B pad].  Indexed through one extern array so that
+// the compiler emits LDS/STS.
 extern __shared__ uint4 g_sweep_smem[];
 
 // one 32-byte half of a bucket: a single 256-bit read-only load
@@ -78,10 +82,18 @@ __device__ __forceinline__ StepOut pair_step(const uint4* __restrict__ bk, uint3
     return finish_step(eq0, eq1, ltd, P0, P1, ch, Cc, primary);
 }
 
+// one 16-byte seed-table entry (read-only path; volatile so that it is issued before the bucket loads' consumers)
+__device__ __forceinline__ uint4 ldg_seed(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 struct DevSweepCtx {
     const SweepArgs& a;
     uint32_t cand0;       // index (uint4) of this pair's candidate slots
     uint32_t bytes0;      // byte offset of this pair's unpacked read
+    uint32_t words0;      // word offset of this pair's packed read
     uint4* stage;         // global: match staging of this pair
     uint4* spill;         // global: candidate spill of this pair
     uint32_t g, gmask, gbase;
@@ -101,6 +113,7 @@ struct DevSweepCtx {
         __syncwarp(gmask);                       // both lanes are done with the previous read's bases
         for (uint32_t c = g; c < nch; c += SWEEP_LPR) {
             const uint4 v = __ldg(a.reads + (size_t)off + c);
+            g_sweep_smem[(words0 >> 2) + c] = v;
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -113,6 +126,12 @@ struct DevSweepCtx {
     }
     __device__ __forceinline__ uint32_t base(uint32_t pos) const {
         return reinterpret_cast<const uint8_t*>(g_sweep_smem)[bytes0 + pos];
+    }
+    __device__ __forceinline__ uint32_t seed_k() const { return a.seed_K; }
+    // code of q[pos:pos+K): top 2K bits of the 64-bit window starting at base pos (MSB-first packing)
+    __device__ __forceinline__ uint32_t kmer(uint32_t pos) const {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(g_sweep_smem) + words0 + (pos >> 4);
+        return __funnelshift_l(w[1], w[0], 2u * (pos & 15u)) >> (32u - 2u * a.seed_K);
     }
     __device__ __forceinline__ void cand_put(uint32_t i, uint32_t j, uint32_t lo, uint32_t cnt) {
         if (i < (uint32_t)SWEEP_CAP) g_sweep_smem[cand0 + i] = make_uint4(j, lo, cnt, 0u);   // same value from both lanes
@@ -153,24 +172,34 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS) k_sweep(const
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t g = lane & 1u;
     const uint32_t pair_in_block = threadIdx.x >> 1;
-    const uint32_t pair_u4 = SWEEP_CAP + a.read_u4;
+    const uint32_t pair_u4 = SWEEP_CAP + a.read_u4 + a.pack_u4;
     const uint32_t p0 = 64u + pair_in_block * pair_u4;               // 64 uint4 = the 1 KB spread table
     const size_t gp = (size_t)blockIdx.x * SWEEP_GROUPS + pair_in_block;
-    DevSweepCtx ctx{a, p0, (p0 + SWEEP_CAP) * 16u, a.scratch + gp * 2 * a.max_len, a.scratch + gp * 2 * a.max_len + a.max_len,
-                    g, 3u << (lane & ~1u), lane & ~1u};
+    DevSweepCtx ctx{a, p0, (p0 + SWEEP_CAP) * 16u, (p0 + SWEEP_CAP + a.read_u4) * 4u, a.scratch + gp * 2 * a.max_len,
+                    a.scratch + gp * 2 * a.max_len + a.max_len, g, 3u << (lane & ~1u), lane & ~1u};
     Sweeper<DevSweepCtx> sw;
     for (;;) {
         const bool need = sw.next(ctx, a.meta);
         if (!__any_sync(0xFFFFFFFFu, need)) break;
+        // ONE uniform memory section per iteration: every pair issues its pending fetch here -- a seed-table entry
+        // or the (at most two) buckets of an FM step -- so all 16 chains' loads are in flight together.
+        const bool is_seed = need && sw.pending_seed();
+        const bool is_step = need && !is_seed;
+        uint4 se = make_uint4(0u, 0u, 0u, 0u);
+        if (is_seed) se = ldg_seed(a.seed_tab + sw.P0);
         const bool rev = sw.on_reverse();
         const StepOut r = pair_step(rev ? a.rev : a.fwd, sw.P0, sw.P0 + sw.cnt, sw.ch, a.meta.C[sw.ch & 3u],
-                                    rev ? a.meta.prim_r : a.meta.prim_f, g, need);
-        if (need) sw.consume(ctx, a.meta, r);
+                                    rev ? a.meta.prim_r : a.meta.prim_f, g, is_step);
+        if (is_step) sw.consume(ctx, a.meta, r);
+        else if (is_seed) sw.consume_seed(ctx, a.meta, SeedEntry{se.x, se.y, se.z, se.w});
     }
 }
 
+// packed words of a read, rounded up to 16-byte chunks
+__host__ __device__ inline uint32_t sweep_pack_u4(uint32_t max_len) { return (max_len + 63u) / 64u; }
+
 inline size_t sweep_smem_bytes(uint32_t max_len) {
-    return 1024 + (size_t)SWEEP_GROUPS * (SWEEP_CAP + sweep_read_u4(max_len)) * sizeof(uint4);
+    return 1024 + (size_t)SWEEP_GROUPS * (SWEEP_CAP + sweep_read_u4(max_len) + sweep_pack_u4(max_len)) * sizeof(uint4) + 16;
 }
 
 }  // namespace gsm

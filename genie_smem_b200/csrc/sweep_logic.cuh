@@ -2,30 +2,38 @@
 // logic test (tests/emu).  It enumerates ALL maximal exact matches of a read with a bidirectional
 // FM index, the way the reference's forward_extension / backward_extension pair
 // (SMEM/SMEM.py:425-443, 389-423) would if each extension cost one FM step instead of a full
-// restart of exact_match_back_prop:
+// restart of exact_match_back_prop, and if the first K steps of an extension were one table fetch
+// (the reference's own LUT idea, SMEM/LUT.py:15-35, applied to both directions):
 //
-//   sweep(x):  FWD   append q[x], q[x+1], ... on the reverse-text index while q[x:j] still occurs
+//   sweep(x):  SEEDF one fetch from the seed table gives the intervals of q[x:x+K) on both indexes
+//                    (absent k-mer or read end closer than K: plain stepping from one base).
+//              FWD   append q[x+K], ... on the reverse-text index while q[x:j] still occurs
 //                    (SMEM.py:431-440); remember (j, interval) whenever the occurrence count is
-//                    about to change: only those ends can be right-maximal.
+//                    about to change: only those ends can be right-maximal.  Ends j < x+K are not
+//                    materialised ("short" candidates): most sweeps never need them.
 //              WALK  prepend q[x-1], q[x-2], ... to the LONGEST candidate until it dies
 //                    (SMEM.py:396-416): its start s is LS[F(x)].  Every other candidate j has
 //                    lb <= LS[j] <= s, where lb = (previous sweep's start) + 1 because that
 //                    sweep's forward extension ended exactly at x.  If s == lb they all share
 //                    LS = s and none of them is maximal: the sweep is over after the minimum
-//                    possible number of steps (the common case inside an exact stretch).
-//              LOCK  otherwise prepend to the remaining candidates in lock step, longest first;
-//                    a candidate that dies while no longer one survives, at a start left of
-//                    every match found so far, is maximal; a survivor whose count equals the
-//                    previous (longer) survivor's is dropped (same occurrences => same LS).
-//                    A single survivor continues in WALK mode (registers only).
+//                    possible number of steps (the common case inside an exact stretch); a walk
+//                    that reaches lb stops there without the failing step.
+//              SEQ   otherwise every remaining candidate end j, longest first, gets its own walk:
+//                    stored candidates continue from their interval at x-1; short candidates start
+//                    from the seed-table entry of q[j-K:j) (SEEDB, one fetch replaces K steps on
+//                    wide intervals) or, if that k-mer is absent / would start left of lb, from a
+//                    plain backward search at j.  LS is non-decreasing in j, so (LS[j], j) is
+//                    maximal iff LS[j] is smaller than the last emitted start, and the first walk
+//                    that reaches lb ends the sweep.
 //              x = F(x) = end of the longest forward match; repeat until x == L.
 //
 // With LS[j] = leftmost start of a match ending at j the emitted set is
 // {(LS[j], j) : j = L or LS[j+1] > LS[j]}; it determines LS[] and F() completely, and the three
 // reference entry points are integer selections over it (select_logic.cuh).
 //
-// One next()/consume() pair = one FM extension step = at most two bucket fetches.  The pending
-// step's operands live in registers (P0, cnt, ch), so the top of the kernel loop is uniform.
+// One next()/consume() pair = one FM extension step (at most two bucket fetches) or one seed-table
+// fetch.  The pending operation's operands live in registers (P0, cnt, ch), so the top of the
+// kernel loop is uniform.
 #pragma once
 #include "fm_core.cuh"
 
@@ -44,14 +52,22 @@ struct MemEntry {
     uint32_t se, lo, cnt, sweep;
 };
 
-enum SweepMode : int { M_FETCH = 0, M_FWD = 1, M_WALK = 2, M_LOCK = 3, M_DONE = 4 };
+// One entry of the seed table (gsm_seed_table_build): the k-mer's rows on the text index, its count, and
+// the rows of the reversed k-mer on the reversed-text index.
+struct SeedEntry {
+    uint32_t fwd_lo, cnt, rev_lo, pad;
+};
+
+enum SweepMode : int { M_FETCH = 0, M_FWD = 1, M_WALK = 2, M_SEEDF = 3, M_SEEDB = 4, M_DONE = 5 };
 
 // Ctx must provide:
 //   bool     fetch(uint32_t& rid, uint32_t& L)          next read (loads its bases), false when none
 //   uint32_t base(uint32_t pos)                         2-bit base of the current read
+//   uint32_t seed_k()                                   K of the seed table, 0 = no table
+//   uint32_t kmer(uint32_t pos)                         code of q[pos:pos+K) (LUT.convert_seq_to_num, LUT.py:37-48)
 //   void     cand_put(uint32_t i, uint32_t j, uint32_t lo, uint32_t cnt)
 //   void     cand_get(uint32_t i, uint32_t& j, uint32_t& lo, uint32_t& cnt)
-//   void     cand_sync()                                make candidate writes visible to the quad
+//   void     cand_sync()                                make candidate writes visible to the pair
 //   void     emit(uint32_t idx, MemEntry e)             stage maximal match #idx of this read
 //   void     finish(uint32_t rid, uint32_t n_mems)      read complete
 template <typename Ctx>
@@ -60,16 +76,18 @@ struct Sweeper {
     uint32_t rid = 0, L = 0;
     uint32_t x = 0, F = 0, lb = 0;
     uint32_t n_mems = 0, sweep_id = 0;
-    // pending step: rows [P0, P0 + cnt) extended by base ch (FWD: on the reverse-text index)
+    // pending FM step: rows [P0, P0 + cnt) extended by base ch (FWD: on the reverse-text index);
+    // pending seed fetch (M_SEEDF / M_SEEDB): P0 holds the k-mer code
     uint32_t P0 = 0, cnt = 0, ch = 0;
     uint32_t k = 0;            // FWD: rows of q[x:pos) on the text index start here
-    uint32_t pos = 0;          // FWD: next base to append; WALK/LOCK: base being prepended
-    uint32_t cur_j = 0;        // WALK/LOCK: end of the candidate being extended
-    uint32_t ncand = 0;
-    uint32_t first_walk = 0;
-    uint32_t t = 0, base_i = 0, top = 0, w = 0, lastkept = 0, last_start = 0;
+    uint32_t pos = 0;          // FWD: next base to append; WALK: base being prepended
+    uint32_t cur_j = 0;        // WALK: end of the candidate being extended
+    uint32_t ncand = 0;        // stored candidates (ends >= x + K when the sweep was seeded)
+    uint32_t short_hi = 0;     // short candidates still to walk: ends x+1 .. short_hi (none if <= x)
+    uint32_t last_start = 0;
 
-    GSM_HD bool pending() const { return mode == M_FWD || mode == M_WALK || mode == M_LOCK; }
+    GSM_HD bool pending_step() const { return mode == M_FWD || mode == M_WALK; }
+    GSM_HD bool pending_seed() const { return mode == M_SEEDF || mode == M_SEEDB; }
     GSM_HD bool on_reverse() const { return mode == M_FWD; }
 
     GSM_HD void emit_match(Ctx& c, uint32_t start, uint32_t end, uint32_t lo, uint32_t n) {
@@ -80,25 +98,6 @@ struct Sweeper {
         last_start = start;
     }
 
-    // A read is in progress and x < L: start sweeps until one has a pending FM step or the read ends.
-    GSM_HD void start_sweeps(Ctx& c, const IndexMeta& m) {
-        for (;;) {
-            const uint32_t b = c.base(x);
-            ncand = 0;
-            k = m.C[b]; P0 = m.C[b]; cnt = m.cnt[b];
-            pos = x + 1;
-            if (cnt == 0) {              // base absent from the text (outside the reference's domain): skip it
-                lb = x + 1; x++; sweep_id++;
-                if (x >= L) { c.finish(rid, n_mems); return; }
-                continue;
-            }
-            if (pos < L) { ch = c.base(pos); mode = M_FWD; return; }
-            c.cand_put(ncand++, pos, k, cnt);
-            if (start_bwd(c)) return;
-            if (x >= L) return;          // end_sweep() finished the read
-        }
-    }
-
     // mode M_FETCH doubles as "needs a transition": x >= L means no read is in progress.
     GSM_HD void end_sweep(Ctx& c) {
         lb = x + 1; x = F; sweep_id++;
@@ -106,35 +105,92 @@ struct Sweeper {
         if (x >= L) c.finish(rid, n_mems);
     }
 
-    // Forward phase over: pop the longest candidate and walk it left.  Returns true if a step is pending.
-    GSM_HD bool start_bwd(Ctx& c) {
+    // Start the sweep at x (a read is in progress, x < L).  Leaves a pending operation, or mode == M_FETCH.
+    GSM_HD void start_sweep(Ctx& c, const IndexMeta& m) {
+        const uint32_t b = c.base(x);
+        ncand = 0; short_hi = 0;
+        if (m.cnt[b] == 0) {              // base absent from the text (outside the reference's domain): skip it
+            lb = x + 1; x++; sweep_id++;
+            if (x >= L) c.finish(rid, n_mems);
+            return;                       // mode stays M_FETCH
+        }
+        const uint32_t K = c.seed_k();
+        if (K != 0 && x + K <= L) { P0 = c.kmer(x); mode = M_SEEDF; return; }
+        fwd_plain(c, m);
+    }
+
+    GSM_HD void fwd_plain(Ctx& c, const IndexMeta& m) {
+        const uint32_t b = c.base(x);
+        k = m.C[b]; P0 = m.C[b]; cnt = m.cnt[b];
+        pos = x + 1;
+        fwd_continue(c, m);
+    }
+
+    // (k, P0, cnt) describe q[x:pos): append q[pos], or close the forward phase at the read end.
+    GSM_HD void fwd_continue(Ctx& c, const IndexMeta& m) {
+        if (pos < L) { ch = c.base(pos); mode = M_FWD; return; }
+        c.cand_put(ncand++, pos, k, cnt);
+        start_bwd(c, m);
+    }
+
+    // Forward phase over: pop the longest candidate and walk it left.
+    GSM_HD void start_bwd(Ctx& c, const IndexMeta& m) {
         c.cand_sync();
         ncand--;
         c.cand_get(ncand, cur_j, P0, cnt);
         F = cur_j;
-        first_walk = 1;
         last_start = 0xFFFFFFFFu;
         if (x == 0) {                       // nothing to prepend: every candidate starts at 0, the longest wins
             emit_match(c, 0, cur_j, P0, cnt);
             end_sweep(c);
-            return false;
+            return;
         }
-        pos = x - 1;
+        walk_from(c, m, x);
+    }
+
+    // (P0, cnt) is the interval of q[start:cur_j): set up the step prepending q[start-1].  False if start is
+    // already the lower bound (no match ending beyond x starts left of lb) or the left end of the read.
+    GSM_HD bool try_walk(Ctx& c, uint32_t start) {
+        if (start == lb || start == 0) return false;
+        pos = start - 1;
         ch = c.base(pos);
         mode = M_WALK;
         return true;
     }
 
-    GSM_HD void start_lock(Ctx& c) {
-        first_walk = 0;
-        base_i = 0; top = ncand; t = ncand; w = ncand; lastkept = 0;
-        pos = x - 1;
-        ch = c.base(pos);
-        c.cand_get(t - 1, cur_j, P0, cnt);
-        mode = M_LOCK;
+    GSM_HD void walk_from(Ctx& c, const IndexMeta& m, uint32_t start) {
+        if (!try_walk(c, start)) walk_end(c, m, start);
     }
 
-    // Bring this quad to its next pending step.  Returns false only when there are no more reads.
+    // The walked candidate (cur_j, P0, cnt) cannot be extended beyond `start`: it is maximal iff it reaches further
+    // left than every longer candidate did.  A walk that stops at lb settles all the shorter candidates too.
+    // Then the next candidate (stored ones first, longest first; then the short ends) is set up.
+    GSM_HD void walk_end(Ctx& c, const IndexMeta& m, uint32_t start) {
+        for (;;) {
+            if (start < last_start) emit_match(c, start, cur_j, P0, cnt);
+            if (start == lb || (ncand == 0 && short_hi <= x)) { end_sweep(c); return; }
+            if (ncand != 0) {                   // stored candidate: continue from its interval at x
+                ncand--;
+                c.cand_get(ncand, cur_j, P0, cnt);
+                start = x;
+            } else {                            // short candidate: end in (x, x + K)
+                cur_j = short_hi--;
+                const uint32_t K = c.seed_k();
+                if (cur_j >= K && cur_j - K >= lb) { P0 = c.kmer(cur_j - K); mode = M_SEEDB; return; }
+                start = plain_begin(c, m);
+            }
+            if (try_walk(c, start)) return;
+        }
+    }
+
+    // backward search of q[..cur_j) from scratch; q[x:cur_j) occurs, so its last base does
+    GSM_HD uint32_t plain_begin(Ctx& c, const IndexMeta& m) {
+        const uint32_t b = c.base(cur_j - 1);
+        P0 = m.C[b]; cnt = m.cnt[b];
+        return cur_j - 1;
+    }
+
+    // Bring this pair to its next pending operation.  Returns false only when there are no more reads.
     GSM_HD bool next(Ctx& c, const IndexMeta& m) {
         while (mode == M_FETCH) {
             if (x >= L) {                   // no read in progress (initial state: x == L == 0)
@@ -142,65 +198,48 @@ struct Sweeper {
                 n_mems = 0; sweep_id = 0; x = 0; lb = 0;
                 if (L == 0) { c.finish(rid, 0); continue; }
             }
-            start_sweeps(c, m);
+            start_sweep(c, m);
         }
         return mode != M_DONE;
     }
 
-    // The walked candidate (cur_j, P0, cnt) cannot be extended beyond `start`.
-    GSM_HD void walk_end(Ctx& c, uint32_t start) {
-        if (start < last_start) emit_match(c, start, cur_j, P0, cnt);
-        if (first_walk && start != lb && ncand != 0) start_lock(c);
-        else end_sweep(c);
-    }
-
-    GSM_HD void consume(Ctx& c, const IndexMeta& m, const StepOut& r) {
-        (void)m;
-        if (mode != M_LOCK) {
-            // FWD (append q[pos] to q[x:pos)) and WALK (prepend q[pos] to q[pos+1:cur_j)) share one hot path:
-            // take the new interval, move one base, fetch it.  Only the ends of an extension branch.
-            const bool fwd = mode == M_FWD;
-            if (fwd && r.cnt_new != cnt) c.cand_put(ncand++, pos, k, cnt);     // count about to change: q[x:pos) is a candidate
-            if (r.cnt_new != 0) {
-                k += r.lt_add; P0 = r.lo_new; cnt = r.cnt_new;
-                const uint32_t last = fwd ? L - 1u : 0u;
-                if (pos != last) { pos += fwd ? 1u : 0xFFFFFFFFu; ch = c.base(pos); return; }
-                if (fwd) { pos++; c.cand_put(ncand++, pos, k, cnt); start_bwd(c); return; }    // ran off the right end
-                walk_end(c, 0u);                                                               // ran off the left end
-                return;
-            }
-            if (fwd) start_bwd(c);
-            else walk_end(c, pos + 1u);
+    // result of the pending seed-table fetch
+    GSM_HD void consume_seed(Ctx& c, const IndexMeta& m, const SeedEntry& e) {
+        if (mode == M_SEEDF) {
+            if (e.cnt == 0) { fwd_plain(c, m); return; }          // q[x:x+K) does not occur: F(x) < x + K
+            k = e.fwd_lo; P0 = e.rev_lo; cnt = e.cnt;
+            pos = x + c.seed_k();
+            short_hi = pos - 1;
+            fwd_continue(c, m);
             return;
         }
-        // M_LOCK: candidate t-1 = (cur_j, P0, cnt) was extended with q[pos]
-        if (r.cnt_new == 0) {
-            if (w == top && pos + 1 < last_start) emit_match(c, pos + 1, cur_j, P0, cnt);
-        } else if (w == top || r.cnt_new != lastkept) {
-            w--;
-            c.cand_put(w, cur_j, r.lo_new, r.cnt_new);
-            lastkept = r.cnt_new;
-        }
-        t--;
-        if (t == base_i) {                       // round finished
-            if (w == top) { end_sweep(c); return; }
-            c.cand_sync();
-            if (pos == 0) {                      // survivors ran off the left end: the longest one is the match
-                c.cand_get(top - 1, cur_j, P0, cnt);
-                if (0 < last_start) emit_match(c, 0, cur_j, P0, cnt);
-                end_sweep(c);
+        // M_SEEDB: seed of the short candidate ending at cur_j
+        if (e.cnt == 0) { walk_from(c, m, plain_begin(c, m)); return; }
+        P0 = e.fwd_lo; cnt = e.cnt;
+        walk_from(c, m, cur_j - c.seed_k());
+    }
+
+    // result of the pending FM step
+    GSM_HD void consume(Ctx& c, const IndexMeta& m, const StepOut& r) {
+        // FWD (append q[pos] to q[x:pos)) and WALK (prepend q[pos] to q[pos+1:cur_j)) share one hot path:
+        // take the new interval, move one base, fetch it.  Only the ends of an extension branch.
+        const bool fwd = mode == M_FWD;
+        if (fwd && r.cnt_new != cnt) c.cand_put(ncand++, pos, k, cnt);     // count about to change: q[x:pos) is a candidate
+        if (r.cnt_new != 0) {
+            k += r.lt_add; P0 = r.lo_new; cnt = r.cnt_new;
+            if (fwd) {
+                pos++;
+                if (pos != L) { ch = c.base(pos); return; }
+                c.cand_put(ncand++, pos, k, cnt);                          // ran off the right end
+                start_bwd(c, m);
                 return;
             }
-            base_i = w; t = top; w = top; lastkept = 0;
-            pos--;
-            ch = c.base(pos);
-            if (top - base_i == 1) {             // one survivor: finish it in registers
-                c.cand_get(top - 1, cur_j, P0, cnt);
-                mode = M_WALK;
-                return;
-            }
+            if (pos != lb && pos != 0) { pos--; ch = c.base(pos); return; }
+            walk_end(c, m, pos);                                           // reached the lower bound (or the left end)
+            return;
         }
-        c.cand_get(t - 1, cur_j, P0, cnt);
+        if (fwd) start_bwd(c, m);
+        else walk_end(c, m, pos + 1u);
     }
 };
 

@@ -200,6 +200,9 @@ class DeviceIndex:
         for c in range(5):
             d.C[c] = info.C[c]
         d.primary_fwd, d.primary_rev = info.primary_fwd, info.primary_rev
+        seed = getattr(self, "seed_table", None)
+        d.seed_K = getattr(self, "seed_K", 0) if seed is not None else 0
+        d.seed_table = seed.data_ptr() if seed is not None else None
         self.c = d
         self.n_rows = int(info.n_rows)
         self.n_bases = int(info.n_bases)
@@ -260,6 +263,30 @@ class DeviceIndex:
         self._bind()
         return self
 
+    def build_seed_table(self, K=None):
+        """Seed table of the sweep kernel (gsm_seed_table_build): 4^K x 16 bytes; K defaults to the largest value with
+        about 16+ expected occurrences per k-mer (12 at 1 Gbp, 10 at 100 Mbp).  Results never depend on it."""
+        if K is None:
+            K = 1
+            while K < 13 and self.n_rows / 4.0 ** (K + 1) >= 10.0:
+                K += 1
+        if self.rev is None:
+            raise ValueError("the seed table needs the reverse-text buckets")
+        K = int(K)
+        self.seed_table, self.seed_K = None, 0
+        self._bind()
+        t = torch.empty((1 << (2 * K)) * 4, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            capi.check(capi.lib.gsm_seed_table_build(C.byref(self.c), K, _ptr(t), _stream()))
+        self.seed_table, self.seed_K = t, K
+        self._bind()
+        return self
+
+    def drop_seed_table(self):
+        self.seed_table, self.seed_K = None, 0
+        self._bind()
+        return self
+
     def suffix_array_host(self):
         """fm_index["suffix_array"] (1-based values, ExactMatch.py:66) copied back from the device."""
         return self.sa.cpu().numpy().view(np.uint32)
@@ -269,7 +296,7 @@ class DeviceIndex:
         return {"": int(i.n_rows), "$": 0, "A": int(i.C[0]), "C": int(i.C[1]), "G": int(i.C[2]), "T": int(i.C[3])}
 
     def bytes(self):
-        return sum(t.numel() * t.element_size() for t in (self.fwd, self.rev, self.sa, self.text) if t is not None)
+        return sum(t.numel() * t.element_size() for t in (self.fwd, self.rev, self.sa, self.text, getattr(self, "seed_table", None)) if t is not None)
 
 
 class ReadBatch:
@@ -316,6 +343,57 @@ class ReadBatch:
             len_t = torch.from_numpy(np.ascontiguousarray(lens).view(np.int32)).pin_memory()
             off, lens = off_t.numpy().view(np.uint32), len_t.numpy().view(np.uint32)
         return cls(packed, off, lens, max(1, int(lens.max())) if n else 1, read_id_base)
+
+    @classmethod
+    def from_device_bases(cls, bases, read_len=None, base_off=None, ascii=False, read_id_base=0, check=True):
+        """Pack ON THE GPU (gsm_pack_reads_device).  bases: torch uint8 on the device -- an (n, read_len) matrix of
+        codes 0..3 / ASCII bytes, or a flat buffer with base_off (n+1 int64 offsets, numpy or torch).  The batch
+        lives on the device; to_host() makes the (pinned) host copies the end-to-end paths start from."""
+        require_cuda()
+        dev = bases.device
+        if base_off is None:
+            if bases.dim() == 2:
+                read_len = int(bases.shape[1])
+            n = bases.numel() // int(read_len)
+            lens = np.full(n, int(read_len), np.uint32)
+            cpr = (int(read_len) + 63) // 64
+            off = (np.arange(n + 1, dtype=np.int64) * cpr)
+            boff_t = None
+        else:
+            boff = np.asarray(base_off.cpu() if isinstance(base_off, torch.Tensor) else base_off, np.int64)
+            n = len(boff) - 1
+            lens = np.diff(boff).astype(np.uint32)
+            off = np.concatenate([[0], np.cumsum((lens.astype(np.int64) + 63) // 64)])
+            boff_t = torch.from_numpy(boff).to(dev)
+        if n and int(off[-1]) >= 1 << 32:
+            raise capi.GsmError(capi.E_CAPACITY, "read batch too large for 32-bit chunk offsets")
+        self = cls(None, off.astype(np.uint32), lens, max(1, int(lens.max())) if n else 1, read_id_base)
+        with torch.cuda.device(dev):
+            self.chunk_off = torch.from_numpy(self.chunk_off_host.view(np.int32)).to(dev)
+            self.packed = torch.empty(int(off[-1]) * 16 + 16, dtype=torch.uint8, device=dev)
+            self.packed[int(off[-1]) * 16:].zero_()
+            self.len = torch.empty(max(n, 1), dtype=torch.int32, device=dev)[:n]
+            scratch = torch.zeros(1, dtype=torch.int64, device=dev)
+            flat = bases.contiguous().view(-1)
+            capi.check(capi.lib.gsm_pack_reads_device(_ptr(flat), _ptr(boff_t), 0 if boff_t is not None else int(read_len), _ptr(self.chunk_off), n,
+                                                      1 if ascii else 0, _ptr(self.packed), _ptr(self.len), _ptr(scratch), _stream()))
+            if check:
+                try:
+                    capi.check(capi.lib.gsm_pack_reads_device_check(_ptr(scratch), _stream()))
+                except ValueError as e:
+                    raise BaseError(str(e)) from None
+        return self
+
+    def to_host(self, pin=True):
+        """Host copies of a device-built batch (pinned by default): what Engine.run / PipelinedEngine.run copy in."""
+        def grab(t):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=bool(pin))
+            h.copy_(t)
+            return h.numpy()
+        self.packed_host = grab(self.packed)
+        self.chunk_off_host = grab(self.chunk_off).view(np.uint32)
+        self.len_host = grab(self.len).view(np.uint32)
+        return self
 
     def to(self, device, non_blocking=False):
         self.packed = torch.from_numpy(self.packed_host).to(device, non_blocking=non_blocking)
@@ -581,9 +659,13 @@ class _ReadView:
 
 
 class PipelinedEngine:
-    """Host reads in, host records out, with the PCIe copies hidden behind the kernels: the batch
-    is cut into chunks that alternate between two workspaces on two CUDA streams, so chunk i+1's
-    H2D and chunk i-1's D2H overlap chunk i's sweep/select kernels.  Inputs must be pinned."""
+    """Host reads in, host records out, with the PCIe copies hidden behind the kernels.  The batch is cut into
+    chunks; three CUDA streams run concurrently:
+      copy-in   every chunk's H2D is queued up front (the device input buffers hold the whole batch),
+      compute   [2-bit packing,] sweep, select, scan, gather of chunk i, in order, alternating between two workspaces,
+      copy-out  records / offsets / status of chunk i to pinned host memory as soon as its record count is known.
+    The compute stream only waits for chunk i's H2D and for the D2H that frees its workspace (chunk i-2), so neither
+    copy direction ever sits between two sweeps.  Inputs must be pinned."""
 
     def __init__(self, index: DeviceIndex, max_reads, max_len, n_chunks=8, mems_per_read=24, recs_per_read=16):
         require_cuda()
@@ -591,13 +673,15 @@ class PipelinedEngine:
         self.n_chunks = max(2, int(n_chunks))
         self.chunk_reads = (int(max_reads) + self.n_chunks - 1) // self.n_chunks
         self.engines = [Engine(index, self.chunk_reads, max_len, mems_per_read, recs_per_read) for _ in range(2)]
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+        self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(device=self.device) for _ in range(3))
         self.max_reads, self.max_len = int(max_reads), int(max_len)
         self._dev = {}
         self._pin = {}
         self._cnt_pin = [torch.zeros(8, dtype=torch.int64).pin_memory() for _ in range(2)]
         self.last_d2h_bytes = 0
+        self.last_h2d_bytes = 0
         self.kernel_launches = 0
+        self.pack_launches = 0
 
     def _buf(self, store, name, nbytes, pinned):
         b = store.get(name)
@@ -609,6 +693,7 @@ class PipelinedEngine:
         return b
 
     def run(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None):
+        """Packed host reads in (pinned), host records out."""
         n = reads.n
         if n > self.max_reads or reads.max_len > self.max_len:
             raise ValueError("batch exceeds the engine's workspace")
@@ -619,23 +704,87 @@ class PipelinedEngine:
         reads.chunk_off = self._buf(self._dev, "coff", hco.numel() * 4, False)[: hco.numel() * 4].view(torch.int32)
         reads.len = self._buf(self._dev, "len", max(hln.numel(), 1) * 4, False)[: hln.numel() * 4].view(torch.int32)
         co = reads.chunk_off_host
-        bounds = [min(n, i * self.chunk_reads) for i in range(self.n_chunks + 1)]
-        bounds = sorted(set(bounds))
+
+        def copy_in(lo, hi):
+            b0, b1 = int(co[lo]) * 16, int(co[hi]) * 16 + 16
+            reads.packed[b0:b1].copy_(hp[b0:b1], non_blocking=True)
+            reads.chunk_off[lo:hi + 1].copy_(hco[lo:hi + 1], non_blocking=True)
+            reads.len[lo:hi].copy_(hln[lo:hi], non_blocking=True)
+
+        self.last_h2d_bytes = reads.h2d_bytes()
+        return self._run_chunks(method, n, copy_in, lambda lo, hi: _ReadView(reads, lo, hi), min_len, K, lut, rmi)
+
+    def run_ascii(self, method, bases, read_len, min_len=1, K=0, lut=None, rmi: RmiParams = None, read_id_base=0):
+        """RAW read bytes in, host records out: `bases` is a pinned uint8 tensor of n x read_len ASCII characters
+        (what a FASTQ parser hands over).  Each chunk crosses PCIe as 1 byte/base and is 2-bit packed on the GPU
+        (gsm_pack_reads_device) right before its sweep.  Raises BaseError if a read holds a non-ACGT character
+        (the reference's KeyError, ExactMatch.py:139)."""
+        read_len = int(read_len)
+        n = bases.numel() // read_len
+        if n > self.max_reads or read_len > self.max_len:
+            raise ValueError("batch exceeds the engine's workspace")
+        flat = bases.view(-1)
+        cpr = (read_len + 63) // 64
+        key = (cpr, n)
+        if self._dev.get("coff_key") != key:                 # chunk offsets of a fixed-length batch are arithmetic: built once
+            self._dev["coff_fixed"] = (torch.arange(n + 1, dtype=torch.int64, device=self.device) * cpr).to(torch.int32)
+            self._dev["coff_key"] = key
+        coff = self._dev["coff_fixed"]
+        packed = self._buf(self._dev, "packed", n * cpr * 16 + 16, False)
+        lens = self._buf(self._dev, "len", max(n, 1) * 4, False)[: n * 4].view(torch.int32)
+        raw = self._buf(self._dev, "raw", max(n * read_len, 1), False)
+        bad = self._buf(self._dev, "bad", 8 * (self.n_chunks + 1), False)[: 8 * (self.n_chunks + 1)].view(torch.int64)
+        slot = {}
+        holder = ReadBatch(None, None, np.zeros(0, np.uint32), read_len, read_id_base)
+        holder.n, holder.packed, holder.chunk_off, holder.len = n, packed, coff, lens
+
+        def copy_in(lo, hi):
+            raw[lo * read_len: hi * read_len].copy_(flat[lo * read_len: hi * read_len], non_blocking=True)
+
+        def prep(lo, hi):
+            capi.check(capi.lib.gsm_pack_reads_device(C.c_void_p(raw.data_ptr() + lo * read_len), None, read_len, C.c_void_p(coff.data_ptr() + 4 * lo),
+                                                      hi - lo, 1, _ptr(packed), C.c_void_p(lens.data_ptr() + 4 * lo),
+                                                      C.c_void_p(bad.data_ptr() + 8 * len(slot)), _stream()))
+            slot[len(slot)] = lo
+            self.pack_launches += 1
+            return _ReadView(holder, lo, hi)
+
+        self.last_h2d_bytes = n * read_len
+        res = self._run_chunks(method, n, copy_in, prep, min_len, K, lut, rmi)
+        b = bad.cpu().numpy()[: len(slot)]
+        if (b != -1).any():
+            k = int(np.nonzero(b != -1)[0][0])
+            raise BaseError(f"non-ACGT base in read {slot[k] + int(b[k])}")
+        return res
+
+    def _run_chunks(self, method, n, copy_in, prep, min_len, K, lut, rmi):
+        bounds = sorted(set(min(n, i * self.chunk_reads) for i in range(self.n_chunks + 1)))
+        n_ch = len(bounds) - 1
         est = self.engines[0].rec_cap * 16
         out_rec = self._buf(self._pin, "rec", max(est, 1 << 20), True)
         out_off = self._buf(self._pin, "off", (n + 1) * 8, True)
         out_st = self._buf(self._pin, "st", max(n, 1), True)
-        main = torch.cuda.current_stream()
         start_ev = torch.cuda.Event()
-        start_ev.record(main)
-        pending = []      # (engine idx, lo, hi, event)
+        start_ev.record(torch.cuda.current_stream())
+        ev_in = []
+        with torch.cuda.stream(self.s_in):                     # every chunk's H2D, queued up front
+            self.s_in.wait_event(start_ev)
+            for i in range(n_ch):
+                copy_in(bounds[i], bounds[i + 1])
+                ev = torch.cuda.Event()
+                ev.record(self.s_in)
+                ev_in.append(ev)
+        self.s_comp.wait_event(start_ev)
+        self.s_out.wait_event(start_ev)
+        pending = []      # (engine idx, lo, hi, compute-done event)
+        ev_out = {}       # chunk index -> its D2H-done event
         rec_total = 0
         mems_total = 0
         chunk_rec = []
 
         def drain(item):
             nonlocal rec_total, mems_total, out_rec
-            e, lo, hi, ev = item
+            i, e, lo, hi, ev = item
             ev.synchronize()
             c = self._cnt_pin[e].numpy()
             if c[2] != 0:
@@ -650,41 +799,43 @@ class PipelinedEngine:
                 out_rec = grown
                 self._pin["rec"] = grown
             eng = self.engines[e]
-            with torch.cuda.stream(self.streams[e]):
+            with torch.cuda.stream(self.s_out):                # the host has seen ev: the chunk's kernels are done
                 out_rec[rec_total * 16:(rec_total + n_rec) * 16].copy_(eng.records[: n_rec * 16], non_blocking=True)
                 out_off[lo * 8:hi * 8].copy_(eng.rec_off[: hi - lo].view(torch.uint8), non_blocking=True)
                 out_st[lo:hi].copy_(eng.read_status[: hi - lo], non_blocking=True)
+                d = torch.cuda.Event()
+                d.record(self.s_out)
+                ev_out[i] = d
             chunk_rec.append((lo, hi, rec_total, n_rec))
             rec_total += n_rec
 
-        for i in range(len(bounds) - 1):
+        for i in range(n_ch):
             lo, hi = bounds[i], bounds[i + 1]
             e = i % 2
-            if len(pending) == 2:                 # this workspace's previous chunk must be fully drained first
+            if len(pending) == 2:                 # workspace e still holds chunk i-2: drain it (count -> D2H) first
                 drain(pending.pop(0))
-            s = self.streams[e]
             eng = self.engines[e]
-            with torch.cuda.stream(s):
-                s.wait_event(start_ev)
-                b0, b1 = int(co[lo]) * 16, int(co[hi]) * 16 + 16
-                reads.packed[b0:b1].copy_(hp[b0:b1], non_blocking=True)
-                reads.chunk_off[lo:hi + 1].copy_(hco[lo:hi + 1], non_blocking=True)
-                reads.len[lo:hi].copy_(hln[lo:hi], non_blocking=True)
-                eng.launch(method, _ReadView(reads, lo, hi), min_len, K, lut, rmi)
+            with torch.cuda.stream(self.s_comp):
+                self.s_comp.wait_event(ev_in[i])
+                if i - 2 in ev_out:
+                    self.s_comp.wait_event(ev_out[i - 2])
+                view = prep(lo, hi)
+                eng.launch(method, view, min_len, K, lut, rmi)
                 self._cnt_pin[e].copy_(eng.counters, non_blocking=True)
                 ev = torch.cuda.Event()
-                ev.record(s)
-            pending.append((e, lo, hi, ev))
+                ev.record(self.s_comp)
+            pending.append((i, e, lo, hi, ev))
         while pending:
             drain(pending.pop(0))
-        for s in self.streams:
-            s.synchronize()
+        self.s_out.synchronize()
+        self.s_comp.synchronize()
+        torch.cuda.current_stream().wait_stream(self.s_out)
         # chunk-local offsets -> global offsets (host, n+1 int64 adds)
         offs = out_off.numpy()[: (n + 1) * 8].view(np.int64)
         for lo, hi, base, n_rec in chunk_rec:
             offs[lo:hi] += base
         offs[n] = rec_total
-        self.kernel_launches = sum(e.kernel_launches for e in self.engines)
+        self.kernel_launches = sum(e.kernel_launches for e in self.engines) + self.pack_launches
         self.last_d2h_bytes = rec_total * 16 + (n + 1) * 8 + n + 64 * len(chunk_rec)
         recs = out_rec.numpy()[: rec_total * 16].view(RECORD_DTYPE)
         return SmemResult(recs, offs, out_st.numpy()[:n], mems_total)

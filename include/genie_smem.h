@@ -123,6 +123,19 @@ int gsm_index_build_device(const uint32_t* text2bit, uint64_t n_bases, uint32_t 
                            void* rev_buckets, void* workspace, uint64_t workspace_bytes, gsm_index_info* info,
                            void* stream);
 
+/* ------------------------------------------------------------------ device-side read ingest */
+/* Pack reads ON THE GPU: bases (device; ASCII ACGT if ascii != 0, else codes 0..3), read r = bytes
+ * [base_off[r], base_off[r+1]) (device uint64, n_reads+1) or, with base_off == NULL, fixed_len bytes at
+ * r*fixed_len; chunk_off (device, n_reads+1, 16-byte chunks: exclusive scan of ceil(len/64)) as in
+ * gsm_pack_reads; packed receives chunk_off[n_reads]*16 bytes; len_out (optional, device) the lengths.
+ * Replaces the per-string query path (ExactMatch.load_query, ExactMatch.py:104-108) for batches.
+ * Asynchronous; gsm_pack_reads_device_check(scratch8) synchronises and returns GSM_E_INVALID if a read
+ * held a non-ACGT byte (the reference raises KeyError, ExactMatch.py:139). */
+int gsm_pack_reads_device(const void* bases, const uint64_t* base_off, uint32_t fixed_len, const uint32_t* chunk_off,
+                          uint64_t n_reads, uint32_t ascii, void* packed, uint32_t* len_out, uint64_t* scratch8,
+                          void* stream);
+int gsm_pack_reads_device_check(const uint64_t* scratch8, void* stream);
+
 /* ------------------------------------------------------------------ device-side views */
 typedef struct {
     uint64_t n_rows;
@@ -134,7 +147,9 @@ typedef struct {
     uint32_t C[5];
     uint32_t primary_fwd;
     uint32_t primary_rev;
-    uint32_t reserved;
+    uint32_t seed_K;          /* K of seed_table (1..14), ignored when seed_table is NULL */
+    const void* seed_table;   /* device, optional: gsm_seed_table_build output (4^K x 16 bytes); lets the sweep
+                                 kernel replace the first K steps of every extension by one fetch */
 } gsm_dev_index;
 
 typedef struct {
@@ -213,6 +228,11 @@ int gsm_sa_lookup_batch(const gsm_dev_index* idx, uint64_t n, const uint32_t* ro
 /* Dense k-mer table: entry[code] = {lo, cnt} for every 4^K code, cnt == 0 for absent k-mers.
  * Replaces LUT.generate_lut (LUT.py:15-35); table: 4^K * 8 bytes of device memory. */
 int gsm_lut_build(const gsm_dev_index* idx, uint32_t K, uint32_t* table, void* stream);
+
+/* Seed table for the sweep kernel: entry[code] = {rows lo of the k-mer on the text index, count, rows lo of the
+ * reversed k-mer on the reversed-text index, 0}, 16 bytes per 4^K code.  The reference's LUT idea (LUT.py:15-35)
+ * applied to both directions of the bidirectional extension; results never depend on it. */
+int gsm_seed_table_build(const gsm_dev_index* idx, uint32_t K, void* table, void* stream);
 
 /* The three SMEM entry points.  Phase 1 (this call) runs the kernels and leaves per-read
  * record counts in ws->rec_cnt, their exclusive scan in ws->rec_off and the total in

@@ -26,6 +26,12 @@ struct HostIndex {
 
 struct SweepCtx {
     const uint32_t* words = nullptr;
+    uint32_t K = 0;                      // seed table K (0 = none)
+    uint32_t seed_k() const { return K; }
+    uint32_t kmer(uint32_t pos) const {
+        auto rd = [&](uint64_t w) { return words[w]; };
+        return (uint32_t)kmer_code(rd, pos, K);
+    }
     std::vector<uint32_t> cj, clo, ccnt;
     std::vector<MemEntry> mems;
     bool fetched = false;
@@ -156,20 +162,28 @@ struct EmuIndex {
 
 // Maximal exact matches of one read: out gets 4 x u32 per match (start, end, lo, cnt), sorted by
 // end.  Returns the number of matches.
-int emu_sweep(const EmuIndex* ei, const uint32_t* words, uint32_t L, uint32_t* out, uint32_t cap, uint64_t* n_steps) {
+int emu_sweep(const EmuIndex* ei, const uint32_t* words, uint32_t L, uint32_t* out, uint32_t cap, uint64_t* n_steps, uint32_t seed_K,
+              const void* seed_tab) {
     HostIndex ix{(const Half*)ei->fwd, (const Half*)ei->rev, ei->sa, ei->text, {}, ei->n_bases};
     for (int c = 0; c < 4; ++c) { ix.meta.C[c] = ei->C[c]; ix.meta.cnt[c] = ei->cnt[c]; }
     ix.meta.prim_f = ei->prim_f; ix.meta.prim_r = ei->prim_r; ix.meta.n_rows = ei->n_rows;
-    SweepCtx ctx; ctx.words = words; ctx.L = L;
+    SweepCtx ctx; ctx.words = words; ctx.L = L; ctx.K = seed_tab ? seed_K : 0;
     Sweeper<SweepCtx> sw;
     uint64_t steps = 0;
     for (;;) {
         if (!sw.next(ctx, ix.meta)) break;
+        if (sw.pending_seed()) {
+            const SeedEntry* t = (const SeedEntry*)seed_tab;
+            g_cnt[6]++;                                                      // [6] seed-table fetches
+            sw.consume_seed(ctx, ix.meta, t[sw.P0]);
+            ++steps;
+            continue;
+        }
         const bool rev = sw.on_reverse();
         const Half* bk = rev ? ix.rev : ix.fwd;
         auto load = [&](uint64_t idx) { return bk[idx]; };
         StepOut r = step_single(load, sw.P0, sw.P0 + sw.cnt, sw.ch, ix.meta.C[sw.ch], rev ? ix.meta.prim_r : ix.meta.prim_f);
-        g_cnt[4 + (sw.mode == M_FWD ? 0 : sw.mode == M_WALK ? 1 : 2)]++;      // [4] FWD [5] WALK [6] LOCK steps
+        g_cnt[4 + (sw.mode == M_FWD ? 0 : 1)]++;                             // [4] FWD [5] WALK steps
         { uint32_t b0, r0, b1, r1; split192(sw.P0, b0, r0); split192(sw.P0 + sw.cnt, b1, r1); g_cnt[7] += (b0 != b1); }   // [7] steps touching two buckets
         sw.consume(ctx, ix.meta, r);
         ++steps;
@@ -188,15 +202,19 @@ int emu_sweep(const EmuIndex* ei, const uint32_t* words, uint32_t L, uint32_t* o
 // -1 if the reference would raise, -2 if the read is shorter than K.
 int emu_smem(const EmuIndex* ei, int method, const uint32_t* words, uint32_t L, uint32_t min_len, uint32_t K,
              const uint32_t* lut, uint32_t n_levels, const uint32_t* level_sizes, const double* coef,
-             const double* intercept, uint32_t* out, uint32_t cap) {
+             const double* intercept, uint32_t* out, uint32_t cap, uint32_t seed_K, const void* seed_tab) {
     HostIndex ix{(const Half*)ei->fwd, (const Half*)ei->rev, ei->sa, ei->text, {}, ei->n_bases};
     for (int c = 0; c < 4; ++c) { ix.meta.C[c] = ei->C[c]; ix.meta.cnt[c] = ei->cnt[c]; }
     ix.meta.prim_f = ei->prim_f; ix.meta.prim_r = ei->prim_r; ix.meta.n_rows = ei->n_rows;
     if (method != 0 && L < K) return -2;
-    SweepCtx ctx; ctx.words = words; ctx.L = L;
+    SweepCtx ctx; ctx.words = words; ctx.L = L; ctx.K = seed_tab ? seed_K : 0;
     Sweeper<SweepCtx> sw;
     for (;;) {
         if (!sw.next(ctx, ix.meta)) break;
+        if (sw.pending_seed()) {
+            sw.consume_seed(ctx, ix.meta, ((const SeedEntry*)seed_tab)[sw.P0]);
+            continue;
+        }
         const bool rev = sw.on_reverse();
         const Half* bk = rev ? ix.rev : ix.fwd;
         auto load = [&](uint64_t idx) { return bk[idx]; };
@@ -235,6 +253,30 @@ void emu_lut_build(const EmuIndex* ei, uint32_t K, uint32_t* table) {
             lo = r.lo_new; cnt = r.cnt_new;
         }
         table[2 * code] = lo; table[2 * code + 1] = cnt;
+    }
+}
+
+// Seed table exactly as the device builder computes it (k_seed_build): per code the k-mer's rows on the text index
+// and the reversed k-mer's rows on the reversed-text index.
+void emu_seed_build(const EmuIndex* ei, uint32_t K, uint32_t* table) {
+    const Half* fwd = (const Half*)ei->fwd;
+    const Half* rev = (const Half*)ei->rev;
+    auto lf = [&](uint64_t idx) { return fwd[idx]; };
+    auto lr = [&](uint64_t idx) { return rev[idx]; };
+    uint64_t ncodes = 1ull << (2 * K);
+    for (uint64_t code = 0; code < ncodes; ++code) {
+        uint32_t lo = 0, cnt = ei->n_rows, rlo = 0, rcnt = ei->n_rows;
+        for (uint32_t t = 0; t < K && cnt; ++t) {
+            uint32_t c = (uint32_t)(code >> (2 * t)) & 3u;                 // last base first: backward search on the text
+            StepOut r = step_single(lf, lo, lo + cnt, c, ei->C[c], ei->prim_f);
+            lo = r.lo_new; cnt = r.cnt_new;
+        }
+        for (uint32_t t = 0; t < K && rcnt && cnt; ++t) {
+            uint32_t c = (uint32_t)(code >> (2 * (K - 1 - t))) & 3u;       // first base first: backward search of the reversed k-mer
+            StepOut r = step_single(lr, rlo, rlo + rcnt, c, ei->C[c], ei->prim_r);
+            rlo = r.lo_new; rcnt = r.cnt_new;
+        }
+        table[4 * code] = lo; table[4 * code + 1] = cnt; table[4 * code + 2] = cnt ? rlo : 0; table[4 * code + 3] = 0;
     }
 }
 

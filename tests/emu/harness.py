@@ -38,8 +38,10 @@ class Emu:
         from genie_smem_b200 import _capi as capi
         self.lib = C.CDLL(build())
         P, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
-        self.lib.emu_sweep.argtypes = [C.POINTER(EmuIndex), P, u32, P, u32, C.POINTER(u64)]
-        self.lib.emu_smem.argtypes = [C.POINTER(EmuIndex), C.c_int, P, u32, u32, u32, P, u32, P, P, P, P, u32]
+        self.lib.emu_sweep.argtypes = [C.POINTER(EmuIndex), P, u32, P, u32, C.POINTER(u64), u32, P]
+        self.lib.emu_smem.argtypes = [C.POINTER(EmuIndex), C.c_int, P, u32, u32, u32, P, u32, P, P, P, P, u32, u32, P]
+        self.lib.emu_seed_build.argtypes = [C.POINTER(EmuIndex), u32, P]
+        self.lib.emu_counters.argtypes = [P, C.c_int]
         self.lib.emu_lut_build.argtypes = [C.POINTER(EmuIndex), u32, P]
         self.lib.emu_rmi_lookup.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u64, C.POINTER(C.c_double),
                                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -68,6 +70,25 @@ class Emu:
         self.e = e
         self.n_rows = int(info.n_rows)
         self._lut = {}
+        self._seed = {}
+        self.seed_K = 0          # seed table used by sweep()/smem(); 0 = plain stepping
+
+    def seed_table(self, K):
+        if K not in self._seed:
+            t = np.zeros(4 << (2 * K), np.uint32)
+            self.lib.emu_seed_build(C.byref(self.e), K, t.ctypes.data)
+            self._seed[K] = t
+        return self._seed[K]
+
+    def _seed_args(self):
+        if not self.seed_K:
+            return 0, None
+        return self.seed_K, self.seed_table(self.seed_K).ctypes.data
+
+    def counters(self, reset=True):
+        out = np.zeros(8, np.uint64)
+        self.lib.emu_counters(out.ctypes.data, 1 if reset else 0)
+        return out
 
     def pack_read(self, q):
         lens = np.asarray([len(q)], np.uint32)
@@ -81,7 +102,8 @@ class Emu:
         w = self.pack_read(q)
         out = np.zeros(4 * (len(q) + 1), np.uint32)
         steps = C.c_uint64()
-        n = self.lib.emu_sweep(C.byref(self.e), w.ctypes.data, len(q), out.ctypes.data, len(q) + 1, C.byref(steps))
+        sk, st = self._seed_args()
+        n = self.lib.emu_sweep(C.byref(self.e), w.ctypes.data, len(q), out.ctypes.data, len(q) + 1, C.byref(steps), sk, st)
         return [tuple(int(x) for x in out[4 * k:4 * k + 4]) for k in range(n)], steps.value
 
     def lut(self, K):
@@ -97,16 +119,17 @@ class Emu:
         cap = len(q) + 1
         out = np.zeros(6 * cap, np.uint32)
         lut_p = self.lut(K).ctypes.data if method == 1 else None
+        sk, st = self._seed_args()
         if method == 2:
             K = rmi["K"]
             ls = np.asarray(rmi["level_sizes"], np.uint32)
             coef = np.ascontiguousarray(rmi["coef"], np.float64)
             icpt = np.ascontiguousarray(rmi["intercept"], np.float64)
             n = self.lib.emu_smem(C.byref(self.e), 2, w.ctypes.data, len(q), min_len, K, None, len(ls), ls.ctypes.data,
-                                  coef.ctypes.data, icpt.ctypes.data, out.ctypes.data, cap)
+                                  coef.ctypes.data, icpt.ctypes.data, out.ctypes.data, cap, sk, st)
         else:
             n = self.lib.emu_smem(C.byref(self.e), method, w.ctypes.data, len(q), min_len, K, lut_p, 0, None, None, None,
-                                  out.ctypes.data, cap)
+                                  out.ctypes.data, cap, sk, st)
         if n == -1:
             return "raises"
         if n == -2:

@@ -1,0 +1,95 @@
+"""Device-side read ingest (gsm_pack_reads_device, PipelinedEngine.run_ascii) against the host packer and the
+packed-input paths: identical packed bytes, identical records."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gs():
+    import genie_smem_b200 as g
+    return g
+
+
+@pytest.fixture(scope="module")
+def setup(gs):
+    rng = np.random.default_rng(21)
+    text = "".join("ACGT"[c] for c in rng.integers(0, 4, 400_000))
+    idx = gs.DeviceIndex(gs.HostIndex.build(text))
+    reads = []
+    for _ in range(5000):
+        L = 151
+        p = int(rng.integers(0, len(text) - L))
+        q = list(text[p:p + L])
+        for k in np.nonzero(rng.random(L) < 0.015)[0]:
+            q[k] = "ACGT"[("ACGT".index(q[k]) + 1) % 4]
+        reads.append("".join(q))
+    return text, idx, reads
+
+
+def test_device_pack_fixed_length_equals_host_pack(gs, setup):
+    import torch
+    _, _, reads = setup
+    host = gs.ReadBatch.from_strings(reads)
+    codes = np.frombuffer("".join(reads).encode(), np.uint8).reshape(len(reads), -1)
+    asc = torch.from_numpy(codes.copy()).cuda()
+    dev = gs.ReadBatch.from_device_bases(asc, ascii=True).to_host(pin=False)
+    assert np.array_equal(dev.chunk_off_host, host.chunk_off_host)
+    assert np.array_equal(dev.len_host, host.len_host)
+    assert np.array_equal(dev.packed_host, host.packed_host)
+    lut = np.zeros(256, np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        lut[ch] = i
+    dev2 = gs.ReadBatch.from_device_bases(torch.from_numpy(lut[codes]).cuda()).to_host(pin=False)
+    assert np.array_equal(dev2.packed_host, host.packed_host)
+
+
+def test_device_pack_ragged_equals_host_pack(gs):
+    import torch
+    rng = np.random.default_rng(3)
+    reads = ["".join("ACGT"[c] for c in rng.integers(0, 4, int(L))) for L in rng.integers(1, 400, 3000)]
+    reads += ["A", "ACGT" * 16, "T" * 64, "G" * 65, "C" * 63]
+    host = gs.ReadBatch.from_strings(reads)
+    flat = torch.from_numpy(np.frombuffer("".join(reads).encode(), np.uint8).copy()).cuda()
+    off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
+    dev = gs.ReadBatch.from_device_bases(flat, base_off=off, ascii=True).to_host(pin=False)
+    assert np.array_equal(dev.chunk_off_host, host.chunk_off_host)
+    assert np.array_equal(dev.len_host, host.len_host)
+    assert np.array_equal(dev.packed_host, host.packed_host)
+
+
+def test_device_pack_rejects_non_acgt(gs):
+    import torch
+    reads = ["ACGTACGT", "ACGNACGT", "TTTTTTTT"]
+    asc = torch.from_numpy(np.frombuffer("".join(reads).encode(), np.uint8).reshape(3, 8).copy()).cuda()
+    with pytest.raises(KeyError):
+        gs.ReadBatch.from_device_bases(asc, ascii=True)
+
+
+@pytest.mark.parametrize("method", ["bwa", "lut"])
+def test_run_ascii_equals_packed_paths(gs, setup, method):
+    import torch
+    _, idx, reads = setup
+    m = {"bwa": gs.METHOD_BWA, "lut": gs.METHOD_LUT}[method]
+    kw = {"min_len": 1} if method == "bwa" else {"K": 8, "lut": gs.lut_build(idx, 8)}
+    plain = gs.Engine(idx, len(reads), 151).run(m, gs.ReadBatch.from_strings(reads), **kw)
+    pipe = gs.PipelinedEngine(idx, len(reads), 151, n_chunks=5)
+    asc = torch.from_numpy(np.frombuffer("".join(reads).encode(), np.uint8).reshape(len(reads), -1).copy()).pin_memory()
+    for _ in range(2):                 # second call reuses every cached buffer
+        got = pipe.run_ascii(m, asc, 151, **kw)
+        assert np.array_equal(got.records, plain.records)
+        assert np.array_equal(got.offsets, plain.offsets)
+    packed = pipe.run(m, gs.ReadBatch.from_strings(reads, pin=True), **kw)
+    assert np.array_equal(packed.records, plain.records)
+
+
+def test_run_ascii_rejects_non_acgt(gs, setup):
+    import torch
+    _, idx, reads = setup
+    bad = list(reads[:600])
+    bad[417] = bad[417][:70] + "N" + bad[417][71:]
+    asc = torch.from_numpy(np.frombuffer("".join(bad).encode(), np.uint8).reshape(len(bad), -1).copy()).pin_memory()
+    pipe = gs.PipelinedEngine(idx, len(bad), 151, n_chunks=4)
+    with pytest.raises(KeyError, match="417"):
+        pipe.run_ascii(gs.METHOD_BWA, asc, 151)

@@ -336,3 +336,74 @@ def test_low_complexity_reads_spill_the_candidate_cache(gs):
     assert _dicts(reads, s.get_SMEMS_batch(reads, 1)) == _oracle_dicts(text, sa, 0, reads, min_len=1)
     s.lut.generate_lut(4)
     assert _dicts(reads, s.get_smems_lut_batch(reads)) == _oracle_dicts(text, sa, 1, reads, K=4)
+
+
+def test_seed_table_equals_host_restatement(gs, matchers):
+    """k_seed_build against the host-compiled builder of tests/emu (same fm_core.cuh arithmetic)."""
+    from tests.emu.harness import Emu
+    gidx, m = matchers["medium_data"]
+    idx = m.device_index
+    try:
+        for K in (1, 3, 6):
+            idx.build_seed_table(K)
+            t = idx.seed_table.cpu().numpy().view(np.uint32)
+            assert np.array_equal(t, Emu(gidx["text"]).seed_table(K))
+    finally:
+        idx.drop_seed_table()
+
+
+@pytest.mark.parametrize("seed_K", [1, 4, 7, None])
+def test_seed_table_changes_nothing(gs, seed_K):
+    """The seed table is an accelerator of the sweep: maximal-match lists and the records of every method are
+    identical with and without it (4 Mbp reference, 20k reads of mixed kinds, K from tiny to auto)."""
+    L = 151
+    ref, reads, _ = _synthetic(4_000_000, 20_000, L, 77, 0.012)
+    rng = np.random.default_rng(8)
+    reads[:2000] = rng.integers(0, 4, (2000, L), dtype=np.uint8)          # uniform random reads
+    reads[2000:2100, 40:] = 0                                             # poly-A tails
+    idx = gs.DeviceIndex.build_on_device(ref)
+    batch = gs.ReadBatch.from_codes(reads, L)
+    e = gs.Engine(idx, len(reads), L, mems_per_read=64, recs_per_read=64)
+    lut = gs.lut_build(idx, 9)
+
+    def run_all():
+        out = []
+        for method, kw in ((gs.METHOD_BWA, {"min_len": 1}), (gs.METHOD_BWA, {"min_len": 19}), (gs.METHOD_LUT, {"K": 9, "lut": lut})):
+            r = e.run(method, batch, **kw)
+            out.append((r.records.copy(), r.offsets.copy(), r.status.copy(), r.n_mems))
+        return out
+
+    plain = run_all()
+    idx.build_seed_table(seed_K)
+    assert idx.seed_K == (seed_K if seed_K else 9)
+    seeded = run_all()
+    for a, b in zip(plain, seeded):
+        assert a[3] == b[3], "number of maximal matches"
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.parametrize("fname", GOLDEN_SETS[:3])
+def test_smem_sets_equal_reference_with_seed_table(gs, matchers, fname):
+    g = gu.load_json(fname)
+    _, m = matchers[g["ref"]]
+    try:
+        m.device_index.build_seed_table(6)
+        s = gs.SMEM(m)
+        reads = g["reads"]
+        assert _dicts(reads, s.get_SMEMS_batch(reads, 1)) == g["bwa"]["1"]
+        s.lut.generate_lut(g["K_lut"])
+        sel = [i for i, e in enumerate(g["lut"]) if e is not None]
+        assert _dicts([reads[i] for i in sel], s.get_smems_lut_batch([reads[i] for i in sel])) == [g["lut"][i] for i in sel]
+    finally:
+        m.device_index.drop_seed_table()
+
+
+def test_low_complexity_reads_with_seed_table(gs):
+    text = "A" * 300 + "C" + "A" * 120 + "G" + "ACGT" * 5 + "T" * 80 + "GATTACA" * 20
+    m = gs.ExactMatch.from_text(text)
+    sa, _ = m._host.export()
+    reads = ["A" * 151, "A" * 100 + "C" + "A" * 50, "T" * 70 + "A" * 81, "A" * 40 + "G" + "ACGT" * 3 + "T" * 60, "GATTACA" * 15 + "A" * 40, "ACG"]
+    exp = _oracle_dicts(text, sa, 0, reads, min_len=1)
+    for K in (2, 5, 8):
+        m.device_index.build_seed_table(K)
+        assert _dicts(reads, gs.SMEM(m).get_SMEMS_batch(reads, 1)) == exp

@@ -47,11 +47,16 @@ def test_rmi_lookup_logic(emus, tag, name):
             assert s == 0 and gp == pred and (glo, ghi) == (lo, hi)
 
 
+@pytest.mark.parametrize("seed_K", [0, 5, 9])
 @pytest.mark.parametrize("fname,stride", [("smems_c1_big_exact101.json.gz", 7), ("smems_c2_big_mixed101.json.gz", 3),
                                           ("smems_big_sub151.json.gz", 2), ("smems_medium_fuzz.json.gz", 2)])
-def test_sweep_and_select_logic_vs_reference(emus, fname, stride):
+def test_sweep_and_select_logic_vs_reference(emus, fname, stride, seed_K):
+    """seed_K: K of the sweep's seed table (0 = plain FM stepping); the records must not depend on it."""
     g = gu.load_json(fname)
     _, em = emus[g["ref"]]
+    em.seed_K = seed_K
+    if seed_K:
+        stride *= 2
     reads = g["reads"]
     for ml, exp in g["bwa"].items():
         for q, e in list(zip(reads, exp))[::stride]:
@@ -71,9 +76,11 @@ def test_sweep_and_select_logic_vs_reference(emus, fname, stride):
                 assert records_to_dict(q, r) == e
 
 
-def test_maximal_matches_are_exactly_the_right_maximal_LS_pairs(emus):
-    """sweep output == {(LS[j], j) : j == L or LS[j+1] > LS[j]} with true SA intervals."""
+@pytest.mark.parametrize("seed_K", [0, 1, 2, 3, 4, 6, 8])
+def test_maximal_matches_are_exactly_the_right_maximal_LS_pairs(emus, seed_K):
+    """sweep output == {(LS[j], j) : j == L or LS[j+1] > LS[j]} with true SA intervals, with and without the seed table."""
     g, em = emus["medium_data"]
+    em.seed_K = seed_K
     idx = rp.RefIndex(g["text"], g["suffix_array"])
     rng = random.Random(5)
     for _ in range(150):
@@ -109,11 +116,12 @@ ACGT = st.text(alphabet="ACGT", min_size=1, max_size=60)
 @settings(max_examples=60, deadline=None)
 @given(text=st.one_of(st.text(alphabet="ACGT", min_size=8, max_size=200),
                       st.builds(lambda u, k: (u * k)[:200], st.text(alphabet="ACGT", min_size=1, max_size=7), st.integers(2, 40))),
-       reads=st.lists(ACGT, min_size=1, max_size=6), K=st.integers(2, 5))
-def test_property_random_and_repetitive_references(text, reads, K):
+       reads=st.lists(ACGT, min_size=1, max_size=6), K=st.integers(2, 5), seed_K=st.integers(0, 6))
+def test_property_random_and_repetitive_references(text, reads, K, seed_K):
     if len(set(text)) < 4:
         text = text + "ACGT"           # parity domain: all four bases occur
     em = Emu(text)
+    em.seed_K = seed_K
     idx = rp.RefIndex(text)
     o = rp.RefSMEM(idx, lut=rp.RefLUT(idx, K))
     for q in reads:
@@ -127,5 +135,26 @@ def test_long_low_complexity_read_overflows_candidate_cache(emus):
     text = "A" * 300 + "C" + "A" * 120 + "G" + "ACGT" * 5 + "T" * 80
     em = Emu(text)
     o = rp.RefSMEM(rp.RefIndex(text))
+    for seed_K in (0, 3, 7):
+        em.seed_K = seed_K
+        for q in ["A" * 151, "A" * 100 + "C" + "A" * 50, "T" * 70 + "A" * 81, "A" * 40 + "G" + "ACGT" * 3 + "T" * 60]:
+            assert records_to_dict(q, em.smem(0, q, 1)) == gu.norm(o.get_SMEMS(q, 1))
+    em.seed_K = 0
     for q in ["A" * 151, "A" * 100 + "C" + "A" * 50, "T" * 70 + "A" * 81, "A" * 40 + "G" + "ACGT" * 3 + "T" * 60]:
         assert records_to_dict(q, em.smem(0, q, 1)) == gu.norm(o.get_SMEMS(q, 1))
+
+
+def test_rmi_vectorised_fit_matches_loop_fit():
+    """The segment-reduction trainer (large models) follows the same rule as the per-bucket loop that is pinned to
+    the reference-trained parameters: predictions agree to rounding on every key."""
+    import numpy as np
+    from genie_smem_b200.surface import RMI
+    rng = np.random.default_rng(4)
+    keys = np.sort(rng.integers(0, 4 ** 12, 60000)).astype(np.int64)
+    keys[100:140] = keys[100]                       # a flat run: zero-variance bucket
+    rows = np.arange(len(keys))
+    for experts in ([10, 100], [7], [50, 3000]):    # [50, 3000] leaves many leaf buckets empty (root aliasing)
+        a = RMI(experts).fit(keys, rows, vectorised=False)
+        b = RMI(experts).fit(keys, rows, vectorised=True)
+        assert a.level_sizes == b.level_sizes and a.coef.shape == b.coef.shape
+        assert np.abs(a.predict(keys) - b.predict(keys)).max() < 1e-6
