@@ -440,6 +440,7 @@ def train_rmi(index, K, experts, dev, max_keys=8_000_000):
     out = g.RmiParams(K, m.level_sizes, m.coef, m.intercept, dev)
     out.probe = rmi.probe
     out.c.probe = rmi.probe.data_ptr()
+    out.build_none_rows(index)
     return out
 
 

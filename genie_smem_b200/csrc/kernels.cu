@@ -14,8 +14,10 @@
 //   * k_scan_* / k_gather_records: counts -> offsets -> records in (read, emission) order.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -85,6 +87,7 @@ struct DevSelCtx {
     uint4* stage;
     uint32_t L, K, n_mems, min_len, rid, n_rec;
     bool raised;
+    bool writer;          // this thread stores the records (false for the non-leader lanes of a selection team)
 
     __device__ __forceinline__ MemEntry mem(uint32_t k) const {
         uint4 v = mems[k];
@@ -114,34 +117,38 @@ struct DevSelCtx {
         }
     }
 
-    __device__ bool seed(uint32_t c, int64_t& lo, int64_t& hi) {
+    // One probe of the RMI last-mile search (RMI_LUT.get_ref_seq, RMI_LUT.py:89-92): the 16-byte {SA value, 32-mer}
+    // record when the probe table exists (one fetch), else the suffix array and then the packed text.
+    __device__ __forceinline__ void probe_row(uint64_t row, int64_t& s, uint64_t& code64) const {
+        if (a.probe) {
+            const uint4 v = __ldg(a.probe + row);
+            s = (int64_t)v.x;
+            code64 = ((uint64_t)v.y << 32) | (uint64_t)v.z;
+        } else {
+            const uint32_t* tx = a.text;
+            auto txl = [tx](uint64_t i) { return __ldg(tx + i); };
+            s = (int64_t)__ldg(a.sa + row);
+            code64 = kmer_code(txl, (uint64_t)(s - 1), 32);
+        }
+    }
+
+    // per-thread lookups of one round (LUT path of k_select): one 8-byte gather per visited window
+    __device__ uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi) {
+        uint32_t hit = 0;
+        for (uint32_t i = 0; i < nwin; ++i) {
+            const uint32_t cpos = first ? 0u : e - i;
+            if (!(first || (i < plen && cpos + K <= L))) continue;
+            const uint2 t = __ldg(a.lut + window_code(cpos));
+            lo[i] = t.x; hi[i] = (int64_t)t.x + t.y - 1;
+            if (t.y != 0) hit |= 1u << i;
+        }
+        return hit;
+    }
+
+    __device__ __forceinline__ uint64_t window_code(uint32_t cpos) const {
         const uint32_t* w = words;
         auto rd = [w](uint64_t i) { return __ldg(w + i); };
-        const uint64_t code = kmer_code(rd, c, K);
-        if (METHOD == GSM_METHOD_LUT) {
-            const uint2 e = __ldg(a.lut + code);
-            lo = e.x; hi = (int64_t)e.x + e.y - 1;
-            return e.y != 0;
-        }
-        double pred;
-        bool r;
-        if (a.probe) {                                       // one 16-byte fetch per probe
-            TableProbe pr{a.probe};
-            RmiTable<TableProbe> t{pr, (int64_t)a.meta.n_rows, (int64_t)a.n_bases, K, false};
-            t.lookup(a.rmi, code, pred, lo, hi);
-            r = t.raised;
-        } else {                                             // suffix array, then packed text
-            const uint32_t* sa = a.sa;
-            const uint32_t* tx = a.text;
-            auto sal = [sa](uint64_t x) { return __ldg(sa + x); };
-            auto txl = [tx](uint64_t i) { return __ldg(tx + i); };
-            SaTextProbe<decltype(sal), decltype(txl)> pr{sal, txl};
-            RmiTable<decltype(pr)> t{pr, (int64_t)a.meta.n_rows, (int64_t)a.n_bases, K, false};
-            t.lookup(a.rmi, code, pred, lo, hi);
-            r = t.raised;
-        }
-        if (r) { raised = true; return false; }
-        return hi >= lo;
+        return kmer_code(rd, cpos, K);
     }
 
     __device__ bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi) {
@@ -168,9 +175,25 @@ struct DevSelCtx {
     }
 
     __device__ __forceinline__ void emit(uint32_t i, uint32_t j, int64_t lo, int64_t hi) {
-        stage[n_rec++] = make_uint4(a.read_id_base + rid, i | (j << 16), (uint32_t)lo, (uint32_t)hi);
+        if (writer) stage[n_rec] = make_uint4(a.read_id_base + rid, i | (j << 16), (uint32_t)lo, (uint32_t)hi);
+        n_rec++;
     }
 };
+
+// the sweep emits each sweep's matches longest-end first: put every segment in ascending order
+// (idempotent: a second selection pass over the same sweep finds the segment ascending)
+__device__ __forceinline__ void order_segments(uint4* mems, uint32_t n_mems) {
+    for (uint32_t s0 = 0; s0 < n_mems;) {
+        uint32_t s1 = s0 + 1;
+        const uint32_t id = mems[s0].w;
+        while (s1 < n_mems && mems[s1].w == id) ++s1;
+        const bool descending = (mems[s0].x >> 16) > (mems[s1 - 1].x >> 16);
+        for (uint32_t x = s0, y = s1 - 1; descending && x < y; ++x, --y) {
+            uint4 t = mems[x]; mems[x] = mems[y]; mems[y] = t;
+        }
+        s0 = s1;
+    }
+}
 
 template <int METHOD>
 __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
@@ -181,19 +204,8 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
                             a.reads + (size_t)__ldg(a.chunk_off + rid) * 4,
                             a.mem_pool + a.mem_off[rid],
                             a.stage + gtid * a.max_len,
-                            __ldg(a.len + rid), a.K, a.mem_cnt[rid], a.min_len, (uint32_t)rid, 0u, false};
-        // the sweep emits each sweep's matches longest-end first: put every segment in ascending order
-        for (uint32_t s0 = 0; s0 < c.n_mems;) {
-            uint32_t s1 = s0 + 1;
-            const uint32_t id = c.mems[s0].w;
-            while (s1 < c.n_mems && c.mems[s1].w == id) ++s1;
-            // (idempotent: a second selection pass over the same sweep finds the segment ascending)
-            const bool descending = (c.mems[s0].x >> 16) > (c.mems[s1 - 1].x >> 16);
-            for (uint32_t x = s0, y = s1 - 1; descending && x < y; ++x, --y) {
-                uint4 t = c.mems[x]; c.mems[x] = c.mems[y]; c.mems[y] = t;
-            }
-            s0 = s1;
-        }
+                            __ldg(a.len + rid), a.K, a.mem_cnt[rid], a.min_len, (uint32_t)rid, 0u, false, true};
+        order_segments(c.mems, c.n_mems);
         uint8_t status = GSM_READ_OK;
         if (METHOD == GSM_METHOD_BWA) Selector<DevSelCtx<METHOD>>::run_bwa(c);
         else if (c.L < c.K) status = GSM_READ_TOO_SHORT;
@@ -208,6 +220,262 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
             a.rec_tmp_off[rid] = (uint32_t)off; a.rec_cnt[rid] = c.n_rec;
         }
         a.read_status[rid] = status;
+    }
+}
+
+// RMI-SMEM selection with the warp kept in lock step on the memory-bound part.  One thread per read (threads pull reads
+// grid-stride: many reads in flight hide the dependent loads of the frame machine), but the round structure of the machine
+// (select_logic.cuh) is driven warp-wide:
+//   pass 1  every thread with a read in progress looks up the windows of its current round: predict + last-mile search
+//           through ONE probe site inside a loop that the whole warp leaves together (__any_sync) -- the error-bounded
+//           RmiFast first, then the literal RmiSearch for the windows it declared hazardous;
+//   pass 2  each thread runs the integer frame machine of its round (divergent, no table probes), emits one record,
+//           and opens its next read when the current one is finished.
+// Measured alternatives (profiles/r01_notes.md): the reference's control flow per thread end to end (2.2 active threads
+// per instruction on the probes), and teams of 16 lanes per read with one window per lane (converged, but 16x fewer reads
+// in flight: latency-bound on the machine's dependent loads, 1.7x slower than this kernel).
+template <int METHOD>
+__global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const SelectArgs a) {
+    using Sel = Selector<DevSelCtx<METHOD>>;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    size_t rid = gtid;
+    bool have = false;
+    DevSelCtx<METHOD> c{a, nullptr, nullptr, a.stage + gtid * a.max_len, 0u, a.K, 0u, a.min_len, 0u, 0u, false, true};
+    typename Sel::Seeded st;
+    int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
+
+    auto close_read = [&](uint8_t status) {
+        if (c.raised) { status = GSM_READ_REF_RAISES; c.n_rec = 0; }
+        const unsigned long long off = atomicAdd(&a.counters[1], (unsigned long long)c.n_rec);
+        if (off + c.n_rec > a.rec_cap) {
+            atomicOr(&a.counters[2], 2ull);
+            a.rec_tmp_off[rid] = 0; a.rec_cnt[rid] = 0;
+        } else {
+            for (uint32_t k = 0; k < c.n_rec; ++k) a.rec_tmp[off + k] = c.stage[k];
+            a.rec_tmp_off[rid] = (uint32_t)off; a.rec_cnt[rid] = c.n_rec;
+        }
+        a.read_status[rid] = status;
+        rid += nthreads;
+        have = false;
+    };
+    // open reads until one needs a round (reads shorter than K are closed at once)
+    auto open_reads = [&]() {
+        while (!have && rid < a.n_reads) {
+            c.words = a.reads + (size_t)__ldg(a.chunk_off + rid) * 4;
+            c.mems = a.mem_pool + a.mem_off[rid];
+            c.L = __ldg(a.len + rid); c.n_mems = a.mem_cnt[rid]; c.rid = (uint32_t)rid; c.n_rec = 0; c.raised = false;
+            order_segments(c.mems, c.n_mems);
+            st = typename Sel::Seeded();
+            if (c.L < c.K) { close_read(GSM_READ_TOO_SHORT); continue; }
+            have = true;
+        }
+    };
+    auto next_window = [&](uint32_t& i, uint32_t nwin, uint32_t& cpos) {       // next visited window at or after i
+        for (; i < nwin; ++i) {
+            cpos = st.first ? 0u : st.e - i;
+            if (st.first || (i < st.plen && cpos + c.K <= c.L)) return true;
+        }
+        return false;
+    };
+
+    for (;;) {
+        while (true) {                                   // finished reads are closed, the next ones opened
+            open_reads();
+            if (!have || Sel::round_needed(c, st)) break;
+            close_read(GSM_READ_OK);
+        }
+        if (!__any_sync(FULL, have)) break;
+        const uint32_t nwin = st.first ? 1u : c.K;
+        uint32_t whit = 0, redo = 0;
+        // ---------------- pass 1: lookups, warp in lock step
+        if (a.rmi.n_none != 0) {
+            // error-bounded search first (RmiFast); windows it declares hazardous (None rows in the bracket, prediction
+            // outside the table -- a handful per million) are redone probe for probe by the literal search below
+            RmiFast rf;
+            uint32_t i = 0;
+            int cur = -1;
+            bool more = have;
+            for (;;) {
+                while (more && !rf.pending()) {          // bank the finished search, start the next window's
+                    if (cur >= 0) {
+                        if (rf.hazard) redo |= 1u << cur;
+                        else {
+                            wlo[cur] = rf.out_lo; whi[cur] = rf.out_hi;
+                            if (rf.hit()) whit |= 1u << cur;
+                        }
+                        cur = -1;
+                    }
+                    uint32_t cpos = 0;
+                    if (!next_window(i, nwin, cpos)) { more = false; break; }
+                    cur = (int)i++;
+                    rf.begin(a.rmi, c.window_code(cpos), a.meta.n_rows, (int64_t)a.n_bases);
+                }
+                const bool need = more && rf.pending();
+                if (!__any_sync(FULL, need)) break;
+                if (need) {
+                    int64_t sv;
+                    uint64_t code64;
+                    c.probe_row(rf.row(), sv, code64);   // the probe site of the fast search
+                    rf.feed(a.rmi, sv, code64);
+                }
+            }
+        } else if (have) {
+            uint32_t i = 0, cpos = 0;
+            while (next_window(i, nwin, cpos)) redo |= 1u << i++;
+        }
+        if (__any_sync(FULL, redo != 0)) {
+            RmiSearch rs;
+            int cur = -1;
+            bool more = redo != 0;
+            for (;;) {
+                while (more && !rs.pending()) {
+                    if (cur >= 0) {
+                        if (rs.raised) { c.raised = true; more = false; break; }
+                        wlo[cur] = rs.out_lo; whi[cur] = rs.out_hi;
+                        if (rs.hit()) whit |= 1u << cur;
+                        cur = -1;
+                    }
+                    if (redo == 0) { more = false; break; }
+                    cur = __ffs(redo) - 1;               // windows in ascending order, like the reference
+                    redo &= redo - 1;
+                    const uint32_t cpos = st.first ? 0u : st.e - (uint32_t)cur;
+                    rs.begin(a.rmi, c.window_code(cpos), (int64_t)a.meta.n_rows, (int64_t)a.n_bases);
+                }
+                const bool need = more && rs.pending();
+                if (!__any_sync(FULL, need)) break;
+                if (need) {
+                    int64_t sv;
+                    uint64_t code64;
+                    c.probe_row(rs.row(), sv, code64);   // the probe site of the literal search
+                    rs.feed(sv, code64);
+                }
+            }
+        }
+        __syncwarp();
+        // ---------------- pass 2: the frame machine of this round
+        if (have) {
+            if (c.raised) close_read(GSM_READ_REF_RAISES);
+            else Sel::round_finish(c, st, wlo, whi, whit);
+        }
+        __syncwarp();
+    }
+}
+
+// The same selection by TEAMS of 16 lanes: one read per team, one window of the round per lane (pass 1 costs the latency
+// of the round's longest search instead of the sum of all), the frame machine run by all 16 lanes on identical data (pass
+// 2 converged; lane 0 writes).  Fewer reads in flight than k_select_seeded; chosen per method by measurement
+// (gsm_smem_select, GSM_SELECT_TEAMS).
+constexpr uint32_t TEAM = 16;
+
+template <int METHOD>
+__global__ void __launch_bounds__(SELECT_THREADS) k_select_team(const SelectArgs a) {
+    using Sel = Selector<DevSelCtx<METHOD>>;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tl = lane & (TEAM - 1u);                   // lane within the team
+    const uint32_t tbase = lane & ~(TEAM - 1u);
+    const uint32_t tmask = 0xFFFFu << tbase;
+    const size_t team = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / TEAM;
+    const size_t n_teams = ((size_t)gridDim.x * blockDim.x) / TEAM;
+    size_t rid = team;
+    bool have = false;
+    DevSelCtx<METHOD> c{a, nullptr, nullptr, a.stage + team * a.max_len, 0u, a.K, 0u, a.min_len, 0u, 0u, false, tl == 0u};
+    typename Sel::Seeded st;
+    int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
+
+    auto close_read = [&](uint8_t status) {                   // every lane runs this with identical data; lane 0 writes
+        if (c.raised) { status = GSM_READ_REF_RAISES; c.n_rec = 0; }
+        unsigned long long off = 0;
+        if (tl == 0u) off = atomicAdd(&a.counters[1], (unsigned long long)c.n_rec);
+        off = __shfl_sync(tmask, off, tbase);
+        __syncwarp(tmask);                                    // lane 0's staged records are visible to the team
+        if (off + c.n_rec > a.rec_cap) {
+            if (tl == 0u) { atomicOr(&a.counters[2], 2ull); a.rec_tmp_off[rid] = 0; a.rec_cnt[rid] = 0; }
+        } else {
+            for (uint32_t k = tl; k < c.n_rec; k += TEAM) a.rec_tmp[off + k] = c.stage[k];
+            if (tl == 0u) { a.rec_tmp_off[rid] = (uint32_t)off; a.rec_cnt[rid] = c.n_rec; }
+        }
+        if (tl == 0u) a.read_status[rid] = status;
+        rid += n_teams;
+        have = false;
+    };
+    auto open_reads = [&]() {
+        while (!have && rid < a.n_reads) {
+            c.words = a.reads + (size_t)__ldg(a.chunk_off + rid) * 4;
+            c.mems = a.mem_pool + a.mem_off[rid];
+            c.L = __ldg(a.len + rid); c.n_mems = a.mem_cnt[rid]; c.rid = (uint32_t)rid; c.n_rec = 0; c.raised = false;
+            if (tl == 0u) order_segments(c.mems, c.n_mems);
+            __syncwarp(tmask);
+            st = typename Sel::Seeded();
+            if (c.L < c.K) { close_read(GSM_READ_TOO_SHORT); continue; }
+            have = true;
+        }
+    };
+
+    for (;;) {
+        while (true) {
+            open_reads();
+            if (!have || Sel::round_needed(c, st)) break;
+            close_read(GSM_READ_OK);
+        }
+        if (!have) break;                                     // team-uniform: the whole team leaves together
+        const uint32_t nwin = st.first ? 1u : c.K;
+        uint32_t whit = 0;
+        for (uint32_t wb = 0; wb < nwin; wb += TEAM) {        // pass 1: one window per lane (two batches when K > 16)
+            const uint32_t i = wb + tl;
+            const uint32_t cpos = st.first ? 0u : st.e - i;
+            const bool visit = i < nwin && (st.first || (i < st.plen && cpos + c.K <= c.L));
+            int64_t mlo = 0, mhi = -1;
+            if (METHOD == GSM_METHOD_LUT) {
+                if (visit) {
+                    const uint2 t = __ldg(a.lut + c.window_code(cpos));
+                    mlo = t.x; mhi = (int64_t)t.x + t.y - 1;
+                }
+            } else {
+                const uint64_t code = visit ? c.window_code(cpos) : 0ull;
+                bool literal = visit;
+                if (a.rmi.n_none != 0) {
+                    RmiFast rf;
+                    if (visit) rf.begin(a.rmi, code, a.meta.n_rows, (int64_t)a.n_bases);
+                    for (;;) {
+                        const bool need = rf.pending();
+                        if (!__any_sync(tmask, need)) break;
+                        if (need) {
+                            int64_t sv;
+                            uint64_t code64;
+                            c.probe_row(rf.row(), sv, code64);
+                            rf.feed(a.rmi, sv, code64);
+                        }
+                    }
+                    if (visit && !rf.hazard) { literal = false; mlo = rf.out_lo; mhi = rf.out_hi; }
+                }
+                if (__any_sync(tmask, literal)) {
+                    RmiSearch rs;
+                    if (literal) rs.begin(a.rmi, code, (int64_t)a.meta.n_rows, (int64_t)a.n_bases);
+                    for (;;) {
+                        const bool need = rs.pending();
+                        if (!__any_sync(tmask, need)) break;
+                        if (need) {
+                            int64_t sv;
+                            uint64_t code64;
+                            c.probe_row(rs.row(), sv, code64);
+                            rs.feed(sv, code64);
+                        }
+                    }
+                    if (literal) { mlo = rs.out_lo; mhi = rs.out_hi; }
+                    // the reference visits every window unless an earlier one raised: a raise anywhere is a raise of the read
+                    if (__any_sync(tmask, literal && rs.raised)) c.raised = true;
+                }
+            }
+            whit |= (__ballot_sync(tmask, visit && mhi >= mlo) >> tbase) << wb;
+            for (uint32_t t = 0; t < TEAM && wb + t < nwin; ++t) {
+                wlo[wb + t] = __shfl_sync(tmask, mlo, tbase + t);
+                whi[wb + t] = __shfl_sync(tmask, mhi, tbase + t);
+            }
+        }
+        if (c.raised) close_read(GSM_READ_REF_RAISES);        // pass 2
+        else Sel::round_finish(c, st, wlo, whi, whit);
+        __syncwarp(tmask);
     }
 }
 
@@ -396,6 +664,16 @@ __global__ void k_rmi_lookup(const uint32_t* sa, const uint32_t* text, uint64_t 
     status[i] = t.raised ? GSM_READ_REF_RAISES : GSM_READ_OK;
 }
 
+// rows whose suffix is shorter than K (RMI_LUT.get_ref_seq returns None there): out[0] = count, out[1..] = rows
+__global__ void k_none_rows(const uint32_t* sa, uint64_t n_rows, uint32_t K, uint32_t* out) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    if ((uint64_t)__ldg(sa + row) - 1u + K > n_rows - 1u) {
+        const uint32_t slot = atomicAdd(out, 1u);
+        if (slot < 32u) out[1 + slot] = (uint32_t)row;
+    }
+}
+
 // {suffix_array[row], code of the 32 bases at that suffix}: makes RMI_LUT.get_ref_seq one 16-byte fetch.
 __global__ void k_rmi_probe_build(const uint32_t* sa, const uint32_t* text, uint64_t n_rows, uint4* out) {
     const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -468,11 +746,23 @@ uint64_t sweep_scratch_bytes(int blocks, uint32_t max_len) {
     return (uint64_t)blocks * SWEEP_GROUPS * 2ull * max_len * 16ull;
 }
 
-int select_grid(int* blocks) {
+int select_grid(int* blocks) {          // upper bound over the selection kernels: sizes the per-thread record staging
     int dev = 0, sms = 0;
     GSM_CUDA(cudaGetDevice(&dev));
     GSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     *blocks = sms * 8;
+    return GSM_OK;
+}
+
+// resident grid of one selection kernel: a persistent grid-stride kernel must not spill into a second wave
+template <typename Kern>
+int resident_grid(Kern kern, int threads, int cap, int* blocks) {
+    int dev = 0, sms = 0, per_sm = 0;
+    GSM_CUDA(cudaGetDevice(&dev));
+    GSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
+    if (per_sm < 1) per_sm = 1;
+    *blocks = sms * per_sm < cap ? sms * per_sm : cap;
     return GSM_OK;
 }
 
@@ -538,6 +828,16 @@ int gsm_lut_build(const gsm_dev_index* ix, uint32_t K, uint32_t* table, void* st
     return GSM_OK;
 }
 
+int gsm_device_l2_fetch_granularity(int32_t set_bytes, uint32_t* current) {
+    int st = device_ready();
+    if (st) return st;
+    if (set_bytes > 0) GSM_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)set_bytes));
+    size_t v = 0;
+    GSM_CUDA(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+    if (current) *current = (uint32_t)v;
+    return GSM_OK;
+}
+
 int gsm_seed_table_build(const gsm_dev_index* ix, uint32_t K, void* table, void* stream) {
     if (!ix || !table || !ix->fwd_buckets || !ix->rev_buckets) return fail(GSM_E_INVALID, "gsm_seed_table_build: needs both bucket arrays");
     if (K < 1 || K > 14) return fail(GSM_E_INVALID, "gsm_seed_table_build: K must be in 1..14");
@@ -550,13 +850,35 @@ int gsm_seed_table_build(const gsm_dev_index* ix, uint32_t K, void* table, void*
     return GSM_OK;
 }
 
-static int fill_rmi(const gsm_dev_rmi* rmi, RmiModel* m) {
+static int fill_rmi(const gsm_dev_rmi* rmi, RmiModel* m, uint64_t n_rows) {
     memset(m, 0, sizeof(*m));
     if (!rmi || !rmi->level_sizes || !rmi->coef || !rmi->intercept) return fail(GSM_E_INVALID, "RMI parameters missing");
     if (rmi->n_levels < 1 || rmi->n_levels > 8 || rmi->K < 1 || rmi->K > 32) return fail(GSM_E_INVALID, "RMI: 1..8 levels, K in 1..32");
     m->K = rmi->K; m->n_levels = rmi->n_levels; m->coef = rmi->coef; m->intercept = rmi->intercept;
     uint32_t off = 0;
     for (uint32_t l = 0; l < rmi->n_levels; ++l) { m->level_size[l] = rmi->level_sizes[l]; m->level_off[l] = off; off += rmi->level_sizes[l]; }
+    if (rmi->none_rows && rmi->n_none_rows) {
+        if (rmi->n_none_rows != rmi->K) return fail(GSM_E_INVALID, "RMI: none_rows must hold exactly K rows (gsm_rmi_none_rows)");
+        rmi_set_none_rows(*m, rmi->none_rows, rmi->n_none_rows, n_rows);
+    }
+    return GSM_OK;
+}
+
+int gsm_rmi_none_rows(const gsm_dev_index* ix, uint32_t K, uint32_t* rows_host, uint32_t* scratch, void* stream) {
+    if (!ix || !ix->sa || !rows_host || !scratch || K < 1 || K > 32) return fail(GSM_E_INVALID, "gsm_rmi_none_rows: needs sa on the device, K in 1..32");
+    int st = device_ready();
+    if (st) return st;
+    if (ix->n_rows <= K) return fail(GSM_E_INVALID, "gsm_rmi_none_rows: reference shorter than K");
+    cudaStream_t s_ = (cudaStream_t)stream;
+    GSM_CUDA(cudaMemsetAsync(scratch, 0, 33 * sizeof(uint32_t), s_));
+    k_none_rows<<<(unsigned)((ix->n_rows + 255) / 256), 256, 0, s_>>>(ix->sa, ix->n_rows, K, scratch);
+    GSM_CUDA(cudaGetLastError());
+    uint32_t h[33];
+    GSM_CUDA(cudaMemcpyAsync(h, scratch, sizeof(h), cudaMemcpyDeviceToHost, s_));
+    GSM_CUDA(cudaStreamSynchronize(s_));
+    if (h[0] != K) return fail(GSM_E_INVALID, "gsm_rmi_none_rows: the suffix array does not hold exactly K short suffixes");
+    std::sort(h + 1, h + 1 + K);
+    for (uint32_t t = 0; t < K; ++t) rows_host[t] = h[1 + t];
     return GSM_OK;
 }
 
@@ -575,7 +897,7 @@ int gsm_rmi_lookup_batch(const gsm_dev_index* ix, const gsm_dev_rmi* rmi, uint64
     int st = device_ready();
     if (st) return st;
     RmiModel m;
-    if ((st = fill_rmi(rmi, &m))) return st;
+    if ((st = fill_rmi(rmi, &m, ix->n_rows))) return st;
     if (n == 0) return GSM_OK;
     k_rmi_lookup<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(ix->sa, ix->text2bit, ix->n_rows, ix->n_rows - 1, m, n, codes, pred, lo, hi, status);
     GSM_CUDA(cudaGetLastError());
@@ -630,7 +952,7 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
     RmiModel rm;
     memset(&rm, 0, sizeof(rm));
     if (method == GSM_METHOD_RMI) {
-        if ((st = fill_rmi(rmi, &rm))) return st;
+        if ((st = fill_rmi(rmi, &rm, ix->n_rows))) return st;
         if (!ix->sa || !ix->text2bit) return fail(GSM_E_INVALID, "RMI method needs the suffix array and packed text on the device");
         K = rmi->K;
     }
@@ -647,9 +969,25 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
     se.rec_tmp = (uint4*)ws->rec_tmp; se.rec_cap = ws->rec_cap; se.rec_tmp_off = ws->rec_tmp_off; se.rec_cnt = ws->rec_cnt;
     se.read_status = ws->read_status; se.counters = (unsigned long long*)ws->counters;
     GSM_CUDA(cudaMemsetAsync((unsigned long long*)ws->counters + 1, 0, sizeof(uint64_t), stream));
-    if (method == GSM_METHOD_BWA) k_select<GSM_METHOD_BWA><<<lb, SELECT_THREADS, 0, stream>>>(se);
-    else if (method == GSM_METHOD_LUT) k_select<GSM_METHOD_LUT><<<lb, SELECT_THREADS, 0, stream>>>(se);
-    else k_select<GSM_METHOD_RMI><<<lb, SELECT_THREADS, 0, stream>>>(se);
+    // GSM_SELECT_TEAMS: bit 0 = LUT by teams, bit 1 = RMI by teams (measurement switch; results are identical)
+    static const int teams = getenv("GSM_SELECT_TEAMS") ? atoi(getenv("GSM_SELECT_TEAMS")) : 0;
+    int grid = lb;
+    if (method == GSM_METHOD_BWA) {
+        if ((st = resident_grid(k_select<GSM_METHOD_BWA>, SELECT_THREADS, lb, &grid))) return st;
+        k_select<GSM_METHOD_BWA><<<grid, SELECT_THREADS, 0, stream>>>(se);
+    } else if (method == GSM_METHOD_LUT && (teams & 1)) {
+        if ((st = resident_grid(k_select_team<GSM_METHOD_LUT>, SELECT_THREADS, lb, &grid))) return st;
+        k_select_team<GSM_METHOD_LUT><<<grid, SELECT_THREADS, 0, stream>>>(se);
+    } else if (method == GSM_METHOD_LUT) {
+        if ((st = resident_grid(k_select<GSM_METHOD_LUT>, SELECT_THREADS, lb, &grid))) return st;
+        k_select<GSM_METHOD_LUT><<<grid, SELECT_THREADS, 0, stream>>>(se);
+    } else if (teams & 2) {
+        if ((st = resident_grid(k_select_team<GSM_METHOD_RMI>, SELECT_THREADS, lb, &grid))) return st;
+        k_select_team<GSM_METHOD_RMI><<<grid, SELECT_THREADS, 0, stream>>>(se);
+    } else {
+        if ((st = resident_grid(k_select_seeded<GSM_METHOD_RMI>, SELECT_THREADS, lb, &grid))) return st;
+        k_select_seeded<GSM_METHOD_RMI><<<grid, SELECT_THREADS, 0, stream>>>(se);
+    }
     GSM_CUDA(cudaGetLastError());
     const uint64_t n_tiles = (rd->n_reads + SCAN_TILE - 1) / SCAN_TILE;
     unsigned long long* tiles = (unsigned long long*)ws->scan_tmp;

@@ -26,7 +26,24 @@ struct RmiModel {
     uint32_t level_off[8];
     const double* coef;
     const double* intercept;
+    uint32_t n_none;            // > 0: none_rows holds the rows of the K short suffixes (enables RmiFast)
+    uint32_t none_rows[32];
+    uint32_t none_shift;        // none_map bit (row >> none_shift) is set iff that region of rows holds a None row
+    uint32_t none_map[32];      // 1024 regions: the usual bracket is cleared with two bit tests
 };
+
+// fill the None-row fields of a model (host side): rows = the K rows of gsm_rmi_none_rows, ascending
+inline void rmi_set_none_rows(RmiModel& m, const uint32_t* rows, uint32_t n, uint64_t n_rows) {
+    m.n_none = n;
+    m.none_shift = 0;
+    while ((n_rows >> m.none_shift) > 1024u) ++m.none_shift;
+    for (int w = 0; w < 32; ++w) m.none_map[w] = 0;
+    for (uint32_t t = 0; t < n && t < 32u; ++t) {
+        m.none_rows[t] = rows[t];
+        const uint32_t r = rows[t] >> m.none_shift;
+        m.none_map[r >> 5] |= 1u << (r & 31u);
+    }
+}
 
 GSM_HD double mul_add_nofma(double x, double a, double b) {
 #if defined(__CUDA_ARCH__)
@@ -194,28 +211,300 @@ struct RmiTable {
     }
 };
 
+// The same last-mile search as RmiTable::lookup, written as a resumable state machine with ONE probe site:
+// begin() sets up the first probe, then the caller alternates  row() -> fetch {s, code64} -> feed()  until
+// !pending().  A GPU thread runs many lookups back to back through the same loop, so all threads of a warp meet at
+// the single fetch no matter which phase of which search each one is in (exponential gallop up / down, shared
+// binary prefix, the two binary searches of RMI_LUT.py:183-184).  Probe for probe identical to RmiTable.
+struct RmiSearch {
+    enum : int { DONE = 0, START, UP, DOWN, SH, SH_SKIP, BIN_END, BIN_MID, BIN_SKIP };
+    int state = DONE;
+    bool raised = false, have_lower = false, have_upper = false, strict = false;
+    int64_t n_rows = 0, n_bases = 0;
+    uint32_t K = 0;
+    uint64_t q = 0;
+    int64_t start = 0, win = 0, ind = 0, lower = 0, upper = 0, bl = 0, bu = 0, mid = 0;
+    int depth = 0;
+    int64_t out_lo = 0, out_hi = -1;
+
+    GSM_HD bool pending() const { return state != DONE; }
+    GSM_HD bool hit() const { return !raised && out_hi >= out_lo; }
+    // row to fetch for the pending probe (Python negative indexing already applied)
+    GSM_HD uint64_t row() const { return (uint64_t)(ind < 0 ? ind + n_rows : ind); }
+
+    GSM_HD static int64_t floor_half(int64_t sum) { return (sum >= 0) ? sum / 2 : -((-sum + 1) / 2); }
+
+    // schedule the probe of `i` in state `st`; an index outside [-n, n) is the reference's IndexError
+    GSM_HD void issue(int st, int64_t i) {
+        ind = i;
+        if (i < -n_rows || i >= n_rows) { raised = true; state = DONE; return; }
+        state = st;
+    }
+
+    GSM_HD void begin(const RmiModel& m, uint64_t code, int64_t rows, int64_t bases) {
+        n_rows = rows; n_bases = bases; K = m.K; q = code;
+        raised = false; have_lower = have_upper = false; strict = false;
+        out_lo = 0; out_hi = -1;
+        const double pred = rmi_predict(m, code);
+        if (!(pred > -9.0e18 && pred < 9.0e18)) { raised = true; state = DONE; return; }
+        start = (int64_t)pred;                                  // int() truncates toward zero (RMI_LUT.py:72)
+        issue(START, start);
+    }
+
+    GSM_HD void gallop_up() {                                   // RMI_LUT.py:151-163
+        if (!have_upper && start + win < n_bases + 1) { const int64_t i = start + win; win *= 2; issue(UP, i); return; }
+        win = 1;
+        gallop_down();
+    }
+    GSM_HD void gallop_down() {                                 // RMI_LUT.py:166-178
+        if (!have_lower && start - win >= 0) { const int64_t i = start - win; win *= 2; issue(DOWN, i); return; }
+        if (!have_lower) lower = 0;
+        if (!have_upper) upper = n_rows - 1;
+        depth = 0;
+        shared_iter();
+    }
+    GSM_HD void shared_iter() {                                 // common prefix of the two binary searches
+        if (depth < 400 && upper - lower > 1) { mid = floor_half(lower + upper); issue(SH, mid); return; }
+        begin_bin(false);
+    }
+    GSM_HD void begin_bin(bool st) {
+        strict = st; bl = lower; bu = upper; depth = 0;
+        bin_iter();
+    }
+    GSM_HD void bin_iter() {                                    // RMI_LUT.py:95-133, the recursion as a loop
+        if (depth >= 400) { raised = true; state = DONE; return; }     // RecursionError in the reference
+        if (bl == bu) { bin_done(bl); return; }
+        if (bu - bl == 1) { issue(BIN_END, strict ? bu : bl); return; }
+        mid = floor_half(bl + bu);
+        issue(BIN_MID, mid);
+    }
+    GSM_HD void bin_done(int64_t r) {
+        if (!strict) { out_lo = r; begin_bin(true); return; }
+        out_hi = r;
+        state = DONE;
+    }
+
+    // result of the pending probe: s = suffix_array[row], code64 = 32-mer code at text position s-1
+    GSM_HD void feed(int64_t s, uint64_t code64) {
+        const bool ok = !(s - 1 + (int64_t)K > n_bases);       // get_ref_seq returns None for a short suffix
+        const uint64_t c = ok ? (code64 >> (64u - 2u * K)) : 0ull;
+        switch (state) {
+        case START:
+            if (!ok) { start += 1; issue(START, start); return; }
+            if (c < q) { lower = start; have_lower = true; }
+            else if (c > q) { upper = start; have_upper = true; }
+            win = 1;
+            gallop_up();
+            return;
+        case UP:
+            if (!ok) { issue(UP, ind + 1); return; }
+            if (c > q) { upper = ind; have_upper = true; win = 1; gallop_down(); return; }
+            if (c < q) { lower = ind; have_lower = true; }
+            gallop_up();
+            return;
+        case DOWN:
+            if (!ok) { issue(DOWN, ind - 1); return; }
+            if (c < q) { lower = ind; have_lower = true; gallop_down(); return; }
+            if (c > q) { upper = ind; have_upper = true; }
+            gallop_down();
+            return;
+        case SH:
+        case SH_SKIP: {
+            bool at_lower = false;
+            if (state == SH_SKIP && mid == lower) at_lower = true;
+            else if (!ok && mid > lower) { mid -= 1; issue(SH_SKIP, mid); return; }
+            if (at_lower || !ok || c == q) { begin_bin(false); return; }      // the searches part ways here
+            if (c < q) lower = mid; else upper = mid;
+            depth++;
+            shared_iter();
+            return;
+        }
+        case BIN_END:
+            if (strict) bin_done((ok && c == q) ? bu : bl);
+            else bin_done((ok && c == q) ? bl : bu);
+            return;
+        case BIN_MID:
+        case BIN_SKIP:
+            if (state == BIN_SKIP && mid == bl) {
+                if (strict) { issue(BIN_END, bu); return; }
+                bin_done((ok && c == q) ? bl : bu);
+                return;
+            }
+            if (!ok && mid > bl) { mid -= 1; issue(BIN_SKIP, mid); return; }
+            if (!ok) { raised = true; state = DONE; return; }                 // None < str: TypeError in the reference
+            if (c < q || (c == q && strict)) bl = mid; else bu = mid;
+            depth++;
+            bin_iter();
+            return;
+        default:
+            return;
+        }
+    }
+};
+
+// Error-bounded last-mile search for the common case, same results as the literal search above at a fraction of the
+// instructions.  The literal algorithm deviates from "first row >= q, last row <= q" only when a row of its bracket is a
+// None row of get_ref_seq (a suffix shorter than K: K rows of the whole table, RMI_LUT.py:89-92), when the prediction
+// falls outside the table, or when a bracket end stays at its default -- its exponential phase otherwise ends with
+// k-mer[lower] < q < k-mer[upper], and both binary searches of a None-free sorted range return the exact bounds whatever
+// pivots they use.  RmiFast therefore replays the exponential phase probe for probe (same rows), declares a HAZARD
+// (-> the caller reruns the window through RmiSearch) if it meets a None row, an out-of-table start, a default bracket
+// end or a None row anywhere inside the bracket (none_rows: the sorted rows of the K short suffixes), and otherwise
+// finishes with a lower-bound binary search and a galloping upper-bound search (k-mer counts are small).  32-bit rows,
+// one probe site, a handful of instructions per state.
+struct RmiFast {
+    enum : int { DONE = 0, START, UP, DOWN, LB, UBG, UBB };
+    int state = DONE;
+    bool hazard = false, have_lower = false, have_upper = false, hi_eq = false;
+    uint32_t n_rows = 0, K = 0;
+    int64_t n_bases = 0;
+    uint64_t q = 0;
+    uint32_t start = 0, win = 0, ind = 0, lower = 0, upper = 0, lo = 0, hi = 0, L = 0, g = 0;
+    int64_t out_lo = 0, out_hi = -1;
+
+    GSM_HD bool pending() const { return state != DONE; }
+    GSM_HD bool hit() const { return out_hi >= out_lo; }
+    GSM_HD uint64_t row() const { return ind; }
+    GSM_HD void bail() { hazard = true; state = DONE; }
+    GSM_HD void probe(int st, uint32_t r) { ind = r; state = st; }
+
+    // int(prediction) when it is a row of the table, else -1 (the literal search wraps or raises there)
+    GSM_HD static int64_t predicted_row(const RmiModel& m, uint64_t code, uint32_t rows) {
+        const double pred = rmi_predict(m, code);
+        if (!(pred > -1.0 && pred < (double)rows)) return -1;
+        return (int64_t)pred;                                   // int() truncates toward zero (RMI_LUT.py:72)
+    }
+    GSM_HD void begin(const RmiModel& m, uint64_t code, uint32_t rows, int64_t bases) {
+        begin_at(m, code, predicted_row(m, code, rows), rows, bases);
+    }
+    // the prediction may be computed ahead of time (k_select_seeded does all windows of a round in one converged loop)
+    GSM_HD void begin_at(const RmiModel& m, uint64_t code, int64_t row0, uint32_t rows, int64_t bases) {
+        n_rows = rows; n_bases = bases; K = m.K; q = code;
+        hazard = false; have_lower = have_upper = false; hi_eq = false;
+        out_lo = 0; out_hi = -1;
+        if (row0 < 0) { bail(); return; }
+        start = (uint32_t)row0;
+        win = 1;
+        probe(START, start);
+    }
+    GSM_HD void next_up(const RmiModel& m) {
+        if (!have_upper && (uint64_t)start + win < n_rows) { const uint32_t r = start + win; win *= 2; probe(UP, r); return; }
+        win = 1;
+        next_down(m);
+    }
+    GSM_HD void next_down(const RmiModel& m) {
+        if (!have_lower && start >= win) { const uint32_t r = start - win; win *= 2; probe(DOWN, r); return; }
+        bracket_ready(m);
+    }
+    GSM_HD void bracket_ready(const RmiModel& m) {
+        if (!have_lower || !have_upper) { bail(); return; }
+        const uint32_t rl = lower >> m.none_shift, ru = upper >> m.none_shift;
+        if (ru - rl > 1u || ((m.none_map[rl >> 5] >> (rl & 31u)) & 1u) || ((m.none_map[ru >> 5] >> (ru & 31u)) & 1u)) {
+            bool bad = false;                                   // a None row nearby: the exact test
+            for (uint32_t t = 0; t < m.n_none; ++t) bad |= (m.none_rows[t] >= lower && m.none_rows[t] <= upper);
+            if (bad) { bail(); return; }
+        }
+        lo = lower; hi = upper; hi_eq = false;
+        lb_iter();
+    }
+    GSM_HD void lb_iter() {                                      // first row of (lower, upper] with k-mer >= q
+        if (hi - lo > 1) { probe(LB, lo + ((hi - lo) >> 1)); return; }
+        L = hi;
+        if (!hi_eq) { out_lo = (int64_t)L; out_hi = (int64_t)L - 1; state = DONE; return; }     // absent: lo = hi + 1
+        lo = L; g = 1;
+        ub_gallop();
+    }
+    GSM_HD void ub_gallop() {                                    // k-mer[lo] == q: last row of [lo, upper) equal to q
+        if ((uint64_t)lo + g >= upper) { hi = upper; ub_bin(); return; }
+        probe(UBG, lo + g);
+    }
+    GSM_HD void ub_bin() {
+        if (hi - lo > 1) { probe(UBB, lo + ((hi - lo) >> 1)); return; }
+        out_lo = (int64_t)L; out_hi = (int64_t)lo;
+        state = DONE;
+    }
+    GSM_HD void feed(const RmiModel& m, int64_t s, uint64_t code64) {
+        if (s - 1 + (int64_t)K > n_bases) { bail(); return; }   // a None row: let the literal search handle this window
+        const uint64_t c = code64 >> (64u - 2u * K);
+        switch (state) {
+        case START:
+            if (c < q) { lower = ind; have_lower = true; }
+            else if (c > q) { upper = ind; have_upper = true; }
+            next_up(m);
+            return;
+        case UP:
+            if (c > q) { upper = ind; have_upper = true; win = 1; next_down(m); return; }
+            if (c < q) { lower = ind; have_lower = true; }
+            next_up(m);
+            return;
+        case DOWN:
+            if (c < q) { lower = ind; have_lower = true; bracket_ready(m); return; }
+            if (c > q) { upper = ind; have_upper = true; }
+            next_down(m);
+            return;
+        case LB:
+            if (c < q) lo = ind; else { hi = ind; hi_eq = (c == q); }
+            lb_iter();
+            return;
+        case UBG:
+            if (c == q) { lo = ind; g *= 2; ub_gallop(); } else { hi = ind; ub_bin(); }
+            return;
+        case UBB:
+            if (c == q) lo = ind; else hi = ind;
+            ub_bin();
+            return;
+        default:
+            return;
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------ selection
 // Ctx must provide:
 //   uint32_t L, K, n_mems;  uint32_t min_len;
 //   MemEntry mem(uint32_t k)                 k-th maximal match, sorted by end (and start)
 //   uint32_t base(uint32_t pos)
-//   bool seed(uint32_t c, int64_t& lo, int64_t& hi)      LUT / RMI lookup of q[c:c+K]; true on a hit
+//   uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi)
+//                                            LUT / RMI lookups of the windows of one round: window i covers
+//                                            q[c:c+K), c = first ? 0 : e - i, and is visited iff first or
+//                                            (i < plen and c + K <= L); bit i of the result = hit
 //   bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi)
 //                                            check_sequential of the two seeds (SMEM.py:196-202)
 //   void interval(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt)   true SA interval of q[i:j]
 //   void emit(uint32_t i, uint32_t j, int64_t lo, int64_t hi)
 //   bool failed()                             the reference raised inside seed()
 //   bool seeds_are_true()                     seed() returns exact SA intervals (LUT), not RMI guesses
+constexpr int MAX_SEED_K = 32;      // LUT K <= 16, RMI K <= 26 (float64-exact codes)
+
 template <typename Ctx>
 struct Selector {
     GSM_HD static uint32_t s_of(const MemEntry& e) { return e.se & 0xFFFFu; }
     GSM_HD static uint32_t e_of(const MemEntry& e) { return e.se >> 16; }
 
+    // Starts and ends of the maximal matches both increase strictly with k, so every lookup into the list is a
+    // binary search: first k with e_k > p (or >= with `incl`), and number of k with s_k <= p.
+    GSM_HD static uint32_t first_end_above(Ctx& c, uint32_t p, uint32_t lo = 0) {
+        uint32_t hi = c.n_mems;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (e_of(c.mem(mid)) <= p) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    }
+    GSM_HD static uint32_t count_starts_upto(Ctx& c, uint32_t p) {
+        uint32_t lo = 0, hi = c.n_mems;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_of(c.mem(mid)) <= p) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    }
+
     // get_SMEM_at_index (SMEM.py:469-484) == longest maximal match covering p, ties to the
     // smallest end (the strict '>' of SMEM.py:413 scanning ends upward).  `from` = first k with
     // e_k > p.  Returns the index of the winner.
     GSM_HD static uint32_t covering_best(Ctx& c, uint32_t p, uint32_t& from) {
-        while (from < c.n_mems && e_of(c.mem(from)) <= p) ++from;
+        from = first_end_above(c, p, from);
         uint32_t best = from, bestlen = 0;
         for (uint32_t k = from; k < c.n_mems; ++k) {
             MemEntry m = c.mem(k);
@@ -248,25 +537,22 @@ struct Selector {
         if (!cd.valid || (j - i) >= (cd.j - cd.i)) { cd.valid = true; cd.i = i; cd.j = j; cd.lo = lo; cd.hi = hi; }
     }
 
-    // F(p) restricted to true matches; 0 matches => p (cannot happen when all four bases occur)
+    // F(p) restricted to true matches = end of the last match starting at or before p; 0 such matches => p
+    // (cannot happen when all four bases occur)
     GSM_HD static uint32_t F_of(Ctx& c, uint32_t p) {
-        uint32_t f = p;
-        for (uint32_t k = 0; k < c.n_mems; ++k) {
-            MemEntry m = c.mem(k);
-            if (s_of(m) > p) break;
-            if (e_of(m) > f) f = e_of(m);
-        }
-        return f;
+        const uint32_t n = count_starts_upto(c, p);
+        if (n == 0) return p;
+        const uint32_t e = e_of(c.mem(n - 1));
+        return e > p ? e : p;
     }
 
     // True SA interval of q[i:j): read it off the match list when (i, j) is itself a maximal match
     // (the usual case), otherwise one backward search from j down to i.
     GSM_HD static void true_iv(Ctx& c, uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt) {
-        for (uint32_t k = 0; k < c.n_mems; ++k) {
+        const uint32_t k = j ? first_end_above(c, j - 1) : 0u;
+        if (k < c.n_mems) {
             MemEntry m = c.mem(k);
-            if (e_of(m) < j) continue;
             if (e_of(m) == j && s_of(m) == i) { lo = m.lo; cnt = m.cnt; return; }
-            break;
         }
         c.interval(i, j, lo, cnt);
     }
@@ -293,10 +579,9 @@ struct Selector {
         uint32_t bi = 0, bj = 0, blo = 0, bcnt = 0;
         bool b_from_mem = false;
         if (seed_true) {
-            for (uint32_t k = 0; k < c.n_mems; ++k) {
+            for (uint32_t k = first_end_above(c, pc + K - 1); k < c.n_mems; ++k) {
                 MemEntry m = c.mem(k);
                 uint32_t s = s_of(m), e = e_of(m);
-                if (e < pc + K) continue;
                 if (s >= pc) break;                    // starts are sorted: no further left extension
                 uint32_t j = e <= jmax ? e : jmax;     // plateau end, or the key range's last key
                 if (!have || (j - s) > (bj - bi)) {
@@ -320,19 +605,45 @@ struct Selector {
         out.lo = (int64_t)blo; out.hi = (int64_t)blo + bcnt - 1;
     }
 
-    // get_smems_lut / get_smems_rmi: the frame machine of SMEM.py:49-186 / :235-379.
-    GSM_HD static void run_seeded(Ctx& c) {
-        const uint32_t K = c.K, L = c.L;
-        bool first = true;
+    // get_smems_lut / get_smems_rmi: the frame machine of SMEM.py:49-186 / :235-379, one ROUND at a time.  A round =
+    // the windows left of the previous SMEM's end (the first round: window 0 only) and emits exactly one record.
+    //   Pass 1 (Ctx::seed_round): the lookups of ALL windows of the round.  The reference visits every window whatever
+    //   the earlier ones returned (no early exit in SMEM.py:56-146), so the lookups can be taken out of the machine and
+    //   run where the threads of a warp are together (k_select_seeded keeps a warp in lock step on them).
+    //   Pass 2 (round_finish): the machine over the stored results.
+    struct Seeded {
+        bool first = true, done = false;
         uint32_t e = 0, plen = 0;
-        for (;;) {
-            if (!first && e >= L) return;
+    };
+
+    // false once the read is finished (SMEM.py:49 `while e < len(query)`)
+    GSM_HD static bool round_needed(const Ctx& c, Seeded& st) {
+        if (st.done || (!st.first && st.e >= c.L)) { st.done = true; return false; }
+        return true;
+    }
+
+    GSM_HD static void run_seeded(Ctx& c) {
+        Seeded st;
+        int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
+        while (round_needed(c, st)) {
+            const uint32_t whit = c.seed_round(st.first, st.e, st.plen, st.first ? 1u : c.K, wlo, whi);
+            if (c.failed()) return;
+            round_finish(c, st, wlo, whi, whit);
+        }
+    }
+
+    GSM_HD static void round_finish(Ctx& c, Seeded& st, const int64_t* wlo, const int64_t* whi, uint32_t whit) {
+        const uint32_t K = c.K, L = c.L;
+        const bool first = st.first;
+        uint32_t e = st.e, plen = st.plen;
+        {
             // frame: 0 = None, 1 = () , 2 = k-mer frame
             int fstate = 0;
             uint32_t pc = 0; bool pfw = false; int64_t plo = 0, phi = -1;
             Cand cd; cd.valid = false; cd.i = cd.j = 0; cd.lo = 0; cd.hi = -1;
             const uint32_t pstart = e - plen;
             const uint32_t nwin = first ? 1u : K;
+            // Pass 2: the frame machine over the stored results
             for (uint32_t i = 0; i < nwin; ++i) {
                 uint32_t cpos;
                 if (first) cpos = 0;
@@ -341,9 +652,8 @@ struct Selector {
                     cpos = e - i;
                     if (cpos + K > L) continue;
                 }
-                int64_t lo, hi;
-                const bool hit = c.seed(cpos, lo, hi);        // the ONLY lookup site
-                if (c.failed()) return;
+                const int64_t lo = wlo[i], hi = whi[i];
+                const bool hit = (whit >> i) & 1u;
                 if (first) {                                   // SMEM.py:26-39 / :213-225
                     uint32_t end; int64_t flo, fhi;
                     if (hit) fwd_only(c, 0, lo, hi, end, flo, fhi);
@@ -383,14 +693,14 @@ struct Selector {
                     fstate = 1;
                 }
             }
-            if (first) { first = false; continue; }
+            if (first) { st.first = false; st.e = e; st.plen = plen; return; }
             if (fstate == 2) {                                                                            // :149-171
                 Cand b; bext(c, pc, plo, phi, pfw, b); upd(cd, b.i, b.j, b.lo, b.hi);
             }
             if (!cd.valid) {                                                                              // :175-179
                 uint32_t from = 0;
                 uint32_t b = covering_best(c, e, from);
-                if (b >= c.n_mems) return;
+                if (b >= c.n_mems) { st.done = true; return; }
                 MemEntry m = c.mem(b);
                 c.emit(s_of(m), e_of(m), (int64_t)m.lo, (int64_t)m.lo + m.cnt - 1);
                 plen = e_of(m) - s_of(m);
@@ -399,6 +709,7 @@ struct Selector {
                 c.emit(cd.i, cd.j, cd.lo, cd.hi);
                 e = cd.j; plen = cd.j - cd.i;
             }
+            st.e = e; st.plen = plen;
         }
     }
 };

@@ -33,6 +33,14 @@ def require_cuda():
         raise capi.GsmError(capi.E_NODEVICE, "no CUDA device visible: genie_smem_b200 has no CPU fallback")
 
 
+def l2_fetch_granularity(set_bytes=0):
+    """Get (and with set_bytes in {32, 64, 128} first request) the device's L2 fetch granularity."""
+    require_cuda()
+    cur = C.c_uint32()
+    capi.check(capi.lib.gsm_device_l2_fetch_granularity(int(set_bytes), C.byref(cur)))
+    return int(cur.value)
+
+
 class HostIndex:
     """Host-side FM index handle (gsm_index).  Replaces ExactMatch.create_fm_index /
     load_fm_index (reference SMEM/ExactMatch.py:22-41)."""
@@ -428,8 +436,22 @@ class RmiParams:
         s.level_sizes = self.level_sizes.ctypes.data_as(capi.u32p)
         s.coef, s.intercept = self.coef.data_ptr(), self.intercept.data_ptr()
         s.probe = None
+        s.none_rows, s.n_none_rows = None, 0
         self.c = s
         self.probe = None
+        self.none_rows = None
+
+    def build_none_rows(self, index):
+        """The K rows where get_ref_seq returns None (gsm_rmi_none_rows): lets the selection kernel run the
+        error-bounded fast search wherever it provably equals the literal one.  Results never depend on it."""
+        rows = np.zeros(self.K, np.uint32)
+        scratch = torch.zeros(33, dtype=torch.int32, device=index.device)
+        with torch.cuda.device(index.device):
+            capi.check(capi.lib.gsm_rmi_none_rows(C.byref(index.c), self.K, rows.ctypes.data, _ptr(scratch), _stream()))
+        self.none_rows = rows
+        self.c.none_rows = rows.ctypes.data_as(capi.u32p)
+        self.c.n_none_rows = self.K
+        return self
 
     def build_probe_table(self, index):
         """16-byte {SA value, 32-mer code} record per row: one fetch per last-mile probe (n_rows x 16 B of HBM)."""

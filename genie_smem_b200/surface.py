@@ -442,6 +442,8 @@ class RMI_LUT:
         if self._params is None:
             self._params = eng.RmiParams(self.prediction_size, self.rmi.level_sizes, self.rmi.coef, self.rmi.intercept,
                                          self.matcher.device_index.device).build_probe_table(self.matcher.device_index)
+            if self.matcher.device_index.n_rows > self.prediction_size:
+                self._params.build_none_rows(self.matcher.device_index)
         return self._params
 
     def _encode(self, query, encoded):

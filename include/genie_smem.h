@@ -179,6 +179,10 @@ typedef struct {
     const double* coef;          /* device */
     const double* intercept;     /* device */
     const void* probe;           /* device, optional: n_rows x 16 B from gsm_rmi_probe_build, else NULL */
+    const uint32_t* none_rows;   /* HOST pointer, optional: the K rows of gsm_rmi_none_rows; enables the error-bounded
+                                    fast search (identical bounds, far fewer instructions), else NULL */
+    uint32_t n_none_rows;        /* K, or 0 */
+    uint32_t reserved;
 } gsm_dev_rmi;
 
 /* Scratch + output buffers for one SMEM batch; all device memory, all caller-allocated.
@@ -261,6 +265,12 @@ int gsm_smem_collect(const gsm_dev_reads* reads, gsm_workspace* ws, gsm_record* 
  * a suffix-array read followed by a text read.  probe: n_rows * 16 bytes of device memory. */
 int gsm_rmi_probe_build(const gsm_dev_index* idx, void* probe, void* stream);
 
+/* The rows whose suffix is shorter than K bases (RMI_LUT.get_ref_seq returns None there, RMI_LUT.py:89-92): exactly K
+ * rows.  rows_host (HOST, K entries, ascending); scratch: 33 uint32 of device memory.  With them in gsm_dev_rmi the
+ * selection kernel can prove, per lookup, that the literal exponential + binary search equals a plain error-bounded
+ * binary search, and runs that instead; the literal search remains the path for every lookup it cannot prove. */
+int gsm_rmi_none_rows(const gsm_dev_index* idx, uint32_t K, uint32_t* rows_host, uint32_t* scratch, void* stream);
+
 /* RMI_LUT.get_suffix_rmi (RMI_LUT.py:67-78) for a batch of K-mer codes: predict + exponential
  * + binary last-mile search.  pred receives the float64 prediction, lo/hi the returned pair
  * (hit <=> hi >= lo as int64), status GSM_READ_REF_RAISES where the reference would raise. */
@@ -274,6 +284,11 @@ int gsm_rmi_lookup_batch(const gsm_dev_index* idx, const gsm_dev_rmi* rmi, uint6
  * every quad chases pointers (one FM chain each); 0: independent fetches.  sink: device u64. */
 int gsm_gather_probe(const void* buf, uint64_t bytes, uint64_t n_fetch, uint32_t dependent,
                      uint64_t* sink, uint64_t* n_done, void* stream);
+
+/* L2 fetch granularity of the current device (cudaLimitMaxL2FetchGranularity): the rank kernels read isolated
+ * 64-byte buckets, so a 128-byte fetch granularity moves twice the necessary DRAM bytes.  set_bytes > 0 requests
+ * 32 / 64 / 128 (a hint to the driver); *current receives the value in force. */
+int gsm_device_l2_fetch_granularity(int32_t set_bytes, uint32_t* current);
 
 const char* gsm_last_error(void);
 int gsm_version(void);

@@ -98,23 +98,50 @@ struct SelCtx {
         }
     }
 
-    bool seed(uint32_t c, int64_t& lo, int64_t& hi) {
-        g_cnt[0]++;
+    uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi) {
         auto rd = [&](uint64_t w) { return words[w]; };
-        uint64_t code = kmer_code(rd, c, K);
-        if (method == GSM_METHOD_LUT_) {
-            uint32_t l = lut[2 * code], n = lut[2 * code + 1];
-            lo = l; hi = (int64_t)l + n - 1;
-            return n != 0;
-        }
         auto sa = [&](uint64_t r) { return ix->sa[r]; };
         auto tx = [&](uint64_t w) { return ix->text[w]; };
         SaTextProbe<decltype(sa), decltype(tx)> pr{sa, tx};
-        RmiTable<decltype(pr)> t{pr, (int64_t)ix->meta.n_rows, (int64_t)ix->n_bases, K, false};
-        double pred;
-        t.lookup(rmi, code, pred, lo, hi);
-        if (t.raised) { raised = true; return false; }
-        return hi >= lo;
+        uint32_t hit = 0;
+        for (uint32_t i = 0; i < nwin; ++i) {
+            const uint32_t cpos = first ? 0u : e - i;
+            if (!(first || (i < plen && cpos + K <= L))) continue;
+            g_cnt[0]++;
+            uint64_t code = kmer_code(rd, cpos, K);
+            if (method == GSM_METHOD_LUT_) {
+                uint32_t l = lut[2 * code], n = lut[2 * code + 1];
+                lo[i] = l; hi[i] = (int64_t)l + n - 1;
+                if (n != 0) hit |= 1u << i;
+                continue;
+            }
+            if (rmi.n_none) {                            // error-bounded fast path first, literal search on a hazard
+                RmiFast rf;
+                rf.begin(rmi, code, ix->meta.n_rows, (int64_t)ix->n_bases);
+                while (rf.pending()) {
+                    int64_t s; uint64_t c64;
+                    pr(rf.row(), s, c64);
+                    rf.feed(rmi, s, c64);
+                }
+                if (!rf.hazard) {
+                    lo[i] = rf.out_lo; hi[i] = rf.out_hi;
+                    if (rf.hit()) hit |= 1u << i;
+                    continue;
+                }
+                g_cnt[5]++;                              // [5] hazards (select runs)
+            }
+            RmiSearch rs;
+            rs.begin(rmi, code, (int64_t)ix->meta.n_rows, (int64_t)ix->n_bases);
+            while (rs.pending()) {
+                int64_t s; uint64_t c64;
+                pr(rs.row(), s, c64);
+                rs.feed(s, c64);
+            }
+            if (rs.raised) { raised = true; return hit; }
+            lo[i] = rs.out_lo; hi[i] = rs.out_hi;
+            if (rs.hit()) hit |= 1u << i;
+        }
+        return hit;
     }
 
     bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi) {
@@ -202,7 +229,8 @@ int emu_sweep(const EmuIndex* ei, const uint32_t* words, uint32_t L, uint32_t* o
 // -1 if the reference would raise, -2 if the read is shorter than K.
 int emu_smem(const EmuIndex* ei, int method, const uint32_t* words, uint32_t L, uint32_t min_len, uint32_t K,
              const uint32_t* lut, uint32_t n_levels, const uint32_t* level_sizes, const double* coef,
-             const double* intercept, uint32_t* out, uint32_t cap, uint32_t seed_K, const void* seed_tab) {
+             const double* intercept, uint32_t* out, uint32_t cap, uint32_t seed_K, const void* seed_tab, uint32_t n_none,
+             const uint32_t* none_rows) {
     HostIndex ix{(const Half*)ei->fwd, (const Half*)ei->rev, ei->sa, ei->text, {}, ei->n_bases};
     for (int c = 0; c < 4; ++c) { ix.meta.C[c] = ei->C[c]; ix.meta.cnt[c] = ei->cnt[c]; }
     ix.meta.prim_f = ei->prim_f; ix.meta.prim_r = ei->prim_r; ix.meta.n_rows = ei->n_rows;
@@ -231,6 +259,7 @@ int emu_smem(const EmuIndex* ei, int method, const uint32_t* words, uint32_t L, 
         sc.rmi.K = K; sc.rmi.n_levels = n_levels; sc.rmi.coef = coef; sc.rmi.intercept = intercept;
         uint32_t off = 0;
         for (uint32_t l = 0; l < n_levels; ++l) { sc.rmi.level_size[l] = level_sizes[l]; sc.rmi.level_off[l] = off; off += level_sizes[l]; }
+        if (none_rows && n_none) rmi_set_none_rows(sc.rmi, none_rows, n_none, ei->n_rows);
     }
     if (method == 0) Selector<SelCtx>::run_bwa(sc);
     else Selector<SelCtx>::run_seeded(sc);
@@ -293,6 +322,54 @@ int emu_rmi_lookup(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint
     RmiTable<decltype(pr)> t{pr, (int64_t)ei->n_rows, (int64_t)ei->n_bases, K, false};
     t.lookup(m, code, *pred, *lo, *hi);
     return t.raised ? -1 : 0;
+}
+
+// the same lookup through the resumable single-probe-site machine (what the kernels run)
+int emu_rmi_search(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint32_t* level_sizes, const double* coef,
+                   const double* intercept, uint64_t code, int64_t* lo, int64_t* hi, uint32_t* n_probes) {
+    RmiModel m; memset(&m, 0, sizeof(m));
+    m.K = K; m.n_levels = n_levels; m.coef = coef; m.intercept = intercept;
+    uint32_t off = 0;
+    for (uint32_t l = 0; l < n_levels; ++l) { m.level_size[l] = level_sizes[l]; m.level_off[l] = off; off += level_sizes[l]; }
+    auto sa = [&](uint64_t r) { return ei->sa[r]; };
+    auto tx = [&](uint64_t w) { return ei->text[w]; };
+    SaTextProbe<decltype(sa), decltype(tx)> pr{sa, tx};
+    RmiSearch rs;
+    rs.begin(m, code, (int64_t)ei->n_rows, (int64_t)ei->n_bases);
+    uint32_t np = 0;
+    while (rs.pending()) {
+        int64_t s; uint64_t c64;
+        pr(rs.row(), s, c64);
+        rs.feed(s, c64);
+        ++np;
+    }
+    *lo = rs.out_lo; *hi = rs.out_hi; *n_probes = np;
+    return rs.raised ? -1 : 0;
+}
+
+// the error-bounded fast search; *hazard = 1 when it defers to the literal search
+int emu_rmi_fast(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint32_t* level_sizes, const double* coef,
+                 const double* intercept, uint32_t n_none, const uint32_t* none_rows, uint64_t code, int64_t* lo, int64_t* hi,
+                 uint32_t* hazard, uint32_t* n_probes) {
+    RmiModel m; memset(&m, 0, sizeof(m));
+    m.K = K; m.n_levels = n_levels; m.coef = coef; m.intercept = intercept;
+    uint32_t off = 0;
+    for (uint32_t l = 0; l < n_levels; ++l) { m.level_size[l] = level_sizes[l]; m.level_off[l] = off; off += level_sizes[l]; }
+    rmi_set_none_rows(m, none_rows, n_none, ei->n_rows);
+    auto sa = [&](uint64_t r) { return ei->sa[r]; };
+    auto tx = [&](uint64_t w) { return ei->text[w]; };
+    SaTextProbe<decltype(sa), decltype(tx)> pr{sa, tx};
+    RmiFast rf;
+    rf.begin(m, code, ei->n_rows, (int64_t)ei->n_bases);
+    uint32_t np = 0;
+    while (rf.pending()) {
+        int64_t s; uint64_t c64;
+        pr(rf.row(), s, c64);
+        rf.feed(m, s, c64);
+        ++np;
+    }
+    *lo = rf.out_lo; *hi = rf.out_hi; *hazard = rf.hazard ? 1u : 0u; *n_probes = np;
+    return 0;
 }
 
 }  // extern "C"

@@ -39,7 +39,11 @@ class Emu:
         self.lib = C.CDLL(build())
         P, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
         self.lib.emu_sweep.argtypes = [C.POINTER(EmuIndex), P, u32, P, u32, C.POINTER(u64), u32, P]
-        self.lib.emu_smem.argtypes = [C.POINTER(EmuIndex), C.c_int, P, u32, u32, u32, P, u32, P, P, P, P, u32, u32, P]
+        self.lib.emu_smem.argtypes = [C.POINTER(EmuIndex), C.c_int, P, u32, u32, u32, P, u32, P, P, P, P, u32, u32, P, u32, P]
+        self.lib.emu_rmi_fast.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u32, P, u64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                          C.POINTER(u32), C.POINTER(u32)]
+        self.lib.emu_rmi_search.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                            C.POINTER(u32)]
         self.lib.emu_seed_build.argtypes = [C.POINTER(EmuIndex), u32, P]
         self.lib.emu_counters.argtypes = [P, C.c_int]
         self.lib.emu_lut_build.argtypes = [C.POINTER(EmuIndex), u32, P]
@@ -72,6 +76,7 @@ class Emu:
         self._lut = {}
         self._seed = {}
         self.seed_K = 0          # seed table used by sweep()/smem(); 0 = plain stepping
+        self.rmi_fast = False    # smem(2, ...): try the error-bounded RmiFast search before the literal one
 
     def seed_table(self, K):
         if K not in self._seed:
@@ -89,6 +94,10 @@ class Emu:
         out = np.zeros(8, np.uint64)
         self.lib.emu_counters(out.ctypes.data, 1 if reset else 0)
         return out
+
+    def none_rows(self, K):
+        """Sorted rows whose suffix is shorter than K (get_ref_seq returns None there, RMI_LUT.py:89-92)."""
+        return np.sort(np.nonzero(self.sa.astype(np.int64) - 1 + K > int(self.info.n_bases))[0]).astype(np.uint32)
 
     def pack_read(self, q):
         lens = np.asarray([len(q)], np.uint32)
@@ -125,11 +134,12 @@ class Emu:
             ls = np.asarray(rmi["level_sizes"], np.uint32)
             coef = np.ascontiguousarray(rmi["coef"], np.float64)
             icpt = np.ascontiguousarray(rmi["intercept"], np.float64)
+            nr = self.none_rows(K) if self.rmi_fast else np.zeros(0, np.uint32)
             n = self.lib.emu_smem(C.byref(self.e), 2, w.ctypes.data, len(q), min_len, K, None, len(ls), ls.ctypes.data,
-                                  coef.ctypes.data, icpt.ctypes.data, out.ctypes.data, cap, sk, st)
+                                  coef.ctypes.data, icpt.ctypes.data, out.ctypes.data, cap, sk, st, len(nr), nr.ctypes.data if len(nr) else None)
         else:
             n = self.lib.emu_smem(C.byref(self.e), method, w.ctypes.data, len(q), min_len, K, lut_p, 0, None, None, None,
-                                  out.ctypes.data, cap, sk, st)
+                                  out.ctypes.data, cap, sk, st, 0, None)
         if n == -1:
             return "raises"
         if n == -2:
@@ -147,6 +157,35 @@ class Emu:
         st = self.lib.emu_rmi_lookup(C.byref(self.e), rmi["K"], len(ls), ls.ctypes.data, coef.ctypes.data, icpt.ctypes.data,
                                      C.c_uint64(code), C.byref(pred), C.byref(lo), C.byref(hi))
         return st, pred.value, lo.value, hi.value
+
+
+def _rmi_search(self, rmi, code):
+    """(status, lo, hi, n_probes) through RmiSearch, the single-probe-site machine the kernels run."""
+    ls = np.asarray(rmi["level_sizes"], np.uint32)
+    coef = np.ascontiguousarray(rmi["coef"], np.float64)
+    icpt = np.ascontiguousarray(rmi["intercept"], np.float64)
+    lo, hi, npb = C.c_int64(), C.c_int64(), C.c_uint32()
+    st = self.lib.emu_rmi_search(C.byref(self.e), rmi["K"], len(ls), ls.ctypes.data, coef.ctypes.data, icpt.ctypes.data,
+                                 C.c_uint64(code), C.byref(lo), C.byref(hi), C.byref(npb))
+    return st, lo.value, hi.value, npb.value
+
+
+Emu.rmi_search = _rmi_search
+
+
+def _rmi_fast(self, rmi, code):
+    """(hazard, lo, hi, n_probes) through RmiFast, the error-bounded search of the common case."""
+    ls = np.asarray(rmi["level_sizes"], np.uint32)
+    coef = np.ascontiguousarray(rmi["coef"], np.float64)
+    icpt = np.ascontiguousarray(rmi["intercept"], np.float64)
+    nr = self.none_rows(rmi["K"])
+    lo, hi, hz, npb = C.c_int64(), C.c_int64(), C.c_uint32(), C.c_uint32()
+    self.lib.emu_rmi_fast(C.byref(self.e), rmi["K"], len(ls), ls.ctypes.data, coef.ctypes.data, icpt.ctypes.data, len(nr), nr.ctypes.data,
+                          C.c_uint64(code), C.byref(lo), C.byref(hi), C.byref(hz), C.byref(npb))
+    return bool(hz.value), lo.value, hi.value, npb.value
+
+
+Emu.rmi_fast_lookup = _rmi_fast
 
 
 def records_to_dict(q, recs):

@@ -407,3 +407,59 @@ def test_low_complexity_reads_with_seed_table(gs):
     for K in (2, 5, 8):
         m.device_index.build_seed_table(K)
         assert _dicts(reads, gs.SMEM(m).get_SMEMS_batch(reads, 1)) == exp
+
+
+def test_rmi_fast_search_changes_nothing(gs):
+    """The error-bounded fast search (enabled by the None-row list) and the literal search give identical records,
+    statuses included, on a 2 Mbp reference with poor and good models (many hazards vs almost none)."""
+    import bench
+    L = 151
+    ref, reads, _ = _synthetic(2_000_000, 12_000, L, 31, 0.015)
+    reads[:1500] = np.random.default_rng(2).integers(0, 4, (1500, L), dtype=np.uint8)
+    reads[1500:1600, :60] = 0                                            # poly-A heads: the smallest k-mers, row 0 territory
+    idx = gs.DeviceIndex.build_on_device(ref).build_seed_table()
+    batch = gs.ReadBatch.from_codes(reads, L)
+    e = gs.Engine(idx, len(reads), L, mems_per_read=64, recs_per_read=64)
+    for K, experts in ((9, (16, 512)), (11, (64, 4096)), (8, (1, 1))):
+        rmi = bench.train_rmi(idx, K, experts, idx.device)                # probe table + None rows
+        assert rmi.c.n_none_rows == K
+        fast = e.run(gs.METHOD_RMI, batch, rmi=rmi)
+        fr, fo, fs = fast.records.copy(), fast.offsets.copy(), fast.status.copy()
+        rmi.c.none_rows, rmi.c.n_none_rows = None, 0                      # literal search only
+        lit = e.run(gs.METHOD_RMI, batch, rmi=rmi)
+        assert np.array_equal(fo, lit.offsets) and np.array_equal(fr, lit.records) and np.array_equal(fs, lit.status)
+
+
+def test_team_selection_kernels_equal_default(gs):
+    """GSM_SELECT_TEAMS=3 runs LUT/RMI selection by 16-lane teams (kept as a measured alternative): same records.
+    The switch is read once per process, so the team run happens in a child process."""
+    import subprocess
+    import sys
+    import tempfile
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import bench, genie_smem_b200 as g
+from tests.test_gpu_parity import _synthetic
+ref, reads, _ = _synthetic(1_500_000, 6000, 151, 5, 0.015)
+reads[:600] = np.random.default_rng(1).integers(0, 4, (600, 151), dtype=np.uint8)
+idx = g.DeviceIndex.build_on_device(ref).build_seed_table()
+batch = g.ReadBatch.from_codes(reads, 151)
+e = g.Engine(idx, len(reads), 151, mems_per_read=64, recs_per_read=64)
+rmi = bench.train_rmi(idx, 10, (32, 1024), idx.device)
+out = {}
+for name, m, kw in (("lut", g.METHOD_LUT, {"K": 9, "lut": g.lut_build(idx, 9)}), ("rmi", g.METHOD_RMI, {"rmi": rmi}), ("rmi17", g.METHOD_RMI, {"rmi": bench.train_rmi(idx, 17, (32, 1024), idx.device)})):
+    r = e.run(m, batch, **kw)
+    out[name + "_rec"] = r.records.copy(); out[name + "_off"] = r.offsets.copy(); out[name + "_st"] = r.status.copy()
+np.savez(sys.argv[1], **out)
+''' % (gu.ROOT if hasattr(gu, "ROOT") else __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))),)
+    import os
+    res = []
+    with tempfile.TemporaryDirectory() as d:
+        for mode in ("0", "3"):
+            path = os.path.join(d, f"m{mode}.npz")
+            subprocess.check_call([sys.executable, "-c", code, path], env=dict(os.environ, GSM_SELECT_TEAMS=mode))
+            res.append(dict(np.load(path)))
+    assert res[0].keys() == res[1].keys() and len(res[0]["rmi_rec"]) > 0
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k

@@ -36,15 +36,45 @@ def test_device_layout_lut_equals_reference_table(emus):
 def test_rmi_lookup_logic(emus, tag, name):
     _, em = emus[name]
     p = gu.load_rmi(tag)
+    n_fast = 0
     for q, pred, lo, hi in gu.load_json(f"rmi_lookups_{tag}.json.gz")[::3]:
         code = 0
         for ch in q:
             code = code << 2 | "ACGT".index(ch)
         s, gp, glo, ghi = em.rmi_lookup(p, code)
+        s2, lo2, hi2, _ = em.rmi_search(p, code)          # the resumable machine the kernels run
+        hz, lo3, hi3, _ = em.rmi_fast_lookup(p, code)     # the error-bounded fast search (defers on a hazard)
+        n_fast += not hz
         if pred is None:
-            assert s == -1
+            assert s == -1 and s2 == -1 and hz
         else:
             assert s == 0 and gp == pred and (glo, ghi) == (lo, hi)
+            assert s2 == 0 and (lo2, hi2) == (lo, hi)
+            assert hz or (lo3, hi3) == (lo, hi), q
+    assert n_fast > 0.8 * len(gu.load_json(f"rmi_lookups_{tag}.json.gz")[::3])
+
+
+def test_rmi_search_machine_equals_literal_search_on_bad_models(emus):
+    """Differential test of RmiSearch against the literal RmiTable on deliberately poor models: predictions far off,
+    negative, beyond the table -- the paths where the reference wraps (negative rows), skips None rows or raises."""
+    g, em = emus["medium_data"]
+    rng = random.Random(11)
+    n = em.n_rows
+    for trial in range(60):
+        K = rng.choice([3, 6, 9])
+        scale = rng.choice([0.0, 0.3, 1.0, 1.7]) * n / 4 ** K
+        rmi = {"K": K, "level_sizes": [1, 4, 1][:rng.choice([1, 3])] if False else [1], "coef": [scale], "intercept": [rng.uniform(-1.5 * n, 1.5 * n) if trial % 3 == 0 else rng.uniform(-40, 40)]}
+        for _ in range(150):
+            code = rng.randrange(4 ** K)
+            a = em.rmi_lookup(rmi, code)
+            b = em.rmi_search(rmi, code)
+            f = em.rmi_fast_lookup(rmi, code)
+            assert (a[0] == -1) == (b[0] == -1), (rmi, code)
+            if a[0] == 0:
+                assert (a[2], a[3]) == (b[1], b[2]), (rmi, code)
+                assert f[0] or (f[1], f[2]) == (a[2], a[3]), (rmi, code)     # no hazard => identical bounds
+            else:
+                assert f[0], (rmi, code)                                     # the reference raises => never the fast path
 
 
 @pytest.mark.parametrize("seed_K", [0, 5, 9])
@@ -66,6 +96,7 @@ def test_sweep_and_select_logic_vs_reference(emus, fname, stride, seed_K):
             assert records_to_dict(q, em.smem(1, q, 1, g["K_lut"])) == e
     for tag, exp in g["rmi"].items():
         p = gu.load_rmi(tag)
+        em.rmi_fast = seed_K != 0          # half of the runs go through the error-bounded fast search first
         for q, e in list(zip(reads, exp))[::stride]:
             if e is None:
                 continue
