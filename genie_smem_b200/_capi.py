@@ -70,6 +70,8 @@ EXPORTS = {
     "gsm_backsearch_batch": (C.c_int, [C.POINTER(DevIndex), C.POINTER(DevReads), C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_backsearch_add_one_batch": (C.c_int, [C.POINTER(DevIndex), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_sa_lookup_batch": (C.c_int, [C.POINTER(DevIndex), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gsm_sa_sample_build": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p]),
+    "gsm_locate_sampled_batch": (C.c_int, [C.POINTER(DevIndex), C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_lut_build": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p]),
     "gsm_seed_table_build": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p]),
     "gsm_smem_batch": (C.c_int, [C.c_int, C.POINTER(DevIndex), C.POINTER(DevReads), C.c_uint32, C.c_uint32, C.c_void_p,

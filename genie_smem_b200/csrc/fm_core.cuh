@@ -150,6 +150,29 @@ GSM_HD StepOut step_single(LoadHalf load, uint32_t P0, uint32_t P1, uint32_t c, 
     return finish_step(eq[0], eq[1], lt[1] - lt[0], P0, P1, c, Cc, primary);
 }
 
+// LF mapping by ONE thread: row r -> the row of the suffix that starts one base earlier (suffix_array[LF(r)] =
+// suffix_array[r] - 1).  One bucket gives both the BWT symbol at r and its rank.  Must not be called for r == primary
+// (that row's BWT symbol is '$': its suffix starts at text position 0).  Used by the sampled-SA locate kernel.
+template <typename LoadHalf>
+GSM_HD uint32_t lf_single(LoadHalf load, uint32_t r, const uint32_t* C, uint32_t primary) {
+    uint32_t b, off;
+    split192(r, b, off);
+    const Half h0 = load((uint64_t)b * 2), h1 = load((uint64_t)b * 2 + 1);
+    const uint32_t g = off >= 96u ? 1u : 0u, o = off - 96u * g;
+    const Half& hs = g ? h1 : h0;
+    const uint32_t lw = o < 32u ? hs.l0 : (o < 64u ? hs.l1 : hs.l2);
+    const uint32_t hw = o < 32u ? hs.h0 : (o < 64u ? hs.h1 : hs.h2);
+    const uint32_t c = ((lw >> (o & 31u)) & 1u) | (((hw >> (o & 31u)) & 1u) << 1);
+    const SymK k = sym_consts(c);
+    uint32_t e0, l0, e1, l1;
+    half_header(h0, c, 0u, e0, l0);
+    half_header(h1, c, 1u, e1, l1);
+    const uint32_t acc = half_counts(h0, off, k, 0u) + half_counts(h1, off, k, 1u);
+    uint32_t rank = e0 + e1 + (acc & 0xFFu);
+    if (c == 0u && r > primary) rank -= 1u;            // the '$' slot is stored as A
+    return C[c] + rank;
+}
+
 // Packed sequences (reads and text) are MSB-first: base i lives in bits [30-2(i%16), 32-2(i%16))
 // of word i/16.
 GSM_HD uint32_t base_msb(const uint32_t* words, uint32_t pos) { return (words[pos >> 4] >> (30u - 2u * (pos & 15u))) & 3u; }

@@ -615,6 +615,29 @@ __global__ void k_sa_lookup(const uint32_t* sa, uint64_t n_rows, uint64_t n, con
 }
 
 // LUT.generate_lut (reference SMEM/LUT.py:15-35) as a dense table: one thread per k-mer code.
+// Sampled suffix array (the "2-bit BWT + sampled SA" index of BASELINE.json configs[3]): ssa[i] = suffix_array[i * S].
+__global__ void k_sa_sample(const uint32_t* sa, uint64_t n_rows, uint32_t S, uint32_t* ssa) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i * S < n_rows) ssa[i] = __ldg(sa + i * S);
+}
+
+// row -> 1-based text position without the full suffix array: walk LF until a sampled row (or the '$' row) is reached.
+// ExactMatch.get_position(s) (ExactMatch.py:191-199); expected (S-1)/2 bucket fetches per row.
+__global__ void __launch_bounds__(128) k_locate_sampled(const uint4* fwd, IndexMeta meta, const uint32_t* ssa, uint32_t S, uint64_t n,
+                                                         const uint32_t* rows, uint32_t* pos) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
+    uint32_t r = __ldg(rows + i), t = 0;
+    if (r >= meta.n_rows) { pos[i] = 0u; return; }
+    for (;;) {
+        if (r == meta.prim_f) { pos[i] = 1u + t; return; }
+        if (r % S == 0u) { pos[i] = __ldg(ssa + r / S) + t; return; }
+        r = lf_single(load, r, meta.C, meta.prim_f);
+        ++t;
+    }
+}
+
 __global__ void k_lut_build(const uint4* fwd, IndexMeta meta, uint32_t K, uint64_t n_codes, uint2* table) {
     const uint64_t code = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (code >= n_codes) return;
@@ -814,6 +837,27 @@ int gsm_sa_lookup_batch(const gsm_dev_index* ix, uint64_t n, const uint32_t* row
     if (st) return st;
     if (n == 0) return GSM_OK;
     k_sa_lookup<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ix->sa, ix->n_rows, n, rows, pos);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_sa_sample_build(const gsm_dev_index* ix, uint32_t sample, uint32_t* ssa, void* stream) {
+    if (!ix || !ix->sa || !ssa || sample == 0) return fail(GSM_E_INVALID, "gsm_sa_sample_build: needs the full suffix array on the device and sample >= 1");
+    int st = device_ready();
+    if (st) return st;
+    const uint64_t n = (ix->n_rows + sample - 1) / sample;
+    k_sa_sample<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ix->sa, ix->n_rows, sample, ssa);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_locate_sampled_batch(const gsm_dev_index* ix, const uint32_t* ssa, uint32_t sample, uint64_t n, const uint32_t* rows, uint32_t* pos,
+                             void* stream) {
+    if (!ix || !ix->fwd_buckets || !ssa || sample == 0 || (n && (!rows || !pos))) return fail(GSM_E_INVALID, "gsm_locate_sampled_batch: null");
+    int st = device_ready();
+    if (st) return st;
+    if (n == 0) return GSM_OK;
+    k_locate_sampled<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>((const uint4*)ix->fwd_buckets, make_meta(ix), ssa, sample, n, rows, pos);
     GSM_CUDA(cudaGetLastError());
     return GSM_OK;
 }

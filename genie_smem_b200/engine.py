@@ -290,6 +290,38 @@ class DeviceIndex:
         self._bind()
         return self
 
+    def build_sampled_sa(self, sample=32, drop_full=False):
+        """Keep every `sample`-th suffix-array value (gsm_sa_sample_build); positions then come from locate() by LF
+        walking.  drop_full releases the 4-byte-per-base suffix array (RMI-SMEM and sa_lookup need it)."""
+        if self.sa is None:
+            raise ValueError("the sampled suffix array is derived from the full one")
+        n = (self.n_rows + sample - 1) // sample
+        self.ssa = torch.empty(n, dtype=torch.int32, device=self.device)
+        self.sa_sample = int(sample)
+        with torch.cuda.device(self.device):
+            capi.check(capi.lib.gsm_sa_sample_build(C.byref(self.c), self.sa_sample, _ptr(self.ssa), _stream()))
+        if drop_full:
+            torch.cuda.synchronize(self.device)
+            self.sa = None
+            self._bind()
+        return self
+
+    def locate(self, rows):
+        """rows -> 1-based text positions (ExactMatch.get_position(s), ExactMatch.py:191-199): direct suffix-array reads
+        when the full array is resident, else LF walks to the sampled rows."""
+        rows = np.ascontiguousarray(rows, np.uint32)
+        if rows.size == 0:
+            return np.zeros(0, np.uint32)
+        if self.sa is not None:
+            return sa_lookup(self, rows)
+        if getattr(self, "ssa", None) is None:
+            raise ValueError("no suffix array on the device: call build_sampled_sa() before dropping it")
+        with torch.cuda.device(self.device):
+            r = torch.from_numpy(rows.view(np.int32)).to(self.device)
+            out = torch.empty_like(r)
+            capi.check(capi.lib.gsm_locate_sampled_batch(C.byref(self.c), _ptr(self.ssa), self.sa_sample, rows.size, _ptr(r), _ptr(out), _stream()))
+        return out.cpu().numpy().view(np.uint32)
+
     def drop_seed_table(self):
         self.seed_table, self.seed_K = None, 0
         self._bind()

@@ -171,11 +171,11 @@ class ExactMatch:
         return sorted(self.get_positions(start, end))
 
     def get_position(self, suffix_array_index):
-        return int(eng.sa_lookup(self.device_index, [suffix_array_index % self.ref_size])[0])
+        return int(self.device_index.locate([suffix_array_index % self.ref_size])[0])
 
     def get_positions(self, suffix_start, suffix_end):
         rows = np.arange(suffix_start, suffix_end + 1, dtype=np.int64) % self.ref_size
-        return [int(x) for x in eng.sa_lookup(self.device_index, rows)]
+        return [int(x) for x in self.device_index.locate(rows)]
 
 
 class _LutView:

@@ -229,6 +229,14 @@ int gsm_backsearch_add_one_batch(const gsm_dev_index* idx, uint64_t n, const uin
 int gsm_sa_lookup_batch(const gsm_dev_index* idx, uint64_t n, const uint32_t* rows, uint32_t* pos,
                         void* stream);
 
+/* Sampled suffix array: ssa[i] = suffix_array[i * sample], ceil(n_rows / sample) entries of device memory (needs idx->sa
+ * once; afterwards the 4-byte-per-base suffix array can be dropped unless RMI-SMEM is used).  gsm_locate_sampled_batch:
+ * rows -> 1-based text positions by LF-walking to the next sampled row -- ExactMatch.get_position(s)
+ * (ExactMatch.py:191-199) with n/sample words instead of n; rows >= n_rows give 0. */
+int gsm_sa_sample_build(const gsm_dev_index* idx, uint32_t sample, uint32_t* ssa, void* stream);
+int gsm_locate_sampled_batch(const gsm_dev_index* idx, const uint32_t* ssa, uint32_t sample, uint64_t n,
+                             const uint32_t* rows, uint32_t* pos, void* stream);
+
 /* Dense k-mer table: entry[code] = {lo, cnt} for every 4^K code, cnt == 0 for absent k-mers.
  * Replaces LUT.generate_lut (LUT.py:15-35); table: 4^K * 8 bytes of device memory. */
 int gsm_lut_build(const gsm_dev_index* idx, uint32_t K, uint32_t* table, void* stream);

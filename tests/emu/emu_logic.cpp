@@ -309,6 +309,21 @@ void emu_seed_build(const EmuIndex* ei, uint32_t K, uint32_t* table) {
     }
 }
 
+// rows -> 1-based positions through lf_single and a sampled suffix array (what k_locate_sampled runs)
+void emu_locate(const EmuIndex* ei, uint32_t S, uint64_t n, const uint32_t* rows, uint32_t* pos) {
+    const Half* fwd = (const Half*)ei->fwd;
+    auto load = [&](uint64_t idx) { return fwd[idx]; };
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t r = rows[i], t = 0;
+        for (;;) {
+            if (r == ei->prim_f) { pos[i] = 1u + t; break; }
+            if (r % S == 0u) { pos[i] = ei->sa[r] + t; break; }
+            r = lf_single(load, r, ei->C, ei->prim_f);
+            ++t;
+        }
+    }
+}
+
 // get_suffix_rmi for one code
 int emu_rmi_lookup(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint32_t* level_sizes, const double* coef,
                    const double* intercept, uint64_t code, double* pred, int64_t* lo, int64_t* hi) {

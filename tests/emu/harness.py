@@ -44,6 +44,7 @@ class Emu:
                                           C.POINTER(u32), C.POINTER(u32)]
         self.lib.emu_rmi_search.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                             C.POINTER(u32)]
+        self.lib.emu_locate.argtypes = [C.POINTER(EmuIndex), u32, u64, P, P]
         self.lib.emu_seed_build.argtypes = [C.POINTER(EmuIndex), u32, P]
         self.lib.emu_counters.argtypes = [P, C.c_int]
         self.lib.emu_lut_build.argtypes = [C.POINTER(EmuIndex), u32, P]
@@ -98,6 +99,12 @@ class Emu:
     def none_rows(self, K):
         """Sorted rows whose suffix is shorter than K (get_ref_seq returns None there, RMI_LUT.py:89-92)."""
         return np.sort(np.nonzero(self.sa.astype(np.int64) - 1 + K > int(self.info.n_bases))[0]).astype(np.uint32)
+
+    def locate(self, rows, sample):
+        rows = np.ascontiguousarray(rows, np.uint32)
+        out = np.zeros(len(rows), np.uint32)
+        self.lib.emu_locate(C.byref(self.e), sample, len(rows), rows.ctypes.data, out.ctypes.data)
+        return out
 
     def pack_read(self, q):
         lens = np.asarray([len(q)], np.uint32)

@@ -89,3 +89,18 @@ def test_device_build_rejects_non_acgt(gs):
         gs.DeviceIndex.build_on_device("ACGTNACGT")
     with pytest.raises(KeyError):
         gs.DeviceIndex.build_on_device("ACGTNACGT")
+
+
+@pytest.mark.parametrize("sample", [1, 5, 32, 64])
+def test_sampled_sa_locate_equals_full_sa(gs, sample):
+    """k_locate_sampled (LF walk to every sample-th row) == direct suffix-array reads, full SA dropped afterwards."""
+    rng = np.random.default_rng(12)
+    for text in ("ACGTA", "A" * 300 + "C" + "A" * 77, "".join("ACGT"[c] for c in rng.integers(0, 4, 150_000))):
+        idx = gs.DeviceIndex.build_on_device(text)
+        sa = idx.suffix_array_host().copy()
+        rows = np.arange(len(sa), dtype=np.uint32) if len(sa) < 2000 else rng.integers(0, len(sa), 30_000).astype(np.uint32)
+        assert np.array_equal(idx.locate(rows), sa[rows])
+        idx.build_sampled_sa(sample, drop_full=True)
+        assert idx.sa is None
+        assert np.array_equal(idx.locate(rows), sa[rows])
+        assert np.array_equal(idx.locate(np.array([len(sa) + 5], np.uint32)), np.array([0], np.uint32))

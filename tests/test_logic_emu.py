@@ -189,3 +189,13 @@ def test_rmi_vectorised_fit_matches_loop_fit():
         b = RMI(experts).fit(keys, rows, vectorised=True)
         assert a.level_sizes == b.level_sizes and a.coef.shape == b.coef.shape
         assert np.abs(a.predict(keys) - b.predict(keys)).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["small_data", "medium_data", "big_data"])
+def test_lf_walk_to_sampled_rows_recovers_the_suffix_array(emus, name):
+    """lf_single + sampled SA (the locate kernel's arithmetic) == the reference's suffix_array, every row."""
+    g, em = emus[name]
+    sa = np.asarray(g["suffix_array"], np.uint32)
+    rows = np.arange(len(sa), dtype=np.uint32) if len(sa) < 5000 else np.random.default_rng(1).integers(0, len(sa), 4000).astype(np.uint32)
+    for sample in (1, 2, 7, 32, 1 << 30):
+        assert np.array_equal(em.locate(rows, sample), sa[rows]), sample
