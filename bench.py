@@ -230,6 +230,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        from genie_smem_b200 import sharding
+        cpus = sharding.bind_to_gpu_numa(local_rank)                # pinned host buffers land on the GPU's NUMA node
+        log(f"[rank {rank}] bound to {len(cpus) if cpus else 'no'} CPUs next to GPU {local_rank}")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- setup: reference, index (built on the GPU), reads, LUT, RMI

@@ -60,6 +60,46 @@ __global__ void __launch_bounds__(256) k_pack_reads(const uint8_t* bases, const 
     }
 }
 
+// Fixed-length reads (the FASTQ case): a block takes PACK_R consecutive reads = one contiguous byte range, stages it in
+// shared memory with coalesced 16-byte loads, and every thread packs whole 16-base words from there -- all lanes busy,
+// global traffic at full sector efficiency (the per-read kernel above keeps 12 of 32 lanes busy on byte loads).
+constexpr int PACK_THREADS = 256;
+
+__global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_fixed(const uint8_t* bases, uint32_t L, uint32_t reads_per_block, const uint32_t* chunk_off,
+                                                                   uint64_t n_reads, int ascii, uint32_t* packed, uint32_t* len_out,
+                                                                   unsigned long long* bad) {
+    extern __shared__ uint4 s_raw[];
+    uint8_t* sb = reinterpret_cast<uint8_t*>(s_raw);
+    const uint64_t r0 = (uint64_t)blockIdx.x * reads_per_block;
+    if (r0 >= n_reads) return;
+    const uint32_t R = (uint32_t)((n_reads - r0) < reads_per_block ? (n_reads - r0) : reads_per_block);
+    // absolute byte range of this block's reads, widened to whole aligned 16-byte units (device allocations are at least
+    // 256-byte aligned and sized, so the widened range never leaves the caller's allocation)
+    const uintptr_t p0 = reinterpret_cast<uintptr_t>(bases) + r0 * L, p1 = p0 + (uintptr_t)R * L;
+    const uintptr_t a0 = p0 & ~(uintptr_t)15;
+    const uint32_t n16 = (uint32_t)((p1 - a0 + 15) >> 4);
+    for (uint32_t i = threadIdx.x; i < n16; i += PACK_THREADS) s_raw[i] = __ldg(reinterpret_cast<const uint4*>(a0) + i);
+    __syncthreads();
+    const uint32_t skew = (uint32_t)(p0 - a0);
+    const uint32_t wpr = ((L + 63u) / 64u) * 4u;                           // output words per read
+    for (uint32_t w = threadIdx.x; w < R * wpr; w += PACK_THREADS) {
+        const uint32_t r = w / wpr, k = w - r * wpr;
+        const uint8_t* src = sb + skew + (size_t)r * L + k * 16u;
+        uint32_t v = 0;
+        for (uint32_t t = 0; t < 16u && k * 16u + t < L; ++t) {
+            uint32_t c = src[t];
+            if (ascii) c = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+            if (c > 3u) {
+                atomicMin(bad, (unsigned long long)(r0 + r));
+                c = 0;
+            }
+            v |= c << (30u - 2u * t);
+        }
+        packed[(uint64_t)chunk_off[r0 + r] * 4u + k] = v;
+        if (len_out && k == 0) len_out[r0 + r] = L;
+    }
+}
+
 }  // namespace
 }  // namespace gsm
 
@@ -76,6 +116,19 @@ int gsm_pack_reads_device(const void* bases, const uint64_t* base_off, uint32_t 
     if (n_reads == 0) return GSM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     GSM_CUDA(cudaMemsetAsync(scratch8, 0xFF, 8, st));
+    if (!base_off && fixed_len <= 2048) {
+        // reads per block: 64, fewer for long reads so that the staged bytes fit 40 KB of shared memory
+        uint32_t rpb = 64;
+        while (rpb > 1 && (uint64_t)rpb * fixed_len + 32 > 40960) rpb >>= 1;
+        const size_t smem = (((size_t)rpb * fixed_len + 31) / 16 + 1) * 16;
+        const uint64_t blocks = (n_reads + rpb - 1) / rpb;
+        if (blocks < (1ull << 31)) {
+            k_pack_reads_fixed<<<(unsigned)blocks, PACK_THREADS, smem, st>>>((const uint8_t*)bases, fixed_len, rpb, chunk_off, n_reads, (int)ascii,
+                                                                           (uint32_t*)packed, len_out, (unsigned long long*)scratch8);
+            GSM_CUDA(cudaGetLastError());
+            return GSM_OK;
+        }
+    }
     const uint64_t warps = n_reads;
     const unsigned grid = (unsigned)std::min<uint64_t>((warps + 7) / 8, 148ull * 32);
     k_pack_reads<<<grid, 256, 0, st>>>((const uint8_t*)bases, (const unsigned long long*)base_off, fixed_len, chunk_off, n_reads, (int)ascii,

@@ -11,6 +11,28 @@ import torch.distributed as dist
 from .engine import RECORD_DTYPE
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity) so that the pinned host buffers of the
+    end-to-end path are first-touched on the GPU's NUMA node.  Best effort: returns the CPU set, or None."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[device_index]) if visible and visible.split(",")[device_index].isdigit() else device_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def shard_range(n_reads, rank, world):
     """Contiguous block [lo, hi) of reads for `rank`: rank r gets reads [r*N/G, (r+1)*N/G)."""
     return (n_reads * rank) // world, (n_reads * (rank + 1)) // world
@@ -36,16 +58,30 @@ def gather_records(records, counts_per_read, dst=0, group=None, device=None):
     dist.all_gather(all_sizes, sizes, group=group)
     all_sizes = torch.stack(all_sizes).cpu().numpy()
     max_rec, max_cnt = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
-    pad_rec = torch.zeros(max(max_rec, 1), dtype=torch.uint8, device=device)
+    pad_rec = torch.empty(max(max_rec, 1), dtype=torch.uint8, device=device)
     pad_rec[: rec_u8.numel()] = rec_u8
-    pad_cnt = torch.zeros(max(max_cnt, 1), dtype=torch.int64, device=device)
+    pad_cnt = torch.empty(max(max_cnt, 1), dtype=torch.int64, device=device)
     pad_cnt[: cnt.numel()] = cnt
-    recv_rec = [torch.zeros_like(pad_rec) for _ in range(world)] if rank == dst else None
-    recv_cnt = [torch.zeros_like(pad_cnt) for _ in range(world)] if rank == dst else None
+    recv_rec = [torch.empty_like(pad_rec) for _ in range(world)] if rank == dst else None
+    recv_cnt = [torch.empty_like(pad_cnt) for _ in range(world)] if rank == dst else None
     dist.gather(pad_rec, recv_rec, dst=dst, group=group)
     dist.gather(pad_cnt, recv_cnt, dst=dst, group=group)
     if rank != dst:
         return None, None
-    recs = np.concatenate([recv_rec[r][: int(all_sizes[r, 0])].cpu().numpy() for r in range(world)]).view(RECORD_DTYPE)
-    cnts = np.concatenate([recv_cnt[r][: int(all_sizes[r, 1])].cpu().numpy() for r in range(world)])
+    n_rec = [int(all_sizes[r, 0]) for r in range(world)]
+    n_cnt = [int(all_sizes[r, 1]) for r in range(world)]
+    if device.type == "cuda":
+        # one pinned destination per array, every shard copied straight to its final place (no pageable staging, no concatenate)
+        out_rec = torch.empty(max(sum(n_rec), 1), dtype=torch.uint8, pin_memory=True)
+        out_cnt = torch.empty(max(sum(n_cnt), 1), dtype=torch.int64, pin_memory=True)
+        a = b = 0
+        for r in range(world):
+            out_rec[a:a + n_rec[r]].copy_(recv_rec[r][: n_rec[r]], non_blocking=True)
+            out_cnt[b:b + n_cnt[r]].copy_(recv_cnt[r][: n_cnt[r]], non_blocking=True)
+            a += n_rec[r]
+            b += n_cnt[r]
+        torch.cuda.synchronize(device)
+        return out_rec.numpy()[: sum(n_rec)].view(RECORD_DTYPE), out_cnt.numpy()[: sum(n_cnt)]
+    recs = np.concatenate([recv_rec[r][: n_rec[r]].numpy() for r in range(world)]).view(RECORD_DTYPE)
+    cnts = np.concatenate([recv_cnt[r][: n_cnt[r]].numpy() for r in range(world)])
     return recs, cnts

@@ -128,6 +128,8 @@ int gsm_index_build_device(const uint32_t* text2bit, uint64_t n_bases, uint32_t 
  * [base_off[r], base_off[r+1]) (device uint64, n_reads+1) or, with base_off == NULL, fixed_len bytes at
  * r*fixed_len; chunk_off (device, n_reads+1, 16-byte chunks: exclusive scan of ceil(len/64)) as in
  * gsm_pack_reads; packed receives chunk_off[n_reads]*16 bytes; len_out (optional, device) the lengths.
+ * Fixed-length batches are staged through shared memory with aligned 16-byte loads: the kernel may read up to 15 bytes
+ * before and after the byte range, inside the caller's (>= 256-byte aligned) allocation.
  * Replaces the per-string query path (ExactMatch.load_query, ExactMatch.py:104-108) for batches.
  * Asynchronous; gsm_pack_reads_device_check(scratch8) synchronises and returns GSM_E_INVALID if a read
  * held a non-ACGT byte (the reference raises KeyError, ExactMatch.py:139). */
