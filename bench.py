@@ -160,7 +160,7 @@ def parse_args():
     ap.add_argument("--ref-bases", type=int, default=0, help="reference size (default: the config's)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget per method")
     ap.add_argument("--skip-rmi", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the pipelined end-to-end path")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks of the pipelined end-to-end path")
     ap.add_argument("--seed-k", type=int, default=-1, help="K of the sweep kernel's seed table (-1 = auto, 0 = none)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
@@ -182,7 +182,7 @@ def workload_dict(args, world):
     return {"workload": f"synthetic {args.ref_bases/1e6:g} Mbp random ACGT reference (PCG64 seed {args.seed}), "
                         f"{args.reads/1e6:g} M reads x {READ_LEN} bp per GPU, exact substrings + {SUB_RATE:.0%} substitutions ({args.cfg_name})",
             "ref_bases": args.ref_bases, "reads_per_gpu": args.reads, "read_len": READ_LEN, "sub_rate": SUB_RATE,
-            "lut_K": LUT_K, "rmi_K": RMI_K, "rmi_experts": list(args.experts), "min_len": 1, "sweep_seed_table_K": args.seed_k,
+            "lut_K": LUT_K, "rmi_K": RMI_K, "rmi_experts": list(args.experts), "min_len": 1,
             "parallelism": f"reads sharded x{world}, index replicated",
             "l2_policy": f"inputs larger than L2: packed read batch {args.reads * 48 / 1e6:.0f} MB, rank buckets {bucket_mb:.0f} MB, outputs "
                          f"> 1 GB vs 126 MB L2 (at --config c3 the 67 MB of buckets are L2-resident by design; see DESIGN.md)"}
@@ -319,7 +319,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (ms_sweep * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tname = {1_000_000_000: "r01_1gbp_sweep_dram_bytes.json", 100_000_000: "r01_sweep_dram_bytes.json"}.get(args.ref_bases)
+    tname = {1_000_000_000: "r01b_1gbp_sweep_dram_bytes.json", 100_000_000: "r01_sweep_dram_bytes.json"}.get(args.ref_bases)
     if tname and os.path.exists(os.path.join(ROOT, "profiles", tname)):        # ncu --set full capture of k_sweep on this reference size
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
@@ -332,8 +332,8 @@ def main():
                 "algorithmic_bytes_per_read": round(alg_bytes / args.reads, 1), "fm_steps_per_read_min": round(steps_alg / args.reads, 2),
                 "records_per_read": round(n_rec / args.reads, 3), "ms_sweep": round(ms_sweep, 3), "ms_select_scan_gather": round(ms_sel_bwa, 3),
                 "note": "achieved = algorithmic bytes (SURVEY 8d: 128 B per necessary FM step + read + records) / k_sweep time; the access "
-                        "pattern is dependent random 64-byte fetches, whose measured ceiling on this GPU is ~50 G fetches/s = 3.2 TB/s at this "
-                        "index size (profiles/r01_probe.jsonl), not the streaming peak"}
+                        "pattern is dependent random 64-byte fetches, whose measured ceiling on this GPU is 45.9 G fetches/s = 2.9 TB/s over a "
+                        "667 MB index (tools/l2gran_probe.py, profiles/r01_notes.md), not the streaming peak"}
 
     # ---- the other two methods (device-resident)
     methods = {"bwa": {"reads_per_s": world * args.reads / (ms_bwa * 1e-3), "ms_per_step": ms_bwa}}
@@ -372,7 +372,7 @@ def main():
     v_ascii, res = e2e_time(lambda: pipe.run_ascii(g.METHOD_BWA, ascii_host, READ_LEN, min_len=1))
     e2e = {"value": v_ascii, "unit": "reads/s", "h2d_bytes_per_step": pipe.last_h2d_bytes, "d2h_bytes_per_step": pipe.last_d2h_bytes,
            "method": "bwa", "records_last_step": int(len(res.records)),
-           "api": f"PipelinedEngine.run_ascii ({args.e2e_chunks} chunks, 2 streams: raw ASCII reads H2D, GPU 2-bit packing, sweep/select, "
+           "api": f"PipelinedEngine.run_ascii ({args.e2e_chunks} chunks, 3 streams: raw ASCII reads H2D | GPU 2-bit packing, sweep, select | "
                   "records D2H, all overlapped)"}
     assert len(res.records) == n_rec, "end-to-end path and device-resident path disagree on the number of records"
     batch.to_host(pin=True)
@@ -418,7 +418,7 @@ def main():
                "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(gpu_launches),
                "clocks": clocks, "methods": methods, "records_total": total_records, "maximal_matches_per_read": round(n_mems / args.reads, 3),
                "record_gather": gather, "index_build": index.build_stats}
-        out["config"]["sweep_seed_table_K"] = int(index.c.seed_K)
+        out["sweep_seed_table_K"] = int(index.c.seed_K)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -223,6 +223,27 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
     }
 }
 
+// One phase of the error-bounded search over the windows in `mask` (bit = window), run by the whole warp in lock step:
+// a thread that finishes a window banks it and begins its next one (divergent, a few instructions), then everybody
+// meets at the single probe + straight-line feed; the warp leaves when no thread has a window left.
+template <typename Machine, typename Begin, typename Bank, typename Feed>
+__device__ __forceinline__ void phase_loop(uint32_t mask, Machine& mach, Begin begin, Bank bank, Feed feed) {
+    int cur = -1;
+    bool more = mask != 0u;
+    for (;;) {
+        while (more && !mach.busy) {
+            if (cur >= 0) { bank(cur); cur = -1; }
+            if (mask == 0u) { more = false; break; }
+            cur = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            begin(cur);
+        }
+        const bool need = more && mach.busy;
+        if (!__any_sync(FULL, need)) break;
+        if (need) feed();
+    }
+}
+
 // RMI-SMEM selection with the warp kept in lock step on the memory-bound part.  One thread per read (threads pull reads
 // grid-stride: many reads in flight hide the dependent loads of the frame machine), but the round structure of the machine
 // (select_logic.cuh) is driven warp-wide:
@@ -244,6 +265,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
     DevSelCtx<METHOD> c{a, nullptr, nullptr, a.stage + gtid * a.max_len, 0u, a.K, 0u, a.min_len, 0u, 0u, false, true};
     typename Sel::Seeded st;
     int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
+    uint64_t wcode[MAX_SEED_K];
 
     auto close_read = [&](uint8_t status) {
         if (c.raised) { status = GSM_READ_REF_RAISES; c.n_rec = 0; }
@@ -290,35 +312,50 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
         uint32_t whit = 0, redo = 0;
         // ---------------- pass 1: lookups, warp in lock step
         if (a.rmi.n_none != 0) {
-            // error-bounded search first (RmiFast); windows it declares hazardous (None rows in the bracket, prediction
-            // outside the table -- a handful per million) are redone probe for probe by the literal search below
-            RmiFast rf;
-            uint32_t i = 0;
-            int cur = -1;
-            bool more = have;
-            for (;;) {
-                while (more && !rf.pending()) {          // bank the finished search, start the next window's
-                    if (cur >= 0) {
-                        if (rf.hazard) redo |= 1u << cur;
-                        else {
-                            wlo[cur] = rf.out_lo; whi[cur] = rf.out_hi;
-                            if (rf.hit()) whit |= 1u << cur;
-                        }
-                        cur = -1;
-                    }
-                    uint32_t cpos = 0;
-                    if (!next_window(i, nwin, cpos)) { more = false; break; }
-                    cur = (int)i++;
-                    rf.begin(a.rmi, c.window_code(cpos), a.meta.n_rows, (int64_t)a.n_bases);
+            // error-bounded search (select_logic.cuh, RmiGallop / RmiLower / RmiUpper): each phase runs over ALL windows of
+            // the round as one lock-step loop with straight-line per-probe code; windows a phase declares hazardous (None
+            // rows in the bracket, prediction outside the table -- a handful per million) go to the literal search below
+            uint32_t todo = 0, lbm = 0, ubm = 0;
+            for (uint32_t i = 0; i < nwin; ++i) {           // codes and model predictions, one converged counted loop
+                const uint32_t cpos = st.first ? 0u : st.e - i;
+                if (have && (st.first || (i < st.plen && cpos + c.K <= c.L))) {
+                    wcode[i] = c.window_code(cpos);
+                    wlo[i] = RmiGallop::predicted_row(a.rmi, wcode[i], a.meta.n_rows);
+                    todo |= 1u << i;
                 }
-                const bool need = more && rf.pending();
-                if (!__any_sync(FULL, need)) break;
-                if (need) {
-                    int64_t sv;
-                    uint64_t code64;
-                    c.probe_row(rf.row(), sv, code64);   // the probe site of the fast search
-                    rf.feed(a.rmi, sv, code64);
-                }
+            }
+            const int64_t nb = (int64_t)a.n_bases;
+            const uint32_t nr = a.meta.n_rows;
+            int64_t sv;
+            uint64_t c64;
+            {
+                RmiGallop ga;                                // phase A: bracket around the prediction
+                phase_loop(todo, ga,
+                           [&](int w) { ga.begin(a.rmi, wcode[w], wlo[w], nr, nb); },
+                           [&](int w) {
+                               if (ga.hazard) redo |= 1u << w;
+                               else { wlo[w] = ga.lower; whi[w] = ga.upper; lbm |= 1u << w; }
+                           },
+                           [&]() { c.probe_row(ga.row(), sv, c64); ga.feed(a.rmi, sv, c64); });
+            }
+            {
+                RmiLower lb;                                 // phase B: first row >= q
+                phase_loop(lbm, lb,
+                           [&](int w) { lb.begin(a.rmi, wcode[w], (uint32_t)wlo[w], (uint32_t)whi[w], nr, nb); },
+                           [&](int w) {
+                               wlo[w] = (int64_t)lb.hi;
+                               if (lb.hi_eq) ubm |= 1u << w;              // hit: whi[w] still holds the bracket's upper end
+                               else whi[w] = (int64_t)lb.hi - 1;          // absent: lo = hi + 1
+                           },
+                           [&]() { c.probe_row(lb.row(), sv, c64); lb.feed(sv, c64); });
+            }
+            {
+                RmiUpper ub;                                 // phase C: last row == q
+                phase_loop(ubm, ub,
+                           [&](int w) { ub.begin(a.rmi, wcode[w], (uint32_t)wlo[w], (uint32_t)whi[w], nr, nb); },
+                           [&](int w) { whi[w] = (int64_t)ub.lo; },
+                           [&]() { c.probe_row(ub.row(), sv, c64); ub.feed(sv, c64); });
+                whit |= ubm;
             }
         } else if (have) {
             uint32_t i = 0, cpos = 0;
@@ -435,19 +472,28 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select_team(const SelectArgs
                 const uint64_t code = visit ? c.window_code(cpos) : 0ull;
                 bool literal = visit;
                 if (a.rmi.n_none != 0) {
-                    RmiFast rf;
-                    if (visit) rf.begin(a.rmi, code, a.meta.n_rows, (int64_t)a.n_bases);
-                    for (;;) {
-                        const bool need = rf.pending();
-                        if (!__any_sync(tmask, need)) break;
-                        if (need) {
-                            int64_t sv;
-                            uint64_t code64;
-                            c.probe_row(rf.row(), sv, code64);
-                            rf.feed(a.rmi, sv, code64);
-                        }
+                    const int64_t nb = (int64_t)a.n_bases;
+                    const uint32_t nr = a.meta.n_rows;
+                    int64_t sv;
+                    uint64_t c64;
+                    RmiGallop ga;
+                    if (visit) ga.begin(a.rmi, code, RmiGallop::predicted_row(a.rmi, code, nr), nr, nb);
+                    while (__any_sync(tmask, ga.busy))
+                        if (ga.busy) { c.probe_row(ga.row(), sv, c64); ga.feed(a.rmi, sv, c64); }
+                    const bool okw = visit && !ga.hazard;
+                    RmiLower lb;
+                    if (okw) lb.begin(a.rmi, code, ga.lower, ga.upper, nr, nb);
+                    while (__any_sync(tmask, lb.busy))
+                        if (lb.busy) { c.probe_row(lb.row(), sv, c64); lb.feed(sv, c64); }
+                    RmiUpper ub;
+                    if (okw && lb.hi_eq) ub.begin(a.rmi, code, lb.hi, ga.upper, nr, nb);
+                    while (__any_sync(tmask, ub.busy))
+                        if (ub.busy) { c.probe_row(ub.row(), sv, c64); ub.feed(sv, c64); }
+                    if (okw) {
+                        literal = false;
+                        mlo = (int64_t)lb.hi;
+                        mhi = lb.hi_eq ? (int64_t)ub.lo : mlo - 1;
                     }
-                    if (visit && !rf.hazard) { literal = false; mlo = rf.out_lo; mhi = rf.out_hi; }
                 }
                 if (__any_sync(tmask, literal)) {
                     RmiSearch rs;

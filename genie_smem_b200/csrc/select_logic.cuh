@@ -342,122 +342,139 @@ struct RmiSearch {
     }
 };
 
-// Error-bounded last-mile search for the common case, same results as the literal search above at a fraction of the
+// Error-bounded last-mile search for the common case: same results as the literal search above at a fraction of the
 // instructions.  The literal algorithm deviates from "first row >= q, last row <= q" only when a row of its bracket is a
 // None row of get_ref_seq (a suffix shorter than K: K rows of the whole table, RMI_LUT.py:89-92), when the prediction
 // falls outside the table, or when a bracket end stays at its default -- its exponential phase otherwise ends with
 // k-mer[lower] < q < k-mer[upper], and both binary searches of a None-free sorted range return the exact bounds whatever
-// pivots they use.  RmiFast therefore replays the exponential phase probe for probe (same rows), declares a HAZARD
-// (-> the caller reruns the window through RmiSearch) if it meets a None row, an out-of-table start, a default bracket
-// end or a None row anywhere inside the bracket (none_rows: the sorted rows of the K short suffixes), and otherwise
-// finishes with a lower-bound binary search and a galloping upper-bound search (k-mer counts are small).  32-bit rows,
-// one probe site, a handful of instructions per state.
-struct RmiFast {
-    enum : int { DONE = 0, START, UP, DOWN, LB, UBG, UBB };
-    int state = DONE;
-    bool hazard = false, have_lower = false, have_upper = false, hi_eq = false;
-    uint32_t n_rows = 0, K = 0;
-    int64_t n_bases = 0;
+// pivots they use.  So: replay the exponential phase probe for probe (same rows); declare a HAZARD (-> the caller reruns
+// the window through RmiSearch) on a None row, an out-of-table start, a default bracket end or a None row anywhere
+// inside the bracket (none_rows: the sorted rows of the K short suffixes, behind a 1024-region bitmap); otherwise
+// finish with a lower-bound binary search and a galloping upper-bound search (k-mer counts are small).
+// The search is cut into three PHASES whose per-probe update is straight-line code on 32-bit rows, so that a warp can
+// run each phase as one lock-step loop with (nearly) uniform instructions: A gallop from the prediction to a bracket,
+// B lower bound, C upper bound (hits only).  k_select_seeded runs phase A for all windows of a round, then B, then C;
+// rmi_fast_lookup below (host test, reference for the kernel) runs them back to back for one k-mer.
+struct RmiCommon {
     uint64_t q = 0;
-    uint32_t start = 0, win = 0, ind = 0, lower = 0, upper = 0, lo = 0, hi = 0, L = 0, g = 0;
-    int64_t out_lo = 0, out_hi = -1;
+    uint32_t K = 0, n_rows = 0;
+    int64_t n_bases = 0;
+    // k-mer of a probed row; false for a None row (suffix shorter than K)
+    GSM_HD bool kmer(int64_t s, uint64_t code64, uint64_t& c) const {
+        c = code64 >> (64u - 2u * K);
+        return !(s - 1 + (int64_t)K > n_bases);
+    }
+};
 
-    GSM_HD bool pending() const { return state != DONE; }
-    GSM_HD bool hit() const { return out_hi >= out_lo; }
-    GSM_HD uint64_t row() const { return ind; }
-    GSM_HD void bail() { hazard = true; state = DONE; }
-    GSM_HD void probe(int st, uint32_t r) { ind = r; state = st; }
-
+struct RmiGallop : RmiCommon {                 // phase A: RMI_LUT.exponential_search's bracket, probe for probe
+    uint32_t start = 0, win = 1, dir = 0, r = 0, lower = 0, upper = 0;
+    bool busy = false, hazard = false, have_lower = false, have_upper = false;
     // int(prediction) when it is a row of the table, else -1 (the literal search wraps or raises there)
     GSM_HD static int64_t predicted_row(const RmiModel& m, uint64_t code, uint32_t rows) {
         const double pred = rmi_predict(m, code);
         if (!(pred > -1.0 && pred < (double)rows)) return -1;
         return (int64_t)pred;                                   // int() truncates toward zero (RMI_LUT.py:72)
     }
-    GSM_HD void begin(const RmiModel& m, uint64_t code, uint32_t rows, int64_t bases) {
-        begin_at(m, code, predicted_row(m, code, rows), rows, bases);
+    GSM_HD void begin(const RmiModel& m, uint64_t code, int64_t row0, uint32_t rows, int64_t bases) {
+        q = code; K = m.K; n_rows = rows; n_bases = bases;
+        have_lower = have_upper = false; dir = 0; win = 1;
+        hazard = row0 < 0;                    // prediction outside the table
+        busy = !hazard;
+        start = r = hazard ? 0u : (uint32_t)row0;
     }
-    // the prediction may be computed ahead of time (k_select_seeded does all windows of a round in one converged loop)
-    GSM_HD void begin_at(const RmiModel& m, uint64_t code, int64_t row0, uint32_t rows, int64_t bases) {
-        n_rows = rows; n_bases = bases; K = m.K; q = code;
-        hazard = false; have_lower = have_upper = false; hi_eq = false;
-        out_lo = 0; out_hi = -1;
-        if (row0 < 0) { bail(); return; }
-        start = (uint32_t)row0;
-        win = 1;
-        probe(START, start);
-    }
-    GSM_HD void next_up(const RmiModel& m) {
-        if (!have_upper && (uint64_t)start + win < n_rows) { const uint32_t r = start + win; win *= 2; probe(UP, r); return; }
-        win = 1;
-        next_down(m);
-    }
-    GSM_HD void next_down(const RmiModel& m) {
-        if (!have_lower && start >= win) { const uint32_t r = start - win; win *= 2; probe(DOWN, r); return; }
-        bracket_ready(m);
-    }
-    GSM_HD void bracket_ready(const RmiModel& m) {
-        if (!have_lower || !have_upper) { bail(); return; }
-        const uint32_t rl = lower >> m.none_shift, ru = upper >> m.none_shift;
-        if (ru - rl > 1u || ((m.none_map[rl >> 5] >> (rl & 31u)) & 1u) || ((m.none_map[ru >> 5] >> (ru & 31u)) & 1u)) {
-            bool bad = false;                                   // a None row nearby: the exact test
-            for (uint32_t t = 0; t < m.n_none; ++t) bad |= (m.none_rows[t] >= lower && m.none_rows[t] <= upper);
-            if (bad) { bail(); return; }
-        }
-        lo = lower; hi = upper; hi_eq = false;
-        lb_iter();
-    }
-    GSM_HD void lb_iter() {                                      // first row of (lower, upper] with k-mer >= q
-        if (hi - lo > 1) { probe(LB, lo + ((hi - lo) >> 1)); return; }
-        L = hi;
-        if (!hi_eq) { out_lo = (int64_t)L; out_hi = (int64_t)L - 1; state = DONE; return; }     // absent: lo = hi + 1
-        lo = L; g = 1;
-        ub_gallop();
-    }
-    GSM_HD void ub_gallop() {                                    // k-mer[lo] == q: last row of [lo, upper) equal to q
-        if ((uint64_t)lo + g >= upper) { hi = upper; ub_bin(); return; }
-        probe(UBG, lo + g);
-    }
-    GSM_HD void ub_bin() {
-        if (hi - lo > 1) { probe(UBB, lo + ((hi - lo) >> 1)); return; }
-        out_lo = (int64_t)L; out_hi = (int64_t)lo;
-        state = DONE;
-    }
+    GSM_HD uint64_t row() const { return r; }
     GSM_HD void feed(const RmiModel& m, int64_t s, uint64_t code64) {
-        if (s - 1 + (int64_t)K > n_bases) { bail(); return; }   // a None row: let the literal search handle this window
-        const uint64_t c = code64 >> (64u - 2u * K);
-        switch (state) {
-        case START:
-            if (c < q) { lower = ind; have_lower = true; }
-            else if (c > q) { upper = ind; have_upper = true; }
-            next_up(m);
-            return;
-        case UP:
-            if (c > q) { upper = ind; have_upper = true; win = 1; next_down(m); return; }
-            if (c < q) { lower = ind; have_lower = true; }
-            next_up(m);
-            return;
-        case DOWN:
-            if (c < q) { lower = ind; have_lower = true; bracket_ready(m); return; }
-            if (c > q) { upper = ind; have_upper = true; }
-            next_down(m);
-            return;
-        case LB:
-            if (c < q) lo = ind; else { hi = ind; hi_eq = (c == q); }
-            lb_iter();
-            return;
-        case UBG:
-            if (c == q) { lo = ind; g *= 2; ub_gallop(); } else { hi = ind; ub_bin(); }
-            return;
-        case UBB:
-            if (c == q) lo = ind; else hi = ind;
-            ub_bin();
-            return;
-        default:
-            return;
-        }
+        uint64_t c;
+        const bool ok = kmer(s, code64, c);
+        const bool lt = c < q, gt = c > q;
+        lower = lt ? r : lower; have_lower |= lt;
+        upper = gt ? r : upper; have_upper |= gt;
+        if (dir == 0u) { dir = 1u; win = 1u; }
+        if (dir == 1u && (have_upper || (uint64_t)start + win >= n_rows)) { dir = 2u; win = 1u; }
+        const bool done = dir == 2u && (have_lower || start < win);
+        r = dir == 1u ? start + win : start - win;
+        win <<= 1;
+        if (!ok) { hazard = true; busy = false; return; }           // a None row: the literal search handles this window
+        if (!done) return;
+        busy = false;
+        hazard = !have_lower || !have_upper;                         // a default bracket end
+        if (hazard) return;
+        const uint32_t rl = lower >> m.none_shift, ru = upper >> m.none_shift;
+        if (ru - rl > 1u || ((m.none_map[rl >> 5] >> (rl & 31u)) & 1u) || ((m.none_map[ru >> 5] >> (ru & 31u)) & 1u))
+            for (uint32_t t = 0; t < m.n_none; ++t) hazard |= (m.none_rows[t] >= lower && m.none_rows[t] <= upper);
     }
 };
+
+struct RmiLower : RmiCommon {                  // phase B: first row of (lower, upper] whose k-mer is >= q
+    uint32_t lo = 0, hi = 0;
+    bool busy = false, hi_eq = false;
+    GSM_HD void begin(const RmiModel& m, uint64_t code, uint32_t lower, uint32_t upper, uint32_t rows, int64_t bases) {
+        q = code; K = m.K; n_rows = rows; n_bases = bases;
+        lo = lower; hi = upper; hi_eq = false;
+        busy = hi - lo > 1u;
+    }
+    GSM_HD uint64_t row() const { return lo + ((hi - lo) >> 1); }
+    GSM_HD void feed(int64_t s, uint64_t code64) {
+        uint64_t c;
+        kmer(s, code64, c);                    // the bracket holds no None row
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const bool lt = c < q;
+        lo = lt ? mid : lo;
+        hi_eq = lt ? hi_eq : (c == q);
+        hi = lt ? hi : mid;
+        busy = hi - lo > 1u;
+    }
+};
+
+struct RmiUpper : RmiCommon {                  // phase C: k-mer[lo] == q < k-mer[hi]: last row equal to q (counts are small: gallop)
+    uint32_t lo = 0, hi = 0, g = 1;
+    bool busy = false;
+    GSM_HD void begin(const RmiModel& m, uint64_t code, uint32_t first, uint32_t upper, uint32_t rows, int64_t bases) {
+        q = code; K = m.K; n_rows = rows; n_bases = bases;
+        lo = first; hi = upper; g = 1;
+        busy = hi - lo > 1u;
+    }
+    GSM_HD uint32_t next() const { return (g != 0u && (uint64_t)lo + g < hi) ? lo + g : lo + ((hi - lo) >> 1); }
+    GSM_HD uint64_t row() const { return next(); }
+    GSM_HD void feed(int64_t s, uint64_t code64) {
+        uint64_t c;
+        kmer(s, code64, c);
+        const uint32_t r = next();
+        const bool eq = c == q;
+        lo = eq ? r : lo;
+        hi = eq ? hi : r;
+        g = eq ? g << 1 : 0u;                  // first larger k-mer: switch to bisection
+        busy = hi - lo > 1u;
+    }
+};
+
+// The three phases back to back for one k-mer.  Returns false on a hazard (use the literal search), else (lo, hi) with
+// hi >= lo <=> hit; n_probes counts the fetches.
+template <typename Probe>
+GSM_HD bool rmi_fast_lookup(Probe& probe, const RmiModel& m, uint64_t code, uint32_t rows, int64_t bases, int64_t& lo, int64_t& hi,
+                            uint32_t* n_probes = nullptr) {
+    int64_t s;
+    uint64_t c64;
+    uint32_t np = 0;
+    RmiGallop a;
+    a.begin(m, code, RmiGallop::predicted_row(m, code, rows), rows, bases);
+    while (a.busy) { probe(a.row(), s, c64); a.feed(m, s, c64); ++np; }
+    if (n_probes) *n_probes = np;
+    if (a.hazard) return false;
+    RmiLower b;
+    b.begin(m, code, a.lower, a.upper, rows, bases);
+    while (b.busy) { probe(b.row(), s, c64); b.feed(s, c64); ++np; }
+    lo = (int64_t)b.hi;
+    hi = lo - 1;                                                // absent: lo = hi + 1
+    if (b.hi_eq) {
+        RmiUpper c;
+        c.begin(m, code, b.hi, a.upper, rows, bases);
+        while (c.busy) { probe(c.row(), s, c64); c.feed(s, c64); ++np; }
+        hi = (int64_t)c.lo;
+    }
+    if (n_probes) *n_probes = np;
+    return true;
+}
 
 // ------------------------------------------------------------------------------------ selection
 // Ctx must provide:

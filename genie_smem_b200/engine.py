@@ -142,6 +142,13 @@ class PackedIndex:
     def from_host(cls, host: HostIndex, with_sa=True, with_text=True):
         return cls(host.info, *host.pack(with_sa, with_text))
 
+    @classmethod
+    def from_device(cls, index, with_sa=True, with_text=True):
+        """Host copies of a DeviceIndex (e.g. one built on the GPU) so that it can be saved and reloaded."""
+        def grab(t):
+            return None if t is None else t.cpu().numpy().view(np.uint32)
+        return cls(index.info, grab(index.fwd), grab(index.rev), grab(index.sa) if with_sa else None, grab(index.text) if with_text else None)
+
     def save(self, directory):
         import json as _json
         import os as _os

@@ -116,16 +116,10 @@ struct SelCtx {
                 continue;
             }
             if (rmi.n_none) {                            // error-bounded fast path first, literal search on a hazard
-                RmiFast rf;
-                rf.begin(rmi, code, ix->meta.n_rows, (int64_t)ix->n_bases);
-                while (rf.pending()) {
-                    int64_t s; uint64_t c64;
-                    pr(rf.row(), s, c64);
-                    rf.feed(rmi, s, c64);
-                }
-                if (!rf.hazard) {
-                    lo[i] = rf.out_lo; hi[i] = rf.out_hi;
-                    if (rf.hit()) hit |= 1u << i;
+                int64_t flo, fhi;
+                if (rmi_fast_lookup(pr, rmi, code, ix->meta.n_rows, (int64_t)ix->n_bases, flo, fhi)) {
+                    lo[i] = flo; hi[i] = fhi;
+                    if (fhi >= flo) hit |= 1u << i;
                     continue;
                 }
                 g_cnt[5]++;                              // [5] hazards (select runs)
@@ -374,16 +368,9 @@ int emu_rmi_fast(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint32
     auto sa = [&](uint64_t r) { return ei->sa[r]; };
     auto tx = [&](uint64_t w) { return ei->text[w]; };
     SaTextProbe<decltype(sa), decltype(tx)> pr{sa, tx};
-    RmiFast rf;
-    rf.begin(m, code, ei->n_rows, (int64_t)ei->n_bases);
-    uint32_t np = 0;
-    while (rf.pending()) {
-        int64_t s; uint64_t c64;
-        pr(rf.row(), s, c64);
-        rf.feed(m, s, c64);
-        ++np;
-    }
-    *lo = rf.out_lo; *hi = rf.out_hi; *hazard = rf.hazard ? 1u : 0u; *n_probes = np;
+    *lo = 0; *hi = -1;
+    const bool ok = rmi_fast_lookup(pr, m, code, ei->n_rows, (int64_t)ei->n_bases, *lo, *hi, n_probes);
+    *hazard = ok ? 0u : 1u;
     return 0;
 }
 

@@ -104,3 +104,20 @@ def test_sampled_sa_locate_equals_full_sa(gs, sample):
         assert idx.sa is None
         assert np.array_equal(idx.locate(rows), sa[rows])
         assert np.array_equal(idx.locate(np.array([len(sa) + 5], np.uint32)), np.array([0], np.uint32))
+
+
+def test_device_built_index_round_trips_through_disk(gs, tmp_path):
+    """PackedIndex.from_device -> save -> load (mmap) -> DeviceIndex: the same arrays, and it searches."""
+    rng = np.random.default_rng(4)
+    codes = rng.integers(0, 4, 120_000, dtype=np.uint8)
+    dev = gs.DeviceIndex.build_on_device(codes)
+    gs.PackedIndex.from_device(dev).save(str(tmp_path / "idx"))
+    back = gs.DeviceIndex(gs.PackedIndex.load(str(tmp_path / "idx")))
+    for name in ("fwd", "rev", "sa"):
+        assert np.array_equal(getattr(back, name).cpu().numpy(), getattr(dev, name).cpu().numpy()), name
+    n_text = (len(codes) + 15) // 16
+    assert np.array_equal(back.text.cpu().numpy()[:n_text], dev.text.cpu().numpy()[:n_text])
+    reads = ["".join("ACGT"[c] for c in codes[p:p + 80]) for p in (0, 5000, 119_900)]
+    a = gs.backsearch_batch(dev, gs.ReadBatch.from_strings(reads))
+    b = gs.backsearch_batch(back, gs.ReadBatch.from_strings(reads))
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.all(a[1] >= 1)
