@@ -56,6 +56,8 @@ struct SelectArgs {
     uint32_t min_len;
     uint32_t K;
     const uint2* lut;
+    const uint4* seed_tab;      // optional sweep seed table (gsm_seed_table_build): shortens explicit backward searches
+    uint32_t seed_K;
     RmiModel rmi;
     uint4* mem_pool;
     const uint32_t* mem_off;
@@ -102,9 +104,13 @@ struct DevSelCtx {
         const uint4* fwd = a.fwd;
         auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
         uint32_t p = j;
-        if (METHOD == GSM_METHOD_LUT && j - i >= K) {      // the table replaces the first K backward steps
-            const uint32_t* w = words;
-            auto rd = [w](uint64_t x) { return __ldg(w + x); };
+        const uint32_t* w = words;
+        auto rd = [w](uint64_t x) { return __ldg(w + x); };
+        if (a.seed_K != 0u && j - i >= a.seed_K && (METHOD != GSM_METHOD_LUT || a.seed_K >= K)) {
+            const uint4 e = __ldg(a.seed_tab + kmer_code(rd, j - a.seed_K, a.seed_K));   // the longest table first
+            lo = e.x; cnt = e.y; p = j - a.seed_K;
+            if (cnt == 0) return;
+        } else if (METHOD == GSM_METHOD_LUT && j - i >= K) {      // the table replaces the first K backward steps
             const uint2 e = __ldg(a.lut + kmer_code(rd, j - K, K));
             lo = e.x; cnt = e.y; p = j - K;
             if (cnt == 0) return;
@@ -1055,6 +1061,7 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
     se.fwd = (const uint4*)ix->fwd_buckets; se.meta = make_meta(ix); se.n_bases = ix->n_rows - 1; se.sa = ix->sa; se.text = ix->text2bit; se.probe = (method == GSM_METHOD_RMI && rmi) ? (const uint4*)rmi->probe : nullptr;
     se.reads = (const uint32_t*)rd->packed; se.chunk_off = rd->chunk_off; se.len = rd->len; se.n_reads = (uint32_t)rd->n_reads;
     se.max_len = rd->max_len; se.read_id_base = rd->read_id_base; se.min_len = min_len; se.K = K; se.lut = (const uint2*)lut; se.rmi = rm;
+    se.seed_tab = (const uint4*)ix->seed_table; se.seed_K = ix->seed_table ? ix->seed_K : 0u;
     se.mem_pool = (uint4*)ws->mem_pool; se.mem_off = ws->mem_off; se.mem_cnt = ws->mem_cnt; se.stage = (uint4*)ws->quad_scratch;
     se.rec_tmp = (uint4*)ws->rec_tmp; se.rec_cap = ws->rec_cap; se.rec_tmp_off = ws->rec_tmp_off; se.rec_cnt = ws->rec_cnt;
     se.read_status = ws->read_status; se.counters = (unsigned long long*)ws->counters;

@@ -279,11 +279,12 @@ class DeviceIndex:
         return self
 
     def build_seed_table(self, K=None):
-        """Seed table of the sweep kernel (gsm_seed_table_build): 4^K x 16 bytes; K defaults to the largest value with
-        about 16+ expected occurrences per k-mer (12 at 1 Gbp, 10 at 100 Mbp).  Results never depend on it."""
+        """Seed table of the sweep kernel (gsm_seed_table_build): 4^K x 16 bytes; K defaults to the largest value that
+        still leaves 2+ expected occurrences per k-mer (14 at 1-3 Gbp: 4.3 GB, 12 at 100 Mbp; measured on B200 at 1 Gbp:
+        k_sweep 127 / 88 / 82 / 77 / 76 ms per 10 M reads for K = none / 11 / 12 / 13 / 14).  Results never depend on it."""
         if K is None:
             K = 1
-            while K < 13 and self.n_rows / 4.0 ** (K + 1) >= 10.0:
+            while K < 14 and self.n_rows / 4.0 ** (K + 1) >= 2.0:
                 K += 1
         if self.rev is None:
             raise ValueError("the seed table needs the reverse-text buckets")
@@ -753,6 +754,25 @@ class PipelinedEngine:
             store[name] = b
         return b
 
+    def _chunk_bounds(self, n):
+        """Chunk boundaries: full chunks of chunk_reads in the middle, a geometric ramp (1/8, 1/8, 1/4, 1/2) at both ends,
+        because the first chunk's H2D and the last chunk's D2H are the only copies nothing can hide."""
+        c = self.chunk_reads
+        ramp = [max(c // 8, 1), max(c // 8, 1), max(c // 4, 1), max(c // 2, 1)]
+        if n <= 4 * c or c < 64:
+            return sorted(set(min(n, i * c) for i in range((n + c - 1) // c + 1))) if n else [0]
+        head, pos = [0], 0
+        for r in ramp:
+            pos += r
+            head.append(pos)
+        tail, end = [n], n
+        for r in ramp:
+            end -= r
+            tail.append(end)
+        tail.reverse()
+        mid = list(range(head[-1] + c, tail[0], c))
+        return head + mid + tail
+
     def run(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None):
         """Packed host reads in (pinned), host records out."""
         n = reads.n
@@ -794,7 +814,8 @@ class PipelinedEngine:
         packed = self._buf(self._dev, "packed", n * cpr * 16 + 16, False)
         lens = self._buf(self._dev, "len", max(n, 1) * 4, False)[: n * 4].view(torch.int32)
         raw = self._buf(self._dev, "raw", max(n * read_len, 1), False)
-        bad = self._buf(self._dev, "bad", 8 * (self.n_chunks + 1), False)[: 8 * (self.n_chunks + 1)].view(torch.int64)
+        n_slots = len(self._chunk_bounds(n))
+        bad = self._buf(self._dev, "bad", 8 * n_slots, False)[: 8 * n_slots].view(torch.int64)
         slot = {}
         holder = ReadBatch(None, None, np.zeros(0, np.uint32), read_len, read_id_base)
         holder.n, holder.packed, holder.chunk_off, holder.len = n, packed, coff, lens
@@ -819,7 +840,7 @@ class PipelinedEngine:
         return res
 
     def _run_chunks(self, method, n, copy_in, prep, min_len, K, lut, rmi):
-        bounds = sorted(set(min(n, i * self.chunk_reads) for i in range(self.n_chunks + 1)))
+        bounds = self._chunk_bounds(n)
         n_ch = len(bounds) - 1
         est = self.engines[0].rec_cap * 16
         out_rec = self._buf(self._pin, "rec", max(est, 1 << 20), True)

@@ -375,7 +375,7 @@ def test_seed_table_changes_nothing(gs, seed_K):
 
     plain = run_all()
     idx.build_seed_table(seed_K)
-    assert idx.seed_K == (seed_K if seed_K else 9)
+    assert idx.seed_K == (seed_K if seed_K else 10)
     seeded = run_all()
     for a, b in zip(plain, seeded):
         assert a[3] == b[3], "number of maximal matches"
