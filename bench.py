@@ -319,7 +319,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (ms_sweep * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tname = {1_000_000_000: "r01b_1gbp_sweep_dram_bytes.json", 100_000_000: "r01_sweep_dram_bytes.json"}.get(args.ref_bases)
+    tname = {1_000_000_000: "r01c_1gbp_sweep_dram_bytes.json", 100_000_000: "r01_sweep_dram_bytes.json"}.get(args.ref_bases)
     if tname and os.path.exists(os.path.join(ROOT, "profiles", tname)):        # ncu --set full capture of k_sweep on this reference size
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
