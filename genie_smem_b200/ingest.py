@@ -1,0 +1,97 @@
+"""Read / reference ingest: FASTA and FASTQ files -> byte buffers the device packers take.
+
+The reference reads one sequence per file with a Python line loop (SMEM/ExactMatch.py:43-50 for the reference,
+:104-108 for a query).  Here a file is mapped once, line ends are found with one vectorised scan, and the sequence
+lines are gathered into one contiguous uint8 buffer plus offsets -- exactly what gsm_pack_reads_device /
+gsm_text_pack_device (GPU 2-bit packing) and PipelinedEngine.run_ascii consume.  Parsing is host-side numpy; nothing
+here computes a search result.
+
+N-base policy (the reference raises KeyError on any character outside ACGT, ExactMatch.py:139):
+  "error"  keep every read; the device packer reports the first offending read (BaseError)      [default]
+  "drop"   remove reads that hold a character outside ACGT; their indices are returned
+"""
+import numpy as np
+
+_VALID = np.zeros(256, bool)
+_VALID[[65, 67, 71, 84]] = True          # A C G T
+
+
+def _lines(buf):
+    """(start, end) of every line of a uint8 buffer, '\n' / '\r\n' stripped, trailing empty line dropped."""
+    nl = np.flatnonzero(buf == 10)
+    starts = np.concatenate(([0], nl + 1))
+    ends = np.concatenate((nl, [len(buf)]))
+    if len(starts) and starts[-1] >= len(buf):
+        starts, ends = starts[:-1], ends[:-1]
+    cr = (ends > starts) & (buf[np.maximum(ends - 1, 0)] == 13)
+    return starts, ends - cr
+
+
+def _gather(buf, starts, ends, pin):
+    """Concatenate buf[starts[i]:ends[i]] -> (flat uint8, offsets int64[n+1])."""
+    lens = (ends - starts).astype(np.int64)
+    off = np.concatenate(([0], np.cumsum(lens)))
+    total = int(off[-1])
+    if pin:
+        import torch
+        out_t = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        out = out_t.numpy()[:total]
+    else:
+        out = np.empty(total, np.uint8)
+    if total:
+        # index of every output byte in the source: start of its read + position inside it
+        idx = np.repeat(starts - off[:-1], lens) + np.arange(total, dtype=np.int64)
+        np.take(buf, idx, out=out)
+    return out, off
+
+
+def read_fasta(path):
+    """-> (names, sequences as uint8 arrays).  Multi-record, multi-line FASTA; the reference's files hold one record."""
+    buf = np.fromfile(path, dtype=np.uint8)
+    starts, ends = _lines(buf)
+    keep = ends > starts
+    starts, ends = starts[keep], ends[keep]
+    is_hdr = buf[starts] == ord(">")
+    hdr_idx = np.flatnonzero(is_hdr)
+    names, seqs = [], []
+    for k, h in enumerate(hdr_idx):
+        nxt = hdr_idx[k + 1] if k + 1 < len(hdr_idx) else len(starts)
+        names.append(bytes(buf[starts[h] + 1:ends[h]]).decode(errors="replace"))
+        seq, _ = _gather(buf, starts[h + 1:nxt], ends[h + 1:nxt], pin=False)
+        seqs.append(seq)
+    if not len(hdr_idx) and len(starts):          # headerless: one sequence
+        seq, _ = _gather(buf, starts, ends, pin=False)
+        names.append("")
+        seqs.append(seq)
+    return names, seqs
+
+
+def read_fastq(path, n_policy="error", pin=True):
+    """4-line FASTQ -> (bases uint8 (pinned when a GPU is present), base_off int64[n+1], dropped read indices).
+    bases/base_off go straight into ReadBatch.from_device_bases(bases_on_device, base_off=base_off, ascii=True); when
+    all reads have one length, bases.reshape(n, L) is what PipelinedEngine.run_ascii takes."""
+    if n_policy not in ("error", "drop"):
+        raise ValueError("n_policy must be 'error' or 'drop'")
+    buf = np.fromfile(path, dtype=np.uint8)
+    starts, ends = _lines(buf)
+    if len(starts) % 4:
+        raise ValueError(f"{path}: {len(starts)} lines is not a multiple of 4 (truncated FASTQ?)")
+    if len(starts) and not (np.all(buf[starts[0::4]] == ord("@")) and np.all(buf[starts[2::4]] == ord("+"))):
+        raise ValueError(f"{path}: not a 4-line FASTQ (records must start with '@' and have a '+' line)")
+    s, e = starts[1::4], ends[1::4]
+    dropped = np.zeros(0, np.int64)
+    if n_policy == "drop" and len(s):
+        bad_byte = ~_VALID[buf]
+        csum = np.concatenate(([0], np.cumsum(bad_byte)))
+        bad_read = (csum[e] - csum[s]) > 0
+        dropped = np.flatnonzero(bad_read)
+        s, e = s[~bad_read], e[~bad_read]
+    bases, off = _gather(buf, s, e, pin)
+    return bases, off, dropped
+
+
+def write_fastq(path, reads, names=None):
+    """Small helper for tests and examples."""
+    with open(path, "w") as f:
+        for i, r in enumerate(reads):
+            f.write(f"@{names[i] if names else 'r%d' % i}\n{r}\n+\n{'I' * len(r)}\n")

@@ -93,3 +93,26 @@ def test_run_ascii_rejects_non_acgt(gs, setup):
     pipe = gs.PipelinedEngine(idx, len(bad), 151, n_chunks=4)
     with pytest.raises(KeyError, match="417"):
         pipe.run_ascii(gs.METHOD_BWA, asc, 151)
+
+
+def test_fastq_file_to_records(gs, setup, tmp_path):
+    """FASTQ on disk -> host reader -> GPU packing -> SMEM records, ragged reads and the 'drop' policy included."""
+    import torch
+    text, idx, reads = setup
+    rng = np.random.default_rng(6)
+    ragged = [r[: int(rng.integers(20, 152))] for r in reads[:700]]
+    ragged[13] = ragged[13][:5] + "N" + ragged[13][6:]
+    path = str(tmp_path / "reads.fq")
+    gs.write_fastq(path, ragged)
+    bases, off, dropped = gs.read_fastq(path, n_policy="drop")
+    assert list(dropped) == [13]
+    kept = [r for i, r in enumerate(ragged) if i != 13]
+    batch = gs.ReadBatch.from_device_bases(torch.from_numpy(bases).cuda(), base_off=off, ascii=True)
+    e = gs.Engine(idx, len(kept), 151)
+    batch.to_host(pin=False)
+    got = e.run(gs.METHOD_BWA, batch, min_len=1)
+    exp = gs.Engine(idx, len(kept), 151).run(gs.METHOD_BWA, gs.ReadBatch.from_strings(kept), min_len=1)
+    assert np.array_equal(got.records, exp.records) and np.array_equal(got.offsets, exp.offsets)
+    bases, off, _ = gs.read_fastq(path, n_policy="error")
+    with pytest.raises(KeyError):
+        gs.ReadBatch.from_device_bases(torch.from_numpy(bases).cuda(), base_off=off, ascii=True)

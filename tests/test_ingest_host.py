@@ -1,0 +1,44 @@
+"""Host-side FASTA / FASTQ readers (genie_smem_b200/ingest.py): pure numpy, no GPU."""
+import numpy as np
+import pytest
+
+from genie_smem_b200 import ingest
+
+
+def test_fastq_reader_ragged_crlf_and_policies(tmp_path):
+    reads = ["ACGT", "A", "ACGTNACGT", "TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT", "acgt", "GGCC"]
+    p = tmp_path / "r.fq"
+    ingest.write_fastq(str(p), reads)
+    bases, off, dropped = ingest.read_fastq(str(p), pin=False)
+    assert len(dropped) == 0 and list(np.diff(off)) == [len(r) for r in reads]
+    assert bytes(bases).decode() == "".join(reads)
+    bases, off, dropped = ingest.read_fastq(str(p), n_policy="drop", pin=False)
+    assert list(dropped) == [2, 4]                       # N and lower case: outside ACGT, like the reference's KeyError
+    assert bytes(bases).decode() == "ACGT" + "A" + "T" * 37 + "GGCC" and off[-1] == len(bases)
+    # CRLF line ends and no trailing newline
+    q = tmp_path / "crlf.fq"
+    q.write_bytes(b"@a\r\nACG\r\n+\r\nIII\r\n@b\r\nTT\r\n+\r\nII")
+    bases, off, _ = ingest.read_fastq(str(q), pin=False)
+    assert bytes(bases) == b"ACGTT" and list(off) == [0, 3, 5]
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.fq").write_text("@a\nACG\n+\n")
+        ingest.read_fastq(str(tmp_path / "bad.fq"), pin=False)
+    (tmp_path / "empty.fq").write_text("")
+    bases, off, _ = ingest.read_fastq(str(tmp_path / "empty.fq"), pin=False)
+    assert len(bases) == 0 and list(off) == [0]
+
+
+def test_fasta_reader_matches_reference_parser(tmp_path):
+    """Same text as ExactMatch.load_ref_sequence (reference ExactMatch.py:43-50: skip the header, join stripped lines)."""
+    seq = "ACGTTGCA" * 40 + "AC"
+    p = tmp_path / "ref.fa"
+    p.write_text(">chr test\n" + "\n".join(seq[i:i + 60] for i in range(0, len(seq), 60)) + "\n")
+    names, seqs = ingest.read_fasta(str(p))
+    assert names == ["chr test"] and bytes(seqs[0]).decode() == seq
+    with open(p) as f:                      # the reference's own parsing rule
+        f.readline()
+        assert "".join(line.strip() for line in f) == seq
+    m = tmp_path / "multi.fa"
+    m.write_text(">a\nAC\nGT\n\n>b\nTTT\n")
+    names, seqs = ingest.read_fasta(str(m))
+    assert names == ["a", "b"] and [bytes(s).decode() for s in seqs] == ["ACGT", "TTT"]
