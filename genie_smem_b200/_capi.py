@@ -36,7 +36,7 @@ class DevReads(C.Structure):
 
 class DevRmi(C.Structure):
     _fields_ = [("K", C.c_uint32), ("n_levels", C.c_uint32), ("level_sizes", u32p), ("coef", C.c_void_p), ("intercept", C.c_void_p), ("probe", C.c_void_p),
-                ("none_rows", u32p), ("n_none_rows", C.c_uint32), ("reserved", C.c_uint32)]
+                ("none_rows", u32p), ("n_none_rows", C.c_uint32), ("param_stride", C.c_uint32)]
 
 
 class Workspace(C.Structure):
@@ -85,6 +85,7 @@ EXPORTS = {
     "gsm_rmi_lookup_batch": (C.c_int, [C.POINTER(DevIndex), C.POINTER(DevRmi), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_gather_probe": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
+    "gsm_l2_persist": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "gsm_device_l2_fetch_granularity": (C.c_int, [C.c_int32, C.POINTER(C.c_uint32)]),
     "gsm_last_error": (C.c_char_p, []),
     "gsm_version": (C.c_int, []),

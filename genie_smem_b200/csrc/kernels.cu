@@ -934,6 +934,30 @@ int gsm_device_l2_fetch_granularity(int32_t set_bytes, uint32_t* current) {
     return GSM_OK;
 }
 
+int gsm_l2_persist(const void* ptr, uint64_t bytes, void* stream) {
+    int st = device_ready();
+    if (st) return st;
+    int dev = 0, max_win = 0, max_persist = 0;
+    GSM_CUDA(cudaGetDevice(&dev));
+    GSM_CUDA(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+    GSM_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    if (ptr && bytes) {
+        if (max_win <= 0 || max_persist <= 0) return fail(GSM_E_INVALID, "gsm_l2_persist: the device has no persisting L2");
+        const uint64_t carve = bytes < (uint64_t)max_persist ? bytes : (uint64_t)max_persist;
+        GSM_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)carve));
+        v.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+        v.accessPolicyWindow.num_bytes = (size_t)(bytes < (uint64_t)max_win ? bytes : (uint64_t)max_win);
+        v.accessPolicyWindow.hitRatio = bytes <= carve ? 1.0f : (float)carve / (float)bytes;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }   // else: an empty window removes the policy from the stream
+    GSM_CUDA(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &v));
+    if (!(ptr && bytes)) GSM_CUDA(cudaCtxResetPersistingL2Cache());
+    return GSM_OK;
+}
+
 int gsm_seed_table_build(const gsm_dev_index* ix, uint32_t K, void* table, void* stream) {
     if (!ix || !table || !ix->fwd_buckets || !ix->rev_buckets) return fail(GSM_E_INVALID, "gsm_seed_table_build: needs both bucket arrays");
     if (K < 1 || K > 14) return fail(GSM_E_INVALID, "gsm_seed_table_build: K must be in 1..14");
@@ -951,6 +975,7 @@ static int fill_rmi(const gsm_dev_rmi* rmi, RmiModel* m, uint64_t n_rows) {
     if (!rmi || !rmi->level_sizes || !rmi->coef || !rmi->intercept) return fail(GSM_E_INVALID, "RMI parameters missing");
     if (rmi->n_levels < 1 || rmi->n_levels > 8 || rmi->K < 1 || rmi->K > 32) return fail(GSM_E_INVALID, "RMI: 1..8 levels, K in 1..32");
     m->K = rmi->K; m->n_levels = rmi->n_levels; m->coef = rmi->coef; m->intercept = rmi->intercept;
+    m->stride = rmi->param_stride ? rmi->param_stride : 1u;
     uint32_t off = 0;
     for (uint32_t l = 0; l < rmi->n_levels; ++l) { m->level_size[l] = rmi->level_sizes[l]; m->level_off[l] = off; off += rmi->level_sizes[l]; }
     if (rmi->none_rows && rmi->n_none_rows) {

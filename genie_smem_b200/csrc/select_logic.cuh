@@ -26,6 +26,8 @@ struct RmiModel {
     uint32_t level_off[8];
     const double* coef;
     const double* intercept;
+    uint32_t stride;            // distance between consecutive models in coef[] / intercept[] (1 = two dense arrays,
+                                // 2 = one interleaved {coef, intercept} array: one 16-byte line per model)
     uint32_t n_none;            // > 0: none_rows holds the rows of the K short suffixes (enables RmiFast)
     uint32_t none_rows[32];
     uint32_t none_shift;        // none_map bit (row >> none_shift) is set iff that region of rows holds a None row
@@ -62,7 +64,7 @@ GSM_HD double rmi_predict(const RmiModel& m, uint64_t code) {
     double p = 0.0;
     for (uint32_t lv = 0; lv < m.n_levels; ++lv) {
         const uint32_t k = m.level_off[lv] + model;
-        p = mul_add_nofma(x, m.coef[k], m.intercept[k]);
+        p = mul_add_nofma(x, m.coef[(size_t)k * m.stride], m.intercept[(size_t)k * m.stride]);
         const uint32_t scale = (lv + 1 < m.n_levels) ? m.level_size[lv + 1] : 1u;
         if (!(p >= 1.0)) model = 0;                       // int(p) <= 0 (also NaN)
         else if (p >= (double)scale) model = scale - 1;

@@ -469,17 +469,29 @@ class RmiParams:
         self.coef_host = np.ascontiguousarray(coef, np.float64)
         self.intercept_host = np.ascontiguousarray(intercept, np.float64)
         assert self.coef_host.shape[0] == int(self.level_sizes.sum()) == self.intercept_host.shape[0]
-        self.coef = torch.from_numpy(self.coef_host).to(device)
-        self.intercept = torch.from_numpy(self.intercept_host).to(device)
+        # one interleaved {coef, intercept} array: a model is one 16-byte line, and one L2 persistence window covers all
+        self.params = torch.from_numpy(np.stack([self.coef_host, self.intercept_host], axis=1).copy()).to(device)
+        self.coef, self.intercept = self.params[:, 0], self.params[:, 1]
         s = capi.DevRmi()
         s.K, s.n_levels = self.K, len(self.level_sizes)
         s.level_sizes = self.level_sizes.ctypes.data_as(capi.u32p)
-        s.coef, s.intercept = self.coef.data_ptr(), self.intercept.data_ptr()
+        s.coef, s.intercept = self.params.data_ptr(), self.params.data_ptr() + 8
+        s.param_stride = 2
         s.probe = None
         s.none_rows, s.n_none_rows = None, 0
         self.c = s
         self.probe = None
         self.none_rows = None
+
+    def persist_in_l2(self, on=True):
+        """Pin the model parameters in the persisting L2 for kernels of the current stream (gsm_l2_persist): every
+        prediction reads one random 16-byte line of this array per level."""
+        with torch.cuda.device(self.params.device):
+            if on:
+                capi.check(capi.lib.gsm_l2_persist(_ptr(self.params), self.params.numel() * 8, _stream()))
+            else:
+                capi.check(capi.lib.gsm_l2_persist(None, 0, _stream()))
+        return self
 
     def build_none_rows(self, index):
         """The K rows where get_ref_seq returns None (gsm_rmi_none_rows): lets the selection kernel run the

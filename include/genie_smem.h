@@ -184,7 +184,8 @@ typedef struct {
     const uint32_t* none_rows;   /* HOST pointer, optional: the K rows of gsm_rmi_none_rows; enables the error-bounded
                                     fast search (identical bounds, far fewer instructions), else NULL */
     uint32_t n_none_rows;        /* K, or 0 */
-    uint32_t reserved;
+    uint32_t param_stride;       /* elements between consecutive models in coef[] / intercept[]: 0 or 1 = two dense arrays;
+                                    2 = one interleaved {coef, intercept} array (intercept == coef + 1): one line per model */
 } gsm_dev_rmi;
 
 /* Scratch + output buffers for one SMEM batch; all device memory, all caller-allocated.
@@ -294,6 +295,11 @@ int gsm_rmi_lookup_batch(const gsm_dev_index* idx, const gsm_dev_rmi* rmi, uint6
  * every quad chases pointers (one FM chain each); 0: independent fetches.  sink: device u64. */
 int gsm_gather_probe(const void* buf, uint64_t bytes, uint64_t n_fetch, uint32_t dependent,
                      uint64_t* sink, uint64_t* n_done, void* stream);
+
+/* Pin [ptr, ptr+bytes) in the persisting part of the L2 for kernels launched on `stream` (access-policy window; the small,
+ * randomly read top of a structure: RMI model parameters, the top of a k-mer table).  ptr == NULL or bytes == 0 removes the
+ * window and resets the persisting lines. */
+int gsm_l2_persist(const void* ptr, uint64_t bytes, void* stream);
 
 /* L2 fetch granularity of the current device (cudaLimitMaxL2FetchGranularity): the rank kernels read isolated
  * 64-byte buckets, so a 128-byte fetch granularity moves twice the necessary DRAM bytes.  set_bytes > 0 requests

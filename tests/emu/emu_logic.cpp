@@ -250,7 +250,7 @@ int emu_smem(const EmuIndex* ei, int method, const uint32_t* words, uint32_t L, 
     sc.mems = ctx.mems.data(); sc.method = method; sc.lut = lut; sc.out = &recs;
     memset(&sc.rmi, 0, sizeof(sc.rmi));
     if (method == 2) {
-        sc.rmi.K = K; sc.rmi.n_levels = n_levels; sc.rmi.coef = coef; sc.rmi.intercept = intercept;
+        sc.rmi.K = K; sc.rmi.n_levels = n_levels; sc.rmi.coef = coef; sc.rmi.intercept = intercept; sc.rmi.stride = 1;
         uint32_t off = 0;
         for (uint32_t l = 0; l < n_levels; ++l) { sc.rmi.level_size[l] = level_sizes[l]; sc.rmi.level_off[l] = off; off += level_sizes[l]; }
         if (none_rows && n_none) rmi_set_none_rows(sc.rmi, none_rows, n_none, ei->n_rows);
@@ -322,7 +322,7 @@ void emu_locate(const EmuIndex* ei, uint32_t S, uint64_t n, const uint32_t* rows
 int emu_rmi_lookup(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint32_t* level_sizes, const double* coef,
                    const double* intercept, uint64_t code, double* pred, int64_t* lo, int64_t* hi) {
     RmiModel m; memset(&m, 0, sizeof(m));
-    m.K = K; m.n_levels = n_levels; m.coef = coef; m.intercept = intercept;
+    m.K = K; m.n_levels = n_levels; m.coef = coef; m.intercept = intercept; m.stride = 1;
     uint32_t off = 0;
     for (uint32_t l = 0; l < n_levels; ++l) { m.level_size[l] = level_sizes[l]; m.level_off[l] = off; off += level_sizes[l]; }
     auto sa = [&](uint64_t r) { return ei->sa[r]; };
@@ -337,7 +337,7 @@ int emu_rmi_lookup(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint
 int emu_rmi_search(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint32_t* level_sizes, const double* coef,
                    const double* intercept, uint64_t code, int64_t* lo, int64_t* hi, uint32_t* n_probes) {
     RmiModel m; memset(&m, 0, sizeof(m));
-    m.K = K; m.n_levels = n_levels; m.coef = coef; m.intercept = intercept;
+    m.K = K; m.n_levels = n_levels; m.coef = coef; m.intercept = intercept; m.stride = 1;
     uint32_t off = 0;
     for (uint32_t l = 0; l < n_levels; ++l) { m.level_size[l] = level_sizes[l]; m.level_off[l] = off; off += level_sizes[l]; }
     auto sa = [&](uint64_t r) { return ei->sa[r]; };
@@ -361,7 +361,7 @@ int emu_rmi_fast(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint32
                  const double* intercept, uint32_t n_none, const uint32_t* none_rows, uint64_t code, int64_t* lo, int64_t* hi,
                  uint32_t* hazard, uint32_t* n_probes) {
     RmiModel m; memset(&m, 0, sizeof(m));
-    m.K = K; m.n_levels = n_levels; m.coef = coef; m.intercept = intercept;
+    m.K = K; m.n_levels = n_levels; m.coef = coef; m.intercept = intercept; m.stride = 1;
     uint32_t off = 0;
     for (uint32_t l = 0; l < n_levels; ++l) { m.level_size[l] = level_sizes[l]; m.level_off[l] = off; off += level_sizes[l]; }
     rmi_set_none_rows(m, none_rows, n_none, ei->n_rows);

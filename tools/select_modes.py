@@ -21,8 +21,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     eng = g.Engine(index, n_reads, bench.READ_LEN, mems_per_read=24, recs_per_read=8)
     lut = g.lut_build(index, bench.LUT_K)
     rmi = bench.train_rmi(index, bench.RMI_K, bench.CONFIGS["c4"]["experts"] if n_ref >= 500_000_000 else bench.CONFIGS["c3"]["experts"], "cuda")
+    if os.environ.get("GSM_RMI_PERSIST") == "1":
+        rmi.persist_in_l2()
     eng.sweep(batch)
-    out = {"GSM_SELECT_TEAMS": os.environ.get("GSM_SELECT_TEAMS", "0")}
+    out = {"GSM_SELECT_TEAMS": os.environ.get("GSM_SELECT_TEAMS", "0"), "GSM_RMI_PERSIST": os.environ.get("GSM_RMI_PERSIST", "0")}
     sums = {}
     for name, method, kw in (("bwa", g.METHOD_BWA, {"min_len": 1}), ("lut", g.METHOD_LUT, {"K": bench.LUT_K, "lut": lut}), ("rmi", g.METHOD_RMI, {"rmi": rmi})):
         for _ in range(2):
