@@ -160,7 +160,7 @@ def parse_args():
     ap.add_argument("--ref-bases", type=int, default=0, help="reference size (default: the config's)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget per method")
     ap.add_argument("--skip-rmi", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=16, help="chunks of the pipelined end-to-end path")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the pipelined end-to-end path")
     ap.add_argument("--seed-k", type=int, default=-1, help="K of the sweep kernel's seed table (-1 = auto, 0 = none)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])

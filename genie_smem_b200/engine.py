@@ -895,6 +895,8 @@ class PipelinedEngine:
             eng = self.engines[e]
             with torch.cuda.stream(self.s_out):                # the host has seen ev: the chunk's kernels are done
                 out_rec[rec_total * 16:(rec_total + n_rec) * 16].copy_(eng.records[: n_rec * 16], non_blocking=True)
+                if rec_total:                                  # chunk-local offsets -> global offsets, on the device
+                    eng.rec_off[: hi - lo].add_(rec_total)
                 out_off[lo * 8:hi * 8].copy_(eng.rec_off[: hi - lo].view(torch.uint8), non_blocking=True)
                 out_st[lo:hi].copy_(eng.read_status[: hi - lo], non_blocking=True)
                 d = torch.cuda.Event()
@@ -924,10 +926,7 @@ class PipelinedEngine:
         self.s_out.synchronize()
         self.s_comp.synchronize()
         torch.cuda.current_stream().wait_stream(self.s_out)
-        # chunk-local offsets -> global offsets (host, n+1 int64 adds)
         offs = out_off.numpy()[: (n + 1) * 8].view(np.int64)
-        for lo, hi, base, n_rec in chunk_rec:
-            offs[lo:hi] += base
         offs[n] = rec_total
         self.kernel_launches = sum(e.kernel_launches for e in self.engines) + self.pack_launches
         self.last_d2h_bytes = rec_total * 16 + (n + 1) * 8 + n + 64 * len(chunk_rec)

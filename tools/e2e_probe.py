@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Where does the end-to-end step spend its time?  PCIe rates of this box, pinned flags of the batch
-buffers, and the pipelined path at several chunk counts (one JSON line each)."""
+"""End-to-end path (raw ASCII reads in pinned host memory -> host records) vs chunk count, next to the device-resident step.
+python tools/e2e_probe.py [ref_bases] [reads] [chunk counts...]"""
 import json
 import os
 import sys
@@ -8,64 +8,50 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
 import bench  # noqa: E402
+import genie_smem_b200 as g  # noqa: E402
 
-
-def main():
-    import torch
-    import genie_smem_b200 as g
-    n = 1 << 30
-    h = torch.empty(n, dtype=torch.uint8).pin_memory()
-    d = torch.empty(n, dtype=torch.uint8, device="cuda")
-    for name, fn in (("h2d", lambda: d.copy_(h, non_blocking=True)), ("d2h", lambda: h.copy_(d, non_blocking=True))):
-        fn(); torch.cuda.synchronize()
-        t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); dt = time.perf_counter() - t0
-        print(json.dumps({"copy": name, "gbytes_per_s": round(n / dt / 1e9, 1)}))
-    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-    h2 = torch.empty(n, dtype=torch.uint8).pin_memory()
-    d2 = torch.empty(n, dtype=torch.uint8, device="cuda")
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    with torch.cuda.stream(s1):
-        d.copy_(h, non_blocking=True)
-    with torch.cuda.stream(s2):
-        h2.copy_(d2, non_blocking=True)
-    torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    print(json.dumps({"copy": "h2d+d2h concurrent", "gbytes_per_s_each": round(n / dt / 1e9, 1)}))
-    del h, d, h2, d2
-
-    ref = bench.make_reference(100_000_000)
-    packed = g.PackedIndex.from_host(g.HostIndex.build(bench._B[ref].tobytes()))
-    index = g.DeviceIndex(packed, "cuda", with_sa=False, with_text=False)
-    reads = bench.make_reads_host(ref, 10_000_000, bench.READ_LEN, seed=101)
-    batch = g.ReadBatch.from_codes(reads, bench.READ_LEN, pin=True)
-    print(json.dumps({"pinned": {k: bool(torch.from_numpy(v).is_pinned()) for k, v in
-                                 (("packed", batch.packed_host), ("chunk_off", batch.chunk_off_host.view("int32")), ("len", batch.len_host.view("int32")))}}))
-    batch.to("cuda")
-    eng = g.Engine(index, batch.n, bench.READ_LEN, mems_per_read=24, recs_per_read=8)
+n_ref = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000_000
+n_reads = int(sys.argv[2]) if len(sys.argv) > 2 else 50_000_000
+chunks = [int(x) for x in sys.argv[3:]] or [8, 16, 32]
+dev = torch.device("cuda")
+ref = bench.make_reference(n_ref, 1000)
+ref_dev = torch.from_numpy(ref).to(dev)
+index = g.DeviceIndex.build_on_device(ref_dev, dev).build_seed_table()
+codes = torch.empty((n_reads, bench.READ_LEN), dtype=torch.uint8, device=dev)
+bench.device_reads(ref_dev, n_reads, bench.READ_LEN, 1001, codes)
+batch = g.ReadBatch.from_device_bases(codes, bench.READ_LEN)
+lut4 = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+ascii_host = torch.empty((n_reads, bench.READ_LEN), dtype=torch.uint8, pin_memory=True)
+for a in range(0, n_reads, 5_000_000):
+    ascii_host[a:a + 5_000_000].copy_(lut4[codes[a:a + 5_000_000].long()])
+del codes, ref_dev
+eng = g.Engine(index, n_reads, bench.READ_LEN, mems_per_read=24, recs_per_read=8)
+for _ in range(2):
+    eng.launch(g.METHOD_BWA, batch, min_len=1)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(3):
+    eng.launch(g.METHOD_BWA, batch, min_len=1)
+e1.record()
+torch.cuda.synchronize()
+print(json.dumps({"path": "device-resident launch", "ms": round(e0.elapsed_time(e1) / 3, 2)}), flush=True)
+del eng
+torch.cuda.empty_cache()
+for nc in chunks:
+    pipe = g.PipelinedEngine(index, n_reads, bench.READ_LEN, n_chunks=nc, mems_per_read=24, recs_per_read=8)
     for _ in range(2):
-        eng.launch(g.METHOD_BWA, batch)
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(3):
-        eng.launch(g.METHOD_BWA, batch)
+        pipe.run_ascii(g.METHOD_BWA, ascii_host, bench.READ_LEN, min_len=1)
     torch.cuda.synchronize()
-    print(json.dumps({"path": "device-resident launch", "ms": round((time.perf_counter() - t0) / 3 * 1e3, 2)}))
-    for _ in range(2):
-        eng.run(g.METHOD_BWA, batch)
     t0 = time.perf_counter()
     for _ in range(3):
-        eng.run(g.METHOD_BWA, batch)
-    print(json.dumps({"path": "Engine.run (serial H2D, kernels, D2H)", "ms": round((time.perf_counter() - t0) / 3 * 1e3, 2)}))
-    del eng
-    for nc in (2, 4, 8, 16):
-        pipe = g.PipelinedEngine(index, batch.n, bench.READ_LEN, n_chunks=nc, mems_per_read=24, recs_per_read=8)
-        for _ in range(2):
-            pipe.run(g.METHOD_BWA, batch)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            pipe.run(g.METHOD_BWA, batch)
-        print(json.dumps({"path": f"PipelinedEngine n_chunks={nc}", "ms": round((time.perf_counter() - t0) / 3 * 1e3, 2)}))
-        del pipe
-
-
-if __name__ == "__main__":
-    main()
+        res = pipe.run_ascii(g.METHOD_BWA, ascii_host, bench.READ_LEN, min_len=1)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / 3 * 1e3
+    print(json.dumps({"path": f"PipelinedEngine.run_ascii n_chunks={nc}", "ms": round(ms, 2), "Mreads_per_s": round(n_reads / ms / 1e3, 1),
+                      "launch_chunks": len(pipe._chunk_bounds(n_reads)) - 1, "records": int(len(res.records))}), flush=True)
+    del pipe
+    torch.cuda.empty_cache()
