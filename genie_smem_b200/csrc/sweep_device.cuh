@@ -40,7 +40,7 @@ struct SweepArgs {
     unsigned long long* counters;
 };
 
-// Shared memory: [256 x u32 spread table][per pair: SWEEP_CAP candidates of 16 B {end, lo, cnt, -}, then
+// Shared memory: [per pair: SWEEP_CAP candidates of 16 B {end, lo, cnt, -}, then
 // the read's bases one per byte, then its packed words][16 B pad].  Indexed through one extern array so that
 // the compiler emits LDS/STS.
 extern __shared__ uint4 g_sweep_smem[];
@@ -89,6 +89,9 @@ __device__ __forceinline__ uint4 ldg_seed(const uint4* p) {
     return v;
 }
 
+// byte of four 2-bit bases (MSB first) -> four bytes, first base at the lowest address (no table: one multiply)
+__device__ __forceinline__ uint32_t spread4(uint32_t x) { return ((x * 0x01004010u) | (x >> 6)) & 0x03030303u; }
+
 struct DevSweepCtx {
     const SweepArgs& a;
     uint32_t cand0;       // index (uint4) of this pair's candidate slots
@@ -107,19 +110,16 @@ struct DevSweepCtx {
         L = __ldg(a.len + rid);
         const uint32_t off = __ldg(a.chunk_off + rid);
         const uint32_t nch = (L + 63u) >> 6;
-        const uint32_t nwords = (L + 3u) >> 2;      // four bases per unpacked word
-        const uint32_t* spread = reinterpret_cast<const uint32_t*>(g_sweep_smem);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(g_sweep_smem) + (bytes0 >> 2);
+        uint4* dst = g_sweep_smem + (bytes0 >> 4);
         __syncwarp(gmask);                       // both lanes are done with the previous read's bases
         for (uint32_t c = g; c < nch; c += SWEEP_LPR) {
             const uint4 v = __ldg(a.reads + (size_t)off + c);
             g_sweep_smem[(words0 >> 2) + c] = v;
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (c * 16 + k * 4 + q < nwords) dst[c * 16 + k * 4 + q] = spread[(w[k] >> (24 - 8 * q)) & 0xFFu];
+            for (int k = 0; k < 4; ++k)          // 16 packed bases -> 16 bytes, first base at the lowest address
+                if (c * 4 + k < a.read_u4)
+                    dst[c * 4 + k] = make_uint4(spread4(w[k] >> 24), spread4((w[k] >> 16) & 0xFFu), spread4((w[k] >> 8) & 0xFFu), spread4(w[k] & 0xFFu));
         }
         __syncwarp(gmask);
         return true;
@@ -165,15 +165,11 @@ struct DevSweepCtx {
 __host__ __device__ inline uint32_t sweep_read_u4(uint32_t max_len) { return (max_len + 15u) / 16u; }
 
 __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS) k_sweep(const SweepArgs a) {
-    // spread table: byte of four 2-bit bases (MSB first) -> four bytes, first base at the lowest address
-    for (uint32_t b = threadIdx.x; b < 256; b += SWEEP_THREADS)
-        reinterpret_cast<uint32_t*>(g_sweep_smem)[b] = ((b >> 6) & 3u) | (((b >> 4) & 3u) << 8) | (((b >> 2) & 3u) << 16) | ((b & 3u) << 24);
-    __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t g = lane & 1u;
     const uint32_t pair_in_block = threadIdx.x >> 1;
     const uint32_t pair_u4 = SWEEP_CAP + a.read_u4 + a.pack_u4;
-    const uint32_t p0 = 64u + pair_in_block * pair_u4;               // 64 uint4 = the 1 KB spread table
+    const uint32_t p0 = pair_in_block * pair_u4;
     const size_t gp = (size_t)blockIdx.x * SWEEP_GROUPS + pair_in_block;
     DevSweepCtx ctx{a, p0, (p0 + SWEEP_CAP) * 16u, (p0 + SWEEP_CAP + a.read_u4) * 4u, a.scratch + gp * 2 * a.max_len,
                     a.scratch + gp * 2 * a.max_len + a.max_len, g, 3u << (lane & ~1u), lane & ~1u};
@@ -199,7 +195,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS) k_sweep(const
 __host__ __device__ inline uint32_t sweep_pack_u4(uint32_t max_len) { return (max_len + 63u) / 64u; }
 
 inline size_t sweep_smem_bytes(uint32_t max_len) {
-    return 1024 + (size_t)SWEEP_GROUPS * (SWEEP_CAP + sweep_read_u4(max_len) + sweep_pack_u4(max_len)) * sizeof(uint4) + 16;
+    return (size_t)SWEEP_GROUPS * (SWEEP_CAP + sweep_read_u4(max_len) + sweep_pack_u4(max_len)) * sizeof(uint4) + 16;
 }
 
 }  // namespace gsm

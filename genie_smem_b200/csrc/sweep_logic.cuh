@@ -227,14 +227,15 @@ struct Sweeper {
         if (fwd && r.cnt_new != cnt) c.cand_put(ncand++, pos, k, cnt);     // count about to change: q[x:pos) is a candidate
         if (r.cnt_new != 0) {
             k += r.lt_add; P0 = r.lo_new; cnt = r.cnt_new;
+            // one site for both directions: FWD and WALK lanes of a warp fetch their next base together
+            const bool more = fwd ? (pos + 1u != L) : (pos != lb && pos != 0u);
+            if (more) { pos += fwd ? 1u : 0xFFFFFFFFu; ch = c.base(pos); return; }
             if (fwd) {
                 pos++;
-                if (pos != L) { ch = c.base(pos); return; }
                 c.cand_put(ncand++, pos, k, cnt);                          // ran off the right end
                 start_bwd(c, m);
                 return;
             }
-            if (pos != lb && pos != 0) { pos--; ch = c.base(pos); return; }
             walk_end(c, m, pos);                                           // reached the lower bound (or the left end)
             return;
         }
