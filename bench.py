@@ -39,6 +39,24 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE JSON line: keep a private copy of it and point fd 1 at stderr, so that nothing a library
+# prints (NCCL's version banner under NCCL_DEBUG, torch warnings) can land next to the result
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_result(obj):
+    _claim_stdout()
+    print(json.dumps(obj), file=_RESULT_OUT, flush=True)
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -211,6 +229,7 @@ def device_reads(ref_dev, n, L, seed, out, sub_rate=SUB_RATE, chunk=2_000_000):
 
 def main():
     args = parse_args()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -419,7 +438,7 @@ def main():
                "clocks": clocks, "methods": methods, "records_total": total_records, "maximal_matches_per_read": round(n_mems / args.reads, 3),
                "record_gather": gather, "index_build": index.build_stats}
         out["sweep_seed_table_K"] = int(index.c.seed_K)
-        print(json.dumps(out), flush=True)
+        emit_result(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -495,7 +514,7 @@ def reference_arm(args, workload):
            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload,
            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": thr, "kind": "port", "sample": sample},
            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit_result(out)
 
 
 if __name__ == "__main__":
