@@ -128,6 +128,8 @@ struct DevSweepCtx {
         return reinterpret_cast<const uint8_t*>(g_sweep_smem)[bytes0 + pos];
     }
     __device__ __forceinline__ uint32_t seed_k() const { return a.seed_K; }
+    // the unique-match shortcut of sweep_logic.cuh stays compiled out of the kernel: measured slower (profiles/r01_notes.md)
+    __device__ __forceinline__ constexpr bool uniq() const { return false; }
     // code of q[pos:pos+K): top 2K bits of the 64-bit window starting at base pos (MSB-first packing)
     __device__ __forceinline__ uint32_t kmer(uint32_t pos) const {
         const uint32_t* w = reinterpret_cast<const uint32_t*>(g_sweep_smem) + words0 + (pos >> 4);

@@ -58,12 +58,23 @@ struct SeedEntry {
     uint32_t fwd_lo, cnt, rev_lo, pad;
 };
 
-enum SweepMode : int { M_FETCH = 0, M_FWD = 1, M_WALK = 2, M_SEEDF = 3, M_SEEDB = 4, M_DONE = 5 };
+enum SweepMode : int { M_FETCH = 0, M_FWD = 1, M_WALK = 2, M_SEEDF = 3, M_SEEDB = 4, M_DONE = 5,
+                       // unique-match shortcut (needs suffix array, inverse suffix array and packed text; see Ctx::uniq):
+                       M_SAF = 6,    // fetch suffix_array[k]: where in the text the unique occurrence of q[x:pos) starts (FWD)
+                       M_SAW = 7,    // the same for the longest candidate when the forward phase never needed it (first WALK)
+                       M_CMPF = 8,   // compare q[pos..) with the text behind the occurrence, up to SWEEP_CMP_CHUNK bases per fetch
+                       M_CMPB = 9,   // compare q[..pos) with the text in front of the occurrence
+                       M_ISA = 10 }; // fetch inverse_suffix_array[text position]: the row of the extended match
+
+constexpr uint32_t SWEEP_CMP_CHUNK = 64;   // bases compared per text fetch
 
 // Ctx must provide:
 //   bool     fetch(uint32_t& rid, uint32_t& L)          next read (loads its bases), false when none
 //   uint32_t base(uint32_t pos)                         2-bit base of the current read
 //   uint32_t seed_k()                                   K of the seed table, 0 = no table
+//   bool     uniq()                                     unique-match shortcut available (k_sweep: compiled out, returns
+//                                                       false -- measured slower until sweep transitions are batched,
+//                                                       profiles/r01_notes.md; the host-compiled test runs both settings)
 //   uint32_t kmer(uint32_t pos)                         code of q[pos:pos+K) (LUT.convert_seq_to_num, LUT.py:37-48)
 //   void     cand_put(uint32_t i, uint32_t j, uint32_t lo, uint32_t cnt)
 //   void     cand_get(uint32_t i, uint32_t& j, uint32_t& lo, uint32_t& cnt)
@@ -85,10 +96,28 @@ struct Sweeper {
     uint32_t ncand = 0;        // stored candidates (ends >= x + K when the sweep was seeded)
     uint32_t short_hi = 0;     // short candidates still to walk: ends x+1 .. short_hi (none if <= x)
     uint32_t last_start = 0;
+    // Unique-match shortcut.  Once q[x:pos) occurs exactly ONCE, every further extension is decided by the text itself:
+    // one suffix-array fetch locates the occurrence (tpos = text index of q[x]), then SWEEP_CMP_CHUNK bases are compared
+    // per text fetch instead of one FM step per base; the row of a match extended to the left is one inverse-suffix-array
+    // fetch.  Same results by construction: a unique occurrence extends exactly as far as the text around it agrees.
+    uint32_t tpos = 0, have_tpos = 0;
+    uint32_t aux = 0;          // index of the pending suffix-array / inverse-suffix-array fetch
 
     GSM_HD bool pending_step() const { return mode == M_FWD || mode == M_WALK; }
     GSM_HD bool pending_seed() const { return mode == M_SEEDF || mode == M_SEEDB; }
+    GSM_HD bool pending_word() const { return mode == M_SAF || mode == M_SAW || mode == M_ISA; }
+    GSM_HD bool pending_cmp() const { return mode == M_CMPF || mode == M_CMPB; }
     GSM_HD bool on_reverse() const { return mode == M_FWD; }
+    // operands of the pending text comparison.  Forward: text[cmp_text() + i] against q[cmp_read() + i]; backward:
+    // text[cmp_text() - 1 - i] against q[cmp_read() - 1 - i]; i < min(cmp_max(n_bases), SWEEP_CMP_CHUNK).
+    GSM_HD uint32_t cmp_text() const { return mode == M_CMPF ? tpos + (pos - x) : tpos - (x - pos); }
+    GSM_HD uint32_t cmp_read() const { return pos; }
+    GSM_HD uint32_t cmp_max(uint32_t n_bases) const {
+        const uint32_t t = cmp_text();
+        const uint32_t a = mode == M_CMPF ? L - pos : pos - lb;
+        const uint32_t b = mode == M_CMPF ? n_bases - t : t;
+        return a < b ? a : b;
+    }
 
     GSM_HD void emit_match(Ctx& c, uint32_t start, uint32_t end, uint32_t lo, uint32_t n) {
         MemEntry e;
@@ -108,7 +137,7 @@ struct Sweeper {
     // Start the sweep at x (a read is in progress, x < L).  Leaves a pending operation, or mode == M_FETCH.
     GSM_HD void start_sweep(Ctx& c, const IndexMeta& m) {
         const uint32_t b = c.base(x);
-        ncand = 0; short_hi = 0;
+        ncand = 0; short_hi = 0; have_tpos = 0;
         if (m.cnt[b] == 0) {              // base absent from the text (outside the reference's domain): skip it
             lb = x + 1; x++; sweep_id++;
             if (x >= L) c.finish(rid, n_mems);
@@ -126,11 +155,59 @@ struct Sweeper {
         fwd_continue(c, m);
     }
 
-    // (k, P0, cnt) describe q[x:pos): append q[pos], or close the forward phase at the read end.
+    // (k, P0, cnt) describe q[x:pos): append q[pos], or close the forward phase at the read end.  A unique occurrence
+    // is followed in the text instead (M_SAF -> M_CMPF).
     GSM_HD void fwd_continue(Ctx& c, const IndexMeta& m) {
-        if (pos < L) { ch = c.base(pos); mode = M_FWD; return; }
+        if (pos < L) {
+            if (cnt == 1u && c.uniq()) { aux = k; mode = M_SAF; return; }
+            ch = c.base(pos); mode = M_FWD;
+            return;
+        }
         c.cand_put(ncand++, pos, k, cnt);
         start_bwd(c, m);
+    }
+
+    // forward comparison finished (or impossible): q[x:pos) is the longest forward match
+    GSM_HD void uniq_fwd_done(Ctx& c, const IndexMeta& m) {
+        c.cand_put(ncand++, pos, k, 1u);
+        start_bwd(c, m);
+    }
+    // q[pos:cur_j) is matched at text index tpos - (x - pos): compare further left, or finish
+    GSM_HD void uniq_walk_next(Ctx& c, const IndexMeta& m) {
+        mode = M_CMPB;
+        if (cmp_max(m.n_rows - 1u) != 0u) return;
+        uniq_walk_done(c, m);
+    }
+    GSM_HD void uniq_walk_done(Ctx& c, const IndexMeta& m) {
+        if (pos == x) { walk_end(c, m, x); return; }            // no extension: the interval of the candidate stands
+        aux = tpos - (x - pos);                                 // the extended match starts here in the text
+        mode = M_ISA;
+    }
+
+    // result of the pending suffix-array / inverse-suffix-array fetch
+    GSM_HD void consume_word(Ctx& c, const IndexMeta& m, uint32_t v) {
+        if (mode == M_ISA) { P0 = v; cnt = 1u; walk_end(c, m, pos); return; }
+        tpos = v - 1u;                                          // suffix-array values are 1-based (ExactMatch.py:66)
+        have_tpos = 1u;
+        if (mode == M_SAF) {
+            mode = M_CMPF;
+            if (cmp_max(m.n_rows - 1u) == 0u) uniq_fwd_done(c, m);
+            return;
+        }
+        uniq_walk_next(c, m);                                   // M_SAW
+    }
+
+    // result of the pending text comparison: `matched` bases agree (already capped by cmp_max and the chunk size)
+    GSM_HD void consume_cmp(Ctx& c, const IndexMeta& m, uint32_t matched) {
+        if (mode == M_CMPF) {
+            pos += matched;
+            if (matched == SWEEP_CMP_CHUNK && cmp_max(m.n_rows - 1u) != 0u) return;     // a whole chunk agreed: next chunk
+            uniq_fwd_done(c, m);
+            return;
+        }
+        pos -= matched;
+        if (matched == SWEEP_CMP_CHUNK && cmp_max(m.n_rows - 1u) != 0u) return;
+        uniq_walk_done(c, m);
     }
 
     // Forward phase over: pop the longest candidate and walk it left.
@@ -143,6 +220,12 @@ struct Sweeper {
         if (x == 0) {                       // nothing to prepend: every candidate starts at 0, the longest wins
             emit_match(c, 0, cur_j, P0, cnt);
             end_sweep(c);
+            return;
+        }
+        if (cnt == 1u && x != lb && c.uniq()) {      // unique occurrence: extend it to the left along the text
+            pos = x;
+            if (have_tpos) uniq_walk_next(c, m);
+            else { aux = P0; mode = M_SAW; }
             return;
         }
         walk_from(c, m, x);
@@ -229,11 +312,10 @@ struct Sweeper {
             k += r.lt_add; P0 = r.lo_new; cnt = r.cnt_new;
             // one site for both directions: FWD and WALK lanes of a warp fetch their next base together
             const bool more = fwd ? (pos + 1u != L) : (pos != lb && pos != 0u);
-            if (more) { pos += fwd ? 1u : 0xFFFFFFFFu; ch = c.base(pos); return; }
+            if (more && !(fwd && cnt == 1u && c.uniq())) { pos += fwd ? 1u : 0xFFFFFFFFu; ch = c.base(pos); return; }
             if (fwd) {
                 pos++;
-                c.cand_put(ncand++, pos, k, cnt);                          // ran off the right end
-                start_bwd(c, m);
+                fwd_continue(c, m);                                        // read end, or unique: follow the text
                 return;
             }
             walk_end(c, m, pos);                                           // reached the lower bound (or the left end)

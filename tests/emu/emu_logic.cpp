@@ -27,6 +27,8 @@ struct HostIndex {
 struct SweepCtx {
     const uint32_t* words = nullptr;
     uint32_t K = 0;                      // seed table K (0 = none)
+    bool use_uniq = false;               // unique-match shortcut (suffix array + inverse suffix array + text)
+    bool uniq() const { return use_uniq; }
     uint32_t seed_k() const { return K; }
     uint32_t kmer(uint32_t pos) const {
         auto rd = [&](uint64_t w) { return words[w]; };
@@ -173,13 +175,40 @@ struct SelCtx {
 }  // namespace
 
 extern "C" {
-
-void emu_counters(uint64_t* out, int reset) { for (int i = 0; i < 8; ++i) { out[i] = g_cnt[i]; if (reset) g_cnt[i] = 0; } }
-
 struct EmuIndex {
     const void* fwd; const void* rev; const uint32_t* sa; const uint32_t* text;
     uint32_t C[4]; uint32_t cnt[4]; uint32_t prim_f, prim_r, n_rows, pad; uint64_t n_bases;
+    const uint32_t* isa;                 // optional: enables the sweep's unique-match shortcut
 };
+}
+
+// the non-FM operations of the sweep's unique-match shortcut; true if one was served
+template <typename Sw, typename Ctx>
+static bool serve_uniq(Sw& sw, Ctx& ctx, const IndexMeta& meta, const EmuIndex* ei, const uint32_t* words) {
+    if (sw.pending_word()) {
+        g_cnt[3]++;                                                          // [3] SA / ISA fetches
+        sw.consume_word(ctx, meta, sw.mode == M_ISA ? ei->isa[sw.aux] : ei->sa[sw.aux]);
+        return true;
+    }
+    if (sw.pending_cmp()) {
+        g_cnt[2]++;                                                          // [2] text comparisons
+        uint32_t mx = sw.cmp_max((uint32_t)ei->n_bases);
+        if (mx > SWEEP_CMP_CHUNK) mx = SWEEP_CMP_CHUNK;
+        const uint32_t t = sw.cmp_text(), q = sw.cmp_read();
+        uint32_t mt = 0;
+        if (sw.mode == M_CMPF) while (mt < mx && base_msb(ei->text, t + mt) == base_msb(words, q + mt)) ++mt;
+        else while (mt < mx && base_msb(ei->text, t - 1 - mt) == base_msb(words, q - 1 - mt)) ++mt;
+        sw.consume_cmp(ctx, meta, mt);
+        return true;
+    }
+    return false;
+}
+
+extern "C" {
+
+void emu_counters(uint64_t* out, int reset) { for (int i = 0; i < 8; ++i) { out[i] = g_cnt[i]; if (reset) g_cnt[i] = 0; } }
+
+
 
 // Maximal exact matches of one read: out gets 4 x u32 per match (start, end, lo, cnt), sorted by
 // end.  Returns the number of matches.
@@ -188,7 +217,7 @@ int emu_sweep(const EmuIndex* ei, const uint32_t* words, uint32_t L, uint32_t* o
     HostIndex ix{(const Half*)ei->fwd, (const Half*)ei->rev, ei->sa, ei->text, {}, ei->n_bases};
     for (int c = 0; c < 4; ++c) { ix.meta.C[c] = ei->C[c]; ix.meta.cnt[c] = ei->cnt[c]; }
     ix.meta.prim_f = ei->prim_f; ix.meta.prim_r = ei->prim_r; ix.meta.n_rows = ei->n_rows;
-    SweepCtx ctx; ctx.words = words; ctx.L = L; ctx.K = seed_tab ? seed_K : 0;
+    SweepCtx ctx; ctx.words = words; ctx.L = L; ctx.K = seed_tab ? seed_K : 0; ctx.use_uniq = ei->isa != nullptr;
     Sweeper<SweepCtx> sw;
     uint64_t steps = 0;
     for (;;) {
@@ -200,6 +229,7 @@ int emu_sweep(const EmuIndex* ei, const uint32_t* words, uint32_t L, uint32_t* o
             ++steps;
             continue;
         }
+        if (serve_uniq(sw, ctx, ix.meta, ei, words)) { ++steps; continue; }
         const bool rev = sw.on_reverse();
         const Half* bk = rev ? ix.rev : ix.fwd;
         auto load = [&](uint64_t idx) { return bk[idx]; };
@@ -229,7 +259,7 @@ int emu_smem(const EmuIndex* ei, int method, const uint32_t* words, uint32_t L, 
     for (int c = 0; c < 4; ++c) { ix.meta.C[c] = ei->C[c]; ix.meta.cnt[c] = ei->cnt[c]; }
     ix.meta.prim_f = ei->prim_f; ix.meta.prim_r = ei->prim_r; ix.meta.n_rows = ei->n_rows;
     if (method != 0 && L < K) return -2;
-    SweepCtx ctx; ctx.words = words; ctx.L = L; ctx.K = seed_tab ? seed_K : 0;
+    SweepCtx ctx; ctx.words = words; ctx.L = L; ctx.K = seed_tab ? seed_K : 0; ctx.use_uniq = ei->isa != nullptr;
     Sweeper<SweepCtx> sw;
     for (;;) {
         if (!sw.next(ctx, ix.meta)) break;
@@ -237,6 +267,7 @@ int emu_smem(const EmuIndex* ei, int method, const uint32_t* words, uint32_t L, 
             sw.consume_seed(ctx, ix.meta, ((const SeedEntry*)seed_tab)[sw.P0]);
             continue;
         }
+        if (serve_uniq(sw, ctx, ix.meta, ei, words)) continue;
         const bool rev = sw.on_reverse();
         const Half* bk = rev ? ix.rev : ix.fwd;
         auto load = [&](uint64_t idx) { return bk[idx]; };

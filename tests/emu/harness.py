@@ -28,7 +28,7 @@ def build():
 class EmuIndex(C.Structure):
     _fields_ = [("fwd", C.c_void_p), ("rev", C.c_void_p), ("sa", C.c_void_p), ("text", C.c_void_p), ("C", C.c_uint32 * 4),
                 ("cnt", C.c_uint32 * 4), ("prim_f", C.c_uint32), ("prim_r", C.c_uint32), ("n_rows", C.c_uint32), ("pad", C.c_uint32),
-                ("n_bases", C.c_uint64)]
+                ("n_bases", C.c_uint64), ("isa", C.c_void_p)]
 
 
 class Emu:
@@ -77,7 +77,19 @@ class Emu:
         self._lut = {}
         self._seed = {}
         self.seed_K = 0          # seed table used by sweep()/smem(); 0 = plain stepping
+        self.isa = np.zeros(self.n_rows, np.uint32)                      # inverse suffix array: row of the suffix at each text index
+        self.isa[self.sa.astype(np.int64) - 1] = np.arange(self.n_rows, dtype=np.uint32)
+        self.e.isa = None
         self.rmi_fast = False    # smem(2, ...): try the error-bounded RmiFast search before the literal one
+
+    @property
+    def uniq(self):
+        """Unique-match shortcut of the sweep logic (needs the inverse suffix array) on / off."""
+        return bool(self.e.isa)
+
+    @uniq.setter
+    def uniq(self, on):
+        self.e.isa = self.isa.ctypes.data if on else None
 
     def seed_table(self, K):
         if K not in self._seed:

@@ -85,6 +85,7 @@ def test_sweep_and_select_logic_vs_reference(emus, fname, stride, seed_K):
     g = gu.load_json(fname)
     _, em = emus[g["ref"]]
     em.seed_K = seed_K
+    em.uniq = seed_K == 9                 # unique-match shortcut of sweep_logic.cuh on for one of the three settings
     if seed_K:
         stride *= 2
     reads = g["reads"]
@@ -107,11 +108,15 @@ def test_sweep_and_select_logic_vs_reference(emus, fname, stride, seed_K):
                 assert records_to_dict(q, r) == e
 
 
+@pytest.mark.parametrize("uniq", [False, True])
 @pytest.mark.parametrize("seed_K", [0, 1, 2, 3, 4, 6, 8])
-def test_maximal_matches_are_exactly_the_right_maximal_LS_pairs(emus, seed_K):
-    """sweep output == {(LS[j], j) : j == L or LS[j+1] > LS[j]} with true SA intervals, with and without the seed table."""
+def test_maximal_matches_are_exactly_the_right_maximal_LS_pairs(emus, seed_K, uniq):
+    """sweep output == {(LS[j], j) : j == L or LS[j+1] > LS[j]} with true SA intervals, with and without the seed table
+    and the unique-match shortcut (text comparison instead of FM steps once a match occurs once; logic only -- the
+    kernel compiles it out, profiles/r01_notes.md)."""
     g, em = emus["medium_data"]
     em.seed_K = seed_K
+    em.uniq = uniq
     idx = rp.RefIndex(g["text"], g["suffix_array"])
     rng = random.Random(5)
     for _ in range(150):
@@ -147,12 +152,14 @@ ACGT = st.text(alphabet="ACGT", min_size=1, max_size=60)
 @settings(max_examples=60, deadline=None)
 @given(text=st.one_of(st.text(alphabet="ACGT", min_size=8, max_size=200),
                       st.builds(lambda u, k: (u * k)[:200], st.text(alphabet="ACGT", min_size=1, max_size=7), st.integers(2, 40))),
-       reads=st.lists(ACGT, min_size=1, max_size=6), K=st.integers(2, 5), seed_K=st.integers(0, 6))
-def test_property_random_and_repetitive_references(text, reads, K, seed_K):
+       reads=st.lists(ACGT, min_size=1, max_size=6), K=st.integers(2, 5), seed_K=st.integers(0, 6), uniq=st.booleans())
+def test_property_random_and_repetitive_references(text, reads, K, seed_K, uniq):
     if len(set(text)) < 4:
         text = text + "ACGT"           # parity domain: all four bases occur
     em = Emu(text)
     em.seed_K = seed_K
+    em.uniq = uniq
+    reads = reads + [text[max(0, len(text) - 40):], text[:50]]     # matches touching both ends of the text
     idx = rp.RefIndex(text)
     o = rp.RefSMEM(idx, lut=rp.RefLUT(idx, K))
     for q in reads:
