@@ -62,6 +62,29 @@ class _FmIndexView(dict):
         return True
 
 
+class _DeviceBuiltIndex:
+    """Adapter with HostIndex's read-only surface (info, n_rows, export, count_dic) over an index that was built ON THE
+    GPU (engine.DeviceIndex.build_on_device): what create_fm_index uses for large references."""
+
+    def __init__(self, dev_index, text):
+        self.dev, self._text = dev_index, text
+        self.info = dev_index.info
+        self.n_rows, self.n_bases = dev_index.n_rows, dev_index.n_bases
+
+    def export(self):
+        sa = self.dev.suffix_array_host().copy()
+        t = np.frombuffer((self._text + "$").encode(), np.uint8)
+        bwt = t[(sa.astype(np.int64) - 2) % len(t)]          # the character before each suffix ('$' before the whole text)
+        return sa, bwt.tobytes()
+
+    def count_dic(self):
+        return self.dev.count_dic()
+
+
+# references at least this long are indexed on the GPU by create_fm_index / from_text (host SA-IS below)
+DEVICE_BUILD_MIN_BASES = 1 << 22
+
+
 class ExactMatch:
     def __init__(self, reference_sequence_file: str, query_sequence_file: str = None, device="cuda"):
         self.ref_seq_file = reference_sequence_file
@@ -87,7 +110,7 @@ class ExactMatch:
 
     def create_fm_index(self):
         self.load_ref_sequence()
-        self._set_host(eng.HostIndex.build(self.ref_sequence[:-1]))
+        self._build(self.ref_sequence[:-1])
         sa, _ = self._host.export()
         np.savez(path.join("data", self._npz), suffix_array=sa, ref_size=np.int64(self.ref_size))
 
@@ -105,13 +128,30 @@ class ExactMatch:
         self._set_host(eng.HostIndex.from_arrays(self.ref_sequence[:-1], sa))
 
     @classmethod
-    def from_text(cls, text, suffix_array=None, device="cuda", name="memory.fa"):
-        """Build directly from a string (no files): used by benchmarks and tests."""
+    def from_text(cls, text, suffix_array=None, device="cuda", name="memory.fa", builder="auto"):
+        """Build directly from a string (no files): used by benchmarks and tests.  builder: "host" (SA-IS), "device"
+        (gsm_index_build_device) or "auto" (device for references of DEVICE_BUILD_MIN_BASES bases and more)."""
         m = cls(name, device=device)
         m.ref_sequence = text + "$"
         m.ref_size = len(text) + 1
-        m._set_host(eng.HostIndex.build(text) if suffix_array is None else eng.HostIndex.from_arrays(text, suffix_array))
+        if suffix_array is not None:
+            m._set_host(eng.HostIndex.from_arrays(text, suffix_array))
+        else:
+            m._build(text, builder)
         return m
+
+    def _build(self, text, builder="auto"):
+        """The index of `text`: on the GPU for large references (seconds at 10^9 bases), host SA-IS otherwise.
+        Replaces the n^2 rotation sort of ExactMatch.create_fm_index (reference ExactMatch.py:52-58)."""
+        import torch
+        on_device = builder == "device" or (builder == "auto" and len(text) >= DEVICE_BUILD_MIN_BASES and torch.cuda.is_available())
+        if not on_device:
+            self._set_host(eng.HostIndex.build(text))
+            return
+        _check_bases(text) if len(text) < 1 << 16 else None       # large texts: the device packer validates
+        dev = eng.DeviceIndex.build_on_device(text, self._device)
+        self._set_host(_DeviceBuiltIndex(dev, text))
+        self._dev = dev
 
     def _set_host(self, host):
         self._host = host

@@ -121,3 +121,19 @@ def test_device_built_index_round_trips_through_disk(gs, tmp_path):
     a = gs.backsearch_batch(dev, gs.ReadBatch.from_strings(reads))
     b = gs.backsearch_batch(back, gs.ReadBatch.from_strings(reads))
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.all(a[1] >= 1)
+
+
+@pytest.mark.parametrize("name", ["medium_data", "big_data"])
+def test_exactmatch_surface_on_a_device_built_index(gs, name):
+    """ExactMatch.from_text(builder="device"): the reference-shaped class over an index built on the GPU exposes the
+    reference's own arrays (suffix_array, bwt_array, count_dic) and answers like the golden sets."""
+    gidx = gu.load_index(name)
+    m = gs.ExactMatch.from_text(gidx["text"], builder="device", name=name + ".fa")
+    assert np.array_equal(m.fm_index["suffix_array"], gidx["suffix_array"])
+    assert "".join(m.fm_index["bwt_array"]) == gidx["bwt"]
+    assert m.fm_index["count_dic"] == gu.meta()[name]["count_dic"]
+    host = gs.ExactMatch.from_text(gidx["text"], builder="host", name=name + ".fa")
+    q = gidx["text"][100:180]
+    assert m.exact_match_back_prop(q) == host.exact_match_back_prop(q)
+    assert m.exact_match(q) == host.exact_match(q)
+    assert gs.SMEM(m).get_SMEMS(q[:30] + "T" + q[31:], 1) == gs.SMEM(host).get_SMEMS(q[:30] + "T" + q[31:], 1)
