@@ -1,0 +1,58 @@
+"""Host-side helpers that need no GPU: chunk schedule of the pipelined engine, bench.py argument / workload plumbing,
+read-sharding arithmetic."""
+import sys
+import types
+
+import numpy as np
+import pytest
+
+
+def test_pipelined_chunk_bounds_cover_the_batch():
+    from genie_smem_b200.engine import PipelinedEngine
+    for c in (1, 7, 64, 1000, 3_125_000):
+        o = types.SimpleNamespace(chunk_reads=c)
+        for n in (0, 1, c - 1, c, c + 1, 4 * c, 4 * c + 1, 16 * c, 16 * c + 3, 50_000_000):
+            if n < 0:
+                continue
+            b = PipelinedEngine._chunk_bounds(o, n)
+            assert b[0] == 0 and b[-1] == n
+            assert all(0 < y - x <= c for x, y in zip(b, b[1:])), (c, n)
+            if n > 4 * c and c >= 64:            # ramp: the first and last chunks are an eighth of a full one
+                assert b[1] - b[0] == c // 8 and b[-1] - b[-2] == c // 8
+
+
+def test_bench_configs_and_workload(monkeypatch):
+    import bench
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    a = bench.parse_args()
+    assert (a.ref_bases, a.reads, a.seed) == (1_000_000_000, 50_000_000, 1000) and "configs[3]" in a.cfg_name
+    w = bench.workload_dict(a, 8)
+    assert "x8" in w["parallelism"] and w["read_len"] == 151 and "configs[3]" in w["workload"]
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--config", "c3", "--gpus", "2"])
+    a = bench.parse_args()
+    assert (a.ref_bases, a.reads, a.seed, a.gpus) == (100_000_000, 10_000_000, 100, 2)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--ref-bases", "2000000", "--reads", "1000"])
+    a = bench.parse_args()
+    assert a.cfg_name == "custom size" and a.experts == bench.CONFIGS["c3"]["experts"]
+
+
+def test_synthetic_reads_are_substitution_only():
+    import bench
+    ref = bench.make_reference(50_000, 7)
+    r = bench.make_reads_host(ref, 200, 151, seed=8, sub_rate=0.02)
+    assert r.shape == (200, 151) and r.dtype == np.uint8 and r.max() <= 3
+    again = bench.make_reads_host(ref, 200, 151, seed=8, sub_rate=0.02)
+    assert np.array_equal(r, again)                        # the CPU arms regenerate exactly these reads
+    exact = bench.make_reads_host(ref, 50, 151, seed=9, sub_rate=0.0)
+    text = ref.tobytes()
+    for row in exact:
+        assert row.tobytes() in text
+
+
+def test_shard_range_partitions_reads():
+    from genie_smem_b200.sharding import shard_range
+    for n in (0, 1, 7, 50_000_000):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
