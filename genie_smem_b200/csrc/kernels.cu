@@ -255,7 +255,8 @@ __device__ __forceinline__ void phase_loop(uint32_t mask, Machine& mach, Begin b
 // (select_logic.cuh) is driven warp-wide:
 //   pass 1  every thread with a read in progress looks up the windows of its current round: predict + last-mile search
 //           through ONE probe site inside a loop that the whole warp leaves together (__any_sync) -- the error-bounded
-//           RmiFast first, then the literal RmiSearch for the windows it declared hazardous;
+//           search (RmiGallop / RmiLower / RmiUpper, one phase at a time) first, then the literal RmiSearch for the windows
+//           it declared hazardous;
 //   pass 2  each thread runs the integer frame machine of its round (divergent, no table probes), emits one record,
 //           and opens its next read when the current one is finished.
 // Measured alternatives (profiles/r01_notes.md): the reference's control flow per thread end to end (2.2 active threads

@@ -28,7 +28,7 @@ struct RmiModel {
     const double* intercept;
     uint32_t stride;            // distance between consecutive models in coef[] / intercept[] (1 = two dense arrays,
                                 // 2 = one interleaved {coef, intercept} array: one 16-byte line per model)
-    uint32_t n_none;            // > 0: none_rows holds the rows of the K short suffixes (enables RmiFast)
+    uint32_t n_none;            // > 0: none_rows holds the rows of the K short suffixes (enables the error-bounded search)
     uint32_t none_rows[32];
     uint32_t none_shift;        // none_map bit (row >> none_shift) is set iff that region of rows holds a None row
     uint32_t none_map[32];      // 1024 regions: the usual bracket is cleared with two bit tests

@@ -80,7 +80,7 @@ class Emu:
         self.isa = np.zeros(self.n_rows, np.uint32)                      # inverse suffix array: row of the suffix at each text index
         self.isa[self.sa.astype(np.int64) - 1] = np.arange(self.n_rows, dtype=np.uint32)
         self.e.isa = None
-        self.rmi_fast = False    # smem(2, ...): try the error-bounded RmiFast search before the literal one
+        self.rmi_fast = False    # smem(2, ...): try the error-bounded search (rmi_fast_lookup) before the literal one
 
     @property
     def uniq(self):
@@ -193,7 +193,7 @@ Emu.rmi_search = _rmi_search
 
 
 def _rmi_fast(self, rmi, code):
-    """(hazard, lo, hi, n_probes) through RmiFast, the error-bounded search of the common case."""
+    """(hazard, lo, hi, n_probes) through rmi_fast_lookup, the error-bounded search of the common case."""
     ls = np.asarray(rmi["level_sizes"], np.uint32)
     coef = np.ascontiguousarray(rmi["coef"], np.float64)
     icpt = np.ascontiguousarray(rmi["intercept"], np.float64)
