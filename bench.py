@@ -180,6 +180,8 @@ def parse_args():
     ap.add_argument("--skip-rmi", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the pipelined end-to-end path")
     ap.add_argument("--seed-k", type=int, default=-1, help="K of the sweep kernel's seed table (-1 = auto, 0 = none)")
+    ap.add_argument("--sub-rate", type=float, default=SUB_RATE, help="substitution rate of the synthetic reads (SURVEY 8d extremes: 0)")
+    ap.add_argument("--random-reads", action="store_true", help="uniform random reads instead of reference substrings (SURVEY 8d extreme)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.ref_bases:
@@ -198,16 +200,20 @@ def parse_args():
 def workload_dict(args, world):
     bucket_mb = 2 * (args.ref_bases // 192 + 1) * 64 / 1e6
     return {"workload": f"synthetic {args.ref_bases/1e6:g} Mbp random ACGT reference (PCG64 seed {args.seed}), "
-                        f"{args.reads/1e6:g} M reads x {READ_LEN} bp per GPU, exact substrings + {SUB_RATE:.0%} substitutions ({args.cfg_name})",
-            "ref_bases": args.ref_bases, "reads_per_gpu": args.reads, "read_len": READ_LEN, "sub_rate": SUB_RATE,
+                        f"{args.reads/1e6:g} M reads x {READ_LEN} bp per GPU, "
+                        + ("uniform random reads" if args.random_reads else f"exact substrings + {args.sub_rate:.0%} substitutions") + f" ({args.cfg_name})",
+            "ref_bases": args.ref_bases, "reads_per_gpu": args.reads, "read_len": READ_LEN,
+            "sub_rate": None if args.random_reads else args.sub_rate,
             "lut_K": LUT_K, "rmi_K": RMI_K, "rmi_experts": list(args.experts), "min_len": 1,
             "parallelism": f"reads sharded x{world}, index replicated",
             "l2_policy": f"inputs larger than L2: packed read batch {args.reads * 48 / 1e6:.0f} MB, rank buckets {bucket_mb:.0f} MB, outputs "
                          f"> 1 GB vs 126 MB L2 (at --config c3 the 67 MB of buckets are L2-resident by design; see DESIGN.md)"}
 
 
-def host_reads(ref_codes, n, seed):
-    return make_reads_host(ref_codes, n, READ_LEN, seed=seed)
+def host_reads(ref_codes, n, seed, sub_rate=SUB_RATE, random_reads=False):
+    if random_reads:
+        return np.random.Generator(np.random.PCG64(seed)).integers(0, 4, (n, READ_LEN), dtype=np.uint8)
+    return make_reads_host(ref_codes, n, READ_LEN, seed=seed, sub_rate=sub_rate)
 
 
 def device_reads(ref_dev, n, L, seed, out, sub_rate=SUB_RATE, chunk=2_000_000):
@@ -266,11 +272,16 @@ def main():
     if args.seed_k != 0:
         index.build_seed_table(None if args.seed_k < 0 else args.seed_k)
     n_host = min(HOST_READS, args.reads)
-    reads_head = host_reads(ref, n_host, seed=args.seed + 1 + rank)          # numpy: the CPU arms regenerate exactly these
+    reads_head = host_reads(ref, n_host, args.seed + 1 + rank, args.sub_rate, args.random_reads)   # numpy: the CPU arms regenerate exactly these
     codes_dev = torch.empty((args.reads, READ_LEN), dtype=torch.uint8, device=dev)
     codes_dev[:n_host] = torch.from_numpy(reads_head).to(dev)
     if args.reads > n_host:
-        device_reads(ref_dev, args.reads - n_host, READ_LEN, args.seed + 1 + rank, codes_dev[n_host:])
+        if args.random_reads:
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(args.seed + 1 + rank)
+            codes_dev[n_host:] = torch.randint(0, 4, (args.reads - n_host, READ_LEN), generator=gen, device=dev, dtype=torch.uint8)
+        else:
+            device_reads(ref_dev, args.reads - n_host, READ_LEN, args.seed + 1 + rank, codes_dev[n_host:], sub_rate=args.sub_rate)
     batch = g.ReadBatch.from_device_bases(codes_dev, READ_LEN, read_id_base=rank * args.reads)
     # raw read bytes in pinned host memory: what the end-to-end path starts from (1 byte/base)
     ascii_lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
@@ -280,7 +291,8 @@ def main():
         ascii_host[a:b].copy_(ascii_lut[codes_dev[a:b].long()])
     del codes_dev, ref_dev
     torch.cuda.empty_cache()
-    engine = g.Engine(index, args.reads, READ_LEN, mems_per_read=24, recs_per_read=8)
+    caps = dict(mems_per_read=96, recs_per_read=64) if args.random_reads else dict(mems_per_read=24, recs_per_read=8)
+    engine = g.Engine(index, args.reads, READ_LEN, **caps)
     lut = g.lut_build(index, LUT_K)
     rmi = None
     if not args.skip_rmi:
@@ -371,7 +383,7 @@ def main():
     rec_cnt_dev = engine.rec_cnt[: args.reads]
 
     # ---- end to end through the public API: raw read bytes (pinned host) in, host records out
-    pipe = g.PipelinedEngine(index, args.reads, READ_LEN, n_chunks=args.e2e_chunks, mems_per_read=24, recs_per_read=8)
+    pipe = g.PipelinedEngine(index, args.reads, READ_LEN, n_chunks=args.e2e_chunks, **caps)
 
     def e2e_time(step):
         for _ in range(2):
@@ -487,7 +499,7 @@ def reference_arm(args, workload):
         log(f"reference arm: GPU index build unavailable ({e}); using host SA-IS")
     if sa1 is None:
         sa1, _ = g.HostIndex.build(text, reverse=False).export()
-    reads_codes = host_reads(ref, min(args.reads, HOST_READS), seed=args.seed + 1)
+    reads_codes = host_reads(ref, min(args.reads, HOST_READS), args.seed + 1, args.sub_rate, args.random_reads)
     from oracle.c_oracle import COracle
     o = COracle(text, sa1)
     thr = o.max_threads
