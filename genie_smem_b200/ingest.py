@@ -38,10 +38,15 @@ def _gather(buf, starts, ends, pin):
         out = out_t.numpy()[:total]
     else:
         out = np.empty(total, np.uint8)
-    if total:
-        # index of every output byte in the source: start of its read + position inside it
-        idx = np.repeat(starts - off[:-1], lens) + np.arange(total, dtype=np.int64)
-        np.take(buf, idx, out=out)
+    # index of every output byte in the source = start of its read + position inside it; in blocks of reads so that the
+    # index array stays small next to a multi-GB file
+    block = 1 << 18
+    for a in range(0, len(starts), block):
+        b = min(len(starts), a + block)
+        o0, o1 = int(off[a]), int(off[b])
+        if o1 > o0:
+            idx = np.repeat(starts[a:b] - off[a:b], lens[a:b]) + np.arange(o0, o1, dtype=np.int64)
+            np.take(buf, idx, out=out[o0:o1])
     return out, off
 
 
