@@ -63,6 +63,8 @@ EXPORTS = {
     "gsm_index_build_device_workspace": (C.c_int, [C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "gsm_index_build_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                          C.POINTER(IndexInfo), C.c_void_p]),
+    "gsm_fastq_scan": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]),
+    "gsm_fastq_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]),
     "gsm_pack_reads_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
     "gsm_pack_reads_device_check": (C.c_int, [C.c_void_p, C.c_void_p]),

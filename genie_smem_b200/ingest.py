@@ -71,27 +71,49 @@ def read_fasta(path):
     return names, seqs
 
 
-def read_fastq(path, n_policy="error", pin=True):
+def read_fastq(path, n_policy="error", pin=True, threads=0):
     """4-line FASTQ -> (bases uint8 (pinned when a GPU is present), base_off int64[n+1], dropped read indices).
-    bases/base_off go straight into ReadBatch.from_device_bases(bases_on_device, base_off=base_off, ascii=True); when
-    all reads have one length, bases.reshape(n, L) is what PipelinedEngine.run_ascii takes."""
+    The file is cut into records and its sequence lines are gathered by the library's multi-threaded scanner
+    (gsm_fastq_scan / gsm_fastq_gather).  bases/base_off go straight into
+    ReadBatch.from_device_bases(bases_on_device, base_off=base_off, ascii=True); when all reads have one length,
+    bases.reshape(n, L) is what PipelinedEngine.run_ascii takes."""
+    import ctypes as C
+    from . import _capi as capi
     if n_policy not in ("error", "drop"):
         raise ValueError("n_policy must be 'error' or 'drop'")
     buf = np.fromfile(path, dtype=np.uint8)
-    starts, ends = _lines(buf)
-    if len(starts) % 4:
-        raise ValueError(f"{path}: {len(starts)} lines is not a multiple of 4 (truncated FASTQ?)")
-    if len(starts) and not (np.all(buf[starts[0::4]] == ord("@")) and np.all(buf[starts[2::4]] == ord("+"))):
-        raise ValueError(f"{path}: not a 4-line FASTQ (records must start with '@' and have a '+' line)")
-    s, e = starts[1::4], ends[1::4]
+    n_rec = C.c_uint64()
+    capi.check(capi.lib.gsm_fastq_scan(buf.ctypes.data, len(buf), C.byref(n_rec), None, None, 0, threads))
+    n = int(n_rec.value)
+    seq_off = np.zeros(max(n, 1), np.uint64)
+    seq_len = np.zeros(max(n, 1), np.uint32)
+    capi.check(capi.lib.gsm_fastq_scan(buf.ctypes.data, len(buf), C.byref(n_rec), seq_off.ctypes.data, seq_len.ctypes.data, max(n, 1), threads))
+
+    def gather(so, sl):
+        k = len(so)
+        off = np.zeros(k + 1, np.uint64)
+        total = int(sl.astype(np.int64).sum())
+        if pin:
+            import torch
+            out = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available()).numpy()
+        else:
+            out = np.empty(max(total, 1), np.uint8)
+        capi.check(capi.lib.gsm_fastq_gather(buf.ctypes.data, so.ctypes.data, sl.ctypes.data, k, out.ctypes.data, off.ctypes.data, threads))
+        return out[:total], off.astype(np.int64)
+
+    seq_off, seq_len = seq_off[:n], seq_len[:n]
+    bases, off = gather(seq_off, seq_len)
     dropped = np.zeros(0, np.int64)
-    if n_policy == "drop" and len(s):
-        bad_byte = ~_VALID[buf]
-        csum = np.concatenate(([0], np.cumsum(bad_byte)))
-        bad_read = (csum[e] - csum[s]) > 0
-        dropped = np.flatnonzero(bad_read)
-        s, e = s[~bad_read], e[~bad_read]
-    bases, off = _gather(buf, s, e, pin)
+    if n_policy == "drop" and n:
+        bad_byte = ~_VALID[bases]
+        if bad_byte.any():
+            nz = seq_len > 0
+            per_read = np.zeros(n, np.int64)
+            per_read[nz] = np.add.reduceat(bad_byte.astype(np.int64), off[:-1][nz])
+            bad_read = per_read > 0
+            dropped = np.flatnonzero(bad_read)
+            keep = ~bad_read
+            bases, off = gather(np.ascontiguousarray(seq_off[keep]), np.ascontiguousarray(seq_len[keep]))
     return bases, off, dropped
 
 

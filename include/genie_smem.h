@@ -123,6 +123,18 @@ int gsm_index_build_device(const uint32_t* text2bit, uint64_t n_bases, uint32_t 
                            void* rev_buckets, void* workspace, uint64_t workspace_bytes, gsm_index_info* info,
                            void* stream);
 
+/* ------------------------------------------------------------------ host-side read ingest */
+/* Multi-threaded scan of a 4-line FASTQ held in memory (threads == 0: all cores).  gsm_fastq_scan: *n_records = lines / 4;
+ * with seq_off / seq_len non-NULL (cap entries) also the offset and length of every sequence line ('\r' stripped).
+ * GSM_E_INVALID for a truncated file or records that do not start with '@' / carry no '+' line.  gsm_fastq_gather copies
+ * the sequence lines into one contiguous buffer (out may be NULL to get base_off only): base_off[i] = start of read i,
+ * n_records + 1 entries -- exactly the (bases, base_off) pair gsm_pack_reads_device takes.  Replaces the one-string-per-
+ * file query path (ExactMatch.load_query, ExactMatch.py:104-108). */
+int gsm_fastq_scan(const char* buf, uint64_t n_bytes, uint64_t* n_records, uint64_t* seq_off, uint32_t* seq_len, uint64_t cap,
+                   uint32_t threads);
+int gsm_fastq_gather(const char* buf, const uint64_t* seq_off, const uint32_t* seq_len, uint64_t n_records, char* out,
+                     uint64_t* base_off, uint32_t threads);
+
 /* ------------------------------------------------------------------ device-side read ingest */
 /* Pack reads ON THE GPU: bases (device; ASCII ACGT if ascii != 0, else codes 0..3), read r = bytes
  * [base_off[r], base_off[r+1]) (device uint64, n_reads+1) or, with base_off == NULL, fixed_len bytes at

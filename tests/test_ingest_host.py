@@ -42,3 +42,25 @@ def test_fasta_reader_matches_reference_parser(tmp_path):
     m.write_text(">a\nAC\nGT\n\n>b\nTTT\n")
     names, seqs = ingest.read_fasta(str(m))
     assert names == ["a", "b"] and [bytes(s).decode() for s in seqs] == ["ACGT", "TTT"]
+
+
+def test_fastq_scanner_slice_boundaries(tmp_path):
+    """The native scanner cuts the buffer into per-thread slices: every slice count must give the same records, whatever
+    falls on a boundary (header, sequence, '+', quality, CRLF, a line longer than a slice)."""
+    rng = np.random.default_rng(7)
+    reads = ["".join("ACGT"[c] for c in rng.integers(0, 4, int(L))) for L in rng.integers(0, 90, 300)]
+    reads[17] = "ACGT" * 200                               # longer than a 64-byte slice many times over
+    p = tmp_path / "r.fq"
+    ingest.write_fastq(str(p), reads, names=["read%d/%s" % (i, "x" * (i % 23)) for i in range(len(reads))])
+    crlf = tmp_path / "c.fq"
+    crlf.write_bytes(p.read_bytes().replace(b"\n", b"\r\n")[:-2])      # CRLF, no trailing newline
+    for path in (p, crlf):
+        ref = None
+        for threads in (1, 2, 3, 5, 8, 13, 64, 1000):
+            bases, off, _ = ingest.read_fastq(str(path), pin=False, threads=threads)
+            got = [bytes(bases[off[i]:off[i + 1]]).decode() for i in range(len(off) - 1)]
+            assert got == reads, (str(path), threads)
+    bad = tmp_path / "b.fq"
+    bad.write_text("@a\nACGT\n+\nIIII\nXb\nAC\n+\nII\n")
+    with pytest.raises(ValueError):
+        ingest.read_fastq(str(bad), pin=False, threads=2)
