@@ -374,23 +374,39 @@ int gsm_pack_reads(const char* bases, const uint32_t* lens, uint64_t n_reads, ui
     chunk_off[n_reads] = (uint32_t)off;
     if (!packed) return GSM_OK;
     uint32_t* w = (uint32_t*)packed;
-    memset(w, 0, off * 16);
-    uint64_t pos = 0;
-    for (uint64_t i = 0; i < n_reads; ++i) {
-        uint32_t* dst = w + (uint64_t)chunk_off[i] * 4;
-        for (uint32_t t = 0; t < lens[i]; ++t) {
-            uint32_t c;
-            switch (bases[pos + t]) {
-                case 'A': c = 0; break;
-                case 'C': c = 1; break;
-                case 'G': c = 2; break;
-                case 'T': c = 3; break;
-                default: return fail(GSM_E_INVALID, "non-ACGT base in read " + std::to_string(i));
+    // offsets of every read in `bases`, then the reads are packed by all cores (each read touches only its own chunks)
+    std::vector<uint64_t> pos(n_reads + 1, 0);
+    for (uint64_t i = 0; i < n_reads; ++i) pos[i + 1] = pos[i] + lens[i];
+    unsigned T = std::max(1u, std::thread::hardware_concurrency());
+    if (pos[n_reads] < (1u << 20)) T = 1;
+    T = (unsigned)std::min<uint64_t>(T, n_reads ? n_reads : 1);
+    std::vector<uint64_t> bad(T, UINT64_MAX);
+    auto work = [&](unsigned t) {
+        const uint64_t a = n_reads * t / T, b = n_reads * (t + 1) / T;
+        for (uint64_t i = a; i < b; ++i) {
+            uint32_t* dst = w + (uint64_t)chunk_off[i] * 4;
+            memset(dst, 0, (size_t)(chunk_off[i + 1] - chunk_off[i]) * 16);
+            const char* src = bases + pos[i];
+            for (uint32_t k = 0; k < lens[i]; ++k) {
+                uint32_t c;
+                switch (src[k]) {
+                    case 'A': c = 0; break;
+                    case 'C': c = 1; break;
+                    case 'G': c = 2; break;
+                    case 'T': c = 3; break;
+                    default: if (bad[t] == UINT64_MAX) bad[t] = i; c = 0; break;
+                }
+                dst[k >> 4] |= c << (30 - 2 * (k & 15));
             }
-            dst[t >> 4] |= c << (30 - 2 * (t & 15));
         }
-        pos += lens[i];
-    }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < T; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    uint64_t first_bad = UINT64_MAX;
+    for (unsigned t = 0; t < T; ++t) first_bad = std::min(first_bad, bad[t]);
+    if (first_bad != UINT64_MAX) return fail(GSM_E_INVALID, "non-ACGT base in read " + std::to_string(first_bad));
     return GSM_OK;
 }
 

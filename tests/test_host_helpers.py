@@ -56,3 +56,32 @@ def test_shard_range_partitions_reads():
             spans = [shard_range(n, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_host_read_packer_multithreaded_equals_bitwise_definition():
+    """gsm_pack_reads (all cores above 1 MB of bases): MSB-first 2-bit words, 16-byte aligned reads, zeroed padding; the first
+    read with a character outside ACGT is reported."""
+    import ctypes as C
+    from genie_smem_b200 import _capi as capi
+    rng = np.random.default_rng(2)
+    lens = rng.integers(0, 400, 9000).astype(np.uint32)
+    lens[:5] = [0, 1, 64, 65, 63]
+    codes = [rng.integers(0, 4, int(L), dtype=np.uint8) for L in lens]
+    joined = b"".join(np.frombuffer(b"ACGT", np.uint8)[c].tobytes() for c in codes)
+    assert len(joined) > 1 << 20                                   # the multi-threaded path
+    off = np.zeros(len(lens) + 1, np.uint32)
+    capi.check(capi.lib.gsm_pack_reads(joined, lens.ctypes.data, len(lens), off.ctypes.data, None))
+    assert np.array_equal(np.diff(off.astype(np.int64)), (lens.astype(np.int64) + 63) // 64)
+    packed = np.full(int(off[-1]) * 4 + 4, 0xFFFFFFFF, np.uint32)  # dirty buffer: padding must be zeroed by the packer
+    capi.check(capi.lib.gsm_pack_reads(joined, lens.ctypes.data, len(lens), off.ctypes.data, packed.ctypes.data))
+    for i in (0, 1, 2, 3, 4, 17, 4000, 8999):
+        words = packed[int(off[i]) * 4:int(off[i + 1]) * 4]
+        exp = np.zeros(len(words), np.uint32)
+        for k, c in enumerate(codes[i]):
+            exp[k >> 4] |= np.uint32(int(c) << (30 - 2 * (k & 15)))
+        assert np.array_equal(words, exp), i
+    bad = bytearray(joined)
+    start = int(lens[:7000].sum())
+    bad[start + 3] = ord("N")
+    with pytest.raises(ValueError, match="read 7000"):
+        capi.check(capi.lib.gsm_pack_reads(bytes(bad), lens.ctypes.data, len(lens), off.ctypes.data, packed.ctypes.data))
