@@ -1,19 +1,27 @@
 #!/usr/bin/env python3
 """bench.py -- SMEM reads/s on B200 (BASELINE.json metric) for the B200-native engine.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c4|c3] [--reads R] [--ref-bases B] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c4|c3|c5] [--scaling strong|weak] [--impl reference] ...
 
-Workload at N=1 = BASELINE.json configs[3], the configuration the metric ("reads/s at 1/2/4/8 B200 + achieved HBM GB/s")
-is quoted on: synthetic 1 Gbp random ACGT reference (numpy PCG64(1000)), 50 M reads of 151 bp (exact substrings with
-i.i.d. 1 % substitutions), all three SMEM methods.  The index (suffix array, both BWT bucket arrays) is built
-ON THE GPU in well under a second (gsm_index_build_device), so the 1 Gbp configuration fits the default run; `--config c3`
-selects configs[2] (100 Mbp, 10 M reads; rank buckets L2-resident).  Under torchrun (N>1) every rank holds a replica of the
-index and its own read shard (weak scaling); the only collective is the final gather of per-rank records (NCCL).
+Workload = BASELINE.json configs[3] (`--config c4`, the configuration the metric is quoted on): synthetic 1 Gbp random ACGT
+reference (numpy PCG64(1000)), 50 M reads of 151 bp (exact substrings with i.i.d. 1 % substitutions), all three
+SMEM methods.  `--config c3` = configs[2] (100 Mbp, 10 M reads), `--config c5` = configs[4] (3 Gbp, 100 M reads, RMI- vs
+BWA-SMEM).  The index (suffix array, both BWT bucket arrays, seed table, LUT) is built ON THE GPU in about a second.
 
-A "step" is one pass of the hot path over one read batch.  `value` = BWA-SMEM reads/s with the packed reads already
-resident in HBM (kernels only: sweep + select + scan + gather); `e2e` = the same through the public API starting from RAW
-read bytes in pinned host memory (1 byte/base H2D, 2-bit packing on the GPU, records + offsets D2H, all inside the timed
-region).  LUT- and RMI-SMEM throughputs are reported under "methods".
+Multi-GPU (torchrun, one rank per GPU): the index is replicated, the config's reads are sharded by rank -- STRONG scaling, as
+configs[3] states ("50M reads sharded across 1/2/4/8"); `--scaling weak` gives every GPU the config's full read count instead.
+The one collective of the path -- per-rank records to rank 0 -- is INSIDE every timed region at N > 1: each rank's ordered
+write kernel stores its records straight into rank 0's HBM through a peer mapping (NVLink / NVSwitch), the per-rank counts
+travel through an 8-byte NCCL all-gather, and a closing all-gather is the completion fence (sharding.RecordGatherer).
+
+A "step" is one pass of the hot path over the read batch.
+  value   BWA-SMEM reads/s, packed reads already resident in HBM: sweep + select + scan + ordered write (+ the gather at N > 1)
+  e2e     the same through the public API from HOST buffers: 2-bit packed reads in pinned host memory -> H2D -> kernels ->
+          records to pinned host memory (N = 1) / gathered into rank 0's HBM with offsets + status D2H per rank (N > 1);
+          e2e.ascii_input = from raw ASCII read bytes (packed on the GPU), e2e.from_fastq = from FASTQ file bytes
+  methods LUT- and RMI-SMEM throughputs; roofline / roofline_methods: algorithmic bytes over time vs the HBM peak
+  parity  GPU records of the first reads of THIS batch against oracle/smem_oracle.c (the reference restated), all methods;
+          any mismatch fails the run
 """
 import argparse
 import json
@@ -128,12 +136,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------ CPU arm
-def cpu_arm(text_bytes, sa_1based, reads_codes, method, threads, budget_s, K=0, rmi=None):
-    """Time the oracle port (oracle/smem_oracle.c, the reference algorithm restated in C) on the host
-    cores over a bounded sample of the same reads.  Returns (reads/s, n_sample, threads)."""
-    from oracle.c_oracle import COracle
-    o = COracle(text_bytes, sa_1based)
+# ------------------------------------------------------------------------------------------ CPU arm (oracle = checker / baseline only)
+def cpu_arm(o, reads_codes, method, threads, budget_s, K=0, rmi=None, n_min=0):
+    """Run the oracle port (oracle/smem_oracle.c, the reference algorithm restated in C) on the host cores over a bounded
+    sample of the same reads.  Returns (reads/s, n_sample, threads, out, counts): the outputs are what `parity` compares
+    the GPU records with."""
     threads = threads or o.max_threads
     L = reads_codes.shape[1]
 
@@ -142,29 +149,52 @@ def cpu_arm(text_bytes, sa_1based, reads_codes, method, threads, budget_s, K=0, 
         joined = _B[sub.reshape(-1)].tobytes()
         lens = np.full(n, L, np.uint32)
         t0 = time.perf_counter()
-        o.smems(method, None, min_len=1, K=K, rmi=rmi, threads=threads, joined=joined, lens=lens)
-        return time.perf_counter() - t0
+        out, counts = o.smems(method, None, min_len=1, K=K, rmi=rmi, threads=threads, joined=joined, lens=lens)
+        return time.perf_counter() - t0, out, counts
 
-    n = min(64 * threads, len(reads_codes))
+    n = min(max(64 * threads, n_min), len(reads_codes))
     if method == 1:
         o.lib.orc_build_lut(o.h, K)          # table build is index construction, not search
-    dt = run(n)
+    dt, out, counts = run(n)
     rate = n / dt
     n2 = int(max(n, min(len(reads_codes), rate * budget_s)))
     if n2 > 2 * n:
-        dt = run(n2)
+        dt, out, counts = run(n2)
         n = n2
-    return n / dt, n, threads
+    return n / dt, n, threads, out, counts
 
 
 def rmi_dict(params):
     return {"K": params.K, "level_sizes": [int(x) for x in params.level_sizes], "coef": params.coef_host, "intercept": params.intercept_host}
 
 
-# ------------------------------------------------------------------------------------------ main
+def compare_with_oracle(reads_codes, snap, out, counts, n):
+    """GPU records of the first n reads (snap = (records, offsets, status) host arrays) against the oracle's output for the
+    same reads, after the reference's dict semantics (duplicate SMEM strings collapse: first insertion keeps its place,
+    last value wins).  Returns (#mismatching reads, #reads where the reference raises)."""
+    recs, offs, status = snap
+    mism = raises = 0
+    for r in range(n):
+        q = reads_codes[r]
+        if counts[r] == -1:                       # the reference raises on this read: the kernel must flag it
+            raises += 1
+            mism += int(status[r] != 1)
+            continue
+        d = {}
+        for rec in recs[offs[r]:offs[r + 1]]:
+            d[q[int(rec["qstart"]):int(rec["qend"])].tobytes()] = (int(rec["sa_lo"]), int(rec["sa_hi"]))
+        got = [(k, v[0], v[1]) for k, v in d.items()]
+        exp = [(q[int(o[0]):int(o[1])].tobytes(), int(o[2]), int(o[3])) for o in out[r, :max(int(counts[r]), 0)]]
+        mism += int(got != exp or status[r] != 0)
+    return mism, raises
+
+
+# ------------------------------------------------------------------------------------------ configuration
 CONFIGS = {"c4": dict(ref_bases=1_000_000_000, reads=50_000_000, seed=1000, experts=(2048, 1048576), name="BASELINE.json configs[3]"),
-           "c3": dict(ref_bases=100_000_000, reads=10_000_000, seed=100, experts=(512, 131072), name="BASELINE.json configs[2]")}
+           "c3": dict(ref_bases=100_000_000, reads=10_000_000, seed=100, experts=(512, 131072), name="BASELINE.json configs[2]"),
+           "c5": dict(ref_bases=3_000_000_000, reads=100_000_000, seed=3000, experts=(4096, 4194304), name="BASELINE.json configs[4]")}
 HOST_READS = 600_000      # the first reads of every batch come from numpy so the CPU arms can regenerate exactly them
+PARITY_READS = 20_000     # reads per method compared with the oracle at N = 1 (2,048 at N > 1)
 
 
 def parse_args():
@@ -174,10 +204,12 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
-    ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (default: the config's)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="N > 1: shard the config's reads (strong) or give every GPU all of them (weak)")
+    ap.add_argument("--reads", type=int, default=0, help="total reads per step (default: the config's)")
     ap.add_argument("--ref-bases", type=int, default=0, help="reference size (default: the config's)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline budget per method")
     ap.add_argument("--skip-rmi", action="store_true")
+    ap.add_argument("--skip-extras", action="store_true", help="skip the ascii / fastq / locate / probe-search legs")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="chunks of the pipelined end-to-end path")
     ap.add_argument("--seed-k", type=int, default=-1, help="K of the sweep kernel's seed table (-1 = auto, 0 = none)")
     ap.add_argument("--sub-rate", type=float, default=SUB_RATE, help="substitution rate of the synthetic reads (SURVEY 8d extremes: 0)")
@@ -187,26 +219,30 @@ def parse_args():
     if args.ref_bases:
         cfg["ref_bases"] = args.ref_bases
         cfg["name"] = "custom size"
-        if args.ref_bases < 500_000_000:
-            cfg["experts"] = CONFIGS["c3"]["experts"]
+        # leaves scale with the reference: about one leaf per 1,000 rows
+        leaves = 1 << max(10, int(np.log2(max(args.ref_bases // 1000, 1024))))
+        cfg["experts"] = (max(16, leaves >> 9), leaves)
     if args.reads:
         cfg["reads"] = args.reads
         if cfg["name"] != "custom size":
             cfg["name"] += f" shape, {args.reads/1e6:g} M reads"
-    args.ref_bases, args.reads, args.seed, args.experts, args.cfg_name = cfg["ref_bases"], cfg["reads"], cfg["seed"], cfg["experts"], cfg["name"]
+    args.ref_bases, args.total_reads, args.seed, args.experts, args.cfg_name = cfg["ref_bases"], cfg["reads"], cfg["seed"], cfg["experts"], cfg["name"]
     return args
 
 
-def workload_dict(args, world):
+def workload_dict(args, world, reads_rank):
     bucket_mb = 2 * (args.ref_bases // 192 + 1) * 64 / 1e6
+    total = args.total_reads if args.scaling == "strong" else args.total_reads * world
     return {"workload": f"synthetic {args.ref_bases/1e6:g} Mbp random ACGT reference (PCG64 seed {args.seed}), "
-                        f"{args.reads/1e6:g} M reads x {READ_LEN} bp per GPU, "
+                        f"{total/1e6:g} M reads x {READ_LEN} bp per step"
+                        + (f" sharded over {world} GPUs ({reads_rank/1e6:g} M each)" if world > 1 else "") + ", "
                         + ("uniform random reads" if args.random_reads else f"exact substrings + {args.sub_rate:.0%} substitutions") + f" ({args.cfg_name})",
-            "ref_bases": args.ref_bases, "reads_per_gpu": args.reads, "read_len": READ_LEN,
+            "ref_bases": args.ref_bases, "reads_per_step": total, "reads_per_gpu": reads_rank, "read_len": READ_LEN,
             "sub_rate": None if args.random_reads else args.sub_rate,
             "lut_K": LUT_K, "rmi_K": RMI_K, "rmi_experts": list(args.experts), "min_len": 1,
-            "parallelism": f"reads sharded x{world}, index replicated",
-            "l2_policy": f"inputs larger than L2: packed read batch {args.reads * 48 / 1e6:.0f} MB, rank buckets {bucket_mb:.0f} MB, outputs "
+            "parallelism": f"reads sharded x{world}, index replicated; records gathered to rank 0 inside the timed region" if world > 1
+                           else "one GPU",
+            "l2_policy": f"inputs larger than L2: packed read batch {reads_rank * 48 / 1e6:.0f} MB, rank buckets {bucket_mb:.0f} MB, seed table + outputs "
                          f"> 1 GB vs 126 MB L2 (at --config c3 the 67 MB of buckets are L2-resident by design; see DESIGN.md)"}
 
 
@@ -233,33 +269,57 @@ def device_reads(ref_dev, n, L, seed, out, sub_rate=SUB_RATE, chunk=2_000_000):
     return out
 
 
+def algorithmic_bytes(recs_i32, n_rec, n_reads, K=0, probe_bytes=0):
+    """bytes(read) = 128 * sum_records(len + [start > 0]) + ceil(L/4) + 16 * #records; for LUT / RMI every record
+    with len >= K trades K of its steps for `probe_bytes` (LUT: one 32-byte sector; RMI: P probes x 64 B)."""
+    import torch
+    steps = n_long = 0
+    for a in range(0, n_rec, 50_000_000):
+        w = recs_i32[a:a + 50_000_000, 1]
+        qs = (w & 0xFFFF).to(torch.int64)
+        qe = ((w >> 16) & 0xFFFF).to(torch.int64)
+        steps += int(((qe - qs) + (qs > 0).to(torch.int64)).sum().item())
+        if K:
+            n_long += int(((qe - qs) >= K).sum().item())
+    total = 128 * (steps - K * n_long) + probe_bytes * n_long + n_reads * ((READ_LEN + 3) // 4) + 16 * n_rec
+    return total, steps, n_long
+
+
 def main():
     args = parse_args()
     _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    workload = workload_dict(args, world)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        reference_arm(args, workload)
+        reference_arm(args, workload_dict(args, world, args.total_reads // world if args.scaling == "strong" else args.total_reads))
         return
 
     import torch
     import torch.distributed as dist
     import genie_smem_b200 as g
+    from genie_smem_b200 import sharding
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        from genie_smem_b200 import sharding
         cpus = sharding.bind_to_gpu_numa(local_rank)                # pinned host buffers land on the GPU's NUMA node
         log(f"[rank {rank}] bound to {len(cpus) if cpus else 'no'} CPUs next to GPU {local_rank}")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
+    if args.scaling == "strong":
+        lo_r, hi_r = sharding.shard_range(args.total_reads, rank, world)
+        n_reads = hi_r - lo_r
+        n_max = max(sharding.shard_range(args.total_reads, r, world)[1] - sharding.shard_range(args.total_reads, r, world)[0] for r in range(world))
+        job_reads = args.total_reads
+    else:
+        lo_r, n_reads, n_max = rank * args.total_reads, args.total_reads, args.total_reads
+        job_reads = args.total_reads * world
+    workload = workload_dict(args, world, n_reads)
 
     # ---- setup: reference, index (built on the GPU), reads, LUT, RMI
     t_setup = time.time()
@@ -271,41 +331,55 @@ def main():
         f"(workspace {index.build_stats['workspace_bytes']/1e9:.1f} GB, {index.build_stats['doubling_rounds']} doubling rounds)")
     if args.seed_k != 0:
         index.build_seed_table(None if args.seed_k < 0 else args.seed_k)
-    n_host = min(HOST_READS, args.reads)
+    n_host = min(HOST_READS, n_reads)
     reads_head = host_reads(ref, n_host, args.seed + 1 + rank, args.sub_rate, args.random_reads)   # numpy: the CPU arms regenerate exactly these
-    codes_dev = torch.empty((args.reads, READ_LEN), dtype=torch.uint8, device=dev)
+    codes_dev = torch.empty((n_reads, READ_LEN), dtype=torch.uint8, device=dev)
     codes_dev[:n_host] = torch.from_numpy(reads_head).to(dev)
-    if args.reads > n_host:
+    if n_reads > n_host:
         if args.random_reads:
             gen = torch.Generator(device=dev)
             gen.manual_seed(args.seed + 1 + rank)
-            codes_dev[n_host:] = torch.randint(0, 4, (args.reads - n_host, READ_LEN), generator=gen, device=dev, dtype=torch.uint8)
+            codes_dev[n_host:] = torch.randint(0, 4, (n_reads - n_host, READ_LEN), generator=gen, device=dev, dtype=torch.uint8)
         else:
-            device_reads(ref_dev, args.reads - n_host, READ_LEN, args.seed + 1 + rank, codes_dev[n_host:], sub_rate=args.sub_rate)
-    batch = g.ReadBatch.from_device_bases(codes_dev, READ_LEN, read_id_base=rank * args.reads)
-    # raw read bytes in pinned host memory: what the end-to-end path starts from (1 byte/base)
-    ascii_lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
-    ascii_host = torch.empty((args.reads, READ_LEN), dtype=torch.uint8, pin_memory=True)
-    for a in range(0, args.reads, 5_000_000):
-        b = min(args.reads, a + 5_000_000)
-        ascii_host[a:b].copy_(ascii_lut[codes_dev[a:b].long()])
+            device_reads(ref_dev, n_reads - n_host, READ_LEN, args.seed + 1 + rank, codes_dev[n_host:], sub_rate=args.sub_rate)
+    batch = g.ReadBatch.from_device_bases(codes_dev, READ_LEN, read_id_base=lo_r)
+    extras = not args.skip_extras
+    ascii_host = None
+    if extras:                      # raw read bytes in pinned host memory (1 byte/base): the ASCII leg of the end-to-end path
+        ascii_lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+        ascii_host = torch.empty((n_reads, READ_LEN), dtype=torch.uint8, pin_memory=True)
+        for a in range(0, n_reads, 5_000_000):
+            b = min(n_reads, a + 5_000_000)
+            ascii_host[a:b].copy_(ascii_lut[codes_dev[a:b].long()])
     del codes_dev, ref_dev
     torch.cuda.empty_cache()
     caps = dict(mems_per_read=96, recs_per_read=64) if args.random_reads else dict(mems_per_read=24, recs_per_read=8)
-    engine = g.Engine(index, args.reads, READ_LEN, **caps)
+    engine = g.Engine(index, n_reads, READ_LEN, **caps)
     lut = g.lut_build(index, LUT_K)
     rmi = None
     if not args.skip_rmi:
         t0 = time.time()
-        rmi = train_rmi(index, RMI_K, args.experts, dev)
-        log(f"[rank {rank}] RMI probe table + training in {time.time()-t0:.1f}s")
+        rmi = train_rmi(index, RMI_K, args.experts, dev, probe_table=False)
+        log(f"[rank {rank}] RMI training in {time.time()-t0:.1f}s (max |prediction error| on the training sample: {rmi.max_err:.0f} rows)")
     torch.cuda.synchronize()
     log(f"[rank {rank}] setup {time.time()-t_setup:.1f}s, index {index.bytes()/1e6:.0f} MB on device")
+
+    gat = None
+    if world > 1:                   # the gather destination: one buffer in rank 0's HBM, mapped by every rank
+        gat = sharding.RecordGatherer(capacity=int(caps["recs_per_read"] * n_max * world * 0.75) + 4096, dst=0, device=dev)
+        log(f"[rank {rank}] gather destination mapped ({gat.capacity * 16 / 1e9:.1f} GB on rank 0, NCCL {gat.comm.nccl_version})")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -317,164 +391,373 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    def step(method, **kw):
+        """one device-resident step: sweep + select + ordered write; at N > 1 the write IS the gather to rank 0"""
+        if gat is None:
+            engine.launch(method, batch, **kw)
+            return
+        gat.reset()
+        engine.launch(method, batch, gatherer=gat, **kw)
+        gat.fence()
+
+    def snapshot(n):
+        """host copies of the records / offsets / status of the first n reads of the batch just run (for `parity`)"""
+        offs = engine.rec_off[: n + 1].cpu().numpy()
+        if gat is not None:         # records went to rank 0's buffer: write them locally too for the check
+            engine.collect_local(batch)
+        recs = engine.records[: int(offs[n]) * 16].cpu().numpy().view(g.RECORD_DTYPE)
+        return recs, offs, engine.read_status[:n].cpu().numpy()
+
+    n_par = min(PARITY_READS if world == 1 else 2048, n_host)
+    snaps = {}
 
     # ---- headline: BWA-SMEM, device-resident inputs
     sampler = ClockSampler(local_rank)
     sampler.start()
     t_region0 = time.time()
     launches0 = engine.kernel_launches
-    ms_bwa = timed(lambda: engine.launch(g.METHOD_BWA, batch, min_len=1), args.steps, args.warmup)
+    ms_bwa = timed(lambda: step(g.METHOD_BWA, min_len=1), args.steps, args.warmup)
     gpu_launches = (engine.kernel_launches - launches0) * args.steps // (args.steps + args.warmup)
     t_region1 = time.time()
     clocks = sampler.stop(t_region0, t_region1)
     n_mems, n_rec = engine.check_overflow()
+    gathered = None
+    if gat is not None:
+        g_recs, seg = gat.finish()
+        tot = torch.tensor([n_rec], device=dev, dtype=torch.int64)
+        dist.all_reduce(tot)
+        if rank == 0:
+            assert int(seg.sum()) == int(tot.item()) == g_recs.numel() // 16, "gathered record count != sum of the ranks' counts"
+            ids = g_recs.view(torch.int32).view(-1, 4)[:, 0]
+            a = 0
+            for r in range(world):              # every rank's segment holds that rank's global read ids, in order
+                k = int(seg[0, r])
+                if k:
+                    lo_s, hi_s = (sharding.shard_range(args.total_reads, r, world) if args.scaling == "strong"
+                                  else (r * args.total_reads, (r + 1) * args.total_reads))
+                    s = ids[a:a + k]
+                    assert int(s[0]) == lo_s and int(s[-1]) == hi_s - 1 and bool((s[1:] >= s[:-1]).all()), f"segment of rank {r} is not its shard"
+                a += k
+            gathered = {"records": int(tot.item()), "bytes": int(tot.item()) * 16, "per_rank": [int(x) for x in seg[0]]}
+    snaps["bwa"] = snapshot(n_par)
 
     # ---- per-kernel split of the step + algorithmic bytes (roofline of the dominant kernel, k_sweep)
     ms_sweep = timed(lambda: engine.sweep(batch), args.steps, 1)
     engine.sweep(batch)
     ms_sel_bwa = timed(lambda: engine.select(g.METHOD_BWA, batch, min_len=1), args.steps, 1)
     recs = engine.records[: n_rec * 16].view(torch.int32).view(-1, 4)
-    steps_alg = 0
-    for a in range(0, n_rec, 50_000_000):
-        w = recs[a:a + 50_000_000, 1]
-        qs = (w & 0xFFFF).to(torch.int64)
-        qe = ((w >> 16) & 0xFFFF).to(torch.int64)
-        steps_alg += int(((qe - qs) + (qs > 0).to(torch.int64)).sum().item())
-    alg_bytes = 128 * steps_alg + args.reads * ((READ_LEN + 3) // 4) + 16 * n_rec
+    alg_bytes, steps_alg, _ = algorithmic_bytes(recs, n_rec, n_reads)
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (ms_sweep * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tname = {1_000_000_000: "r01c_1gbp_sweep_dram_bytes.json", 100_000_000: "r01_sweep_dram_bytes.json"}.get(args.ref_bases)
+    tname = {1_000_000_000: "r02_1gbp_sweep_dram_bytes.json", 100_000_000: "r01_sweep_dram_bytes.json"}.get(args.ref_bases)
+    if tname and not os.path.exists(os.path.join(ROOT, "profiles", tname)):
+        tname = tname.replace("r02_", "r01c_")
     if tname and os.path.exists(os.path.join(ROOT, "profiles", tname)):        # ncu --set full capture of k_sweep on this reference size
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
-            traffic = tj["dram_bytes_per_read"] * args.reads
+            traffic = tj["dram_bytes_per_read"] * n_reads
             traffic_src = f"profiles/{tname}: {tj['dram_bytes_per_read']:.0f} DRAM bytes/read (ncu dram__bytes_read+write of k_sweep) x reads per launch"
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_sweep", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_read": round(alg_bytes / args.reads, 1), "fm_steps_per_read_min": round(steps_alg / args.reads, 2),
-                "records_per_read": round(n_rec / args.reads, 3), "ms_sweep": round(ms_sweep, 3), "ms_select_scan_gather": round(ms_sel_bwa, 3),
-                "note": "achieved = algorithmic bytes (SURVEY 8d: 128 B per necessary FM step + read + records) / k_sweep time; the access "
-                        "pattern is dependent random 64-byte fetches, whose measured ceiling on this GPU is 45.9 G fetches/s = 2.9 TB/s over a "
-                        "667 MB index (tools/l2gran_probe.py, profiles/r01_notes.md), not the streaming peak"}
+                "algorithmic_bytes_per_read": round(alg_bytes / n_reads, 1), "fm_steps_per_read_min": round(steps_alg / n_reads, 2),
+                "records_per_read": round(n_rec / n_reads, 3), "ms_sweep": round(ms_sweep, 3), "ms_select_scan_write": round(ms_sel_bwa, 3),
+                "reads_per_launch": n_reads,
+                "note": "achieved = algorithmic bytes (SURVEY 8d: 128 B per necessary FM step + read + records) of one launch / k_sweep's "
+                        "average launch time (CUDA events on the launching stream); the access pattern is dependent random 64-byte "
+                        "fetches, whose measured ceiling on this GPU is below the streaming peak (profiles/r02_notes.md)"}
+    methods = {"bwa": {"reads_per_s": job_reads / (ms_bwa * 1e-3), "ms_per_step": ms_bwa}}
+    roofline_methods = {"bwa": {"achieved": round(alg_bytes / (ms_bwa * 1e-3) / 1e9, 2), "frac": round(alg_bytes / (ms_bwa * 1e-3) / 1e9 / peak, 4),
+                                "algorithmic_bytes_per_read": round(alg_bytes / n_reads, 1), "ms_sweep": round(ms_sweep, 3),
+                                "ms_select": round(ms_sel_bwa, 3), "dominant_kernel": "k_sweep"}}
 
-    # ---- the other two methods (device-resident)
-    methods = {"bwa": {"reads_per_s": world * args.reads / (ms_bwa * 1e-3), "ms_per_step": ms_bwa}}
-    ms_lut = timed(lambda: engine.launch(g.METHOD_LUT, batch, K=LUT_K, lut=lut), max(2, args.steps // 2), 1)
-    methods["lut"] = {"reads_per_s": world * args.reads / (ms_lut * 1e-3), "ms_per_step": ms_lut, "K": LUT_K}
-    engine.check_overflow()
+    # ---- the other two methods (device-resident; same step definition)
+    def method_leg(name, method, steps, kw, K, probe_bytes, extra):
+        ms = timed(lambda: step(method, **kw), steps, 1)
+        _, nr = engine.check_overflow()
+        if gat is not None:
+            gat.finish()
+        snaps[name] = snapshot(n_par)
+        engine.sweep(batch)
+        ms_sel = timed(lambda: engine.select(method, batch, **kw), max(2, steps), 1)
+        rr = engine.records[: nr * 16].view(torch.int32).view(-1, 4)
+        ab, st_, nl = algorithmic_bytes(rr, nr, n_reads, K=K, probe_bytes=probe_bytes)
+        methods[name] = dict({"reads_per_s": job_reads / (ms * 1e-3), "ms_per_step": ms, "K": K}, **extra)
+        roofline_methods[name] = {"achieved": round(ab / (ms * 1e-3) / 1e9, 2), "frac": round(ab / (ms * 1e-3) / 1e9 / peak, 4),
+                                  "algorithmic_bytes_per_read": round(ab / n_reads, 1), "records_with_len_ge_K_per_read": round(nl / n_reads, 3),
+                                  "ms_sweep": round(ms_sweep, 3), "ms_select": round(ms_sel, 3),
+                                  "dominant_kernel": "k_sweep" if ms_sweep >= ms_sel else f"k_select_seeded<{name.upper()}>"}
+        return ms
+
+    method_leg("lut", g.METHOD_LUT, max(2, args.steps // 2), {"K": LUT_K, "lut": lut}, LUT_K, 32, {})
     if rmi is not None:
-        ms_rmi = timed(lambda: engine.launch(g.METHOD_RMI, batch, rmi=rmi), 2, 1)
-        methods["rmi"] = {"reads_per_s": world * args.reads / (ms_rmi * 1e-3), "ms_per_step": ms_rmi, "K": RMI_K,
-                          "experts": list(args.experts)}
-        st = engine.read_status[: args.reads]
+        P = 2 * int(np.ceil(np.log2(2 * rmi.max_err + 2)))
+        method_leg("rmi", g.METHOD_RMI, max(2, args.steps // 2), {"rmi": rmi}, RMI_K, 64 * P,
+                   {"experts": list(args.experts), "max_abs_prediction_error_rows": rmi.max_err, "probes_P": P,
+                    "lookup": "predict + seed-table bounds + arithmetic replay of the error-bounded search (no probes); literal search on hazards"})
+        st = engine.read_status[:n_reads]
         methods["rmi"]["reads_where_reference_raises"] = int((st == g.READ_REF_RAISES).sum().item())
-        engine.check_overflow()
-    # the device-resident engine's pools are no longer needed: release them before the pipelined path allocates its own
-    total_records_dev = engine.records[: n_rec * 16]
-    rec_cnt_dev = engine.rec_cnt[: args.reads]
+        if extras and world == 1:
+            # the probe-based error-bounded search (round-1 path: 16-byte {SA, 32-mer} probe records): same records, more fetches
+            rmi.build_probe_table(index)
+            seed_keep = (index.seed_table, index.seed_K)
+            engine.sweep(batch)
+            index.seed_table, index.seed_K = None, 0
+            index._bind()
+            ms_probe = timed(lambda: engine.select(g.METHOD_RMI, batch, rmi=rmi), 1, 1)
+            index.seed_table, index.seed_K = seed_keep
+            index._bind()
+            _, nr2 = engine.check_overflow()
+            methods["rmi"]["probe_search_select_ms"] = round(ms_probe, 3)
+            snaps["rmi_probe"] = snapshot(n_par)
+            rmi.probe = None
+            rmi.c.probe = None
+            torch.cuda.empty_cache()
 
-    # ---- end to end through the public API: raw read bytes (pinned host) in, host records out
-    pipe = g.PipelinedEngine(index, args.reads, READ_LEN, n_chunks=args.e2e_chunks, **caps)
+    # ---- locate: SA intervals -> text positions with the sampled suffix array configs[3] names (1/32)
+    locate = None
+    if extras and world == 1:
+        engine.launch(g.METHOD_BWA, batch, min_len=1)
+        rows = engine.records[: n_rec * 16].view(torch.int32).view(-1, 4)[:, 2].contiguous()
+        index.build_sampled_sa(32, drop_full=False)
+        pos = torch.empty_like(rows)
+        import ctypes as C
+        from genie_smem_b200 import _capi as capi
 
-    def e2e_time(step):
-        for _ in range(2):
-            step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            res = step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return world * args.reads * args.steps / dt, res
+        def loc():
+            capi.check(capi.lib.gsm_locate_sampled_batch(C.byref(index.c), C.c_void_p(index.ssa.data_ptr()), 32, n_rec, C.c_void_p(rows.data_ptr()),
+                                                          C.c_void_p(pos.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ms_loc = timed(loc, 2, 1)
+        chk = slice(0, min(n_rec, 2_000_000))
+        ok = bool((index.sa[rows[chk].long()] == pos[chk]).all().item())
+        assert ok, "sampled-SA positions differ from the full suffix array"
+        lf_steps = 31.0          # row-sampled: geometric with p = 1/32
+        locate = {"rows_per_s": n_rec / (ms_loc * 1e-3), "reads_per_s": n_reads / (ms_loc * 1e-3), "ms": round(ms_loc, 3), "rows": n_rec,
+                  "sample": 32, "expected_lf_steps_per_row": lf_steps,
+                  "achieved_GBs": round(n_rec * (64 * lf_steps + 12) / (ms_loc * 1e-3) / 1e9, 1),
+                  "frac": round(n_rec * (64 * lf_steps + 12) / (ms_loc * 1e-3) / 1e9 / peak, 4),
+                  "equals_full_sa_on": chk.stop,
+                  "hbm_footprint_MB": {"buckets_fwd_rev": round(2 * index.fwd.numel() * 4 / 1e6), "sampled_sa": round(index.ssa.numel() * 4 / 1e6),
+                                       "full_sa": round(index.sa.numel() * 4 / 1e6), "text": round(index.text.numel() * 4 / 1e6),
+                                       "seed_table": round(index.seed_table.numel() * 4 / 1e6) if index.seed_table is not None else 0,
+                                       "lut": round(lut.numel() * 4 / 1e6), "rmi_params": round(rmi.params.numel() * 8 / 1e6) if rmi is not None else 0,
+                                       "rmi_probe_table_optional": round(index.n_rows * 16 / 1e6)},
+                  "note": "one thread per row, LF-walk to the next sampled row (k_locate_sampled); BWA/LUT-SMEM + locate need buckets + sampled SA "
+                          "only; the full SA (and text) are kept for RMI-SMEM's literal fallback"}
+        del rows, pos
 
-    v_ascii, res = e2e_time(lambda: pipe.run_ascii(g.METHOD_BWA, ascii_host, READ_LEN, min_len=1))
-    e2e = {"value": v_ascii, "unit": "reads/s", "h2d_bytes_per_step": pipe.last_h2d_bytes, "d2h_bytes_per_step": pipe.last_d2h_bytes,
-           "method": "bwa", "records_last_step": int(len(res.records)),
-           "api": f"PipelinedEngine.run_ascii ({args.e2e_chunks} chunks, 3 streams: raw ASCII reads H2D | GPU 2-bit packing, sweep, select | "
-                  "records D2H, all overlapped)"}
-    assert len(res.records) == n_rec, "end-to-end path and device-resident path disagree on the number of records"
-    batch.to_host(pin=True)
-    v_packed, _ = e2e_time(lambda: pipe.run(g.METHOD_BWA, batch, min_len=1))
-    e2e["packed_input"] = {"value": v_packed, "h2d_bytes_per_step": batch.h2d_bytes(),
-                           "api": "PipelinedEngine.run (reads already 2-bit packed on the host)"}
-
-    # ---- multi-GPU: the one collective of the path -- gather of per-rank records to rank 0
-    total_records = n_rec
-    gather = None
+    # ---- NCCL point-to-point gather of the same records (baseline transport of the collective)
+    record_gather = None
     if world > 1:
-        from genie_smem_b200 import sharding
-        cnt_dev = rec_cnt_dev.to(torch.int64)
+        engine.launch(g.METHOD_BWA, batch, min_len=1)
+        cnts = torch.zeros(world, dtype=torch.int64, device=dev)
+        mine = torch.tensor([n_rec], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(cnts, mine)
+        cnts_h = cnts.cpu().numpy().astype(np.uint64)
+        dst_buf = gat.buffer if rank == 0 else None
+        ms_g = timed(lambda: gat.comm.gather_records(engine.records, n_rec, cnts_h, dst_buf, 0), 3, 1)
+        tb = int(cnts_h.sum()) * 16
+        record_gather = {"transport": "gsm_gather_records: one ncclGroup of exact-size ncclSend/ncclRecv into a preallocated device buffer on rank 0",
+                         "ms": round(ms_g, 3), "bytes": tb, "GBs": round(tb / (ms_g * 1e-3) / 1e9, 1),
+                         "fused_alternative": "in `value`/`e2e` the gather is the ordered-write kernel's stores into rank 0's HBM (peer mapping)"}
+
+    # ---- end to end through the public API: host reads in, records out
+    del engine
+    torch.cuda.empty_cache()
+    pipe = g.PipelinedEngine(index, n_max, READ_LEN, n_chunks=args.e2e_chunks, **caps)
+
+    def e2e_time(step_fn, steps=None):
+        steps = steps or args.steps
+        for _ in range(2):
+            step_fn()
         barrier()
         t0 = time.perf_counter()
-        g_recs, g_cnts = sharding.gather_records(total_records_dev, cnt_dev, dst=0, device=dev)
+        for _ in range(steps):
+            res = step_fn()
         torch.cuda.synchronize()
-        dtg = time.perf_counter() - t0
-        if rank == 0:
-            total_records = int(len(g_recs))
-            gather = {"ms": round(dtg * 1e3, 2), "bytes_received": int(len(g_recs)) * 16, "backend": "nccl",
-                      "note": "includes the device-to-host read of the gathered array on rank 0; outside the timed steps"}
+        dt = max_over_ranks(time.perf_counter() - t0)
+        return job_reads * steps / dt, res
 
-    # ---- CPU baseline on the host cores, rank 0 at N=1 only
-    cpu_baseline = None
-    if rank == 0 and world == 1 and args.cpu_seconds > 0:
+    batch.to_host(pin=True)
+
+    def run_packed(gatherer):
+        if gatherer is not None:
+            gatherer.reset()
+        r = pipe.run(g.METHOD_BWA, batch, min_len=1, reuse_host_buffers=True, gatherer=gatherer)
+        if gatherer is not None:
+            gatherer.fence()
+        return r
+
+    v_packed, res = e2e_time(lambda: run_packed(gat))
+    e2e = {"value": v_packed, "unit": "reads/s", "h2d_bytes_per_step": batch.h2d_bytes(), "d2h_bytes_per_step": pipe.last_d2h_bytes,
+           "method": "bwa", "input": "2-bit packed reads in pinned host memory (48 B per 151-bp read)",
+           "api": f"PipelinedEngine.run ({args.e2e_chunks} chunks, 3 streams: reads H2D | sweep, select, ordered write | records D2H, all overlapped)"}
+    if gat is not None:
+        g_recs, seg = gat.finish()
+        e2e["api"] = (f"PipelinedEngine.run(gatherer=RecordGatherer) ({args.e2e_chunks} chunks: reads H2D | sweep, select, 8-byte count all-gather, "
+                      "ordered write into rank 0's HBM over NVLink | offsets + status D2H); records are delivered gathered on rank 0's device")
+        e2e["gathered_records"] = int(seg.sum()) if rank == 0 else None
+        e2e["nvlink_bytes_into_rank0_per_step"] = (int(seg.sum()) - int(seg[:, 0].sum())) * 16 if rank == 0 else None
+        v_shard, res2 = e2e_time(lambda: run_packed(None))
+        e2e["sharded_host_output"] = {"value": v_shard, "d2h_bytes_per_step": pipe.last_d2h_bytes,
+                                      "api": "PipelinedEngine.run: every rank copies its own records to its pinned host memory, no gather"}
+    else:
+        assert len(res.records) == n_rec, "end-to-end path and device-resident path disagree on the number of records"
+        e2e["records_last_step"] = int(len(res.records))
+    if extras and ascii_host is not None:
+        v_ascii, res3 = e2e_time(lambda: pipe.run_ascii(g.METHOD_BWA, ascii_host, READ_LEN, min_len=1, reuse_host_buffers=True), max(2, args.steps // 2))
+        e2e["ascii_input"] = {"value": v_ascii, "h2d_bytes_per_step": pipe.last_h2d_bytes,
+                              "api": "PipelinedEngine.run_ascii (raw ASCII read bytes, 1 byte/base H2D, 2-bit packing on the GPU; per-rank host output)"}
+        assert len(res3.records) == n_rec
+    if extras and world == 1:
+        e2e["from_fastq"] = fastq_leg(g, pipe, reads_head, n_rec_expected=None)
+
+    # ---- parity + CPU baseline on the host cores (rank 0; the timed baseline at N = 1 only)
+    cpu_baseline, parity = None, None
+    if rank == 0:
+        from oracle.c_oracle import COracle
         text = _B[ref].tobytes()
-        sa1 = index.suffix_array_host()
-        v, n_s, thr = cpu_arm(text, sa1, reads_head, 0, 0, args.cpu_seconds)
-        cpu_baseline = {"value": round(v, 1), "unit": "reads/s", "cores": thr, "kind": "port",
-                        "sample": f"first {n_s} reads of the same batch, BWA-SMEM, oracle/smem_oracle.c (reference algorithm, "
-                                  f"O(L^2) restarts included) on {thr} pthreads"}
-        v2, n2, _ = cpu_arm(text, sa1, reads_head, 1, 0, args.cpu_seconds / 2, K=LUT_K)
-        cpu_baseline["lut_reads_per_s"] = round(v2, 1)
+        o = COracle(text, index.suffix_array_host())
+        budget = args.cpu_seconds if world == 1 else 0.0
+        parity = {"reads": n_par, "against": "oracle/smem_oracle.c (reference get_SMEMS / get_smems_lut / get_smems_rmi restated literally, "
+                                             "pinned to tests/golden) on the first reads of this batch"}
+        v, n_s, thr, out, counts = cpu_arm(o, reads_head, 0, 0, budget, n_min=n_par)
+        parity["bwa"], _ = compare_with_oracle(reads_head, snaps["bwa"], out, counts, n_par)
+        if world == 1 and budget > 0:
+            cpu_baseline = {"value": round(v, 1), "unit": "reads/s", "cores": thr, "kind": "port",
+                            "sample": f"first {n_s} reads of the same batch, BWA-SMEM, oracle/smem_oracle.c (reference algorithm, "
+                                      f"O(L^2) restarts included) on {thr} pthreads"}
+        v2, _, _, out, counts = cpu_arm(o, reads_head, 1, 0, budget / 2, K=LUT_K, n_min=n_par)
+        parity["lut"], _ = compare_with_oracle(reads_head, snaps["lut"], out, counts, n_par)
+        if cpu_baseline:
+            cpu_baseline["lut_reads_per_s"] = round(v2, 1)
         if rmi is not None:
-            v3, n3, _ = cpu_arm(text, sa1, reads_head, 2, 0, args.cpu_seconds / 2, rmi=rmi_dict(rmi))
-            cpu_baseline["rmi_reads_per_s"] = round(v3, 1)
+            v3, _, _, out, counts = cpu_arm(o, reads_head, 2, 0, budget / 2, rmi=rmi_dict(rmi), n_min=n_par)
+            parity["rmi"], parity["ref_raises"] = compare_with_oracle(reads_head, snaps["rmi"], out, counts, n_par)
+            if "rmi_probe" in snaps:
+                parity["rmi_probe_search"], _ = compare_with_oracle(reads_head, snaps["rmi_probe"], out, counts, n_par)
+            if cpu_baseline:
+                cpu_baseline["rmi_reads_per_s"] = round(v3, 1)
+        if cpu_baseline:
+            cpu_baseline["python_port"] = python_port_baseline()
+        del o
 
     if rank == 0:
-        out = {"metric": "SMEM reads/sec (BWA-SMEM; LUT/RMI under methods)", "value": world * args.reads / (ms_bwa * 1e-3), "unit": "reads/s",
+        out = {"metric": "SMEM reads/sec (BWA-SMEM; LUT/RMI under methods)", "value": job_reads / (ms_bwa * 1e-3), "unit": "reads/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_bwa, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload,
-               "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(gpu_launches),
-               "clocks": clocks, "methods": methods, "records_total": total_records, "maximal_matches_per_read": round(n_mems / args.reads, 3),
-               "record_gather": gather, "index_build": index.build_stats}
+               "scaling": args.scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload,
+               "roofline": roofline, "roofline_methods": roofline_methods, "cpu_baseline": cpu_baseline, "e2e": e2e, "parity": parity,
+               "gpu_launches": int(gpu_launches), "clocks": clocks, "methods": methods, "records_total": n_rec if gathered is None else gathered["records"],
+               "maximal_matches_per_read": round(n_mems / n_reads, 3), "gathered": gathered, "record_gather": record_gather, "locate": locate,
+               "index_build": index.build_stats}
         out["sweep_seed_table_K"] = int(index.c.seed_K)
+        if world > 1:
+            out["value_includes"] = "sweep + select + scan + ordered write of every rank, the write being the gather into rank 0's HBM (NVLink), + completion fence"
         emit_result(out)
+    bad = rank == 0 and parity is not None and any(parity.get(k, 0) for k in ("bwa", "lut", "rmi", "rmi_probe_search"))
     if world > 1:
         dist.destroy_process_group()
+    if bad:
+        log(f"PARITY FAILURE: {parity}")
+        sys.exit(3)
 
 
-def train_rmi(index, K, experts, dev, max_keys=8_000_000):
-    """RMI over the k-mer -> row keys of this index (reference RMI_LUT.py:36-50).  The {SA value, 32-mer} probe table is
-    built on the device (it also serves the last-mile search); a strided sample of its rows is the training set --
-    model quality only changes the last-mile length, never the result -- and the fit is the vectorised host trainer."""
+def fastq_leg(g, pipe, reads_head, n_rec_expected):
+    """File bytes in, records out: a 4-line FASTQ of the batch's first reads is written to a temporary file, then timed
+    through ingest.read_fastq (multi-threaded scan + gather on the host) -> PipelinedEngine.run_ascii."""
+    import tempfile
+    import torch
+    from genie_smem_b200 import ingest
+    n = min(len(reads_head), 400_000, pipe.max_reads)
+    L = reads_head.shape[1]
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "reads.fq")
+        rec = np.empty((n, 2 * L + 16), np.uint8)
+        hdr = np.frombuffer(b"@r0000000\n", np.uint8)
+        rec[:, :10] = hdr
+        idx = np.arange(n)
+        for k in range(7):
+            rec[:, 8 - k] = 48 + (idx // 10 ** k) % 10
+        rec[:, 10:10 + L] = _B[reads_head[:n]]
+        rec[:, 10 + L] = 10
+        rec[:, 11 + L] = ord("+")
+        rec[:, 12 + L] = 10
+        rec[:, 13 + L:13 + 2 * L] = ord("I")
+        rec[:, 13 + 2 * L] = 10
+        rec = rec[:, :14 + 2 * L]
+        rec.tofile(path)
+        nbytes = os.path.getsize(path)
+        t0 = time.perf_counter()
+        bases, off, _ = ingest.read_fastq(path)
+        t_ingest = time.perf_counter() - t0
+        asc = torch.from_numpy(bases).view(n, L)
+        if torch.cuda.is_available() and not asc.is_pinned():
+            asc = asc.pin_memory()
+        pipe.run_ascii(g.METHOD_BWA, asc, L, min_len=1, reuse_host_buffers=True)
+        t0 = time.perf_counter()
+        bases, off, _ = ingest.read_fastq(path)
+        asc = torch.from_numpy(bases).view(n, L)
+        r = pipe.run_ascii(g.METHOD_BWA, asc, L, min_len=1, reuse_host_buffers=True)
+        dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "reads/s", "reads": n, "file_bytes": nbytes, "host_scan_gather_reads_per_s": n / t_ingest,
+            "records": int(len(r.records)),
+            "api": "ingest.read_fastq (page-cached file -> multi-threaded gsm_fastq_scan / gsm_fastq_gather on the host cores) -> "
+                   "PipelinedEngine.run_ascii; the host scanner is the limiter"}
+
+
+def python_port_baseline(budget_s=6.0):
+    """BASELINE.md section 3 asks for the reference's own Python on the box's cores.  /root/reference does not travel to the
+    GPU box, so the literal Python restatement (oracle/ref_port.py, pinned to the same goldens) is timed instead on
+    configs[0] (big_data, 100 kb; 101-bp exact substrings): one process, reads/s/core."""
+    try:
+        from oracle import ref_port as rp
+        from tests import golden_util as gu
+        gidx = gu.load_index("big_data")
+        idx = rp.RefIndex(gidx["text"], gidx["suffix_array"])
+        s = rp.RefSMEM(idx)
+        rng = np.random.default_rng(20261018)
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < budget_s and n < 1000:
+            p = int(rng.integers(0, len(gidx["text"]) - 101))
+            s.get_SMEMS(gidx["text"][p:p + 101], 1)
+            n += 1
+        return {"reads_per_s_one_process": round(n / (time.perf_counter() - t0), 1), "reads": n,
+                "what": "oracle/ref_port.py get_SMEMS (literal Python restatement of SMEM.py:456-484), configs[0] shape, one process"}
+    except Exception as e:          # fixtures absent: report, do not fail the bench
+        return {"unavailable": str(e)}
+
+
+def train_rmi(index, K, experts, dev, max_keys=8_000_000, probe_table=True):
+    """RMI over the k-mer -> row keys of this index (reference RMI_LUT.py:36-50).  Training set = a strided sample of the
+    (suffix array row, k-mer) pairs read from the suffix array + packed text on the device; model quality only changes the
+    last-mile length, never the result.  The fit is the vectorised host trainer.  probe_table: also build the 16-byte
+    {SA value, 32-mer} probe records the probe-based search uses (not needed by the seed-table lookup path)."""
     import torch
     import genie_smem_b200 as g
-    rmi = g.RmiParams(K, [1] + list(experts), np.zeros(1 + sum(experts)), np.zeros(1 + sum(experts)), dev)
-    rmi.build_probe_table(index)
     n_rows = index.n_rows
     stride = max(1, n_rows // max_keys)
-    tab = rmi.probe.view(torch.int32).view(-1, 4)[::stride].cpu().numpy().view(np.uint32)
-    rows = np.arange(0, n_rows, stride, dtype=np.int64)
-    start = tab[:, 0].astype(np.int64) - 1
-    code = (tab[:, 1].astype(np.uint64) << np.uint64(32)) | tab[:, 2].astype(np.uint64)
+    rows_t = torch.arange(0, n_rows, stride, device=dev, dtype=torch.int64)
+    start = index.sa[rows_t].to(torch.int64) & 0xFFFFFFFF
+    start = start - 1                                               # 0-based text index of the suffix
     ok = start + K <= index.n_bases
-    key = (code[ok] >> np.uint64(64 - 2 * K)).astype(np.int64)
-    m = g.RMI(list(experts)).fit(key, rows[ok])
+    rows_t, start = rows_t[ok], start[ok]
+    text = index.text.to(torch.int64) & 0xFFFFFFFF
+    key = torch.zeros_like(start)
+    for t in range(K):                                              # MSB-first k-mer code (LUT.convert_seq_to_num)
+        p = start + t
+        key = key * 4 + ((text[p >> 4] >> (30 - 2 * (p & 15))) & 3)
+    del text
+    key_h, rows_h = key.cpu().numpy(), rows_t.cpu().numpy()
+    m = g.RMI(list(experts)).fit(key_h, rows_h)
     out = g.RmiParams(K, m.level_sizes, m.coef, m.intercept, dev)
-    out.probe = rmi.probe
-    out.c.probe = rmi.probe.data_ptr()
+    out.max_err = float(np.abs(m.predict(key_h) - rows_h).max())
+    if probe_table:
+        out.build_probe_table(index)
     out.build_none_rows(index)
     return out
 
@@ -487,19 +770,21 @@ def reference_arm(args, workload):
     import genie_smem_b200 as g
     ref = make_reference(args.ref_bases, args.seed)
     text = _B[ref].tobytes()
-    sa1 = None
+    sa1, built_by = None, None
     try:
         import torch
         if torch.cuda.is_available():
             idx = g.DeviceIndex.build_on_device(ref, "cuda:0", reverse=False)
             sa1 = idx.suffix_array_host()
+            built_by = "gsm_index_build_device (this repo's GPU builder, before the timed region; bit-equal to host SA-IS in tests)"
             del idx
             torch.cuda.empty_cache()
     except Exception as e:          # no usable device: fall through to the host builder
         log(f"reference arm: GPU index build unavailable ({e}); using host SA-IS")
     if sa1 is None:
         sa1, _ = g.HostIndex.build(text, reverse=False).export()
-    reads_codes = host_reads(ref, min(args.reads, HOST_READS), args.seed + 1, args.sub_rate, args.random_reads)
+        built_by = "gsm_index_build (this repo's host SA-IS, before the timed region)"
+    reads_codes = host_reads(ref, min(args.total_reads, HOST_READS), args.seed + 1, args.sub_rate, args.random_reads)
     from oracle.c_oracle import COracle
     o = COracle(text, sa1)
     thr = o.max_threads
@@ -522,10 +807,11 @@ def reference_arm(args, workload):
     v = n / dt
     sample = f"{n} reads per step (first reads of the batch), BWA-SMEM, oracle/smem_oracle.c on {thr} pthreads"
     out = {"impl": "reference", "metric": "SMEM reads/sec (BWA-SMEM; LUT/RMI under methods)", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
            "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": workload,
            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": thr, "kind": "port", "sample": sample},
-           "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+           "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+           "reference_class": "cpu", "index_built_by": built_by}
     emit_result(out)
 
 

@@ -86,6 +86,18 @@ EXPORTS = {
     "gsm_rmi_none_rows": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_rmi_lookup_batch": (C.c_int, [C.POINTER(DevIndex), C.POINTER(DevRmi), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gsm_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "gsm_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "gsm_comm_free": (C.c_int, [C.c_void_p]),
+    "gsm_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gsm_comm_allgather_u64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "gsm_gather_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gsm_peer_export": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "gsm_peer_open": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "gsm_peer_close": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "gsm_smem_collect_gathered": (C.c_int, [C.POINTER(DevReads), C.POINTER(Workspace), C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32,
+                                            C.c_void_p, C.c_void_p]),
+    "gsm_gather_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "gsm_gather_probe": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "gsm_l2_persist": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "gsm_device_l2_fetch_granularity": (C.c_int, [C.c_int32, C.POINTER(C.c_uint32)]),

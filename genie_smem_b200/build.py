@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libgenie_smem.so")
-SOURCES = ["kernels.cu", "index_device.cu", "ingest.cu", "index_host.cpp", "ingest_host.cpp"]
+SOURCES = ["kernels.cu", "index_device.cu", "ingest.cu", "comm.cu", "index_host.cpp", "ingest_host.cpp"]
 HEADERS = ["fm_core.cuh", "sweep_logic.cuh", "sweep_device.cuh", "select_logic.cuh", "host_common.hpp", "../../include/genie_smem.h"]
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC,-O3,-fno-strict-aliasing", "-Xptxas", "-v"]
@@ -60,14 +60,14 @@ def build(force=False, verbose=False):
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed compiling {f}")
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + \
-          [os.path.join(OBJ, f + ".o") for f in SOURCES] + ["-lpthread"]
+          [os.path.join(OBJ, f + ".o") for f in SOURCES] + ["-lpthread", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed linking libgenie_smem.so")
     for f, text in logs.items():
-        with open(os.path.join(HERE, "ptxas.log" if f == "kernels.cu" else f"ptxas_{f.split('.')[0]}.log"), "w") as out:
+        with open(os.path.join(OBJ, f"ptxas_{f.split('.')[0]}.log"), "w") as out:     # untracked; profiles/ keeps one copy per round
             out.write(text)
     return LIB
 

@@ -1,17 +1,19 @@
 // sm_100a kernels + C ABI of the SMEM-seeding engine.
 //
 // Work decomposition (B200: 148 SMs, 126 MB L2, HBM3e):
-//   * a rank query is one aligned 64-byte bucket; four lanes ("quad") fetch it with one 128-bit
-//     load each, so one warp-wide load instruction moves eight buckets = eight independent
-//     FM chains.  The path is random-access and latency-bound: no TMA, no tensor cores.
-//   * k_sweep:  persistent grid, one quad per read (8 reads in flight per warp, dynamic read
-//     queue), bidirectional FM extension enumerating every maximal exact match of the read.
-//     All quads of a warp execute ONE uniform load/popcount section per iteration, so the
-//     eight chains' bucket fetches are always in flight together.
-//   * k_select: one thread per read, integer selection of the reference's records from the
-//     match list (BWA / LUT / RMI semantics), LUT gather and RMI predict + last-mile search
-//     fused in.
-//   * k_scan_* / k_gather_records: counts -> offsets -> records in (read, emission) order.
+//   * a rank query is one aligned 64-byte bucket = two 32-byte halves; a lane PAIR fetches it with one 256-bit load per
+//     lane (LDG.E.ENL2.256), so one warp-wide load instruction moves 16 buckets = 16 independent FM chains.  The path
+//     is random-access and latency-bound: no TMA, no tensor cores.
+//   * k_sweep (sweep_device.cuh): persistent grid, one lane pair per read (16 reads in flight per warp, dynamic read
+//     queue), bidirectional FM extension enumerating every maximal exact match of the read.  All pairs of a warp
+//     execute ONE uniform load/popcount section per iteration, so the 16 chains' fetches are in flight together.
+//   * k_select<BWA>: one thread per read, the reference's get_SMEMS selection over the match list.
+//   * k_select_seeded<LUT|RMI>: persistent threads, one read per thread, the reference's frame machine one ROUND at a
+//     time with the warp in lock step: pass 1 = all table lookups of the round (LUT gather; RMI predict + seed-table
+//     bounds + arithmetic replay of the error-bounded search, literal probe search only on a hazard), pass 2 = the
+//     integer machine, pass 3 = the (rare) explicit backward search of the round's winner.
+//   * k_scan_* / k_gather_records: counts -> offsets -> records in (read, emission) order; the destination may be a
+//     peer GPU's memory (gsm_peer_*), which makes the ordered write the NVLink gather of the multi-GPU path.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -38,6 +40,7 @@ namespace gsm {
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr int SELECT_THREADS = 128;
+constexpr uint32_t SELECT_STAGE = 64;   // staged records per selection thread; reads emitting more are run twice (see DevSelCtx::close)
 
 // ===================================================================================== select
 struct SelectArgs {
@@ -62,7 +65,8 @@ struct SelectArgs {
     uint4* mem_pool;
     const uint32_t* mem_off;
     const uint32_t* mem_cnt;
-    uint4* stage;               // per thread: max_len records
+    uint4* stage;               // per thread: stage_stride records (a read that emits more is run a second time, writing in place)
+    uint32_t stage_stride;
     uint4* rec_tmp;
     unsigned long long rec_cap;
     uint32_t* rec_tmp_off;
@@ -86,10 +90,11 @@ struct DevSelCtx {
     const SelectArgs& a;
     const uint32_t* words;
     uint4* mems;
-    uint4* stage;
+    uint4* out;           // where this read's records go: the thread's staging slots, or (second run of a read that
+    uint32_t cap;         // overflowed them) its exactly sized segment of the record pool; cap = slots available
     uint32_t L, K, n_mems, min_len, rid, n_rec;
     bool raised;
-    bool writer;          // this thread stores the records (false for the non-leader lanes of a selection team)
+    bool overflow;        // more records than slots: counted, not stored
 
     __device__ __forceinline__ MemEntry mem(uint32_t k) const {
         uint4 v = mems[k];
@@ -99,28 +104,31 @@ struct DevSelCtx {
     __device__ __forceinline__ bool failed() const { return raised; }
     __device__ __forceinline__ bool seeds_are_true() const { return METHOD == GSM_METHOD_LUT; }
 
-    __device__ void interval(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt) {
-        lo = 0; cnt = a.meta.n_rows;
-        const uint4* fwd = a.fwd;
-        auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
-        uint32_t p = j;
+    // True SA interval of q[i:j) by backward search (ExactMatch.exact_match_back_prop, ExactMatch.py:132-151), resumable:
+    // interval_begin takes the first K / seed_K steps from a table entry, interval_step prepends q[p-1].
+    __device__ __forceinline__ void interval_begin(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt, uint32_t& p) const {
+        lo = 0; cnt = a.meta.n_rows; p = j;
         const uint32_t* w = words;
         auto rd = [w](uint64_t x) { return __ldg(w + x); };
         if (a.seed_K != 0u && j - i >= a.seed_K && (METHOD != GSM_METHOD_LUT || a.seed_K >= K)) {
             const uint4 e = __ldg(a.seed_tab + kmer_code(rd, j - a.seed_K, a.seed_K));   // the longest table first
             lo = e.x; cnt = e.y; p = j - a.seed_K;
-            if (cnt == 0) return;
         } else if (METHOD == GSM_METHOD_LUT && j - i >= K) {      // the table replaces the first K backward steps
             const uint2 e = __ldg(a.lut + kmer_code(rd, j - K, K));
             lo = e.x; cnt = e.y; p = j - K;
-            if (cnt == 0) return;
         }
-        for (; p > i; --p) {
-            const uint32_t c = base(p - 1);
-            StepOut r = step_single(load, lo, lo + cnt, c, a.meta.C[c], a.meta.prim_f);
-            lo = r.lo_new; cnt = r.cnt_new;
-            if (cnt == 0) return;
-        }
+    }
+    __device__ __forceinline__ void interval_step(uint32_t& lo, uint32_t& cnt, uint32_t& p) const {
+        const uint4* fwd = a.fwd;
+        auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
+        const uint32_t ch = base(p - 1);
+        const StepOut r = step_single(load, lo, lo + cnt, ch, a.meta.C[ch], a.meta.prim_f);
+        lo = r.lo_new; cnt = r.cnt_new; --p;
+    }
+    __device__ void interval(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt) {
+        uint32_t p;
+        interval_begin(i, j, lo, cnt, p);
+        while (p > i && cnt != 0u) interval_step(lo, cnt, p);
     }
 
     // One probe of the RMI last-mile search (RMI_LUT.get_ref_seq, RMI_LUT.py:89-92): the 16-byte {SA value, 32-mer}
@@ -138,14 +146,16 @@ struct DevSelCtx {
         }
     }
 
-    // per-thread lookups of one round (LUT path of k_select): one 8-byte gather per visited window
-    __device__ uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi) {
+    // per-thread lookups of one round (Selector::run_seeded, LUT): one 8-byte gather per visited window
+    __device__ uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi, uint32_t& wtrue) {
         uint32_t hit = 0;
+        wtrue = 0;
         for (uint32_t i = 0; i < nwin; ++i) {
             const uint32_t cpos = first ? 0u : e - i;
             if (!(first || (i < plen && cpos + K <= L))) continue;
             const uint2 t = __ldg(a.lut + window_code(cpos));
             lo[i] = t.x; hi[i] = (int64_t)t.x + t.y - 1;
+            wtrue |= 1u << i;
             if (t.y != 0) hit |= 1u << i;
         }
         return hit;
@@ -157,32 +167,61 @@ struct DevSelCtx {
         return kmer_code(rd, cpos, K);
     }
 
-    __device__ bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi) {
-        if (METHOD == GSM_METHOD_LUT) {
-            // check_sequential (SMEM.py:196-202) on two TRUE k-mer intervals: some occurrence of
-            // q[c:c+K] is followed one base later by q[pc:pc+K]  <=>  the k-mers overlap
-            // consistently and q[c] + q[pc:pc+K] occurs (one backward step on the second seed).
-            for (uint32_t t = 1; t < K; ++t)
-                if (base(c + t) != base(pc + t - 1)) return false;
-            const uint32_t ch = base(c);
-            const uint4* fwd = a.fwd;
-            auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
-            StepOut r = step_single(load, (uint32_t)plo, (uint32_t)phi + 1u, ch, a.meta.C[ch], a.meta.prim_f);
-            return r.cnt_new != 0;
+    // true bounds (first row >= k-mer, occurrences) of window cpos from the sweep's seed table (needs seed_K <= K)
+    __device__ __forceinline__ void window_bounds(uint32_t cpos, uint32_t& A, uint32_t& cnt) const {
+        const uint32_t* w = words;
+        const uint4* fwd = a.fwd;
+        const uint4* tab = a.seed_tab;
+        auto rd = [w](uint64_t i) { return __ldg(w + i); };
+        auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
+        auto seed = [tab](uint64_t code) { const uint4 v = __ldg(tab + code); return U4{v.x, v.y, v.z, v.w}; };
+        kmer_bounds_seeded(rd, load, seed, a.meta, cpos, K, a.seed_K, A, cnt);
+    }
+
+    __device__ bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi, bool both_true) {
+        const uint4* fwd = a.fwd;
+        auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
+        if (METHOD == GSM_METHOD_LUT || both_true) {
+            const DevSelCtx* self = this;
+            auto bs = [self](uint32_t p) { return self->base(p); };
+            return true_sequential(bs, load, a.meta, K, c, pc, plo, phi);
         }
-        // RMI: literal check on the RETURNED intervals (SMEM.py:262-265), which may be wrong
-        const int64_t n = (int64_t)a.meta.n_rows;
-        for (int64_t x = clo; x <= chi; ++x) {
-            const uint32_t px = __ldg(a.sa + (x < 0 ? x + n : x));
-            for (int64_t y = plo; y <= phi; ++y)
-                if (px + 1u == __ldg(a.sa + (y < 0 ? y + n : y))) return true;
-        }
-        return false;
+        // RMI: check on the RETURNED intervals (SMEM.py:262-265), which may be wrong: x == LF(y) in O(1)
+        const uint32_t* sa = a.sa;
+        auto sal = [sa](uint64_t r) { return __ldg(sa + r); };
+        return rmi_sequential(load, sal, a.meta, clo, chi, plo, phi);
     }
 
     __device__ __forceinline__ void emit(uint32_t i, uint32_t j, int64_t lo, int64_t hi) {
-        if (writer) stage[n_rec] = make_uint4(a.read_id_base + rid, i | (j << 16), (uint32_t)lo, (uint32_t)hi);
+        if (n_rec < cap) out[n_rec] = make_uint4(a.read_id_base + rid, i | (j << 16), (uint32_t)lo, (uint32_t)hi);
+        else overflow = true;
         n_rec++;
+    }
+
+    // Read finished: hand its records to the pool.  Staged records are copied to a freshly reserved segment; a read that
+    // overflowed its staging slots reserves its exact count and returns true -- the caller runs it again (the selection
+    // is deterministic) with `out` pointing at that segment, and the second close only publishes offset and count.
+    __device__ __forceinline__ bool close(uint8_t status, bool& direct) {
+        if (raised) { status = GSM_READ_REF_RAISES; n_rec = 0; overflow = false; }
+        bool again = false;
+        if (direct) {
+            a.rec_tmp_off[rid] = (uint32_t)(out - a.rec_tmp); a.rec_cnt[rid] = n_rec;
+            direct = false;
+        } else {
+            const unsigned long long off = atomicAdd(&a.counters[1], (unsigned long long)n_rec);
+            if (off + n_rec > a.rec_cap) {
+                atomicOr(&a.counters[2], 2ull);
+                a.rec_tmp_off[rid] = 0; a.rec_cnt[rid] = 0;
+            } else if (overflow) {
+                out = a.rec_tmp + off; cap = n_rec; n_rec = 0; overflow = false;
+                direct = again = true;
+            } else {
+                for (uint32_t k = 0; k < n_rec; ++k) a.rec_tmp[off + k] = out[k];
+                a.rec_tmp_off[rid] = (uint32_t)off; a.rec_cnt[rid] = n_rec;
+            }
+        }
+        if (!again) a.read_status[rid] = status;
+        return again;
     }
 };
 
@@ -205,27 +244,22 @@ template <int METHOD>
 __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    uint4* const stage = a.stage + gtid * a.stage_stride;
     for (size_t rid = gtid; rid < a.n_reads; rid += nthreads) {
         DevSelCtx<METHOD> c{a,
                             a.reads + (size_t)__ldg(a.chunk_off + rid) * 4,
                             a.mem_pool + a.mem_off[rid],
-                            a.stage + gtid * a.max_len,
-                            __ldg(a.len + rid), a.K, a.mem_cnt[rid], a.min_len, (uint32_t)rid, 0u, false, true};
+                            stage, a.stage_stride,
+                            __ldg(a.len + rid), a.K, a.mem_cnt[rid], a.min_len, (uint32_t)rid, 0u, false, false};
         order_segments(c.mems, c.n_mems);
-        uint8_t status = GSM_READ_OK;
-        if (METHOD == GSM_METHOD_BWA) Selector<DevSelCtx<METHOD>>::run_bwa(c);
-        else if (c.L < c.K) status = GSM_READ_TOO_SHORT;
-        else Selector<DevSelCtx<METHOD>>::run_seeded(c);
-        if (c.raised) { status = GSM_READ_REF_RAISES; c.n_rec = 0; }
-        unsigned long long off = atomicAdd(&a.counters[1], (unsigned long long)c.n_rec);
-        if (off + c.n_rec > a.rec_cap) {
-            atomicOr(&a.counters[2], 2ull);
-            a.rec_tmp_off[rid] = 0; a.rec_cnt[rid] = 0;
-        } else {
-            for (uint32_t k = 0; k < c.n_rec; ++k) a.rec_tmp[off + k] = c.stage[k];
-            a.rec_tmp_off[rid] = (uint32_t)off; a.rec_cnt[rid] = c.n_rec;
-        }
-        a.read_status[rid] = status;
+        bool direct = false;
+        do {
+            uint8_t status = GSM_READ_OK;
+            if (METHOD == GSM_METHOD_BWA) Selector<DevSelCtx<METHOD>>::run_bwa(c);
+            else if (c.L < c.K) status = GSM_READ_TOO_SHORT;
+            else Selector<DevSelCtx<METHOD>>::run_seeded(c);
+            if (!c.close(status, direct)) break;
+        } while (true);
     }
 }
 
@@ -250,15 +284,19 @@ __device__ __forceinline__ void phase_loop(uint32_t mask, Machine& mach, Begin b
     }
 }
 
-// RMI-SMEM selection with the warp kept in lock step on the memory-bound part.  One thread per read (threads pull reads
-// grid-stride: many reads in flight hide the dependent loads of the frame machine), but the round structure of the machine
-// (select_logic.cuh) is driven warp-wide:
-//   pass 1  every thread with a read in progress looks up the windows of its current round: predict + last-mile search
-//           through ONE probe site inside a loop that the whole warp leaves together (__any_sync) -- the error-bounded
-//           search (RmiGallop / RmiLower / RmiUpper, one phase at a time) first, then the literal RmiSearch for the windows
-//           it declared hazardous;
-//   pass 2  each thread runs the integer frame machine of its round (divergent, no table probes), emits one record,
-//           and opens its next read when the current one is finished.
+// LUT- and RMI-SMEM selection with the warp kept in lock step.  One thread per read (persistent threads pull reads
+// grid-stride: a thread always has a round to run, whatever the record counts of its neighbours' reads), and the round
+// structure of the frame machine (select_logic.cuh) is driven warp-wide:
+//   pass 1  the table lookups of every window of the round, one converged counted loop:
+//             LUT  one 8-byte gather per window (LUT.py:15-35 as a dense table);
+//             RMI  predict (RMI.py:52-69) + the k-mer's true bounds from the sweep's seed table (one 16-byte fetch and
+//                  K - seed_K FM steps) + rmi_arith_lookup: the error-bounded search replayed on row numbers, no probes.
+//                  Without a usable seed table: the probe-based phases RmiGallop / RmiLower / RmiUpper (one probe site
+//                  each, warp in lock step).  Windows either path declares hazardous (None rows in the bracket,
+//                  prediction outside the table: a handful per million) go through the literal RmiSearch;
+//   pass 2  each thread runs the integer frame machine of its round (divergent, no table probes) -> the round's winner;
+//   pass 3  the winner's interval if it is not on the match list (rare): explicit backward search, one lock-step loop;
+//           then emit, and open the next read when the current one is finished.
 // Measured alternatives (profiles/r01_notes.md): the reference's control flow per thread end to end (2.2 active threads
 // per instruction on the probes), and teams of 16 lanes per read with one window per lane (converged, but 16x fewer reads
 // in flight: latency-bound on the machine's dependent loads, 1.7x slower than this kernel).
@@ -269,22 +307,15 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     size_t rid = gtid;
     bool have = false;
-    DevSelCtx<METHOD> c{a, nullptr, nullptr, a.stage + gtid * a.max_len, 0u, a.K, 0u, a.min_len, 0u, 0u, false, true};
+    uint4* const stage = a.stage + gtid * a.stage_stride;
+    DevSelCtx<METHOD> c{a, nullptr, nullptr, stage, a.stage_stride, 0u, a.K, 0u, a.min_len, 0u, 0u, false, false};
+    bool direct = false;
     typename Sel::Seeded st;
     int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
     uint64_t wcode[MAX_SEED_K];
 
     auto close_read = [&](uint8_t status) {
-        if (c.raised) { status = GSM_READ_REF_RAISES; c.n_rec = 0; }
-        const unsigned long long off = atomicAdd(&a.counters[1], (unsigned long long)c.n_rec);
-        if (off + c.n_rec > a.rec_cap) {
-            atomicOr(&a.counters[2], 2ull);
-            a.rec_tmp_off[rid] = 0; a.rec_cnt[rid] = 0;
-        } else {
-            for (uint32_t k = 0; k < c.n_rec; ++k) a.rec_tmp[off + k] = c.stage[k];
-            a.rec_tmp_off[rid] = (uint32_t)off; a.rec_cnt[rid] = c.n_rec;
-        }
-        a.read_status[rid] = status;
+        if (c.close(status, direct)) { st = typename Sel::Seeded(); return; }      // overflowed its staging slots: run it again in place
         rid += nthreads;
         have = false;
     };
@@ -293,20 +324,15 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
         while (!have && rid < a.n_reads) {
             c.words = a.reads + (size_t)__ldg(a.chunk_off + rid) * 4;
             c.mems = a.mem_pool + a.mem_off[rid];
-            c.L = __ldg(a.len + rid); c.n_mems = a.mem_cnt[rid]; c.rid = (uint32_t)rid; c.n_rec = 0; c.raised = false;
+            c.L = __ldg(a.len + rid); c.n_mems = a.mem_cnt[rid]; c.rid = (uint32_t)rid; c.n_rec = 0; c.raised = false; c.overflow = false;
+            c.out = stage; c.cap = a.stage_stride;
             order_segments(c.mems, c.n_mems);
             st = typename Sel::Seeded();
             if (c.L < c.K) { close_read(GSM_READ_TOO_SHORT); continue; }
             have = true;
         }
     };
-    auto next_window = [&](uint32_t& i, uint32_t nwin, uint32_t& cpos) {       // next visited window at or after i
-        for (; i < nwin; ++i) {
-            cpos = st.first ? 0u : st.e - i;
-            if (st.first || (i < st.plen && cpos + c.K <= c.L)) return true;
-        }
-        return false;
-    };
+    const bool arith = METHOD == GSM_METHOD_RMI && a.rmi.n_none != 0u && a.seed_K != 0u && a.seed_K <= a.K;
 
     for (;;) {
         while (true) {                                   // finished reads are closed, the next ones opened
@@ -316,12 +342,38 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
         }
         if (!__any_sync(FULL, have)) break;
         const uint32_t nwin = st.first ? 1u : c.K;
-        uint32_t whit = 0, redo = 0;
+        uint32_t whit = 0, wtrue = 0, redo = 0;
         // ---------------- pass 1: lookups, warp in lock step
-        if (a.rmi.n_none != 0) {
-            // error-bounded search (select_logic.cuh, RmiGallop / RmiLower / RmiUpper): each phase runs over ALL windows of
-            // the round as one lock-step loop with straight-line per-probe code; windows a phase declares hazardous (None
-            // rows in the bracket, prediction outside the table -- a handful per million) go to the literal search below
+        if (METHOD == GSM_METHOD_LUT) {
+            for (uint32_t i = 0; i < nwin; ++i) {
+                const uint32_t cpos = st.first ? 0u : st.e - i;
+                if (have && (st.first || (i < st.plen && cpos + c.K <= c.L))) {
+                    const uint2 t = __ldg(a.lut + c.window_code(cpos));
+                    wlo[i] = t.x; whi[i] = (int64_t)t.x + t.y - 1;
+                    wtrue |= 1u << i;
+                    if (t.y != 0u) whit |= 1u << i;
+                }
+            }
+        } else if (arith) {
+            for (uint32_t i = 0; i < nwin; ++i) {
+                const uint32_t cpos = st.first ? 0u : st.e - i;
+                if (have && (st.first || (i < st.plen && cpos + c.K <= c.L))) {
+                    const int64_t row0 = RmiGallop::predicted_row(a.rmi, c.window_code(cpos), a.meta.n_rows);
+                    uint32_t A, n;
+                    c.window_bounds(cpos, A, n);
+                    int64_t lo, hi;
+                    if (rmi_arith_lookup(a.rmi, row0, A, n, a.meta.n_rows, lo, hi)) {
+                        wlo[i] = lo; whi[i] = hi;
+                        wtrue |= 1u << i;
+                        if (hi >= lo) whit |= 1u << i;
+                    } else {
+                        redo |= 1u << i;
+                    }
+                }
+            }
+        } else if (a.rmi.n_none != 0) {
+            // probe-based error-bounded search (select_logic.cuh, RmiGallop / RmiLower / RmiUpper): each phase runs over ALL
+            // windows of the round as one lock-step loop with straight-line per-probe code
             uint32_t todo = 0, lbm = 0, ubm = 0;
             for (uint32_t i = 0; i < nwin; ++i) {           // codes and model predictions, one converged counted loop
                 const uint32_t cpos = st.first ? 0u : st.e - i;
@@ -345,6 +397,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
                            },
                            [&]() { c.probe_row(ga.row(), sv, c64); ga.feed(a.rmi, sv, c64); });
             }
+            wtrue = lbm;                                     // no hazard: the bounds found below are the k-mer's true interval
             {
                 RmiLower lb;                                 // phase B: first row >= q
                 phase_loop(lbm, lb,
@@ -365,10 +418,12 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
                 whit |= ubm;
             }
         } else if (have) {
-            uint32_t i = 0, cpos = 0;
-            while (next_window(i, nwin, cpos)) redo |= 1u << i++;
+            for (uint32_t i = 0; i < nwin; ++i) {
+                const uint32_t cpos = st.first ? 0u : st.e - i;
+                if (st.first || (i < st.plen && cpos + c.K <= c.L)) redo |= 1u << i;
+            }
         }
-        if (__any_sync(FULL, redo != 0)) {
+        if (METHOD == GSM_METHOD_RMI && __any_sync(FULL, redo != 0)) {
             RmiSearch rs;
             int cur = -1;
             bool more = redo != 0;
@@ -397,138 +452,26 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
             }
         }
         __syncwarp();
-        // ---------------- pass 2: the frame machine of this round
+        // ---------------- pass 2: the frame machine of this round -> its winner
+        typename Sel::Cand w{false, false, 0u, 0u, 0, -1};
+        bool run = have && !c.raised;
+        if (run) w = Sel::round_decide(c, st, wlo, whi, whit, wtrue);
+        __syncwarp();
+        // ---------------- pass 3: explicit backward search for winners that are not on the match list (rare), lock step
+        uint32_t slo = 0, scnt = 0, sp = 0;
+        bool search = run && w.valid && Sel::resolve(c, w);
+        if (search) c.interval_begin(w.i, w.j, slo, scnt, sp);
+        while (__any_sync(FULL, search)) {
+            if (search) {
+                if (sp > w.i && scnt != 0u) c.interval_step(slo, scnt, sp);
+                else { w.lo = (int64_t)slo; w.hi = (int64_t)slo + scnt - 1; w.lazy = false; search = false; }
+            }
+        }
         if (have) {
             if (c.raised) close_read(GSM_READ_REF_RAISES);
-            else Sel::round_finish(c, st, wlo, whi, whit);
+            else Sel::round_commit(c, st, w);
         }
         __syncwarp();
-    }
-}
-
-// The same selection by TEAMS of 16 lanes: one read per team, one window of the round per lane (pass 1 costs the latency
-// of the round's longest search instead of the sum of all), the frame machine run by all 16 lanes on identical data (pass
-// 2 converged; lane 0 writes).  Fewer reads in flight than k_select_seeded; chosen per method by measurement
-// (gsm_smem_select, GSM_SELECT_TEAMS).
-constexpr uint32_t TEAM = 16;
-
-template <int METHOD>
-__global__ void __launch_bounds__(SELECT_THREADS) k_select_team(const SelectArgs a) {
-    using Sel = Selector<DevSelCtx<METHOD>>;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t tl = lane & (TEAM - 1u);                   // lane within the team
-    const uint32_t tbase = lane & ~(TEAM - 1u);
-    const uint32_t tmask = 0xFFFFu << tbase;
-    const size_t team = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / TEAM;
-    const size_t n_teams = ((size_t)gridDim.x * blockDim.x) / TEAM;
-    size_t rid = team;
-    bool have = false;
-    DevSelCtx<METHOD> c{a, nullptr, nullptr, a.stage + team * a.max_len, 0u, a.K, 0u, a.min_len, 0u, 0u, false, tl == 0u};
-    typename Sel::Seeded st;
-    int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
-
-    auto close_read = [&](uint8_t status) {                   // every lane runs this with identical data; lane 0 writes
-        if (c.raised) { status = GSM_READ_REF_RAISES; c.n_rec = 0; }
-        unsigned long long off = 0;
-        if (tl == 0u) off = atomicAdd(&a.counters[1], (unsigned long long)c.n_rec);
-        off = __shfl_sync(tmask, off, tbase);
-        __syncwarp(tmask);                                    // lane 0's staged records are visible to the team
-        if (off + c.n_rec > a.rec_cap) {
-            if (tl == 0u) { atomicOr(&a.counters[2], 2ull); a.rec_tmp_off[rid] = 0; a.rec_cnt[rid] = 0; }
-        } else {
-            for (uint32_t k = tl; k < c.n_rec; k += TEAM) a.rec_tmp[off + k] = c.stage[k];
-            if (tl == 0u) { a.rec_tmp_off[rid] = (uint32_t)off; a.rec_cnt[rid] = c.n_rec; }
-        }
-        if (tl == 0u) a.read_status[rid] = status;
-        rid += n_teams;
-        have = false;
-    };
-    auto open_reads = [&]() {
-        while (!have && rid < a.n_reads) {
-            c.words = a.reads + (size_t)__ldg(a.chunk_off + rid) * 4;
-            c.mems = a.mem_pool + a.mem_off[rid];
-            c.L = __ldg(a.len + rid); c.n_mems = a.mem_cnt[rid]; c.rid = (uint32_t)rid; c.n_rec = 0; c.raised = false;
-            if (tl == 0u) order_segments(c.mems, c.n_mems);
-            __syncwarp(tmask);
-            st = typename Sel::Seeded();
-            if (c.L < c.K) { close_read(GSM_READ_TOO_SHORT); continue; }
-            have = true;
-        }
-    };
-
-    for (;;) {
-        while (true) {
-            open_reads();
-            if (!have || Sel::round_needed(c, st)) break;
-            close_read(GSM_READ_OK);
-        }
-        if (!have) break;                                     // team-uniform: the whole team leaves together
-        const uint32_t nwin = st.first ? 1u : c.K;
-        uint32_t whit = 0;
-        for (uint32_t wb = 0; wb < nwin; wb += TEAM) {        // pass 1: one window per lane (two batches when K > 16)
-            const uint32_t i = wb + tl;
-            const uint32_t cpos = st.first ? 0u : st.e - i;
-            const bool visit = i < nwin && (st.first || (i < st.plen && cpos + c.K <= c.L));
-            int64_t mlo = 0, mhi = -1;
-            if (METHOD == GSM_METHOD_LUT) {
-                if (visit) {
-                    const uint2 t = __ldg(a.lut + c.window_code(cpos));
-                    mlo = t.x; mhi = (int64_t)t.x + t.y - 1;
-                }
-            } else {
-                const uint64_t code = visit ? c.window_code(cpos) : 0ull;
-                bool literal = visit;
-                if (a.rmi.n_none != 0) {
-                    const int64_t nb = (int64_t)a.n_bases;
-                    const uint32_t nr = a.meta.n_rows;
-                    int64_t sv;
-                    uint64_t c64;
-                    RmiGallop ga;
-                    if (visit) ga.begin(a.rmi, code, RmiGallop::predicted_row(a.rmi, code, nr), nr, nb);
-                    while (__any_sync(tmask, ga.busy))
-                        if (ga.busy) { c.probe_row(ga.row(), sv, c64); ga.feed(a.rmi, sv, c64); }
-                    const bool okw = visit && !ga.hazard;
-                    RmiLower lb;
-                    if (okw) lb.begin(a.rmi, code, ga.lower, ga.upper, nr, nb);
-                    while (__any_sync(tmask, lb.busy))
-                        if (lb.busy) { c.probe_row(lb.row(), sv, c64); lb.feed(sv, c64); }
-                    RmiUpper ub;
-                    if (okw && lb.hi_eq) ub.begin(a.rmi, code, lb.hi, ga.upper, nr, nb);
-                    while (__any_sync(tmask, ub.busy))
-                        if (ub.busy) { c.probe_row(ub.row(), sv, c64); ub.feed(sv, c64); }
-                    if (okw) {
-                        literal = false;
-                        mlo = (int64_t)lb.hi;
-                        mhi = lb.hi_eq ? (int64_t)ub.lo : mlo - 1;
-                    }
-                }
-                if (__any_sync(tmask, literal)) {
-                    RmiSearch rs;
-                    if (literal) rs.begin(a.rmi, code, (int64_t)a.meta.n_rows, (int64_t)a.n_bases);
-                    for (;;) {
-                        const bool need = rs.pending();
-                        if (!__any_sync(tmask, need)) break;
-                        if (need) {
-                            int64_t sv;
-                            uint64_t code64;
-                            c.probe_row(rs.row(), sv, code64);
-                            rs.feed(sv, code64);
-                        }
-                    }
-                    if (literal) { mlo = rs.out_lo; mhi = rs.out_hi; }
-                    // the reference visits every window unless an earlier one raised: a raise anywhere is a raise of the read
-                    if (__any_sync(tmask, literal && rs.raised)) c.raised = true;
-                }
-            }
-            whit |= (__ballot_sync(tmask, visit && mhi >= mlo) >> tbase) << wb;
-            for (uint32_t t = 0; t < TEAM && wb + t < nwin; ++t) {
-                wlo[wb + t] = __shfl_sync(tmask, mlo, tbase + t);
-                whi[wb + t] = __shfl_sync(tmask, mhi, tbase + t);
-            }
-        }
-        if (c.raised) close_read(GSM_READ_REF_RAISES);        // pass 2
-        else Sel::round_finish(c, st, wlo, whi, whit);
-        __syncwarp(tmask);
     }
 }
 
@@ -595,6 +538,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_top(unsigned long long* t
     if (threadIdx.x == 0) *grand_total = carry;
 }
 
+__global__ void k_gather_advance(unsigned long long* base, const unsigned long long* rank_counts, uint32_t world) {
+    unsigned long long t = 0;
+    for (uint32_t r = 0; r < world; ++r) t += rank_counts[r];
+    *base += t;
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(unsigned long long* off, uint64_t n, const unsigned long long* tile_sums, const unsigned long long* grand_total) {
     const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
     const unsigned long long add = tile_sums[blockIdx.x];
@@ -604,14 +553,21 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(unsigned long long* o
     if (blockIdx.x == 0 && threadIdx.x == 0) off[n] = *grand_total;
 }
 
+// Records in (read, emission) order.  `out` may be another GPU's memory (gsm_peer_open): then these stores ARE the
+// gather of the multi-GPU path, over NVLink.  The batch's first record goes to out[*base + sum(rank_counts[0..rank))]:
+// rank_counts = the all-gathered per-rank record counts of this batch, *base = records of earlier batches (both device
+// memory, either may be NULL = 0), so no host round trip sits between the selection and the write.
 __global__ void k_gather_records(const uint4* rec_tmp, const uint32_t* tmp_off, const uint32_t* cnt, const unsigned long long* off,
-                                 uint64_t n_reads, uint4* out, unsigned long long out_cap, unsigned long long* counters) {
+                                 uint64_t n_reads, uint4* out, unsigned long long out_cap, unsigned long long* counters,
+                                 const unsigned long long* rank_counts, uint32_t rank, const unsigned long long* base) {
     // four lanes per read: records are 16 bytes, a read has a handful of them
     const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const uint32_t ql = threadIdx.x & 3u;
     if (q >= n_reads) return;
+    unsigned long long first = base ? *base : 0ull;
+    for (uint32_t r = 0; rank_counts && r < rank; ++r) first += rank_counts[r];
     const uint32_t n = cnt[q];
-    const unsigned long long dst = off[q];
+    const unsigned long long dst = first + off[q];
     if (dst + n > out_cap) { if (ql == 0 && n) atomicOr(&counters[2], 4ull); return; }
     const uint32_t src = tmp_off[q];
     for (uint32_t k = ql; k < n; k += 4) out[dst + k] = rec_tmp[(size_t)src + k];
@@ -713,7 +669,7 @@ __global__ void k_seed_build(const uint4* fwd, const uint4* rev, IndexMeta meta,
     auto lf = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
     auto lr = [rev](uint64_t idx) { return ldg_half(rev, idx); };
     uint32_t lo = 0, cnt = meta.n_rows, rlo = 0, rcnt = meta.n_rows;
-    for (uint32_t t = 0; t < K && cnt; ++t) {
+    for (uint32_t t = 0; t < K; ++t) {                                        // through empty intervals too: lo ends as the insertion point
         const uint32_t c = (uint32_t)(code >> (2 * t)) & 3u;                  // last base first
         const StepOut r = step_single(lf, lo, lo + cnt, c, meta.C[c], meta.prim_f);
         lo = r.lo_new; cnt = r.cnt_new;
@@ -822,6 +778,8 @@ uint64_t sweep_scratch_bytes(int blocks, uint32_t max_len) {
     return (uint64_t)blocks * SWEEP_GROUPS * 2ull * max_len * 16ull;
 }
 
+uint32_t select_stage_stride(uint32_t max_len) { return max_len < SELECT_STAGE ? max_len : SELECT_STAGE; }
+
 int select_grid(int* blocks) {          // upper bound over the selection kernels: sizes the per-thread record staging
     int dev = 0, sms = 0;
     GSM_CUDA(cudaGetDevice(&dev));
@@ -854,7 +812,7 @@ int gsm_smem_workspace_info(uint64_t n_reads, uint32_t max_len, gsm_workspace_in
     if ((st = sweep_grid(max_len, &sb))) return st;
     if ((st = select_grid(&lb))) return st;
     const uint64_t sweep_bytes = sweep_scratch_bytes(sb, max_len);
-    const uint64_t sel_bytes = (uint64_t)lb * SELECT_THREADS * (uint64_t)max_len * 16ull;
+    const uint64_t sel_bytes = (uint64_t)lb * SELECT_THREADS * (uint64_t)select_stage_stride(max_len) * 16ull;
     out->quad_scratch_bytes = sweep_bytes > sel_bytes ? sweep_bytes : sel_bytes;
     out->scan_tmp_bytes = ((n_reads + SCAN_TILE - 1) / SCAN_TILE + 2) * 8ull;
     out->grid_blocks = (uint32_t)sb;
@@ -1037,7 +995,7 @@ static int smem_check(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_work
     if ((st = sweep_grid(rd->max_len, sb))) return st;
     if ((st = select_grid(lb))) return st;
     const uint64_t need_sweep = sweep_scratch_bytes(*sb, rd->max_len);
-    const uint64_t need_sel = (uint64_t)*lb * SELECT_THREADS * (uint64_t)rd->max_len * 16ull;
+    const uint64_t need_sel = (uint64_t)*lb * SELECT_THREADS * (uint64_t)select_stage_stride(rd->max_len) * 16ull;
     if (ws->quad_scratch_bytes < need_sweep || ws->quad_scratch_bytes < need_sel) return fail(GSM_E_CAPACITY, "quad_scratch too small (see gsm_smem_workspace_info)");
     const uint64_t n_tiles = (rd->n_reads + SCAN_TILE - 1) / SCAN_TILE;
     if (ws->scan_tmp_bytes < (n_tiles + 2) * 8) return fail(GSM_E_CAPACITY, "scan_tmp too small");
@@ -1088,25 +1046,17 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
     se.reads = (const uint32_t*)rd->packed; se.chunk_off = rd->chunk_off; se.len = rd->len; se.n_reads = (uint32_t)rd->n_reads;
     se.max_len = rd->max_len; se.read_id_base = rd->read_id_base; se.min_len = min_len; se.K = K; se.lut = (const uint2*)lut; se.rmi = rm;
     se.seed_tab = (const uint4*)ix->seed_table; se.seed_K = ix->seed_table ? ix->seed_K : 0u;
-    se.mem_pool = (uint4*)ws->mem_pool; se.mem_off = ws->mem_off; se.mem_cnt = ws->mem_cnt; se.stage = (uint4*)ws->quad_scratch;
+    se.mem_pool = (uint4*)ws->mem_pool; se.mem_off = ws->mem_off; se.mem_cnt = ws->mem_cnt; se.stage = (uint4*)ws->quad_scratch; se.stage_stride = select_stage_stride(rd->max_len);
     se.rec_tmp = (uint4*)ws->rec_tmp; se.rec_cap = ws->rec_cap; se.rec_tmp_off = ws->rec_tmp_off; se.rec_cnt = ws->rec_cnt;
     se.read_status = ws->read_status; se.counters = (unsigned long long*)ws->counters;
     GSM_CUDA(cudaMemsetAsync((unsigned long long*)ws->counters + 1, 0, sizeof(uint64_t), stream));
-    // GSM_SELECT_TEAMS: bit 0 = LUT by teams, bit 1 = RMI by teams (measurement switch; results are identical)
-    static const int teams = getenv("GSM_SELECT_TEAMS") ? atoi(getenv("GSM_SELECT_TEAMS")) : 0;
     int grid = lb;
     if (method == GSM_METHOD_BWA) {
         if ((st = resident_grid(k_select<GSM_METHOD_BWA>, SELECT_THREADS, lb, &grid))) return st;
         k_select<GSM_METHOD_BWA><<<grid, SELECT_THREADS, 0, stream>>>(se);
-    } else if (method == GSM_METHOD_LUT && (teams & 1)) {
-        if ((st = resident_grid(k_select_team<GSM_METHOD_LUT>, SELECT_THREADS, lb, &grid))) return st;
-        k_select_team<GSM_METHOD_LUT><<<grid, SELECT_THREADS, 0, stream>>>(se);
     } else if (method == GSM_METHOD_LUT) {
-        if ((st = resident_grid(k_select<GSM_METHOD_LUT>, SELECT_THREADS, lb, &grid))) return st;
-        k_select<GSM_METHOD_LUT><<<grid, SELECT_THREADS, 0, stream>>>(se);
-    } else if (teams & 2) {
-        if ((st = resident_grid(k_select_team<GSM_METHOD_RMI>, SELECT_THREADS, lb, &grid))) return st;
-        k_select_team<GSM_METHOD_RMI><<<grid, SELECT_THREADS, 0, stream>>>(se);
+        if ((st = resident_grid(k_select_seeded<GSM_METHOD_LUT>, SELECT_THREADS, lb, &grid))) return st;
+        k_select_seeded<GSM_METHOD_LUT><<<grid, SELECT_THREADS, 0, stream>>>(se);
     } else {
         if ((st = resident_grid(k_select_seeded<GSM_METHOD_RMI>, SELECT_THREADS, lb, &grid))) return st;
         k_select_seeded<GSM_METHOD_RMI><<<grid, SELECT_THREADS, 0, stream>>>(se);
@@ -1136,7 +1086,30 @@ int gsm_smem_collect(const gsm_dev_reads* rd, gsm_workspace* ws, gsm_record* out
     const uint64_t threads = rd->n_reads * 4;
     k_gather_records<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)ws->rec_tmp, ws->rec_tmp_off, ws->rec_cnt, (const unsigned long long*)ws->rec_off, rd->n_reads, (uint4*)out, out_cap,
-        (unsigned long long*)ws->counters);
+        (unsigned long long*)ws->counters, nullptr, 0u, nullptr);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_smem_collect_gathered(const gsm_dev_reads* rd, gsm_workspace* ws, gsm_record* out, uint64_t out_cap, const uint64_t* counts_dev,
+                              uint32_t rank, const uint64_t* base_dev, void* stream) {
+    if (!rd || !ws || (!out && out_cap)) return fail(GSM_E_INVALID, "null");
+    int st = device_ready();
+    if (st) return st;
+    if (rd->n_reads == 0) return GSM_OK;
+    const uint64_t threads = rd->n_reads * 4;
+    k_gather_records<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)ws->rec_tmp, ws->rec_tmp_off, ws->rec_cnt, (const unsigned long long*)ws->rec_off, rd->n_reads, (uint4*)out, out_cap,
+        (unsigned long long*)ws->counters, (const unsigned long long*)counts_dev, rank, (const unsigned long long*)base_dev);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_gather_advance(uint64_t* base_dev, const uint64_t* counts_dev, uint32_t world, void* stream) {
+    if (!base_dev || !counts_dev || world == 0) return fail(GSM_E_INVALID, "gsm_gather_advance: null");
+    int st = device_ready();
+    if (st) return st;
+    k_gather_advance<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)base_dev, (const unsigned long long*)counts_dev, world);
     GSM_CUDA(cudaGetLastError());
     return GSM_OK;
 }

@@ -478,16 +478,113 @@ GSM_HD bool rmi_fast_lookup(Probe& probe, const RmiModel& m, uint64_t code, uint
     return true;
 }
 
+// Any None row of get_ref_seq (the K short suffixes) inside rows [a, b]?  Bitmap over 1024 regions first, exact list second.
+GSM_HD bool rmi_none_in_range(const RmiModel& m, uint32_t a, uint32_t b) {
+    const uint32_t ra = a >> m.none_shift, rb = b >> m.none_shift;
+    if (rb - ra <= 1u && !((m.none_map[ra >> 5] >> (ra & 31u)) & 1u) && !((m.none_map[rb >> 5] >> (rb & 31u)) & 1u)) return false;
+    bool hit = false;
+    for (uint32_t t = 0; t < m.n_none; ++t) hit |= (m.none_rows[t] >= a && m.none_rows[t] <= b);
+    return hit;
+}
+
+// The error-bounded search WITHOUT probes, for a k-mer whose true bounds are already known from the FM index
+// (seed-table entry of its last seed_K bases + K - seed_K backward steps, continued through empty intervals so that an
+// absent k-mer still yields its insertion point): A = number of rows whose suffix is smaller than q (first row >= q),
+// B = A + occurrences (first row > q).  Rows are sorted, so a probed non-None row r compares as  k-mer[r] < q <=> r < A  and
+// k-mer[r] > q <=> r >= B: the exponential phase of RMI_LUT.exponential_search (RMI_LUT.py:136-184) is replayed on row
+// NUMBERS alone -- same probe rows as RmiGallop, no table fetch -- which yields the bracket the literal search would
+// reach.  If no None row lies between the lowest and the highest probed row (they enclose the bracket) and neither
+// bracket end stays at its default, both binary searches of the literal algorithm return the exact bounds (see
+// RmiGallop): lo = A, hi = B - 1 (hi = lo - 1 <=> absent).  Otherwise: hazard, the caller runs the literal search.
+// row0 = RmiGallop::predicted_row.  Returns false on a hazard.
+GSM_HD bool rmi_arith_lookup(const RmiModel& m, int64_t row0, uint32_t A, uint32_t cnt, uint32_t n_rows, int64_t& lo, int64_t& hi) {
+    if (row0 < 0) return false;                                   // prediction outside the table
+    const uint32_t start = (uint32_t)row0, B = A + cnt;
+    bool have_lower = start < A, have_upper = start >= B;
+    uint32_t rmin = start, rmax = start;
+    for (uint32_t w = 1; !have_upper && (uint64_t)start + w < n_rows && w != 0u; w <<= 1) {      // RMI_LUT.py:151-163
+        rmax = start + w;
+        have_upper = rmax >= B;
+        have_lower |= rmax < A;
+    }
+    for (uint32_t w = 1; !have_lower && start >= w && w != 0u; w <<= 1) {                         // RMI_LUT.py:166-178
+        rmin = start - w;
+        have_lower = rmin < A;
+        have_upper |= rmin >= B;
+    }
+    if (!have_lower || !have_upper) return false;                 // a default bracket end
+    if (rmi_none_in_range(m, rmin, rmax)) return false;           // a None row probed or inside the bracket
+    lo = (int64_t)A;
+    hi = (int64_t)B - 1;
+    return true;
+}
+
+// True bounds (A, occurrences) of the K-mer q[cpos:cpos+K) from the sweep's seed table: entry of its last seed_K bases,
+// then K - seed_K backward steps.  The table stores the insertion point in fwd_lo for absent k-mers (cnt == 0) and a
+// backward step on an empty interval keeps tracking it, so (A, 0) is exact for absent k-mers too.
+// rd(w) = packed read word w; load(i) = i-th 32-byte bucket half; seed(code) = table entry.  Needs seed_K <= K.
+template <typename ReadW, typename LoadHalf, typename LoadSeed>
+GSM_HD void kmer_bounds_seeded(ReadW rd, LoadHalf load, LoadSeed seed, const IndexMeta& meta, uint32_t cpos, uint32_t K, uint32_t seed_K,
+                               uint32_t& A, uint32_t& cnt) {
+    const U4 e = seed(kmer_code(rd, (uint64_t)cpos + K - seed_K, seed_K));
+    A = e.x; cnt = e.y;
+    for (uint32_t p = cpos + K - seed_K; p > cpos; --p) {
+        const uint32_t w = rd((p - 1) >> 4);
+        const uint32_t c = (w >> (30u - 2u * ((p - 1) & 15u))) & 3u;
+        const StepOut r = step_single(load, A, A + cnt, c, meta.C[c], meta.prim_f);
+        A = r.lo_new; cnt = r.cnt_new;
+    }
+}
+
+// check_sequential (SMEM.py:196-202) on the positions of two RETURNED intervals [clo, chi] and [plo, phi] (SMEM.py:262-265),
+// which may be wrong: is there x in the first and y in the second with suffix_array[x] + 1 == suffix_array[y]?
+// suffix_array[x] + 1 == suffix_array[y]  <=>  x == LF(y), and LF maps the rows of [plo, phi] whose BWT symbol is b onto the
+// contiguous rows C[b] + rank(b, plo) .. C[b] + rank(b, phi + 1) - 1: four rank pairs on the same two buckets, O(1) whatever
+// the interval sizes (a poly-A k-mer on a human-scale text has 10^5..10^6 rows; the literal double loop would be 10^10+
+// dependent suffix-array reads in one thread).  The '$' row has no predecessor and is excluded by the rank correction.
+// Rows outside [0, n) (Python negative indexing of a wrong interval) take the literal loop, as the reference does.
+template <typename LoadHalf, typename LoadSa>
+GSM_HD bool rmi_sequential(LoadHalf load, LoadSa sa, const IndexMeta& meta, int64_t clo, int64_t chi, int64_t plo, int64_t phi) {
+    const int64_t n = (int64_t)meta.n_rows;
+    if (clo >= 0 && plo >= 0 && chi < n && phi < n) {
+        if (chi < clo || phi < plo) return false;
+        for (uint32_t b = 0; b < 4u; ++b) {
+            const StepOut r = step_single(load, (uint32_t)plo, (uint32_t)phi + 1u, b, meta.C[b], meta.prim_f);
+            if (r.cnt_new != 0u && (int64_t)r.lo_new <= chi && (int64_t)r.lo_new + r.cnt_new - 1 >= clo) return true;
+        }
+        return false;
+    }
+    for (int64_t x = clo; x <= chi; ++x) {
+        const uint32_t px = sa((uint64_t)(x < 0 ? x + n : x));
+        for (int64_t y = plo; y <= phi; ++y)
+            if (px + 1u == sa((uint64_t)(y < 0 ? y + n : y))) return true;
+    }
+    return false;
+}
+
+// check_sequential on two TRUE k-mer intervals (LUT entries, or RMI lookups proven exact): some occurrence of q[c:c+K) is
+// followed one base later by q[pc:pc+K)  <=>  the k-mers overlap consistently and q[c] + q[pc:pc+K) occurs (one backward
+// step on the second seed).
+template <typename Base, typename LoadHalf>
+GSM_HD bool true_sequential(Base base, LoadHalf load, const IndexMeta& meta, uint32_t K, uint32_t c, uint32_t pc, int64_t plo, int64_t phi) {
+    for (uint32_t t = 1; t < K; ++t)
+        if (base(c + t) != base(pc + t - 1)) return false;
+    const uint32_t ch = base(c);
+    const StepOut r = step_single(load, (uint32_t)plo, (uint32_t)phi + 1u, ch, meta.C[ch], meta.prim_f);
+    return r.cnt_new != 0;
+}
+
 // ------------------------------------------------------------------------------------ selection
 // Ctx must provide:
 //   uint32_t L, K, n_mems;  uint32_t min_len;
 //   MemEntry mem(uint32_t k)                 k-th maximal match, sorted by end (and start)
 //   uint32_t base(uint32_t pos)
-//   uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi)
+//   uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi, uint32_t& wtrue)
 //                                            LUT / RMI lookups of the windows of one round: window i covers
 //                                            q[c:c+K), c = first ? 0 : e - i, and is visited iff first or
-//                                            (i < plen and c + K <= L); bit i of the result = hit
-//   bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi)
+//                                            (i < plen and c + K <= L); bit i of the result = hit; bit i of wtrue =
+//                                            the stored pair is the k-mer's TRUE interval (LUT: always)
+//   bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi, bool both_true)
 //                                            check_sequential of the two seeds (SMEM.py:196-202)
 //   void interval(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt)   true SA interval of q[i:j]
 //   void emit(uint32_t i, uint32_t j, int64_t lo, int64_t hi)
@@ -546,15 +643,20 @@ struct Selector {
         }
     }
 
+    // A candidate record of the frame machine.  Only LENGTHS decide which candidate survives (SMEM.py replaces on >=), so
+    // the SA interval of a candidate that is neither a seed tuple nor an entry of the match list is left unresolved
+    // (lazy) and computed once, for the round's winner only (resolve): at most one explicit backward search per record.
     struct Cand {
-        bool valid;
+        bool valid, lazy;
         uint32_t i, j;
         int64_t lo, hi;
     };
 
-    GSM_HD static void upd(Cand& cd, uint32_t i, uint32_t j, int64_t lo, int64_t hi) {
-        if (!cd.valid || (j - i) >= (cd.j - cd.i)) { cd.valid = true; cd.i = i; cd.j = j; cd.lo = lo; cd.hi = hi; }
+    GSM_HD static void upd(Cand& cd, const Cand& x) {
+        if (!cd.valid || (x.j - x.i) >= (cd.j - cd.i)) cd = x;
     }
+    GSM_HD static Cand known(uint32_t i, uint32_t j, int64_t lo, int64_t hi) { return Cand{true, false, i, j, lo, hi}; }
+    GSM_HD static Cand lazy_iv(uint32_t i, uint32_t j) { return Cand{true, true, i, j, 0, -1}; }
 
     // F(p) restricted to true matches = end of the last match starting at or before p; 0 such matches => p
     // (cannot happen when all four bases occur)
@@ -566,29 +668,39 @@ struct Selector {
     }
 
     // True SA interval of q[i:j): read it off the match list when (i, j) is itself a maximal match
-    // (the usual case), otherwise one backward search from j down to i.
-    GSM_HD static void true_iv(Ctx& c, uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt) {
+    // (the usual case); false = one backward search from j down to i is needed (Ctx::interval).
+    GSM_HD static bool listed_iv(Ctx& c, uint32_t i, uint32_t j, int64_t& lo, int64_t& hi) {
         const uint32_t k = j ? first_end_above(c, j - 1) : 0u;
         if (k < c.n_mems) {
             MemEntry m = c.mem(k);
-            if (e_of(m) == j && s_of(m) == i) { lo = m.lo; cnt = m.cnt; return; }
+            if (e_of(m) == j && s_of(m) == i) { lo = (int64_t)m.lo; hi = (int64_t)m.lo + m.cnt - 1; return true; }
         }
-        c.interval(i, j, lo, cnt);
+        return false;
+    }
+
+    // winner of a round -> its interval.  Returns true if cd still needs Ctx::interval(cd.i, cd.j) (explicit search).
+    GSM_HD static bool resolve(Ctx& c, Cand& cd) {
+        if (!cd.lazy) return false;
+        if (listed_iv(c, cd.i, cd.j, cd.lo, cd.hi)) { cd.lazy = false; return false; }
+        return true;
+    }
+    GSM_HD static void resolve_now(Ctx& c, Cand& cd) {
+        if (!resolve(c, cd)) return;
+        uint32_t l, n;
+        c.interval(cd.i, cd.j, l, n);
+        cd.lo = (int64_t)l; cd.hi = (int64_t)l + n - 1; cd.lazy = false;
     }
 
     // forward_extension(query, pc+K, kmer, seed) (SMEM.py:425-443): longest key and its value
-    GSM_HD static void fwd_only(Ctx& c, uint32_t pc, int64_t slo, int64_t shi, uint32_t& end, int64_t& lo, int64_t& hi) {
-        uint32_t f = F_of(c, pc);
-        if (f <= pc + c.K) { end = pc + c.K; lo = slo; hi = shi; return; }   // the seed key itself
-        end = f;
-        uint32_t l, n;
-        true_iv(c, pc, f, l, n);
-        lo = (int64_t)l; hi = (int64_t)l + n - 1;
+    GSM_HD static Cand fwd_only(Ctx& c, uint32_t pc, int64_t slo, int64_t shi) {
+        const uint32_t f = F_of(c, pc);
+        if (f <= pc + c.K) return known(pc, pc + c.K, slo, shi);     // the seed key itself
+        return lazy_iv(pc, f);
     }
 
     // backward_extension(query, pc, keys) (SMEM.py:389-423) over keys pc+K .. max(F(pc), pc+K)
     // (all_keys) or over the seed key only.
-    GSM_HD static void bext(Ctx& c, uint32_t pc, int64_t slo, int64_t shi, bool all_keys, Cand& out) {
+    GSM_HD static Cand bext(Ctx& c, uint32_t pc, int64_t slo, int64_t shi, bool all_keys) {
         const uint32_t K = c.K;
         uint32_t f = F_of(c, pc);
         const bool seed_true = f >= pc + K;           // the k-mer really occurs
@@ -614,14 +726,11 @@ struct Selector {
         // the longest key wins only if strictly longer (SMEM.py:418)
         uint32_t fend = jmax;
         if (!have || (fend - pc) > (bj - bi)) {
-            out.valid = true; out.i = pc; out.j = fend;
-            if (fend == pc + K) { out.lo = slo; out.hi = shi; }
-            else { uint32_t l, n; true_iv(c, pc, fend, l, n); out.lo = (int64_t)l; out.hi = (int64_t)l + n - 1; }
-            return;
+            if (fend == pc + K) return known(pc, fend, slo, shi);
+            return lazy_iv(pc, fend);
         }
-        out.valid = true; out.i = bi; out.j = bj;
-        if (!b_from_mem) true_iv(c, bi, bj, blo, bcnt);
-        out.lo = (int64_t)blo; out.hi = (int64_t)blo + bcnt - 1;
+        if (!b_from_mem) return lazy_iv(bi, bj);
+        return known(bi, bj, (int64_t)blo, (int64_t)blo + bcnt - 1);
     }
 
     // get_smems_lut / get_smems_rmi: the frame machine of SMEM.py:49-186 / :235-379, one ROUND at a time.  A round =
@@ -629,7 +738,8 @@ struct Selector {
     //   Pass 1 (Ctx::seed_round): the lookups of ALL windows of the round.  The reference visits every window whatever
     //   the earlier ones returned (no early exit in SMEM.py:56-146), so the lookups can be taken out of the machine and
     //   run where the threads of a warp are together (k_select_seeded keeps a warp in lock step on them).
-    //   Pass 2 (round_finish): the machine over the stored results.
+    //   Pass 2 (round_decide): the machine over the stored results -> the round's winner, its interval possibly lazy.
+    //   Pass 3 (resolve + Ctx::interval, at most one explicit backward search) and round_commit (emit, advance).
     struct Seeded {
         bool first = true, done = false;
         uint32_t e = 0, plen = 0;
@@ -645,91 +755,90 @@ struct Selector {
         Seeded st;
         int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
         while (round_needed(c, st)) {
-            const uint32_t whit = c.seed_round(st.first, st.e, st.plen, st.first ? 1u : c.K, wlo, whi);
+            uint32_t wtrue = 0;
+            const uint32_t whit = c.seed_round(st.first, st.e, st.plen, st.first ? 1u : c.K, wlo, whi, wtrue);
             if (c.failed()) return;
-            round_finish(c, st, wlo, whi, whit);
+            round_finish(c, st, wlo, whi, whit, wtrue);
         }
     }
 
-    GSM_HD static void round_finish(Ctx& c, Seeded& st, const int64_t* wlo, const int64_t* whi, uint32_t whit) {
+    GSM_HD static void round_finish(Ctx& c, Seeded& st, const int64_t* wlo, const int64_t* whi, uint32_t whit, uint32_t wtrue) {
+        Cand w = round_decide(c, st, wlo, whi, whit, wtrue);
+        if (w.valid) resolve_now(c, w);
+        round_commit(c, st, w);
+    }
+
+    // emit the round's winner and advance; an invalid winner ends the read (no match covers e: only when a base of the read
+    // is absent from the text, outside the reference's domain)
+    GSM_HD static void round_commit(Ctx& c, Seeded& st, const Cand& w) {
+        if (!w.valid) { st.done = true; return; }
+        c.emit(w.i, w.j, w.lo, w.hi);
+        st.first = false;
+        st.e = w.j; st.plen = w.j - w.i;
+    }
+
+    // wtrue: bit i set = (wlo[i], whi[i]) is the TRUE interval of window i's k-mer (always for LUT; for RMI when the lookup
+    // was proven exact), which lets check_sequential be evaluated in closed form.
+    GSM_HD static Cand round_decide(Ctx& c, const Seeded& st, const int64_t* wlo, const int64_t* whi, uint32_t whit, uint32_t wtrue) {
         const uint32_t K = c.K, L = c.L;
-        const bool first = st.first;
-        uint32_t e = st.e, plen = st.plen;
-        {
-            // frame: 0 = None, 1 = () , 2 = k-mer frame
-            int fstate = 0;
-            uint32_t pc = 0; bool pfw = false; int64_t plo = 0, phi = -1;
-            Cand cd; cd.valid = false; cd.i = cd.j = 0; cd.lo = 0; cd.hi = -1;
-            const uint32_t pstart = e - plen;
-            const uint32_t nwin = first ? 1u : K;
-            // Pass 2: the frame machine over the stored results
-            for (uint32_t i = 0; i < nwin; ++i) {
-                uint32_t cpos;
-                if (first) cpos = 0;
-                else {
-                    if (i >= plen) continue;
-                    cpos = e - i;
-                    if (cpos + K > L) continue;
-                }
-                const int64_t lo = wlo[i], hi = whi[i];
-                const bool hit = (whit >> i) & 1u;
-                if (first) {                                   // SMEM.py:26-39 / :213-225
-                    uint32_t end; int64_t flo, fhi;
-                    if (hit) fwd_only(c, 0, lo, hi, end, flo, fhi);
-                    else {
-                        end = F_of(c, 0);
-                        uint32_t l, n; true_iv(c, 0, end, l, n); flo = (int64_t)l; fhi = (int64_t)l + n - 1;
-                    }
-                    c.emit(0, end, flo, fhi);
-                    e = end; plen = end;
-                    break;
-                }
-                if (hit) {
-                    if (fstate == 0) { fstate = 2; pc = cpos; pfw = true; plo = lo; phi = hi; }          // :70
-                    else if (fstate == 1) { fstate = 2; pc = cpos; pfw = false; plo = lo; phi = hi; }    // :73
-                    else {
-                        // check_sequential of two TRUE k-mer intervals at adjacent windows is just
-                        // "q[cpos : cpos+K+1) occurs" (SURVEY A13): read it off the match list
-                        const bool seq = (c.seeds_are_true() && pc == cpos + 1) ? (F_of(c, cpos) >= cpos + K + 1)
-                                                                               : c.sequential(cpos, lo, hi, pc, plo, phi);
-                        if (seq) {                                                                        // Case 1
-                            if (pfw) { Cand b; bext(c, pc, plo, phi, true, b); upd(cd, b.i, b.j, b.lo, b.hi); }
-                            else {
-                                if (cd.valid && (pc - pstart) + K < (cd.j - cd.i)) continue;              // :94-95
-                                Cand b; bext(c, pc, plo, phi, false, b); upd(cd, b.i, b.j, b.lo, b.hi);
-                            }
-                        } else {                                                                          // Case 2
-                            if (pfw) { uint32_t end; int64_t flo, fhi; fwd_only(c, pc, plo, phi, end, flo, fhi); upd(cd, pc, end, flo, fhi); }
-                            else upd(cd, cpos, cpos + K, lo, hi);
-                        }
-                        pc = cpos; pfw = false; plo = lo; phi = hi;
-                    }
-                } else {
-                    if (fstate == 2) {                                                                    // Case 3
-                        if (pfw) { uint32_t end; int64_t flo, fhi; fwd_only(c, pc, plo, phi, end, flo, fhi); upd(cd, pc, end, flo, fhi); }
-                        else upd(cd, pc, pc + K, plo, phi);
-                    }
-                    fstate = 1;
-                }
-            }
-            if (first) { st.first = false; st.e = e; st.plen = plen; return; }
-            if (fstate == 2) {                                                                            // :149-171
-                Cand b; bext(c, pc, plo, phi, pfw, b); upd(cd, b.i, b.j, b.lo, b.hi);
-            }
-            if (!cd.valid) {                                                                              // :175-179
-                uint32_t from = 0;
-                uint32_t b = covering_best(c, e, from);
-                if (b >= c.n_mems) { st.done = true; return; }
-                MemEntry m = c.mem(b);
-                c.emit(s_of(m), e_of(m), (int64_t)m.lo, (int64_t)m.lo + m.cnt - 1);
-                plen = e_of(m) - s_of(m);
-                e = e_of(m);
-            } else {
-                c.emit(cd.i, cd.j, cd.lo, cd.hi);
-                e = cd.j; plen = cd.j - cd.i;
-            }
-            st.e = e; st.plen = plen;
+        const uint32_t e = st.e, plen = st.plen;
+        if (st.first) {                                    // SMEM.py:26-39 / :213-225
+            if (whit & 1u) return fwd_only(c, 0, wlo[0], whi[0]);
+            const uint32_t end = F_of(c, 0);
+            if (end == 0) return Cand{false, false, 0, 0, 0, -1};
+            return lazy_iv(0, end);
         }
+        // frame: 0 = None, 1 = () , 2 = k-mer frame
+        int fstate = 0;
+        uint32_t pc = 0; bool pfw = false, ptrue = false; int64_t plo = 0, phi = -1;
+        Cand cd{false, false, 0, 0, 0, -1};
+        const uint32_t pstart = e - plen;
+        // Pass 2: the frame machine over the stored results
+        for (uint32_t i = 0; i < K; ++i) {
+            if (i >= plen) continue;
+            const uint32_t cpos = e - i;
+            if (cpos + K > L) continue;
+            const int64_t lo = wlo[i], hi = whi[i];
+            const bool hit = (whit >> i) & 1u;
+            const bool tru = (wtrue >> i) & 1u;
+            if (hit) {
+                if (fstate == 0) { fstate = 2; pc = cpos; pfw = true; plo = lo; phi = hi; ptrue = tru; }          // :70
+                else if (fstate == 1) { fstate = 2; pc = cpos; pfw = false; plo = lo; phi = hi; ptrue = tru; }    // :73
+                else {
+                    // check_sequential of two TRUE k-mer intervals at adjacent windows is just
+                    // "q[cpos : cpos+K+1) occurs" (SURVEY A13): read it off the match list
+                    const bool both = tru && ptrue;
+                    const bool seq = (both && pc == cpos + 1) ? (F_of(c, cpos) >= cpos + K + 1)
+                                                              : c.sequential(cpos, lo, hi, pc, plo, phi, both);
+                    if (seq) {                                                                        // Case 1
+                        if (pfw) upd(cd, bext(c, pc, plo, phi, true));
+                        else {
+                            if (cd.valid && (pc - pstart) + K < (cd.j - cd.i)) continue;              // :94-95
+                            upd(cd, bext(c, pc, plo, phi, false));
+                        }
+                    } else {                                                                          // Case 2
+                        if (pfw) upd(cd, fwd_only(c, pc, plo, phi));
+                        else upd(cd, known(cpos, cpos + K, lo, hi));
+                    }
+                    pc = cpos; pfw = false; plo = lo; phi = hi; ptrue = tru;
+                }
+            } else {
+                if (fstate == 2) {                                                                    // Case 3
+                    if (pfw) upd(cd, fwd_only(c, pc, plo, phi));
+                    else upd(cd, known(pc, pc + K, plo, phi));
+                }
+                fstate = 1;
+            }
+        }
+        if (fstate == 2) upd(cd, bext(c, pc, plo, phi, pfw));                                         // :149-171
+        if (!cd.valid) {                                                                              // :175-179
+            uint32_t from = 0;
+            const uint32_t b = covering_best(c, e, from);
+            if (b >= c.n_mems) return cd;
+            const MemEntry m = c.mem(b);
+            return known(s_of(m), e_of(m), (int64_t)m.lo, (int64_t)m.lo + m.cnt - 1);
+        }
+        return cd;
     }
 };
 

@@ -514,10 +514,18 @@ class RmiParams:
 
 
 class SmemResult:
-    """Records of one batch in (read, emission) order + CSR offsets per read."""
+    """Records of one batch in (read, emission) order + CSR offsets per read.
+
+    Lifetime: by default the arrays are the caller's own copies.  With reuse_host_buffers=True (Engine.run /
+    PipelinedEngine.run*) they are VIEWS of the engine's pinned staging buffers and are overwritten by that engine's
+    next run -- the zero-copy mode bench.py times; copy what you keep."""
 
     def __init__(self, records, offsets, status, n_mems):
         self.records, self.offsets, self.status, self.n_mems = records, offsets, status, n_mems
+
+    def detach(self):
+        self.records, self.offsets, self.status = self.records.copy(), self.offsets.copy(), self.status.copy()
+        return self
 
     def for_read(self, i):
         return self.records[self.offsets[i]:self.offsets[i + 1]]
@@ -576,17 +584,27 @@ class Engine:
         capi.check(capi.lib.gsm_smem_sweep(C.byref(self.index.c), C.byref(r), C.byref(self.ws), _stream()))
         self.kernel_launches += 1 if reads.n else 0
 
-    def select(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None):
-        """k_select + scan + gather: the reference's records for one method, in (read, emission) order."""
+    def select(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None, gatherer=None):
+        """k_select + scan + ordered write: the reference's records for one method, in (read, emission) order -- into
+        this engine's `records` buffer, or with a sharding.RecordGatherer straight into the gathering rank's HBM."""
         r = self._check_batch(reads)
         capi.check(capi.lib.gsm_smem_select(method, C.byref(self.index.c), C.byref(r), int(min_len), int(K), _ptr(lut),
                                             C.byref(rmi.c) if rmi is not None else None, C.byref(self.ws), _stream()))
+        if gatherer is not None:
+            gatherer.collect(self, r)                  # collective: every rank calls it, empty batches included
+            self.kernel_launches += (6 if reads.n else 2)
+            return
         capi.check(capi.lib.gsm_smem_collect(C.byref(r), C.byref(self.ws), _ptr(self.records), self.rec_cap, _stream()))
-        self.kernel_launches += 5 if reads.n else 0    # select, 3 scan kernels, gather
+        self.kernel_launches += 5 if reads.n else 0    # select, 3 scan kernels, ordered write
 
-    def launch(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None):
+    def collect_local(self, reads: ReadBatch):
+        """(Re)write the records of the batch just selected into this engine's own `records` buffer."""
+        r = self._check_batch(reads)
+        capi.check(capi.lib.gsm_smem_collect(C.byref(r), C.byref(self.ws), _ptr(self.records), self.rec_cap, _stream()))
+
+    def launch(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None, gatherer=None):
         self.sweep(reads)
-        self.select(method, reads, min_len, K, lut, rmi)
+        self.select(method, reads, min_len, K, lut, rmi, gatherer)
 
     def check_overflow(self):
         c = self.counters.cpu().numpy()
@@ -603,7 +621,7 @@ class Engine:
         return buf
 
     # -- end-to-end step: host reads in (H2D), host records out (D2H)
-    def run(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None, grow=True):
+    def run(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None, grow=True, reuse_host_buffers=False):
         reads.to(self.device, non_blocking=True)
         while True:
             self.launch(method, reads, min_len, K, lut, rmi)
@@ -625,7 +643,8 @@ class Engine:
         self.last_d2h_bytes = n_rec * 16 + (n + 1) * 8 + n + 64
         recs = hrec.numpy()[: n_rec * 16].view(RECORD_DTYPE)
         offs = hoff.numpy()[: (n + 1) * 8].view(np.int64)
-        return SmemResult(recs, offs, hst.numpy()[:n], n_mems)
+        res = SmemResult(recs, offs, hst.numpy()[:n], n_mems)
+        return res if reuse_host_buffers else res.detach()
 
     def _grow(self):
         dev = self.device
@@ -785,8 +804,9 @@ class PipelinedEngine:
         mid = list(range(head[-1] + c, tail[0], c))
         return head + mid + tail
 
-    def run(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None):
-        """Packed host reads in (pinned), host records out."""
+    def run(self, method, reads: ReadBatch, min_len=1, K=0, lut=None, rmi: RmiParams = None, reuse_host_buffers=False, gatherer=None):
+        """Packed host reads in (pinned), host records out -- or, with a sharding.RecordGatherer, records written straight
+        into the gathering rank's HBM (the result then carries offsets and status only)."""
         n = reads.n
         if n > self.max_reads or reads.max_len > self.max_len:
             raise ValueError("batch exceeds the engine's workspace")
@@ -805,9 +825,11 @@ class PipelinedEngine:
             reads.len[lo:hi].copy_(hln[lo:hi], non_blocking=True)
 
         self.last_h2d_bytes = reads.h2d_bytes()
-        return self._run_chunks(method, n, copy_in, lambda lo, hi: _ReadView(reads, lo, hi), min_len, K, lut, rmi)
+        res = self._run_chunks(method, n, copy_in, lambda lo, hi: _ReadView(reads, lo, hi), min_len, K, lut, rmi, gatherer)
+        return res if reuse_host_buffers else res.detach()
 
-    def run_ascii(self, method, bases, read_len, min_len=1, K=0, lut=None, rmi: RmiParams = None, read_id_base=0):
+    def run_ascii(self, method, bases, read_len, min_len=1, K=0, lut=None, rmi: RmiParams = None, read_id_base=0, reuse_host_buffers=False,
+                  gatherer=None):
         """RAW read bytes in, host records out: `bases` is a pinned uint8 tensor of n x read_len ASCII characters
         (what a FASTQ parser hands over).  Each chunk crosses PCIe as 1 byte/base and is 2-bit packed on the GPU
         (gsm_pack_reads_device) right before its sweep.  Raises BaseError if a read holds a non-ACGT character
@@ -844,15 +866,17 @@ class PipelinedEngine:
             return _ReadView(holder, lo, hi)
 
         self.last_h2d_bytes = n * read_len
-        res = self._run_chunks(method, n, copy_in, prep, min_len, K, lut, rmi)
+        res = self._run_chunks(method, n, copy_in, prep, min_len, K, lut, rmi, gatherer)
         b = bad.cpu().numpy()[: len(slot)]
         if (b != -1).any():
             k = int(np.nonzero(b != -1)[0][0])
             raise BaseError(f"non-ACGT base in read {slot[k] + int(b[k])}")
-        return res
+        return res if reuse_host_buffers else res.detach()
 
-    def _run_chunks(self, method, n, copy_in, prep, min_len, K, lut, rmi):
-        bounds = self._chunk_bounds(n)
+    def _run_chunks(self, method, n, copy_in, prep, min_len, K, lut, rmi, gatherer=None):
+        # with a gatherer every chunk holds a collective: all ranks must cut the same number of chunks, so the bounds are
+        # those of the engine's capacity (equal on all ranks), clipped to this rank's read count
+        bounds = [min(b, n) for b in self._chunk_bounds(self.max_reads)] if gatherer is not None else self._chunk_bounds(n)
         n_ch = len(bounds) - 1
         est = self.engines[0].rec_cap * 16
         out_rec = self._buf(self._pin, "rec", max(est, 1 << 20), True)
@@ -894,7 +918,8 @@ class PipelinedEngine:
                 self._pin["rec"] = grown
             eng = self.engines[e]
             with torch.cuda.stream(self.s_out):                # the host has seen ev: the chunk's kernels are done
-                out_rec[rec_total * 16:(rec_total + n_rec) * 16].copy_(eng.records[: n_rec * 16], non_blocking=True)
+                if gatherer is None:
+                    out_rec[rec_total * 16:(rec_total + n_rec) * 16].copy_(eng.records[: n_rec * 16], non_blocking=True)
                 if rec_total:                                  # chunk-local offsets -> global offsets, on the device
                     eng.rec_off[: hi - lo].add_(rec_total)
                 out_off[lo * 8:hi * 8].copy_(eng.rec_off[: hi - lo].view(torch.uint8), non_blocking=True)
@@ -916,7 +941,7 @@ class PipelinedEngine:
                 if i - 2 in ev_out:
                     self.s_comp.wait_event(ev_out[i - 2])
                 view = prep(lo, hi)
-                eng.launch(method, view, min_len, K, lut, rmi)
+                eng.launch(method, view, min_len, K, lut, rmi, gatherer)
                 self._cnt_pin[e].copy_(eng.counters, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self.s_comp)
@@ -929,6 +954,6 @@ class PipelinedEngine:
         offs = out_off.numpy()[: (n + 1) * 8].view(np.int64)
         offs[n] = rec_total
         self.kernel_launches = sum(e.kernel_launches for e in self.engines) + self.pack_launches
-        self.last_d2h_bytes = rec_total * 16 + (n + 1) * 8 + n + 64 * len(chunk_rec)
-        recs = out_rec.numpy()[: rec_total * 16].view(RECORD_DTYPE)
+        self.last_d2h_bytes = (rec_total * 16 if gatherer is None else 0) + (n + 1) * 8 + n + 64 * len(chunk_rec)
+        recs = out_rec.numpy()[: (rec_total if gatherer is None else 0) * 16].view(RECORD_DTYPE)
         return SmemResult(recs, offs, out_st.numpy()[:n], mems_total)

@@ -1,13 +1,20 @@
 """Multi-GPU plumbing: reads shard by rank, the index is replicated per GPU, and the only
 collective is the final gather of per-rank SMEM records (north_star (4)).
 
-One process per GPU (torchrun); torch.distributed is the transport (NCCL on GPUs, gloo in the CPU
-tests).  There is no data-path collective: every rank searches its own contiguous block of reads.
+One process per GPU (torchrun).  torch.distributed carries the bootstrap (the 128-byte NCCL id, the
+CUDA IPC handle of the destination buffer) and is the transport of the gloo CPU tests; on GPUs the
+data path is the library's own: gsm_gather_records (exact-size ncclSend / ncclRecv into a
+preallocated device buffer) or, fused, gsm_smem_collect_gathered writing each rank's ordered
+records straight into the gathering rank's HBM through a peer mapping (NVLink / NVSwitch).
+There is no data-path collective besides this one: every rank searches its own contiguous block of reads.
 """
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import _capi as capi
 from .engine import RECORD_DTYPE
 
 
@@ -38,50 +45,207 @@ def shard_range(n_reads, rank, world):
     return (n_reads * rank) // world, (n_reads * (rank + 1)) // world
 
 
-def gather_records(records, counts_per_read, dst=0, group=None, device=None):
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class NativeComm:
+    """The library's NCCL communicator (gsm_comm_*), bootstrapped over an existing torch.distributed group: rank 0
+    draws the 128-byte id, the group broadcasts it, every rank calls gsm_comm_init on its current CUDA device."""
+
+    def __init__(self, group=None):
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        ident = np.zeros(128, np.uint8)
+        if self.rank == 0:
+            capi.check(capi.lib.gsm_comm_unique_id(ident.ctypes.data))
+        box = [ident.tobytes()]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = np.frombuffer(box[0], np.uint8).copy()
+        h = C.c_void_p()
+        capi.check(capi.lib.gsm_comm_init(ident.ctypes.data, self.rank, self.world, C.byref(h)))
+        self._h = h
+        ver = C.c_int()
+        capi.check(capi.lib.gsm_comm_info(self._h, None, None, C.byref(ver)))
+        self.nccl_version = int(ver.value)
+
+    def allgather_u64(self, send_dev, recv_dev, n=1):
+        capi.check(capi.lib.gsm_comm_allgather_u64(self._h, C.c_void_p(send_dev), n, C.c_void_p(recv_dev), _stream()))
+
+    def gather_records(self, send, n_send, counts, recv, dst=0):
+        """send / recv: device uint8 tensors (or None); counts: host uint64 array, records per rank."""
+        counts = np.ascontiguousarray(counts, np.uint64)
+        capi.check(capi.lib.gsm_gather_records(self._h, C.c_void_p(send.data_ptr() if send is not None else 0), int(n_send),
+                                               counts.ctypes.data, C.c_void_p(recv.data_ptr() if recv is not None else 0), int(dst), _stream()))
+
+    def close(self):
+        if self._h is not None:
+            capi.lib.gsm_comm_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_comms = {}
+
+
+def native_comm(group=None):
+    """One cached NativeComm per process group (collective on first use)."""
+    key = id(group)
+    if key not in _comms:
+        _comms[key] = NativeComm(group)
+    return _comms[key]
+
+
+def gather_records(records, counts_per_read, dst=0, group=None, device=None, out=None):
     """Gather variable-length record arrays to `dst`.
 
-    records: structured array (RECORD_DTYPE) of this rank, read ids already global (read_id_base);
-    counts_per_read: int64 array, records per local read.  Returns (records, counts) concatenated
-    in rank order on dst, (None, None) elsewhere.  Two collectives: all_gather of the two sizes,
-    then gather of the payloads padded to the largest shard.
+    records: this rank's records (structured RECORD_DTYPE array, or a uint8 tensor of 16-byte records already on the
+    device), read ids already global (read_id_base); counts_per_read: records per local read (int64 array / tensor).
+    Returns (records, counts) concatenated in rank order on dst -- device tensors (uint8 view of 16-byte records, int64)
+    when the backend is NCCL, numpy arrays with gloo -- and (None, None) elsewhere.  `out`: optional preallocated
+    device uint8 tensor for the records on dst (NCCL).  Exact sizes travel: one all_gather of the two sizes, then
+    gsm_gather_records / gsm-free torch point-to-point (gloo).  Nothing is padded, nothing is staged through the host.
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    nccl = dist.get_backend(group) == "nccl"
     if device is None:
-        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    rec_u8 = torch.from_numpy(np.ascontiguousarray(records).view(np.uint8).copy()) if not torch.is_tensor(records) else records
-    cnt = torch.from_numpy(np.ascontiguousarray(counts_per_read, dtype=np.int64)) if not torch.is_tensor(counts_per_read) else counts_per_read
-    rec_u8, cnt = rec_u8.to(device), cnt.to(device)
-    sizes = torch.tensor([rec_u8.numel(), cnt.numel()], dtype=torch.int64, device=device)
-    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
-    dist.all_gather(all_sizes, sizes, group=group)
-    all_sizes = torch.stack(all_sizes).cpu().numpy()
-    max_rec, max_cnt = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
-    pad_rec = torch.empty(max(max_rec, 1), dtype=torch.uint8, device=device)
-    pad_rec[: rec_u8.numel()] = rec_u8
-    pad_cnt = torch.empty(max(max_cnt, 1), dtype=torch.int64, device=device)
-    pad_cnt[: cnt.numel()] = cnt
-    recv_rec = [torch.empty_like(pad_rec) for _ in range(world)] if rank == dst else None
-    recv_cnt = [torch.empty_like(pad_cnt) for _ in range(world)] if rank == dst else None
-    dist.gather(pad_rec, recv_rec, dst=dst, group=group)
-    dist.gather(pad_cnt, recv_cnt, dst=dst, group=group)
-    if rank != dst:
-        return None, None
-    n_rec = [int(all_sizes[r, 0]) for r in range(world)]
-    n_cnt = [int(all_sizes[r, 1]) for r in range(world)]
-    if device.type == "cuda":
-        # one pinned destination per array, every shard copied straight to its final place (no pageable staging, no concatenate)
-        out_rec = torch.empty(max(sum(n_rec), 1), dtype=torch.uint8, pin_memory=True)
-        out_cnt = torch.empty(max(sum(n_cnt), 1), dtype=torch.int64, pin_memory=True)
-        a = b = 0
+        device = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+    rec_u8 = torch.from_numpy(np.ascontiguousarray(records).view(np.uint8).copy()) if not torch.is_tensor(records) else records.view(torch.uint8)
+    cnt = torch.from_numpy(np.ascontiguousarray(counts_per_read, dtype=np.int64)) if not torch.is_tensor(counts_per_read) else counts_per_read.to(torch.int64)
+    rec_u8, cnt = rec_u8.to(device).contiguous(), cnt.to(device).contiguous()
+    sizes = torch.tensor([rec_u8.numel() // 16, cnt.numel()], dtype=torch.int64, device=device)
+    lst = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(lst, sizes, group=group)
+    all_sizes = torch.stack(lst).cpu().numpy()
+    n_rec, n_cnt = all_sizes[:, 0].astype(np.uint64), all_sizes[:, 1].astype(np.uint64)
+    if nccl:
+        comm = native_comm(group)
+        recv_rec = recv_cnt = None
+        if rank == dst:
+            need = int(n_rec.sum()) * 16
+            recv_rec = out[:need] if out is not None and out.numel() >= need else torch.empty(max(need, 16), dtype=torch.uint8, device=device)[:need]
+            recv_cnt = torch.empty(max(int(n_cnt.sum()), 1), dtype=torch.int64, device=device)[: int(n_cnt.sum())]
+        comm.gather_records(rec_u8, int(n_rec[rank]), n_rec, recv_rec, dst)
+        # per-read counts: 8-byte items through the same exact-size exchange (two counts = one 16-byte "record")
+        pad = cnt if cnt.numel() % 2 == 0 else torch.cat([cnt, cnt.new_zeros(1)])
+        n_pair = ((n_cnt + np.uint64(1)) // np.uint64(2)).astype(np.uint64)
+        recv_pairs = torch.empty(max(int(n_pair.sum()) * 2, 2), dtype=torch.int64, device=device) if rank == dst else None
+        comm.gather_records(pad.view(torch.uint8), int(n_pair[rank]), n_pair, recv_pairs.view(torch.uint8) if recv_pairs is not None else None, dst)
+        if rank != dst:
+            return None, None
+        a = 0
+        parts = []
         for r in range(world):
-            out_rec[a:a + n_rec[r]].copy_(recv_rec[r][: n_rec[r]], non_blocking=True)
-            out_cnt[b:b + n_cnt[r]].copy_(recv_cnt[r][: n_cnt[r]], non_blocking=True)
-            a += n_rec[r]
-            b += n_cnt[r]
-        torch.cuda.synchronize(device)
-        return out_rec.numpy()[: sum(n_rec)].view(RECORD_DTYPE), out_cnt.numpy()[: sum(n_cnt)]
-    recs = np.concatenate([recv_rec[r][: n_rec[r]].numpy() for r in range(world)]).view(RECORD_DTYPE)
-    cnts = np.concatenate([recv_cnt[r][: n_cnt[r]].numpy() for r in range(world)])
-    return recs, cnts
+            parts.append(recv_pairs[a:a + int(n_cnt[r])])
+            a += int(n_pair[r]) * 2
+        recv_cnt = torch.cat(parts) if parts else recv_cnt
+        return recv_rec, recv_cnt
+    # gloo (CPU tests): exact-size point-to-point
+    if rank == dst:
+        recs, cnts = [], []
+        for r in range(world):
+            if r == rank:
+                recs.append(rec_u8)
+                cnts.append(cnt)
+                continue
+            br = torch.empty(int(n_rec[r]) * 16, dtype=torch.uint8)
+            bc = torch.empty(int(n_cnt[r]), dtype=torch.int64)
+            if br.numel():
+                dist.recv(br, src=r, group=group)
+            if bc.numel():
+                dist.recv(bc, src=r, group=group)
+            recs.append(br)
+            cnts.append(bc)
+        return torch.cat(recs).numpy().view(RECORD_DTYPE), torch.cat(cnts).numpy()
+    if rec_u8.numel():
+        dist.send(rec_u8, dst=dst, group=group)
+    if cnt.numel():
+        dist.send(cnt, dst=dst, group=group)
+    return None, None
+
+
+class RecordGatherer:
+    """The fused gather: every rank's ordered-write kernel stores its records directly into ONE buffer in the HBM of
+    rank `dst` (peer mapping over NVLink / NVSwitch), batch after batch, with no host round trip and no separate copy.
+
+    Collective constructor: dst allocates `capacity` records, exports the allocation (CUDA IPC), the group carries the
+    64-byte handle, the other ranks map it.  Per batch (collect): all-gather of the batch's per-rank record counts
+    (8 bytes each, device to device, on the current stream), gsm_smem_collect_gathered into the mapping at
+    running total + sum of lower ranks' counts, running total advanced on the device.  finish(): a last small
+    all-gather is the completion fence; on dst it returns the records and the (batch, rank) segment table."""
+
+    def __init__(self, capacity, dst=0, group=None, device=None, max_batches=4096, comm=None):
+        self.group, self.dst = group, dst
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.comm = comm or native_comm(group)
+        self.capacity = int(capacity)
+        self.max_batches = int(max_batches)
+        self.counts = torch.zeros(self.max_batches * self.world, dtype=torch.int64, device=self.device)
+        self.base = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.fence_buf = torch.zeros(self.world + 1, dtype=torch.int64, device=self.device)
+        self.n_batches = 0
+        self._offset = 0
+        handle = np.zeros(64, np.uint8)
+        off = C.c_uint64(0)
+        self.buffer = None
+        if self.rank == dst:
+            self.buffer = torch.empty(self.capacity * 16, dtype=torch.uint8, device=self.device)
+            capi.check(capi.lib.gsm_peer_export(C.c_void_p(self.buffer.data_ptr()), handle.ctypes.data, C.byref(off)))
+        box = [(handle.tobytes(), int(off.value))]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
+        if self.rank == dst:
+            self.out_ptr = self.buffer.data_ptr()
+        else:
+            handle = np.frombuffer(box[0][0], np.uint8).copy()
+            p = C.c_void_p()
+            capi.check(capi.lib.gsm_peer_open(handle.ctypes.data, box[0][1], C.byref(p)))
+            self.out_ptr, self._offset = int(p.value), int(box[0][1])
+
+    def reset(self):
+        self.base.zero_()
+        self.n_batches = 0
+
+    def collect(self, engine, reads_c):
+        """engine: the Engine whose workspace holds the batch just selected; reads_c: its gsm_dev_reads struct."""
+        if self.n_batches >= self.max_batches:
+            raise capi.GsmError(capi.E_CAPACITY, "RecordGatherer: more batches than max_batches")
+        row = self.counts.data_ptr() + 8 * self.world * self.n_batches
+        self.comm.allgather_u64(engine.counters.data_ptr() + 8, row)
+        capi.check(capi.lib.gsm_smem_collect_gathered(C.byref(reads_c), C.byref(engine.ws), C.c_void_p(self.out_ptr), self.capacity,
+                                                      C.c_void_p(row), self.rank, C.c_void_p(self.base.data_ptr()), _stream()))
+        capi.check(capi.lib.gsm_gather_advance(C.c_void_p(self.base.data_ptr()), C.c_void_p(row), self.world, _stream()))
+        self.n_batches += 1
+
+    def fence(self):
+        """Completion fence on the current stream (all ranks): dst's copy of this small all-gather completes only after
+        every rank's stream has reached it, i.e. after every rank's ordered writes into dst's buffer."""
+        self.comm.allgather_u64(self.base.data_ptr(), self.fence_buf.data_ptr())
+
+    def finish(self):
+        """Fence + synchronise, then on dst: (records uint8 device view, counts[batch, rank] numpy)."""
+        self.fence()
+        torch.cuda.current_stream().synchronize()
+        total = int(self.base.item())
+        if total > self.capacity:
+            raise capi.GsmError(capi.E_CAPACITY, f"RecordGatherer: {total} records exceed the destination's capacity {self.capacity}")
+        if self.rank != self.dst:
+            return None, None
+        seg = self.counts[: self.n_batches * self.world].view(self.n_batches, self.world).cpu().numpy()
+        return self.buffer[: total * 16], seg
+
+    def close(self):
+        if self.rank != self.dst and self.out_ptr:
+            capi.lib.gsm_peer_close(C.c_void_p(self.out_ptr), self._offset)
+            self.out_ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -283,6 +283,40 @@ int gsm_smem_select(int method, const gsm_dev_index* idx, const gsm_dev_reads* r
 int gsm_smem_collect(const gsm_dev_reads* reads, gsm_workspace* ws, gsm_record* out, uint64_t out_cap,
                      void* stream);
 
+/* ------------------------------------------------------------------ multi-GPU: the gather of per-rank records
+ * The path shards by reads (rank r searches reads [r*N/G, (r+1)*N/G) against its own replica of the index); its only
+ * exchange is the final gather of the per-rank record arrays to one rank (north_star (4)).  One process per
+ * GPU; the launcher (torchrun, mpirun, ...) only has to carry the 128-byte id from rank 0 to the other ranks.
+ *
+ * gsm_comm_*: an NCCL communicator owned by the library (libnccl.so.2 is dlopen'ed on first use; GSM_E_INVALID when absent).
+ *   gsm_comm_unique_id  rank 0: 128 bytes to broadcast;  gsm_comm_init: every rank, on its current CUDA device.
+ * gsm_comm_allgather_u64: n values per rank, device to device (the per-rank record counts: ws->counters + 1).
+ * gsm_gather_records: counts[world] (HOST) = records per rank; `send` = this rank's n_send = counts[rank] records
+ *   (device); on dst `recv` (device, preallocated, sum(counts) records) receives every rank's records in rank order
+ *   (one ncclGroup of exact-size ncclSend / ncclRecv; dst's own shard is a device-to-device copy).  Asynchronous on stream.
+ *
+ * Peer-memory gather (the fused path): gsm_peer_export names the allocation behind a device pointer of the gathering
+ * rank (64-byte CUDA IPC handle + offset of the pointer in it), gsm_peer_open maps it in another process of the same
+ * node (NVLink / NVSwitch peer access), gsm_peer_close(ptr, offset) unmaps it.  gsm_smem_collect_gathered is
+ * gsm_smem_collect writing record k of this batch to out[*base_dev + sum(counts_dev[0..rank)) + k]: with `out` a peer
+ * mapping, each rank's ordered write lands in the gathering rank's HBM and no separate gather pass exists.  counts_dev =
+ * output of gsm_comm_allgather_u64 for this batch, base_dev = running total of earlier batches (device; NULL = 0),
+ * advanced by gsm_gather_advance(base_dev, counts_dev, world) after each batch. */
+typedef struct gsm_comm gsm_comm;
+int gsm_comm_unique_id(void* id128);
+int gsm_comm_init(const void* id128, int rank, int world, gsm_comm** out);
+int gsm_comm_free(gsm_comm* comm);
+int gsm_comm_info(const gsm_comm* comm, int* rank, int* world, int* nccl_version);
+int gsm_comm_allgather_u64(gsm_comm* comm, const uint64_t* send_dev, uint64_t n, uint64_t* recv_dev, void* stream);
+int gsm_gather_records(gsm_comm* comm, const gsm_record* send, uint64_t n_send, const uint64_t* counts, gsm_record* recv,
+                       int dst, void* stream);
+int gsm_peer_export(const void* dev_ptr, void* handle64, uint64_t* offset);
+int gsm_peer_open(const void* handle64, uint64_t offset, void** dev_ptr);
+int gsm_peer_close(void* dev_ptr, uint64_t offset);
+int gsm_smem_collect_gathered(const gsm_dev_reads* reads, gsm_workspace* ws, gsm_record* out, uint64_t out_cap,
+                              const uint64_t* counts_dev, uint32_t rank, const uint64_t* base_dev, void* stream);
+int gsm_gather_advance(uint64_t* base_dev, const uint64_t* counts_dev, uint32_t world, void* stream);
+
 /* Optional accelerator for the RMI last-mile search: probe[row] = {suffix_array[row], code of the 32
  * bases at that suffix} (16 bytes), so RMI_LUT.get_ref_seq (RMI_LUT.py:89-92) is ONE fetch instead of
  * a suffix-array read followed by a text read.  probe: n_rows * 16 bytes of device memory. */

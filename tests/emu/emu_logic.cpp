@@ -74,6 +74,8 @@ struct SelCtx {
     const uint32_t* lut;
     RmiModel rmi;
     bool raised = false;
+    uint32_t seed_K = 0;                 // sweep seed table (optional): lets RMI lookups use rmi_arith_lookup
+    const U4* seed_tab = nullptr;
     std::vector<uint32_t>* out;   // 6 x u32 per record: i, j, lo_lo, lo_hi, hi_lo, hi_hi
 
     MemEntry mem(uint32_t k) const { return mems[k]; }
@@ -100,8 +102,11 @@ struct SelCtx {
         }
     }
 
-    uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi) {
+    uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi, uint32_t& wtrue) {
         auto rd = [&](uint64_t w) { return words[w]; };
+        auto load = [&](uint64_t idx) { return ix->fwd[idx]; };
+        auto seed = [&](uint64_t code) { return seed_tab[code]; };
+        wtrue = 0;
         auto sa = [&](uint64_t r) { return ix->sa[r]; };
         auto tx = [&](uint64_t w) { return ix->text[w]; };
         SaTextProbe<decltype(sa), decltype(tx)> pr{sa, tx};
@@ -114,13 +119,24 @@ struct SelCtx {
             if (method == GSM_METHOD_LUT_) {
                 uint32_t l = lut[2 * code], n = lut[2 * code + 1];
                 lo[i] = l; hi[i] = (int64_t)l + n - 1;
+                wtrue |= 1u << i;
                 if (n != 0) hit |= 1u << i;
                 continue;
             }
             if (rmi.n_none) {                            // error-bounded fast path first, literal search on a hazard
                 int64_t flo, fhi;
-                if (rmi_fast_lookup(pr, rmi, code, ix->meta.n_rows, (int64_t)ix->n_bases, flo, fhi)) {
+                bool ok;
+                if (seed_tab && seed_K <= K) {           // no probes: true bounds from the seed table + arithmetic replay
+                    uint32_t A, n;
+                    kmer_bounds_seeded(rd, load, seed, ix->meta, cpos, K, seed_K, A, n);
+                    ok = rmi_arith_lookup(rmi, RmiGallop::predicted_row(rmi, code, ix->meta.n_rows), A, n, ix->meta.n_rows, flo, fhi);
+                    g_cnt[6]++;                          // [6] arithmetic lookups (select runs)
+                } else {
+                    ok = rmi_fast_lookup(pr, rmi, code, ix->meta.n_rows, (int64_t)ix->n_bases, flo, fhi);
+                }
+                if (ok) {
                     lo[i] = flo; hi[i] = fhi;
+                    wtrue |= 1u << i;
                     if (fhi >= flo) hit |= 1u << i;
                     continue;
                 }
@@ -140,27 +156,13 @@ struct SelCtx {
         return hit;
     }
 
-    bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi) {
+    bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi, bool both_true) {
         g_cnt[3]++;
-        if (method == GSM_METHOD_LUT_) {
-            // closed form of check_sequential on two TRUE k-mer intervals
-            for (uint32_t t = 1; t < K; ++t)
-                if (base(c + t) != base(pc + t - 1)) return false;
-            uint32_t ch = base(c);
-            auto load = [&](uint64_t idx) { return ix->fwd[idx]; };
-            StepOut r = step_single(load, (uint32_t)plo, (uint32_t)phi + 1, ch, ix->meta.C[ch], ix->meta.prim_f);
-            return r.cnt_new != 0;
-        }
-        const int64_t n = ix->meta.n_rows;
-        for (int64_t a = clo; a <= chi; ++a) {
-            int64_t ra = a < 0 ? a + n : a;
-            uint32_t x = ix->sa[ra];
-            for (int64_t b = plo; b <= phi; ++b) {
-                int64_t rb = b < 0 ? b + n : b;
-                if (x + 1 == ix->sa[rb]) return true;
-            }
-        }
-        return false;
+        auto load = [&](uint64_t idx) { return ix->fwd[idx]; };
+        auto bs = [&](uint32_t p) { return base(p); };
+        if (method == GSM_METHOD_LUT_ || both_true) return true_sequential(bs, load, ix->meta, K, c, pc, plo, phi);
+        auto sal = [&](uint64_t r) { return ix->sa[r]; };
+        return rmi_sequential(load, sal, ix->meta, clo, chi, plo, phi);
     }
 
     void emit(uint32_t i, uint32_t j, int64_t lo, int64_t hi) {
@@ -279,6 +281,7 @@ int emu_smem(const EmuIndex* ei, int method, const uint32_t* words, uint32_t L, 
     SelCtx sc;
     sc.ix = &ix; sc.words = words; sc.L = L; sc.K = K; sc.n_mems = (uint32_t)ctx.mems.size(); sc.min_len = min_len;
     sc.mems = ctx.mems.data(); sc.method = method; sc.lut = lut; sc.out = &recs;
+    sc.seed_K = seed_tab ? seed_K : 0; sc.seed_tab = (const U4*)seed_tab;
     memset(&sc.rmi, 0, sizeof(sc.rmi));
     if (method == 2) {
         sc.rmi.K = K; sc.rmi.n_levels = n_levels; sc.rmi.coef = coef; sc.rmi.intercept = intercept; sc.rmi.stride = 1;
@@ -320,7 +323,7 @@ void emu_seed_build(const EmuIndex* ei, uint32_t K, uint32_t* table) {
     uint64_t ncodes = 1ull << (2 * K);
     for (uint64_t code = 0; code < ncodes; ++code) {
         uint32_t lo = 0, cnt = ei->n_rows, rlo = 0, rcnt = ei->n_rows;
-        for (uint32_t t = 0; t < K && cnt; ++t) {
+        for (uint32_t t = 0; t < K; ++t) {                                 // through empty intervals too: lo stays the insertion point
             uint32_t c = (uint32_t)(code >> (2 * t)) & 3u;                 // last base first: backward search on the text
             StepOut r = step_single(lf, lo, lo + cnt, c, ei->C[c], ei->prim_f);
             lo = r.lo_new; cnt = r.cnt_new;
@@ -401,6 +404,30 @@ int emu_rmi_fast(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint32
     SaTextProbe<decltype(sa), decltype(tx)> pr{sa, tx};
     *lo = 0; *hi = -1;
     const bool ok = rmi_fast_lookup(pr, m, code, ei->n_rows, (int64_t)ei->n_bases, *lo, *hi, n_probes);
+    *hazard = ok ? 0u : 1u;
+    return 0;
+}
+
+// the probe-free error-bounded lookup (rmi_arith_lookup): true bounds by a plain backward search continued through empty
+// intervals, then the arithmetic replay of the exponential phase; *hazard = 1 when it defers to the literal search
+int emu_rmi_arith(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint32_t* level_sizes, const double* coef,
+                  const double* intercept, uint32_t n_none, const uint32_t* none_rows, uint64_t code, int64_t* lo, int64_t* hi,
+                  uint32_t* hazard) {
+    RmiModel m; memset(&m, 0, sizeof(m));
+    m.K = K; m.n_levels = n_levels; m.coef = coef; m.intercept = intercept; m.stride = 1;
+    uint32_t off = 0;
+    for (uint32_t l = 0; l < n_levels; ++l) { m.level_size[l] = level_sizes[l]; m.level_off[l] = off; off += level_sizes[l]; }
+    rmi_set_none_rows(m, none_rows, n_none, ei->n_rows);
+    const Half* fwd = (const Half*)ei->fwd;
+    auto load = [&](uint64_t idx) { return fwd[idx]; };
+    uint32_t A = 0, cnt = ei->n_rows;
+    for (uint32_t t = 0; t < K; ++t) {
+        const uint32_t c = (uint32_t)(code >> (2 * t)) & 3u;
+        const StepOut r = step_single(load, A, A + cnt, c, ei->C[c], ei->prim_f);
+        A = r.lo_new; cnt = r.cnt_new;
+    }
+    *lo = 0; *hi = -1;
+    const bool ok = rmi_arith_lookup(m, RmiGallop::predicted_row(m, code, ei->n_rows), A, cnt, ei->n_rows, *lo, *hi);
     *hazard = ok ? 0u : 1u;
     return 0;
 }

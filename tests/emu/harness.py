@@ -42,6 +42,8 @@ class Emu:
         self.lib.emu_smem.argtypes = [C.POINTER(EmuIndex), C.c_int, P, u32, u32, u32, P, u32, P, P, P, P, u32, u32, P, u32, P]
         self.lib.emu_rmi_fast.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u32, P, u64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                           C.POINTER(u32), C.POINTER(u32)]
+        self.lib.emu_rmi_arith.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u32, P, u64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                           C.POINTER(u32)]
         self.lib.emu_rmi_search.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                             C.POINTER(u32)]
         self.lib.emu_locate.argtypes = [C.POINTER(EmuIndex), u32, u64, P, P]
@@ -205,6 +207,21 @@ def _rmi_fast(self, rmi, code):
 
 
 Emu.rmi_fast_lookup = _rmi_fast
+
+
+def _rmi_arith(self, rmi, code):
+    """(hazard, lo, hi) through rmi_arith_lookup: true bounds from the FM index + arithmetic replay, no table probes."""
+    ls = np.asarray(rmi["level_sizes"], np.uint32)
+    coef = np.ascontiguousarray(rmi["coef"], np.float64)
+    icpt = np.ascontiguousarray(rmi["intercept"], np.float64)
+    nr = self.none_rows(rmi["K"])
+    lo, hi, hz = C.c_int64(), C.c_int64(), C.c_uint32()
+    self.lib.emu_rmi_arith(C.byref(self.e), rmi["K"], len(ls), ls.ctypes.data, coef.ctypes.data, icpt.ctypes.data, len(nr), nr.ctypes.data,
+                           C.c_uint64(code), C.byref(lo), C.byref(hi), C.byref(hz))
+    return bool(hz.value), lo.value, hi.value
+
+
+Emu.rmi_arith_lookup = _rmi_arith
 
 
 def records_to_dict(q, recs):

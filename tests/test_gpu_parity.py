@@ -430,36 +430,107 @@ def test_rmi_fast_search_changes_nothing(gs):
         assert np.array_equal(fo, lit.offsets) and np.array_equal(fr, lit.records) and np.array_equal(fs, lit.status)
 
 
-def test_team_selection_kernels_equal_default(gs):
-    """GSM_SELECT_TEAMS=3 runs LUT/RMI selection by 16-lane teams (kept as a measured alternative): same records.
-    The switch is read once per process, so the team run happens in a child process."""
-    import subprocess
-    import sys
-    import tempfile
-    code = r'''
-import sys, numpy as np
-sys.path.insert(0, %r)
-import bench, genie_smem_b200 as g
-from tests.test_gpu_parity import _synthetic
-ref, reads, _ = _synthetic(1_500_000, 6000, 151, 5, 0.015)
-reads[:600] = np.random.default_rng(1).integers(0, 4, (600, 151), dtype=np.uint8)
-idx = g.DeviceIndex.build_on_device(ref).build_seed_table()
-batch = g.ReadBatch.from_codes(reads, 151)
-e = g.Engine(idx, len(reads), 151, mems_per_read=64, recs_per_read=64)
-rmi = bench.train_rmi(idx, 10, (32, 1024), idx.device)
-out = {}
-for name, m, kw in (("lut", g.METHOD_LUT, {"K": 9, "lut": g.lut_build(idx, 9)}), ("rmi", g.METHOD_RMI, {"rmi": rmi}), ("rmi17", g.METHOD_RMI, {"rmi": bench.train_rmi(idx, 17, (32, 1024), idx.device)})):
-    r = e.run(m, batch, **kw)
-    out[name + "_rec"] = r.records.copy(); out[name + "_off"] = r.offsets.copy(); out[name + "_st"] = r.status.copy()
-np.savez(sys.argv[1], **out)
-''' % (gu.ROOT if hasattr(gu, "ROOT") else __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))),)
-    import os
-    res = []
-    with tempfile.TemporaryDirectory() as d:
-        for mode in ("0", "3"):
-            path = os.path.join(d, f"m{mode}.npz")
-            subprocess.check_call([sys.executable, "-c", code, path], env=dict(os.environ, GSM_SELECT_TEAMS=mode))
-            res.append(dict(np.load(path)))
-    assert res[0].keys() == res[1].keys() and len(res[0]["rmi_rec"]) > 0
-    for k in res[0]:
-        assert np.array_equal(res[0][k], res[1][k]), k
+def _codes_to_strings(reads):
+    return [r.decode() for r in np.frombuffer(b"ACGT", np.uint8)[reads].view(f"S{reads.shape[1]}").reshape(-1)]
+
+
+def _check_against_oracle(gs, res, reads_s, exp, what):
+    got = _dicts(reads_s, res)
+    n_raise = 0
+    for k, e in enumerate(exp):
+        if e == "raises":
+            assert res.status[k] == gs.READ_REF_RAISES, (what, k)
+            n_raise += 1
+        else:
+            assert res.status[k] == gs.READ_OK, (what, k)
+            assert got[k] == e, (what, k, reads_s[k])
+    return n_raise
+
+
+@pytest.mark.parametrize("seed_table", [True, False])
+def test_all_methods_vs_oracle_on_synthetic_reference(gs, seed_table):
+    """Tier-B parity at a size the C oracle finishes in seconds: 4 Mbp synthetic reference, 2,400 reads of
+    151 bp -- 1 % substitution reads, uniform-random reads, poly-A heads / tails / whole reads -- through BWA-, LUT- and
+    RMI-SMEM, the RMI being the one bench.py trains (vectorised trainer, probe table, None rows), against
+    oracle/smem_oracle.c (the reference's get_SMEMS / get_smems_lut / get_smems_rmi restated literally).
+    seed_table=True: sweep seed table on, RMI lookups by seed-table bounds + arithmetic replay (rmi_arith_lookup);
+    False: plain FM stepping, RMI lookups by the probe-based error-bounded search.  Same records either way."""
+    import bench
+    from oracle.c_oracle import COracle
+    L = 151
+    ref, reads, _ = _synthetic(4_000_000, 2_400, L, 4242, 0.01)
+    rng = np.random.default_rng(6)
+    reads[:600] = rng.integers(0, 4, (600, L), dtype=np.uint8)          # uniform random
+    reads[600:640, :70] = 0                                             # poly-A heads (the smallest k-mers: row 0 territory)
+    reads[640:680, 90:] = 0                                             # poly-A tails
+    reads[680:690] = 0                                                  # poly-A reads
+    reads[690:700] = 3                                                  # poly-T reads (the largest k-mers: table end)
+    reads[700:720, 50:100] = np.tile(np.array([0, 1], np.uint8), 25)    # dinucleotide repeats
+    text = np.frombuffer(b"ACGT", np.uint8)[ref].tobytes()
+    idx = gs.DeviceIndex.build_on_device(ref)
+    if seed_table:
+        idx.build_seed_table()
+    sa = idx.suffix_array_host()
+    reads_s = _codes_to_strings(reads)
+    batch = gs.ReadBatch.from_codes(reads, L)
+    e = gs.Engine(idx, len(reads), L, mems_per_read=128, recs_per_read=96)
+    o = COracle(text, sa)
+    res = e.run(gs.METHOD_BWA, batch, min_len=1)
+    _check_against_oracle(gs, res, reads_s, o.smem_dicts(0, reads_s, min_len=1), "bwa")
+    res = e.run(gs.METHOD_BWA, batch, min_len=20)
+    _check_against_oracle(gs, res, reads_s, o.smem_dicts(0, reads_s, min_len=20), "bwa minlen 20")
+    for K in (8, 12):
+        res = e.run(gs.METHOD_LUT, batch, K=K, lut=gs.lut_build(idx, K))
+        _check_against_oracle(gs, res, reads_s, o.smem_dicts(1, reads_s, K=K), f"lut K={K}")
+    n_raise = 0
+    for K, experts in ((11, (64, 4096)), (15, (256, 16384)), (9, (4, 64))):
+        rmi = bench.train_rmi(idx, K, experts, idx.device)
+        res = e.run(gs.METHOD_RMI, batch, rmi=rmi)
+        n_raise += _check_against_oracle(gs, res, reads_s, o.smem_dicts(2, reads_s, rmi=bench.rmi_dict(rmi)), f"rmi K={K}")
+    assert n_raise < 200
+
+
+def test_add_one_vs_oracle_on_many_pairs(gs, matchers, oracles):
+    """exact_match_back_prop_add_one (ExactMatch.py:155-171) on 1,200 (char, interval) pairs per reference, hits and misses."""
+    for name in ("medium_data", "big_data"):
+        gidx, m = matchers[name]
+        text = gidx["text"]
+        rng = random.Random(3)
+        subs = []
+        for _ in range(1200):
+            L = rng.randint(1, 24)
+            p = rng.randrange(0, len(text) - L)
+            subs.append(text[p:p + L])
+        lo, cnt = m.exact_match_back_prop_batch(subs)
+        chars = [rng.choice("ACGT") for _ in subs]
+        nlo, ncnt = gs.add_one_batch(m.device_index, ["ACGT".index(c) for c in chars], lo, cnt)
+        n_miss = 0
+        for q, ch, l, c, a, b in zip(subs, chars, lo, cnt, nlo, ncnt):
+            exp = oracles[name].exact_match_back_prop_add_one(ch, (int(l), int(l) + int(c) - 1))
+            got = -1 if b == 0 else (int(a), int(a) + int(b) - 1)
+            assert got == exp, (q, ch)
+            assert exp == oracles[name].exact_match_back_prop(ch + q)
+            n_miss += exp == -1
+        assert 50 < n_miss < 1150
+
+
+def test_selection_staging_overflow_reruns_the_read(gs, matchers):
+    """A read that emits more records than a selection thread can stage (64) is run a second time writing in place:
+    long uniform-random reads (hundreds of records each) through all three methods equal the oracle."""
+    gidx, m = matchers["big_data"]
+    text = gidx["text"]
+    rng = random.Random(17)
+    reads = ["".join(rng.choice("ACGT") for _ in range(L)) for L in (900, 1500, 2000, 700, 64, 2000)]
+    reads.append(text[100:1900])
+    s = gs.SMEM(m)
+    s.lut.generate_lut(6)
+    exp = _oracle_dicts(text, gidx["suffix_array"], 0, reads, min_len=1)
+    assert max(len(e) for e in exp) > 64
+    assert _dicts(reads, s.get_SMEMS_batch(reads, 1)) == exp
+    assert _dicts(reads, s.get_smems_lut_batch(reads)) == _oracle_dicts(text, gidx["suffix_array"], 1, reads, K=6)
+    p = gu.load_rmi("big_data_k12")
+    s.rmi_lut = gs.RMI_LUT([p["experts"][0], p["experts"][1]], p["K"], "big_data.fa", matcher=m)
+    s.rmi_lut.rmi = gs.RMI.from_params(p["level_sizes"], p["coef"], p["intercept"])
+    res = s.get_smems_rmi_batch(reads)
+    expr = _oracle_dicts(text, gidx["suffix_array"], 2, reads, rmi=p)
+    _check_against_oracle(gs, res, reads, expr, "rmi long")

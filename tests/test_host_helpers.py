@@ -25,15 +25,40 @@ def test_bench_configs_and_workload(monkeypatch):
     import bench
     monkeypatch.setattr(sys, "argv", ["bench.py"])
     a = bench.parse_args()
-    assert (a.ref_bases, a.reads, a.seed) == (1_000_000_000, 50_000_000, 1000) and "configs[3]" in a.cfg_name
-    w = bench.workload_dict(a, 8)
+    assert (a.ref_bases, a.total_reads, a.seed, a.scaling) == (1_000_000_000, 50_000_000, 1000, "strong") and "configs[3]" in a.cfg_name
+    w = bench.workload_dict(a, 8, 6_250_000)
     assert "x8" in w["parallelism"] and w["read_len"] == 151 and "configs[3]" in w["workload"]
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--config", "c3", "--gpus", "2"])
+    assert w["reads_per_step"] == 50_000_000 and w["reads_per_gpu"] == 6_250_000          # strong scaling: the config's reads are sharded
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--config", "c3", "--gpus", "2", "--scaling", "weak"])
     a = bench.parse_args()
-    assert (a.ref_bases, a.reads, a.seed, a.gpus) == (100_000_000, 10_000_000, 100, 2)
+    assert (a.ref_bases, a.total_reads, a.seed, a.gpus) == (100_000_000, 10_000_000, 100, 2)
+    assert bench.workload_dict(a, 2, a.total_reads)["reads_per_step"] == 20_000_000
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--config", "c5"])
+    a = bench.parse_args()
+    assert (a.ref_bases, a.total_reads) == (3_000_000_000, 100_000_000) and a.experts[1] > bench.CONFIGS["c4"]["experts"][1]
     monkeypatch.setattr(sys, "argv", ["bench.py", "--ref-bases", "2000000", "--reads", "1000"])
     a = bench.parse_args()
-    assert a.cfg_name == "custom size" and a.experts == bench.CONFIGS["c3"]["experts"]
+    assert a.cfg_name == "custom size" and a.experts[1] >= 1024 and a.total_reads == 1000
+
+
+def test_bench_parity_comparison_applies_the_reference_dict_semantics():
+    """compare_with_oracle: duplicate SMEM strings collapse (first insertion keeps its place, last value wins), raising
+    reads must be flagged, any difference counts."""
+    import bench
+    from genie_smem_b200.engine import RECORD_DTYPE
+    reads = np.array([[0, 1, 0, 1, 2], [3, 3, 3, 3, 3]], np.uint8)
+    recs = np.array([(0, 0, 2, 5, 6), (0, 2, 4, 7, 8), (0, 4, 5, 1, 1)], RECORD_DTYPE)      # read 0: "AC" twice (second value wins), then "G"
+    offs = np.array([0, 3, 3])
+    status = np.array([0, 1], np.uint8)
+    out = np.zeros((2, 6, 4), np.int64)
+    out[0, 0] = (0, 2, 7, 8)
+    out[0, 1] = (4, 5, 1, 1)
+    counts = np.array([2, -1], np.int32)
+    assert bench.compare_with_oracle(reads, (recs, offs, status), out, counts, 2) == (0, 1)
+    out[0, 1] = (4, 5, 1, 2)
+    assert bench.compare_with_oracle(reads, (recs, offs, status), out, counts, 2) == (1, 1)
+    status[1] = 0                                                                            # the kernel missed a raising read
+    assert bench.compare_with_oracle(reads, (recs, offs, status), out, counts, 2) == (2, 1)
 
 
 def test_synthetic_reads_are_substitution_only():

@@ -36,7 +36,7 @@ def test_device_layout_lut_equals_reference_table(emus):
 def test_rmi_lookup_logic(emus, tag, name):
     _, em = emus[name]
     p = gu.load_rmi(tag)
-    n_fast = 0
+    n_fast = n_arith = 0
     for q, pred, lo, hi in gu.load_json(f"rmi_lookups_{tag}.json.gz")[::3]:
         code = 0
         for ch in q:
@@ -44,14 +44,18 @@ def test_rmi_lookup_logic(emus, tag, name):
         s, gp, glo, ghi = em.rmi_lookup(p, code)
         s2, lo2, hi2, _ = em.rmi_search(p, code)          # the resumable machine the kernels run
         hz, lo3, hi3, _ = em.rmi_fast_lookup(p, code)     # the error-bounded fast search (defers on a hazard)
+        hz4, lo4, hi4 = em.rmi_arith_lookup(p, code)      # the same without probes (bounds from the FM index)
         n_fast += not hz
+        n_arith += not hz4
         if pred is None:
-            assert s == -1 and s2 == -1 and hz
+            assert s == -1 and s2 == -1 and hz and hz4
         else:
             assert s == 0 and gp == pred and (glo, ghi) == (lo, hi)
             assert s2 == 0 and (lo2, hi2) == (lo, hi)
             assert hz or (lo3, hi3) == (lo, hi), q
+            assert hz4 or (lo4, hi4) == (lo, hi), q
     assert n_fast > 0.8 * len(gu.load_json(f"rmi_lookups_{tag}.json.gz")[::3])
+    assert n_arith > 0.8 * len(gu.load_json(f"rmi_lookups_{tag}.json.gz")[::3])
 
 
 def test_rmi_search_machine_equals_literal_search_on_bad_models(emus):
@@ -69,12 +73,14 @@ def test_rmi_search_machine_equals_literal_search_on_bad_models(emus):
             a = em.rmi_lookup(rmi, code)
             b = em.rmi_search(rmi, code)
             f = em.rmi_fast_lookup(rmi, code)
+            h = em.rmi_arith_lookup(rmi, code)
             assert (a[0] == -1) == (b[0] == -1), (rmi, code)
             if a[0] == 0:
                 assert (a[2], a[3]) == (b[1], b[2]), (rmi, code)
                 assert f[0] or (f[1], f[2]) == (a[2], a[3]), (rmi, code)     # no hazard => identical bounds
+                assert h[0] or (h[1], h[2]) == (a[2], a[3]), (rmi, code)
             else:
-                assert f[0], (rmi, code)                                     # the reference raises => never the fast path
+                assert f[0] and h[0], (rmi, code)                            # the reference raises => never the fast paths
 
 
 @pytest.mark.parametrize("seed_K", [0, 5, 9])
