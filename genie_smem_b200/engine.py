@@ -184,6 +184,125 @@ class PackedIndex:
         return cls(info, *arrs)
 
 
+class IndexFile:
+    """ONE memory-mappable file holding everything a search process needs, so that loading skips every rebuild: rank
+    buckets of both directions, suffix array (full and / or sampled), packed text, the sweep's seed table, the dense LUT,
+    the RMI parameters + None rows and (optionally) the RMI probe table.  Replaces the reference's three artefacts --
+    <ref>-FM.json (ExactMatch.py:32-39), <ref>-LUT.json (LUT.py:50-63) and rmi_file.pkl (RMI_LUT.py:186-198).
+
+    Layout: 8-byte magic "GSMIDX02", u64 length of a JSON header, the header (index info, per-section name / dtype /
+    shape / offset / byte count / CRC-32, table parameters), then the sections, each starting on a 4096-byte boundary.
+    """
+
+    MAGIC = b"GSMIDX02"
+    ALIGN = 4096
+
+    @staticmethod
+    def _sections(index, lut, rmi):
+        def host(t):
+            return None if t is None else t.detach().cpu().numpy()
+        sec = [("fwd", host(index.fwd)), ("rev", host(index.rev)), ("sa", host(index.sa)), ("text", host(index.text)),
+               ("ssa", host(getattr(index, "ssa", None))), ("seed_table", host(getattr(index, "seed_table", None))), ("lut", host(lut))]
+        if rmi is not None:
+            sec += [("rmi_params", host(rmi.params)), ("rmi_probe", host(rmi.probe))]
+        return [(n, a) for n, a in sec if a is not None]
+
+    @classmethod
+    def save(cls, path, index, lut=None, lut_K=0, rmi=None):
+        """index: DeviceIndex; lut: device table of lut_build (K = lut_K); rmi: RmiParams (None rows / probe table kept if built)."""
+        import json as _json
+        import zlib
+        info = {k: int(getattr(index.info, k)) for k in PackedIndex.FIELDS}
+        info["count"] = [int(x) for x in index.info.count]
+        info["C"] = [int(x) for x in index.info.C]
+        head = {"format": "genie_smem_b200 index file v2", "info": info, "seed_K": int(getattr(index, "seed_K", 0) or 0),
+                "sa_sample": int(getattr(index, "sa_sample", 0) or 0), "lut_K": int(lut_K) if lut is not None else 0, "rmi": None, "sections": []}
+        if rmi is not None:
+            head["rmi"] = {"K": rmi.K, "level_sizes": [int(x) for x in rmi.level_sizes],
+                           "none_rows": [int(x) for x in rmi.none_rows] if rmi.none_rows is not None else None,
+                           "max_err": float(getattr(rmi, "max_err", -1.0))}
+        secs = cls._sections(index, lut, rmi)
+        for n, a in secs:
+            head["sections"].append({"name": n, "dtype": str(a.dtype), "shape": list(a.shape), "offset": 0, "nbytes": int(a.nbytes),
+                                     "crc32": zlib.crc32(memoryview(np.ascontiguousarray(a)).cast("B")) & 0xFFFFFFFF})
+        # offsets depend on the header length, which depends on the offsets' digits: reserve room, then fill
+        blob = _json.dumps(head).encode()
+        room = ((len(blob) + 16 + 64 * len(secs) + cls.ALIGN - 1) // cls.ALIGN) * cls.ALIGN
+        off = room
+        for d in head["sections"]:
+            d["offset"] = off
+            off += ((d["nbytes"] + cls.ALIGN - 1) // cls.ALIGN) * cls.ALIGN
+        blob = _json.dumps(head).encode()
+        assert 16 + len(blob) <= room
+        with open(path, "wb") as f:
+            f.write(cls.MAGIC)
+            f.write(np.uint64(len(blob)).tobytes())
+            f.write(blob)
+            for d, (n, a) in zip(head["sections"], secs):
+                f.seek(d["offset"])
+                np.ascontiguousarray(a).tofile(f)
+            f.truncate(off)
+        return off
+
+    @classmethod
+    def header(cls, path):
+        import json as _json
+        with open(path, "rb") as f:
+            if f.read(8) != cls.MAGIC:
+                raise ValueError(f"{path}: not a genie_smem_b200 index file")
+            n = int(np.frombuffer(f.read(8), np.uint64)[0])
+            return _json.loads(f.read(n).decode())
+
+    @classmethod
+    def load(cls, path, device="cuda", verify=False):
+        """-> (DeviceIndex, lut table or None, lut_K, RmiParams or None).  Sections are memory-mapped and copied to the
+        device; nothing is rebuilt.  verify=True checks every section's CRC-32 first (ValueError on a mismatch)."""
+        import zlib
+        require_cuda()
+        head = cls.header(path)
+        arrs = {}
+        for d in head["sections"]:
+            a = np.memmap(path, mode="r", dtype=np.dtype(d["dtype"]), offset=d["offset"], shape=tuple(d["shape"]))
+            if verify and (zlib.crc32(memoryview(a).cast("B")) & 0xFFFFFFFF) != d["crc32"]:
+                raise ValueError(f"{path}: section {d['name']} is corrupt (CRC-32 mismatch)")
+            arrs[d["name"]] = a
+        info = capi.IndexInfo()
+        for k in PackedIndex.FIELDS:
+            setattr(info, k, head["info"][k])
+        for c in range(4):
+            info.count[c] = head["info"]["count"][c]
+        for c in range(5):
+            info.C[c] = head["info"]["C"][c]
+        dev = torch.device(device)
+
+        def up(name):
+            a = arrs.get(name)
+            return None if a is None else torch.from_numpy(np.array(a)).to(dev)
+        index = DeviceIndex.__new__(DeviceIndex)
+        index.device, index.info, index.build_stats = dev, info, None
+        index.fwd, index.rev, index.sa, index.text = up("fwd"), up("rev"), up("sa"), up("text")
+        if "ssa" in arrs:
+            index.ssa, index.sa_sample = up("ssa"), head["sa_sample"]
+        if "seed_table" in arrs:
+            index.seed_table, index.seed_K = up("seed_table"), head["seed_K"]
+        index._bind()
+        lut = up("lut")
+        rmi = None
+        if head["rmi"] is not None:
+            p = np.array(arrs["rmi_params"])
+            rmi = RmiParams(head["rmi"]["K"], head["rmi"]["level_sizes"], p[:, 0], p[:, 1], dev)
+            rmi.max_err = head["rmi"]["max_err"]
+            if head["rmi"]["none_rows"] is not None:
+                rows = np.asarray(head["rmi"]["none_rows"], np.uint32)
+                rmi.none_rows = rows
+                rmi.c.none_rows = rows.ctypes.data_as(capi.u32p)
+                rmi.c.n_none_rows = len(rows)
+            if "rmi_probe" in arrs:
+                rmi.probe = up("rmi_probe")
+                rmi.c.probe = rmi.probe.data_ptr()
+        return index, lut, head["lut_K"], rmi
+
+
 class DeviceIndex:
     """The index resident in HBM: two bucket arrays (text / reversed text), optionally the full
     suffix array and the 2-bit text (needed by RMI and by position lookups)."""

@@ -108,23 +108,50 @@ class ExactMatch:
         self.ref_sequence += "$"
         self.ref_size = len(self.ref_sequence)
 
-    def create_fm_index(self):
+    def create_fm_index(self, reference_json=False):
+        """Writes data/<ref>-FM.npz (binary suffix array).  reference_json=True also writes data/<ref>-FM.json in the
+        reference's own schema (ExactMatch.py:29-33), loadable by the reference's load_fm_index / RMI_LUT / train.py."""
         self.load_ref_sequence()
         self._build(self.ref_sequence[:-1])
         sa, _ = self._host.export()
         np.savez(path.join("data", self._npz), suffix_array=sa, ref_size=np.int64(self.ref_size))
+        if reference_json:
+            self.export_reference_json()
+
+    def export_reference_json(self, file=None):
+        """The index in the reference's on-disk schema: {bwt_array, suffix_array, occurance_matrix, count_dic, ref_size}
+        exactly as ExactMatch.create_fm_index dumps it (ExactMatch.py:29-33; inclusive occurrence counts per
+        row, 1-based suffix array).  O(5n) Python ints: for references of the reference's own scale."""
+        fm = self.fm_index
+        obj = {"bwt_array": list(fm["bwt_array"]), "suffix_array": [int(x) for x in fm["suffix_array"]],
+               "occurance_matrix": {c: [int(x) for x in v] for c, v in fm["occurance_matrix"].items()},
+               "count_dic": dict(fm["count_dic"]), "ref_size": int(fm["ref_size"])}
+        file = file or path.join("data", self.fm_file)
+        with open(file, "w+") as f:
+            f.write(json.dumps(obj, indent=4, sort_keys=True))
+        return file
 
     def load_fm_index(self):
+        """data/<ref>-FM.npz or the reference's data/<ref>-FM.json (ExactMatch.py:35-41); when both exist the newer file
+        wins.  The loaded suffix array must fit the text (ref_size rows), else ValueError."""
         if self.ref_sequence is None:
             self.load_ref_sequence()
         npz, js = path.join("data", self._npz), path.join("data", self.fm_file)
-        if path.exists(npz):
-            sa = np.load(npz)["suffix_array"]
-        elif path.exists(js):
-            with open(js, "r") as f:
-                sa = np.asarray(json.load(f)["suffix_array"], dtype=np.uint32)
-        else:
+        have = [p for p in (npz, js) if path.exists(p)]
+        if not have:
             raise FileNotFoundError("No FM index file found. Run ExactMatch.createFMIndex to create an FM index.")
+        src = max(have, key=path.getmtime)
+        if src == npz:
+            sa = np.load(npz)["suffix_array"]
+        else:
+            with open(js, "r") as f:
+                fm = json.load(f)
+            fm = fm.get("fm_index", fm)
+            if int(fm.get("ref_size", len(fm["suffix_array"]))) != len(self.ref_sequence):
+                raise ValueError(f"{js}: ref_size does not match {self.ref_seq_file}")
+            sa = np.asarray(fm["suffix_array"], dtype=np.uint32)
+        if len(sa) != len(self.ref_sequence):
+            raise ValueError(f"{src}: suffix array length {len(sa)} does not match the reference ({len(self.ref_sequence)} rows)")
         self._set_host(eng.HostIndex.from_arrays(self.ref_sequence[:-1], sa))
 
     @classmethod
@@ -281,8 +308,20 @@ class LUT:
             f.write(json.dumps({"lut": out, "lut_size": self.lut_size}, indent=4, sort_keys=True))
 
     def load_lut(self):
+        """<ref>-LUT.json as LUT.save_lut of the reference writes it (LUT.py:50-63).  The dense device table is derived
+        from the index for the file's lut_size; the file's own intervals are then checked against it (ValueError if the
+        file belongs to another reference)."""
         with open(self._file(), "r") as f:
-            self.generate_lut(json.load(f)["lut_size"])
+            obj = json.load(f)
+        self.generate_lut(obj["lut_size"])
+        entries = obj.get("lut", {})
+        if entries:
+            t = self.table.cpu().numpy().view(np.uint32).reshape(-1, 2)
+            codes = np.fromiter((int(k) for k in entries), np.int64, len(entries))
+            lo = np.fromiter((int(v[0][0]) for v in entries.values()), np.int64, len(entries))
+            hi = np.fromiter((int(v[0][1]) for v in entries.values()), np.int64, len(entries))
+            if len(entries) != int((t[:, 1] != 0).sum()) or not (np.array_equal(t[codes, 0], lo) and np.array_equal(t[codes, 0].astype(np.int64) + t[codes, 1] - 1, hi)):
+                raise ValueError(f"{self._file()} does not describe this reference")
 
 
 class RMI:
@@ -432,6 +471,32 @@ class RMI:
             self.__dict__.pop("all_buckets", None)
 
 
+def _reference_rmi_object(rmi):
+    """An object that pickles as the reference's RMI.RMI (module "RMI"): experts, models[level][k] = LinearRegression."""
+    import sys
+    import types
+    from sklearn.linear_model import LinearRegression
+    mod = sys.modules.get("RMI")
+    if mod is None or not hasattr(mod, "RMI"):
+        mod = types.ModuleType("RMI")
+        mod.RMI = type("RMI", (), {"__module__": "RMI"})
+        sys.modules["RMI"] = mod
+    obj = mod.RMI.__new__(mod.RMI)
+    models, k = [], 0
+    for n in rmi.level_sizes:
+        level = []
+        for _ in range(n):
+            m = LinearRegression()
+            m.coef_ = np.asarray([rmi.coef[k]], np.float64)
+            m.intercept_ = np.float64(rmi.intercept[k])
+            m.n_features_in_ = 1
+            level.append(m)
+            k += 1
+        models.append(level)
+    obj.__dict__.update({"experts": list(rmi.experts), "models": models})
+    return obj
+
+
 class _RefUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module == "RMI" and name == "RMI":
@@ -504,9 +569,15 @@ class RMI_LUT:
             raise RecursionError("RMI last-mile search left the table (the reference raises here too)")
         return int(lo[0]), int(hi[0])
 
-    def save(self, file):
+    def save(self, file, reference_format=False):
+        """Pickle [structure, prediction_size, data_file, rmi] (RMI_LUT.py:186-190).  reference_format=True writes what the
+        reference's own RMI_LUT.load can unpickle: an object of class RMI.RMI whose .models are sklearn LinearRegression
+        instances carrying these coefficients (needs scikit-learn; RMI.py:8,49,52-69)."""
+        rmi = self.rmi
+        if reference_format:
+            rmi = _reference_rmi_object(self.rmi)
         with open(file, "wb") as f:
-            pickle.dump([self.structure, self.prediction_size, self.data_file, self.rmi], f)
+            pickle.dump([self.structure, self.prediction_size, self.data_file, rmi], f)
 
     @staticmethod
     def load(file, matcher: ExactMatch = None):
