@@ -100,6 +100,109 @@ __global__ void __launch_bounds__(PACK_THREADS) k_pack_reads_fixed(const uint8_t
     }
 }
 
+// ---------------------------------------------------------------------------------------------- FASTQ on the device
+// A 4-line FASTQ held in device memory is cut into records here instead of on the host cores (the host scanner manages a
+// few million reads/s; the search kernels take > 100 M reads/s): line ends are counted per 16 KB tile, the tile counts are
+// prefix-summed by the caller, and a second pass gives every newline its global line number: line 4r ends where read
+// r's bases begin, line 4r+1 ends where they end.  Replaces the one-string-per-file query path of the reference
+// (ExactMatch.load_query, ExactMatch.py:104-108) for sequencer output.
+constexpr uint32_t FQ_TILE = 16384;          // bytes per block
+constexpr uint32_t FQ_THREADS = 256;         // 64 bytes per thread
+
+__device__ __forceinline__ uint32_t count_nl16(uint4 v) {
+    return __popc(__vcmpeq4(v.x, 0x0A0A0A0Au) & 0x01010101u) + __popc(__vcmpeq4(v.y, 0x0A0A0A0Au) & 0x01010101u) +
+           __popc(__vcmpeq4(v.z, 0x0A0A0A0Au) & 0x01010101u) + __popc(__vcmpeq4(v.w, 0x0A0A0A0Au) & 0x01010101u);
+}
+
+// newlines in this thread's 64-byte piece [p, p+64) of buf (clipped to n); buf is 16-byte aligned
+__device__ __forceinline__ uint32_t piece_newlines(const uint8_t* buf, uint64_t p, uint64_t n) {
+    uint32_t c = 0;
+    if (p + 64 <= n) {
+        const uint4* q = reinterpret_cast<const uint4*>(buf + p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c += count_nl16(__ldg(q + i));
+    } else {
+        for (uint64_t i = p; i < n; ++i) c += buf[i] == '\n';
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(FQ_THREADS) k_fq_count(const uint8_t* buf, uint64_t n, uint32_t* tile_counts) {
+    __shared__ uint32_t warp_sum[FQ_THREADS / 32];
+    const uint64_t p = (uint64_t)blockIdx.x * FQ_TILE + (uint64_t)threadIdx.x * 64u;
+    uint32_t c = p < n ? piece_newlines(buf, p, n) : 0u;
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+    if ((threadIdx.x & 31u) == 0) warp_sum[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (uint32_t w = 0; w < FQ_THREADS / 32; ++w) t += warp_sum[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+// err[0]: smallest byte offset at which the 4-line structure is violated (a record not starting with '@', a third line
+// not starting with '+'), ~0 if none
+__global__ void __launch_bounds__(FQ_THREADS) k_fq_records(const uint8_t* buf, uint64_t n, const unsigned long long* tile_prefix, uint64_t n_records,
+                                                           unsigned long long* seq_start, unsigned long long* seq_end, unsigned long long* err) {
+    __shared__ uint32_t scan[FQ_THREADS];
+    const uint64_t p = (uint64_t)blockIdx.x * FQ_TILE + (uint64_t)threadIdx.x * 64u;
+    const uint32_t mine = p < n ? piece_newlines(buf, p, n) : 0u;
+    scan[threadIdx.x] = mine;
+    __syncthreads();
+    for (uint32_t d = 1; d < FQ_THREADS; d <<= 1) {          // inclusive Hillis-Steele scan of 256 counts
+        const uint32_t v = threadIdx.x >= d ? scan[threadIdx.x - d] : 0u;
+        __syncthreads();
+        scan[threadIdx.x] += v;
+        __syncthreads();
+    }
+    if (mine == 0u) return;
+    unsigned long long line = tile_prefix[blockIdx.x] + scan[threadIdx.x] - mine;      // number of the first line that ends in this piece
+    const uint64_t end = p + 64 < n ? p + 64 : n;
+    for (uint64_t i = p; i < end; ++i) {
+        if (buf[i] != '\n') continue;
+        const unsigned long long r = line >> 2;
+        const uint32_t k = (uint32_t)(line & 3u);
+        if (r < n_records) {
+            if (k == 0u) seq_start[r] = i + 1;
+            else if (k == 1u) {
+                seq_end[r] = (i > 0 && buf[i - 1] == '\r') ? i - 1 : i;
+                if (i + 1 < n && buf[i + 1] != '+') atomicMin(err, (unsigned long long)i + 1);
+            } else if (k == 3u && i + 1 < n && buf[i + 1] != '@') atomicMin(err, (unsigned long long)i + 1);
+        }
+        ++line;
+    }
+}
+
+// reads scattered in a byte buffer (FASTQ sequence lines): read r = bases[start[r], start[r] + len[r])
+__global__ void __launch_bounds__(256) k_pack_reads_scattered(const uint8_t* bases, const unsigned long long* start, const uint32_t* len,
+                                                              const uint32_t* chunk_off, uint64_t n_reads, int ascii, uint32_t* packed,
+                                                              unsigned long long* bad) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp0; r < n_reads; r += n_warps) {
+        const uint64_t b0 = start[r];
+        const uint32_t L = len[r];
+        uint32_t* dst = packed + (uint64_t)chunk_off[r] * 4u;
+        const uint32_t n_words = ((L + 63u) / 64u) * 4u;
+        for (uint32_t w = lane; w < n_words; w += 32u) {
+            uint32_t v = 0;
+            const uint32_t t0 = w * 16u;
+            for (uint32_t t = 0; t < 16u && t0 + t < L; ++t) {
+                uint32_t c = bases[b0 + t0 + t];
+                if (ascii) c = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+                if (c > 3u) {
+                    atomicMin(bad, (unsigned long long)r);
+                    c = 0;
+                }
+                v |= c << (30u - 2u * t);
+            }
+            dst[w] = v;
+        }
+    }
+}
+
 }  // namespace
 }  // namespace gsm
 
@@ -133,6 +236,50 @@ int gsm_pack_reads_device(const void* bases, const uint64_t* base_off, uint32_t 
     const unsigned grid = (unsigned)std::min<uint64_t>((warps + 7) / 8, 148ull * 32);
     k_pack_reads<<<grid, 256, 0, st>>>((const uint8_t*)bases, (const unsigned long long*)base_off, fixed_len, chunk_off, n_reads, (int)ascii,
                                        (uint32_t*)packed, len_out, (unsigned long long*)scratch8);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_fastq_count_device(const void* buf, uint64_t n_bytes, uint32_t* tile_counts, void* stream) {
+    if (!buf || !tile_counts) return fail(GSM_E_INVALID, "gsm_fastq_count_device: null");
+    if ((reinterpret_cast<uintptr_t>(buf) & 15u) != 0) return fail(GSM_E_INVALID, "gsm_fastq_count_device: buf must be 16-byte aligned");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(GSM_E_NODEVICE, "no CUDA device");
+    if (n_bytes == 0) return GSM_OK;
+    const uint64_t tiles = (n_bytes + FQ_TILE - 1) / FQ_TILE;
+    if (tiles >= (1ull << 31)) return fail(GSM_E_INVALID, "gsm_fastq_count_device: buffer too large for one call");
+    k_fq_count<<<(unsigned)tiles, FQ_THREADS, 0, (cudaStream_t)stream>>>((const uint8_t*)buf, n_bytes, tile_counts);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_fastq_records_device(const void* buf, uint64_t n_bytes, const uint64_t* tile_prefix, uint64_t n_records, uint64_t* seq_start,
+                             uint64_t* seq_end, uint64_t* err8, void* stream) {
+    if (!buf || !tile_prefix || !err8 || (n_records && (!seq_start || !seq_end))) return fail(GSM_E_INVALID, "gsm_fastq_records_device: null");
+    if ((reinterpret_cast<uintptr_t>(buf) & 15u) != 0) return fail(GSM_E_INVALID, "gsm_fastq_records_device: buf must be 16-byte aligned");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(GSM_E_NODEVICE, "no CUDA device");
+    cudaStream_t st = (cudaStream_t)stream;
+    GSM_CUDA(cudaMemsetAsync(err8, 0xFF, 8, st));
+    if (n_bytes == 0 || n_records == 0) return GSM_OK;
+    const uint64_t tiles = (n_bytes + FQ_TILE - 1) / FQ_TILE;
+    k_fq_records<<<(unsigned)tiles, FQ_THREADS, 0, st>>>((const uint8_t*)buf, n_bytes, (const unsigned long long*)tile_prefix, n_records,
+                                                          (unsigned long long*)seq_start, (unsigned long long*)seq_end, (unsigned long long*)err8);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_pack_reads_scattered_device(const void* bases, const uint64_t* seq_start, const uint32_t* seq_len, const uint32_t* chunk_off,
+                                    uint64_t n_reads, uint32_t ascii, void* packed, uint64_t* scratch8, void* stream) {
+    if (!bases || !seq_start || !seq_len || !chunk_off || !packed || !scratch8) return fail(GSM_E_INVALID, "gsm_pack_reads_scattered_device: null");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(GSM_E_NODEVICE, "no CUDA device");
+    cudaStream_t st = (cudaStream_t)stream;
+    GSM_CUDA(cudaMemsetAsync(scratch8, 0xFF, 8, st));
+    if (n_reads == 0) return GSM_OK;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_reads + 7) / 8, 148ull * 32);
+    k_pack_reads_scattered<<<grid, 256, 0, st>>>((const uint8_t*)bases, (const unsigned long long*)seq_start, seq_len, chunk_off, n_reads, (int)ascii,
+                                                 (uint32_t*)packed, (unsigned long long*)scratch8);
     GSM_CUDA(cudaGetLastError());
     return GSM_OK;
 }

@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
                             a.reads + (size_t)__ldg(a.chunk_off + rid) * 4,
                             a.mem_pool + a.mem_off[rid],
                             stage, a.stage_stride,
-                            __ldg(a.len + rid), a.K, a.mem_cnt[rid], a.min_len, (uint32_t)rid, 0u, false, false};
-        order_segments(c.mems, c.n_mems);
+                            __ldg(a.len + rid), a.K, a.mem_cnt[rid] & 0x7FFFFFFFu, a.min_len, (uint32_t)rid, 0u, false, false};
+        if (!(a.mem_cnt[rid] >> 31)) order_segments(c.mems, c.n_mems);        // bit 31: the sweep already ordered the list
         bool direct = false;
         do {
             uint8_t status = GSM_READ_OK;
@@ -324,9 +324,10 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
         while (!have && rid < a.n_reads) {
             c.words = a.reads + (size_t)__ldg(a.chunk_off + rid) * 4;
             c.mems = a.mem_pool + a.mem_off[rid];
-            c.L = __ldg(a.len + rid); c.n_mems = a.mem_cnt[rid]; c.rid = (uint32_t)rid; c.n_rec = 0; c.raised = false; c.overflow = false;
+            const uint32_t mc = a.mem_cnt[rid];
+            c.L = __ldg(a.len + rid); c.n_mems = mc & 0x7FFFFFFFu; c.rid = (uint32_t)rid; c.n_rec = 0; c.raised = false; c.overflow = false;
             c.out = stage; c.cap = a.stage_stride;
-            order_segments(c.mems, c.n_mems);
+            if (!(mc >> 31)) order_segments(c.mems, c.n_mems);                 // bit 31: the sweep already ordered the list
             st = typename Sel::Seeded();
             if (c.L < c.K) { close_read(GSM_READ_TOO_SHORT); continue; }
             have = true;
@@ -762,20 +763,52 @@ int device_ready() {
     return GSM_OK;
 }
 
+// Which sweep kernel runs a batch: lane pairs (k_sweep) or one lane per read with the read in shared memory
+// (k_sweep1<false>) for reads up to SWEEP1_SMEM_MAX_LEN bases -- GSM_SWEEP_LPR=1|2 picks between them -- and
+// k_sweep1<true> (bases from global memory, grid sized by the staging budget) for anything longer, up to 65535 bases.
+enum SweepKind { SWEEP_PAIR = 0, SWEEP_LANE = 1, SWEEP_LANE_LONG = 2 };
+
+int sweep_kind(uint32_t max_len) {
+    static const int lpr = getenv("GSM_SWEEP_LPR") ? atoi(getenv("GSM_SWEEP_LPR")) : 2;
+    if (max_len > SWEEP1_SMEM_MAX_LEN) return SWEEP_LANE_LONG;
+    return lpr == 1 ? SWEEP_LANE : SWEEP_PAIR;
+}
+
 int sweep_grid(uint32_t max_len, int* blocks) {
     int dev = 0, sms = 0, per_sm = 0;
     GSM_CUDA(cudaGetDevice(&dev));
     GSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t smem = sweep_smem_bytes(max_len);
-    GSM_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep, SWEEP_THREADS, smem));
+    const int kind = sweep_kind(max_len);
+    if (kind == SWEEP_LANE) {
+        const size_t smem = sweep1_smem_bytes(max_len, false);
+        GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int a0 = 0, a1 = 0;                 // the grid must be resident for either instantiation (with / without the text shortcut)
+        GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k_sweep1<false, false>, SWEEP1_THREADS, smem));
+        GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a1, k_sweep1<false, true>, SWEEP1_THREADS, smem));
+        per_sm = a0 < a1 ? a0 : a1;
+    } else if (kind == SWEEP_LANE_LONG) {
+        int a0 = 0, a1 = 0;
+        GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k_sweep1<true, false>, SWEEP1_THREADS, sweep1_smem_bytes(max_len, true)));
+        GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a1, k_sweep1<true, true>, SWEEP1_THREADS, sweep1_smem_bytes(max_len, true)));
+        per_sm = a0 < a1 ? a0 : a1;
+    } else {
+        const size_t smem = sweep_smem_bytes(max_len);
+        GSM_CUDA(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep, SWEEP_THREADS, smem));
+    }
     if (per_sm < 1) return fail(GSM_E_CAPACITY, "read length too large for the sweep kernel's shared memory");
     *blocks = sms * per_sm;
+    if (kind == SWEEP_LANE_LONG) {        // long reads: as many blocks as the staging budget allows (2 x max_len x 16 B per lane)
+        const uint64_t fit = SWEEP1_LONG_SCRATCH / ((uint64_t)SWEEP1_THREADS * 2ull * max_len * 16ull);
+        if ((uint64_t)*blocks > fit) *blocks = fit < 1 ? 1 : (int)fit;
+    }
     return GSM_OK;
 }
 
 uint64_t sweep_scratch_bytes(int blocks, uint32_t max_len) {
-    return (uint64_t)blocks * SWEEP_GROUPS * 2ull * max_len * 16ull;
+    const uint64_t reads_per_block = sweep_kind(max_len) == SWEEP_PAIR ? SWEEP_GROUPS : SWEEP1_THREADS;
+    return (uint64_t)blocks * reads_per_block * 2ull * max_len * 16ull;
 }
 
 uint32_t select_stage_stride(uint32_t max_len) { return max_len < SELECT_STAGE ? max_len : SELECT_STAGE; }
@@ -816,7 +849,7 @@ int gsm_smem_workspace_info(uint64_t n_reads, uint32_t max_len, gsm_workspace_in
     out->quad_scratch_bytes = sweep_bytes > sel_bytes ? sweep_bytes : sel_bytes;
     out->scan_tmp_bytes = ((n_reads + SCAN_TILE - 1) / SCAN_TILE + 2) * 8ull;
     out->grid_blocks = (uint32_t)sb;
-    out->block_threads = SWEEP_THREADS;
+    out->block_threads = sweep_kind(max_len) == SWEEP_PAIR ? SWEEP_THREADS : SWEEP1_THREADS;
     return GSM_OK;
 }
 
@@ -1017,7 +1050,20 @@ int gsm_smem_sweep(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_workspa
     if (sa.seed_tab && (sa.seed_K < 1 || sa.seed_K > 16)) return fail(GSM_E_INVALID, "seed table K must be in 1..16");
     sa.mem_pool = (uint4*)ws->mem_pool; sa.mem_cap = ws->mem_cap; sa.mem_off = ws->mem_off; sa.mem_cnt = ws->mem_cnt;
     sa.scratch = (uint4*)ws->quad_scratch; sa.counters = (unsigned long long*)ws->counters;
-    k_sweep<<<sb, SWEEP_THREADS, sweep_smem_bytes(rd->max_len), stream>>>(sa);
+    // unique-match shortcut of the lane kernels: needs the suffix array and the packed text on the device (GSM_SWEEP_UNIQ=0 disables)
+    static const int uniq_env = getenv("GSM_SWEEP_UNIQ") ? atoi(getenv("GSM_SWEEP_UNIQ")) : 1;
+    sa.sa = ix->sa; sa.text = ix->text2bit; sa.n_bases = (uint32_t)(ix->n_rows - 1);
+    const bool uniq = uniq_env != 0 && ix->sa && ix->text2bit;
+    const int kind = sweep_kind(rd->max_len);
+    if (kind == SWEEP_LANE) {
+        if (uniq) k_sweep1<false, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
+        else k_sweep1<false, false><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
+    } else if (kind == SWEEP_LANE_LONG) {
+        if (uniq) k_sweep1<true, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, true), stream>>>(sa);
+        else k_sweep1<true, false><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, true), stream>>>(sa);
+    } else {
+        k_sweep<<<sb, SWEEP_THREADS, sweep_smem_bytes(rd->max_len), stream>>>(sa);
+    }
     GSM_CUDA(cudaGetLastError());
     return GSM_OK;
 }

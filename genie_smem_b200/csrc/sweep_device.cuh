@@ -38,6 +38,9 @@ struct SweepArgs {
     uint32_t* mem_cnt;
     uint4* scratch;          // per pair: [0, max_len) match staging, [max_len, 2 max_len) candidate spill
     unsigned long long* counters;
+    const uint32_t* sa;      // unique-match shortcut of the lane kernels (k_sweep1<.., true>): suffix array (1-based values) ...
+    const uint32_t* text;    // ... and the 2-bit packed text (MSB-first, readable 2 words past its end)
+    uint32_t n_bases;
 };
 
 // Shared memory: [per pair: SWEEP_CAP candidates of 16 B {end, lo, cnt, -}, then
@@ -130,6 +133,7 @@ struct DevSweepCtx {
     __device__ __forceinline__ uint32_t seed_k() const { return a.seed_K; }
     // the unique-match shortcut of sweep_logic.cuh stays compiled out of the kernel: measured slower (profiles/r01_notes.md)
     __device__ __forceinline__ constexpr bool uniq() const { return false; }
+    __device__ __forceinline__ constexpr bool uniq_back() const { return false; }
     // code of q[pos:pos+K): top 2K bits of the 64-bit window starting at base pos (MSB-first packing)
     __device__ __forceinline__ uint32_t kmer(uint32_t pos) const {
         const uint32_t* w = reinterpret_cast<const uint32_t*>(g_sweep_smem) + words0 + (pos >> 4);
@@ -190,6 +194,250 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS) k_sweep(const
                                     rev ? a.meta.prim_r : a.meta.prim_f, g, is_step);
         if (is_step) sw.consume(ctx, a.meta, r);
         else if (is_seed) sw.consume_seed(ctx, a.meta, SeedEntry{se.x, se.y, se.z, se.w});
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ one lane per read
+// The same sweep with ONE lane per read: every lane fetches whole 64-byte buckets itself (two 256-bit loads) and
+// popcounts all 192 symbols, so a warp-wide instruction of the uniform section advances 32 FM chains instead of 16, no
+// shuffles are needed, and the divergent per-read control is amortised over twice as many steps.  The kernel is bound
+// by instruction issue (profiles/r01_notes.md), which is what the quad -> pair change already showed; this is the next
+// halving.  Same Sweeper logic (sweep_logic.cuh), same outputs; chosen at run time (gsm_smem_sweep, GSM_SWEEP_LPR).
+constexpr int SWEEP1_THREADS = 128;
+constexpr int SWEEP1_CAP = 8;                              // candidates kept in shared memory per read
+constexpr int SWEEP1_MIN_BLOCKS = 6;
+
+// counts of one bucket (its two halves) below in-bucket offset r: (#symbols == c) | (#symbols < c) << 16.  E[] / T[] are the
+// per-word "equals c" / "less than c" bit masks of the bucket's 6 x 32 symbols.
+__device__ __forceinline__ uint32_t bucket_counts(const uint32_t (&E)[6], const uint32_t (&T)[6], uint32_t r) {
+    uint32_t eq = 0, lt = 0;
+#pragma unroll
+    for (int w = 0; w < 6; ++w) {
+        const uint32_t m = mask_low(clamp32((int)r - 32 * w));
+        eq += popc32(E[w] & m);
+        lt += popc32(T[w] & m);
+    }
+    return eq | (lt << 16);
+}
+
+__device__ __forceinline__ void bucket_masks(const Half& h0, const Half& h1, const SymK& k, uint32_t (&E)[6], uint32_t (&T)[6]) {
+    const uint32_t L[6] = {h0.l0, h0.l1, h0.l2, h1.l0, h1.l1, h1.l2}, H[6] = {h0.h0, h0.h1, h0.h2, h1.h0, h1.h1, h1.h2};
+#pragma unroll
+    for (int w = 0; w < 6; ++w) {
+        E[w] = (L[w] ^ k.fl) & (H[w] ^ k.fh);
+        T[w] = ((~H[w] & (~L[w] | k.X)) | (~L[w] & k.Y)) & k.nz;
+    }
+}
+
+// One FM extension step by ONE lane: both halves of the bucket of P0 and (if different) of the bucket of P1, all four
+// 256-bit loads issued before anything is consumed.
+__device__ __forceinline__ StepOut lane_step(const uint4* __restrict__ bk, uint32_t P0, uint32_t P1, uint32_t ch, uint32_t Cc,
+                                             uint32_t primary, bool active) {
+    uint32_t b0, r0, b1, r1;
+    split192(P0, b0, r0);
+    split192(P1, b1, r1);
+    Half a0 = Half{0, 0, 0, 0, 0, 0, 0, 0}, a1 = a0;
+    if (active) { a0 = ldg_half(bk, (size_t)b0 * 2); a1 = ldg_half(bk, (size_t)b0 * 2 + 1); }
+    Half c0 = a0, c1 = a1;
+    if (active && b1 != b0) { c0 = ldg_half(bk, (size_t)b1 * 2); c1 = ldg_half(bk, (size_t)b1 * 2 + 1); }
+    const SymK k = sym_consts(ch);
+    uint32_t E[6], T[6];
+    bucket_masks(a0, a1, k, E, T);
+    const uint32_t acc0 = bucket_counts(E, T, r0);
+    bucket_masks(c0, c1, k, E, T);
+    const uint32_t acc1 = bucket_counts(E, T, r1);
+    uint32_t e00, l00, e01, l01, e10, l10, e11, l11;
+    half_header(a0, ch, 0u, e00, l00);
+    half_header(a1, ch, 1u, e01, l01);
+    half_header(c0, ch, 0u, e10, l10);
+    half_header(c1, ch, 1u, e11, l11);
+    const uint32_t eq0 = e00 + e01 + (acc0 & 0xFFFFu);
+    const uint32_t eq1 = e10 + e11 + (acc1 & 0xFFFFu);
+    const uint32_t ltd = (l10 + l11 + (acc1 >> 16)) - (l00 + l01 + (acc0 >> 16));
+    return finish_step(eq0, eq1, ltd, P0, P1, ch, Cc, primary);
+}
+
+// LONG = false: the packed read is staged in shared memory (reads up to SWEEP1_SMEM_MAX_LEN bases).
+// LONG = true : the bases are read from the packed batch in global memory (L1 / L2 hits: 4 bases per byte), shared
+//               memory only holds the candidate slots, so any length up to 65535 runs; the grid is sized so that the
+//               per-lane match / candidate staging (2 x max_len x 16 bytes) fits a fixed budget.
+template <bool LONG, bool UNIQ>
+struct DevSweepCtx1 {
+    const SweepArgs& a;
+    uint32_t cand0;       // index (uint4) of this lane's candidate slots
+    uint32_t words0;      // word offset of this lane's packed read in shared memory (!LONG)
+    uint4* stage;         // global: match staging of this lane
+    uint4* spill;         // global: candidate spill of this lane
+    const uint32_t* gwords;   // LONG: the read's packed words in global memory
+    uint32_t fin_rid, fin_n;  // a finished read waiting for the warp's cooperative flush (fin_n == NO_FIN: none)
+    static constexpr uint32_t NO_FIN = 0xFFFFFFFFu;
+
+    __device__ __forceinline__ bool fetch(uint32_t& rid, uint32_t& L) {
+        const unsigned long long r = atomicAdd(&a.counters[3], 1ull);
+        if (r >= a.n_reads) return false;
+        rid = (uint32_t)r;
+        L = __ldg(a.len + rid);
+        const uint32_t off = __ldg(a.chunk_off + rid);
+        if (LONG) {
+            gwords = reinterpret_cast<const uint32_t*>(a.reads + (size_t)off);
+        } else {
+            const uint32_t nch = (L + 63u) >> 6;
+            for (uint32_t c = 0; c < nch; ++c) g_sweep_smem[(words0 >> 2) + c] = __ldg(a.reads + (size_t)off + c);
+        }
+        return true;
+    }
+    __device__ __forceinline__ uint32_t word(uint32_t w) const {
+        return LONG ? __ldg(gwords + w) : reinterpret_cast<const uint32_t*>(g_sweep_smem)[words0 + w];
+    }
+    __device__ __forceinline__ uint32_t base(uint32_t pos) const { return (word(pos >> 4) >> (30u - 2u * (pos & 15u))) & 3u; }
+    __device__ __forceinline__ uint32_t seed_k() const { return a.seed_K; }
+    // unique-match shortcut, forward direction: once q[x:pos) occurs once, its extent is read off the text (sweep_logic.cuh)
+    __device__ __forceinline__ constexpr bool uniq() const { return UNIQ; }
+    __device__ __forceinline__ constexpr bool uniq_back() const { return false; }
+    __device__ __forceinline__ uint32_t kmer(uint32_t pos) const {
+        return __funnelshift_l(word((pos >> 4) + 1u), word(pos >> 4), 2u * (pos & 15u)) >> (32u - 2u * a.seed_K);
+    }
+    // Number of leading bases (at most 64) on which text[t..) and q[p..) agree: both sides are MSB-first 2-bit words, so
+    // after one funnel shift per word to a common phase a mismatch is the first set bit of the XOR.  Callers cap the
+    // result by the bases that really exist on both sides (Sweeper::cmp_max).
+    __device__ __forceinline__ uint32_t match_forward(uint32_t t, uint32_t p) const {
+        const uint32_t tw = t >> 4, ts = 2u * (t & 15u), qw = p >> 4, qs = 2u * (p & 15u);
+        const uint32_t tlast = ((a.n_bases + 15u) >> 4) + 1u;           // the text is readable 2 words past its end
+        uint32_t T[5], Q[5];
+#pragma unroll
+        for (uint32_t i = 0; i < 5u; ++i) {
+            const uint32_t w = tw + i;
+            T[i] = __ldg(a.text + (w < tlast ? w : tlast));
+            Q[i] = word(qw + i);
+        }
+        uint32_t matched = 64u;
+#pragma unroll
+        for (int i = 3; i >= 0; --i) {
+            const uint32_t x = __funnelshift_l(T[i + 1], T[i], ts) ^ __funnelshift_l(Q[i + 1], Q[i], qs);
+            if (x != 0u) matched = 16u * (uint32_t)i + ((uint32_t)__clz((int)x) >> 1);
+        }
+        return matched;
+    }
+    __device__ __forceinline__ void cand_put(uint32_t i, uint32_t j, uint32_t lo, uint32_t cnt) {
+        if (i < (uint32_t)SWEEP1_CAP) g_sweep_smem[cand0 + i] = make_uint4(j, lo, cnt, 0u);
+        else __stcg(spill + (i - SWEEP1_CAP), make_uint4(j, lo, cnt, 0u));
+    }
+    __device__ __forceinline__ void cand_get(uint32_t i, uint32_t& j, uint32_t& lo, uint32_t& cnt) const {
+        uint4 v;
+        if (i < (uint32_t)SWEEP1_CAP) v = g_sweep_smem[cand0 + i];
+        else v = __ldcg(spill + (i - SWEEP1_CAP));
+        j = v.x; lo = v.y; cnt = v.z;
+    }
+    __device__ __forceinline__ void cand_sync() {}
+    __device__ __forceinline__ void emit(uint32_t idx, MemEntry e) { __stcg(stage + idx, make_uint4(e.se, e.lo, e.cnt, e.sweep)); }
+    // the read's matches stay in this lane's staging slots until the warp flushes them together (flush_finished)
+    __device__ __forceinline__ void finish(uint32_t rid, uint32_t n) { fin_rid = rid; fin_n = n; }
+
+    // Warp-cooperative hand-over of the finished reads' matches to the pool: one atomic per warp reserves the space, then
+    // all 32 lanes copy each finished read's staged matches (coalesced 16-byte stores) instead of the owning lane copying
+    // them one by one behind dependent L2 loads.  Lists of up to 32 matches are put in ascending order on the way -- the
+    // sweep emits every sweep's matches longest end first -- and flagged (bit 31 of mem_cnt) so that the selection
+    // kernels need not reorder them.  Called by the whole warp.
+    __device__ __forceinline__ void flush_finished() {
+        constexpr uint32_t FULLM = 0xFFFFFFFFu;
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t todo = __ballot_sync(FULLM, fin_n != NO_FIN);
+        if (todo == 0u) return;
+        // exclusive prefix of the finished reads' match counts, warp total to the pool counter
+        const uint32_t mine = fin_n != NO_FIN ? fin_n : 0u;
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULLM, incl, d);
+            if (lane >= (uint32_t)d) incl += y;
+        }
+        const uint32_t total = __shfl_sync(FULLM, incl, 31);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&a.counters[0], (unsigned long long)total);
+        base = __shfl_sync(FULLM, base, 0);
+        const bool fits = base + total <= a.mem_cap;
+        if (!fits && lane == 0) atomicOr(&a.counters[2], 1ull);
+        const unsigned long long my_off = base + (incl - mine);
+        const unsigned long long st = (unsigned long long)(uintptr_t)stage;
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t n = __shfl_sync(FULLM, fin_n, src);
+            const unsigned long long off = __shfl_sync(FULLM, my_off, src);
+            const uint4* sp = reinterpret_cast<const uint4*>((uintptr_t)__shfl_sync(FULLM, st, src));
+            if (!fits) continue;
+            if (n <= 32u) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (lane < n) v = __ldcg(sp + lane);
+                // segment = run of equal sweep ordinals (v.w), emitted in descending order of the end: reverse each run
+                const uint32_t prev = __shfl_up_sync(FULLM, v.w, 1);
+                const uint32_t heads = __ballot_sync(FULLM, lane < n && (lane == 0u || v.w != prev));
+                if (lane < n) {
+                    const uint32_t upto = heads & (0xFFFFFFFFu >> (31u - lane));          // heads at or below this lane
+                    const uint32_t s0 = 31u - (uint32_t)__clz((int)upto);
+                    const uint32_t above = lane == 31u ? 0u : heads & (0xFFFFFFFFu << (lane + 1u));
+                    const uint32_t s1 = above ? (uint32_t)__ffs((int)above) - 1u : n;
+                    a.mem_pool[off + s0 + (s1 - 1u - lane)] = v;
+                }
+            } else {
+                for (uint32_t k = lane; k < n; k += 32u) a.mem_pool[off + k] = __ldcg(sp + k);
+            }
+        }
+        if (fin_n != NO_FIN) {
+            a.mem_off[fin_rid] = fits ? (uint32_t)my_off : 0u;
+            a.mem_cnt[fin_rid] = fits ? (fin_n | (fin_n <= 32u ? 0x80000000u : 0u)) : 0u;
+            fin_n = NO_FIN;
+        }
+    }
+};
+
+constexpr uint32_t SWEEP1_SMEM_MAX_LEN = 1024;             // longer reads run k_sweep1<true> (bases from global memory)
+constexpr uint64_t SWEEP1_LONG_SCRATCH = 4ull << 30;       // staging budget that sizes the long-read grid
+
+// shared memory per lane: SWEEP1_CAP candidates + (short reads) the packed read and one readable pad chunk for kmer()
+__host__ __device__ inline uint32_t sweep1_lane_u4(uint32_t max_len, bool long_reads) {
+    return SWEEP1_CAP + (long_reads ? 0u : (max_len + 63u) / 64u + 1u);
+}
+inline size_t sweep1_smem_bytes(uint32_t max_len, bool long_reads) {
+    return (size_t)SWEEP1_THREADS * sweep1_lane_u4(max_len, long_reads) * sizeof(uint4) + 16;
+}
+
+template <bool LONG, bool UNIQ>
+__global__ void __launch_bounds__(SWEEP1_THREADS, SWEEP1_MIN_BLOCKS) k_sweep1(const SweepArgs a) {
+    using Ctx = DevSweepCtx1<LONG, UNIQ>;
+    const uint32_t lane_u4 = sweep1_lane_u4(a.max_len, LONG);
+    const uint32_t p0 = threadIdx.x * lane_u4;
+    const size_t gl = (size_t)blockIdx.x * SWEEP1_THREADS + threadIdx.x;
+    Ctx ctx{a, p0, (p0 + SWEEP1_CAP) * 4u, a.scratch + gl * 2 * a.max_len, a.scratch + gl * 2 * a.max_len + a.max_len, nullptr, 0u, Ctx::NO_FIN};
+    Sweeper<Ctx> sw;
+    for (;;) {
+        ctx.flush_finished();                 // reads finished by the last iteration's consume: before their lanes reuse the staging slots
+        const bool need = sw.next(ctx, a.meta);
+        if (__any_sync(0xFFFFFFFFu, ctx.fin_n != Ctx::NO_FIN)) ctx.flush_finished();      // reads finished inside next() (empty reads)
+        if (!__any_sync(0xFFFFFFFFu, need)) break;
+        // ONE uniform memory section per iteration: every lane issues its pending fetch here -- a seed-table entry, the
+        // (at most two) buckets of an FM step, a suffix-array value or the text words of a comparison -- so all 32 chains'
+        // loads are in flight together.
+        const bool is_seed = need && sw.pending_seed();
+        const bool is_word = UNIQ && need && sw.pending_word();
+        const bool is_cmp = UNIQ && need && sw.pending_cmp();
+        const bool is_step = need && !is_seed && !is_word && !is_cmp;
+        uint4 se = make_uint4(0u, 0u, 0u, 0u);
+        if (is_seed) se = ldg_seed(a.seed_tab + sw.P0);
+        uint32_t wv = 0u, matched = 0u;
+        if (UNIQ && is_word) wv = __ldg(a.sa + sw.aux);
+        if (UNIQ && is_cmp) {
+            matched = ctx.match_forward(sw.cmp_text(), sw.cmp_read());
+            const uint32_t mx = sw.cmp_max(a.n_bases);
+            matched = matched < mx ? matched : mx;
+        }
+        const bool rev = sw.on_reverse();
+        const StepOut r = lane_step(rev ? a.rev : a.fwd, sw.P0, sw.P0 + sw.cnt, sw.ch, a.meta.C[sw.ch & 3u],
+                                    rev ? a.meta.prim_r : a.meta.prim_f, is_step);
+        if (is_step) sw.consume(ctx, a.meta, r);
+        else if (is_seed) sw.consume_seed(ctx, a.meta, SeedEntry{se.x, se.y, se.z, se.w});
+        else if (UNIQ && is_word) sw.consume_word(ctx, a.meta, wv);
+        else if (UNIQ && is_cmp) sw.consume_cmp(ctx, a.meta, matched);
     }
 }
 

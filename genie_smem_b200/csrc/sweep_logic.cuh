@@ -72,9 +72,12 @@ constexpr uint32_t SWEEP_CMP_CHUNK = 64;   // bases compared per text fetch
 //   bool     fetch(uint32_t& rid, uint32_t& L)          next read (loads its bases), false when none
 //   uint32_t base(uint32_t pos)                         2-bit base of the current read
 //   uint32_t seed_k()                                   K of the seed table, 0 = no table
-//   bool     uniq()                                     unique-match shortcut available (k_sweep: compiled out, returns
-//                                                       false -- measured slower until sweep transitions are batched,
-//                                                       profiles/r01_notes.md; the host-compiled test runs both settings)
+//   bool     uniq()                                     unique-match shortcut available: once q[x:pos) occurs exactly once
+//                                                       the forward extension follows the TEXT (one suffix-array fetch, then
+//                                                       64 bases per compare) instead of one FM step per base.  The lane
+//                                                       kernels (k_sweep1) run it; the pair kernel compiles it out.
+//   bool     uniq_back()                                also walk unique matches to the LEFT along the text (needs the inverse
+//                                                       suffix array; host-compiled test only)
 //   uint32_t kmer(uint32_t pos)                         code of q[pos:pos+K) (LUT.convert_seq_to_num, LUT.py:37-48)
 //   void     cand_put(uint32_t i, uint32_t j, uint32_t lo, uint32_t cnt)
 //   void     cand_get(uint32_t i, uint32_t& j, uint32_t& lo, uint32_t& cnt)
@@ -222,7 +225,7 @@ struct Sweeper {
             end_sweep(c);
             return;
         }
-        if (cnt == 1u && x != lb && c.uniq()) {      // unique occurrence: extend it to the left along the text
+        if (cnt == 1u && x != lb && c.uniq() && c.uniq_back()) {      // unique occurrence: extend it to the left along the text
             pos = x;
             if (have_tpos) uniq_walk_next(c, m);
             else { aux = P0; mode = M_SAW; }

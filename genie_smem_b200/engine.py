@@ -870,6 +870,22 @@ class _ReadView:
         return r
 
 
+class _ChunkView:
+    """One self-contained chunk of reads on the device (its own packed buffer, offsets and lengths)."""
+
+    def __init__(self, packed, chunk_off, lens, n, max_len, read_id_base, lo):
+        self.packed, self.chunk_off, self.len = packed, chunk_off, lens
+        self.n, self.max_len, self.read_id_base = int(n), int(max_len), int(read_id_base)
+        self.lo, self.hi = int(lo), int(lo) + int(n)
+
+    def cstruct(self):
+        r = capi.DevReads()
+        r.n_reads = self.n
+        r.packed, r.chunk_off, r.len = self.packed.data_ptr(), self.chunk_off.data_ptr(), self.len.data_ptr()
+        r.max_len, r.read_id_base = self.max_len, self.read_id_base
+        return r
+
+
 class PipelinedEngine:
     """Host reads in, host records out, with the PCIe copies hidden behind the kernels.  The batch is cut into
     chunks; three CUDA streams run concurrently:
@@ -992,11 +1008,91 @@ class PipelinedEngine:
             raise BaseError(f"non-ACGT base in read {slot[k] + int(b[k])}")
         return res if reuse_host_buffers else res.detach()
 
-    def _run_chunks(self, method, n, copy_in, prep, min_len, K, lut, rmi, gatherer=None):
+    def run_fastq(self, method, fq, min_len=1, K=0, lut=None, rmi: RmiParams = None, read_id_base=0, reuse_host_buffers=False, n_chunks=None):
+        """FASTQ FILE BYTES in (a pinned uint8 tensor holding a 4-line FASTQ), host records out.  The host only looks for
+        a record boundary near each chunk cut (ingest.fastq_cuts: a few hundred bytes per cut); every chunk crosses PCIe
+        as raw file bytes and is cut into records and 2-bit packed ON THE GPU (gsm_fastq_count_device /
+        gsm_fastq_records_device / gsm_pack_reads_scattered_device) on the copy-in stream, ahead of the sweeps.  Read
+        lengths may differ.  Raises BaseError for a non-ACGT base (ExactMatch.py:139), ValueError for a malformed file."""
+        from . import ingest
+        fq = fq.view(-1)
+        nb_total = int(fq.numel())
+        n_ch = int(n_chunks or 2 * self.n_chunks)
+        cuts = ingest.fastq_cuts(fq.numpy(), n_ch)
+        n_ch = len(cuts) - 1
+        TILE = 16384
+        cap = self.chunk_reads
+        chunks = [None] * n_ch
+        stats_pin = self._buf(self._pin, "fq_stats", 8 * 8 * max(n_ch, 1), True)[: 64 * n_ch].view(torch.int64).view(n_ch, 8)
+        ev_parse = [None] * n_ch
+
+        def copy_in(i):
+            c0, c1 = cuts[i], cuts[i + 1]
+            nb = c1 - c0
+            raw = torch.empty(nb + 16, dtype=torch.uint8, device=self.device)
+            raw[:nb].copy_(fq[c0:c1], non_blocking=True)
+            tiles = (nb + TILE - 1) // TILE
+            cnt = torch.empty(max(tiles, 1), dtype=torch.int32, device=self.device)
+            capi.check(capi.lib.gsm_fastq_count_device(_ptr(raw), nb, _ptr(cnt), _stream()))
+            incl = torch.cumsum(cnt[:tiles].to(torch.int64), 0)
+            prefix = (incl - cnt[:tiles]).contiguous()
+            seq_start = torch.zeros(cap, dtype=torch.int64, device=self.device)
+            seq_end = torch.zeros(cap, dtype=torch.int64, device=self.device)
+            flags = torch.empty(2, dtype=torch.int64, device=self.device)          # [0] structure error offset, [1] first bad read
+            capi.check(capi.lib.gsm_fastq_records_device(_ptr(raw), nb, _ptr(prefix), cap, _ptr(seq_start), _ptr(seq_end), _ptr(flags), _stream()))
+            lens = (seq_end - seq_start).to(torch.int32)
+            coff = torch.zeros(cap + 1, dtype=torch.int32, device=self.device)
+            coff[1:] = torch.cumsum((lens + 63) // 64, 0).to(torch.int32)
+            packed = torch.empty(nb // 4 + 16 * cap + 32, dtype=torch.uint8, device=self.device)
+            capi.check(capi.lib.gsm_pack_reads_scattered_device(_ptr(raw), _ptr(seq_start), _ptr(lens), _ptr(coff), cap, 1, _ptr(packed),
+                                                                C.c_void_p(flags.data_ptr() + 8), _stream()))
+            st = torch.stack([incl[-1] if tiles else incl.new_zeros(()), lens.max().to(torch.int64), flags[0], flags[1],
+                              coff[-1].to(torch.int64)])
+            stats_pin[i, :5].copy_(st, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            ev_parse[i] = ev
+            chunks[i] = (packed, coff, lens, raw)
+            self.pack_launches += 3
+
+        seen = [0]
+
+        def prep(i):
+            ev_parse[i].synchronize()
+            n_nl, max_len, err, bad, _ = (int(x) for x in stats_pin[i, :5])
+            c0, c1 = cuts[i], cuts[i + 1]
+            n_lines = n_nl + (0 if c1 == c0 or int(fq[c1 - 1]) == 10 else 1)
+            if err != -1:
+                raise ValueError(f"malformed FASTQ near byte {c0 + err}: a record must start with '@' and its third line with '+'")
+            if n_lines % 4:
+                raise ValueError(f"truncated FASTQ: {n_lines} lines in the chunk starting at byte {c0}")
+            n_i = n_lines // 4
+            if n_i > cap:
+                raise capi.GsmError(capi.E_CAPACITY, f"a FASTQ chunk holds {n_i} reads, more than the engine's chunk capacity {cap}: raise n_chunks")
+            if bad != -1 and bad < n_i:
+                raise BaseError(f"non-ACGT base in read {seen[0] + bad}")
+            if max_len > self.max_len:
+                raise ValueError(f"a read of {max_len} bases exceeds the engine's max_len {self.max_len}")
+            packed, coff, lens, _raw = chunks[i]
+            v = _ChunkView(packed, coff, lens, n_i, self.max_len, read_id_base + seen[0], seen[0])
+            seen[0] += n_i
+            return v
+
+        self.last_h2d_bytes = nb_total
+        res = self._run_chunks(method, self.max_reads, copy_in, prep, min_len, K, lut, rmi, None, dynamic_chunks=n_ch)
+        return res if reuse_host_buffers else res.detach()
+
+    def _run_chunks(self, method, n, copy_in, prep, min_len, K, lut, rmi, gatherer=None, dynamic_chunks=0):
+        """dynamic_chunks = 0: the batch of n reads is cut by _chunk_bounds; copy_in(lo, hi) / prep(lo, hi) take read ranges.
+        dynamic_chunks = k: k chunks whose read counts are only known once they are prepared (FASTQ bytes): copy_in(i) /
+        prep(i) take the chunk index, prep's view carries .lo / .hi, and n is the capacity the outputs are sized for."""
         # with a gatherer every chunk holds a collective: all ranks must cut the same number of chunks, so the bounds are
         # those of the engine's capacity (equal on all ranks), clipped to this rank's read count
-        bounds = [min(b, n) for b in self._chunk_bounds(self.max_reads)] if gatherer is not None else self._chunk_bounds(n)
-        n_ch = len(bounds) - 1
+        if dynamic_chunks:
+            bounds, n_ch = None, int(dynamic_chunks)
+        else:
+            bounds = [min(b, n) for b in self._chunk_bounds(self.max_reads)] if gatherer is not None else self._chunk_bounds(n)
+            n_ch = len(bounds) - 1
         est = self.engines[0].rec_cap * 16
         out_rec = self._buf(self._pin, "rec", max(est, 1 << 20), True)
         out_off = self._buf(self._pin, "off", (n + 1) * 8, True)
@@ -1007,7 +1103,10 @@ class PipelinedEngine:
         with torch.cuda.stream(self.s_in):                     # every chunk's H2D, queued up front
             self.s_in.wait_event(start_ev)
             for i in range(n_ch):
-                copy_in(bounds[i], bounds[i + 1])
+                if dynamic_chunks:
+                    copy_in(i)
+                else:
+                    copy_in(bounds[i], bounds[i + 1])
                 ev = torch.cuda.Event()
                 ev.record(self.s_in)
                 ev_in.append(ev)
@@ -1049,8 +1148,8 @@ class PipelinedEngine:
             chunk_rec.append((lo, hi, rec_total, n_rec))
             rec_total += n_rec
 
+        n_seen = 0
         for i in range(n_ch):
-            lo, hi = bounds[i], bounds[i + 1]
             e = i % 2
             if len(pending) == 2:                 # workspace e still holds chunk i-2: drain it (count -> D2H) first
                 drain(pending.pop(0))
@@ -1059,7 +1158,15 @@ class PipelinedEngine:
                 self.s_comp.wait_event(ev_in[i])
                 if i - 2 in ev_out:
                     self.s_comp.wait_event(ev_out[i - 2])
-                view = prep(lo, hi)
+                if dynamic_chunks:
+                    view = prep(i)
+                    lo, hi = view.lo, view.hi
+                    if hi > n:
+                        raise capi.GsmError(capi.E_CAPACITY, f"the input holds more than the engine's {n} reads")
+                else:
+                    lo, hi = bounds[i], bounds[i + 1]
+                    view = prep(lo, hi)
+                n_seen = max(n_seen, hi)
                 eng.launch(method, view, min_len, K, lut, rmi, gatherer)
                 self._cnt_pin[e].copy_(eng.counters, non_blocking=True)
                 ev = torch.cuda.Event()
@@ -1070,6 +1177,8 @@ class PipelinedEngine:
         self.s_out.synchronize()
         self.s_comp.synchronize()
         torch.cuda.current_stream().wait_stream(self.s_out)
+        if dynamic_chunks:
+            n = n_seen
         offs = out_off.numpy()[: (n + 1) * 8].view(np.int64)
         offs[n] = rec_total
         self.kernel_launches = sum(e.kernel_launches for e in self.engines) + self.pack_launches

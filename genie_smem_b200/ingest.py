@@ -117,6 +117,42 @@ def read_fastq(path, n_policy="error", pin=True, threads=0):
     return bases, off, dropped
 
 
+def fastq_cuts(buf, n_chunks):
+    """Byte offsets that cut a 4-line FASTQ held in `buf` (uint8 array) into about n_chunks pieces at RECORD boundaries:
+    near each even split point, the first line that starts with '@' and whose next-but-one line starts with '+' (a quality
+    line may start with '@', but then the line two below it is a sequence line, never '+').  Only a few hundred bytes per
+    cut are looked at; everything else of the parse runs on the GPU (PipelinedEngine.run_fastq)."""
+    n = len(buf)
+    cuts = [0]
+
+    def line_end(p):
+        while p < n:
+            w = buf[p:p + 4096]
+            k = np.flatnonzero(w == 10)
+            if len(k):
+                return p + int(k[0])
+            p += 4096
+        return n
+
+    for i in range(1, max(int(n_chunks), 1)):
+        p = max((n * i) // n_chunks, cuts[-1])
+        while p < n:
+            cand = line_end(p) + 1                     # start of the next line
+            if cand >= n:
+                p = n
+                break
+            if buf[cand] == 64:                        # '@'
+                l2 = line_end(line_end(cand) + 1) + 1  # start of the line two below
+                if l2 < n and buf[l2] == 43:           # '+'
+                    p = cand
+                    break
+            p = cand
+        if p < n and p > cuts[-1]:
+            cuts.append(p)
+    cuts.append(n)
+    return cuts
+
+
 def write_fastq(path, reads, names=None):
     """Small helper for tests and examples."""
     with open(path, "w") as f:

@@ -150,6 +150,23 @@ int gsm_pack_reads_device(const void* bases, const uint64_t* base_off, uint32_t 
                           void* stream);
 int gsm_pack_reads_device_check(const uint64_t* scratch8, void* stream);
 
+/* FASTQ record cutting ON THE GPU (the host scanner above manages a few million reads/s; the search takes > 100 M/s).
+ * buf: the bytes of a 4-line FASTQ in DEVICE memory, 16-byte aligned.  Tiles are GSM_FASTQ_TILE bytes.
+ *   gsm_fastq_count_device    tile_counts[t] = line feeds in tile t (ceil(n_bytes / tile) uint32).  The caller prefix-sums them
+ *                             (exclusive, uint64: tile_prefix) and reads the total: lines = total (+1 without a final line feed),
+ *                             records = lines / 4.
+ *   gsm_fastq_records_device  seq_start[r] / seq_end[r] = byte range of record r's sequence line ('\r' stripped); *err8 (device
+ *                             uint64) = smallest offset where a record does not begin with '@' or its third line with '+', else ~0.
+ *   gsm_pack_reads_scattered_device  gsm_pack_reads_device for reads that are NOT contiguous: read r = bases[seq_start[r],
+ *                             seq_start[r] + seq_len[r]); chunk_off as there; scratch8 as there (gsm_pack_reads_device_check).
+ * Replaces ExactMatch.load_query (ExactMatch.py:104-108) for sequencer output; all asynchronous on `stream`. */
+#define GSM_FASTQ_TILE 16384
+int gsm_fastq_count_device(const void* buf, uint64_t n_bytes, uint32_t* tile_counts, void* stream);
+int gsm_fastq_records_device(const void* buf, uint64_t n_bytes, const uint64_t* tile_prefix, uint64_t n_records, uint64_t* seq_start,
+                             uint64_t* seq_end, uint64_t* err8, void* stream);
+int gsm_pack_reads_scattered_device(const void* bases, const uint64_t* seq_start, const uint32_t* seq_len, const uint32_t* chunk_off,
+                                    uint64_t n_reads, uint32_t ascii, void* packed, uint64_t* scratch8, void* stream);
+
 /* ------------------------------------------------------------------ device-side views */
 typedef struct {
     uint64_t n_rows;
@@ -208,7 +225,7 @@ typedef struct {
     void* quad_scratch;    /* per-resident-quad staging */
     uint64_t quad_scratch_bytes;
     uint32_t* mem_off;     /* n_reads */
-    uint32_t* mem_cnt;     /* n_reads */
+    uint32_t* mem_cnt;     /* n_reads: matches per read; bit 31 set = the list is already in ascending order */
     gsm_record* rec_tmp;   /* unordered record pool, rec_cap entries */
     uint64_t rec_cap;
     uint32_t* rec_tmp_off; /* n_reads */

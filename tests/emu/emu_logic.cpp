@@ -27,8 +27,10 @@ struct HostIndex {
 struct SweepCtx {
     const uint32_t* words = nullptr;
     uint32_t K = 0;                      // seed table K (0 = none)
-    bool use_uniq = false;               // unique-match shortcut (suffix array + inverse suffix array + text)
+    bool use_uniq = false;               // unique-match shortcut, forward (suffix array + text)
+    bool use_uniq_back = false;          // ... and to the left (inverse suffix array)
     bool uniq() const { return use_uniq; }
+    bool uniq_back() const { return use_uniq_back; }
     uint32_t seed_k() const { return K; }
     uint32_t kmer(uint32_t pos) const {
         auto rd = [&](uint64_t w) { return words[w]; };
@@ -179,8 +181,8 @@ struct SelCtx {
 extern "C" {
 struct EmuIndex {
     const void* fwd; const void* rev; const uint32_t* sa; const uint32_t* text;
-    uint32_t C[4]; uint32_t cnt[4]; uint32_t prim_f, prim_r, n_rows, pad; uint64_t n_bases;
-    const uint32_t* isa;                 // optional: enables the sweep's unique-match shortcut
+    uint32_t C[4]; uint32_t cnt[4]; uint32_t prim_f, prim_r, n_rows, uniq_mode; uint64_t n_bases;     // uniq_mode: 0 off, 1 forward only, 2 forward + backward
+    const uint32_t* isa;                 // inverse suffix array (uniq_mode 2)
 };
 }
 
@@ -219,7 +221,7 @@ int emu_sweep(const EmuIndex* ei, const uint32_t* words, uint32_t L, uint32_t* o
     HostIndex ix{(const Half*)ei->fwd, (const Half*)ei->rev, ei->sa, ei->text, {}, ei->n_bases};
     for (int c = 0; c < 4; ++c) { ix.meta.C[c] = ei->C[c]; ix.meta.cnt[c] = ei->cnt[c]; }
     ix.meta.prim_f = ei->prim_f; ix.meta.prim_r = ei->prim_r; ix.meta.n_rows = ei->n_rows;
-    SweepCtx ctx; ctx.words = words; ctx.L = L; ctx.K = seed_tab ? seed_K : 0; ctx.use_uniq = ei->isa != nullptr;
+    SweepCtx ctx; ctx.words = words; ctx.L = L; ctx.K = seed_tab ? seed_K : 0; ctx.use_uniq = ei->uniq_mode != 0; ctx.use_uniq_back = ei->uniq_mode == 2 && ei->isa != nullptr;
     Sweeper<SweepCtx> sw;
     uint64_t steps = 0;
     for (;;) {
@@ -261,7 +263,7 @@ int emu_smem(const EmuIndex* ei, int method, const uint32_t* words, uint32_t L, 
     for (int c = 0; c < 4; ++c) { ix.meta.C[c] = ei->C[c]; ix.meta.cnt[c] = ei->cnt[c]; }
     ix.meta.prim_f = ei->prim_f; ix.meta.prim_r = ei->prim_r; ix.meta.n_rows = ei->n_rows;
     if (method != 0 && L < K) return -2;
-    SweepCtx ctx; ctx.words = words; ctx.L = L; ctx.K = seed_tab ? seed_K : 0; ctx.use_uniq = ei->isa != nullptr;
+    SweepCtx ctx; ctx.words = words; ctx.L = L; ctx.K = seed_tab ? seed_K : 0; ctx.use_uniq = ei->uniq_mode != 0; ctx.use_uniq_back = ei->uniq_mode == 2 && ei->isa != nullptr;
     Sweeper<SweepCtx> sw;
     for (;;) {
         if (!sw.next(ctx, ix.meta)) break;

@@ -27,7 +27,7 @@ def build():
 
 class EmuIndex(C.Structure):
     _fields_ = [("fwd", C.c_void_p), ("rev", C.c_void_p), ("sa", C.c_void_p), ("text", C.c_void_p), ("C", C.c_uint32 * 4),
-                ("cnt", C.c_uint32 * 4), ("prim_f", C.c_uint32), ("prim_r", C.c_uint32), ("n_rows", C.c_uint32), ("pad", C.c_uint32),
+                ("cnt", C.c_uint32 * 4), ("prim_f", C.c_uint32), ("prim_r", C.c_uint32), ("n_rows", C.c_uint32), ("uniq_mode", C.c_uint32),
                 ("n_bases", C.c_uint64), ("isa", C.c_void_p)]
 
 
@@ -86,12 +86,15 @@ class Emu:
 
     @property
     def uniq(self):
-        """Unique-match shortcut of the sweep logic (needs the inverse suffix array) on / off."""
-        return bool(self.e.isa)
+        """Unique-match shortcut of the sweep logic: False / 0 off, 1 = forward only (what k_sweep1 runs: suffix array +
+        text), True / 2 = forward and backward (also needs the inverse suffix array)."""
+        return int(self.e.uniq_mode)
 
     @uniq.setter
     def uniq(self, on):
-        self.e.isa = self.isa.ctypes.data if on else None
+        mode = 2 if on is True else int(on)
+        self.e.uniq_mode = mode
+        self.e.isa = self.isa.ctypes.data if mode == 2 else None
 
     def seed_table(self, K):
         if K not in self._seed:

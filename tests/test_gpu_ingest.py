@@ -116,3 +116,65 @@ def test_fastq_file_to_records(gs, setup, tmp_path):
     bases, off, _ = gs.read_fastq(path, n_policy="error")
     with pytest.raises(KeyError):
         gs.ReadBatch.from_device_bases(torch.from_numpy(bases).cuda(), base_off=off, ascii=True)
+
+
+def _fastq_bytes(reads, rng, crlf=False, final_newline=True):
+    nl = "\r\n" if crlf else "\n"
+    recs = []
+    for i, r in enumerate(reads):
+        q = "".join(chr(int(c)) for c in rng.integers(33, 74, len(r)))
+        if i % 5 == 0 and len(q):
+            q = "@" + q[1:]                       # quality lines may start with '@': the record cutter must not be fooled
+        recs.append(f"@read{i} some description{nl}{r}{nl}+{nl}{q}{nl}")
+    data = "".join(recs)
+    if not final_newline:
+        data = data[:-len(nl)]
+    return data.encode()
+
+
+@pytest.mark.parametrize("crlf,final_newline,n_chunks", [(False, True, None), (True, True, 3), (False, False, 7)])
+def test_fastq_bytes_cut_and_packed_on_the_gpu_equal_the_string_path(gs, setup, crlf, final_newline, n_chunks):
+    """PipelinedEngine.run_fastq (file bytes in: records cut and 2-bit packed by GPU kernels) == Engine.run on the same reads
+    as Python strings.  Ragged read lengths, CRLF line ends, a missing final line feed, '@' at the start of quality lines."""
+    import torch
+    text, idx, reads = setup
+    rng = np.random.default_rng(4)
+    mixed = []
+    for k, r in enumerate(reads[:3000]):
+        mixed.append(r[: int(rng.integers(20, 152))] if k % 3 else r)
+    data = _fastq_bytes(mixed, rng, crlf, final_newline)
+    fq = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
+    plain = gs.Engine(idx, len(mixed), 160, mems_per_read=48, recs_per_read=48)
+    want = plain.run(gs.METHOD_BWA, gs.ReadBatch.from_strings(mixed), min_len=1)
+    pipe = gs.PipelinedEngine(idx, len(mixed) + 10, 160, n_chunks=4, mems_per_read=48, recs_per_read=48)
+    got = pipe.run_fastq(gs.METHOD_BWA, fq, min_len=1, n_chunks=n_chunks)
+    assert len(got.offsets) == len(mixed) + 1
+    assert np.array_equal(got.offsets, want.offsets) and np.array_equal(got.records, want.records) and np.array_equal(got.status, want.status)
+    lut = gs.lut_build(idx, 8)
+    got = pipe.run_fastq(gs.METHOD_LUT, fq, K=8, lut=lut)
+    want = plain.run(gs.METHOD_LUT, gs.ReadBatch.from_strings(mixed), K=8, lut=lut)
+    assert np.array_equal(got.offsets, want.offsets) and np.array_equal(got.records, want.records) and np.array_equal(got.status, want.status)
+
+
+def test_fastq_on_the_gpu_reports_bad_input(gs, setup):
+    import torch
+    text, idx, reads = setup
+    rng = np.random.default_rng(5)
+    pipe = gs.PipelinedEngine(idx, 1000, 160, n_chunks=2, mems_per_read=48, recs_per_read=48)
+
+    def run(data):
+        return pipe.run_fastq(gs.METHOD_BWA, torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory(), min_len=1)
+
+    good = _fastq_bytes(reads[:200], rng)
+    assert len(run(good).offsets) == 201
+    bad_base = _fastq_bytes(reads[:100] + [reads[100][:70] + "N" + reads[100][71:]] + reads[101:200], rng)
+    with pytest.raises(KeyError):                              # BaseError is a KeyError (the reference's, ExactMatch.py:139) and a ValueError
+        run(bad_base)
+    lines = good.decode().split("\n")
+    lines[4 * 50 + 2] = "-"                                     # third line of record 50 does not start with '+'
+    with pytest.raises(ValueError):
+        run("\n".join(lines).encode())
+    with pytest.raises(ValueError):
+        run(good[: len(good) // 2 + 7])                         # truncated in the middle of a record
+    with pytest.raises(Exception):
+        gs.PipelinedEngine(idx, 50, 160, n_chunks=2).run_fastq(gs.METHOD_BWA, torch.frombuffer(bytearray(good), dtype=torch.uint8).pin_memory())

@@ -534,3 +534,30 @@ def test_selection_staging_overflow_reruns_the_read(gs, matchers):
     res = s.get_smems_rmi_batch(reads)
     expr = _oracle_dicts(text, gidx["suffix_array"], 2, reads, rmi=p)
     _check_against_oracle(gs, res, reads, expr, "rmi long")
+
+
+def test_reads_longer_than_the_shared_memory_path_vs_oracle(gs, matchers):
+    """Reads above 1,024 bases run the long-read sweep (bases from global memory, grid sized by the staging budget); the
+    reference's get_SMEMS / get_smems_lut / create_query(query_size) take any length.  Up to 60,000 bases here (records
+    carry 16-bit read offsets: 65,535 is the documented limit)."""
+    gidx, m = matchers["big_data"]
+    text = gidx["text"]
+    rng = random.Random(33)
+    reads = []
+    for L in (1025, 1100, 3000, 9000, 30000, 60000):
+        p = rng.randrange(0, len(text) - L)
+        q = list(text[p:p + L])
+        for k in range(L):
+            if rng.random() < 0.02:
+                q[k] = rng.choice("ACGT")
+        reads.append("".join(q))
+    reads.append("".join(rng.choice("ACGT") for _ in range(5000)))
+    reads.append(text[500:2600])                                            # one exact 2,100-base stretch
+    reads.append("ACGT" * 10)                                               # a short read in the same batch
+    s = gs.SMEM(m)
+    s.lut.generate_lut(10)
+    exp = _oracle_dicts(text, gidx["suffix_array"], 0, reads, min_len=1)
+    assert _dicts(reads, s.get_SMEMS_batch(reads, 1)) == exp
+    assert _dicts(reads, s.get_smems_lut_batch(reads)) == _oracle_dicts(text, gidx["suffix_array"], 1, reads, K=10)
+    with pytest.raises(ValueError):
+        s.get_SMEMS_batch(["A" * 65536], 1)

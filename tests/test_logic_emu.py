@@ -91,7 +91,7 @@ def test_sweep_and_select_logic_vs_reference(emus, fname, stride, seed_K):
     g = gu.load_json(fname)
     _, em = emus[g["ref"]]
     em.seed_K = seed_K
-    em.uniq = seed_K == 9                 # unique-match shortcut of sweep_logic.cuh on for one of the three settings
+    em.uniq = {0: 0, 5: 1, 9: 2}[seed_K]  # unique-match shortcut of sweep_logic.cuh: off / forward only (the kernel's) / both directions
     if seed_K:
         stride *= 2
     reads = g["reads"]
@@ -114,7 +114,7 @@ def test_sweep_and_select_logic_vs_reference(emus, fname, stride, seed_K):
                 assert records_to_dict(q, r) == e
 
 
-@pytest.mark.parametrize("uniq", [False, True])
+@pytest.mark.parametrize("uniq", [0, 1, 2])
 @pytest.mark.parametrize("seed_K", [0, 1, 2, 3, 4, 6, 8])
 def test_maximal_matches_are_exactly_the_right_maximal_LS_pairs(emus, seed_K, uniq):
     """sweep output == {(LS[j], j) : j == L or LS[j+1] > LS[j]} with true SA intervals, with and without the seed table
@@ -158,7 +158,7 @@ ACGT = st.text(alphabet="ACGT", min_size=1, max_size=60)
 @settings(max_examples=60, deadline=None)
 @given(text=st.one_of(st.text(alphabet="ACGT", min_size=8, max_size=200),
                       st.builds(lambda u, k: (u * k)[:200], st.text(alphabet="ACGT", min_size=1, max_size=7), st.integers(2, 40))),
-       reads=st.lists(ACGT, min_size=1, max_size=6), K=st.integers(2, 5), seed_K=st.integers(0, 6), uniq=st.booleans())
+       reads=st.lists(ACGT, min_size=1, max_size=6), K=st.integers(2, 5), seed_K=st.integers(0, 6), uniq=st.integers(0, 2))
 def test_property_random_and_repetitive_references(text, reads, K, seed_K, uniq):
     if len(set(text)) < 4:
         text = text + "ACGT"           # parity domain: all four bases occur

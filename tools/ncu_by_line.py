@@ -26,6 +26,17 @@ for ln in open(dis_txt):
     if m:
         addr2line[int(m.group(1), 16)] = (cur, m.group(2).strip())
 rows = list(csv.reader(open(sass_csv)))
+# the dump may hold several kernels, each introduced by a "Kernel Name" row: keep the one whose name matches
+want = sys.argv[4] if len(sys.argv) > 4 else None
+blocks, cur_rows = [], None
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        cur_rows = [r]
+        blocks.append(cur_rows)
+    elif cur_rows is not None:
+        cur_rows.append(r)
+rows = next((b for b in blocks if want is None or want in b[0][1]), blocks[0])
+print("kernel:", rows[0][1])
 hdr = rows[1]
 ai, ii, ti, si = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
 base = None

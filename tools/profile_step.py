@@ -38,7 +38,7 @@ def main():
         method, kw = g.METHOD_LUT, {"K": bench.LUT_K, "lut": g.lut_build(index, bench.LUT_K)}
     elif a.method == "rmi":
         experts = bench.CONFIGS["c3" if a.ref_bases < 500_000_000 else "c4"]["experts"]
-        method, kw = g.METHOD_RMI, {"rmi": bench.train_rmi(index, bench.RMI_K, experts, "cuda")}
+        method, kw = g.METHOD_RMI, {"rmi": bench.train_rmi(index, bench.RMI_K, experts, "cuda", probe_table=False)}
     torch.cuda.synchronize()
     print(f"setup {time.time()-t0:.1f}s, seed table K={index.seed_K}", file=sys.stderr)
     for _ in range(1 + a.steps):
