@@ -95,6 +95,17 @@ struct DevSelCtx {
     uint32_t L, K, n_mems, min_len, rid, n_rec;
     bool raised;
     bool overflow;        // more records than slots: counted, not stored
+    // compact copy of the first matches' (start | end << 16) words: the frame machine's lookups are binary searches over
+    // starts and ends, i.e. chains of dependent loads; from this per-thread array they are L1 hits instead of 16-byte
+    // entries spread over the pool (L2)
+    static constexpr uint32_t LSE_CAP = 32;
+    uint32_t lse[LSE_CAP];
+
+    __device__ __forceinline__ void cache_se() {
+        const uint32_t n = n_mems < LSE_CAP ? n_mems : LSE_CAP;
+        for (uint32_t k = 0; k < n; ++k) lse[k] = mems[k].x;
+    }
+    __device__ __forceinline__ uint32_t se(uint32_t k) const { return k < LSE_CAP ? lse[k] : mems[k].x; }
 
     __device__ __forceinline__ MemEntry mem(uint32_t k) const {
         uint4 v = mems[k];
@@ -250,8 +261,9 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
                             a.reads + (size_t)__ldg(a.chunk_off + rid) * 4,
                             a.mem_pool + a.mem_off[rid],
                             stage, a.stage_stride,
-                            __ldg(a.len + rid), a.K, a.mem_cnt[rid] & 0x7FFFFFFFu, a.min_len, (uint32_t)rid, 0u, false, false};
+                            __ldg(a.len + rid), a.K, a.mem_cnt[rid] & 0x7FFFFFFFu, a.min_len, (uint32_t)rid, 0u, false, false, {}};
         if (!(a.mem_cnt[rid] >> 31)) order_segments(c.mems, c.n_mems);        // bit 31: the sweep already ordered the list
+        c.cache_se();
         bool direct = false;
         do {
             uint8_t status = GSM_READ_OK;
@@ -308,7 +320,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
     size_t rid = gtid;
     bool have = false;
     uint4* const stage = a.stage + gtid * a.stage_stride;
-    DevSelCtx<METHOD> c{a, nullptr, nullptr, stage, a.stage_stride, 0u, a.K, 0u, a.min_len, 0u, 0u, false, false};
+    DevSelCtx<METHOD> c{a, nullptr, nullptr, stage, a.stage_stride, 0u, a.K, 0u, a.min_len, 0u, 0u, false, false, {}};
     bool direct = false;
     typename Sel::Seeded st;
     int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
@@ -328,6 +340,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
             c.L = __ldg(a.len + rid); c.n_mems = mc & 0x7FFFFFFFu; c.rid = (uint32_t)rid; c.n_rec = 0; c.raised = false; c.overflow = false;
             c.out = stage; c.cap = a.stage_stride;
             if (!(mc >> 31)) order_segments(c.mems, c.n_mems);                 // bit 31: the sweep already ordered the list
+            c.cache_se();
             st = typename Sel::Seeded();
             if (c.L < c.K) { close_read(GSM_READ_TOO_SHORT); continue; }
             have = true;
@@ -345,32 +358,70 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
         const uint32_t nwin = st.first ? 1u : c.K;
         uint32_t whit = 0, wtrue = 0, redo = 0;
         // ---------------- pass 1: lookups, warp in lock step
-        if (METHOD == GSM_METHOD_LUT) {
+        // visited windows of this round, as a bit mask (window i covers q[cpos_i : cpos_i + K), cpos_i = first ? 0 : e - i)
+        uint32_t vis = 0;
+        if (have) {
             for (uint32_t i = 0; i < nwin; ++i) {
                 const uint32_t cpos = st.first ? 0u : st.e - i;
-                if (have && (st.first || (i < st.plen && cpos + c.K <= c.L))) {
-                    const uint2 t = __ldg(a.lut + c.window_code(cpos));
-                    wlo[i] = t.x; whi[i] = (int64_t)t.x + t.y - 1;
-                    wtrue |= 1u << i;
-                    if (t.y != 0u) whit |= 1u << i;
-                }
+                if (st.first || (i < st.plen && cpos + c.K <= c.L)) vis |= 1u << i;
             }
-        } else if (arith) {
-            for (uint32_t i = 0; i < nwin; ++i) {
-                const uint32_t cpos = st.first ? 0u : st.e - i;
-                if (have && (st.first || (i < st.plen && cpos + c.K <= c.L))) {
-                    const int64_t row0 = RmiGallop::predicted_row(a.rmi, c.window_code(cpos), a.meta.n_rows);
-                    uint32_t A, n;
-                    c.window_bounds(cpos, A, n);
-                    int64_t lo, hi;
-                    if (rmi_arith_lookup(a.rmi, row0, A, n, a.meta.n_rows, lo, hi)) {
-                        wlo[i] = lo; whi[i] = hi;
-                        wtrue |= 1u << i;
-                        if (hi >= lo) whit |= 1u << i;
-                    } else {
-                        redo |= 1u << i;
+        }
+        constexpr uint32_t WB = 4;                          // windows whose table fetches are issued together (independent loads in flight)
+        if (METHOD == GSM_METHOD_LUT) {
+            for (uint32_t i0 = 0; i0 < nwin; i0 += WB) {
+                uint2 t[WB];
+#pragma unroll
+                for (uint32_t j = 0; j < WB; ++j)
+                    if ((vis >> (i0 + j)) & 1u) t[j] = __ldg(a.lut + c.window_code(st.first ? 0u : st.e - (i0 + j)));
+#pragma unroll
+                for (uint32_t j = 0; j < WB; ++j)
+                    if ((vis >> (i0 + j)) & 1u) {
+                        wlo[i0 + j] = t[j].x; whi[i0 + j] = (int64_t)t[j].x + t[j].y - 1;
+                        if (t[j].y != 0u) whit |= 1u << (i0 + j);
                     }
+            }
+            wtrue = vis;
+        } else if (arith) {
+            const uint4* fwd = a.fwd;
+            auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
+            for (uint32_t i0 = 0; i0 < nwin; i0 += WB) {
+                uint32_t A[WB], n[WB];
+                int64_t row0[WB];
+#pragma unroll
+                for (uint32_t j = 0; j < WB; ++j)          // stage 1: the seed-table entries of the windows' last seed_K bases
+                    if ((vis >> (i0 + j)) & 1u) {
+                        const uint32_t cpos = st.first ? 0u : st.e - (i0 + j);
+                        const uint32_t* w = c.words;
+                        auto rd = [w](uint64_t x) { return __ldg(w + x); };
+                        const uint4 e = __ldg(a.seed_tab + kmer_code(rd, (uint64_t)cpos + c.K - a.seed_K, a.seed_K));
+                        A[j] = e.x; n[j] = e.y;
+                    }
+#pragma unroll
+                for (uint32_t j = 0; j < WB; ++j)          // ... while they travel: the model predictions (parameters are L2-resident)
+                    if ((vis >> (i0 + j)) & 1u)
+                        row0[j] = RmiGallop::predicted_row(a.rmi, c.window_code(st.first ? 0u : st.e - (i0 + j)), a.meta.n_rows);
+                for (uint32_t p = c.K - a.seed_K; p > 0; --p) {        // stage 2: K - seed_K backward steps, the windows' buckets in flight together
+#pragma unroll
+                    for (uint32_t j = 0; j < WB; ++j)
+                        if ((vis >> (i0 + j)) & 1u) {
+                            const uint32_t cpos = st.first ? 0u : st.e - (i0 + j);
+                            const uint32_t ch = c.base(cpos + p - 1);
+                            const StepOut r = step_single(load, A[j], A[j] + n[j], ch, a.meta.C[ch], a.meta.prim_f);
+                            A[j] = r.lo_new; n[j] = r.cnt_new;
+                        }
                 }
+#pragma unroll
+                for (uint32_t j = 0; j < WB; ++j)          // stage 3: the error-bounded search replayed on row numbers
+                    if ((vis >> (i0 + j)) & 1u) {
+                        int64_t lo, hi;
+                        if (rmi_arith_lookup(a.rmi, row0[j], A[j], n[j], a.meta.n_rows, lo, hi)) {
+                            wlo[i0 + j] = lo; whi[i0 + j] = hi;
+                            wtrue |= 1u << (i0 + j);
+                            if (hi >= lo) whit |= 1u << (i0 + j);
+                        } else {
+                            redo |= 1u << (i0 + j);
+                        }
+                    }
             }
         } else if (a.rmi.n_none != 0) {
             // probe-based error-bounded search (select_logic.cuh, RmiGallop / RmiLower / RmiUpper): each phase runs over ALL
@@ -418,11 +469,8 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
                            [&]() { c.probe_row(ub.row(), sv, c64); ub.feed(sv, c64); });
                 whit |= ubm;
             }
-        } else if (have) {
-            for (uint32_t i = 0; i < nwin; ++i) {
-                const uint32_t cpos = st.first ? 0u : st.e - i;
-                if (st.first || (i < st.plen && cpos + c.K <= c.L)) redo |= 1u << i;
-            }
+        } else {
+            redo = vis;
         }
         if (METHOD == GSM_METHOD_RMI && __any_sync(FULL, redo != 0)) {
             RmiSearch rs;
@@ -769,9 +817,14 @@ int device_ready() {
 enum SweepKind { SWEEP_PAIR = 0, SWEEP_LANE = 1, SWEEP_LANE_LONG = 2 };
 
 int sweep_kind(uint32_t max_len) {
-    static const int lpr = getenv("GSM_SWEEP_LPR") ? atoi(getenv("GSM_SWEEP_LPR")) : 2;
+    static const int lpr = getenv("GSM_SWEEP_LPR") ? atoi(getenv("GSM_SWEEP_LPR")) : 1;
     if (max_len > SWEEP1_SMEM_MAX_LEN) return SWEEP_LANE_LONG;
-    return lpr == 1 ? SWEEP_LANE : SWEEP_PAIR;
+    return lpr == 2 ? SWEEP_PAIR : SWEEP_LANE;
+}
+
+int sweep_blocks_env() {       // GSM_SWEEP_BLOCKS=7|8: the lane kernel compiled for more resident blocks (fewer registers); A/B switch
+    static const int v = getenv("GSM_SWEEP_BLOCKS") ? atoi(getenv("GSM_SWEEP_BLOCKS")) : 0;
+    return v;
 }
 
 int sweep_grid(uint32_t max_len, int* blocks) {
@@ -783,10 +836,14 @@ int sweep_grid(uint32_t max_len, int* blocks) {
         const size_t smem = sweep1_smem_bytes(max_len, false);
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int a0 = 0, a1 = 0;                 // the grid must be resident for either instantiation (with / without the text shortcut)
         GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k_sweep1<false, false>, SWEEP1_THREADS, smem));
         GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a1, k_sweep1<false, true>, SWEEP1_THREADS, smem));
         per_sm = a0 < a1 ? a0 : a1;
+        if (sweep_blocks_env() == 7) GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep1<false, true, 7>, SWEEP1_THREADS, smem));
+        if (sweep_blocks_env() == 8) GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep1<false, true, 8>, SWEEP1_THREADS, smem));
     } else if (kind == SWEEP_LANE_LONG) {
         int a0 = 0, a1 = 0;
         GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k_sweep1<true, false>, SWEEP1_THREADS, sweep1_smem_bytes(max_len, true)));
@@ -1056,7 +1113,9 @@ int gsm_smem_sweep(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_workspa
     const bool uniq = uniq_env != 0 && ix->sa && ix->text2bit;
     const int kind = sweep_kind(rd->max_len);
     if (kind == SWEEP_LANE) {
-        if (uniq) k_sweep1<false, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
+        if (uniq && sweep_blocks_env() == 7) k_sweep1<false, true, 7><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
+        else if (uniq && sweep_blocks_env() == 8) k_sweep1<false, true, 8><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
+        else if (uniq) k_sweep1<false, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
         else k_sweep1<false, false><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
     } else if (kind == SWEEP_LANE_LONG) {
         if (uniq) k_sweep1<true, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, true), stream>>>(sa);

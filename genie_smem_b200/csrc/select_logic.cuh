@@ -578,6 +578,7 @@ GSM_HD bool true_sequential(Base base, LoadHalf load, const IndexMeta& meta, uin
 // Ctx must provide:
 //   uint32_t L, K, n_mems;  uint32_t min_len;
 //   MemEntry mem(uint32_t k)                 k-th maximal match, sorted by end (and start)
+//   uint32_t se(uint32_t k)                  its start | end << 16 word alone
 //   uint32_t base(uint32_t pos)
 //   uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi, uint32_t& wtrue)
 //                                            LUT / RMI lookups of the windows of one round: window i covers
@@ -596,6 +597,10 @@ template <typename Ctx>
 struct Selector {
     GSM_HD static uint32_t s_of(const MemEntry& e) { return e.se & 0xFFFFu; }
     GSM_HD static uint32_t e_of(const MemEntry& e) { return e.se >> 16; }
+    // start / end of match k from its packed (start | end << 16) word alone: Ctx::se(k) may come from a compact per-read
+    // copy (the lookups below only need these 4 bytes of the 16-byte entries)
+    GSM_HD static uint32_t sk(Ctx& c, uint32_t k) { return c.se(k) & 0xFFFFu; }
+    GSM_HD static uint32_t ek(Ctx& c, uint32_t k) { return c.se(k) >> 16; }
 
     // Starts and ends of the maximal matches both increase strictly with k, so every lookup into the list is a
     // binary search: first k with e_k > p (or >= with `incl`), and number of k with s_k <= p.
@@ -603,7 +608,7 @@ struct Selector {
         uint32_t hi = c.n_mems;
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (e_of(c.mem(mid)) <= p) lo = mid + 1; else hi = mid;
+            if (ek(c, mid) <= p) lo = mid + 1; else hi = mid;
         }
         return lo;
     }
@@ -611,7 +616,7 @@ struct Selector {
         uint32_t lo = 0, hi = c.n_mems;
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (s_of(c.mem(mid)) <= p) lo = mid + 1; else hi = mid;
+            if (sk(c, mid) <= p) lo = mid + 1; else hi = mid;
         }
         return lo;
     }
@@ -623,9 +628,9 @@ struct Selector {
         from = first_end_above(c, p, from);
         uint32_t best = from, bestlen = 0;
         for (uint32_t k = from; k < c.n_mems; ++k) {
-            MemEntry m = c.mem(k);
-            if (s_of(m) > p) break;
-            uint32_t len = e_of(m) - s_of(m);
+            const uint32_t w = c.se(k), st = w & 0xFFFFu;
+            if (st > p) break;
+            const uint32_t len = (w >> 16) - st;
             if (len > bestlen) { bestlen = len; best = k; }
         }
         return best;
@@ -663,7 +668,7 @@ struct Selector {
     GSM_HD static uint32_t F_of(Ctx& c, uint32_t p) {
         const uint32_t n = count_starts_upto(c, p);
         if (n == 0) return p;
-        const uint32_t e = e_of(c.mem(n - 1));
+        const uint32_t e = ek(c, n - 1);
         return e > p ? e : p;
     }
 
@@ -671,9 +676,10 @@ struct Selector {
     // (the usual case); false = one backward search from j down to i is needed (Ctx::interval).
     GSM_HD static bool listed_iv(Ctx& c, uint32_t i, uint32_t j, int64_t& lo, int64_t& hi) {
         const uint32_t k = j ? first_end_above(c, j - 1) : 0u;
-        if (k < c.n_mems) {
-            MemEntry m = c.mem(k);
-            if (e_of(m) == j && s_of(m) == i) { lo = (int64_t)m.lo; hi = (int64_t)m.lo + m.cnt - 1; return true; }
+        if (k < c.n_mems && c.se(k) == (i | (j << 16))) {
+            const MemEntry m = c.mem(k);
+            lo = (int64_t)m.lo; hi = (int64_t)m.lo + m.cnt - 1;
+            return true;
         }
         return false;
     }
@@ -707,18 +713,16 @@ struct Selector {
         uint32_t jmax = all_keys ? (f > pc + K ? f : pc + K) : pc + K;
         // extended keys: j in [pc+K, jmax] with LS[j] < pc; only maximal-match ends and jmax matter
         bool have = false;
-        uint32_t bi = 0, bj = 0, blo = 0, bcnt = 0;
+        uint32_t bi = 0, bj = 0, bk = 0;
         bool b_from_mem = false;
         if (seed_true) {
             for (uint32_t k = first_end_above(c, pc + K - 1); k < c.n_mems; ++k) {
-                MemEntry m = c.mem(k);
-                uint32_t s = s_of(m), e = e_of(m);
+                const uint32_t w = c.se(k), s = w & 0xFFFFu, e = w >> 16;
                 if (s >= pc) break;                    // starts are sorted: no further left extension
                 uint32_t j = e <= jmax ? e : jmax;     // plateau end, or the key range's last key
                 if (!have || (j - s) > (bj - bi)) {
-                    have = true; bi = s; bj = j;
+                    have = true; bi = s; bj = j; bk = k;
                     b_from_mem = (j == e);
-                    blo = m.lo; bcnt = m.cnt;
                 }
                 if (e >= jmax) break;
             }
@@ -730,7 +734,8 @@ struct Selector {
             return lazy_iv(pc, fend);
         }
         if (!b_from_mem) return lazy_iv(bi, bj);
-        return known(bi, bj, (int64_t)blo, (int64_t)blo + bcnt - 1);
+        const MemEntry bm = c.mem(bk);
+        return known(bi, bj, (int64_t)bm.lo, (int64_t)bm.lo + bm.cnt - 1);
     }
 
     // get_smems_lut / get_smems_rmi: the frame machine of SMEM.py:49-186 / :235-379, one ROUND at a time.  A round =

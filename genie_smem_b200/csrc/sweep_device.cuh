@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS) k_sweep(const
 // halving.  Same Sweeper logic (sweep_logic.cuh), same outputs; chosen at run time (gsm_smem_sweep, GSM_SWEEP_LPR).
 constexpr int SWEEP1_THREADS = 128;
 constexpr int SWEEP1_CAP = 8;                              // candidates kept in shared memory per read
-constexpr int SWEEP1_MIN_BLOCKS = 6;
+constexpr int SWEEP1_MIN_BLOCKS = 6;                       // default register budget: 85 per thread (see k_sweep1's MB)
 
 // counts of one bucket (its two halves) below in-bucket offset r: (#symbols == c) | (#symbols < c) << 16.  E[] / T[] are the
 // per-word "equals c" / "less than c" bit masks of the bucket's 6 x 32 symbols.
@@ -229,32 +229,47 @@ __device__ __forceinline__ void bucket_masks(const Half& h0, const Half& h1, con
     }
 }
 
-// One FM extension step by ONE lane: both halves of the bucket of P0 and (if different) of the bucket of P1, all four
-// 256-bit loads issued before anything is consumed.
-__device__ __forceinline__ StepOut lane_step(const uint4* __restrict__ bk, uint32_t P0, uint32_t P1, uint32_t ch, uint32_t Cc,
-                                             uint32_t primary, bool active) {
+// One FM extension step by ONE lane, ONE bucket per pass.  Rows P0 and P1 usually fall into the same 192-row bucket
+// (the interval is narrow after the seed): one pass reads that bucket (two 256-bit loads), builds the "equals c" /
+// "less than c" masks once and counts below both offsets.  When they straddle two buckets (about one step in eight) the
+// first pass banks the counts at P0 and the lane comes back in the next iteration for P1's bucket: one more trip for
+// those steps instead of 16 more live registers and a second set of masks in every step.
+struct LanePartial {
+    uint32_t eq0, lt0;
+    bool have;
+};
+
+__device__ __forceinline__ bool lane_step(const uint4* __restrict__ bk, uint32_t P0, uint32_t P1, uint32_t ch, uint32_t Cc, uint32_t primary,
+                                          bool active, LanePartial& part, StepOut& out) {
     uint32_t b0, r0, b1, r1;
     split192(P0, b0, r0);
     split192(P1, b1, r1);
+    const bool second = part.have;
+    const uint32_t b = second ? b1 : b0;
     Half a0 = Half{0, 0, 0, 0, 0, 0, 0, 0}, a1 = a0;
-    if (active) { a0 = ldg_half(bk, (size_t)b0 * 2); a1 = ldg_half(bk, (size_t)b0 * 2 + 1); }
-    Half c0 = a0, c1 = a1;
-    if (active && b1 != b0) { c0 = ldg_half(bk, (size_t)b1 * 2); c1 = ldg_half(bk, (size_t)b1 * 2 + 1); }
+    if (active) { a0 = ldg_half(bk, (size_t)b * 2); a1 = ldg_half(bk, (size_t)b * 2 + 1); }
     const SymK k = sym_consts(ch);
     uint32_t E[6], T[6];
     bucket_masks(a0, a1, k, E, T);
-    const uint32_t acc0 = bucket_counts(E, T, r0);
-    bucket_masks(c0, c1, k, E, T);
-    const uint32_t acc1 = bucket_counts(E, T, r1);
-    uint32_t e00, l00, e01, l01, e10, l10, e11, l11;
-    half_header(a0, ch, 0u, e00, l00);
-    half_header(a1, ch, 1u, e01, l01);
-    half_header(c0, ch, 0u, e10, l10);
-    half_header(c1, ch, 1u, e11, l11);
-    const uint32_t eq0 = e00 + e01 + (acc0 & 0xFFFFu);
-    const uint32_t eq1 = e10 + e11 + (acc1 & 0xFFFFu);
-    const uint32_t ltd = (l10 + l11 + (acc1 >> 16)) - (l00 + l01 + (acc0 >> 16));
-    return finish_step(eq0, eq1, ltd, P0, P1, ch, Cc, primary);
+    const uint32_t accA = bucket_counts(E, T, second ? r1 : r0);
+    const uint32_t accB = bucket_counts(E, T, r1);
+    uint32_t e0, l0, e1, l1;
+    half_header(a0, ch, 0u, e0, l0);
+    half_header(a1, ch, 1u, e1, l1);
+    const uint32_t he = e0 + e1, hl = l0 + l1;
+    if (!active) return false;
+    if (!second && b1 != b0) {                       // P1 lies in the next bucket: bank P0's counts, come back for it
+        part.eq0 = he + (accA & 0xFFFFu);
+        part.lt0 = hl + (accA >> 16);
+        part.have = true;
+        return false;
+    }
+    const uint32_t eq0 = second ? part.eq0 : he + (accA & 0xFFFFu);
+    const uint32_t eq1 = he + ((second ? accA : accB) & 0xFFFFu);
+    const uint32_t ltd = second ? hl + (accA >> 16) - part.lt0 : (accB >> 16) - (accA >> 16);
+    part.have = false;
+    out = finish_step(eq0, eq1, ltd, P0, P1, ch, Cc, primary);
+    return true;
 }
 
 // LONG = false: the packed read is staged in shared memory (reads up to SWEEP1_SMEM_MAX_LEN bases).
@@ -402,14 +417,17 @@ inline size_t sweep1_smem_bytes(uint32_t max_len, bool long_reads) {
     return (size_t)SWEEP1_THREADS * sweep1_lane_u4(max_len, long_reads) * sizeof(uint4) + 16;
 }
 
-template <bool LONG, bool UNIQ>
-__global__ void __launch_bounds__(SWEEP1_THREADS, SWEEP1_MIN_BLOCKS) k_sweep1(const SweepArgs a) {
+// MB = resident blocks per SM the register allocation aims at (6: 80 registers, 7: 72, 8: 64 with spills); measured per
+// workload by tools/sweep_ab.py (GSM_SWEEP_BLOCKS)
+template <bool LONG, bool UNIQ, int MB = SWEEP1_MIN_BLOCKS>
+__global__ void __launch_bounds__(SWEEP1_THREADS, MB) k_sweep1(const SweepArgs a) {
     using Ctx = DevSweepCtx1<LONG, UNIQ>;
     const uint32_t lane_u4 = sweep1_lane_u4(a.max_len, LONG);
     const uint32_t p0 = threadIdx.x * lane_u4;
     const size_t gl = (size_t)blockIdx.x * SWEEP1_THREADS + threadIdx.x;
     Ctx ctx{a, p0, (p0 + SWEEP1_CAP) * 4u, a.scratch + gl * 2 * a.max_len, a.scratch + gl * 2 * a.max_len + a.max_len, nullptr, 0u, Ctx::NO_FIN};
     Sweeper<Ctx> sw;
+    LanePartial part{0u, 0u, false};
     for (;;) {
         ctx.flush_finished();                 // reads finished by the last iteration's consume: before their lanes reuse the staging slots
         const bool need = sw.next(ctx, a.meta);
@@ -432,9 +450,10 @@ __global__ void __launch_bounds__(SWEEP1_THREADS, SWEEP1_MIN_BLOCKS) k_sweep1(co
             matched = matched < mx ? matched : mx;
         }
         const bool rev = sw.on_reverse();
-        const StepOut r = lane_step(rev ? a.rev : a.fwd, sw.P0, sw.P0 + sw.cnt, sw.ch, a.meta.C[sw.ch & 3u],
-                                    rev ? a.meta.prim_r : a.meta.prim_f, is_step);
-        if (is_step) sw.consume(ctx, a.meta, r);
+        StepOut r;
+        const bool stepped = lane_step(rev ? a.rev : a.fwd, sw.P0, sw.P0 + sw.cnt, sw.ch, a.meta.C[sw.ch & 3u],
+                                       rev ? a.meta.prim_r : a.meta.prim_f, is_step, part, r);
+        if (stepped) sw.consume(ctx, a.meta, r);
         else if (is_seed) sw.consume_seed(ctx, a.meta, SeedEntry{se.x, se.y, se.z, se.w});
         else if (UNIQ && is_word) sw.consume_word(ctx, a.meta, wv);
         else if (UNIQ && is_cmp) sw.consume_cmp(ctx, a.meta, matched);

@@ -81,6 +81,7 @@ struct SelCtx {
     std::vector<uint32_t>* out;   // 6 x u32 per record: i, j, lo_lo, lo_hi, hi_lo, hi_hi
 
     MemEntry mem(uint32_t k) const { return mems[k]; }
+    uint32_t se(uint32_t k) const { return mems[k].se; }
     uint32_t base(uint32_t pos) const { return base_msb(words, pos); }
     bool failed() const { return raised; }
     bool seeds_are_true() const { return method == GSM_METHOD_LUT_; }

@@ -64,3 +64,26 @@ def test_fastq_scanner_slice_boundaries(tmp_path):
     bad.write_text("@a\nACGT\n+\nIIII\nXb\nAC\n+\nII\n")
     with pytest.raises(ValueError):
         ingest.read_fastq(str(bad), pin=False, threads=2)
+
+
+def test_fastq_cuts_fall_on_record_boundaries():
+    """ingest.fastq_cuts (the only host-side work of PipelinedEngine.run_fastq): every cut is the first byte of a record,
+    also when quality lines start with '@'."""
+    import numpy as np
+    from genie_smem_b200 import ingest
+    rng = np.random.default_rng(1)
+    recs = []
+    for i in range(2000):
+        L = int(rng.integers(30, 160))
+        s = "".join("ACGT"[c] for c in rng.integers(0, 4, L))
+        q = "".join(chr(int(c)) for c in rng.integers(33, 75, L))
+        if i % 7 == 0:
+            q = "@" + q[1:]
+        recs.append(f"@r{i} desc\n{s}\n+\n{q}\n")
+    buf = np.frombuffer("".join(recs).encode(), np.uint8)
+    starts = set(np.cumsum([0] + [len(r) for r in recs]).tolist())
+    for k in (1, 2, 5, 16, 100, 5000):
+        cuts = ingest.fastq_cuts(buf, k)
+        assert cuts[0] == 0 and cuts[-1] == len(buf) and cuts == sorted(set(cuts))
+        assert all(c in starts for c in cuts), k
+    assert ingest.fastq_cuts(buf[:0], 4) == [0, 0] or ingest.fastq_cuts(buf[:0], 4) == [0]
