@@ -657,6 +657,8 @@ def main():
         out["sweep_seed_table_K"] = int(index.c.seed_K)
         if world > 1:
             out["value_includes"] = "sweep + select + scan + ordered write of every rank, the write being the gather into rank 0's HBM (NVLink), + completion fence"
+            out["gather_transport"] = ("peer mapping (CUDA IPC): each rank's ordered-write kernel stores into rank 0's buffer" if gat.fused else
+                                       f"NCCL send/recv per batch (peer mapping unavailable: {gat.fallback_reason})")
         emit_result(out)
     bad = rank == 0 and parity is not None and any(parity.get(k, 0) for k in ("bwa", "lut", "rmi", "rmi_probe_search"))
     if world > 1:

@@ -419,7 +419,8 @@ inline size_t sweep1_smem_bytes(uint32_t max_len, bool long_reads) {
 
 // MB = resident blocks per SM the register allocation aims at (6: 80 registers, 7: 72, 8: 64 with spills); measured per
 // workload by tools/sweep_ab.py (GSM_SWEEP_BLOCKS)
-template <bool LONG, bool UNIQ, int MB = SWEEP1_MIN_BLOCKS>
+// STATS: count lane-slots / FM passes / seed fetches / text operations into counters[4..7] (measurement builds only)
+template <bool LONG, bool UNIQ, int MB = SWEEP1_MIN_BLOCKS, bool STATS = false>
 __global__ void __launch_bounds__(SWEEP1_THREADS, MB) k_sweep1(const SweepArgs a) {
     using Ctx = DevSweepCtx1<LONG, UNIQ>;
     const uint32_t lane_u4 = sweep1_lane_u4(a.max_len, LONG);
@@ -428,6 +429,7 @@ __global__ void __launch_bounds__(SWEEP1_THREADS, MB) k_sweep1(const SweepArgs a
     Ctx ctx{a, p0, (p0 + SWEEP1_CAP) * 4u, a.scratch + gl * 2 * a.max_len, a.scratch + gl * 2 * a.max_len + a.max_len, nullptr, 0u, Ctx::NO_FIN};
     Sweeper<Ctx> sw;
     LanePartial part{0u, 0u, false};
+    uint32_t n_it = 0, n_step = 0, n_seed = 0, n_text = 0;
     for (;;) {
         ctx.flush_finished();                 // reads finished by the last iteration's consume: before their lanes reuse the staging slots
         const bool need = sw.next(ctx, a.meta);
@@ -440,6 +442,7 @@ __global__ void __launch_bounds__(SWEEP1_THREADS, MB) k_sweep1(const SweepArgs a
         const bool is_word = UNIQ && need && sw.pending_word();
         const bool is_cmp = UNIQ && need && sw.pending_cmp();
         const bool is_step = need && !is_seed && !is_word && !is_cmp;
+        if (STATS) { n_it++; n_step += is_step; n_seed += is_seed; n_text += is_word || is_cmp; }
         uint4 se = make_uint4(0u, 0u, 0u, 0u);
         if (is_seed) se = ldg_seed(a.seed_tab + sw.P0);
         uint32_t wv = 0u, matched = 0u;
@@ -457,6 +460,12 @@ __global__ void __launch_bounds__(SWEEP1_THREADS, MB) k_sweep1(const SweepArgs a
         else if (is_seed) sw.consume_seed(ctx, a.meta, SeedEntry{se.x, se.y, se.z, se.w});
         else if (UNIQ && is_word) sw.consume_word(ctx, a.meta, wv);
         else if (UNIQ && is_cmp) sw.consume_cmp(ctx, a.meta, matched);
+    }
+    if (STATS) {
+        atomicAdd(&a.counters[4], (unsigned long long)n_it);
+        atomicAdd(&a.counters[5], (unsigned long long)n_step);
+        atomicAdd(&a.counters[6], (unsigned long long)n_seed);
+        atomicAdd(&a.counters[7], (unsigned long long)n_text);
     }
 }
 

@@ -194,18 +194,34 @@ class RecordGatherer:
         handle = np.zeros(64, np.uint8)
         off = C.c_uint64(0)
         self.buffer = None
+        self.out_ptr = 0
+        ok, why = True, ""
         if self.rank == dst:
             self.buffer = torch.empty(self.capacity * 16, dtype=torch.uint8, device=self.device)
-            capi.check(capi.lib.gsm_peer_export(C.c_void_p(self.buffer.data_ptr()), handle.ctypes.data, C.byref(off)))
-        box = [(handle.tobytes(), int(off.value))]
+            try:
+                capi.check(capi.lib.gsm_peer_export(C.c_void_p(self.buffer.data_ptr()), handle.ctypes.data, C.byref(off)))
+            except Exception as e:          # e.g. an allocator whose memory cannot be exported
+                ok, why = False, str(e)
+        box = [(handle.tobytes(), int(off.value), ok, why)]
         dist.broadcast_object_list(box, src=dist.get_global_rank(group, dst) if group is not None else dst, group=group)
-        if self.rank == dst:
+        ok, why = box[0][2], box[0][3]
+        if ok and self.rank == dst:
             self.out_ptr = self.buffer.data_ptr()
-        else:
+        elif ok:
             handle = np.frombuffer(box[0][0], np.uint8).copy()
             p = C.c_void_p()
-            capi.check(capi.lib.gsm_peer_open(handle.ctypes.data, box[0][1], C.byref(p)))
-            self.out_ptr, self._offset = int(p.value), int(box[0][1])
+            try:
+                capi.check(capi.lib.gsm_peer_open(handle.ctypes.data, box[0][1], C.byref(p)))
+                self.out_ptr, self._offset = int(p.value), int(box[0][1])
+            except Exception as e:
+                ok, why = False, str(e)
+        # every rank must take the same path: the peer mapping is used only if it worked everywhere
+        flags = [None] * self.world
+        dist.all_gather_object(flags, (bool(ok), why), group=group)
+        self.fused = all(f[0] for f in flags)
+        self.fallback_reason = next((f[1] for f in flags if not f[0]), "")
+        if not self.fused and self.rank != dst and self.out_ptr:
+            self.close()
 
     def reset(self):
         self.base.zero_()
@@ -217,8 +233,19 @@ class RecordGatherer:
             raise capi.GsmError(capi.E_CAPACITY, "RecordGatherer: more batches than max_batches")
         row = self.counts.data_ptr() + 8 * self.world * self.n_batches
         self.comm.allgather_u64(engine.counters.data_ptr() + 8, row)
-        capi.check(capi.lib.gsm_smem_collect_gathered(C.byref(reads_c), C.byref(engine.ws), C.c_void_p(self.out_ptr), self.capacity,
-                                                      C.c_void_p(row), self.rank, C.c_void_p(self.base.data_ptr()), _stream()))
+        if self.fused:
+            capi.check(capi.lib.gsm_smem_collect_gathered(C.byref(reads_c), C.byref(engine.ws), C.c_void_p(self.out_ptr), self.capacity,
+                                                          C.c_void_p(row), self.rank, C.c_void_p(self.base.data_ptr()), _stream()))
+        else:
+            # no peer mapping (CUDA IPC unavailable): ordered write into the rank's own buffer, then exact-size NCCL
+            # send / recv into dst's buffer -- needs the counts on the host, i.e. one stream synchronisation per batch
+            capi.check(capi.lib.gsm_smem_collect(C.byref(reads_c), C.byref(engine.ws), C.c_void_p(engine.records.data_ptr()), engine.rec_cap, _stream()))
+            cnt = self.counts[self.world * self.n_batches: self.world * (self.n_batches + 1)].cpu().numpy().astype(np.uint64)
+            base = int(self.base.item())
+            if base + int(cnt.sum()) > self.capacity:
+                raise capi.GsmError(capi.E_CAPACITY, "RecordGatherer: the destination buffer is too small")
+            dst_view = self.buffer[base * 16:] if self.rank == self.dst else None
+            self.comm.gather_records(engine.records, int(cnt[self.rank]), cnt, dst_view, self.dst)
         capi.check(capi.lib.gsm_gather_advance(C.c_void_p(self.base.data_ptr()), C.c_void_p(row), self.world, _stream()))
         self.n_batches += 1
 

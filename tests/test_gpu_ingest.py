@@ -146,7 +146,7 @@ def test_fastq_bytes_cut_and_packed_on_the_gpu_equal_the_string_path(gs, setup, 
     fq = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
     plain = gs.Engine(idx, len(mixed), 160, mems_per_read=48, recs_per_read=48)
     want = plain.run(gs.METHOD_BWA, gs.ReadBatch.from_strings(mixed), min_len=1)
-    pipe = gs.PipelinedEngine(idx, len(mixed) + 10, 160, n_chunks=4, mems_per_read=48, recs_per_read=48)
+    pipe = gs.PipelinedEngine(idx, len(mixed) + 10, 160, n_chunks=2, mems_per_read=48, recs_per_read=48)
     got = pipe.run_fastq(gs.METHOD_BWA, fq, min_len=1, n_chunks=n_chunks)
     assert len(got.offsets) == len(mixed) + 1
     assert np.array_equal(got.offsets, want.offsets) and np.array_equal(got.records, want.records) and np.array_equal(got.status, want.status)

@@ -66,6 +66,10 @@ def main():
     out = {"tag": a.tag, "env": {k: v for k, v in os.environ.items() if k.startswith("GSM_")}, "reads": a.reads, "ref_bases": a.ref_bases,
            "seed_K": int(index.seed_K), "setup_s": round(setup, 1)}
     out["ms_sweep"] = round(timed(lambda: eng.sweep(batch), a.steps), 3)
+    if os.environ.get("GSM_SWEEP_STATS"):
+        c = eng.counters.cpu().numpy()
+        out["stats_per_read"] = {"lane_slots": round(float(c[4]) / a.reads, 2), "fm_passes": round(float(c[5]) / a.reads, 2),
+                                 "seed_fetches": round(float(c[6]) / a.reads, 2), "text_ops": round(float(c[7]) / a.reads, 2)}
     legs = [("bwa", g.METHOD_BWA, {"min_len": 1}), ("lut", g.METHOD_LUT, {"K": bench.LUT_K, "lut": lut})]
     if rmi is not None:
         legs.append(("rmi", g.METHOD_RMI, {"rmi": rmi}))
