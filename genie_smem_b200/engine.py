@@ -1040,7 +1040,10 @@ class PipelinedEngine:
             seq_end = torch.zeros(cap, dtype=torch.int64, device=self.device)
             flags = torch.empty(2, dtype=torch.int64, device=self.device)          # [0] structure error offset, [1] first bad read
             capi.check(capi.lib.gsm_fastq_records_device(_ptr(raw), nb, _ptr(prefix), cap, _ptr(seq_start), _ptr(seq_end), _ptr(flags), _stream()))
-            lens = (seq_end - seq_start).to(torch.int32)
+            # a record counts only if both ends of its sequence line were seen (a truncated file leaves the last one open);
+            # anything else packs as an empty read, so no length derived from the input can send the packer out of bounds
+            whole = (seq_start > 0) & (seq_end >= seq_start) & (seq_end <= nb)
+            lens = torch.where(whole, seq_end - seq_start, torch.zeros_like(seq_end)).to(torch.int32)
             coff = torch.zeros(cap + 1, dtype=torch.int32, device=self.device)
             coff[1:] = torch.cumsum((lens + 63) // 64, 0).to(torch.int32)
             packed = torch.empty(nb // 4 + 16 * cap + 32, dtype=torch.uint8, device=self.device)
