@@ -85,7 +85,7 @@ struct TableProbe {
     }
 };
 
-template <int METHOD, bool LSE = true>
+template <int METHOD>
 struct DevSelCtx {
     const SelectArgs& a;
     const uint32_t* words;
@@ -95,18 +95,7 @@ struct DevSelCtx {
     uint32_t L, K, n_mems, min_len, rid, n_rec;
     bool raised;
     bool overflow;        // more records than slots: counted, not stored
-    // compact copy of the first matches' (start | end << 16) words: the frame machine's lookups are binary searches over
-    // starts and ends, i.e. chains of dependent loads; from this per-thread array they are L1 hits instead of 16-byte
-    // entries spread over the pool (L2)
-    static constexpr uint32_t LSE_CAP = 32;
-    uint32_t lse[LSE ? LSE_CAP : 1];
-
-    __device__ __forceinline__ void cache_se() {
-        if (!LSE) return;
-        const uint32_t n = n_mems < LSE_CAP ? n_mems : LSE_CAP;
-        for (uint32_t k = 0; k < n; ++k) lse[k] = mems[k].x;
-    }
-    __device__ __forceinline__ uint32_t se(uint32_t k) const { return (LSE && k < LSE_CAP) ? lse[k] : mems[k].x; }
+    __device__ __forceinline__ uint32_t se(uint32_t k) const { return mems[k].x; }
 
     __device__ __forceinline__ MemEntry mem(uint32_t k) const {
         uint4 v = mems[k];
@@ -262,9 +251,8 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
                             a.reads + (size_t)__ldg(a.chunk_off + rid) * 4,
                             a.mem_pool + a.mem_off[rid],
                             stage, a.stage_stride,
-                            __ldg(a.len + rid), a.K, a.mem_cnt[rid] & 0x7FFFFFFFu, a.min_len, (uint32_t)rid, 0u, false, false, {}};
+                            __ldg(a.len + rid), a.K, a.mem_cnt[rid] & 0x7FFFFFFFu, a.min_len, (uint32_t)rid, 0u, false, false};
         if (!(a.mem_cnt[rid] >> 31)) order_segments(c.mems, c.n_mems);        // bit 31: the sweep already ordered the list
-        c.cache_se();
         bool direct = false;
         do {
             uint8_t status = GSM_READ_OK;
@@ -313,18 +301,16 @@ __device__ __forceinline__ void phase_loop(uint32_t mask, Machine& mach, Begin b
 // Measured alternatives (profiles/r01_notes.md): the reference's control flow per thread end to end (2.2 active threads
 // per instruction on the probes), and teams of 16 lanes per read with one window per lane (converged, but 16x fewer reads
 // in flight: latency-bound on the machine's dependent loads, 1.7x slower than this kernel).
-// VARIANT (measurement switch GSM_SELECT_VARIANT, results identical): bit 0 = compact start/end cache, bit 1 = table
-// fetches of a round issued WB at a time
-template <int METHOD, int VARIANT = 0>
+template <int METHOD>
 __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const SelectArgs a) {
-    using CtxT = DevSelCtx<METHOD, (VARIANT & 1) != 0>;
+    using CtxT = DevSelCtx<METHOD>;
     using Sel = Selector<CtxT>;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     size_t rid = gtid;
     bool have = false;
     uint4* const stage = a.stage + gtid * a.stage_stride;
-    CtxT c{a, nullptr, nullptr, stage, a.stage_stride, 0u, a.K, 0u, a.min_len, 0u, 0u, false, false, {}};
+    CtxT c{a, nullptr, nullptr, stage, a.stage_stride, 0u, a.K, 0u, a.min_len, 0u, 0u, false, false};
     bool direct = false;
     typename Sel::Seeded st;
     int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
@@ -344,7 +330,6 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
             c.L = __ldg(a.len + rid); c.n_mems = mc & 0x7FFFFFFFu; c.rid = (uint32_t)rid; c.n_rec = 0; c.raised = false; c.overflow = false;
             c.out = stage; c.cap = a.stage_stride;
             if (!(mc >> 31)) order_segments(c.mems, c.n_mems);                 // bit 31: the sweep already ordered the list
-            c.cache_se();
             st = typename Sel::Seeded();
             if (c.L < c.K) { close_read(GSM_READ_TOO_SHORT); continue; }
             have = true;
@@ -370,7 +355,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
                 if (st.first || (i < st.plen && cpos + c.K <= c.L)) vis |= 1u << i;
             }
         }
-        constexpr uint32_t WB = (VARIANT & 2) ? 4 : 1;      // windows whose table fetches are issued together (independent loads in flight)
+        constexpr uint32_t WB = 1;                          // windows per batch (batches of 4 measured slower: register spills, profiles/r02_notes.md)
         if (METHOD == GSM_METHOD_LUT) {
             for (uint32_t i0 = 0; i0 < nwin; i0 += WB) {
                 uint2 t[WB];
@@ -826,7 +811,7 @@ int sweep_kind(uint32_t max_len) {
     return lpr == 2 ? SWEEP_PAIR : SWEEP_LANE;
 }
 
-int sweep_blocks_env() {       // GSM_SWEEP_BLOCKS=7|8: the lane kernel compiled for more resident blocks (fewer registers); A/B switch
+int sweep_blocks_env() {       // GSM_SWEEP_BLOCKS=6|8: the lane kernel compiled for more resident blocks (fewer registers); A/B switch
     static const int v = getenv("GSM_SWEEP_BLOCKS") ? atoi(getenv("GSM_SWEEP_BLOCKS")) : 0;
     return v;
 }
@@ -840,14 +825,14 @@ int sweep_grid(uint32_t max_len, int* blocks) {
         const size_t smem = sweep1_smem_bytes(max_len, false);
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, SWEEP1_MIN_BLOCKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int a0 = 0, a1 = 0;                 // the grid must be resident for either instantiation (with / without the text shortcut)
         GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k_sweep1<false, false>, SWEEP1_THREADS, smem));
         GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a1, k_sweep1<false, true>, SWEEP1_THREADS, smem));
         per_sm = a0 < a1 ? a0 : a1;
-        if (sweep_blocks_env() == 7) GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep1<false, true, 7>, SWEEP1_THREADS, smem));
+        if (sweep_blocks_env() == 6) GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep1<false, true, 6>, SWEEP1_THREADS, smem));
         if (sweep_blocks_env() == 8) GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep1<false, true, 8>, SWEEP1_THREADS, smem));
     } else if (kind == SWEEP_LANE_LONG) {
         int a0 = 0, a1 = 0;
@@ -1120,7 +1105,7 @@ int gsm_smem_sweep(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_workspa
     if (kind == SWEEP_LANE) {
         static const int stats = getenv("GSM_SWEEP_STATS") ? atoi(getenv("GSM_SWEEP_STATS")) : 0;
         if (uniq && stats) k_sweep1<false, true, SWEEP1_MIN_BLOCKS, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
-        else if (uniq && sweep_blocks_env() == 7) k_sweep1<false, true, 7><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
+        else if (uniq && sweep_blocks_env() == 6) k_sweep1<false, true, 6><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
         else if (uniq && sweep_blocks_env() == 8) k_sweep1<false, true, 8><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
         else if (uniq) k_sweep1<false, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
         else k_sweep1<false, false><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
@@ -1167,24 +1152,13 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
         if ((st = resident_grid(k_select<GSM_METHOD_BWA>, SELECT_THREADS, lb, &grid))) return st;
         k_select<GSM_METHOD_BWA><<<grid, SELECT_THREADS, 0, stream>>>(se);
     } else {
-        static const int variant = getenv("GSM_SELECT_VARIANT") ? atoi(getenv("GSM_SELECT_VARIANT")) & 3 : 0;
-#define GSM_LAUNCH_SEEDED(M, V)                                                                           \
-    do {                                                                                                  \
-        if ((st = resident_grid(k_select_seeded<M, V>, SELECT_THREADS, lb, &grid))) return st;            \
-        k_select_seeded<M, V><<<grid, SELECT_THREADS, 0, stream>>>(se);                                   \
-    } while (0)
         if (method == GSM_METHOD_LUT) {
-            if (variant == 0) GSM_LAUNCH_SEEDED(GSM_METHOD_LUT, 0);
-            else if (variant == 1) GSM_LAUNCH_SEEDED(GSM_METHOD_LUT, 1);
-            else if (variant == 2) GSM_LAUNCH_SEEDED(GSM_METHOD_LUT, 2);
-            else GSM_LAUNCH_SEEDED(GSM_METHOD_LUT, 3);
+            if ((st = resident_grid(k_select_seeded<GSM_METHOD_LUT>, SELECT_THREADS, lb, &grid))) return st;
+            k_select_seeded<GSM_METHOD_LUT><<<grid, SELECT_THREADS, 0, stream>>>(se);
         } else {
-            if (variant == 0) GSM_LAUNCH_SEEDED(GSM_METHOD_RMI, 0);
-            else if (variant == 1) GSM_LAUNCH_SEEDED(GSM_METHOD_RMI, 1);
-            else if (variant == 2) GSM_LAUNCH_SEEDED(GSM_METHOD_RMI, 2);
-            else GSM_LAUNCH_SEEDED(GSM_METHOD_RMI, 3);
+            if ((st = resident_grid(k_select_seeded<GSM_METHOD_RMI>, SELECT_THREADS, lb, &grid))) return st;
+            k_select_seeded<GSM_METHOD_RMI><<<grid, SELECT_THREADS, 0, stream>>>(se);
         }
-#undef GSM_LAUNCH_SEEDED
     }
     GSM_CUDA(cudaGetLastError());
     const uint64_t n_tiles = (rd->n_reads + SCAN_TILE - 1) / SCAN_TILE;

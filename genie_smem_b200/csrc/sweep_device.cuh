@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS, SWEEP_MIN_BLOCKS) k_sweep(const
 // halving.  Same Sweeper logic (sweep_logic.cuh), same outputs; chosen at run time (gsm_smem_sweep, GSM_SWEEP_LPR).
 constexpr int SWEEP1_THREADS = 128;
 constexpr int SWEEP1_CAP = 8;                              // candidates kept in shared memory per read
-constexpr int SWEEP1_MIN_BLOCKS = 6;                       // default register budget: 85 per thread (see k_sweep1's MB)
+constexpr int SWEEP1_MIN_BLOCKS = 7;                       // register budget: 72 per thread (measured best of 6 / 7 / 8, profiles/r02_notes.md)
 
 // counts of one bucket (its two halves) below in-bucket offset r: (#symbols == c) | (#symbols < c) << 16.  E[] / T[] are the
 // per-word "equals c" / "less than c" bit masks of the bucket's 6 x 32 symbols.
