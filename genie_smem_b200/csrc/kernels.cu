@@ -95,9 +95,15 @@ struct DevSelCtx {
     uint32_t L, K, n_mems, min_len, rid, n_rec;
     bool raised;
     bool overflow;        // more records than slots: counted, not stored
-    __device__ __forceinline__ uint32_t se(uint32_t k) const { return mems[k].x; }
+    // bit 31 of mem_cnt: the sweep stored this list in ascending order and field by field (n start|end words, n lo, n count, ...)
+    bool soa;
+    __device__ __forceinline__ uint32_t se(uint32_t k) const { return soa ? reinterpret_cast<const uint32_t*>(mems)[k] : mems[k].x; }
 
     __device__ __forceinline__ MemEntry mem(uint32_t k) const {
+        if (soa) {
+            const uint32_t* seg = reinterpret_cast<const uint32_t*>(mems);
+            return MemEntry{seg[k], seg[n_mems + k], seg[2u * n_mems + k], seg[3u * n_mems + k]};
+        }
         uint4 v = mems[k];
         return MemEntry{v.x, v.y, v.z, v.w};
     }
@@ -251,8 +257,8 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
                             a.reads + (size_t)__ldg(a.chunk_off + rid) * 4,
                             a.mem_pool + a.mem_off[rid],
                             stage, a.stage_stride,
-                            __ldg(a.len + rid), a.K, a.mem_cnt[rid] & 0x7FFFFFFFu, a.min_len, (uint32_t)rid, 0u, false, false};
-        if (!(a.mem_cnt[rid] >> 31)) order_segments(c.mems, c.n_mems);        // bit 31: the sweep already ordered the list
+                            __ldg(a.len + rid), a.K, a.mem_cnt[rid] & 0x7FFFFFFFu, a.min_len, (uint32_t)rid, 0u, false, false, (a.mem_cnt[rid] >> 31) != 0u};
+        if (!c.soa) order_segments(c.mems, c.n_mems);        // bit 31: the sweep already ordered the list
         bool direct = false;
         do {
             uint8_t status = GSM_READ_OK;
@@ -301,8 +307,11 @@ __device__ __forceinline__ void phase_loop(uint32_t mask, Machine& mach, Begin b
 // Measured alternatives (profiles/r01_notes.md): the reference's control flow per thread end to end (2.2 active threads
 // per instruction on the probes), and teams of 16 lanes per read with one window per lane (converged, but 16x fewer reads
 // in flight: latency-bound on the machine's dependent loads, 1.7x slower than this kernel).
-template <int METHOD>
-__global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const SelectArgs a) {
+// ARITH (RMI only): the launch has a usable seed table (seed_K <= K) and the None rows, so every lookup is the probe-free
+// rmi_arith_lookup and the probe-based phases are compiled out (fewer registers for the path that always runs).
+// MB: resident blocks per SM the register allocation aims at (8: 64 registers with spills, 6: 80); GSM_SELECT_BLOCKS=6 for A/B
+template <int METHOD, bool ARITH = false, int MB = 8>
+__global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const SelectArgs a) {
     using CtxT = DevSelCtx<METHOD>;
     using Sel = Selector<CtxT>;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
     size_t rid = gtid;
     bool have = false;
     uint4* const stage = a.stage + gtid * a.stage_stride;
-    CtxT c{a, nullptr, nullptr, stage, a.stage_stride, 0u, a.K, 0u, a.min_len, 0u, 0u, false, false};
+    CtxT c{a, nullptr, nullptr, stage, a.stage_stride, 0u, a.K, 0u, a.min_len, 0u, 0u, false, false, false};
     bool direct = false;
     typename Sel::Seeded st;
     int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
@@ -329,13 +338,14 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
             const uint32_t mc = a.mem_cnt[rid];
             c.L = __ldg(a.len + rid); c.n_mems = mc & 0x7FFFFFFFu; c.rid = (uint32_t)rid; c.n_rec = 0; c.raised = false; c.overflow = false;
             c.out = stage; c.cap = a.stage_stride;
-            if (!(mc >> 31)) order_segments(c.mems, c.n_mems);                 // bit 31: the sweep already ordered the list
+            c.soa = (mc >> 31) != 0u;
+            if (!c.soa) order_segments(c.mems, c.n_mems);                      // bit 31: the sweep already ordered the list
             st = typename Sel::Seeded();
             if (c.L < c.K) { close_read(GSM_READ_TOO_SHORT); continue; }
             have = true;
         }
     };
-    const bool arith = METHOD == GSM_METHOD_RMI && a.rmi.n_none != 0u && a.seed_K != 0u && a.seed_K <= a.K;
+    constexpr bool arith = METHOD == GSM_METHOD_RMI && ARITH;
 
     for (;;) {
         while (true) {                                   // finished reads are closed, the next ones opened
@@ -412,7 +422,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, 8) k_select_seeded(const Selec
                         }
                     }
             }
-        } else if (a.rmi.n_none != 0) {
+        } else if (!ARITH && a.rmi.n_none != 0) {
             // probe-based error-bounded search (select_logic.cuh, RmiGallop / RmiLower / RmiUpper): each phase runs over ALL
             // windows of the round as one lock-step loop with straight-line per-probe code
             uint32_t todo = 0, lbm = 0, ubm = 0;
@@ -1152,12 +1162,23 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
         if ((st = resident_grid(k_select<GSM_METHOD_BWA>, SELECT_THREADS, lb, &grid))) return st;
         k_select<GSM_METHOD_BWA><<<grid, SELECT_THREADS, 0, stream>>>(se);
     } else {
-        if (method == GSM_METHOD_LUT) {
+        static const int sel_blocks = getenv("GSM_SELECT_BLOCKS") ? atoi(getenv("GSM_SELECT_BLOCKS")) : 8;
+        const bool arith = rm.n_none != 0u && se.seed_K != 0u && se.seed_K <= K;       // lookups from the seed table: no probes
+        if (method == GSM_METHOD_LUT && sel_blocks == 6) {
+            if ((st = resident_grid(k_select_seeded<GSM_METHOD_LUT, false, 6>, SELECT_THREADS, lb, &grid))) return st;
+            k_select_seeded<GSM_METHOD_LUT, false, 6><<<grid, SELECT_THREADS, 0, stream>>>(se);
+        } else if (method == GSM_METHOD_LUT) {
             if ((st = resident_grid(k_select_seeded<GSM_METHOD_LUT>, SELECT_THREADS, lb, &grid))) return st;
             k_select_seeded<GSM_METHOD_LUT><<<grid, SELECT_THREADS, 0, stream>>>(se);
+        } else if (arith && sel_blocks == 6) {
+            if ((st = resident_grid(k_select_seeded<GSM_METHOD_RMI, true, 6>, SELECT_THREADS, lb, &grid))) return st;
+            k_select_seeded<GSM_METHOD_RMI, true, 6><<<grid, SELECT_THREADS, 0, stream>>>(se);
+        } else if (arith) {
+            if ((st = resident_grid(k_select_seeded<GSM_METHOD_RMI, true>, SELECT_THREADS, lb, &grid))) return st;
+            k_select_seeded<GSM_METHOD_RMI, true><<<grid, SELECT_THREADS, 0, stream>>>(se);
         } else {
-            if ((st = resident_grid(k_select_seeded<GSM_METHOD_RMI>, SELECT_THREADS, lb, &grid))) return st;
-            k_select_seeded<GSM_METHOD_RMI><<<grid, SELECT_THREADS, 0, stream>>>(se);
+            if ((st = resident_grid(k_select_seeded<GSM_METHOD_RMI, false>, SELECT_THREADS, lb, &grid))) return st;
+            k_select_seeded<GSM_METHOD_RMI, false><<<grid, SELECT_THREADS, 0, stream>>>(se);
         }
     }
     GSM_CUDA(cudaGetLastError());

@@ -798,44 +798,55 @@ struct Selector {
         uint32_t pc = 0; bool pfw = false, ptrue = false; int64_t plo = 0, phi = -1;
         Cand cd{false, false, 0, 0, 0, -1};
         const uint32_t pstart = e - plen;
-        // Pass 2: the frame machine over the stored results
-        for (uint32_t i = 0; i < K; ++i) {
-            if (i >= plen) continue;
-            const uint32_t cpos = e - i;
-            if (cpos + K > L) continue;
-            const int64_t lo = wlo[i], hi = whi[i];
-            const bool hit = (whit >> i) & 1u;
-            const bool tru = (wtrue >> i) & 1u;
-            if (hit) {
-                if (fstate == 0) { fstate = 2; pc = cpos; pfw = true; plo = lo; phi = hi; ptrue = tru; }          // :70
-                else if (fstate == 1) { fstate = 2; pc = cpos; pfw = false; plo = lo; phi = hi; ptrue = tru; }    // :73
-                else {
-                    // check_sequential of two TRUE k-mer intervals at adjacent windows is just
-                    // "q[cpos : cpos+K+1) occurs" (SURVEY A13): read it off the match list
-                    const bool both = tru && ptrue;
-                    const bool seq = (both && pc == cpos + 1) ? (F_of(c, cpos) >= cpos + K + 1)
-                                                              : c.sequential(cpos, lo, hi, pc, plo, phi, both);
-                    if (seq) {                                                                        // Case 1
-                        if (pfw) upd(cd, bext(c, pc, plo, phi, true));
-                        else {
-                            if (cd.valid && (pc - pstart) + K < (cd.j - cd.i)) continue;              // :94-95
-                            upd(cd, bext(c, pc, plo, phi, false));
-                        }
-                    } else {                                                                          // Case 2
-                        if (pfw) upd(cd, fwd_only(c, pc, plo, phi));
-                        else upd(cd, known(cpos, cpos + K, lo, hi));
-                    }
-                    pc = cpos; pfw = false; plo = lo; phi = hi; ptrue = tru;
-                }
+        // Pass 2: the frame machine over the stored results.  Each window only DECIDES what happens to the previous frame
+        // (A_*); the extension itself runs at one place below, so that the threads of a warp that extend a frame do it
+        // together whichever case of the reference they are in.  Step i == K is the closing extension (SMEM.py:149-171).
+        enum { A_NONE = 0, A_BEXT = 1, A_FWD = 2, A_KNOWN = 3 };
+        for (uint32_t i = 0; i <= K; ++i) {
+            int act = A_NONE;
+            uint32_t ai = 0, aj = 0;                // A_BEXT / A_FWD: frame start in ai; A_KNOWN: the candidate (ai, aj)
+            int64_t alo = 0, ahi = -1;
+            bool aall = false;
+            if (i == K) {
+                if (fstate == 2) { act = A_BEXT; ai = pc; alo = plo; ahi = phi; aall = pfw; }
             } else {
-                if (fstate == 2) {                                                                    // Case 3
-                    if (pfw) upd(cd, fwd_only(c, pc, plo, phi));
-                    else upd(cd, known(pc, pc + K, plo, phi));
+                if (i >= plen) continue;
+                const uint32_t cpos = e - i;
+                if (cpos + K > L) continue;
+                const int64_t lo = wlo[i], hi = whi[i];
+                const bool hit = (whit >> i) & 1u;
+                const bool tru = (wtrue >> i) & 1u;
+                if (hit) {
+                    if (fstate == 0) { fstate = 2; pc = cpos; pfw = true; plo = lo; phi = hi; ptrue = tru; }          // :70
+                    else if (fstate == 1) { fstate = 2; pc = cpos; pfw = false; plo = lo; phi = hi; ptrue = tru; }    // :73
+                    else {
+                        // check_sequential of two TRUE k-mer intervals at adjacent windows is just
+                        // "q[cpos : cpos+K+1) occurs" (SURVEY A13): read it off the match list
+                        const bool both = tru && ptrue;
+                        const bool seq = (both && pc == cpos + 1) ? (F_of(c, cpos) >= cpos + K + 1)
+                                                                  : c.sequential(cpos, lo, hi, pc, plo, phi, both);
+                        if (seq) {                                                                        // Case 1
+                            if (!pfw && cd.valid && (pc - pstart) + K < (cd.j - cd.i)) continue;          // :94-95 (the frame stays)
+                            act = A_BEXT; ai = pc; alo = plo; ahi = phi; aall = pfw;
+                        } else if (pfw) {                                                                 // Case 2
+                            act = A_FWD; ai = pc; alo = plo; ahi = phi;
+                        } else {
+                            act = A_KNOWN; ai = cpos; aj = cpos + K; alo = lo; ahi = hi;
+                        }
+                        pc = cpos; pfw = false; plo = lo; phi = hi; ptrue = tru;
+                    }
+                } else {
+                    if (fstate == 2) {                                                                    // Case 3
+                        if (pfw) { act = A_FWD; ai = pc; alo = plo; ahi = phi; }
+                        else { act = A_KNOWN; ai = pc; aj = pc + K; alo = plo; ahi = phi; }
+                    }
+                    fstate = 1;
                 }
-                fstate = 1;
             }
+            if (act == A_BEXT) upd(cd, bext(c, ai, alo, ahi, aall));
+            else if (act == A_FWD) upd(cd, fwd_only(c, ai, alo, ahi));
+            else if (act == A_KNOWN) upd(cd, known(ai, aj, alo, ahi));
         }
-        if (fstate == 2) upd(cd, bext(c, pc, plo, phi, pfw));                                         // :149-171
         if (!cd.valid) {                                                                              // :175-179
             uint32_t from = 0;
             const uint32_t b = covering_best(c, e, from);

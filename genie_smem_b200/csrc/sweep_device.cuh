@@ -351,8 +351,8 @@ struct DevSweepCtx1 {
     // Warp-cooperative hand-over of the finished reads' matches to the pool: one atomic per warp reserves the space, then
     // all 32 lanes copy each finished read's staged matches (coalesced 16-byte stores) instead of the owning lane copying
     // them one by one behind dependent L2 loads.  Lists of up to 32 matches are put in ascending order on the way -- the
-    // sweep emits every sweep's matches longest end first -- and flagged (bit 31 of mem_cnt) so that the selection
-    // kernels need not reorder them.  Called by the whole warp.
+    // sweep emits every sweep's matches longest end first -- stored field by field, and flagged (bit 31 of mem_cnt) so
+    // that the selection kernels neither reorder them nor read them as 16-byte entries.  Called by the whole warp.
     __device__ __forceinline__ void flush_finished() {
         constexpr uint32_t FULLM = 0xFFFFFFFFu;
         const uint32_t lane = threadIdx.x & 31u;
@@ -392,7 +392,11 @@ struct DevSweepCtx1 {
                     const uint32_t s0 = 31u - (uint32_t)__clz((int)upto);
                     const uint32_t above = lane == 31u ? 0u : heads & (0xFFFFFFFFu << (lane + 1u));
                     const uint32_t s1 = above ? (uint32_t)__ffs((int)above) - 1u : n;
-                    a.mem_pool[off + s0 + (s1 - 1u - lane)] = v;
+                    // short lists are stored field by field (n start|end words, then n lo, n count, n sweep ordinals): the
+                    // selection kernels binary-search starts and ends, and this way those probes share one or two sectors
+                    uint32_t* seg = reinterpret_cast<uint32_t*>(a.mem_pool + off);
+                    const uint32_t d = s0 + (s1 - 1u - lane);
+                    seg[d] = v.x; seg[n + d] = v.y; seg[2u * n + d] = v.z; seg[3u * n + d] = v.w;
                 }
             } else {
                 for (uint32_t k = lane; k < n; k += 32u) a.mem_pool[off + k] = __ldcg(sp + k);

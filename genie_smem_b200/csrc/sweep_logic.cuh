@@ -59,20 +59,12 @@ struct SeedEntry {
 };
 
 enum SweepMode : int { M_FETCH = 0, M_FWD = 1, M_WALK = 2, M_SEEDF = 3, M_SEEDB = 4, M_DONE = 5,
-                       // unique-match shortcut (needs suffix array [, inverse suffix array] and packed text; see Ctx::uniq):
+                       // unique-match shortcut (needs suffix array, inverse suffix array and packed text; see Ctx::uniq):
                        M_SAF = 6,    // fetch suffix_array[k]: where in the text the unique occurrence of q[x:pos) starts (FWD)
                        M_SAW = 7,    // the same for the longest candidate when the forward phase never needed it (first WALK)
                        M_CMPF = 8,   // compare q[pos..) with the text behind the occurrence, up to SWEEP_CMP_CHUNK bases per fetch
                        M_CMPB = 9,   // compare q[..pos) with the text in front of the occurrence
-                       M_ISA = 10,   // fetch inverse_suffix_array[text position]: the row of the extended match
-                       // TRANSITIONS (no memory operation pending): resolved by next(), each at ONE place in the code, so that
-                       // the lanes of a warp that need the same transition run it together whatever operation they came from
-                       T_FWD_PLAIN = 11,   // forward extension of q[x:..) from its first base (no usable seed entry)
-                       T_FWD_CONT = 12,    // (k, P0, cnt) describe q[x:pos): append q[pos], follow the text, or close at the read end
-                       T_FWD_END = 13,     // forward phase over at pos with a live interval: q[x:pos) is the last candidate
-                       T_START_BWD = 14,   // pop the longest candidate and walk it left
-                       T_WALK_FROM = 15,   // (P0, cnt) is the interval of q[pos:cur_j): prepend q[pos-1] if that may still matter
-                       T_WALK_END = 16 };  // the walked candidate cannot be extended beyond pos
+                       M_ISA = 10 }; // fetch inverse_suffix_array[text position]: the row of the extended match
 
 constexpr uint32_t SWEEP_CMP_CHUNK = 64;   // bases compared per text fetch
 
@@ -92,10 +84,6 @@ constexpr uint32_t SWEEP_CMP_CHUNK = 64;   // bases compared per text fetch
 //   void     cand_sync()                                make candidate writes visible to the pair
 //   void     emit(uint32_t idx, MemEntry e)             stage maximal match #idx of this read
 //   void     finish(uint32_t rid, uint32_t n_mems)      read complete
-//
-// Protocol: next() brings the read to its next pending memory operation (or reports that no read is left); the caller
-// performs that operation for all lanes together and hands the result to consume / consume_seed / consume_word /
-// consume_cmp, which only update registers and name the transition that follows.
 template <typename Ctx>
 struct Sweeper {
     int mode = M_FETCH;
@@ -106,7 +94,7 @@ struct Sweeper {
     // pending seed fetch (M_SEEDF / M_SEEDB): P0 holds the k-mer code
     uint32_t P0 = 0, cnt = 0, ch = 0;
     uint32_t k = 0;            // FWD: rows of q[x:pos) on the text index start here
-    uint32_t pos = 0;          // FWD: next base to append; WALK: base being prepended; T_WALK_*: start of the walked candidate
+    uint32_t pos = 0;          // FWD: next base to append; WALK: base being prepended
     uint32_t cur_j = 0;        // WALK: end of the candidate being extended
     uint32_t ncand = 0;        // stored candidates (ends >= x + K when the sweep was seeded)
     uint32_t short_hi = 0;     // short candidates still to walk: ends x+1 .. short_hi (none if <= x)
@@ -142,11 +130,143 @@ struct Sweeper {
         last_start = start;
     }
 
-    // mode M_FETCH doubles as "start the next sweep": x >= L means no read is in progress.
+    // mode M_FETCH doubles as "needs a transition": x >= L means no read is in progress.
     GSM_HD void end_sweep(Ctx& c) {
         lb = x + 1; x = F; sweep_id++;
         mode = M_FETCH;
         if (x >= L) c.finish(rid, n_mems);
+    }
+
+    // Start the sweep at x (a read is in progress, x < L).  Leaves a pending operation, or mode == M_FETCH.
+    GSM_HD void start_sweep(Ctx& c, const IndexMeta& m) {
+        const uint32_t b = c.base(x);
+        ncand = 0; short_hi = 0; have_tpos = 0;
+        if (m.cnt[b] == 0) {              // base absent from the text (outside the reference's domain): skip it
+            lb = x + 1; x++; sweep_id++;
+            if (x >= L) c.finish(rid, n_mems);
+            return;                       // mode stays M_FETCH
+        }
+        const uint32_t K = c.seed_k();
+        if (K != 0 && x + K <= L) { P0 = c.kmer(x); mode = M_SEEDF; return; }
+        fwd_plain(c, m);
+    }
+
+    GSM_HD void fwd_plain(Ctx& c, const IndexMeta& m) {
+        const uint32_t b = c.base(x);
+        k = m.C[b]; P0 = m.C[b]; cnt = m.cnt[b];
+        pos = x + 1;
+        fwd_continue(c, m);
+    }
+
+    // (k, P0, cnt) describe q[x:pos): append q[pos], or close the forward phase at the read end.  A unique occurrence
+    // is followed in the text instead (M_SAF -> M_CMPF).
+    GSM_HD void fwd_continue(Ctx& c, const IndexMeta& m) {
+        if (pos < L) {
+            if (cnt == 1u && c.uniq()) { aux = k; mode = M_SAF; return; }
+            ch = c.base(pos); mode = M_FWD;
+            return;
+        }
+        c.cand_put(ncand++, pos, k, cnt);
+        start_bwd(c, m);
+    }
+
+    // forward comparison finished (or impossible): q[x:pos) is the longest forward match
+    GSM_HD void uniq_fwd_done(Ctx& c, const IndexMeta& m) {
+        c.cand_put(ncand++, pos, k, 1u);
+        start_bwd(c, m);
+    }
+    // q[pos:cur_j) is matched at text index tpos - (x - pos): compare further left, or finish
+    GSM_HD void uniq_walk_next(Ctx& c, const IndexMeta& m) {
+        mode = M_CMPB;
+        if (cmp_max(m.n_rows - 1u) != 0u) return;
+        uniq_walk_done(c, m);
+    }
+    GSM_HD void uniq_walk_done(Ctx& c, const IndexMeta& m) {
+        if (pos == x) { walk_end(c, m, x); return; }            // no extension: the interval of the candidate stands
+        aux = tpos - (x - pos);                                 // the extended match starts here in the text
+        mode = M_ISA;
+    }
+
+    // result of the pending suffix-array / inverse-suffix-array fetch
+    GSM_HD void consume_word(Ctx& c, const IndexMeta& m, uint32_t v) {
+        if (mode == M_ISA) { P0 = v; cnt = 1u; walk_end(c, m, pos); return; }
+        tpos = v - 1u;                                          // suffix-array values are 1-based (ExactMatch.py:66)
+        have_tpos = 1u;
+        if (mode == M_SAF) {
+            mode = M_CMPF;
+            if (cmp_max(m.n_rows - 1u) == 0u) uniq_fwd_done(c, m);
+            return;
+        }
+        uniq_walk_next(c, m);                                   // M_SAW
+    }
+
+    // result of the pending text comparison: `matched` bases agree (already capped by cmp_max and the chunk size)
+    GSM_HD void consume_cmp(Ctx& c, const IndexMeta& m, uint32_t matched) {
+        if (mode == M_CMPF) {
+            pos += matched;
+            if (matched == SWEEP_CMP_CHUNK && cmp_max(m.n_rows - 1u) != 0u) return;     // a whole chunk agreed: next chunk
+            uniq_fwd_done(c, m);
+            return;
+        }
+        pos -= matched;
+        if (matched == SWEEP_CMP_CHUNK && cmp_max(m.n_rows - 1u) != 0u) return;
+        uniq_walk_done(c, m);
+    }
+
+    // Forward phase over: pop the longest candidate and walk it left.
+    GSM_HD void start_bwd(Ctx& c, const IndexMeta& m) {
+        c.cand_sync();
+        ncand--;
+        c.cand_get(ncand, cur_j, P0, cnt);
+        F = cur_j;
+        last_start = 0xFFFFFFFFu;
+        if (x == 0) {                       // nothing to prepend: every candidate starts at 0, the longest wins
+            emit_match(c, 0, cur_j, P0, cnt);
+            end_sweep(c);
+            return;
+        }
+        if (cnt == 1u && x != lb && c.uniq() && c.uniq_back()) {      // unique occurrence: extend it to the left along the text
+            pos = x;
+            if (have_tpos) uniq_walk_next(c, m);
+            else { aux = P0; mode = M_SAW; }
+            return;
+        }
+        walk_from(c, m, x);
+    }
+
+    // (P0, cnt) is the interval of q[start:cur_j): set up the step prepending q[start-1].  False if start is
+    // already the lower bound (no match ending beyond x starts left of lb) or the left end of the read.
+    GSM_HD bool try_walk(Ctx& c, uint32_t start) {
+        if (start == lb || start == 0) return false;
+        pos = start - 1;
+        ch = c.base(pos);
+        mode = M_WALK;
+        return true;
+    }
+
+    GSM_HD void walk_from(Ctx& c, const IndexMeta& m, uint32_t start) {
+        if (!try_walk(c, start)) walk_end(c, m, start);
+    }
+
+    // The walked candidate (cur_j, P0, cnt) cannot be extended beyond `start`: it is maximal iff it reaches further
+    // left than every longer candidate did.  A walk that stops at lb settles all the shorter candidates too.
+    // Then the next candidate (stored ones first, longest first; then the short ends) is set up.
+    GSM_HD void walk_end(Ctx& c, const IndexMeta& m, uint32_t start) {
+        for (;;) {
+            if (start < last_start) emit_match(c, start, cur_j, P0, cnt);
+            if (start == lb || (ncand == 0 && short_hi <= x)) { end_sweep(c); return; }
+            if (ncand != 0) {                   // stored candidate: continue from its interval at x
+                ncand--;
+                c.cand_get(ncand, cur_j, P0, cnt);
+                start = x;
+            } else {                            // short candidate: end in (x, x + K)
+                cur_j = short_hi--;
+                const uint32_t K = c.seed_k();
+                if (cur_j >= K && cur_j - K >= lb) { P0 = c.kmer(cur_j - K); mode = M_SEEDB; return; }
+                start = plain_begin(c, m);
+            }
+            if (try_walk(c, start)) return;
+        }
     }
 
     // backward search of q[..cur_j) from scratch; q[x:cur_j) occurs, so its last base does
@@ -156,155 +276,39 @@ struct Sweeper {
         return cur_j - 1;
     }
 
-    // q[pos:cur_j) is matched at text index tpos - (x - pos): compare further left, or finish (host-compiled test only)
-    GSM_HD void uniq_walk_next(const IndexMeta& m) {
-        mode = M_CMPB;
-        if (cmp_max(m.n_rows - 1u) != 0u) return;
-        uniq_walk_done();
-    }
-    GSM_HD void uniq_walk_done() {
-        if (pos == x) { mode = T_WALK_END; return; }            // no extension: the interval of the candidate stands
-        aux = tpos - (x - pos);                                 // the extended match starts here in the text
-        mode = M_ISA;
-    }
-
-    // Bring this read to its next pending operation.  Returns false only when there are no more reads.
-    // The transitions below are written as consecutive blocks in the order they follow one another, so one pass of the
-    // loop resolves a whole chain (forward phase over -> pop the longest candidate -> ... -> next sweep -> its seed
-    // fetch), and every block exists ONCE: lanes that need the same transition execute it together.
+    // Bring this pair to its next pending operation.  Returns false only when there are no more reads.
     GSM_HD bool next(Ctx& c, const IndexMeta& m) {
-        for (;;) {
-            if (mode == T_FWD_PLAIN) {
-                const uint32_t b = c.base(x);
-                k = m.C[b]; P0 = m.C[b]; cnt = m.cnt[b];
-                pos = x + 1;
-                mode = T_FWD_CONT;
+        while (mode == M_FETCH) {
+            if (x >= L) {                   // no read in progress (initial state: x == L == 0)
+                if (!c.fetch(rid, L)) { mode = M_DONE; return false; }
+                n_mems = 0; sweep_id = 0; x = 0; lb = 0;
+                if (L == 0) { c.finish(rid, 0); continue; }
             }
-            if (mode == T_FWD_CONT) {
-                // (k, P0, cnt) describe q[x:pos): append q[pos], or close the forward phase at the read end.  A unique
-                // occurrence is followed in the text instead (M_SAF -> M_CMPF).
-                if (pos >= L) mode = T_FWD_END;
-                else if (cnt == 1u && c.uniq()) { aux = k; mode = M_SAF; }
-                else { ch = c.base(pos); mode = M_FWD; }
-            }
-            if (mode == T_FWD_END) {
-                c.cand_put(ncand++, pos, k, cnt);
-                mode = T_START_BWD;
-            }
-            if (mode == T_START_BWD) {
-                // Forward phase over: pop the longest candidate and walk it left.
-                c.cand_sync();
-                ncand--;
-                c.cand_get(ncand, cur_j, P0, cnt);
-                F = cur_j;
-                last_start = 0xFFFFFFFFu;
-                pos = x;
-                if (x == 0) {                       // nothing to prepend: every candidate starts at 0, the longest wins
-                    emit_match(c, 0, cur_j, P0, cnt);
-                    end_sweep(c);
-                } else if (cnt == 1u && x != lb && c.uniq() && c.uniq_back()) {      // unique: extend it to the left along the text
-                    if (have_tpos) uniq_walk_next(m);
-                    else { aux = P0; mode = M_SAW; }
-                } else {
-                    mode = T_WALK_FROM;
-                }
-            }
-            if (mode == T_WALK_FROM) {
-                // (P0, cnt) is the interval of q[pos:cur_j): set up the step prepending q[pos-1] -- unless pos is already
-                // the lower bound (no match ending beyond x starts left of lb) or the left end of the read.
-                if (pos == lb || pos == 0u) mode = T_WALK_END;
-                else { pos -= 1u; ch = c.base(pos); mode = M_WALK; }
-            }
-            if (mode == T_WALK_END) {
-                // The walked candidate (cur_j, P0, cnt) cannot be extended beyond `start`: it is maximal iff it reaches
-                // further left than every longer candidate did.  A walk that stops at lb settles all the shorter
-                // candidates too.  Then the next candidate (stored ones first, longest first; then the short ends) is set up.
-                uint32_t start = pos;
-                for (;;) {
-                    if (start < last_start) emit_match(c, start, cur_j, P0, cnt);
-                    if (start == lb || (ncand == 0 && short_hi <= x)) { end_sweep(c); break; }
-                    if (ncand != 0) {                   // stored candidate: continue from its interval at x
-                        ncand--;
-                        c.cand_get(ncand, cur_j, P0, cnt);
-                        start = x;
-                    } else {                            // short candidate: end in (x, x + K)
-                        cur_j = short_hi--;
-                        const uint32_t K = c.seed_k();
-                        if (cur_j >= K && cur_j - K >= lb) { P0 = c.kmer(cur_j - K); mode = M_SEEDB; break; }
-                        start = plain_begin(c, m);
-                    }
-                    if (start != lb && start != 0u) { pos = start - 1u; ch = c.base(pos); mode = M_WALK; break; }
-                }
-            }
-            if (mode == M_FETCH) {
-                if (x >= L) {                   // no read in progress (initial state: x == L == 0)
-                    if (!c.fetch(rid, L)) { mode = M_DONE; return false; }
-                    n_mems = 0; sweep_id = 0; x = 0; lb = 0;
-                    if (L == 0) { c.finish(rid, 0); continue; }
-                }
-                // start the sweep at x (a read is in progress, x < L)
-                const uint32_t b = c.base(x);
-                ncand = 0; short_hi = 0; have_tpos = 0;
-                if (m.cnt[b] == 0) {              // base absent from the text (outside the reference's domain): skip it
-                    lb = x + 1; x++; sweep_id++;
-                    if (x >= L) c.finish(rid, n_mems);
-                    continue;
-                }
-                const uint32_t K = c.seed_k();
-                if (K != 0 && x + K <= L) { P0 = c.kmer(x); mode = M_SEEDF; }
-                else { mode = T_FWD_PLAIN; continue; }
-            }
-            if (mode >= T_FWD_PLAIN) continue;          // a transition named by an earlier block of this pass (rare back edge)
-            return mode != M_DONE;
+            start_sweep(c, m);
         }
-    }
-
-    // result of the pending suffix-array / inverse-suffix-array fetch
-    GSM_HD void consume_word(Ctx& c, const IndexMeta& m, uint32_t v) {
-        if (mode == M_ISA) { P0 = v; cnt = 1u; mode = T_WALK_END; return; }
-        tpos = v - 1u;                                          // suffix-array values are 1-based (ExactMatch.py:66)
-        have_tpos = 1u;
-        if (mode == M_SAF) {
-            mode = M_CMPF;
-            if (cmp_max(m.n_rows - 1u) == 0u) mode = T_FWD_END;
-            return;
-        }
-        uniq_walk_next(m);                                      // M_SAW
-    }
-
-    // result of the pending text comparison: `matched` bases agree (already capped by cmp_max and the chunk size)
-    GSM_HD void consume_cmp(Ctx& c, const IndexMeta& m, uint32_t matched) {
-        if (mode == M_CMPF) {
-            pos += matched;
-            if (matched == SWEEP_CMP_CHUNK && cmp_max(m.n_rows - 1u) != 0u) return;     // a whole chunk agreed: next chunk
-            mode = T_FWD_END;                                   // q[x:pos) is the longest forward match
-            return;
-        }
-        pos -= matched;
-        if (matched == SWEEP_CMP_CHUNK && cmp_max(m.n_rows - 1u) != 0u) return;
-        uniq_walk_done();
+        return mode != M_DONE;
     }
 
     // result of the pending seed-table fetch
     GSM_HD void consume_seed(Ctx& c, const IndexMeta& m, const SeedEntry& e) {
         if (mode == M_SEEDF) {
-            if (e.cnt == 0) { mode = T_FWD_PLAIN; return; }       // q[x:x+K) does not occur: F(x) < x + K
+            if (e.cnt == 0) { fwd_plain(c, m); return; }          // q[x:x+K) does not occur: F(x) < x + K
             k = e.fwd_lo; P0 = e.rev_lo; cnt = e.cnt;
             pos = x + c.seed_k();
             short_hi = pos - 1;
-            mode = T_FWD_CONT;
+            fwd_continue(c, m);
             return;
         }
         // M_SEEDB: seed of the short candidate ending at cur_j
-        if (e.cnt == 0) pos = plain_begin(c, m);
-        else { P0 = e.fwd_lo; cnt = e.cnt; pos = cur_j - c.seed_k(); }
-        mode = T_WALK_FROM;
+        if (e.cnt == 0) { walk_from(c, m, plain_begin(c, m)); return; }
+        P0 = e.fwd_lo; cnt = e.cnt;
+        walk_from(c, m, cur_j - c.seed_k());
     }
 
     // result of the pending FM step
     GSM_HD void consume(Ctx& c, const IndexMeta& m, const StepOut& r) {
         // FWD (append q[pos] to q[x:pos)) and WALK (prepend q[pos] to q[pos+1:cur_j)) share one hot path:
-        // take the new interval, move one base, fetch it.  Only the ends of an extension name a transition.
+        // take the new interval, move one base, fetch it.  Only the ends of an extension branch.
         const bool fwd = mode == M_FWD;
         if (fwd && r.cnt_new != cnt) c.cand_put(ncand++, pos, k, cnt);     // count about to change: q[x:pos) is a candidate
         if (r.cnt_new != 0) {
@@ -312,12 +316,16 @@ struct Sweeper {
             // one site for both directions: FWD and WALK lanes of a warp fetch their next base together
             const bool more = fwd ? (pos + 1u != L) : (pos != lb && pos != 0u);
             if (more && !(fwd && cnt == 1u && c.uniq())) { pos += fwd ? 1u : 0xFFFFFFFFu; ch = c.base(pos); return; }
-            if (fwd) { pos++; mode = T_FWD_CONT; }                         // read end, or unique: follow the text
-            else mode = T_WALK_END;                                        // reached the lower bound (or the left end): start = pos
+            if (fwd) {
+                pos++;
+                fwd_continue(c, m);                                        // read end, or unique: follow the text
+                return;
+            }
+            walk_end(c, m, pos);                                           // reached the lower bound (or the left end)
             return;
         }
-        if (fwd) mode = T_START_BWD;
-        else { pos += 1u; mode = T_WALK_END; }
+        if (fwd) start_bwd(c, m);
+        else walk_end(c, m, pos + 1u);
     }
 };
 

@@ -225,7 +225,7 @@ typedef struct {
     void* quad_scratch;    /* per-resident-quad staging */
     uint64_t quad_scratch_bytes;
     uint32_t* mem_off;     /* n_reads */
-    uint32_t* mem_cnt;     /* n_reads: matches per read; bit 31 set = the list is already in ascending order */
+    uint32_t* mem_cnt;     /* n_reads: matches per read; bit 31 set = the list is in ascending order and stored field by field */
     gsm_record* rec_tmp;   /* unordered record pool, rec_cap entries */
     uint64_t rec_cap;
     uint32_t* rec_tmp_off; /* n_reads */
