@@ -103,6 +103,7 @@ EXPORTS = {
                                             C.c_void_p, C.c_void_p]),
     "gsm_gather_advance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "gsm_gather_probe": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
+    "gsm_gather_probe2": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "gsm_l2_persist": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "gsm_device_l2_fetch_granularity": (C.c_int, [C.c_int32, C.POINTER(C.c_uint32)]),
     "gsm_last_error": (C.c_char_p, []),

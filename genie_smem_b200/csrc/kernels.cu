@@ -786,6 +786,39 @@ __global__ void __launch_bounds__(128) k_gather_probe(const uint4* buf, uint64_t
     if (acc == 0x7FFFFFFFu) atomicAdd(sink, 1ull);
 }
 
+// The same ceiling measured without the probe's own bottlenecks: U independent fetches in flight per lane,
+// power-of-two masking instead of a 64-bit modulo, and the access shapes the kernels really use -- BYTES = 64 (one lane
+// reads a whole bucket: two 256-bit loads, k_sweep1 / k_locate_sampled), 32 (one 256-bit load), 16 (one seed-table entry).
+template <int BYTES, int U>
+__global__ void __launch_bounds__(128) k_gather_probe2(const uint4* buf, uint64_t unit_mask, uint32_t iters, unsigned long long* sink) {
+    const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t state = gt * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    uint32_t acc = 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+        uint64_t idx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            state = state * 6364136223846793005ull + 1442695040888963407ull;
+            idx[u] = (state >> 20) & unit_mask;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (BYTES == 16) {
+                const uint4 v = ldg_seed(buf + idx[u]);
+                acc += v.x ^ v.y ^ v.z ^ v.w;
+            } else {
+                const Half h0 = ldg_half(buf, idx[u] * (BYTES / 32));
+                acc += h0.c0 ^ h0.c1 ^ h0.l0 ^ h0.l1 ^ h0.l2 ^ h0.h0 ^ h0.h1 ^ h0.h2;
+                if (BYTES == 64) {
+                    const Half h1 = ldg_half(buf, idx[u] * 2 + 1);
+                    acc += h1.c0 ^ h1.c1 ^ h1.l0 ^ h1.l1 ^ h1.l2 ^ h1.h0 ^ h1.h1 ^ h1.h2;
+                }
+            }
+        }
+    }
+    if (acc == 0x7FFFFFFFu) atomicAdd(sink, 1ull);
+}
+
 }  // namespace gsm
 
 // ===================================================================================== C ABI
@@ -1231,6 +1264,34 @@ int gsm_gather_advance(uint64_t* base_dev, const uint64_t* counts_dev, uint32_t 
     if (st) return st;
     k_gather_advance<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)base_dev, (const unsigned long long*)counts_dev, world);
     GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
+int gsm_gather_probe2(const void* buf, uint64_t bytes, uint64_t n_fetch, uint32_t fetch_bytes, uint32_t in_flight, uint64_t* sink, uint64_t* n_done,
+                      void* stream) {
+    if (!buf || !sink || bytes < 64 || (fetch_bytes != 16 && fetch_bytes != 32 && fetch_bytes != 64) || (in_flight != 1 && in_flight != 4 && in_flight != 8))
+        return fail(GSM_E_INVALID, "gsm_gather_probe2: fetch_bytes in {16, 32, 64}, in_flight in {1, 4, 8}");
+    int st = device_ready();
+    if (st) return st;
+    int dev = 0, sms = 0;
+    GSM_CUDA(cudaGetDevice(&dev));
+    GSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    uint64_t units = bytes / fetch_bytes, pow2 = 1;
+    while (pow2 * 2 <= units) pow2 *= 2;                  // the largest power of two of units: index by mask
+    const uint64_t threads = (uint64_t)sms * 16 * 128;
+    uint32_t iters = (uint32_t)((n_fetch + threads * in_flight - 1) / (threads * in_flight));
+    if (iters == 0) iters = 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint4* b = (const uint4*)buf;
+    unsigned long long* sk = (unsigned long long*)sink;
+    const unsigned grid = (unsigned)(sms * 16);
+#define GSM_PROBE2(B, U) k_gather_probe2<B, U><<<grid, 128, 0, s>>>(b, pow2 - 1, iters, sk)
+    if (fetch_bytes == 16) { if (in_flight == 1) GSM_PROBE2(16, 1); else if (in_flight == 4) GSM_PROBE2(16, 4); else GSM_PROBE2(16, 8); }
+    else if (fetch_bytes == 32) { if (in_flight == 1) GSM_PROBE2(32, 1); else if (in_flight == 4) GSM_PROBE2(32, 4); else GSM_PROBE2(32, 8); }
+    else { if (in_flight == 1) GSM_PROBE2(64, 1); else if (in_flight == 4) GSM_PROBE2(64, 4); else GSM_PROBE2(64, 8); }
+#undef GSM_PROBE2
+    GSM_CUDA(cudaGetLastError());
+    if (n_done) *n_done = threads * in_flight * iters;
     return GSM_OK;
 }
 

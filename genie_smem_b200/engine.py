@@ -850,6 +850,22 @@ def gather_probe(buf: torch.Tensor, n_fetch, dependent):
     return int(done.value), e0.elapsed_time(e1) * 1e-3
 
 
+def gather_probe2(buf: torch.Tensor, n_fetch, fetch_bytes=64, in_flight=4):
+    """Random gather ceiling with the kernels' access shapes (gsm_gather_probe2); returns (#fetches, seconds)."""
+    require_cuda()
+    sink = torch.zeros(1, dtype=torch.int64, device=buf.device)
+    done = C.c_uint64()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nbytes = buf.numel() * buf.element_size()
+    capi.check(capi.lib.gsm_gather_probe2(_ptr(buf), nbytes, max(n_fetch // 8, 1), int(fetch_bytes), int(in_flight), _ptr(sink), C.byref(done), _stream()))
+    torch.cuda.synchronize()
+    e0.record()
+    capi.check(capi.lib.gsm_gather_probe2(_ptr(buf), nbytes, int(n_fetch), int(fetch_bytes), int(in_flight), _ptr(sink), C.byref(done), _stream()))
+    e1.record()
+    torch.cuda.synchronize()
+    return int(done.value), e0.elapsed_time(e1) * 1e-3
+
+
 # ---------------------------------------------------------------------------- pipelined end-to-end path
 class _ReadView:
     """Reads [lo, hi) of a ReadBatch whose buffers are (being) copied to the device."""

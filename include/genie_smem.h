@@ -359,6 +359,12 @@ int gsm_rmi_lookup_batch(const gsm_dev_index* idx, const gsm_dev_rmi* rmi, uint6
 int gsm_gather_probe(const void* buf, uint64_t bytes, uint64_t n_fetch, uint32_t dependent,
                      uint64_t* sink, uint64_t* n_done, void* stream);
 
+/* The same ceiling with the kernels' real access shapes and enough memory parallelism: every lane keeps `in_flight`
+ * (1, 4 or 8) independent fetches of `fetch_bytes` (64 = a whole bucket by one lane, 32 = one 256-bit load, 16 = one seed-table
+ * entry) outstanding, indices masked to the largest power of two of units in `bytes`. */
+int gsm_gather_probe2(const void* buf, uint64_t bytes, uint64_t n_fetch, uint32_t fetch_bytes, uint32_t in_flight,
+                      uint64_t* sink, uint64_t* n_done, void* stream);
+
 /* Pin [ptr, ptr+bytes) in the persisting part of the L2 for kernels launched on `stream` (access-policy window; the small,
  * randomly read top of a structure: RMI model parameters, the top of a k-mer table).  ptr == NULL or bytes == 0 removes the
  * window and resets the persisting lines. */
