@@ -126,28 +126,62 @@ GSM_HD StepOut finish_step(uint32_t eq0, uint32_t eq1, uint32_t ltd, uint32_t P0
     return o;
 }
 
-// Whole-bucket rank by ONE thread (selection kernels' rare paths, LUT builder, host logic test).
-// load(i) returns the i-th 32-byte half of the bucket array.
+// "equals c" / "less than c" bit masks of a whole bucket's 6 x 32 symbols (half 0: words 0..2, half 1: words 3..5)
+GSM_HD void bucket_masks(const Half& h0, const Half& h1, const SymK& k, uint32_t (&E)[6], uint32_t (&T)[6]) {
+    const uint32_t L[6] = {h0.l0, h0.l1, h0.l2, h1.l0, h1.l1, h1.l2}, H[6] = {h0.h0, h0.h1, h0.h2, h1.h0, h1.h1, h1.h2};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int w = 0; w < 6; ++w) {
+        E[w] = (L[w] ^ k.fl) & (H[w] ^ k.fh);
+        T[w] = ((~H[w] & (~L[w] | k.X)) | (~L[w] & k.Y)) & k.nz;
+    }
+}
+
+// counts below in-bucket offset r (0..191): (#symbols == c) | (#symbols < c) << 16
+GSM_HD uint32_t bucket_counts(const uint32_t (&E)[6], const uint32_t (&T)[6], uint32_t r) {
+    uint32_t eq = 0, lt = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int w = 0; w < 6; ++w) {
+        const uint32_t m = mask_low(clamp32((int)r - 32 * w));
+        eq += popc32(E[w] & m);
+        lt += popc32(T[w] & m);
+    }
+    return eq | (lt << 16);
+}
+
+// Whole-bucket rank by ONE thread (selection kernels, table builders, host logic test).
+// load(i) returns the i-th 32-byte half of the bucket array.  Rows P0 and P1 usually lie in the same bucket (narrow
+// intervals): its two halves are loaded once and the symbol masks built once for both offsets.
 template <typename LoadHalf>
 GSM_HD StepOut step_single(LoadHalf load, uint32_t P0, uint32_t P1, uint32_t c, uint32_t Cc, uint32_t primary) {
     const SymK k = sym_consts(c);
-    uint32_t eq[2], lt[2];
-    const uint32_t P[2] = {P0, P1};
-    for (int e = 0; e < 2; ++e) {
-        uint32_t b, r;
-        split192(P[e], b, r);
-        uint32_t acc = 0, he = 0, hl = 0;
-        for (uint32_t g = 0; g < 2; ++g) {
-            const Half v = load((uint64_t)b * 2 + g);
-            uint32_t a, l;
-            half_header(v, c, g, a, l);
-            he += a; hl += l;
-            acc += half_counts(v, r, k, g);
-        }
-        eq[e] = he + (acc & 0xFFu);
-        lt[e] = hl + ((acc >> 8) & 0xFFu);
+    uint32_t b0, r0, b1, r1;
+    split192(P0, b0, r0);
+    split192(P1, b1, r1);
+    uint32_t E[6], T[6];
+    const Half a0 = load((uint64_t)b0 * 2), a1 = load((uint64_t)b0 * 2 + 1);
+    bucket_masks(a0, a1, k, E, T);
+    const uint32_t acc0 = bucket_counts(E, T, r0);
+    uint32_t e0, l0, e1, l1;
+    half_header(a0, c, 0u, e0, l0);
+    half_header(a1, c, 1u, e1, l1);
+    const uint32_t eq0 = e0 + e1 + (acc0 & 0xFFFFu), lt0 = l0 + l1 + (acc0 >> 16);
+    uint32_t eq1, lt1;
+    if (b1 == b0) {
+        const uint32_t acc1 = bucket_counts(E, T, r1);
+        eq1 = e0 + e1 + (acc1 & 0xFFFFu); lt1 = l0 + l1 + (acc1 >> 16);
+    } else {
+        const Half c0 = load((uint64_t)b1 * 2), c1 = load((uint64_t)b1 * 2 + 1);
+        bucket_masks(c0, c1, k, E, T);
+        const uint32_t acc1 = bucket_counts(E, T, r1);
+        half_header(c0, c, 0u, e0, l0);
+        half_header(c1, c, 1u, e1, l1);
+        eq1 = e0 + e1 + (acc1 & 0xFFFFu); lt1 = l0 + l1 + (acc1 >> 16);
     }
-    return finish_step(eq[0], eq[1], lt[1] - lt[0], P0, P1, c, Cc, primary);
+    return finish_step(eq0, eq1, lt1 - lt0, P0, P1, c, Cc, primary);
 }
 
 // LF mapping by ONE thread: row r -> the row of the suffix that starts one base earlier (suffix_array[LF(r)] =

@@ -207,28 +207,6 @@ constexpr int SWEEP1_THREADS = 128;
 constexpr int SWEEP1_CAP = 8;                              // candidates kept in shared memory per read
 constexpr int SWEEP1_MIN_BLOCKS = 7;                       // register budget: 72 per thread (measured best of 6 / 7 / 8, profiles/r02_notes.md)
 
-// counts of one bucket (its two halves) below in-bucket offset r: (#symbols == c) | (#symbols < c) << 16.  E[] / T[] are the
-// per-word "equals c" / "less than c" bit masks of the bucket's 6 x 32 symbols.
-__device__ __forceinline__ uint32_t bucket_counts(const uint32_t (&E)[6], const uint32_t (&T)[6], uint32_t r) {
-    uint32_t eq = 0, lt = 0;
-#pragma unroll
-    for (int w = 0; w < 6; ++w) {
-        const uint32_t m = mask_low(clamp32((int)r - 32 * w));
-        eq += popc32(E[w] & m);
-        lt += popc32(T[w] & m);
-    }
-    return eq | (lt << 16);
-}
-
-__device__ __forceinline__ void bucket_masks(const Half& h0, const Half& h1, const SymK& k, uint32_t (&E)[6], uint32_t (&T)[6]) {
-    const uint32_t L[6] = {h0.l0, h0.l1, h0.l2, h1.l0, h1.l1, h1.l2}, H[6] = {h0.h0, h0.h1, h0.h2, h1.h0, h1.h1, h1.h2};
-#pragma unroll
-    for (int w = 0; w < 6; ++w) {
-        E[w] = (L[w] ^ k.fl) & (H[w] ^ k.fh);
-        T[w] = ((~H[w] & (~L[w] | k.X)) | (~L[w] & k.Y)) & k.nz;
-    }
-}
-
 // One FM extension step by ONE lane, ONE bucket per pass.  Rows P0 and P1 usually fall into the same 192-row bucket
 // (the interval is narrow after the seed): one pass reads that bucket (two 256-bit loads), builds the "equals c" /
 // "less than c" masks once and counts below both offsets.  When they straddle two buckets (about one step in eight) the
