@@ -51,22 +51,66 @@ static int is_miss(tup t) { return t.hi < t.lo; }
 static int code_of(char ch) { return ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : -1; }
 
 /* ------------------------------------------------------------------ index */
+/* The arrays of orc_create are filled by all cores (three passes over n rows; the middle one gathers text[sa - 2] at random
+ * and takes minutes single-threaded at 10^9 rows).  Rows are cut into one contiguous slice per thread. */
+typedef struct {
+    orc_index* ix; const char* text; uint64_t n_bases; int pass; int tid, nthreads;
+    int64_t cnt[4];          /* pass 0: base counts of the slice; pass 2: BWT symbol counts of the slice's 64-row blocks */
+} create_job;
+
+static void* create_worker(void* arg) {
+    create_job* j = (create_job*)arg;
+    orc_index* ix = j->ix;
+    const int64_t n = ix->n;
+    if (j->pass == 0) {                 /* text codes + per-slice base counts */
+        uint64_t a = j->n_bases * (uint64_t)j->tid / j->nthreads, b = j->n_bases * (uint64_t)(j->tid + 1) / j->nthreads;
+        for (uint64_t i = a; i < b; ++i) { int c = code_of(j->text[i]); ix->text[i] = (uint8_t)c; if (c >= 0) j->cnt[c]++; }
+    } else if (j->pass == 1) {          /* bwt[r] = text[sa[r] - 2] (ExactMatch.py:59-64), '$' (code 4) where sa[r] == 1 */
+        int64_t a = n * j->tid / j->nthreads, b = n * (j->tid + 1) / j->nthreads;
+        for (int64_t r = a; r < b; ++r) { uint32_t p = ix->sa[r]; ix->bwt[r] = p == 1 ? 4 : ix->text[p - 2]; }
+    } else {                            /* slices of whole 64-row blocks: count symbols, checkpoints filled after the prefix */
+        int64_t nb = (n >> 6) + 1, a = nb * j->tid / j->nthreads, b = nb * (j->tid + 1) / j->nthreads;
+        if (j->pass == 2) {
+            for (int64_t r = a << 6; r < (b << 6) && r < n; ++r) if (ix->bwt[r] < 4) j->cnt[ix->bwt[r]]++;
+        } else {                        /* pass 3: j->cnt holds the counts before the slice */
+            uint32_t run[4] = {(uint32_t)j->cnt[0], (uint32_t)j->cnt[1], (uint32_t)j->cnt[2], (uint32_t)j->cnt[3]};
+            for (int64_t blk = a; blk < b; ++blk) {
+                memcpy(ix->ckpt + 4 * blk, run, sizeof(run));
+                for (int64_t r = blk << 6; r < ((blk + 1) << 6) && r < n; ++r) if (ix->bwt[r] < 4) run[ix->bwt[r]]++;
+            }
+        }
+    }
+    return 0;
+}
+
+static void create_pass(create_job* jobs, int nthreads, int pass) {
+    pthread_t th[256];
+    for (int t = 0; t < nthreads; ++t) { jobs[t].pass = pass; pthread_create(&th[t], 0, create_worker, &jobs[t]); }
+    for (int t = 0; t < nthreads; ++t) pthread_join(th[t], 0);
+}
+
 void* orc_create(const char* text, uint64_t n_bases, const uint32_t* sa1) {
     orc_index* ix = (orc_index*)calloc(1, sizeof(orc_index));
     int64_t n = (int64_t)n_bases + 1;
     ix->n = n; ix->sa = sa1;
     ix->bwt = (uint8_t*)malloc(n);
     ix->text = (uint8_t*)malloc(n_bases ? n_bases : 1);
-    for (uint64_t i = 0; i < n_bases; ++i) { ix->text[i] = (uint8_t)code_of(text[i]); ix->cnt[ix->text[i]]++; }
+    ix->ckpt = (uint32_t*)malloc(sizeof(uint32_t) * 4 * (n / 64 + 2));
+    long cores = sysconf(_SC_NPROCESSORS_ONLN);
+    int nthreads = n < (1 << 20) ? 1 : (cores < 1 ? 1 : (cores > 256 ? 256 : (int)cores));
+    create_job* jobs = (create_job*)calloc((size_t)nthreads, sizeof(create_job));
+    for (int t = 0; t < nthreads; ++t) { jobs[t].ix = ix; jobs[t].text = text; jobs[t].n_bases = n_bases; jobs[t].tid = t; jobs[t].nthreads = nthreads; }
+    create_pass(jobs, nthreads, 0);
+    for (int t = 0; t < nthreads; ++t) for (int c = 0; c < 4; ++c) { ix->cnt[c] += jobs[t].cnt[c]; jobs[t].cnt[c] = 0; }
     ix->C[0] = 1;
     for (int c = 1; c < 4; ++c) ix->C[c] = ix->C[c - 1] + ix->cnt[c - 1];
-    for (int64_t r = 0; r < n; ++r) { uint32_t p = sa1[r]; ix->bwt[r] = p == 1 ? 4 : ix->text[p - 2]; }
-    ix->ckpt = (uint32_t*)malloc(sizeof(uint32_t) * 4 * (n / 64 + 2));
-    uint32_t run[4] = {0, 0, 0, 0};
-    for (int64_t r = 0; r <= n; ++r) {
-        if ((r & 63) == 0) memcpy(ix->ckpt + 4 * (r >> 6), run, sizeof(run));
-        if (r < n && ix->bwt[r] < 4) run[ix->bwt[r]]++;
-    }
+    create_pass(jobs, nthreads, 1);
+    create_pass(jobs, nthreads, 2);
+    int64_t run[4] = {0, 0, 0, 0};      /* exclusive prefix of the slices' symbol counts */
+    for (int t = 0; t < nthreads; ++t) for (int c = 0; c < 4; ++c) { int64_t v = jobs[t].cnt[c]; jobs[t].cnt[c] = run[c]; run[c] += v; }
+    create_pass(jobs, nthreads, 3);
+    { uint32_t last[4] = {(uint32_t)run[0], (uint32_t)run[1], (uint32_t)run[2], (uint32_t)run[3]}; memcpy(ix->ckpt + 4 * ((n >> 6) + 1), last, sizeof(last)); }
+    free(jobs);
     return ix;
 }
 
