@@ -697,18 +697,17 @@ struct Selector {
         cd.lo = (int64_t)l; cd.hi = (int64_t)l + n - 1; cd.lazy = false;
     }
 
-    // forward_extension(query, pc+K, kmer, seed) (SMEM.py:425-443): longest key and its value
-    GSM_HD static Cand fwd_only(Ctx& c, uint32_t pc, int64_t slo, int64_t shi) {
-        const uint32_t f = F_of(c, pc);
+    // forward_extension(query, pc+K, kmer, seed) (SMEM.py:425-443): longest key and its value.  f = F(pc).
+    GSM_HD static Cand fwd_only(Ctx& c, uint32_t pc, int64_t slo, int64_t shi, uint32_t f) {
         if (f <= pc + c.K) return known(pc, pc + c.K, slo, shi);     // the seed key itself
         return lazy_iv(pc, f);
     }
+    GSM_HD static Cand fwd_only(Ctx& c, uint32_t pc, int64_t slo, int64_t shi) { return fwd_only(c, pc, slo, shi, F_of(c, pc)); }
 
     // backward_extension(query, pc, keys) (SMEM.py:389-423) over keys pc+K .. max(F(pc), pc+K)
-    // (all_keys) or over the seed key only.
-    GSM_HD static Cand bext(Ctx& c, uint32_t pc, int64_t slo, int64_t shi, bool all_keys) {
+    // (all_keys) or over the seed key only.  f = F(pc), k0 = first match whose end exceeds pc + K - 1.
+    GSM_HD static Cand bext(Ctx& c, uint32_t pc, int64_t slo, int64_t shi, bool all_keys, uint32_t f, uint32_t k0) {
         const uint32_t K = c.K;
-        uint32_t f = F_of(c, pc);
         const bool seed_true = f >= pc + K;           // the k-mer really occurs
         uint32_t jmax = all_keys ? (f > pc + K ? f : pc + K) : pc + K;
         // extended keys: j in [pc+K, jmax] with LS[j] < pc; only maximal-match ends and jmax matter
@@ -716,7 +715,7 @@ struct Selector {
         uint32_t bi = 0, bj = 0, bk = 0;
         bool b_from_mem = false;
         if (seed_true) {
-            for (uint32_t k = first_end_above(c, pc + K - 1); k < c.n_mems; ++k) {
+            for (uint32_t k = k0; k < c.n_mems; ++k) {
                 const uint32_t w = c.se(k), s = w & 0xFFFFu, e = w >> 16;
                 if (s >= pc) break;                    // starts are sorted: no further left extension
                 uint32_t j = e <= jmax ? e : jmax;     // plateau end, or the key range's last key
@@ -796,8 +795,13 @@ struct Selector {
         // frame: 0 = None, 1 = () , 2 = k-mer frame
         int fstate = 0;
         uint32_t pc = 0; bool pfw = false, ptrue = false; int64_t plo = 0, phi = -1;
+        uint32_t pF = 0, pE = 0;                 // of the frame's window: F(pc) and the first match whose end exceeds pc + K - 1
         Cand cd{false, false, 0, 0, 0, -1};
         const uint32_t pstart = e - plen;
+        // The windows of a round move left one base at a time, so the two positions the machine looks up in the match list
+        // per window (starts <= cpos, ends > cpos + K - 1) are CURSORS that only step left: two binary searches per round
+        // instead of three per window.
+        uint32_t nf = count_starts_upto(c, e), ne = first_end_above(c, e + K - 1);
         // Pass 2: the frame machine over the stored results.  Each window only DECIDES what happens to the previous frame
         // (A_*); the extension itself runs at one place below, so that the threads of a warp that extend a frame do it
         // together whichever case of the reference they are in.  Step i == K is the closing extension (SMEM.py:149-171).
@@ -805,46 +809,51 @@ struct Selector {
         for (uint32_t i = 0; i <= K; ++i) {
             int act = A_NONE;
             uint32_t ai = 0, aj = 0;                // A_BEXT / A_FWD: frame start in ai; A_KNOWN: the candidate (ai, aj)
+            uint32_t aF = 0, aE = 0;                // A_BEXT / A_FWD: the frame's F(pc) and first-end cursor
             int64_t alo = 0, ahi = -1;
             bool aall = false;
             if (i == K) {
-                if (fstate == 2) { act = A_BEXT; ai = pc; alo = plo; ahi = phi; aall = pfw; }
+                if (fstate == 2) { act = A_BEXT; ai = pc; alo = plo; ahi = phi; aall = pfw; aF = pF; aE = pE; }
             } else {
                 if (i >= plen) continue;
                 const uint32_t cpos = e - i;
                 if (cpos + K > L) continue;
+                while (nf > 0u && sk(c, nf - 1u) > cpos) --nf;                    // matches starting at or before cpos
+                while (ne > 0u && ek(c, ne - 1u) > cpos + K - 1u) --ne;           // first match ending beyond the window
+                uint32_t Fc = cpos;                                               // F(cpos): end of the longest match starting there
+                if (nf > 0u) { const uint32_t en = ek(c, nf - 1u); Fc = en > cpos ? en : cpos; }
                 const int64_t lo = wlo[i], hi = whi[i];
                 const bool hit = (whit >> i) & 1u;
                 const bool tru = (wtrue >> i) & 1u;
                 if (hit) {
-                    if (fstate == 0) { fstate = 2; pc = cpos; pfw = true; plo = lo; phi = hi; ptrue = tru; }          // :70
-                    else if (fstate == 1) { fstate = 2; pc = cpos; pfw = false; plo = lo; phi = hi; ptrue = tru; }    // :73
+                    if (fstate == 0) { fstate = 2; pc = cpos; pfw = true; plo = lo; phi = hi; ptrue = tru; pF = Fc; pE = ne; }          // :70
+                    else if (fstate == 1) { fstate = 2; pc = cpos; pfw = false; plo = lo; phi = hi; ptrue = tru; pF = Fc; pE = ne; }    // :73
                     else {
                         // check_sequential of two TRUE k-mer intervals at adjacent windows is just
                         // "q[cpos : cpos+K+1) occurs" (SURVEY A13): read it off the match list
                         const bool both = tru && ptrue;
-                        const bool seq = (both && pc == cpos + 1) ? (F_of(c, cpos) >= cpos + K + 1)
+                        const bool seq = (both && pc == cpos + 1) ? (Fc >= cpos + K + 1)
                                                                   : c.sequential(cpos, lo, hi, pc, plo, phi, both);
                         if (seq) {                                                                        // Case 1
                             if (!pfw && cd.valid && (pc - pstart) + K < (cd.j - cd.i)) continue;          // :94-95 (the frame stays)
-                            act = A_BEXT; ai = pc; alo = plo; ahi = phi; aall = pfw;
+                            act = A_BEXT; ai = pc; alo = plo; ahi = phi; aall = pfw; aF = pF; aE = pE;
                         } else if (pfw) {                                                                 // Case 2
-                            act = A_FWD; ai = pc; alo = plo; ahi = phi;
+                            act = A_FWD; ai = pc; alo = plo; ahi = phi; aF = pF;
                         } else {
                             act = A_KNOWN; ai = cpos; aj = cpos + K; alo = lo; ahi = hi;
                         }
-                        pc = cpos; pfw = false; plo = lo; phi = hi; ptrue = tru;
+                        pc = cpos; pfw = false; plo = lo; phi = hi; ptrue = tru; pF = Fc; pE = ne;
                     }
                 } else {
                     if (fstate == 2) {                                                                    // Case 3
-                        if (pfw) { act = A_FWD; ai = pc; alo = plo; ahi = phi; }
+                        if (pfw) { act = A_FWD; ai = pc; alo = plo; ahi = phi; aF = pF; }
                         else { act = A_KNOWN; ai = pc; aj = pc + K; alo = plo; ahi = phi; }
                     }
                     fstate = 1;
                 }
             }
-            if (act == A_BEXT) upd(cd, bext(c, ai, alo, ahi, aall));
-            else if (act == A_FWD) upd(cd, fwd_only(c, ai, alo, ahi));
+            if (act == A_BEXT) upd(cd, bext(c, ai, alo, ahi, aall, aF, aE));
+            else if (act == A_FWD) upd(cd, fwd_only(c, ai, alo, ahi, aF));
             else if (act == A_KNOWN) upd(cd, known(ai, aj, alo, ahi));
         }
         if (!cd.valid) {                                                                              // :175-179
