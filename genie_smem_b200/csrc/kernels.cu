@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(128) k_gather_probe(const uint4* buf, uint64_t
 // The same ceiling measured without the probe's own bottlenecks: U independent fetches in flight per lane,
 // power-of-two masking instead of a 64-bit modulo, and the access shapes the kernels really use -- BYTES = 64 (one lane
 // reads a whole bucket: two 256-bit loads, k_sweep1 / k_locate_sampled), 32 (one 256-bit load), 16 (one seed-table entry).
-template <int BYTES, int U, int PF = 0>
+template <int BYTES, int U, int PF = 0>      // PF == 1: 64-byte fetches by lane PAIRS (one load instruction, one request per bucket)
 __global__ void __launch_bounds__(128) k_gather_probe2(const uint4* buf, uint64_t unit_mask, uint32_t iters, unsigned long long* sink) {
     const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t state = gt * 0x9E3779B97F4A7C15ull + 0x1234567ull;
@@ -807,10 +807,16 @@ __global__ void __launch_bounds__(128) k_gather_probe2(const uint4* buf, uint64_
                 const uint4 v = ldg_seed(buf + idx[u]);
                 acc += v.x ^ v.y ^ v.z ^ v.w;
             } else {
-                const Half h0 = ldg_half_pf<PF>(buf, idx[u] * (BYTES / 32));
+                if (PF == 1) {               // the pair shares the even lane's index: each lane loads one half of that bucket
+                    const uint64_t shared_idx = __shfl_sync(0xFFFFFFFFu, idx[u], threadIdx.x & 30u);
+                    const Half hp = ldg_half(buf, shared_idx * 2 + (threadIdx.x & 1u));
+                    acc += hp.c0 ^ hp.c1 ^ hp.l0 ^ hp.l1 ^ hp.l2 ^ hp.h0 ^ hp.h1 ^ hp.h2;
+                    continue;
+                }
+                const Half h0 = ldg_half(buf, idx[u] * (BYTES / 32));
                 acc += h0.c0 ^ h0.c1 ^ h0.l0 ^ h0.l1 ^ h0.l2 ^ h0.h0 ^ h0.h1 ^ h0.h2;
                 if (BYTES == 64) {
-                    const Half h1 = ldg_half_pf<PF>(buf, idx[u] * 2 + 1);
+                    const Half h1 = ldg_half(buf, idx[u] * 2 + 1);
                     acc += h1.c0 ^ h1.c1 ^ h1.l0 ^ h1.l1 ^ h1.l2 ^ h1.h0 ^ h1.h1 ^ h1.h2;
                 }
             }
@@ -870,8 +876,7 @@ int sweep_grid(uint32_t max_len, int* blocks) {
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, SWEEP1_MIN_BLOCKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, SWEEP1_MIN_BLOCKS, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, SWEEP1_MIN_BLOCKS, false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, SWEEP1_MIN_BLOCKS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int a0 = 0, a1 = 0;                 // the grid must be resident for either instantiation (with / without the text shortcut)
         GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k_sweep1<false, false>, SWEEP1_THREADS, smem));
@@ -1149,9 +1154,8 @@ int gsm_smem_sweep(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_workspa
     const int kind = sweep_kind(rd->max_len);
     if (kind == SWEEP_LANE) {
         static const int stats = getenv("GSM_SWEEP_STATS") ? atoi(getenv("GSM_SWEEP_STATS")) : 0;
-        static const int pfh = getenv("GSM_SWEEP_PF") ? atoi(getenv("GSM_SWEEP_PF")) : 0;
-        if (uniq && pfh == 64) { k_sweep1<false, true, SWEEP1_MIN_BLOCKS, false, 64><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa); GSM_CUDA(cudaGetLastError()); return GSM_OK; }
-        if (uniq && pfh == 128) { k_sweep1<false, true, SWEEP1_MIN_BLOCKS, false, 128><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa); GSM_CUDA(cudaGetLastError()); return GSM_OK; }
+        static const int unpaired = getenv("GSM_SWEEP_UNPAIRED") ? atoi(getenv("GSM_SWEEP_UNPAIRED")) : 0;      // A/B: every lane loads both halves itself
+        if (uniq && unpaired) { k_sweep1<false, true, SWEEP1_MIN_BLOCKS, false, false><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa); GSM_CUDA(cudaGetLastError()); return GSM_OK; }
         if (uniq && stats) k_sweep1<false, true, SWEEP1_MIN_BLOCKS, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
         else if (uniq && sweep_blocks_env() == 6) k_sweep1<false, true, 6><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
         else if (uniq && sweep_blocks_env() == 8) k_sweep1<false, true, 8><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
@@ -1274,10 +1278,10 @@ int gsm_gather_advance(uint64_t* base_dev, const uint64_t* counts_dev, uint32_t 
 
 int gsm_gather_probe2(const void* buf, uint64_t bytes, uint64_t n_fetch, uint32_t fetch_bytes, uint32_t in_flight, uint64_t* sink, uint64_t* n_done,
                       void* stream) {
-    const uint32_t pf = fetch_bytes == 65 ? 64u : fetch_bytes == 129 ? 128u : 0u;      // 65 / 129: 64-byte fetches with an L2::64B / L2::128B hint
+    const uint32_t pf = fetch_bytes == 66 ? 1u : 0u;      // 66: 64-byte fetches by lane pairs (one request per bucket, half as many buckets per instruction)
     if (pf) fetch_bytes = 64;
     if (!buf || !sink || bytes < 64 || (fetch_bytes != 16 && fetch_bytes != 32 && fetch_bytes != 64) || (in_flight != 1 && in_flight != 4 && in_flight != 8))
-        return fail(GSM_E_INVALID, "gsm_gather_probe2: fetch_bytes in {16, 32, 64, 65, 129}, in_flight in {1, 4, 8}");
+        return fail(GSM_E_INVALID, "gsm_gather_probe2: fetch_bytes in {16, 32, 64, 66}, in_flight in {1, 4, 8}");
     int st = device_ready();
     if (st) return st;
     int dev = 0, sms = 0;
@@ -1295,12 +1299,11 @@ int gsm_gather_probe2(const void* buf, uint64_t bytes, uint64_t n_fetch, uint32_
 #define GSM_PROBE2(B, U) k_gather_probe2<B, U><<<grid, 128, 0, s>>>(b, pow2 - 1, iters, sk)
     if (fetch_bytes == 16) { if (in_flight == 1) GSM_PROBE2(16, 1); else if (in_flight == 4) GSM_PROBE2(16, 4); else GSM_PROBE2(16, 8); }
     else if (fetch_bytes == 32) { if (in_flight == 1) GSM_PROBE2(32, 1); else if (in_flight == 4) GSM_PROBE2(32, 4); else GSM_PROBE2(32, 8); }
-    else if (pf == 64) k_gather_probe2<64, 4, 64><<<grid, 128, 0, s>>>(b, pow2 - 1, iters * in_flight / 4 + 1, sk);
-    else if (pf == 128) k_gather_probe2<64, 4, 128><<<grid, 128, 0, s>>>(b, pow2 - 1, iters * in_flight / 4 + 1, sk);
+    else if (pf == 1) k_gather_probe2<64, 4, 1><<<grid, 128, 0, s>>>(b, pow2 - 1, iters * in_flight / 4 + 1, sk);
     else { if (in_flight == 1) GSM_PROBE2(64, 1); else if (in_flight == 4) GSM_PROBE2(64, 4); else GSM_PROBE2(64, 8); }
 #undef GSM_PROBE2
     GSM_CUDA(cudaGetLastError());
-    if (n_done) *n_done = pf ? threads * 4ull * (iters * in_flight / 4 + 1) : threads * in_flight * iters;
+    if (n_done) *n_done = pf ? threads / 2 * 4ull * (iters * in_flight / 4 + 1) : threads * in_flight * iters;
     return GSM_OK;
 }
 

@@ -57,26 +57,6 @@ __device__ __forceinline__ Half ldg_half(const uint4* halves_base, size_t half_i
     return h;
 }
 
-// The same load with an L2 prefetch-size hint (LDG.E.ENL2.LTC64B / LTC128B): the miss brings the whole aligned 64 / 128 bytes
-// into L2, so the load of the bucket's other half is an L2 hit instead of a second DRAM request.  The memory system
-// sustains about 45 G random requests/s whatever their size up to 64 bytes (tools/gather_ceiling.py), so one request per
-// bucket instead of two is what matters for a kernel that fetches a bucket with two 256-bit loads.
-template <int PF>
-__device__ __forceinline__ Half ldg_half_pf(const uint4* halves_base, size_t half_index) {
-    Half h;
-    if (PF == 64)
-        asm volatile("ld.global.nc.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(h.c0), "=r"(h.c1), "=r"(h.l0), "=r"(h.l1), "=r"(h.l2), "=r"(h.h0), "=r"(h.h1), "=r"(h.h2)
-                     : "l"(halves_base + half_index * 2));
-    else if (PF == 128)
-        asm volatile("ld.global.nc.L2::128B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=r"(h.c0), "=r"(h.c1), "=r"(h.l0), "=r"(h.l1), "=r"(h.l2), "=r"(h.h0), "=r"(h.h1), "=r"(h.h2)
-                     : "l"(halves_base + half_index * 2));
-    else
-        h = ldg_half(halves_base, half_index);
-    return h;
-}
-
 // One FM extension step executed by all pairs of a warp together.  Every lane passes its pair's
 // operands; `active` pairs get their result, inactive ones issue no loads.  g = lane within pair.
 __device__ __forceinline__ StepOut pair_step(const uint4* __restrict__ bk, uint32_t P0, uint32_t P1, uint32_t ch, uint32_t Cc,
@@ -237,16 +217,44 @@ struct LanePartial {
     bool have;
 };
 
-template <int PF>
-__device__ __forceinline__ bool lane_step(const uint4* __restrict__ bk, uint32_t P0, uint32_t P1, uint32_t ch, uint32_t Cc, uint32_t primary,
-                                          bool active, LanePartial& part, StepOut& out) {
+// PAIRED: the two 32-byte halves of a lane's bucket are fetched by the lane and its neighbour with ONE load instruction
+// (lane g == r owns round r and loads half 0 of its bucket, the neighbour loads half 1 of the same bucket; eight shuffles
+// hand that half over), so a bucket is one 64-byte L2 request instead of two 32-byte ones.  The memory system sustains a
+// fixed RATE of random requests (about 58 G/s over a 667 MB index, tools/gather_ceiling.py) whatever their size up to 64
+// bytes, and the kernel runs at that rate: half the requests per bucket is what counts.  PAIRED = false: the lane loads
+// both halves itself (two requests).
+template <bool PAIRED>
+__device__ __forceinline__ bool lane_step(const uint4* __restrict__ fwd, const uint4* __restrict__ rev, bool use_rev, uint32_t P0, uint32_t P1,
+                                          uint32_t ch, uint32_t Cc, uint32_t primary, bool active, LanePartial& part, StepOut& out) {
+    constexpr uint32_t FULLM = 0xFFFFFFFFu;
     uint32_t b0, r0, b1, r1;
     split192(P0, b0, r0);
     split192(P1, b1, r1);
     const bool second = part.have;
     const uint32_t b = second ? b1 : b0;
     Half a0 = Half{0, 0, 0, 0, 0, 0, 0, 0}, a1 = a0;
-    if (active) { a0 = ldg_half_pf<PF>(bk, (size_t)b * 2); a1 = ldg_half_pf<PF>(bk, (size_t)b * 2 + 1); }
+    if (PAIRED) {
+        const uint32_t g = threadIdx.x & 1u;
+        const uint32_t mine = (active ? 1u : 0u) | (use_rev ? 2u : 0u);
+        const uint32_t pb = __shfl_xor_sync(FULLM, b, 1);
+        const uint32_t theirs = __shfl_xor_sync(FULLM, mine, 1);
+#pragma unroll
+        for (uint32_t r = 0; r < 2u; ++r) {
+            const bool own = g == r;
+            const uint32_t bb = own ? b : pb, fl = own ? mine : theirs;
+            Half h = Half{0, 0, 0, 0, 0, 0, 0, 0};
+            if (fl & 1u) h = ldg_half((fl & 2u) ? rev : fwd, (size_t)bb * 2 + (own ? 0u : 1u));
+            Half o;
+            o.c0 = __shfl_xor_sync(FULLM, h.c0, 1); o.c1 = __shfl_xor_sync(FULLM, h.c1, 1);
+            o.l0 = __shfl_xor_sync(FULLM, h.l0, 1); o.l1 = __shfl_xor_sync(FULLM, h.l1, 1); o.l2 = __shfl_xor_sync(FULLM, h.l2, 1);
+            o.h0 = __shfl_xor_sync(FULLM, h.h0, 1); o.h1 = __shfl_xor_sync(FULLM, h.h1, 1); o.h2 = __shfl_xor_sync(FULLM, h.h2, 1);
+            if (own) { a0 = h; a1 = o; }
+        }
+    } else if (active) {
+        const uint4* bk = use_rev ? rev : fwd;
+        a0 = ldg_half(bk, (size_t)b * 2);
+        a1 = ldg_half(bk, (size_t)b * 2 + 1);
+    }
     const SymK k = sym_consts(ch);
     uint32_t E[6], T[6];
     bucket_masks(a0, a1, k, E, T);
@@ -423,8 +431,8 @@ inline size_t sweep1_smem_bytes(uint32_t max_len, bool long_reads) {
 // MB = resident blocks per SM the register allocation aims at (6: 80 registers, 7: 72, 8: 64 with spills); measured per
 // workload by tools/sweep_ab.py (GSM_SWEEP_BLOCKS)
 // STATS: count lane-slots / FM passes / seed fetches / text operations into counters[4..7] (measurement builds only)
-// PF: L2 prefetch-size hint of the bucket loads (0 = none, 64, 128)
-template <bool LONG, bool UNIQ, int MB = SWEEP1_MIN_BLOCKS, bool STATS = false, int PF = 0>
+// PAIRED: buckets fetched as one 64-byte request by lane pairs (lane_step)
+template <bool LONG, bool UNIQ, int MB = SWEEP1_MIN_BLOCKS, bool STATS = false, bool PAIRED = true>
 __global__ void __launch_bounds__(SWEEP1_THREADS, MB) k_sweep1(const SweepArgs a) {
     using Ctx = DevSweepCtx1<LONG, UNIQ>;
     const uint32_t lane_u4 = sweep1_lane_u4(a.max_len, LONG);
@@ -458,8 +466,8 @@ __global__ void __launch_bounds__(SWEEP1_THREADS, MB) k_sweep1(const SweepArgs a
         }
         const bool rev = sw.on_reverse();
         StepOut r;
-        const bool stepped = lane_step<PF>(rev ? a.rev : a.fwd, sw.P0, sw.P0 + sw.cnt, sw.ch, a.meta.C[sw.ch & 3u],
-                                       rev ? a.meta.prim_r : a.meta.prim_f, is_step, part, r);
+        const bool stepped = lane_step<PAIRED>(a.fwd, a.rev, rev, sw.P0, sw.P0 + sw.cnt, sw.ch, a.meta.C[sw.ch & 3u],
+                                               rev ? a.meta.prim_r : a.meta.prim_f, is_step, part, r);
         if (stepped) sw.consume(ctx, a.meta, r);
         else if (is_seed) sw.consume_seed(ctx, a.meta, SeedEntry{se.x, se.y, se.z, se.w});
         else if (UNIQ && is_word) sw.consume_word(ctx, a.meta, wv);

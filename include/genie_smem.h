@@ -360,8 +360,9 @@ int gsm_gather_probe(const void* buf, uint64_t bytes, uint64_t n_fetch, uint32_t
                      uint64_t* sink, uint64_t* n_done, void* stream);
 
 /* The same ceiling with the kernels' real access shapes and enough memory parallelism: every lane keeps `in_flight`
- * (1, 4 or 8) independent fetches of `fetch_bytes` (64 = a whole bucket by one lane, 32 = one 256-bit load, 16 = one seed-table
- * entry) outstanding, indices masked to the largest power of two of units in `bytes`. */
+ * (1, 4 or 8) independent fetches of `fetch_bytes` (64 = a whole bucket by one lane: two requests, 66 = a whole bucket by a lane
+ * pair: one 64-byte request, 32 = one 256-bit load, 16 = one seed-table entry) outstanding, indices masked to the largest
+ * power of two of units in `bytes`. */
 int gsm_gather_probe2(const void* buf, uint64_t bytes, uint64_t n_fetch, uint32_t fetch_bytes, uint32_t in_flight,
                       uint64_t* sink, uint64_t* n_done, void* stream);
 
