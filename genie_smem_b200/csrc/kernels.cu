@@ -876,7 +876,7 @@ int sweep_grid(uint32_t max_len, int* blocks) {
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, SWEEP1_MIN_BLOCKS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, SWEEP1_MIN_BLOCKS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, SWEEP1_MIN_BLOCKS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSM_CUDA(cudaFuncSetAttribute(k_sweep1<false, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int a0 = 0, a1 = 0;                 // the grid must be resident for either instantiation (with / without the text shortcut)
         GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a0, k_sweep1<false, false>, SWEEP1_THREADS, smem));
@@ -1154,8 +1154,8 @@ int gsm_smem_sweep(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_workspa
     const int kind = sweep_kind(rd->max_len);
     if (kind == SWEEP_LANE) {
         static const int stats = getenv("GSM_SWEEP_STATS") ? atoi(getenv("GSM_SWEEP_STATS")) : 0;
-        static const int unpaired = getenv("GSM_SWEEP_UNPAIRED") ? atoi(getenv("GSM_SWEEP_UNPAIRED")) : 0;      // A/B: every lane loads both halves itself
-        if (uniq && unpaired) { k_sweep1<false, true, SWEEP1_MIN_BLOCKS, false, false><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa); GSM_CUDA(cudaGetLastError()); return GSM_OK; }
+        static const int paired = getenv("GSM_SWEEP_PAIRED") ? atoi(getenv("GSM_SWEEP_PAIRED")) : 0;      // A/B: buckets as one 64-byte request per lane pair
+        if (uniq && paired) { k_sweep1<false, true, SWEEP1_MIN_BLOCKS, false, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa); GSM_CUDA(cudaGetLastError()); return GSM_OK; }
         if (uniq && stats) k_sweep1<false, true, SWEEP1_MIN_BLOCKS, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
         else if (uniq && sweep_blocks_env() == 6) k_sweep1<false, true, 6><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
         else if (uniq && sweep_blocks_env() == 8) k_sweep1<false, true, 8><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);

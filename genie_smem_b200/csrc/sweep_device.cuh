@@ -221,8 +221,7 @@ struct LanePartial {
 // (lane g == r owns round r and loads half 0 of its bucket, the neighbour loads half 1 of the same bucket; eight shuffles
 // hand that half over), so a bucket is one 64-byte L2 request instead of two 32-byte ones.  The memory system sustains a
 // fixed RATE of random requests (about 58 G/s over a 667 MB index, tools/gather_ceiling.py) whatever their size up to 64
-// bytes, and the kernel runs at that rate: half the requests per bucket is what counts.  PAIRED = false: the lane loads
-// both halves itself (two requests).
+// bytes.  PAIRED = false (the default: measured faster, profiles/r02_notes.md): the lane loads both halves itself.
 template <bool PAIRED>
 __device__ __forceinline__ bool lane_step(const uint4* __restrict__ fwd, const uint4* __restrict__ rev, bool use_rev, uint32_t P0, uint32_t P1,
                                           uint32_t ch, uint32_t Cc, uint32_t primary, bool active, LanePartial& part, StepOut& out) {
@@ -431,8 +430,9 @@ inline size_t sweep1_smem_bytes(uint32_t max_len, bool long_reads) {
 // MB = resident blocks per SM the register allocation aims at (6: 80 registers, 7: 72, 8: 64 with spills); measured per
 // workload by tools/sweep_ab.py (GSM_SWEEP_BLOCKS)
 // STATS: count lane-slots / FM passes / seed fetches / text operations into counters[4..7] (measurement builds only)
-// PAIRED: buckets fetched as one 64-byte request by lane pairs (lane_step)
-template <bool LONG, bool UNIQ, int MB = SWEEP1_MIN_BLOCKS, bool STATS = false, bool PAIRED = true>
+// PAIRED: buckets fetched as one 64-byte request by lane pairs (lane_step); measured slower than two requests per lane
+// (54.7 vs 44.3 ms per 10 M reads at C4: the shuffles sit between the loads and their use), kept as GSM_SWEEP_PAIRED=1
+template <bool LONG, bool UNIQ, int MB = SWEEP1_MIN_BLOCKS, bool STATS = false, bool PAIRED = false>
 __global__ void __launch_bounds__(SWEEP1_THREADS, MB) k_sweep1(const SweepArgs a) {
     using Ctx = DevSweepCtx1<LONG, UNIQ>;
     const uint32_t lane_u4 = sweep1_lane_u4(a.max_len, LONG);
