@@ -11,8 +11,8 @@ BWA-SMEM).  The index (suffix array, both BWT bucket arrays, seed table, LUT) is
 Multi-GPU (torchrun, one rank per GPU): the index is replicated, the config's reads are sharded by rank -- STRONG scaling, as
 configs[3] states ("50M reads sharded across 1/2/4/8"); `--scaling weak` gives every GPU the config's full read count instead.
 The one collective of the path -- per-rank records to rank 0 -- is INSIDE every timed region at N > 1: each rank's ordered
-write kernel stores its records straight into rank 0's HBM through a peer mapping (NVLink / NVSwitch), the per-rank counts
-travel through an 8-byte NCCL all-gather, and a closing all-gather is the completion fence (sharding.RecordGatherer).
+write kernel stores its records straight into its region of a buffer in rank 0's HBM through a peer mapping (NVLink /
+NVSwitch), and one 8-byte-per-rank NCCL all-gather of the counts is the completion fence (sharding.RecordGatherer).
 
 A "step" is one pass of the hot path over the read batch.
   value   BWA-SMEM reads/s, packed reads already resident in HBM: sweep + select + scan + ordered write (+ the gather at N > 1)
@@ -366,7 +366,7 @@ def main():
 
     gat = None
     if world > 1:                   # the gather destination: one buffer in rank 0's HBM, mapped by every rank
-        gat = sharding.RecordGatherer(capacity=int(caps["recs_per_read"] * n_max * world * 0.75) + 4096, dst=0, device=dev)
+        gat = sharding.RecordGatherer(capacity=(int(caps["recs_per_read"] * n_max * 0.75) + 4096) * world, dst=0, device=dev)
         log(f"[rank {rank}] gather destination mapped ({gat.capacity * 16 / 1e9:.1f} GB on rank 0, NCCL {gat.comm.nccl_version})")
 
     def barrier():
@@ -425,22 +425,18 @@ def main():
     n_mems, n_rec = engine.check_overflow()
     gathered = None
     if gat is not None:
-        g_recs, seg = gat.finish()
+        parts, totals = gat.finish()
         tot = torch.tensor([n_rec], device=dev, dtype=torch.int64)
         dist.all_reduce(tot)
         if rank == 0:
-            assert int(seg.sum()) == int(tot.item()) == g_recs.numel() // 16, "gathered record count != sum of the ranks' counts"
-            ids = g_recs.view(torch.int32).view(-1, 4)[:, 0]
-            a = 0
-            for r in range(world):              # every rank's segment holds that rank's global read ids, in order
-                k = int(seg[0, r])
-                if k:
+            assert int(totals.sum()) == int(tot.item()) == sum(p.numel() for p in parts) // 16, "gathered record count != sum of the ranks' counts"
+            for r in range(world):              # every rank's region holds that rank's global read ids, in order
+                if int(totals[r]):
                     lo_s, hi_s = (sharding.shard_range(args.total_reads, r, world) if args.scaling == "strong"
                                   else (r * args.total_reads, (r + 1) * args.total_reads))
-                    s = ids[a:a + k]
-                    assert int(s[0]) == lo_s and int(s[-1]) == hi_s - 1 and bool((s[1:] >= s[:-1]).all()), f"segment of rank {r} is not its shard"
-                a += k
-            gathered = {"records": int(tot.item()), "bytes": int(tot.item()) * 16, "per_rank": [int(x) for x in seg[0]]}
+                    s = parts[r].view(torch.int32).view(-1, 4)[:, 0]
+                    assert int(s[0]) == lo_s and int(s[-1]) == hi_s - 1 and bool((s[1:] >= s[:-1]).all()), f"region of rank {r} is not its shard"
+            gathered = {"records": int(tot.item()), "bytes": int(tot.item()) * 16, "per_rank": [int(x) for x in totals]}
     snaps["bwa"] = snapshot(n_par)
 
     # ---- per-kernel split of the step + algorithmic bytes (roofline of the dominant kernel, k_sweep)
@@ -452,28 +448,27 @@ def main():
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (ms_sweep * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tname = {1_000_000_000: "r02_1gbp_sweep_dram_bytes.json", 100_000_000: "r01_sweep_dram_bytes.json"}.get(args.ref_bases)
-    if tname and not os.path.exists(os.path.join(ROOT, "profiles", tname)):
-        tname = tname.replace("r02_", "r01c_")
-    if tname and os.path.exists(os.path.join(ROOT, "profiles", tname)):        # ncu --set full capture of k_sweep on this reference size
+    tname = {1_000_000_000: "r02_1gbp_sweep_dram_bytes.json", 100_000_000: "r02_100mbp_sweep_dram_bytes.json"}.get(args.ref_bases)
+    if tname and os.path.exists(os.path.join(ROOT, "profiles", tname)):        # ncu --set full capture of k_sweep1 on this reference size
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
             traffic = tj["dram_bytes_per_read"] * n_reads
-            traffic_src = f"profiles/{tname}: {tj['dram_bytes_per_read']:.0f} DRAM bytes/read (ncu dram__bytes_read+write of k_sweep) x reads per launch"
+            traffic_src = f"profiles/{tname}: {tj['dram_bytes_per_read']:.0f} DRAM bytes/read (ncu dram__bytes_read+write of k_sweep1) x reads per launch"
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_sweep", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_sweep1", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_read": round(alg_bytes / n_reads, 1), "fm_steps_per_read_min": round(steps_alg / n_reads, 2),
                 "records_per_read": round(n_rec / n_reads, 3), "ms_sweep": round(ms_sweep, 3), "ms_select_scan_write": round(ms_sel_bwa, 3),
                 "reads_per_launch": n_reads,
-                "note": "achieved = algorithmic bytes (SURVEY 8d: 128 B per necessary FM step + read + records) of one launch / k_sweep's "
-                        "average launch time (CUDA events on the launching stream); the access pattern is dependent random 64-byte "
-                        "fetches, whose measured ceiling on this GPU is below the streaming peak (profiles/r02_notes.md)"}
+                "note": "achieved = algorithmic bytes (SURVEY 8d: 128 B per necessary FM step + read + records) of one launch / k_sweep1's "
+                        "average launch time (CUDA events on the launching stream).  The kernel replaces the FM steps of unique matches by "
+                        "text comparisons, so it moves fewer bytes than the algorithmic count charges (see `traffic`); the access pattern "
+                        "is dependent random 16..64-byte fetches, bound by the request rate of the memory system (profiles/r02_notes.md)"}
     methods = {"bwa": {"reads_per_s": job_reads / (ms_bwa * 1e-3), "ms_per_step": ms_bwa}}
     roofline_methods = {"bwa": {"achieved": round(alg_bytes / (ms_bwa * 1e-3) / 1e9, 2), "frac": round(alg_bytes / (ms_bwa * 1e-3) / 1e9 / peak, 4),
                                 "algorithmic_bytes_per_read": round(alg_bytes / n_reads, 1), "ms_sweep": round(ms_sweep, 3),
-                                "ms_select": round(ms_sel_bwa, 3), "dominant_kernel": "k_sweep"}}
+                                "ms_select": round(ms_sel_bwa, 3), "dominant_kernel": "k_sweep1"}}
 
     # ---- the other two methods (device-resident; same step definition)
     def method_leg(name, method, steps, kw, K, probe_bytes, extra):
@@ -490,7 +485,7 @@ def main():
         roofline_methods[name] = {"achieved": round(ab / (ms * 1e-3) / 1e9, 2), "frac": round(ab / (ms * 1e-3) / 1e9 / peak, 4),
                                   "algorithmic_bytes_per_read": round(ab / n_reads, 1), "records_with_len_ge_K_per_read": round(nl / n_reads, 3),
                                   "ms_sweep": round(ms_sweep, 3), "ms_select": round(ms_sel, 3),
-                                  "dominant_kernel": "k_sweep" if ms_sweep >= ms_sel else f"k_select_seeded<{name.upper()}>"}
+                                  "dominant_kernel": "k_sweep1" if ms_sweep >= ms_sel else f"k_select_seeded<{name.upper()}>"}
         return ms
 
     method_leg("lut", g.METHOD_LUT, max(2, args.steps // 2), {"K": LUT_K, "lut": lut}, LUT_K, 32, {})
@@ -558,7 +553,7 @@ def main():
         mine = torch.tensor([n_rec], dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(cnts, mine)
         cnts_h = cnts.cpu().numpy().astype(np.uint64)
-        dst_buf = gat.buffer if rank == 0 else None
+        dst_buf = gat.buffer if rank == 0 else None          # (contiguous from the buffer's start: the regions are rewritten by the next step)
         ms_g = timed(lambda: gat.comm.gather_records(engine.records, n_rec, cnts_h, dst_buf, 0), 3, 1)
         tb = int(cnts_h.sum()) * 16
         record_gather = {"transport": "gsm_gather_records: one ncclGroup of exact-size ncclSend/ncclRecv into a preallocated device buffer on rank 0",
@@ -597,11 +592,12 @@ def main():
            "method": "bwa", "input": "2-bit packed reads in pinned host memory (48 B per 151-bp read)",
            "api": f"PipelinedEngine.run ({args.e2e_chunks} chunks, 3 streams: reads H2D | sweep, select, ordered write | records D2H, all overlapped)"}
     if gat is not None:
-        g_recs, seg = gat.finish()
-        e2e["api"] = (f"PipelinedEngine.run(gatherer=RecordGatherer) ({args.e2e_chunks} chunks: reads H2D | sweep, select, 8-byte count all-gather, "
-                      "ordered write into rank 0's HBM over NVLink | offsets + status D2H); records are delivered gathered on rank 0's device")
-        e2e["gathered_records"] = int(seg.sum()) if rank == 0 else None
-        e2e["nvlink_bytes_into_rank0_per_step"] = (int(seg.sum()) - int(seg[:, 0].sum())) * 16 if rank == 0 else None
+        parts, totals = gat.finish()
+        e2e["api"] = (f"PipelinedEngine.run(gatherer=RecordGatherer) ({args.e2e_chunks} chunks: reads H2D | sweep, select, ordered write into this "
+                      "rank's region of rank 0's buffer over NVLink | offsets + status D2H; one 8-byte-per-rank all-gather as the fence); "
+                      "records are delivered gathered on rank 0's device")
+        e2e["gathered_records"] = int(totals.sum())
+        e2e["nvlink_bytes_into_rank0_per_step"] = (int(totals.sum()) - int(totals[0])) * 16
         v_shard, res2 = e2e_time(lambda: run_packed(None))
         e2e["sharded_host_output"] = {"value": v_shard, "d2h_bytes_per_step": pipe.last_d2h_bytes,
                                       "api": "PipelinedEngine.run: every rank copies its own records to its pinned host memory, no gather"}

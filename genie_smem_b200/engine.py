@@ -710,8 +710,8 @@ class Engine:
         capi.check(capi.lib.gsm_smem_select(method, C.byref(self.index.c), C.byref(r), int(min_len), int(K), _ptr(lut),
                                             C.byref(rmi.c) if rmi is not None else None, C.byref(self.ws), _stream()))
         if gatherer is not None:
-            gatherer.collect(self, r)                  # collective: every rank calls it, empty batches included
-            self.kernel_launches += (6 if reads.n else 2)
+            gatherer.collect(self, r)
+            self.kernel_launches += (6 if reads.n else 1)
             return
         capi.check(capi.lib.gsm_smem_collect(C.byref(r), C.byref(self.ws), _ptr(self.records), self.rec_cap, _stream()))
         self.kernel_launches += 5 if reads.n else 0    # select, 3 scan kernels, ordered write
@@ -1107,12 +1107,10 @@ class PipelinedEngine:
         """dynamic_chunks = 0: the batch of n reads is cut by _chunk_bounds; copy_in(lo, hi) / prep(lo, hi) take read ranges.
         dynamic_chunks = k: k chunks whose read counts are only known once they are prepared (FASTQ bytes): copy_in(i) /
         prep(i) take the chunk index, prep's view carries .lo / .hi, and n is the capacity the outputs are sized for."""
-        # with a gatherer every chunk holds a collective: all ranks must cut the same number of chunks, so the bounds are
-        # those of the engine's capacity (equal on all ranks), clipped to this rank's read count
         if dynamic_chunks:
             bounds, n_ch = None, int(dynamic_chunks)
         else:
-            bounds = [min(b, n) for b in self._chunk_bounds(self.max_reads)] if gatherer is not None else self._chunk_bounds(n)
+            bounds = self._chunk_bounds(n)
             n_ch = len(bounds) - 1
         est = self.engines[0].rec_cap * 16
         out_rec = self._buf(self._pin, "rec", max(est, 1 << 20), True)

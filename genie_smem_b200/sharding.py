@@ -171,24 +171,26 @@ def gather_records(records, counts_per_read, dst=0, group=None, device=None, out
 
 class RecordGatherer:
     """The fused gather: every rank's ordered-write kernel stores its records directly into ONE buffer in the HBM of
-    rank `dst` (peer mapping over NVLink / NVSwitch), batch after batch, with no host round trip and no separate copy.
+    rank `dst` (peer mapping over NVLink / NVSwitch), batch after batch, with no host round trip, no separate copy and
+    no collective per batch.
 
     Collective constructor: dst allocates `capacity` records, exports the allocation (CUDA IPC), the group carries the
-    64-byte handle, the other ranks map it.  Per batch (collect): all-gather of the batch's per-rank record counts
-    (8 bytes each, device to device, on the current stream), gsm_smem_collect_gathered into the mapping at
-    running total + sum of lower ranks' counts, running total advanced on the device.  finish(): a last small
-    all-gather is the completion fence; on dst it returns the records and the (batch, rank) segment table."""
+    64-byte handle, the other ranks map it.  The buffer is cut into one REGION per rank (capacity / world records); rank r
+    appends its batches to region r (gsm_smem_collect_gathered at region base + its own running count, kept on the device),
+    so the ranks never wait for one another while they work.  fence(): ONE 8-byte-per-rank all-gather of the running counts
+    -- dst's copy of it completes only after every rank's stream has passed its ordered writes -- and finish() returns, on
+    dst, the per-rank views (rank order = global read order) and the counts; compact() joins them into one array.
+    Without CUDA IPC (self.fused False) every batch falls back to gsm_gather_records (exact-size NCCL send / recv)."""
 
-    def __init__(self, capacity, dst=0, group=None, device=None, max_batches=4096, comm=None):
+    def __init__(self, capacity, dst=0, group=None, device=None, comm=None):
         self.group, self.dst = group, dst
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.comm = comm or native_comm(group)
-        self.capacity = int(capacity)
-        self.max_batches = int(max_batches)
-        self.counts = torch.zeros(self.max_batches * self.world, dtype=torch.int64, device=self.device)
-        self.base = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self.fence_buf = torch.zeros(self.world + 1, dtype=torch.int64, device=self.device)
+        self.region = max(int(capacity) // self.world, 1)
+        self.capacity = self.region * self.world
+        self.base = torch.zeros(1, dtype=torch.int64, device=self.device)          # records this rank has written since reset()
+        self.totals = torch.zeros(self.world, dtype=torch.int64, device=self.device)
         self.n_batches = 0
         self._offset = 0
         handle = np.zeros(64, np.uint8)
@@ -229,42 +231,50 @@ class RecordGatherer:
 
     def collect(self, engine, reads_c):
         """engine: the Engine whose workspace holds the batch just selected; reads_c: its gsm_dev_reads struct."""
-        if self.n_batches >= self.max_batches:
-            raise capi.GsmError(capi.E_CAPACITY, "RecordGatherer: more batches than max_batches")
-        row = self.counts.data_ptr() + 8 * self.world * self.n_batches
-        self.comm.allgather_u64(engine.counters.data_ptr() + 8, row)
+        count = engine.counters.data_ptr() + 8                       # ws->counters[1]: records of this batch (device)
         if self.fused:
-            capi.check(capi.lib.gsm_smem_collect_gathered(C.byref(reads_c), C.byref(engine.ws), C.c_void_p(self.out_ptr), self.capacity,
-                                                          C.c_void_p(row), self.rank, C.c_void_p(self.base.data_ptr()), _stream()))
+            region = self.out_ptr + self.rank * self.region * 16
+            capi.check(capi.lib.gsm_smem_collect_gathered(C.byref(reads_c), C.byref(engine.ws), C.c_void_p(region), self.region,
+                                                          None, 0, C.c_void_p(self.base.data_ptr()), _stream()))
         else:
-            # no peer mapping (CUDA IPC unavailable): ordered write into the rank's own buffer, then exact-size NCCL
-            # send / recv into dst's buffer -- needs the counts on the host, i.e. one stream synchronisation per batch
+            # no peer mapping (CUDA IPC unavailable): ordered write into the rank's own buffer, then exact-size NCCL send /
+            # recv into the rank's region of dst's buffer -- needs the counts on the host: one all-gather + sync per batch
             capi.check(capi.lib.gsm_smem_collect(C.byref(reads_c), C.byref(engine.ws), C.c_void_p(engine.records.data_ptr()), engine.rec_cap, _stream()))
-            cnt = self.counts[self.world * self.n_batches: self.world * (self.n_batches + 1)].cpu().numpy().astype(np.uint64)
-            base = int(self.base.item())
-            if base + int(cnt.sum()) > self.capacity:
-                raise capi.GsmError(capi.E_CAPACITY, "RecordGatherer: the destination buffer is too small")
-            dst_view = self.buffer[base * 16:] if self.rank == self.dst else None
-            self.comm.gather_records(engine.records, int(cnt[self.rank]), cnt, dst_view, self.dst)
-        capi.check(capi.lib.gsm_gather_advance(C.c_void_p(self.base.data_ptr()), C.c_void_p(row), self.world, _stream()))
+            mine = torch.stack([engine.counters[1], self.base[0]])                     # [records of this batch, records written so far]
+            both = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
+            self.comm.allgather_u64(mine.data_ptr(), both.data_ptr(), 2)
+            both = both.cpu().numpy().reshape(self.world, 2)
+            cnt, bases = both[:, 0].astype(np.uint64), both[:, 1]
+            if int((bases + both[:, 0]).max()) > self.region:
+                raise capi.GsmError(capi.E_CAPACITY, "RecordGatherer: a rank's region of the destination buffer is too small")
+            for r in range(self.world):                    # one exact-size transfer per source rank, into that rank's region
+                if self.rank == self.dst or self.rank == r:
+                    one = np.zeros(self.world, np.uint64)
+                    one[r] = cnt[r]
+                    view = self.buffer[(r * self.region + int(bases[r])) * 16:] if self.rank == self.dst else None
+                    self.comm.gather_records(engine.records, int(cnt[r]) if self.rank == r else 0, one, view, self.dst)
+        capi.check(capi.lib.gsm_gather_advance(C.c_void_p(self.base.data_ptr()), C.c_void_p(count), 1, _stream()))
         self.n_batches += 1
 
     def fence(self):
-        """Completion fence on the current stream (all ranks): dst's copy of this small all-gather completes only after
-        every rank's stream has reached it, i.e. after every rank's ordered writes into dst's buffer."""
-        self.comm.allgather_u64(self.base.data_ptr(), self.fence_buf.data_ptr())
+        """Completion fence on the current stream (all ranks): dst's copy of this small all-gather of the running counts
+        completes only after every rank's stream has reached it, i.e. after every rank's ordered writes into dst's buffer."""
+        self.comm.allgather_u64(self.base.data_ptr(), self.totals.data_ptr())
 
     def finish(self):
-        """Fence + synchronise, then on dst: (records uint8 device view, counts[batch, rank] numpy)."""
+        """Fence + synchronise.  On dst: (list of per-rank uint8 views of 16-byte records, in rank order; counts per rank)."""
         self.fence()
         torch.cuda.current_stream().synchronize()
-        total = int(self.base.item())
-        if total > self.capacity:
-            raise capi.GsmError(capi.E_CAPACITY, f"RecordGatherer: {total} records exceed the destination's capacity {self.capacity}")
+        totals = self.totals.cpu().numpy()
+        if int(totals.max()) > self.region:
+            raise capi.GsmError(capi.E_CAPACITY, f"RecordGatherer: {int(totals.max())} records exceed a rank's region of {self.region}")
         if self.rank != self.dst:
-            return None, None
-        seg = self.counts[: self.n_batches * self.world].view(self.n_batches, self.world).cpu().numpy()
-        return self.buffer[: total * 16], seg
+            return None, totals
+        return [self.buffer[r * self.region * 16:(r * self.region + int(totals[r])) * 16] for r in range(self.world)], totals
+
+    def compact(self, parts):
+        """One contiguous array of the gathered records in global read order (a device-to-device copy on dst)."""
+        return torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=self.device)
 
     def close(self):
         if self.rank != self.dst and self.out_ptr:
