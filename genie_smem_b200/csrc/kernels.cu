@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 
 #include "../../include/genie_smem.h"
 #include "host_common.hpp"
@@ -87,6 +88,8 @@ struct TableProbe {
 
 template <int METHOD>
 struct DevSelCtx {
+    // LUT seeds are real table rows (32 bits); the RMI search may return negative or wrapped rows
+    using iv_t = typename std::conditional<METHOD == GSM_METHOD_RMI, int64_t, uint32_t>::type;
     const SelectArgs& a;
     const uint32_t* words;
     uint4* mems;
@@ -154,14 +157,14 @@ struct DevSelCtx {
     }
 
     // per-thread lookups of one round (Selector::run_seeded, LUT): one 8-byte gather per visited window
-    __device__ uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi, uint32_t& wtrue) {
+    __device__ uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, iv_t* lo, iv_t* hi, uint32_t& wtrue) {
         uint32_t hit = 0;
         wtrue = 0;
         for (uint32_t i = 0; i < nwin; ++i) {
             const uint32_t cpos = first ? 0u : e - i;
             if (!(first || (i < plen && cpos + K <= L))) continue;
             const uint2 t = __ldg(a.lut + window_code(cpos));
-            lo[i] = t.x; hi[i] = (int64_t)t.x + t.y - 1;
+            lo[i] = (iv_t)t.x; hi[i] = (iv_t)(t.x + t.y - 1u);
             wtrue |= 1u << i;
             if (t.y != 0) hit |= 1u << i;
         }
@@ -322,7 +325,8 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
     CtxT c{a, nullptr, nullptr, stage, a.stage_stride, 0u, a.K, 0u, a.min_len, 0u, 0u, false, false, false};
     bool direct = false;
     typename Sel::Seeded st;
-    int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
+    using iv_t = typename CtxT::iv_t;
+    iv_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
     uint64_t wcode[MAX_SEED_K];
 
     auto close_read = [&](uint8_t status) {
@@ -375,7 +379,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
 #pragma unroll
                 for (uint32_t j = 0; j < WB; ++j)
                     if ((vis >> (i0 + j)) & 1u) {
-                        wlo[i0 + j] = t[j].x; whi[i0 + j] = (int64_t)t[j].x + t[j].y - 1;
+                        wlo[i0 + j] = (iv_t)t[j].x; whi[i0 + j] = (iv_t)(t[j].x + t[j].y - 1u);
                         if (t[j].y != 0u) whit |= 1u << (i0 + j);
                     }
             }
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
                     if ((vis >> (i0 + j)) & 1u) {
                         int64_t lo, hi;
                         if (rmi_arith_lookup(a.rmi, row0[j], A[j], n[j], a.meta.n_rows, lo, hi)) {
-                            wlo[i0 + j] = lo; whi[i0 + j] = hi;
+                            wlo[i0 + j] = (iv_t)lo; whi[i0 + j] = (iv_t)hi;
                             wtrue |= 1u << (i0 + j);
                             if (hi >= lo) whit |= 1u << (i0 + j);
                         } else {
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
                 const uint32_t cpos = st.first ? 0u : st.e - i;
                 if (have && (st.first || (i < st.plen && cpos + c.K <= c.L))) {
                     wcode[i] = c.window_code(cpos);
-                    wlo[i] = RmiGallop::predicted_row(a.rmi, wcode[i], a.meta.n_rows);
+                    wlo[i] = (iv_t)RmiGallop::predicted_row(a.rmi, wcode[i], a.meta.n_rows);
                     todo |= 1u << i;
                 }
             }
@@ -441,10 +445,10 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
             {
                 RmiGallop ga;                                // phase A: bracket around the prediction
                 phase_loop(todo, ga,
-                           [&](int w) { ga.begin(a.rmi, wcode[w], wlo[w], nr, nb); },
+                           [&](int w) { ga.begin(a.rmi, wcode[w], (int64_t)wlo[w], nr, nb); },
                            [&](int w) {
                                if (ga.hazard) redo |= 1u << w;
-                               else { wlo[w] = ga.lower; whi[w] = ga.upper; lbm |= 1u << w; }
+                               else { wlo[w] = (iv_t)ga.lower; whi[w] = (iv_t)ga.upper; lbm |= 1u << w; }
                            },
                            [&]() { c.probe_row(ga.row(), sv, c64); ga.feed(a.rmi, sv, c64); });
             }
@@ -454,9 +458,9 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
                 phase_loop(lbm, lb,
                            [&](int w) { lb.begin(a.rmi, wcode[w], (uint32_t)wlo[w], (uint32_t)whi[w], nr, nb); },
                            [&](int w) {
-                               wlo[w] = (int64_t)lb.hi;
+                               wlo[w] = (iv_t)lb.hi;
                                if (lb.hi_eq) ubm |= 1u << w;              // hit: whi[w] still holds the bracket's upper end
-                               else whi[w] = (int64_t)lb.hi - 1;          // absent: lo = hi + 1
+                               else whi[w] = (iv_t)((int64_t)lb.hi - 1);  // absent: lo = hi + 1
                            },
                            [&]() { c.probe_row(lb.row(), sv, c64); lb.feed(sv, c64); });
             }
@@ -464,7 +468,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
                 RmiUpper ub;                                 // phase C: last row == q
                 phase_loop(ubm, ub,
                            [&](int w) { ub.begin(a.rmi, wcode[w], (uint32_t)wlo[w], (uint32_t)whi[w], nr, nb); },
-                           [&](int w) { whi[w] = (int64_t)ub.lo; },
+                           [&](int w) { whi[w] = (iv_t)ub.lo; },
                            [&]() { c.probe_row(ub.row(), sv, c64); ub.feed(sv, c64); });
                 whit |= ubm;
             }
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
                 while (more && !rs.pending()) {
                     if (cur >= 0) {
                         if (rs.raised) { c.raised = true; more = false; break; }
-                        wlo[cur] = rs.out_lo; whi[cur] = rs.out_hi;
+                        wlo[cur] = (iv_t)rs.out_lo; whi[cur] = (iv_t)rs.out_hi;
                         if (rs.hit()) whit |= 1u << cur;
                         cur = -1;
                     }
@@ -501,7 +505,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
         }
         __syncwarp();
         // ---------------- pass 2: the frame machine of this round -> its winner
-        typename Sel::Cand w{false, false, 0u, 0u, 0, -1};
+        typename Sel::Cand w{false, false, 0u, 0u, (iv_t)0, (iv_t)0};
         bool run = have && !c.raised;
         if (run) w = Sel::round_decide(c, st, wlo, whi, whit, wtrue);
         __syncwarp();
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
         while (__any_sync(FULL, search)) {
             if (search) {
                 if (sp > w.i && scnt != 0u) c.interval_step(slo, scnt, sp);
-                else { w.lo = (int64_t)slo; w.hi = (int64_t)slo + scnt - 1; w.lazy = false; search = false; }
+                else { w.lo = (iv_t)slo; w.hi = (iv_t)(slo + scnt - 1u); w.lazy = false; search = false; }
             }
         }
         if (have) {

@@ -589,12 +589,16 @@ GSM_HD bool true_sequential(Base base, LoadHalf load, const IndexMeta& meta, uin
 //                                            check_sequential of the two seeds (SMEM.py:196-202)
 //   void interval(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt)   true SA interval of q[i:j]
 //   void emit(uint32_t i, uint32_t j, int64_t lo, int64_t hi)
+//   typename iv_t                             type of SA rows in seeds / candidates (uint32_t, or int64_t if rows may be negative)
 //   bool failed()                             the reference raised inside seed()
 //   bool seeds_are_true()                     seed() returns exact SA intervals (LUT), not RMI guesses
 constexpr int MAX_SEED_K = 32;      // LUT K <= 16, RMI K <= 26 (float64-exact codes)
 
 template <typename Ctx>
 struct Selector {
+    // SA rows of a seed / candidate: Ctx::iv_t is uint32_t where rows are always real (LUT) and int64_t where the RMI search
+    // may return negative or wrapped rows
+    using iv_t = typename Ctx::iv_t;
     GSM_HD static uint32_t s_of(const MemEntry& e) { return e.se & 0xFFFFu; }
     GSM_HD static uint32_t e_of(const MemEntry& e) { return e.se >> 16; }
     // start / end of match k from its packed (start | end << 16) word alone: Ctx::se(k) may come from a compact per-read
@@ -654,14 +658,14 @@ struct Selector {
     struct Cand {
         bool valid, lazy;
         uint32_t i, j;
-        int64_t lo, hi;
+        iv_t lo, hi;
     };
 
     GSM_HD static void upd(Cand& cd, const Cand& x) {
         if (!cd.valid || (x.j - x.i) >= (cd.j - cd.i)) cd = x;
     }
-    GSM_HD static Cand known(uint32_t i, uint32_t j, int64_t lo, int64_t hi) { return Cand{true, false, i, j, lo, hi}; }
-    GSM_HD static Cand lazy_iv(uint32_t i, uint32_t j) { return Cand{true, true, i, j, 0, -1}; }
+    GSM_HD static Cand known(uint32_t i, uint32_t j, iv_t lo, iv_t hi) { return Cand{true, false, i, j, lo, hi}; }
+    GSM_HD static Cand lazy_iv(uint32_t i, uint32_t j) { return Cand{true, true, i, j, (iv_t)0, (iv_t)0}; }
 
     // F(p) restricted to true matches = end of the last match starting at or before p; 0 such matches => p
     // (cannot happen when all four bases occur)
@@ -674,11 +678,11 @@ struct Selector {
 
     // True SA interval of q[i:j): read it off the match list when (i, j) is itself a maximal match
     // (the usual case); false = one backward search from j down to i is needed (Ctx::interval).
-    GSM_HD static bool listed_iv(Ctx& c, uint32_t i, uint32_t j, int64_t& lo, int64_t& hi) {
+    GSM_HD static bool listed_iv(Ctx& c, uint32_t i, uint32_t j, iv_t& lo, iv_t& hi) {
         const uint32_t k = j ? first_end_above(c, j - 1) : 0u;
         if (k < c.n_mems && c.se(k) == (i | (j << 16))) {
             const MemEntry m = c.mem(k);
-            lo = (int64_t)m.lo; hi = (int64_t)m.lo + m.cnt - 1;
+            lo = (iv_t)m.lo; hi = (iv_t)(m.lo + m.cnt - 1u);
             return true;
         }
         return false;
@@ -694,19 +698,19 @@ struct Selector {
         if (!resolve(c, cd)) return;
         uint32_t l, n;
         c.interval(cd.i, cd.j, l, n);
-        cd.lo = (int64_t)l; cd.hi = (int64_t)l + n - 1; cd.lazy = false;
+        cd.lo = (iv_t)l; cd.hi = (iv_t)(l + n - 1u); cd.lazy = false;
     }
 
     // forward_extension(query, pc+K, kmer, seed) (SMEM.py:425-443): longest key and its value.  f = F(pc).
-    GSM_HD static Cand fwd_only(Ctx& c, uint32_t pc, int64_t slo, int64_t shi, uint32_t f) {
+    GSM_HD static Cand fwd_only(Ctx& c, uint32_t pc, iv_t slo, iv_t shi, uint32_t f) {
         if (f <= pc + c.K) return known(pc, pc + c.K, slo, shi);     // the seed key itself
         return lazy_iv(pc, f);
     }
-    GSM_HD static Cand fwd_only(Ctx& c, uint32_t pc, int64_t slo, int64_t shi) { return fwd_only(c, pc, slo, shi, F_of(c, pc)); }
+    GSM_HD static Cand fwd_only(Ctx& c, uint32_t pc, iv_t slo, iv_t shi) { return fwd_only(c, pc, slo, shi, F_of(c, pc)); }
 
     // backward_extension(query, pc, keys) (SMEM.py:389-423) over keys pc+K .. max(F(pc), pc+K)
     // (all_keys) or over the seed key only.  f = F(pc), k0 = first match whose end exceeds pc + K - 1.
-    GSM_HD static Cand bext(Ctx& c, uint32_t pc, int64_t slo, int64_t shi, bool all_keys, uint32_t f, uint32_t k0) {
+    GSM_HD static Cand bext(Ctx& c, uint32_t pc, iv_t slo, iv_t shi, bool all_keys, uint32_t f, uint32_t k0) {
         const uint32_t K = c.K;
         const bool seed_true = f >= pc + K;           // the k-mer really occurs
         uint32_t jmax = all_keys ? (f > pc + K ? f : pc + K) : pc + K;
@@ -734,7 +738,7 @@ struct Selector {
         }
         if (!b_from_mem) return lazy_iv(bi, bj);
         const MemEntry bm = c.mem(bk);
-        return known(bi, bj, (int64_t)bm.lo, (int64_t)bm.lo + bm.cnt - 1);
+        return known(bi, bj, (iv_t)bm.lo, (iv_t)(bm.lo + bm.cnt - 1u));
     }
 
     // get_smems_lut / get_smems_rmi: the frame machine of SMEM.py:49-186 / :235-379, one ROUND at a time.  A round =
@@ -757,7 +761,7 @@ struct Selector {
 
     GSM_HD static void run_seeded(Ctx& c) {
         Seeded st;
-        int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
+        iv_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
         while (round_needed(c, st)) {
             uint32_t wtrue = 0;
             const uint32_t whit = c.seed_round(st.first, st.e, st.plen, st.first ? 1u : c.K, wlo, whi, wtrue);
@@ -766,7 +770,7 @@ struct Selector {
         }
     }
 
-    GSM_HD static void round_finish(Ctx& c, Seeded& st, const int64_t* wlo, const int64_t* whi, uint32_t whit, uint32_t wtrue) {
+    GSM_HD static void round_finish(Ctx& c, Seeded& st, const iv_t* wlo, const iv_t* whi, uint32_t whit, uint32_t wtrue) {
         Cand w = round_decide(c, st, wlo, whi, whit, wtrue);
         if (w.valid) resolve_now(c, w);
         round_commit(c, st, w);
@@ -783,20 +787,20 @@ struct Selector {
 
     // wtrue: bit i set = (wlo[i], whi[i]) is the TRUE interval of window i's k-mer (always for LUT; for RMI when the lookup
     // was proven exact), which lets check_sequential be evaluated in closed form.
-    GSM_HD static Cand round_decide(Ctx& c, const Seeded& st, const int64_t* wlo, const int64_t* whi, uint32_t whit, uint32_t wtrue) {
+    GSM_HD static Cand round_decide(Ctx& c, const Seeded& st, const iv_t* wlo, const iv_t* whi, uint32_t whit, uint32_t wtrue) {
         const uint32_t K = c.K, L = c.L;
         const uint32_t e = st.e, plen = st.plen;
         if (st.first) {                                    // SMEM.py:26-39 / :213-225
             if (whit & 1u) return fwd_only(c, 0, wlo[0], whi[0]);
             const uint32_t end = F_of(c, 0);
-            if (end == 0) return Cand{false, false, 0, 0, 0, -1};
+            if (end == 0) return Cand{false, false, 0, 0, (iv_t)0, (iv_t)0};
             return lazy_iv(0, end);
         }
         // frame: 0 = None, 1 = () , 2 = k-mer frame
         int fstate = 0;
-        uint32_t pc = 0; bool pfw = false, ptrue = false; int64_t plo = 0, phi = -1;
+        uint32_t pc = 0; bool pfw = false, ptrue = false; iv_t plo = 0, phi = 0;
         uint32_t pF = 0, pE = 0;                 // of the frame's window: F(pc) and the first match whose end exceeds pc + K - 1
-        Cand cd{false, false, 0, 0, 0, -1};
+        Cand cd{false, false, 0, 0, (iv_t)0, (iv_t)0};
         const uint32_t pstart = e - plen;
         // The windows of a round move left one base at a time, so the two positions the machine looks up in the match list
         // per window (starts <= cpos, ends > cpos + K - 1) are CURSORS that only step left: two binary searches per round
@@ -810,7 +814,7 @@ struct Selector {
             int act = A_NONE;
             uint32_t ai = 0, aj = 0;                // A_BEXT / A_FWD: frame start in ai; A_KNOWN: the candidate (ai, aj)
             uint32_t aF = 0, aE = 0;                // A_BEXT / A_FWD: the frame's F(pc) and first-end cursor
-            int64_t alo = 0, ahi = -1;
+            iv_t alo = 0, ahi = 0;
             bool aall = false;
             if (i == K) {
                 if (fstate == 2) { act = A_BEXT; ai = pc; alo = plo; ahi = phi; aall = pfw; aF = pF; aE = pE; }
@@ -822,7 +826,7 @@ struct Selector {
                 while (ne > 0u && ek(c, ne - 1u) > cpos + K - 1u) --ne;           // first match ending beyond the window
                 uint32_t Fc = cpos;                                               // F(cpos): end of the longest match starting there
                 if (nf > 0u) { const uint32_t en = ek(c, nf - 1u); Fc = en > cpos ? en : cpos; }
-                const int64_t lo = wlo[i], hi = whi[i];
+                const iv_t lo = wlo[i], hi = whi[i];
                 const bool hit = (whit >> i) & 1u;
                 const bool tru = (wtrue >> i) & 1u;
                 if (hit) {
@@ -861,7 +865,7 @@ struct Selector {
             const uint32_t b = covering_best(c, e, from);
             if (b >= c.n_mems) return cd;
             const MemEntry m = c.mem(b);
-            return known(s_of(m), e_of(m), (int64_t)m.lo, (int64_t)m.lo + m.cnt - 1);
+            return known(s_of(m), e_of(m), (iv_t)m.lo, (iv_t)(m.lo + m.cnt - 1u));
         }
         return cd;
     }

@@ -68,6 +68,7 @@ void sort_mems(std::vector<MemEntry>& m) {
 }
 
 struct SelCtx {
+    using iv_t = int64_t;
     const HostIndex* ix;
     const uint32_t* words;
     uint32_t L, K, n_mems, min_len;
