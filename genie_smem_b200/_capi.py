@@ -36,7 +36,7 @@ class DevReads(C.Structure):
 
 class DevRmi(C.Structure):
     _fields_ = [("K", C.c_uint32), ("n_levels", C.c_uint32), ("level_sizes", u32p), ("coef", C.c_void_p), ("intercept", C.c_void_p), ("probe", C.c_void_p),
-                ("none_rows", u32p), ("n_none_rows", C.c_uint32), ("param_stride", C.c_uint32)]
+                ("none_rows", u32p), ("n_none_rows", C.c_uint32), ("param_stride", C.c_uint32), ("bounds", C.c_void_p)]
 
 
 class Workspace(C.Structure):
@@ -87,6 +87,7 @@ EXPORTS = {
                                   C.POINTER(DevRmi), C.POINTER(Workspace), C.c_void_p]),
     "gsm_smem_collect": (C.c_int, [C.POINTER(DevReads), C.POINTER(Workspace), C.c_void_p, C.c_uint64, C.c_void_p]),
     "gsm_rmi_probe_build": (C.c_int, [C.POINTER(DevIndex), C.c_void_p, C.c_void_p]),
+    "gsm_rmi_bounds_build": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p]),
     "gsm_rmi_none_rows": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_rmi_lookup_batch": (C.c_int, [C.POINTER(DevIndex), C.POINTER(DevRmi), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -63,6 +63,7 @@ struct SelectArgs {
     const uint4* seed_tab;      // optional sweep seed table (gsm_seed_table_build): shortens explicit backward searches
     uint32_t seed_K;
     RmiModel rmi;
+    const uint2* rmi_bounds;    // optional {first row >= k-mer, occurrences} per K-mer code (gsm_rmi_bounds_build), else NULL
     uint4* mem_pool;
     const uint32_t* mem_off;
     const uint32_t* mem_cnt;
@@ -154,21 +155,6 @@ struct DevSelCtx {
             s = (int64_t)__ldg(a.sa + row);
             code64 = kmer_code(txl, (uint64_t)(s - 1), 32);
         }
-    }
-
-    // per-thread lookups of one round (Selector::run_seeded, LUT): one 8-byte gather per visited window
-    __device__ uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, iv_t* lo, iv_t* hi, uint32_t& wtrue) {
-        uint32_t hit = 0;
-        wtrue = 0;
-        for (uint32_t i = 0; i < nwin; ++i) {
-            const uint32_t cpos = first ? 0u : e - i;
-            if (!(first || (i < plen && cpos + K <= L))) continue;
-            const uint2 t = __ldg(a.lut + window_code(cpos));
-            lo[i] = (iv_t)t.x; hi[i] = (iv_t)(t.x + t.y - 1u);
-            wtrue |= 1u << i;
-            if (t.y != 0) hit |= 1u << i;
-        }
-        return hit;
     }
 
     __device__ __forceinline__ uint64_t window_code(uint32_t cpos) const {
@@ -264,14 +250,43 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
         if (!c.soa) order_segments(c.mems, c.n_mems);        // bit 31: the sweep already ordered the list
         bool direct = false;
         do {
-            uint8_t status = GSM_READ_OK;
-            if (METHOD == GSM_METHOD_BWA) Selector<DevSelCtx<METHOD>>::run_bwa(c);
-            else if (c.L < c.K) status = GSM_READ_TOO_SHORT;
-            else Selector<DevSelCtx<METHOD>>::run_seeded(c);
-            if (!c.close(status, direct)) break;
+            static_assert(METHOD == GSM_METHOD_BWA, "LUT- and RMI-SMEM run in k_select_seeded");
+            Selector<DevSelCtx<METHOD>>::run_bwa(c);
+            if (!c.close(GSM_READ_OK, direct)) break;
         } while (true);
     }
 }
+
+// The lookup results of one round (Selector::round_decide's `win`) in shared memory: window i of this thread is word
+// i * SELECT_THREADS of its column in the lo plane, the hi plane K windows further -- a warp's 32 threads touch 32
+// consecutive words, and nothing of it lives in local memory (as per-thread arrays the two planes were 512 bytes of stack
+// per thread: with 151,552 resident threads more than the L2 holds).  RMI rows may be negative (down to -n_rows, Python
+// indexing of a wrong interval; n_rows < 2^32): the low 32 bits are stored and the signs kept in two register masks.
+template <int METHOD>
+struct SmemWindows {
+    using iv_t = typename DevSelCtx<METHOD>::iv_t;
+    uint32_t* lo_w;
+    uint32_t* hi_w;
+    uint32_t neg_lo, neg_hi;
+    __device__ __forceinline__ iv_t lo(uint32_t i) const {
+        const uint32_t v = lo_w[i * SELECT_THREADS];
+        if (METHOD == GSM_METHOD_RMI) return (iv_t)((int64_t)v - ((int64_t)((neg_lo >> i) & 1u) << 32));
+        return (iv_t)v;
+    }
+    __device__ __forceinline__ iv_t hi(uint32_t i) const {
+        const uint32_t v = hi_w[i * SELECT_THREADS];
+        if (METHOD == GSM_METHOD_RMI) return (iv_t)((int64_t)v - ((int64_t)((neg_hi >> i) & 1u) << 32));
+        return (iv_t)v;
+    }
+    __device__ __forceinline__ void put(uint32_t i, iv_t l, iv_t h) {
+        lo_w[i * SELECT_THREADS] = (uint32_t)l;
+        hi_w[i * SELECT_THREADS] = (uint32_t)h;
+        if (METHOD == GSM_METHOD_RMI) {
+            neg_lo = (neg_lo & ~(1u << i)) | ((uint32_t)((int64_t)l < 0) << i);
+            neg_hi = (neg_hi & ~(1u << i)) | ((uint32_t)((int64_t)h < 0) << i);
+        }
+    }
+};
 
 // One phase of the error-bounded search over the windows in `mask` (bit = window), run by the whole warp in lock step:
 // a thread that finishes a window banks it and begins its next one (divergent, a few instructions), then everybody
@@ -294,6 +309,45 @@ __device__ __forceinline__ void phase_loop(uint32_t mask, Machine& mach, Begin b
     }
 }
 
+// The literal exponential + binary search (RmiSearch: probe for probe the reference's) for the windows in `redo` of every
+// thread of the warp, one probe site.  Only hazardous lookups come here (a handful per million), and the search state is
+// large: kept out of line so that its registers are not the selection kernel's.
+// Arguments and results travel by value (nothing of the caller's state has its address taken).
+struct LiteralOut { uint32_t whit, neg_lo, neg_hi, raised; };
+template <int METHOD>
+__device__ __noinline__ LiteralOut literal_lookups(const SelectArgs& a, const uint32_t* words, SmemWindows<METHOD> win, uint32_t redo,
+                                                   uint32_t e, bool first, uint32_t whit) {
+    using iv_t = typename DevSelCtx<METHOD>::iv_t;
+    DevSelCtx<METHOD> c{a, words, nullptr, nullptr, 0u, 0u, a.K, 0u, 0u, 0u, 0u, false, false, false};
+    RmiSearch rs;
+    int cur = -1;
+    bool more = redo != 0;
+    for (;;) {
+        while (more && !rs.pending()) {
+            if (cur >= 0) {
+                if (rs.raised) { c.raised = true; more = false; break; }
+                win.put((uint32_t)cur, (iv_t)rs.out_lo, (iv_t)rs.out_hi);
+                if (rs.hit()) whit |= 1u << cur;
+                cur = -1;
+            }
+            if (redo == 0) { more = false; break; }
+            cur = __ffs(redo) - 1;               // windows in ascending order, like the reference
+            redo &= redo - 1;
+            const uint32_t cpos = first ? 0u : e - (uint32_t)cur;
+            rs.begin(a.rmi, c.window_code(cpos), (int64_t)a.meta.n_rows, (int64_t)a.n_bases);
+        }
+        const bool need = more && rs.pending();
+        if (!__any_sync(FULL, need)) break;
+        if (need) {
+            int64_t sv;
+            uint64_t code64;
+            c.probe_row(rs.row(), sv, code64);   // the probe site of the literal search
+            rs.feed(sv, code64);
+        }
+    }
+    return LiteralOut{whit, win.neg_lo, win.neg_hi, c.raised ? 1u : 0u};
+}
+
 // LUT- and RMI-SMEM selection with the warp kept in lock step.  One thread per read (persistent threads pull reads
 // grid-stride: a thread always has a round to run, whatever the record counts of its neighbours' reads), and the round
 // structure of the frame machine (select_logic.cuh) is driven warp-wide:
@@ -310,11 +364,12 @@ __device__ __forceinline__ void phase_loop(uint32_t mask, Machine& mach, Begin b
 // Measured alternatives (profiles/r01_notes.md): the reference's control flow per thread end to end (2.2 active threads
 // per instruction on the probes), and teams of 16 lanes per read with one window per lane (converged, but 16x fewer reads
 // in flight: latency-bound on the machine's dependent loads, 1.7x slower than this kernel).
-// ARITH (RMI only): the launch has a usable seed table (seed_K <= K) and the None rows, so every lookup is the probe-free
-// rmi_arith_lookup and the probe-based phases are compiled out (fewer registers for the path that always runs).
+// ARITH (RMI only): 1 = the launch has a usable seed table (seed_K <= K) and the None rows, so every lookup is the probe-free
+// rmi_arith_lookup and the probe-based phases are compiled out (fewer registers for the path that always runs);
+// 2 = as 1, the k-mer's true bounds read from the dense table of gsm_rmi_bounds_build (one fetch, no backward steps).
 // MB: resident blocks per SM the register allocation aims at (8: 64 registers with spills, 6: 80); GSM_SELECT_BLOCKS=6 for A/B
-template <int METHOD, bool ARITH = false, int MB = 8>
-__global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const SelectArgs a) {
+template <int METHOD, int ARITH = 0, int MB = 8>
+__global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __grid_constant__ SelectArgs a) {
     using CtxT = DevSelCtx<METHOD>;
     using Sel = Selector<CtxT>;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -326,8 +381,8 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
     bool direct = false;
     typename Sel::Seeded st;
     using iv_t = typename CtxT::iv_t;
-    iv_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
-    uint64_t wcode[MAX_SEED_K];
+    extern __shared__ uint32_t sel_windows[];              // 2 planes x K windows x SELECT_THREADS words
+    SmemWindows<METHOD> win{sel_windows + threadIdx.x, sel_windows + a.K * SELECT_THREADS + threadIdx.x, 0u, 0u};
 
     auto close_read = [&](uint8_t status) {
         if (c.close(status, direct)) { st = typename Sel::Seeded(); return; }      // overflowed its staging slots: run it again in place
@@ -349,7 +404,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
             have = true;
         }
     };
-    constexpr bool arith = METHOD == GSM_METHOD_RMI && ARITH;
+    constexpr bool arith = METHOD == GSM_METHOD_RMI && ARITH != 0;
 
     for (;;) {
         while (true) {                                   // finished reads are closed, the next ones opened
@@ -379,7 +434,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
 #pragma unroll
                 for (uint32_t j = 0; j < WB; ++j)
                     if ((vis >> (i0 + j)) & 1u) {
-                        wlo[i0 + j] = (iv_t)t[j].x; whi[i0 + j] = (iv_t)(t[j].x + t[j].y - 1u);
+                        win.put(i0 + j, (iv_t)t[j].x, (iv_t)(t[j].x + t[j].y - 1u));
                         if (t[j].y != 0u) whit |= 1u << (i0 + j);
                     }
             }
@@ -387,49 +442,42 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
         } else if (arith) {
             const uint4* fwd = a.fwd;
             auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
-            for (uint32_t i0 = 0; i0 < nwin; i0 += WB) {
-                uint32_t A[WB], n[WB];
-                int64_t row0[WB];
-#pragma unroll
-                for (uint32_t j = 0; j < WB; ++j)          // stage 1: the seed-table entries of the windows' last seed_K bases
-                    if ((vis >> (i0 + j)) & 1u) {
-                        const uint32_t cpos = st.first ? 0u : st.e - (i0 + j);
-                        const uint32_t* w = c.words;
-                        auto rd = [w](uint64_t x) { return __ldg(w + x); };
-                        const uint4 e = __ldg(a.seed_tab + kmer_code(rd, (uint64_t)cpos + c.K - a.seed_K, a.seed_K));
-                        A[j] = e.x; n[j] = e.y;
-                    }
-#pragma unroll
-                for (uint32_t j = 0; j < WB; ++j)          // ... while they travel: the model predictions (parameters are L2-resident)
-                    if ((vis >> (i0 + j)) & 1u)
-                        row0[j] = RmiGallop::predicted_row(a.rmi, c.window_code(st.first ? 0u : st.e - (i0 + j)), a.meta.n_rows);
-                for (uint32_t p = c.K - a.seed_K; p > 0; --p) {        // stage 2: K - seed_K backward steps, the windows' buckets in flight together
-#pragma unroll
-                    for (uint32_t j = 0; j < WB; ++j)
-                        if ((vis >> (i0 + j)) & 1u) {
-                            const uint32_t cpos = st.first ? 0u : st.e - (i0 + j);
-                            const uint32_t ch = c.base(cpos + p - 1);
-                            const StepOut r = step_single(load, A[j], A[j] + n[j], ch, a.meta.C[ch], a.meta.prim_f);
-                            A[j] = r.lo_new; n[j] = r.cnt_new;
-                        }
+            const uint64_t seed_mask = (1ull << (2u * a.seed_K)) - 1ull;
+            for (uint32_t i = 0; i < nwin; ++i) {
+                if (!((vis >> i) & 1u)) continue;
+                const uint64_t code = c.window_code(st.first ? 0u : st.e - i);
+                uint32_t A, n;
+                if (ARITH == 2) {                           // the k-mer's true bounds straight from the dense table
+                    const uint2 e = __ldg(a.rmi_bounds + code);
+                    A = e.x; n = e.y;
+                } else {                                    // seed-table entry of the window's last seed_K bases ...
+                    const uint4 e = __ldg(a.seed_tab + (code & seed_mask));
+                    A = e.x; n = e.y;
                 }
-#pragma unroll
-                for (uint32_t j = 0; j < WB; ++j)          // stage 3: the error-bounded search replayed on row numbers
-                    if ((vis >> (i0 + j)) & 1u) {
-                        int64_t lo, hi;
-                        if (rmi_arith_lookup(a.rmi, row0[j], A[j], n[j], a.meta.n_rows, lo, hi)) {
-                            wlo[i0 + j] = (iv_t)lo; whi[i0 + j] = (iv_t)hi;
-                            wtrue |= 1u << (i0 + j);
-                            if (hi >= lo) whit |= 1u << (i0 + j);
-                        } else {
-                            redo |= 1u << (i0 + j);
-                        }
+                // ... while it travels: the model prediction (parameters are L2-resident)
+                const int64_t row0 = RmiGallop::predicted_row(a.rmi, code, a.meta.n_rows);
+                if (ARITH != 2) {
+                    for (uint32_t p = c.K - a.seed_K; p > 0; --p) {        // ... then K - seed_K backward steps
+                        const uint32_t ch = (uint32_t)(code >> (2u * (c.K - p))) & 3u;
+                        const StepOut r = step_single(load, A, A + n, ch, a.meta.C[ch], a.meta.prim_f);
+                        A = r.lo_new; n = r.cnt_new;
                     }
+                }
+                int64_t lo, hi;                             // the error-bounded search replayed on row numbers
+                if (rmi_arith_lookup(a.rmi, row0, A, n, a.meta.n_rows, lo, hi)) {
+                    win.put(i, (iv_t)lo, (iv_t)hi);
+                    wtrue |= 1u << i;
+                    if (hi >= lo) whit |= 1u << i;
+                } else {
+                    redo |= 1u << i;
+                }
             }
-        } else if (!ARITH && a.rmi.n_none != 0) {
+        } else if (ARITH == 0 && a.rmi.n_none != 0) {
             // probe-based error-bounded search (select_logic.cuh, RmiGallop / RmiLower / RmiUpper): each phase runs over ALL
             // windows of the round as one lock-step loop with straight-line per-probe code
             uint32_t todo = 0, lbm = 0, ubm = 0;
+            uint64_t wcode[MAX_SEED_K];
+            int64_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
             for (uint32_t i = 0; i < nwin; ++i) {           // codes and model predictions, one converged counted loop
                 const uint32_t cpos = st.first ? 0u : st.e - i;
                 if (have && (st.first || (i < st.plen && cpos + c.K <= c.L))) {
@@ -472,56 +520,36 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const Sele
                            [&]() { c.probe_row(ub.row(), sv, c64); ub.feed(sv, c64); });
                 whit |= ubm;
             }
+            for (uint32_t m = lbm; m != 0u; m &= m - 1u) { const uint32_t w = __ffs(m) - 1; win.put(w, (iv_t)wlo[w], (iv_t)whi[w]); }
         } else {
             redo = vis;
         }
         if (METHOD == GSM_METHOD_RMI && __any_sync(FULL, redo != 0)) {
-            RmiSearch rs;
-            int cur = -1;
-            bool more = redo != 0;
-            for (;;) {
-                while (more && !rs.pending()) {
-                    if (cur >= 0) {
-                        if (rs.raised) { c.raised = true; more = false; break; }
-                        wlo[cur] = (iv_t)rs.out_lo; whi[cur] = (iv_t)rs.out_hi;
-                        if (rs.hit()) whit |= 1u << cur;
-                        cur = -1;
-                    }
-                    if (redo == 0) { more = false; break; }
-                    cur = __ffs(redo) - 1;               // windows in ascending order, like the reference
-                    redo &= redo - 1;
-                    const uint32_t cpos = st.first ? 0u : st.e - (uint32_t)cur;
-                    rs.begin(a.rmi, c.window_code(cpos), (int64_t)a.meta.n_rows, (int64_t)a.n_bases);
-                }
-                const bool need = more && rs.pending();
-                if (!__any_sync(FULL, need)) break;
-                if (need) {
-                    int64_t sv;
-                    uint64_t code64;
-                    c.probe_row(rs.row(), sv, code64);   // the probe site of the literal search
-                    rs.feed(sv, code64);
-                }
-            }
+            const LiteralOut r = literal_lookups<METHOD>(a, c.words, win, redo, st.first ? 0u : st.e, st.first, whit);
+            whit = r.whit; win.neg_lo = r.neg_lo; win.neg_hi = r.neg_hi;
+            if (r.raised) c.raised = true;
         }
         __syncwarp();
         // ---------------- pass 2: the frame machine of this round -> its winner
-        typename Sel::Cand w{false, false, 0u, 0u, (iv_t)0, (iv_t)0};
+        typename Sel::Cand w{};
         bool run = have && !c.raised;
-        if (run) w = Sel::round_decide(c, st, wlo, whi, whit, wtrue);
+        if (run) w = Sel::round_decide(c, st, win, whit, wtrue);
         __syncwarp();
-        // ---------------- pass 3: explicit backward search for winners that are not on the match list (rare), lock step
+        // ---------------- pass 3: the winner's interval -- from its window, the match list, or (rare) an explicit backward
+        // search, one lock-step loop
+        iv_t rlo = 0, rhi = 0;
         uint32_t slo = 0, scnt = 0, sp = 0;
-        bool search = run && w.valid && Sel::resolve(c, w);
-        if (search) c.interval_begin(w.i, w.j, slo, scnt, sp);
+        bool search = run && w.valid() && Sel::resolve(c, w, win, rlo, rhi);
+        if (search) c.interval_begin(w.i(), w.j(), slo, scnt, sp);
         while (__any_sync(FULL, search)) {
             if (search) {
-                if (sp > w.i && scnt != 0u) c.interval_step(slo, scnt, sp);
-                else { w.lo = (iv_t)slo; w.hi = (iv_t)(slo + scnt - 1u); w.lazy = false; search = false; }
+                if (sp > w.i() && scnt != 0u) c.interval_step(slo, scnt, sp);
+                else { rlo = (iv_t)slo; rhi = (iv_t)(slo + scnt - 1u); search = false; }
             }
         }
         if (have) {
             if (c.raised) close_read(GSM_READ_REF_RAISES);
-            else Sel::round_commit(c, st, w);
+            else Sel::round_commit(c, st, w, rlo, rhi);
         }
         __syncwarp();
     }
@@ -712,7 +740,6 @@ __global__ void k_lut_build(const uint4* fwd, IndexMeta meta, uint32_t K, uint64
     table[code] = make_uint2(lo, cnt);
 }
 
-// RMI_LUT.get_suffix_rmi (reference SMEM/RMI_LUT.py:67-78) for a batch of codes
 // Seed table of the sweep kernel: per K-mer code the rows of the k-mer on the text index, its count, and the rows
 // of the reversed k-mer on the reversed-text index -- the state (k, P0, cnt) a forward extension has after K steps.
 __global__ void k_seed_build(const uint4* fwd, const uint4* rev, IndexMeta meta, uint32_t K, uint64_t n_codes, uint4* table) {
@@ -734,6 +761,28 @@ __global__ void k_seed_build(const uint4* fwd, const uint4* rev, IndexMeta meta,
     table[code] = make_uint4(lo, cnt, cnt ? rlo : 0u, 0u);
 }
 
+// bounds[code] = {first row >= the K-mer, its occurrences}: what kmer_bounds_seeded computes per window, for every code.
+// With a seed table (seed_K <= K) a thread starts from the entry of its code's last seed_K bases (consecutive codes:
+// consecutive entries) and takes the remaining K - seed_K backward steps, through empty intervals too.
+__global__ void k_bounds_build(const uint4* fwd, IndexMeta meta, uint32_t K, uint64_t n_codes, const uint4* seed_tab, uint32_t seed_K,
+                               uint2* table) {
+    const uint64_t code = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (code >= n_codes) return;
+    auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
+    uint32_t lo = 0, cnt = meta.n_rows, t = 0;
+    if (seed_tab) {
+        const uint4 e = __ldg(seed_tab + (code & ((1ull << (2u * seed_K)) - 1ull)));
+        lo = e.x; cnt = e.y; t = seed_K;
+    }
+    for (; t < K; ++t) {
+        const uint32_t c = (uint32_t)(code >> (2 * t)) & 3u;                  // last base first
+        const StepOut r = step_single(load, lo, lo + cnt, c, meta.C[c], meta.prim_f);
+        lo = r.lo_new; cnt = r.cnt_new;
+    }
+    table[code] = make_uint2(lo, cnt);
+}
+
+// RMI_LUT.get_suffix_rmi (reference SMEM/RMI_LUT.py:67-78) for a batch of codes
 __global__ void k_rmi_lookup(const uint32_t* sa, const uint32_t* text, uint64_t n_rows, uint64_t n_bases, RmiModel m, uint64_t n,
                              const uint64_t* codes, double* pred, int64_t* lo, int64_t* hi, uint8_t* status) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -924,13 +973,22 @@ int select_grid(int* blocks) {          // upper bound over the selection kernel
 
 // resident grid of one selection kernel: a persistent grid-stride kernel must not spill into a second wave
 template <typename Kern>
-int resident_grid(Kern kern, int threads, int cap, int* blocks) {
+int resident_grid(Kern kern, int threads, size_t smem, int cap, int* blocks) {
     int dev = 0, sms = 0, per_sm = 0;
     GSM_CUDA(cudaGetDevice(&dev));
     GSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0));
+    GSM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) per_sm = 1;
     *blocks = sms * per_sm < cap ? sms * per_sm : cap;
+    return GSM_OK;
+}
+
+template <int METHOD, int ARITH, int MB>
+int launch_seeded(const SelectArgs& se, size_t win_bytes, int cap, cudaStream_t stream) {
+    int grid = cap;
+    const int st = resident_grid(k_select_seeded<METHOD, ARITH, MB>, SELECT_THREADS, win_bytes, cap, &grid);
+    if (st) return st;
+    k_select_seeded<METHOD, ARITH, MB><<<grid, SELECT_THREADS, win_bytes, stream>>>(se);
     return GSM_OK;
 }
 
@@ -1096,6 +1154,19 @@ int gsm_rmi_none_rows(const gsm_dev_index* ix, uint32_t K, uint32_t* rows_host, 
     return GSM_OK;
 }
 
+int gsm_rmi_bounds_build(const gsm_dev_index* ix, uint32_t K, void* bounds, void* stream) {
+    if (!ix || !ix->fwd_buckets || !bounds || K < 1 || K > 16) return fail(GSM_E_INVALID, "gsm_rmi_bounds_build: needs the rank buckets and K in 1..16");
+    int st = device_ready();
+    if (st) return st;
+    const uint64_t n_codes = 1ull << (2 * K);
+    const bool seeded = ix->seed_table && ix->seed_K >= 1 && ix->seed_K <= K;
+    k_bounds_build<<<(unsigned)((n_codes + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)ix->fwd_buckets, make_meta(ix), K, n_codes,
+                                                                                       seeded ? (const uint4*)ix->seed_table : nullptr,
+                                                                                       seeded ? ix->seed_K : 0u, (uint2*)bounds);
+    GSM_CUDA(cudaGetLastError());
+    return GSM_OK;
+}
+
 int gsm_rmi_probe_build(const gsm_dev_index* ix, void* probe, void* stream) {
     if (!ix || !ix->sa || !ix->text2bit || !probe) return fail(GSM_E_INVALID, "gsm_rmi_probe_build needs sa + text on the device");
     int st = device_ready();
@@ -1198,6 +1269,7 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
     se.fwd = (const uint4*)ix->fwd_buckets; se.meta = make_meta(ix); se.n_bases = ix->n_rows - 1; se.sa = ix->sa; se.text = ix->text2bit; se.probe = (method == GSM_METHOD_RMI && rmi) ? (const uint4*)rmi->probe : nullptr;
     se.reads = (const uint32_t*)rd->packed; se.chunk_off = rd->chunk_off; se.len = rd->len; se.n_reads = (uint32_t)rd->n_reads;
     se.max_len = rd->max_len; se.read_id_base = rd->read_id_base; se.min_len = min_len; se.K = K; se.lut = (const uint2*)lut; se.rmi = rm;
+    se.rmi_bounds = (method == GSM_METHOD_RMI && rmi && rm.n_none != 0u && K <= 16) ? (const uint2*)rmi->bounds : nullptr;
     se.seed_tab = (const uint4*)ix->seed_table; se.seed_K = ix->seed_table ? ix->seed_K : 0u;
     se.mem_pool = (uint4*)ws->mem_pool; se.mem_off = ws->mem_off; se.mem_cnt = ws->mem_cnt; se.stage = (uint4*)ws->quad_scratch; se.stage_stride = select_stage_stride(rd->max_len);
     se.rec_tmp = (uint4*)ws->rec_tmp; se.rec_cap = ws->rec_cap; se.rec_tmp_off = ws->rec_tmp_off; se.rec_cnt = ws->rec_cnt;
@@ -1205,27 +1277,28 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
     GSM_CUDA(cudaMemsetAsync((unsigned long long*)ws->counters + 1, 0, sizeof(uint64_t), stream));
     int grid = lb;
     if (method == GSM_METHOD_BWA) {
-        if ((st = resident_grid(k_select<GSM_METHOD_BWA>, SELECT_THREADS, lb, &grid))) return st;
+        if ((st = resident_grid(k_select<GSM_METHOD_BWA>, SELECT_THREADS, 0, lb, &grid))) return st;
         k_select<GSM_METHOD_BWA><<<grid, SELECT_THREADS, 0, stream>>>(se);
     } else {
-        static const int sel_blocks = getenv("GSM_SELECT_BLOCKS") ? atoi(getenv("GSM_SELECT_BLOCKS")) : 8;
+        static const int sel_blocks = getenv("GSM_SELECT_BLOCKS") ? atoi(getenv("GSM_SELECT_BLOCKS")) : 8;   // A/B: 6, 7
         const bool arith = rm.n_none != 0u && se.seed_K != 0u && se.seed_K <= K;       // lookups from the seed table: no probes
-        if (method == GSM_METHOD_LUT && sel_blocks == 6) {
-            if ((st = resident_grid(k_select_seeded<GSM_METHOD_LUT, false, 6>, SELECT_THREADS, lb, &grid))) return st;
-            k_select_seeded<GSM_METHOD_LUT, false, 6><<<grid, SELECT_THREADS, 0, stream>>>(se);
-        } else if (method == GSM_METHOD_LUT) {
-            if ((st = resident_grid(k_select_seeded<GSM_METHOD_LUT>, SELECT_THREADS, lb, &grid))) return st;
-            k_select_seeded<GSM_METHOD_LUT><<<grid, SELECT_THREADS, 0, stream>>>(se);
-        } else if (arith && sel_blocks == 6) {
-            if ((st = resident_grid(k_select_seeded<GSM_METHOD_RMI, true, 6>, SELECT_THREADS, lb, &grid))) return st;
-            k_select_seeded<GSM_METHOD_RMI, true, 6><<<grid, SELECT_THREADS, 0, stream>>>(se);
+        const size_t win_bytes = 2ull * K * SELECT_THREADS * sizeof(uint32_t);         // SmemWindows: at most 32 KB (K <= 32)
+        if (method == GSM_METHOD_LUT) {
+            if (sel_blocks == 6) st = launch_seeded<GSM_METHOD_LUT, 0, 6>(se, win_bytes, lb, stream);
+            else if (sel_blocks == 7) st = launch_seeded<GSM_METHOD_LUT, 0, 7>(se, win_bytes, lb, stream);
+            else st = launch_seeded<GSM_METHOD_LUT, 0, 8>(se, win_bytes, lb, stream);
+        } else if (se.rmi_bounds) {
+            if (sel_blocks == 6) st = launch_seeded<GSM_METHOD_RMI, 2, 6>(se, win_bytes, lb, stream);
+            else if (sel_blocks == 7) st = launch_seeded<GSM_METHOD_RMI, 2, 7>(se, win_bytes, lb, stream);
+            else st = launch_seeded<GSM_METHOD_RMI, 2, 8>(se, win_bytes, lb, stream);
         } else if (arith) {
-            if ((st = resident_grid(k_select_seeded<GSM_METHOD_RMI, true>, SELECT_THREADS, lb, &grid))) return st;
-            k_select_seeded<GSM_METHOD_RMI, true><<<grid, SELECT_THREADS, 0, stream>>>(se);
+            if (sel_blocks == 6) st = launch_seeded<GSM_METHOD_RMI, 1, 6>(se, win_bytes, lb, stream);
+            else if (sel_blocks == 7) st = launch_seeded<GSM_METHOD_RMI, 1, 7>(se, win_bytes, lb, stream);
+            else st = launch_seeded<GSM_METHOD_RMI, 1, 8>(se, win_bytes, lb, stream);
         } else {
-            if ((st = resident_grid(k_select_seeded<GSM_METHOD_RMI, false>, SELECT_THREADS, lb, &grid))) return st;
-            k_select_seeded<GSM_METHOD_RMI, false><<<grid, SELECT_THREADS, 0, stream>>>(se);
+            st = launch_seeded<GSM_METHOD_RMI, 0, 8>(se, win_bytes, lb, stream);
         }
+        if (st) return st;
     }
     GSM_CUDA(cudaGetLastError());
     const uint64_t n_tiles = (rd->n_reads + SCAN_TILE - 1) / SCAN_TILE;

@@ -580,16 +580,17 @@ GSM_HD bool true_sequential(Base base, LoadHalf load, const IndexMeta& meta, uin
 //   MemEntry mem(uint32_t k)                 k-th maximal match, sorted by end (and start)
 //   uint32_t se(uint32_t k)                  its start | end << 16 word alone
 //   uint32_t base(uint32_t pos)
-//   uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi, uint32_t& wtrue)
-//                                            LUT / RMI lookups of the windows of one round: window i covers
-//                                            q[c:c+K), c = first ? 0 : e - i, and is visited iff first or
-//                                            (i < plen and c + K <= L); bit i of the result = hit; bit i of wtrue =
-//                                            the stored pair is the k-mer's TRUE interval (LUT: always)
+//   uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, W& win, uint32_t& wtrue)
+//                                            (only for Selector::run_seeded) LUT / RMI lookups of the windows of one
+//                                            round: window i covers q[c:c+K), c = first ? 0 : e - i, and is visited iff
+//                                            first or (i < plen and c + K <= L); win.put(i, lo, hi) stores its result;
+//                                            bit i of the return value = hit; bit i of wtrue = the stored pair is the
+//                                            k-mer's TRUE interval (LUT: always)
 //   bool sequential(uint32_t c, int64_t clo, int64_t chi, uint32_t pc, int64_t plo, int64_t phi, bool both_true)
 //                                            check_sequential of the two seeds (SMEM.py:196-202)
 //   void interval(uint32_t i, uint32_t j, uint32_t& lo, uint32_t& cnt)   true SA interval of q[i:j]
 //   void emit(uint32_t i, uint32_t j, int64_t lo, int64_t hi)
-//   typename iv_t                             type of SA rows in seeds / candidates (uint32_t, or int64_t if rows may be negative)
+//   typename iv_t                             type of SA rows in seed tuples (uint32_t, or int64_t if rows may be negative)
 //   bool failed()                             the reference raised inside seed()
 //   bool seeds_are_true()                     seed() returns exact SA intervals (LUT), not RMI guesses
 constexpr int MAX_SEED_K = 32;      // LUT K <= 16, RMI K <= 26 (float64-exact codes)
@@ -652,20 +653,25 @@ struct Selector {
         }
     }
 
-    // A candidate record of the frame machine.  Only LENGTHS decide which candidate survives (SMEM.py replaces on >=), so
-    // the SA interval of a candidate that is neither a seed tuple nor an entry of the match list is left unresolved
-    // (lazy) and computed once, for the round's winner only (resolve): at most one explicit backward search per record.
+    // A candidate record of the frame machine: the match q[i:j) and WHERE its SA interval can be read.  Only LENGTHS decide
+    // which candidate survives (SMEM.py replaces on >=), so a candidate is two words -- (i | j << 16) and the source of its
+    // interval: a window of the round (the seed tuple itself), an entry of the match list, or "lazy" = neither, computed once
+    // for the round's winner only (resolve): at most one explicit backward search per record.
     struct Cand {
-        bool valid, lazy;
-        uint32_t i, j;
-        iv_t lo, hi;
+        uint32_t ij = 0, src = 0;                       // ij == 0: no candidate (a candidate has j > 0)
+        GSM_HD bool valid() const { return ij != 0u; }
+        GSM_HD uint32_t i() const { return ij & 0xFFFFu; }
+        GSM_HD uint32_t j() const { return ij >> 16; }
+        GSM_HD uint32_t len() const { return j() - i(); }
     };
+    static constexpr uint32_t SRC_LAZY = 0xFFFFFFFFu, SRC_WIN = 0x80000000u;     // else: index into the match list
 
     GSM_HD static void upd(Cand& cd, const Cand& x) {
-        if (!cd.valid || (x.j - x.i) >= (cd.j - cd.i)) cd = x;
+        if (!cd.valid() || x.len() >= cd.len()) cd = x;
     }
-    GSM_HD static Cand known(uint32_t i, uint32_t j, iv_t lo, iv_t hi) { return Cand{true, false, i, j, lo, hi}; }
-    GSM_HD static Cand lazy_iv(uint32_t i, uint32_t j) { return Cand{true, true, i, j, (iv_t)0, (iv_t)0}; }
+    GSM_HD static Cand seed_key(uint32_t i, uint32_t K, uint32_t w) { return Cand{i | ((i + K) << 16), SRC_WIN | w}; }
+    GSM_HD static Cand listed(uint32_t i, uint32_t j, uint32_t k) { return Cand{i | (j << 16), k}; }
+    GSM_HD static Cand lazy_iv(uint32_t i, uint32_t j) { return Cand{i | (j << 16), SRC_LAZY}; }
 
     // F(p) restricted to true matches = end of the last match starting at or before p; 0 such matches => p
     // (cannot happen when all four bases occur)
@@ -688,29 +694,27 @@ struct Selector {
         return false;
     }
 
-    // winner of a round -> its interval.  Returns true if cd still needs Ctx::interval(cd.i, cd.j) (explicit search).
-    GSM_HD static bool resolve(Ctx& c, Cand& cd) {
-        if (!cd.lazy) return false;
-        if (listed_iv(c, cd.i, cd.j, cd.lo, cd.hi)) { cd.lazy = false; return false; }
-        return true;
-    }
-    GSM_HD static void resolve_now(Ctx& c, Cand& cd) {
-        if (!resolve(c, cd)) return;
-        uint32_t l, n;
-        c.interval(cd.i, cd.j, l, n);
-        cd.lo = (iv_t)l; cd.hi = (iv_t)(l + n - 1u); cd.lazy = false;
+    // winner of a round -> its interval, from the round's window results W (lo(i) / hi(i)), the match list, or (returns
+    // true) one explicit backward search from j down to i (Ctx::interval) that the caller still has to run.
+    template <typename W>
+    GSM_HD static bool resolve(Ctx& c, const Cand& cd, const W& win, iv_t& lo, iv_t& hi) {
+        if (cd.src == SRC_LAZY) return !listed_iv(c, cd.i(), cd.j(), lo, hi);
+        if (cd.src & SRC_WIN) { lo = win.lo(cd.src & 0xFFu); hi = win.hi(cd.src & 0xFFu); return false; }
+        const MemEntry m = c.mem(cd.src);
+        lo = (iv_t)m.lo; hi = (iv_t)(m.lo + m.cnt - 1u);
+        return false;
     }
 
-    // forward_extension(query, pc+K, kmer, seed) (SMEM.py:425-443): longest key and its value.  f = F(pc).
-    GSM_HD static Cand fwd_only(Ctx& c, uint32_t pc, iv_t slo, iv_t shi, uint32_t f) {
-        if (f <= pc + c.K) return known(pc, pc + c.K, slo, shi);     // the seed key itself
+    // forward_extension(query, pc+K, kmer, seed) (SMEM.py:425-443): longest key and its value.  f = F(pc), w = the
+    // window whose lookup is the frame's seed tuple.
+    GSM_HD static Cand fwd_only(Ctx& c, uint32_t pc, uint32_t w, uint32_t f) {
+        if (f <= pc + c.K) return seed_key(pc, c.K, w);              // the seed key itself
         return lazy_iv(pc, f);
     }
-    GSM_HD static Cand fwd_only(Ctx& c, uint32_t pc, iv_t slo, iv_t shi) { return fwd_only(c, pc, slo, shi, F_of(c, pc)); }
 
     // backward_extension(query, pc, keys) (SMEM.py:389-423) over keys pc+K .. max(F(pc), pc+K)
     // (all_keys) or over the seed key only.  f = F(pc), k0 = first match whose end exceeds pc + K - 1.
-    GSM_HD static Cand bext(Ctx& c, uint32_t pc, iv_t slo, iv_t shi, bool all_keys, uint32_t f, uint32_t k0) {
+    GSM_HD static Cand bext(Ctx& c, uint32_t pc, uint32_t w, bool all_keys, uint32_t f, uint32_t k0) {
         const uint32_t K = c.K;
         const bool seed_true = f >= pc + K;           // the k-mer really occurs
         uint32_t jmax = all_keys ? (f > pc + K ? f : pc + K) : pc + K;
@@ -720,7 +724,7 @@ struct Selector {
         bool b_from_mem = false;
         if (seed_true) {
             for (uint32_t k = k0; k < c.n_mems; ++k) {
-                const uint32_t w = c.se(k), s = w & 0xFFFFu, e = w >> 16;
+                const uint32_t v = c.se(k), s = v & 0xFFFFu, e = v >> 16;
                 if (s >= pc) break;                    // starts are sorted: no further left extension
                 uint32_t j = e <= jmax ? e : jmax;     // plateau end, or the key range's last key
                 if (!have || (j - s) > (bj - bi)) {
@@ -733,12 +737,11 @@ struct Selector {
         // the longest key wins only if strictly longer (SMEM.py:418)
         uint32_t fend = jmax;
         if (!have || (fend - pc) > (bj - bi)) {
-            if (fend == pc + K) return known(pc, fend, slo, shi);
+            if (fend == pc + K) return seed_key(pc, K, w);
             return lazy_iv(pc, fend);
         }
         if (!b_from_mem) return lazy_iv(bi, bj);
-        const MemEntry bm = c.mem(bk);
-        return known(bi, bj, (iv_t)bm.lo, (iv_t)(bm.lo + bm.cnt - 1u));
+        return listed(bi, bj, bk);
     }
 
     // get_smems_lut / get_smems_rmi: the frame machine of SMEM.py:49-186 / :235-379, one ROUND at a time.  A round =
@@ -759,48 +762,58 @@ struct Selector {
         return true;
     }
 
+    // the lookup results of one round, per window: plain arrays here; k_select_seeded keeps them in shared memory
+    struct Windows {
+        iv_t l[MAX_SEED_K], h[MAX_SEED_K];
+        GSM_HD iv_t lo(uint32_t i) const { return l[i]; }
+        GSM_HD iv_t hi(uint32_t i) const { return h[i]; }
+        GSM_HD void put(uint32_t i, iv_t lo_, iv_t hi_) { l[i] = lo_; h[i] = hi_; }
+    };
+
     GSM_HD static void run_seeded(Ctx& c) {
         Seeded st;
-        iv_t wlo[MAX_SEED_K], whi[MAX_SEED_K];
+        Windows win;
         while (round_needed(c, st)) {
             uint32_t wtrue = 0;
-            const uint32_t whit = c.seed_round(st.first, st.e, st.plen, st.first ? 1u : c.K, wlo, whi, wtrue);
+            const uint32_t whit = c.seed_round(st.first, st.e, st.plen, st.first ? 1u : c.K, win, wtrue);
             if (c.failed()) return;
-            round_finish(c, st, wlo, whi, whit, wtrue);
+            const Cand w = round_decide(c, st, win, whit, wtrue);
+            iv_t lo = 0, hi = 0;
+            if (w.valid() && resolve(c, w, win, lo, hi)) {
+                uint32_t l, n;
+                c.interval(w.i(), w.j(), l, n);
+                lo = (iv_t)l; hi = (iv_t)(l + n - 1u);
+            }
+            round_commit(c, st, w, lo, hi);
         }
-    }
-
-    GSM_HD static void round_finish(Ctx& c, Seeded& st, const iv_t* wlo, const iv_t* whi, uint32_t whit, uint32_t wtrue) {
-        Cand w = round_decide(c, st, wlo, whi, whit, wtrue);
-        if (w.valid) resolve_now(c, w);
-        round_commit(c, st, w);
     }
 
     // emit the round's winner and advance; an invalid winner ends the read (no match covers e: only when a base of the read
     // is absent from the text, outside the reference's domain)
-    GSM_HD static void round_commit(Ctx& c, Seeded& st, const Cand& w) {
-        if (!w.valid) { st.done = true; return; }
-        c.emit(w.i, w.j, w.lo, w.hi);
+    GSM_HD static void round_commit(Ctx& c, Seeded& st, const Cand& w, iv_t lo, iv_t hi) {
+        if (!w.valid()) { st.done = true; return; }
+        c.emit(w.i(), w.j(), lo, hi);
         st.first = false;
-        st.e = w.j; st.plen = w.j - w.i;
+        st.e = w.j(); st.plen = w.len();
     }
 
-    // wtrue: bit i set = (wlo[i], whi[i]) is the TRUE interval of window i's k-mer (always for LUT; for RMI when the lookup
+    // wtrue: bit i set = window i's (lo, hi) is the TRUE interval of its k-mer (always for LUT; for RMI when the lookup
     // was proven exact), which lets check_sequential be evaluated in closed form.
-    GSM_HD static Cand round_decide(Ctx& c, const Seeded& st, const iv_t* wlo, const iv_t* whi, uint32_t whit, uint32_t wtrue) {
+    template <typename W>
+    GSM_HD static Cand round_decide(Ctx& c, const Seeded& st, const W& win, uint32_t whit, uint32_t wtrue) {
         const uint32_t K = c.K, L = c.L;
         const uint32_t e = st.e, plen = st.plen;
         if (st.first) {                                    // SMEM.py:26-39 / :213-225
-            if (whit & 1u) return fwd_only(c, 0, wlo[0], whi[0]);
+            if (whit & 1u) return fwd_only(c, 0, 0, F_of(c, 0));
             const uint32_t end = F_of(c, 0);
-            if (end == 0) return Cand{false, false, 0, 0, (iv_t)0, (iv_t)0};
+            if (end == 0) return Cand{};
             return lazy_iv(0, end);
         }
-        // frame: 0 = None, 1 = () , 2 = k-mer frame
+        // frame: 0 = None, 1 = () , 2 = k-mer frame (start pc, seed tuple = the lookup of window pw)
         int fstate = 0;
-        uint32_t pc = 0; bool pfw = false, ptrue = false; iv_t plo = 0, phi = 0;
+        uint32_t pc = 0, pw = 0; bool pfw = false;
         uint32_t pF = 0, pE = 0;                 // of the frame's window: F(pc) and the first match whose end exceeds pc + K - 1
-        Cand cd{false, false, 0, 0, (iv_t)0, (iv_t)0};
+        Cand cd{};
         const uint32_t pstart = e - plen;
         // The windows of a round move left one base at a time, so the two positions the machine looks up in the match list
         // per window (starts <= cpos, ends > cpos + K - 1) are CURSORS that only step left: two binary searches per round
@@ -812,12 +825,11 @@ struct Selector {
         enum { A_NONE = 0, A_BEXT = 1, A_FWD = 2, A_KNOWN = 3 };
         for (uint32_t i = 0; i <= K; ++i) {
             int act = A_NONE;
-            uint32_t ai = 0, aj = 0;                // A_BEXT / A_FWD: frame start in ai; A_KNOWN: the candidate (ai, aj)
+            uint32_t ai = 0, aw = 0;                // the frame (start, window of its seed) the action applies to
             uint32_t aF = 0, aE = 0;                // A_BEXT / A_FWD: the frame's F(pc) and first-end cursor
-            iv_t alo = 0, ahi = 0;
             bool aall = false;
             if (i == K) {
-                if (fstate == 2) { act = A_BEXT; ai = pc; alo = plo; ahi = phi; aall = pfw; aF = pF; aE = pE; }
+                if (fstate == 2) { act = A_BEXT; ai = pc; aw = pw; aall = pfw; aF = pF; aE = pE; }
             } else {
                 if (i >= plen) continue;
                 const uint32_t cpos = e - i;
@@ -826,46 +838,45 @@ struct Selector {
                 while (ne > 0u && ek(c, ne - 1u) > cpos + K - 1u) --ne;           // first match ending beyond the window
                 uint32_t Fc = cpos;                                               // F(cpos): end of the longest match starting there
                 if (nf > 0u) { const uint32_t en = ek(c, nf - 1u); Fc = en > cpos ? en : cpos; }
-                const iv_t lo = wlo[i], hi = whi[i];
                 const bool hit = (whit >> i) & 1u;
-                const bool tru = (wtrue >> i) & 1u;
                 if (hit) {
-                    if (fstate == 0) { fstate = 2; pc = cpos; pfw = true; plo = lo; phi = hi; ptrue = tru; pF = Fc; pE = ne; }          // :70
-                    else if (fstate == 1) { fstate = 2; pc = cpos; pfw = false; plo = lo; phi = hi; ptrue = tru; pF = Fc; pE = ne; }    // :73
+                    if (fstate == 0) { fstate = 2; pc = cpos; pw = i; pfw = true; pF = Fc; pE = ne; }          // :70
+                    else if (fstate == 1) { fstate = 2; pc = cpos; pw = i; pfw = false; pF = Fc; pE = ne; }    // :73
                     else {
                         // check_sequential of two TRUE k-mer intervals at adjacent windows is just
                         // "q[cpos : cpos+K+1) occurs" (SURVEY A13): read it off the match list
-                        const bool both = tru && ptrue;
+                        const bool both = ((wtrue >> i) & (wtrue >> pw) & 1u) != 0u;
                         const bool seq = (both && pc == cpos + 1) ? (Fc >= cpos + K + 1)
-                                                                  : c.sequential(cpos, lo, hi, pc, plo, phi, both);
+                                                                  : c.sequential(cpos, (int64_t)win.lo(i), (int64_t)win.hi(i), pc,
+                                                                                 (int64_t)win.lo(pw), (int64_t)win.hi(pw), both);
                         if (seq) {                                                                        // Case 1
-                            if (!pfw && cd.valid && (pc - pstart) + K < (cd.j - cd.i)) continue;          // :94-95 (the frame stays)
-                            act = A_BEXT; ai = pc; alo = plo; ahi = phi; aall = pfw; aF = pF; aE = pE;
+                            if (!pfw && cd.valid() && (pc - pstart) + K < cd.len()) continue;             // :94-95 (the frame stays)
+                            act = A_BEXT; ai = pc; aw = pw; aall = pfw; aF = pF; aE = pE;
                         } else if (pfw) {                                                                 // Case 2
-                            act = A_FWD; ai = pc; alo = plo; ahi = phi; aF = pF;
+                            act = A_FWD; ai = pc; aw = pw; aF = pF;
                         } else {
-                            act = A_KNOWN; ai = cpos; aj = cpos + K; alo = lo; ahi = hi;
+                            act = A_KNOWN; ai = cpos; aw = i;
                         }
-                        pc = cpos; pfw = false; plo = lo; phi = hi; ptrue = tru; pF = Fc; pE = ne;
+                        pc = cpos; pw = i; pfw = false; pF = Fc; pE = ne;
                     }
                 } else {
                     if (fstate == 2) {                                                                    // Case 3
-                        if (pfw) { act = A_FWD; ai = pc; alo = plo; ahi = phi; aF = pF; }
-                        else { act = A_KNOWN; ai = pc; aj = pc + K; alo = plo; ahi = phi; }
+                        if (pfw) { act = A_FWD; ai = pc; aw = pw; aF = pF; }
+                        else { act = A_KNOWN; ai = pc; aw = pw; }
                     }
                     fstate = 1;
                 }
             }
-            if (act == A_BEXT) upd(cd, bext(c, ai, alo, ahi, aall, aF, aE));
-            else if (act == A_FWD) upd(cd, fwd_only(c, ai, alo, ahi, aF));
-            else if (act == A_KNOWN) upd(cd, known(ai, aj, alo, ahi));
+            if (act == A_BEXT) upd(cd, bext(c, ai, aw, aall, aF, aE));
+            else if (act == A_FWD) upd(cd, fwd_only(c, ai, aw, aF));
+            else if (act == A_KNOWN) upd(cd, seed_key(ai, K, aw));
         }
-        if (!cd.valid) {                                                                              // :175-179
+        if (!cd.valid()) {                                                                            // :175-179
             uint32_t from = 0;
             const uint32_t b = covering_best(c, e, from);
             if (b >= c.n_mems) return cd;
-            const MemEntry m = c.mem(b);
-            return known(s_of(m), e_of(m), (iv_t)m.lo, (iv_t)(m.lo + m.cnt - 1u));
+            const uint32_t v = c.se(b);
+            return listed(v & 0xFFFFu, v >> 16, b);
         }
         return cd;
     }

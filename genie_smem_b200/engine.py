@@ -597,9 +597,11 @@ class RmiParams:
         s.coef, s.intercept = self.params.data_ptr(), self.params.data_ptr() + 8
         s.param_stride = 2
         s.probe = None
+        s.bounds = None
         s.none_rows, s.n_none_rows = None, 0
         self.c = s
         self.probe = None
+        self.bounds = None
         self.none_rows = None
 
     def persist_in_l2(self, on=True):
@@ -622,6 +624,23 @@ class RmiParams:
         self.none_rows = rows
         self.c.none_rows = rows.ctypes.data_as(capi.u32p)
         self.c.n_none_rows = self.K
+        return self
+
+    def build_bounds_table(self, index):
+        """Dense {first row >= k-mer, occurrences} pair per K-mer code (gsm_rmi_bounds_build; 4^K x 8 B of HBM, 8.6 GB for
+        K = 15): with the None rows, every RMI lookup of the selection kernel is the model prediction plus ONE fetch.
+        Results never depend on it."""
+        if self.K > 16:
+            raise ValueError("bounds table: K must be <= 16")
+        self.bounds = torch.empty((1 << (2 * self.K)) * 2, dtype=torch.int32, device=index.device)
+        with torch.cuda.device(index.device):
+            capi.check(capi.lib.gsm_rmi_bounds_build(C.byref(index.c), self.K, _ptr(self.bounds), _stream()))
+        self.c.bounds = self.bounds.data_ptr()
+        return self
+
+    def drop_bounds_table(self):
+        self.bounds = None
+        self.c.bounds = None
         return self
 
     def build_probe_table(self, index):

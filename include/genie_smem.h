@@ -215,6 +215,7 @@ typedef struct {
     uint32_t n_none_rows;        /* K, or 0 */
     uint32_t param_stride;       /* elements between consecutive models in coef[] / intercept[]: 0 or 1 = two dense arrays;
                                     2 = one interleaved {coef, intercept} array (intercept == coef + 1): one line per model */
+    const void* bounds;          /* device, optional: 4^K x 8 B from gsm_rmi_bounds_build (used with none_rows), else NULL */
 } gsm_dev_rmi;
 
 /* Scratch + output buffers for one SMEM batch; all device memory, all caller-allocated.
@@ -338,6 +339,13 @@ int gsm_gather_advance(uint64_t* base_dev, const uint64_t* counts_dev, uint32_t 
  * bases at that suffix} (16 bytes), so RMI_LUT.get_ref_seq (RMI_LUT.py:89-92) is ONE fetch instead of
  * a suffix-array read followed by a text read.  probe: n_rows * 16 bytes of device memory. */
 int gsm_rmi_probe_build(const gsm_dev_index* idx, void* probe, void* stream);
+
+/* Optional accelerator for the RMI lookups of gsm_smem_select: bounds[code] = {first row whose K-mer >= code, occurrences of
+ * the K-mer} (two uint32) for all 4^K codes, K = the model's prediction size (K <= 16; 8.6 GB for K = 15).  The error-bounded
+ * search of RMI_LUT.get_suffix_rmi (RMI_LUT.py:67-184) is a function of the prediction and of these true bounds
+ * (rmi_arith_lookup), so a window then costs ONE fetch instead of a seed-table fetch plus K - seed_K backward steps.  Uses the
+ * index's seed table when present (seed_K <= K) to shorten the build.  Results never depend on it. */
+int gsm_rmi_bounds_build(const gsm_dev_index* idx, uint32_t K, void* bounds, void* stream);
 
 /* The rows whose suffix is shorter than K bases (RMI_LUT.get_ref_seq returns None there, RMI_LUT.py:89-92): exactly K
  * rows.  rows_host (HOST, K entries, ascending); scratch: 33 uint32 of device memory.  With them in gsm_dev_rmi the

@@ -106,7 +106,8 @@ struct SelCtx {
         }
     }
 
-    uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, int64_t* lo, int64_t* hi, uint32_t& wtrue) {
+    template <typename W>
+    uint32_t seed_round(bool first, uint32_t e, uint32_t plen, uint32_t nwin, W& win, uint32_t& wtrue) {
         auto rd = [&](uint64_t w) { return words[w]; };
         auto load = [&](uint64_t idx) { return ix->fwd[idx]; };
         auto seed = [&](uint64_t code) { return seed_tab[code]; };
@@ -122,7 +123,7 @@ struct SelCtx {
             uint64_t code = kmer_code(rd, cpos, K);
             if (method == GSM_METHOD_LUT_) {
                 uint32_t l = lut[2 * code], n = lut[2 * code + 1];
-                lo[i] = l; hi[i] = (int64_t)l + n - 1;
+                win.put(i, (int64_t)l, (int64_t)l + n - 1);
                 wtrue |= 1u << i;
                 if (n != 0) hit |= 1u << i;
                 continue;
@@ -139,7 +140,7 @@ struct SelCtx {
                     ok = rmi_fast_lookup(pr, rmi, code, ix->meta.n_rows, (int64_t)ix->n_bases, flo, fhi);
                 }
                 if (ok) {
-                    lo[i] = flo; hi[i] = fhi;
+                    win.put(i, flo, fhi);
                     wtrue |= 1u << i;
                     if (fhi >= flo) hit |= 1u << i;
                     continue;
@@ -154,7 +155,7 @@ struct SelCtx {
                 rs.feed(s, c64);
             }
             if (rs.raised) { raised = true; return hit; }
-            lo[i] = rs.out_lo; hi[i] = rs.out_hi;
+            win.put(i, rs.out_lo, rs.out_hi);
             if (rs.hit()) hit |= 1u << i;
         }
         return hit;

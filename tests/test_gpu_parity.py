@@ -425,6 +425,9 @@ def test_rmi_fast_search_changes_nothing(gs):
         assert rmi.c.n_none_rows == K
         fast = e.run(gs.METHOD_RMI, batch, rmi=rmi)
         fr, fo, fs = fast.records.copy(), fast.offsets.copy(), fast.status.copy()
+        bnd = e.run(gs.METHOD_RMI, batch, rmi=rmi.build_bounds_table(idx))   # true bounds from the dense table
+        assert np.array_equal(fo, bnd.offsets) and np.array_equal(fr, bnd.records) and np.array_equal(fs, bnd.status)
+        rmi.drop_bounds_table()
         rmi.c.none_rows, rmi.c.n_none_rows = None, 0                      # literal search only
         lit = e.run(gs.METHOD_RMI, batch, rmi=rmi)
         assert np.array_equal(fo, lit.offsets) and np.array_equal(fr, lit.records) and np.array_equal(fs, lit.status)
@@ -486,7 +489,12 @@ def test_all_methods_vs_oracle_on_synthetic_reference(gs, seed_table):
     for K, experts in ((11, (64, 4096)), (15, (256, 16384)), (9, (4, 64))):
         rmi = bench.train_rmi(idx, K, experts, idx.device)
         res = e.run(gs.METHOD_RMI, batch, rmi=rmi)
-        n_raise += _check_against_oracle(gs, res, reads_s, o.smem_dicts(2, reads_s, rmi=bench.rmi_dict(rmi)), f"rmi K={K}")
+        exp = o.smem_dicts(2, reads_s, rmi=bench.rmi_dict(rmi))
+        n_raise += _check_against_oracle(gs, res, reads_s, exp, f"rmi K={K}")
+        rmi.build_bounds_table(idx)                                       # lookups from the dense k-mer bounds table
+        res = e.run(gs.METHOD_RMI, batch, rmi=rmi)
+        _check_against_oracle(gs, res, reads_s, exp, f"rmi K={K}, bounds table")
+        rmi.drop_bounds_table()
     assert n_raise < 200
 
 

@@ -73,7 +73,10 @@ def main():
     legs = [("bwa", g.METHOD_BWA, {"min_len": 1}), ("lut", g.METHOD_LUT, {"K": bench.LUT_K, "lut": lut})]
     if rmi is not None:
         legs.append(("rmi", g.METHOD_RMI, {"rmi": rmi}))
+        legs.append(("rmi_bounds", g.METHOD_RMI, {"rmi": rmi}))
     for name, method, kw in legs:
+        if name == "rmi_bounds":                      # same lookups from the dense bounds table (gsm_rmi_bounds_build)
+            out["ms_bounds_build"] = round(timed(lambda: rmi.build_bounds_table(index), 1), 1)
         out[f"ms_select_{name}"] = round(timed(lambda: eng.select(method, batch, **kw), a.steps), 3)
         n_mems, n_rec = eng.check_overflow()
         recs = eng.records[: n_rec * 16].cpu().numpy()
