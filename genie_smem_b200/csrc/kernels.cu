@@ -257,34 +257,47 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
     }
 }
 
-// The lookup results of one round (Selector::round_decide's `win`) in shared memory: window i of this thread is word
-// i * SELECT_THREADS of its column in the lo plane, the hi plane K windows further -- a warp's 32 threads touch 32
-// consecutive words, and nothing of it lives in local memory (as per-thread arrays the two planes were 512 bytes of stack
-// per thread: with 151,552 resident threads more than the L2 holds).  RMI rows may be negative (down to -n_rows, Python
-// indexing of a wrong interval; n_rows < 2^32): the low 32 bits are stored and the signs kept in two register masks.
+// The lookup results of one round (Selector::round_decide's `win`) in shared memory: two planes (lo, hi) of K windows x
+// WIN_STRIDE words, window i of a thread at word i * WIN_STRIDE + threadIdx.x -- nothing of it lives in local memory (as
+// per-thread arrays the two planes were 512 bytes of stack per thread: with 151,552 resident threads more than the L2
+// holds), and ANY lane of the warp can store a thread's result (pass 1 of k_select_seeded spreads the windows of the warp's
+// 32 reads evenly over its lanes).  WIN_STRIDE is odd: the windows of one thread lie in different banks, and so do the
+// same window of the 32 threads.  RMI rows may be negative (down to -n_rows, Python indexing of a wrong interval;
+// n_rows < 2^32): the low 32 bits are stored and the signs kept in two masks (bit = window).
+constexpr int WIN_STRIDE = SELECT_THREADS + 1;
+constexpr int WIN_MASKS = 5;                               // per thread: hit, true, redo, lo negative, hi negative
+enum : int { WM_HIT = 0, WM_TRUE = 1, WM_REDO = 2, WM_NEG_LO = 3, WM_NEG_HI = 4 };
+__host__ __device__ constexpr size_t select_smem_bytes(uint32_t K) {
+    return (2ull * K * WIN_STRIDE + (size_t)WIN_MASKS * SELECT_THREADS) * sizeof(uint32_t) + (size_t)K * SELECT_THREADS * sizeof(uint16_t);
+}
 template <int METHOD>
 struct SmemWindows {
     using iv_t = typename DevSelCtx<METHOD>::iv_t;
-    uint32_t* lo_w;
+    uint32_t* lo_w;         // this thread's column of the two planes
     uint32_t* hi_w;
     uint32_t neg_lo, neg_hi;
     __device__ __forceinline__ iv_t lo(uint32_t i) const {
-        const uint32_t v = lo_w[i * SELECT_THREADS];
+        const uint32_t v = lo_w[i * WIN_STRIDE];
         if (METHOD == GSM_METHOD_RMI) return (iv_t)((int64_t)v - ((int64_t)((neg_lo >> i) & 1u) << 32));
         return (iv_t)v;
     }
     __device__ __forceinline__ iv_t hi(uint32_t i) const {
-        const uint32_t v = hi_w[i * SELECT_THREADS];
+        const uint32_t v = hi_w[i * WIN_STRIDE];
         if (METHOD == GSM_METHOD_RMI) return (iv_t)((int64_t)v - ((int64_t)((neg_hi >> i) & 1u) << 32));
         return (iv_t)v;
     }
     __device__ __forceinline__ void put(uint32_t i, iv_t l, iv_t h) {
-        lo_w[i * SELECT_THREADS] = (uint32_t)l;
-        hi_w[i * SELECT_THREADS] = (uint32_t)h;
+        lo_w[i * WIN_STRIDE] = (uint32_t)l;
+        hi_w[i * WIN_STRIDE] = (uint32_t)h;
         if (METHOD == GSM_METHOD_RMI) {
             neg_lo = (neg_lo & ~(1u << i)) | ((uint32_t)((int64_t)l < 0) << i);
             neg_hi = (neg_hi & ~(1u << i)) | ((uint32_t)((int64_t)h < 0) << i);
         }
+    }
+    // store into the column of the thread `d` lanes away (same warp); signs are the caller's business
+    __device__ __forceinline__ void put_for(int d, uint32_t i, uint32_t l, uint32_t h) const {
+        lo_w[(int)(i * WIN_STRIDE) + d] = l;
+        hi_w[(int)(i * WIN_STRIDE) + d] = h;
     }
 };
 
@@ -381,8 +394,12 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __gr
     bool direct = false;
     typename Sel::Seeded st;
     using iv_t = typename CtxT::iv_t;
-    extern __shared__ uint32_t sel_windows[];              // 2 planes x K windows x SELECT_THREADS words
-    SmemWindows<METHOD> win{sel_windows + threadIdx.x, sel_windows + a.K * SELECT_THREADS + threadIdx.x, 0u, 0u};
+    extern __shared__ uint32_t sel_smem[];                 // select_smem_bytes(K): window planes | masks | the warps' item lists
+    SmemWindows<METHOD> win{sel_smem + threadIdx.x, sel_smem + a.K * WIN_STRIDE + threadIdx.x, 0u, 0u};
+    uint32_t* const wm = sel_smem + 2u * a.K * WIN_STRIDE + threadIdx.x;                      // mask m of this thread: wm[m * SELECT_THREADS]
+    uint16_t* const items = reinterpret_cast<uint16_t*>(sel_smem + 2u * a.K * WIN_STRIDE + WIN_MASKS * SELECT_THREADS)
+                            + (threadIdx.x >> 5) * (a.K * 32u);                                // this warp's (lane, window) pairs of a round
+    const uint32_t lane = threadIdx.x & 31u;
 
     auto close_read = [&](uint8_t status) {
         if (c.close(status, direct)) { st = typename Sel::Seeded(); return; }      // overflowed its staging slots: run it again in place
@@ -424,53 +441,98 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __gr
                 if (st.first || (i < st.plen && cpos + c.K <= c.L)) vis |= 1u << i;
             }
         }
-        constexpr uint32_t WB = 1;                          // windows per batch (batches of 4 measured slower: register spills, profiles/r02_notes.md)
-        if (METHOD == GSM_METHOD_LUT) {
-            for (uint32_t i0 = 0; i0 < nwin; i0 += WB) {
-                uint2 t[WB];
-#pragma unroll
-                for (uint32_t j = 0; j < WB; ++j)
-                    if ((vis >> (i0 + j)) & 1u) t[j] = __ldg(a.lut + c.window_code(st.first ? 0u : st.e - (i0 + j)));
-#pragma unroll
-                for (uint32_t j = 0; j < WB; ++j)
-                    if ((vis >> (i0 + j)) & 1u) {
-                        win.put(i0 + j, (iv_t)t[j].x, (iv_t)(t[j].x + t[j].y - 1u));
-                        if (t[j].y != 0u) whit |= 1u << (i0 + j);
-                    }
+        if (METHOD == GSM_METHOD_LUT || arith) {
+            // The threads of a warp visit different numbers of windows (1 in a read's first round, min(K, previous SMEM's
+            // length) later): the warp lists its (thread, window) pairs and every lane takes every 32nd pair, whoever's it is
+            // -- the read's words and the round's position come over by shuffle, the result goes to the owner's column of the
+            // planes, the hit / true / redo bits to the owner's masks (one shared-memory atomic per owner and loop trip).
+            uint32_t incl = __popc(vis);
+            const uint32_t nv = incl;
+            for (uint32_t d = 1; d < 32u; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += y;
             }
-            wtrue = vis;
-        } else if (arith) {
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            uint32_t slot = incl - nv;
+            for (uint32_t m = vis; m != 0u; m &= m - 1u) items[slot++] = (uint16_t)(lane | ((uint32_t)(__ffs(m) - 1) << 5));
+#pragma unroll
+            for (int m = 0; m < WIN_MASKS; ++m) wm[m * SELECT_THREADS] = 0u;
+            __syncwarp();
+            const uint32_t e_eff = st.first ? 0u : st.e;        // window w of the round starts at e_eff - w (first round: window 0 at 0)
+            const unsigned long long my_words = (unsigned long long)c.words;
             const uint4* fwd = a.fwd;
             auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
             const uint64_t seed_mask = (1ull << (2u * a.seed_K)) - 1ull;
-            for (uint32_t i = 0; i < nwin; ++i) {
-                if (!((vis >> i) & 1u)) continue;
-                const uint64_t code = c.window_code(st.first ? 0u : st.e - i);
-                uint32_t A, n;
-                if (ARITH == 2) {                           // the k-mer's true bounds straight from the dense table
-                    const uint2 e = __ldg(a.rmi_bounds + code);
-                    A = e.x; n = e.y;
-                } else {                                    // seed-table entry of the window's last seed_K bases ...
-                    const uint4 e = __ldg(a.seed_tab + (code & seed_mask));
-                    A = e.x; n = e.y;
-                }
-                // ... while it travels: the model prediction (parameters are L2-resident)
-                const int64_t row0 = RmiGallop::predicted_row(a.rmi, code, a.meta.n_rows);
-                if (ARITH != 2) {
-                    for (uint32_t p = c.K - a.seed_K; p > 0; --p) {        // ... then K - seed_K backward steps
-                        const uint32_t ch = (uint32_t)(code >> (2u * (c.K - p))) & 3u;
-                        const StepOut r = step_single(load, A, A + n, ch, a.meta.C[ch], a.meta.prim_f);
-                        A = r.lo_new; n = r.cnt_new;
+            for (uint32_t k0 = 0; k0 < total; k0 += 32u) {
+                const bool on = k0 + lane < total;
+                const uint32_t it = on ? items[k0 + lane] : 0u;
+                const uint32_t owner = it & 31u, w = it >> 5;
+                const uint32_t* ow = (const uint32_t*)__shfl_sync(FULL, my_words, owner);
+                const uint32_t cpos = __shfl_sync(FULL, e_eff, owner) - w;
+                uint32_t fhit = 0, ftrue = 0, fredo = 0, fnl = 0, fnh = 0;
+                if (on) {
+                    auto rd = [ow](uint64_t x) { return __ldg(ow + x); };
+                    const uint64_t code = kmer_code(rd, cpos, c.K);
+                    if (METHOD == GSM_METHOD_LUT) {             // one 8-byte gather (LUT.py:15-35 as a dense table)
+                        const uint2 t = __ldg(a.lut + code);
+                        win.put_for((int)owner - (int)lane, w, t.x, t.x + t.y - 1u);
+                        fhit = t.y != 0u;
+                    } else {
+                        uint32_t A, n;
+                        if (ARITH == 2) {                       // the k-mer's true bounds straight from the dense table
+                            const uint2 e = __ldg(a.rmi_bounds + code);
+                            A = e.x; n = e.y;
+                        } else {                                // seed-table entry of the window's last seed_K bases ...
+                            const uint4 e = __ldg(a.seed_tab + (code & seed_mask));
+                            A = e.x; n = e.y;
+                        }
+                        // ... while it travels: the model prediction (parameters are L2-resident)
+                        const int64_t row0 = RmiGallop::predicted_row(a.rmi, code, a.meta.n_rows);
+                        if (ARITH != 2) {
+                            for (uint32_t p = c.K - a.seed_K; p > 0; --p) {        // ... then K - seed_K backward steps
+                                const uint32_t ch = (uint32_t)(code >> (2u * (c.K - p))) & 3u;
+                                const StepOut r = step_single(load, A, A + n, ch, a.meta.C[ch], a.meta.prim_f);
+                                A = r.lo_new; n = r.cnt_new;
+                            }
+                        }
+                        int64_t lo, hi;                         // the error-bounded search replayed on row numbers
+                        if (rmi_arith_lookup(a.rmi, row0, A, n, a.meta.n_rows, lo, hi)) {
+                            win.put_for((int)owner - (int)lane, w, (uint32_t)lo, (uint32_t)hi);
+                            ftrue = 1u; fhit = hi >= lo; fnl = lo < 0; fnh = hi < 0;
+                        } else {
+                            fredo = 1u;
+                        }
                     }
                 }
-                int64_t lo, hi;                             // the error-bounded search replayed on row numbers
-                if (rmi_arith_lookup(a.rmi, row0, A, n, a.meta.n_rows, lo, hi)) {
-                    win.put(i, (iv_t)lo, (iv_t)hi);
-                    wtrue |= 1u << i;
-                    if (hi >= lo) whit |= 1u << i;
-                } else {
-                    redo |= 1u << i;
+                // the pairs of one owner are neighbours in the list: combine their bits before touching its masks
+                const uint32_t peers = __match_any_sync(FULL, on ? owner : 32u);
+                const uint32_t bit = 1u << w;
+                const bool lead = on && lane == (uint32_t)(__ffs(peers) - 1);
+                uint32_t* const om = wm + ((int)owner - (int)lane);
+                uint32_t v = __reduce_or_sync(peers, fhit ? bit : 0u);
+                if (lead && v) atomicOr(om + WM_HIT * SELECT_THREADS, v);
+                if (METHOD == GSM_METHOD_RMI) {
+                    v = __reduce_or_sync(peers, ftrue ? bit : 0u);
+                    if (lead && v) atomicOr(om + WM_TRUE * SELECT_THREADS, v);
+                    v = __reduce_or_sync(peers, fredo ? bit : 0u);
+                    if (lead && v) atomicOr(om + WM_REDO * SELECT_THREADS, v);
+                    if (__any_sync(FULL, (fnl | fnh) != 0u)) {                    // negative rows: rare
+                        v = __reduce_or_sync(peers, fnl ? bit : 0u);
+                        if (lead && v) atomicOr(om + WM_NEG_LO * SELECT_THREADS, v);
+                        v = __reduce_or_sync(peers, fnh ? bit : 0u);
+                        if (lead && v) atomicOr(om + WM_NEG_HI * SELECT_THREADS, v);
+                    }
                 }
+            }
+            __syncwarp();
+            whit = wm[WM_HIT * SELECT_THREADS];
+            if (METHOD == GSM_METHOD_LUT) {
+                wtrue = vis;
+            } else {
+                wtrue = wm[WM_TRUE * SELECT_THREADS];
+                redo = wm[WM_REDO * SELECT_THREADS];
+                win.neg_lo = wm[WM_NEG_LO * SELECT_THREADS];
+                win.neg_hi = wm[WM_NEG_HI * SELECT_THREADS];
             }
         } else if (ARITH == 0 && a.rmi.n_none != 0) {
             // probe-based error-bounded search (select_logic.cuh, RmiGallop / RmiLower / RmiUpper): each phase runs over ALL
@@ -1282,7 +1344,7 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
     } else {
         static const int sel_blocks = getenv("GSM_SELECT_BLOCKS") ? atoi(getenv("GSM_SELECT_BLOCKS")) : 8;   // A/B: 6, 7
         const bool arith = rm.n_none != 0u && se.seed_K != 0u && se.seed_K <= K;       // lookups from the seed table: no probes
-        const size_t win_bytes = 2ull * K * SELECT_THREADS * sizeof(uint32_t);         // SmemWindows: at most 32 KB (K <= 32)
+        const size_t win_bytes = select_smem_bytes(K);                                  // at most 44 KB (K <= 32)
         if (method == GSM_METHOD_LUT) {
             if (sel_blocks == 6) st = launch_seeded<GSM_METHOD_LUT, 0, 6>(se, win_bytes, lb, stream);
             else if (sel_blocks == 7) st = launch_seeded<GSM_METHOD_LUT, 0, 7>(se, win_bytes, lb, stream);

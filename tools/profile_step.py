@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--method", default="bwa")
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--seed-k", type=int, default=-1)
+    ap.add_argument("--bounds", action="store_true", help="RMI: lookups from the dense k-mer bounds table")
     a = ap.parse_args()
     import torch
     import genie_smem_b200 as g
@@ -39,6 +40,8 @@ def main():
     elif a.method == "rmi":
         experts = bench.CONFIGS["c3" if a.ref_bases < 500_000_000 else "c4"]["experts"]
         method, kw = g.METHOD_RMI, {"rmi": bench.train_rmi(index, bench.RMI_K, experts, "cuda", probe_table=False)}
+        if a.bounds:
+            kw["rmi"].build_bounds_table(index)
     torch.cuda.synchronize()
     print(f"setup {time.time()-t0:.1f}s, seed table K={index.seed_K}", file=sys.stderr)
     for _ in range(1 + a.steps):
