@@ -41,6 +41,8 @@ namespace gsm {
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr int SELECT_THREADS = 128;
+constexpr int SELECT_DEFAULT_BLOCKS = 7;     // k_select_seeded: resident blocks per SM / variant when the environment says nothing
+constexpr int SELECT_DEFAULT_OPT = 0;
 constexpr uint32_t SELECT_STAGE = 64;   // staged records per selection thread; reads emitting more are run twice (see DevSelCtx::close)
 
 // ===================================================================================== select
@@ -101,7 +103,15 @@ struct DevSelCtx {
     bool overflow;        // more records than slots: counted, not stored
     // bit 31 of mem_cnt: the sweep stored this list in ascending order and field by field (n start|end words, n lo, n count, ...)
     bool soa;
-    __device__ __forceinline__ uint32_t se(uint32_t k) const { return soa ? reinterpret_cast<const uint32_t*>(mems)[k] : mems[k].x; }
+    // k_select_seeded: the (start, end) pairs of a short ordered list of a read of up to 255 bases, one byte each, in the
+    // thread's column of a shared-memory table (entry k at sec[k * SELECT_THREADS]); every lookup of the frame machine into
+    // the match list then stays on the SM
+    const uint16_t* sec = nullptr;
+    bool cached = false;
+    __device__ __forceinline__ uint32_t se(uint32_t k) const {
+        if (cached) { const uint32_t v = sec[k * SELECT_THREADS]; return (v & 0xFFu) | ((v >> 8) << 16); }
+        return soa ? reinterpret_cast<const uint32_t*>(mems)[k] : mems[k].x;
+    }
 
     __device__ __forceinline__ MemEntry mem(uint32_t k) const {
         if (soa) {
@@ -267,8 +277,10 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
 constexpr int WIN_STRIDE = SELECT_THREADS + 1;
 constexpr int WIN_MASKS = 5;                               // per thread: hit, true, redo, lo negative, hi negative
 enum : int { WM_HIT = 0, WM_TRUE = 1, WM_REDO = 2, WM_NEG_LO = 3, WM_NEG_HI = 4 };
-__host__ __device__ constexpr size_t select_smem_bytes(uint32_t K) {
-    return (2ull * K * WIN_STRIDE + (size_t)WIN_MASKS * SELECT_THREADS) * sizeof(uint32_t) + (size_t)K * SELECT_THREADS * sizeof(uint16_t);
+constexpr int SEC_ENTRIES = 32;                            // longest match list kept in shared memory (= the sweep's ordered lists)
+__host__ __device__ constexpr size_t select_smem_bytes(uint32_t K, bool se_cache) {
+    return (2ull * K * WIN_STRIDE + (size_t)WIN_MASKS * SELECT_THREADS) * sizeof(uint32_t) + (size_t)K * SELECT_THREADS * sizeof(uint16_t) +
+           (se_cache ? (size_t)SEC_ENTRIES * SELECT_THREADS * sizeof(uint16_t) : 0);
 }
 template <int METHOD>
 struct SmemWindows {
@@ -381,7 +393,7 @@ __device__ __noinline__ LiteralOut literal_lookups(const SelectArgs& a, const ui
 // rmi_arith_lookup and the probe-based phases are compiled out (fewer registers for the path that always runs);
 // 2 = as 1, the k-mer's true bounds read from the dense table of gsm_rmi_bounds_build (one fetch, no backward steps).
 // MB: resident blocks per SM the register allocation aims at (8: 64 registers with spills, 6: 80); GSM_SELECT_BLOCKS=6 for A/B
-template <int METHOD, int ARITH = 0, int MB = 8>
+template <int METHOD, int ARITH = 0, int MB = 8, int OPT = 0>
 __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __grid_constant__ SelectArgs a) {
     using CtxT = DevSelCtx<METHOD>;
     using Sel = Selector<CtxT>;
@@ -400,6 +412,10 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __gr
     uint16_t* const items = reinterpret_cast<uint16_t*>(sel_smem + 2u * a.K * WIN_STRIDE + WIN_MASKS * SELECT_THREADS)
                             + (threadIdx.x >> 5) * (a.K * 32u);                                // this warp's (lane, window) pairs of a round
     const uint32_t lane = threadIdx.x & 31u;
+    constexpr bool SE_CACHE = (OPT & 1) != 0;              // match-list (start, end) pairs in shared memory
+    constexpr int IPL = (OPT & 2) ? 2 : 1;                 // (thread, window) pairs per lane and trip of pass 1
+    uint16_t* const sec = reinterpret_cast<uint16_t*>(sel_smem + 2u * a.K * WIN_STRIDE + WIN_MASKS * SELECT_THREADS) + a.K * SELECT_THREADS + threadIdx.x;
+    if (SE_CACHE) c.sec = sec;
 
     auto close_read = [&](uint8_t status) {
         if (c.close(status, direct)) { st = typename Sel::Seeded(); return; }      // overflowed its staging slots: run it again in place
@@ -416,8 +432,14 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __gr
             c.out = stage; c.cap = a.stage_stride;
             c.soa = (mc >> 31) != 0u;
             if (!c.soa) order_segments(c.mems, c.n_mems);                      // bit 31: the sweep already ordered the list
+            c.cached = false;
             st = typename Sel::Seeded();
             if (c.L < c.K) { close_read(GSM_READ_TOO_SHORT); continue; }
+            if (SE_CACHE && c.soa && c.L <= 255u && c.n_mems <= (uint32_t)SEC_ENTRIES) {
+                const uint32_t* seg = reinterpret_cast<const uint32_t*>(c.mems);
+                for (uint32_t k = 0; k < c.n_mems; ++k) { const uint32_t v = seg[k]; sec[k * SELECT_THREADS] = (uint16_t)((v & 0xFFu) | ((v >> 16) << 8)); }
+                c.cached = true;
+            }
             have = true;
         }
     };
@@ -463,64 +485,86 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __gr
             const uint4* fwd = a.fwd;
             auto load = [fwd](uint64_t idx) { return ldg_half(fwd, idx); };
             const uint64_t seed_mask = (1ull << (2u * a.seed_K)) - 1ull;
-            for (uint32_t k0 = 0; k0 < total; k0 += 32u) {
-                const bool on = k0 + lane < total;
-                const uint32_t it = on ? items[k0 + lane] : 0u;
-                const uint32_t owner = it & 31u, w = it >> 5;
-                const uint32_t* ow = (const uint32_t*)__shfl_sync(FULL, my_words, owner);
-                const uint32_t cpos = __shfl_sync(FULL, e_eff, owner) - w;
-                uint32_t fhit = 0, ftrue = 0, fredo = 0, fnl = 0, fnh = 0;
-                if (on) {
-                    auto rd = [ow](uint64_t x) { return __ldg(ow + x); };
-                    const uint64_t code = kmer_code(rd, cpos, c.K);
-                    if (METHOD == GSM_METHOD_LUT) {             // one 8-byte gather (LUT.py:15-35 as a dense table)
-                        const uint2 t = __ldg(a.lut + code);
-                        win.put_for((int)owner - (int)lane, w, t.x, t.x + t.y - 1u);
-                        fhit = t.y != 0u;
-                    } else {
-                        uint32_t A, n;
-                        if (ARITH == 2) {                       // the k-mer's true bounds straight from the dense table
-                            const uint2 e = __ldg(a.rmi_bounds + code);
-                            A = e.x; n = e.y;
-                        } else {                                // seed-table entry of the window's last seed_K bases ...
-                            const uint4 e = __ldg(a.seed_tab + (code & seed_mask));
-                            A = e.x; n = e.y;
-                        }
-                        // ... while it travels: the model prediction (parameters are L2-resident)
-                        const int64_t row0 = RmiGallop::predicted_row(a.rmi, code, a.meta.n_rows);
-                        if (ARITH != 2) {
-                            for (uint32_t p = c.K - a.seed_K; p > 0; --p) {        // ... then K - seed_K backward steps
-                                const uint32_t ch = (uint32_t)(code >> (2u * (c.K - p))) & 3u;
-                                const StepOut r = step_single(load, A, A + n, ch, a.meta.C[ch], a.meta.prim_f);
-                                A = r.lo_new; n = r.cnt_new;
-                            }
-                        }
-                        int64_t lo, hi;                         // the error-bounded search replayed on row numbers
-                        if (rmi_arith_lookup(a.rmi, row0, A, n, a.meta.n_rows, lo, hi)) {
-                            win.put_for((int)owner - (int)lane, w, (uint32_t)lo, (uint32_t)hi);
-                            ftrue = 1u; fhit = hi >= lo; fnl = lo < 0; fnh = hi < 0;
-                        } else {
-                            fredo = 1u;
+            for (uint32_t k0 = 0; k0 < total; k0 += 32u * IPL) {
+                bool on[IPL];
+                uint32_t owner[IPL], w[IPL], tA[IPL], tn[IPL];
+                uint64_t code[IPL];
+                uint32_t fhit[IPL], ftrue[IPL], fredo[IPL], fnl[IPL], fnh[IPL];
+#pragma unroll
+                for (int j = 0; j < IPL; ++j) {                 // the pairs' k-mer codes and table fetches, all in flight together
+                    const uint32_t idx = k0 + 32u * j + lane;
+                    on[j] = idx < total;
+                    const uint32_t it = on[j] ? items[idx] : 0u;
+                    owner[j] = it & 31u; w[j] = it >> 5;
+                    const uint32_t* ow = (const uint32_t*)__shfl_sync(FULL, my_words, owner[j]);
+                    const uint32_t cpos = __shfl_sync(FULL, e_eff, owner[j]) - w[j];
+                    code[j] = 0; tA[j] = 0; tn[j] = 0;
+                    fhit[j] = ftrue[j] = fredo[j] = fnl[j] = fnh[j] = 0u;
+                    if (on[j]) {
+                        auto rd = [ow](uint64_t x) { return __ldg(ow + x); };
+                        code[j] = kmer_code(rd, cpos, c.K);
+                        if (METHOD == GSM_METHOD_LUT) {         // one 8-byte gather (LUT.py:15-35 as a dense table)
+                            const uint2 t = __ldg(a.lut + code[j]);
+                            tA[j] = t.x; tn[j] = t.y;
+                        } else if (ARITH == 2) {                // the k-mer's true bounds straight from the dense table
+                            const uint2 t = __ldg(a.rmi_bounds + code[j]);
+                            tA[j] = t.x; tn[j] = t.y;
+                        } else {                                // seed-table entry of the window's last seed_K bases
+                            const uint4 t = __ldg(a.seed_tab + (code[j] & seed_mask));
+                            tA[j] = t.x; tn[j] = t.y;
                         }
                     }
                 }
-                // the pairs of one owner are neighbours in the list: combine their bits before touching its masks
-                const uint32_t peers = __match_any_sync(FULL, on ? owner : 32u);
-                const uint32_t bit = 1u << w;
-                const bool lead = on && lane == (uint32_t)(__ffs(peers) - 1);
-                uint32_t* const om = wm + ((int)owner - (int)lane);
-                uint32_t v = __reduce_or_sync(peers, fhit ? bit : 0u);
-                if (lead && v) atomicOr(om + WM_HIT * SELECT_THREADS, v);
-                if (METHOD == GSM_METHOD_RMI) {
-                    v = __reduce_or_sync(peers, ftrue ? bit : 0u);
-                    if (lead && v) atomicOr(om + WM_TRUE * SELECT_THREADS, v);
-                    v = __reduce_or_sync(peers, fredo ? bit : 0u);
-                    if (lead && v) atomicOr(om + WM_REDO * SELECT_THREADS, v);
-                    if (__any_sync(FULL, (fnl | fnh) != 0u)) {                    // negative rows: rare
-                        v = __reduce_or_sync(peers, fnl ? bit : 0u);
-                        if (lead && v) atomicOr(om + WM_NEG_LO * SELECT_THREADS, v);
-                        v = __reduce_or_sync(peers, fnh ? bit : 0u);
-                        if (lead && v) atomicOr(om + WM_NEG_HI * SELECT_THREADS, v);
+                if (METHOD == GSM_METHOD_LUT) {
+#pragma unroll
+                    for (int j = 0; j < IPL; ++j)
+                        if (on[j]) {
+                            win.put_for((int)owner[j] - (int)lane, w[j], tA[j], tA[j] + tn[j] - 1u);
+                            fhit[j] = tn[j] != 0u;
+                        }
+                } else {
+                    double pred[IPL];                           // while the fetches travel: the model predictions (parameters are L2-resident)
+                    rmi_predict_n<IPL>(a.rmi, code, pred);
+#pragma unroll
+                    for (int j = 0; j < IPL; ++j)
+                        if (on[j]) {
+                            uint32_t A = tA[j], n = tn[j];
+                            if (ARITH != 2) {
+                                for (uint32_t p = c.K - a.seed_K; p > 0; --p) {        // K - seed_K backward steps
+                                    const uint32_t ch = (uint32_t)(code[j] >> (2u * (c.K - p))) & 3u;
+                                    const StepOut r = step_single(load, A, A + n, ch, a.meta.C[ch], a.meta.prim_f);
+                                    A = r.lo_new; n = r.cnt_new;
+                                }
+                            }
+                            int64_t lo, hi;                     // the error-bounded search replayed on row numbers
+                            if (rmi_arith_lookup(a.rmi, RmiGallop::row_of(pred[j], a.meta.n_rows), A, n, a.meta.n_rows, lo, hi)) {
+                                win.put_for((int)owner[j] - (int)lane, w[j], (uint32_t)lo, (uint32_t)hi);
+                                ftrue[j] = 1u; fhit[j] = hi >= lo; fnl[j] = lo < 0; fnh[j] = hi < 0;
+                            } else {
+                                fredo[j] = 1u;
+                            }
+                        }
+                }
+#pragma unroll
+                for (int j = 0; j < IPL; ++j) {
+                    // the pairs of one owner are neighbours in the list: combine their bits before touching its masks
+                    const uint32_t peers = __match_any_sync(FULL, on[j] ? owner[j] : 32u);
+                    const uint32_t bit = 1u << w[j];
+                    const bool lead = on[j] && lane == (uint32_t)(__ffs(peers) - 1);
+                    uint32_t* const om = wm + ((int)owner[j] - (int)lane);
+                    uint32_t v = __reduce_or_sync(peers, fhit[j] ? bit : 0u);
+                    if (lead && v) atomicOr(om + WM_HIT * SELECT_THREADS, v);
+                    if (METHOD == GSM_METHOD_RMI) {
+                        v = __reduce_or_sync(peers, ftrue[j] ? bit : 0u);
+                        if (lead && v) atomicOr(om + WM_TRUE * SELECT_THREADS, v);
+                        v = __reduce_or_sync(peers, fredo[j] ? bit : 0u);
+                        if (lead && v) atomicOr(om + WM_REDO * SELECT_THREADS, v);
+                        if (__any_sync(FULL, (fnl[j] | fnh[j]) != 0u)) {              // negative rows: rare
+                            v = __reduce_or_sync(peers, fnl[j] ? bit : 0u);
+                            if (lead && v) atomicOr(om + WM_NEG_LO * SELECT_THREADS, v);
+                            v = __reduce_or_sync(peers, fnh[j] ? bit : 0u);
+                            if (lead && v) atomicOr(om + WM_NEG_HI * SELECT_THREADS, v);
+                        }
                     }
                 }
             }
@@ -1045,13 +1089,28 @@ int resident_grid(Kern kern, int threads, size_t smem, int cap, int* blocks) {
     return GSM_OK;
 }
 
-template <int METHOD, int ARITH, int MB>
-int launch_seeded(const SelectArgs& se, size_t win_bytes, int cap, cudaStream_t stream) {
+template <int METHOD, int ARITH, int MB, int OPT>
+int launch_seeded1(const SelectArgs& se, int cap, cudaStream_t stream) {
     int grid = cap;
-    const int st = resident_grid(k_select_seeded<METHOD, ARITH, MB>, SELECT_THREADS, win_bytes, cap, &grid);
+    const size_t smem = select_smem_bytes(se.K, (OPT & 1) != 0);          // at most 52 KB (K <= 32)
+    if (smem > 48u * 1024u) GSM_CUDA(cudaFuncSetAttribute(k_select_seeded<METHOD, ARITH, MB, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int st = resident_grid(k_select_seeded<METHOD, ARITH, MB, OPT>, SELECT_THREADS, smem, cap, &grid);
     if (st) return st;
-    k_select_seeded<METHOD, ARITH, MB><<<grid, SELECT_THREADS, win_bytes, stream>>>(se);
+    k_select_seeded<METHOD, ARITH, MB, OPT><<<grid, SELECT_THREADS, smem, stream>>>(se);
     return GSM_OK;
+}
+// A/B switches (tools/sweep_ab.py): GSM_SELECT_BLOCKS = 6 | 7 | 8 resident blocks per SM the registers are allocated for,
+// GSM_SELECT_OPT bit 0 = match-list pairs in shared memory, bit 1 = two (thread, window) pairs per lane and trip
+template <int METHOD, int ARITH>
+int launch_seeded(const SelectArgs& se, int cap, cudaStream_t stream) {
+    static const int mb = getenv("GSM_SELECT_BLOCKS") ? atoi(getenv("GSM_SELECT_BLOCKS")) : SELECT_DEFAULT_BLOCKS;
+    static const int opt = getenv("GSM_SELECT_OPT") ? atoi(getenv("GSM_SELECT_OPT")) : SELECT_DEFAULT_OPT;
+#define GSM_SEL_CASE(M, O) if (mb == M && opt == O) return launch_seeded1<METHOD, ARITH, M, O>(se, cap, stream);
+    GSM_SEL_CASE(6, 0) GSM_SEL_CASE(6, 1) GSM_SEL_CASE(6, 2) GSM_SEL_CASE(6, 3)
+    GSM_SEL_CASE(7, 0) GSM_SEL_CASE(7, 1) GSM_SEL_CASE(7, 2) GSM_SEL_CASE(7, 3)
+    GSM_SEL_CASE(8, 0) GSM_SEL_CASE(8, 1) GSM_SEL_CASE(8, 2) GSM_SEL_CASE(8, 3)
+#undef GSM_SEL_CASE
+    return fail(GSM_E_INVALID, "GSM_SELECT_BLOCKS must be 6..8 and GSM_SELECT_OPT 0..3");
 }
 
 }  // namespace
@@ -1342,24 +1401,11 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
         if ((st = resident_grid(k_select<GSM_METHOD_BWA>, SELECT_THREADS, 0, lb, &grid))) return st;
         k_select<GSM_METHOD_BWA><<<grid, SELECT_THREADS, 0, stream>>>(se);
     } else {
-        static const int sel_blocks = getenv("GSM_SELECT_BLOCKS") ? atoi(getenv("GSM_SELECT_BLOCKS")) : 8;   // A/B: 6, 7
         const bool arith = rm.n_none != 0u && se.seed_K != 0u && se.seed_K <= K;       // lookups from the seed table: no probes
-        const size_t win_bytes = select_smem_bytes(K);                                  // at most 44 KB (K <= 32)
-        if (method == GSM_METHOD_LUT) {
-            if (sel_blocks == 6) st = launch_seeded<GSM_METHOD_LUT, 0, 6>(se, win_bytes, lb, stream);
-            else if (sel_blocks == 7) st = launch_seeded<GSM_METHOD_LUT, 0, 7>(se, win_bytes, lb, stream);
-            else st = launch_seeded<GSM_METHOD_LUT, 0, 8>(se, win_bytes, lb, stream);
-        } else if (se.rmi_bounds) {
-            if (sel_blocks == 6) st = launch_seeded<GSM_METHOD_RMI, 2, 6>(se, win_bytes, lb, stream);
-            else if (sel_blocks == 7) st = launch_seeded<GSM_METHOD_RMI, 2, 7>(se, win_bytes, lb, stream);
-            else st = launch_seeded<GSM_METHOD_RMI, 2, 8>(se, win_bytes, lb, stream);
-        } else if (arith) {
-            if (sel_blocks == 6) st = launch_seeded<GSM_METHOD_RMI, 1, 6>(se, win_bytes, lb, stream);
-            else if (sel_blocks == 7) st = launch_seeded<GSM_METHOD_RMI, 1, 7>(se, win_bytes, lb, stream);
-            else st = launch_seeded<GSM_METHOD_RMI, 1, 8>(se, win_bytes, lb, stream);
-        } else {
-            st = launch_seeded<GSM_METHOD_RMI, 0, 8>(se, win_bytes, lb, stream);
-        }
+        if (method == GSM_METHOD_LUT) st = launch_seeded<GSM_METHOD_LUT, 0>(se, lb, stream);
+        else if (se.rmi_bounds) st = launch_seeded<GSM_METHOD_RMI, 2>(se, lb, stream);
+        else if (arith) st = launch_seeded<GSM_METHOD_RMI, 1>(se, lb, stream);
+        else st = launch_seeded1<GSM_METHOD_RMI, 0, 8, 0>(se, lb, stream);
         if (st) return st;
     }
     GSM_CUDA(cudaGetLastError());

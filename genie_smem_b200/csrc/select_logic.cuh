@@ -73,6 +73,23 @@ GSM_HD double rmi_predict(const RmiModel& m, uint64_t code) {
     return p;
 }
 
+// rmi_predict for N keys at once, level by level: the N chains of dependent parameter loads travel together
+template <int N>
+GSM_HD void rmi_predict_n(const RmiModel& m, const uint64_t* code, double* p) {
+    uint32_t model[N];
+    for (int j = 0; j < N; ++j) { model[j] = 0; p[j] = 0.0; }
+    for (uint32_t lv = 0; lv < m.n_levels; ++lv) {
+        const uint32_t scale = (lv + 1 < m.n_levels) ? m.level_size[lv + 1] : 1u;
+        for (int j = 0; j < N; ++j) {
+            const uint32_t k = m.level_off[lv] + model[j];
+            p[j] = mul_add_nofma((double)code[j], m.coef[(size_t)k * m.stride], m.intercept[(size_t)k * m.stride]);
+            if (!(p[j] >= 1.0)) model[j] = 0;
+            else if (p[j] >= (double)scale) model[j] = scale - 1;
+            else model[j] = (uint32_t)p[j];
+        }
+    }
+}
+
 // Table access for the last-mile search.  Probe(row, s, code64): s = suffix_array[row] (1-based) and
 // code64 = the MSB-first code of the 32 bases at text position s-1 (zero-padded past the end), either
 // from the suffix array + packed text (two dependent fetches) or from a precomputed 16-byte probe
@@ -372,11 +389,11 @@ struct RmiGallop : RmiCommon {                 // phase A: RMI_LUT.exponential_s
     uint32_t start = 0, win = 1, dir = 0, r = 0, lower = 0, upper = 0;
     bool busy = false, hazard = false, have_lower = false, have_upper = false;
     // int(prediction) when it is a row of the table, else -1 (the literal search wraps or raises there)
-    GSM_HD static int64_t predicted_row(const RmiModel& m, uint64_t code, uint32_t rows) {
-        const double pred = rmi_predict(m, code);
+    GSM_HD static int64_t row_of(double pred, uint32_t rows) {
         if (!(pred > -1.0 && pred < (double)rows)) return -1;
         return (int64_t)pred;                                   // int() truncates toward zero (RMI_LUT.py:72)
     }
+    GSM_HD static int64_t predicted_row(const RmiModel& m, uint64_t code, uint32_t rows) { return row_of(rmi_predict(m, code), rows); }
     GSM_HD void begin(const RmiModel& m, uint64_t code, int64_t row0, uint32_t rows, int64_t bases) {
         q = code; K = m.K; n_rows = rows; n_bases = bases;
         have_lower = have_upper = false; dir = 0; win = 1;
