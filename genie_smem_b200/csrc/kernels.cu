@@ -77,6 +77,8 @@ struct SelectArgs {
     uint32_t* rec_cnt;
     uint8_t* read_status;
     unsigned long long* counters;
+    uint4* fix;                 // deferred explicit searches {read, record ordinal, start | end << 16, 0} (k_resolve_lazy): the tail of the record pool
+    unsigned long long fix_cap;
 };
 
 // 16-byte probe record {s, code64 hi, code64 lo, 0}: one fetch per get_ref_seq (RMI_LUT.py:89-92)
@@ -88,6 +90,8 @@ struct TableProbe {
         code64 = ((uint64_t)v.y << 32) | (uint64_t)v.z;
     }
 };
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int METHOD>
 struct DevSelCtx {
@@ -103,15 +107,7 @@ struct DevSelCtx {
     bool overflow;        // more records than slots: counted, not stored
     // bit 31 of mem_cnt: the sweep stored this list in ascending order and field by field (n start|end words, n lo, n count, ...)
     bool soa;
-    // k_select_seeded: the (start, end) pairs of a short ordered list of a read of up to 255 bases, one byte each, in the
-    // thread's column of a shared-memory table (entry k at sec[k * SELECT_THREADS]); every lookup of the frame machine into
-    // the match list then stays on the SM
-    const uint16_t* sec = nullptr;
-    bool cached = false;
-    __device__ __forceinline__ uint32_t se(uint32_t k) const {
-        if (cached) { const uint32_t v = sec[k * SELECT_THREADS]; return (v & 0xFFu) | ((v >> 8) << 16); }
-        return soa ? reinterpret_cast<const uint32_t*>(mems)[k] : mems[k].x;
-    }
+    __device__ __forceinline__ uint32_t se(uint32_t k) const { return soa ? reinterpret_cast<const uint32_t*>(mems)[k] : mems[k].x; }
 
     __device__ __forceinline__ MemEntry mem(uint32_t k) const {
         if (soa) {
@@ -277,10 +273,8 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
 constexpr int WIN_STRIDE = SELECT_THREADS + 1;
 constexpr int WIN_MASKS = 5;                               // per thread: hit, true, redo, lo negative, hi negative
 enum : int { WM_HIT = 0, WM_TRUE = 1, WM_REDO = 2, WM_NEG_LO = 3, WM_NEG_HI = 4 };
-constexpr int SEC_ENTRIES = 32;                            // longest match list kept in shared memory (= the sweep's ordered lists)
-__host__ __device__ constexpr size_t select_smem_bytes(uint32_t K, bool se_cache) {
-    return (2ull * K * WIN_STRIDE + (size_t)WIN_MASKS * SELECT_THREADS) * sizeof(uint32_t) + (size_t)K * SELECT_THREADS * sizeof(uint16_t) +
-           (se_cache ? (size_t)SEC_ENTRIES * SELECT_THREADS * sizeof(uint16_t) : 0);
+__host__ __device__ constexpr size_t select_smem_bytes(uint32_t K) {
+    return (2ull * K * WIN_STRIDE + (size_t)WIN_MASKS * SELECT_THREADS) * sizeof(uint32_t) + (size_t)K * SELECT_THREADS * sizeof(uint16_t);
 }
 template <int METHOD>
 struct SmemWindows {
@@ -412,10 +406,9 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __gr
     uint16_t* const items = reinterpret_cast<uint16_t*>(sel_smem + 2u * a.K * WIN_STRIDE + WIN_MASKS * SELECT_THREADS)
                             + (threadIdx.x >> 5) * (a.K * 32u);                                // this warp's (lane, window) pairs of a round
     const uint32_t lane = threadIdx.x & 31u;
-    constexpr bool SE_CACHE = (OPT & 1) != 0;              // match-list (start, end) pairs in shared memory
-    constexpr int IPL = (OPT & 2) ? 2 : 1;                 // (thread, window) pairs per lane and trip of pass 1
-    uint16_t* const sec = reinterpret_cast<uint16_t*>(sel_smem + 2u * a.K * WIN_STRIDE + WIN_MASKS * SELECT_THREADS) + a.K * SELECT_THREADS + threadIdx.x;
-    if (SE_CACHE) c.sec = sec;
+    constexpr int IPL = (OPT & 1) ? 2 : 1;                 // (thread, window) pairs per lane and trip of pass 1
+    constexpr bool PREFETCH = (OPT & 2) != 0;              // the thread's next read is brought into the L2 while this one runs
+    uint32_t nx_chunk = 0, nx_off = 0;                     // PREFETCH: where the next read's bases and match list are
 
     auto close_read = [&](uint8_t status) {
         if (c.close(status, direct)) { st = typename Sel::Seeded(); return; }      // overflowed its staging slots: run it again in place
@@ -432,14 +425,16 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __gr
             c.out = stage; c.cap = a.stage_stride;
             c.soa = (mc >> 31) != 0u;
             if (!c.soa) order_segments(c.mems, c.n_mems);                      // bit 31: the sweep already ordered the list
-            c.cached = false;
             st = typename Sel::Seeded();
-            if (c.L < c.K) { close_read(GSM_READ_TOO_SHORT); continue; }
-            if (SE_CACHE && c.soa && c.L <= 255u && c.n_mems <= (uint32_t)SEC_ENTRIES) {
-                const uint32_t* seg = reinterpret_cast<const uint32_t*>(c.mems);
-                for (uint32_t k = 0; k < c.n_mems; ++k) { const uint32_t v = seg[k]; sec[k * SELECT_THREADS] = (uint16_t)((v & 0xFFu) | ((v >> 16) << 8)); }
-                c.cached = true;
+            if (PREFETCH && rid + nthreads < a.n_reads) {
+                // the next read's offsets: loaded now, used (prefetch_next) once this read's first round is over, by when
+                // they have arrived; its length and match count are pulled into the L2 for its own open_reads
+                nx_chunk = __ldg(a.chunk_off + rid + nthreads);
+                nx_off = a.mem_off[rid + nthreads];
+                prefetch_l2(a.mem_cnt + rid + nthreads);
+                prefetch_l2(a.len + rid + nthreads);
             }
+            if (c.L < c.K) { close_read(GSM_READ_TOO_SHORT); continue; }
             have = true;
         }
     };
@@ -646,6 +641,15 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __gr
         iv_t rlo = 0, rhi = 0;
         uint32_t slo = 0, scnt = 0, sp = 0;
         bool search = run && w.valid() && Sel::resolve(c, w, win, rlo, rhi);
+        if (search) {
+            // a backward search of up to |SMEM| dependent bucket fetches would hold the other 31 reads of the warp up: the
+            // record goes out with its rows open and k_resolve_lazy (one thread per search) fills them in afterwards
+            const unsigned long long q = atomicAdd(&a.counters[4], 1ull);
+            if (q < a.fix_cap) {
+                a.fix[q] = make_uint4(c.rid, c.n_rec, w.ij, 0u);
+                search = false;
+            }
+        }
         if (search) c.interval_begin(w.i(), w.j(), slo, scnt, sp);
         while (__any_sync(FULL, search)) {
             if (search) {
@@ -654,10 +658,34 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __gr
             }
         }
         if (have) {
+            if (PREFETCH && st.first && rid + nthreads < a.n_reads) {          // once per read
+                prefetch_l2(a.reads + (size_t)nx_chunk * 4);
+                prefetch_l2(a.mem_pool + nx_off);
+                prefetch_l2(a.mem_pool + nx_off + 8);
+            }
             if (c.raised) close_read(GSM_READ_REF_RAISES);
             else Sel::round_commit(c, st, w, rlo, rhi);
         }
         __syncwarp();
+    }
+}
+
+// The explicit backward searches k_select_seeded deferred (winners whose interval is neither a seed tuple nor on the
+// match list), one thread per search: rows of record `ordinal` of read `rid` <- SA interval of q[i:j).  A read that was
+// closed without records (the reference raises, pool overflow) has fewer records than the ordinal says: skipped.
+template <int METHOD>
+__global__ void __launch_bounds__(SELECT_THREADS) k_resolve_lazy(const __grid_constant__ SelectArgs a) {
+    const unsigned long long queued = a.counters[4];
+    const unsigned long long n = queued < a.fix_cap ? queued : a.fix_cap;
+    for (unsigned long long q = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 f = a.fix[q];
+        const uint32_t rid = f.x;
+        if (f.y >= a.rec_cnt[rid]) continue;
+        DevSelCtx<METHOD> c{a, a.reads + (size_t)__ldg(a.chunk_off + rid) * 4, nullptr, nullptr, 0u, __ldg(a.len + rid), a.K, 0u, 0u, rid, 0u, false, false, false};
+        uint32_t lo, cnt;
+        c.interval(f.z & 0xFFFFu, f.z >> 16, lo, cnt);
+        uint4* r = a.rec_tmp + a.rec_tmp_off[rid] + f.y;
+        r->z = lo; r->w = lo + cnt - 1u;
     }
 }
 
@@ -1092,15 +1120,14 @@ int resident_grid(Kern kern, int threads, size_t smem, int cap, int* blocks) {
 template <int METHOD, int ARITH, int MB, int OPT>
 int launch_seeded1(const SelectArgs& se, int cap, cudaStream_t stream) {
     int grid = cap;
-    const size_t smem = select_smem_bytes(se.K, (OPT & 1) != 0);          // at most 52 KB (K <= 32)
-    if (smem > 48u * 1024u) GSM_CUDA(cudaFuncSetAttribute(k_select_seeded<METHOD, ARITH, MB, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = select_smem_bytes(se.K);                          // at most 44 KB (K <= 32)
     const int st = resident_grid(k_select_seeded<METHOD, ARITH, MB, OPT>, SELECT_THREADS, smem, cap, &grid);
     if (st) return st;
     k_select_seeded<METHOD, ARITH, MB, OPT><<<grid, SELECT_THREADS, smem, stream>>>(se);
     return GSM_OK;
 }
 // A/B switches (tools/sweep_ab.py): GSM_SELECT_BLOCKS = 6 | 7 | 8 resident blocks per SM the registers are allocated for,
-// GSM_SELECT_OPT bit 0 = match-list pairs in shared memory, bit 1 = two (thread, window) pairs per lane and trip
+// GSM_SELECT_OPT bit 0 = two (thread, window) pairs per lane and trip of pass 1, bit 1 = prefetch of the thread's next read
 template <int METHOD, int ARITH>
 int launch_seeded(const SelectArgs& se, int cap, cudaStream_t stream) {
     static const int mb = getenv("GSM_SELECT_BLOCKS") ? atoi(getenv("GSM_SELECT_BLOCKS")) : SELECT_DEFAULT_BLOCKS;
@@ -1395,7 +1422,14 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
     se.mem_pool = (uint4*)ws->mem_pool; se.mem_off = ws->mem_off; se.mem_cnt = ws->mem_cnt; se.stage = (uint4*)ws->quad_scratch; se.stage_stride = select_stage_stride(rd->max_len);
     se.rec_tmp = (uint4*)ws->rec_tmp; se.rec_cap = ws->rec_cap; se.rec_tmp_off = ws->rec_tmp_off; se.rec_cnt = ws->rec_cnt;
     se.read_status = ws->read_status; se.counters = (unsigned long long*)ws->counters;
+    se.fix = nullptr; se.fix_cap = 0;
+    if (method != GSM_METHOD_BWA) {           // deferred explicit searches queue in the last eighth of the record pool (at most one per read)
+        const uint64_t reserve = ws->rec_cap / 8 < rd->n_reads ? ws->rec_cap / 8 : rd->n_reads;
+        se.rec_cap = ws->rec_cap - reserve;
+        se.fix = (uint4*)ws->rec_tmp + se.rec_cap; se.fix_cap = reserve;
+    }
     GSM_CUDA(cudaMemsetAsync((unsigned long long*)ws->counters + 1, 0, sizeof(uint64_t), stream));
+    GSM_CUDA(cudaMemsetAsync((unsigned long long*)ws->counters + 4, 0, sizeof(uint64_t), stream));
     int grid = lb;
     if (method == GSM_METHOD_BWA) {
         if ((st = resident_grid(k_select<GSM_METHOD_BWA>, SELECT_THREADS, 0, lb, &grid))) return st;
@@ -1407,6 +1441,11 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
         else if (arith) st = launch_seeded<GSM_METHOD_RMI, 1>(se, lb, stream);
         else st = launch_seeded1<GSM_METHOD_RMI, 0, 8, 0>(se, lb, stream);
         if (st) return st;
+        int dev = 0, sms = 148;
+        GSM_CUDA(cudaGetDevice(&dev));
+        GSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (method == GSM_METHOD_LUT) k_resolve_lazy<GSM_METHOD_LUT><<<sms * 8, SELECT_THREADS, 0, stream>>>(se);
+        else k_resolve_lazy<GSM_METHOD_RMI><<<sms * 8, SELECT_THREADS, 0, stream>>>(se);
     }
     GSM_CUDA(cudaGetLastError());
     const uint64_t n_tiles = (rd->n_reads + SCAN_TILE - 1) / SCAN_TILE;

@@ -359,6 +359,7 @@ struct DevSweepCtx1 {
     // them one by one behind dependent L2 loads.  Lists of up to 32 matches are put in ascending order on the way -- the
     // sweep emits every sweep's matches longest end first -- stored field by field, and flagged (bit 31 of mem_cnt) so
     // that the selection kernels neither reorder them nor read them as 16-byte entries.  Called by the whole warp.
+    static constexpr uint32_t SOA_MAX = 64;          // lists up to this long are handed over ordered and field by field
     __device__ __forceinline__ void flush_finished() {
         constexpr uint32_t FULLM = 0xFFFFFFFFu;
         const uint32_t lane = threadIdx.x & 31u;
@@ -387,22 +388,34 @@ struct DevSweepCtx1 {
             const unsigned long long off = __shfl_sync(FULLM, my_off, src);
             const uint4* sp = reinterpret_cast<const uint4*>((uintptr_t)__shfl_sync(FULLM, st, src));
             if (!fits) continue;
-            if (n <= 32u) {
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (lane < n) v = __ldcg(sp + lane);
-                // segment = run of equal sweep ordinals (v.w), emitted in descending order of the end: reverse each run
-                const uint32_t prev = __shfl_up_sync(FULLM, v.w, 1);
-                const uint32_t heads = __ballot_sync(FULLM, lane < n && (lane == 0u || v.w != prev));
-                if (lane < n) {
-                    const uint32_t upto = heads & (0xFFFFFFFFu >> (31u - lane));          // heads at or below this lane
-                    const uint32_t s0 = 31u - (uint32_t)__clz((int)upto);
-                    const uint32_t above = lane == 31u ? 0u : heads & (0xFFFFFFFFu << (lane + 1u));
-                    const uint32_t s1 = above ? (uint32_t)__ffs((int)above) - 1u : n;
-                    // short lists are stored field by field (n start|end words, then n lo, n count, n sweep ordinals): the
-                    // selection kernels binary-search starts and ends, and this way those probes share one or two sectors
-                    uint32_t* seg = reinterpret_cast<uint32_t*>(a.mem_pool + off);
-                    const uint32_t d = s0 + (s1 - 1u - lane);
-                    seg[d] = v.x; seg[n + d] = v.y; seg[2u * n + d] = v.z; seg[3u * n + d] = v.w;
+            if (n <= SOA_MAX) {
+                // entry x of the list sits in lane x & 31 (x < 32: v0, else v1).  A segment = run of equal sweep ordinals
+                // (.w), emitted in descending order of the end: reverse each run.  Short lists are stored field by field
+                // (n start|end words, then n lo, n count, n sweep ordinals): the selection kernels look starts and ends up
+                // over and over, and this way those lookups share one or two sectors
+                uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+                if (lane < n) v0 = __ldcg(sp + lane);
+                if (lane + 32u < n) v1 = __ldcg(sp + lane + 32u);
+                const uint32_t prev0 = __shfl_up_sync(FULLM, v0.w, 1);
+                const uint32_t last0 = __shfl_sync(FULLM, v0.w, 31);
+                uint32_t prev1 = __shfl_up_sync(FULLM, v1.w, 1);
+                if (lane == 0u) prev1 = last0;
+                const unsigned long long heads =
+                    (unsigned long long)__ballot_sync(FULLM, lane < n && (lane == 0u || v0.w != prev0)) |
+                    ((unsigned long long)__ballot_sync(FULLM, lane + 32u < n && v1.w != prev1) << 32);
+                uint32_t* seg = reinterpret_cast<uint32_t*>(a.mem_pool + off);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t x = lane + 32u * half;
+                    if (x < n) {
+                        const uint4 v = half ? v1 : v0;
+                        const unsigned long long upto = heads & (~0ull >> (63u - x));              // heads at or below this entry
+                        const uint32_t s0 = 63u - (uint32_t)__clzll((long long)upto);
+                        const unsigned long long above = x == 63u ? 0ull : heads & (~0ull << (x + 1u));
+                        const uint32_t s1 = above ? (uint32_t)__ffsll((long long)above) - 1u : n;
+                        const uint32_t d = s0 + (s1 - 1u - x);
+                        seg[d] = v.x; seg[n + d] = v.y; seg[2u * n + d] = v.z; seg[3u * n + d] = v.w;
+                    }
                 }
             } else {
                 for (uint32_t k = lane; k < n; k += 32u) a.mem_pool[off + k] = __ldcg(sp + k);
@@ -410,7 +423,7 @@ struct DevSweepCtx1 {
         }
         if (fin_n != NO_FIN) {
             a.mem_off[fin_rid] = fits ? (uint32_t)my_off : 0u;
-            a.mem_cnt[fin_rid] = fits ? (fin_n | (fin_n <= 32u ? 0x80000000u : 0u)) : 0u;
+            a.mem_cnt[fin_rid] = fits ? (fin_n | (fin_n <= SOA_MAX ? 0x80000000u : 0u)) : 0u;
             fin_n = NO_FIN;
         }
     }

@@ -1,7 +1,8 @@
 #!/bin/bash
-# A/B harness under selection-kernel variants (GSM_SELECT_BLOCKS x GSM_SELECT_OPT); records must keep their SHA
+# parity tests, then the A/B harness under selection-kernel variants (GSM_SELECT_BLOCKS x GSM_SELECT_OPT); records must keep their SHA
 T=${1:-r2s}
 mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest exit=$?"; tail -4 gpurun_out/${T}_pytest.log
 ab() { n=$1; shift; env "$@" python tools/sweep_ab.py --tag "$*" > gpurun_out/${T}_ab_$n.json 2> gpurun_out/${T}_ab_$n.err; echo "[$*] exit=$?"; python - gpurun_out/${T}_ab_$n.json <<'PY'
 import json,sys
 d=json.load(open(sys.argv[1]))
