@@ -359,7 +359,7 @@ def main():
     rmi = None
     if not args.skip_rmi:
         t0 = time.time()
-        rmi = train_rmi(index, RMI_K, args.experts, dev, probe_table=False)
+        rmi = train_rmi(index, RMI_K, args.experts, dev, probe_table=False, bounds_table=True)
         log(f"[rank {rank}] RMI training in {time.time()-t0:.1f}s (max |prediction error| on the training sample: {rmi.max_err:.0f} rows)")
     torch.cuda.synchronize()
     log(f"[rank {rank}] setup {time.time()-t_setup:.1f}s, index {index.bytes()/1e6:.0f} MB on device")
@@ -493,10 +493,20 @@ def main():
         P = 2 * int(np.ceil(np.log2(2 * rmi.max_err + 2)))
         method_leg("rmi", g.METHOD_RMI, max(2, args.steps // 2), {"rmi": rmi}, RMI_K, 64 * P,
                    {"experts": list(args.experts), "max_abs_prediction_error_rows": rmi.max_err, "probes_P": P,
-                    "lookup": "predict + seed-table bounds + arithmetic replay of the error-bounded search (no probes); literal search on hazards"})
+                    "lookup": ("predict + true bounds from the dense k-mer bounds table (one fetch)" if rmi.bounds is not None else
+                               "predict + seed-table bounds (one fetch + K - seed_K backward steps)") +
+                              " + arithmetic replay of the error-bounded search (no probes); literal search on hazards"})
         st = engine.read_status[:n_reads]
         methods["rmi"]["reads_where_reference_raises"] = int((st == g.READ_REF_RAISES).sum().item())
         if extras and world == 1:
+            if rmi.bounds is not None:
+                # the same lookups with the true bounds taken from the sweep's seed table + K - seed_K backward steps
+                rmi.drop_bounds_table()
+                torch.cuda.empty_cache()
+                engine.sweep(batch)
+                methods["rmi"]["seed_table_lookup_select_ms"] = round(timed(lambda: engine.select(g.METHOD_RMI, batch, rmi=rmi), 1, 1), 3)
+                engine.check_overflow()
+                snaps["rmi_seed_table"] = snapshot(n_par)
             # the probe-based error-bounded search (round-1 path: 16-byte {SA, 32-mer} probe records): same records, more fetches
             rmi.build_probe_table(index)
             seed_keep = (index.seed_table, index.seed_K)
@@ -540,6 +550,7 @@ def main():
                                        "full_sa": round(index.sa.numel() * 4 / 1e6), "text": round(index.text.numel() * 4 / 1e6),
                                        "seed_table": round(index.seed_table.numel() * 4 / 1e6) if index.seed_table is not None else 0,
                                        "lut": round(lut.numel() * 4 / 1e6), "rmi_params": round(rmi.params.numel() * 8 / 1e6) if rmi is not None else 0,
+                                       "rmi_bounds_table": round((8 << (2 * RMI_K)) / 1e6) if rmi is not None else 0,
                                        "rmi_probe_table_optional": round(index.n_rows * 16 / 1e6)},
                   "note": "one thread per row, LF-walk to the next sampled row (k_locate_sampled); BWA/LUT-SMEM + locate need buckets + sampled SA "
                           "only; the full SA (and text) are kept for RMI-SMEM's literal fallback"}
@@ -636,6 +647,8 @@ def main():
             parity["rmi"], parity["ref_raises"] = compare_with_oracle(reads_head, snaps["rmi"], out, counts, n_par)
             if "rmi_probe" in snaps:
                 parity["rmi_probe_search"], _ = compare_with_oracle(reads_head, snaps["rmi_probe"], out, counts, n_par)
+            if "rmi_seed_table" in snaps:
+                parity["rmi_seed_table_lookup"], _ = compare_with_oracle(reads_head, snaps["rmi_seed_table"], out, counts, n_par)
             if cpu_baseline:
                 cpu_baseline["rmi_reads_per_s"] = round(v3, 1)
         if cpu_baseline:
@@ -656,7 +669,7 @@ def main():
             out["gather_transport"] = ("peer mapping (CUDA IPC): each rank's ordered-write kernel stores into rank 0's buffer" if gat.fused else
                                        f"NCCL send/recv per batch (peer mapping unavailable: {gat.fallback_reason})")
         emit_result(out)
-    bad = rank == 0 and parity is not None and any(parity.get(k, 0) for k in ("bwa", "lut", "rmi", "rmi_probe_search"))
+    bad = rank == 0 and parity is not None and any(parity.get(k, 0) for k in ("bwa", "lut", "rmi", "rmi_probe_search", "rmi_seed_table_lookup"))
     if world > 1:
         dist.destroy_process_group()
     if bad:
@@ -741,11 +754,12 @@ def python_port_baseline(budget_s=6.0):
         return {"unavailable": str(e)}
 
 
-def train_rmi(index, K, experts, dev, max_keys=8_000_000, probe_table=True):
+def train_rmi(index, K, experts, dev, max_keys=8_000_000, probe_table=True, bounds_table=False):
     """RMI over the k-mer -> row keys of this index (reference RMI_LUT.py:36-50).  Training set = a strided sample of the
     (suffix array row, k-mer) pairs read from the suffix array + packed text on the device; model quality only changes the
     last-mile length, never the result.  The fit is the vectorised host trainer.  probe_table: also build the 16-byte
-    {SA value, 32-mer} probe records the probe-based search uses (not needed by the seed-table lookup path)."""
+    {SA value, 32-mer} probe records the probe-based search uses (not needed by the seed-table lookup path).  bounds_table:
+    also the dense {first row >= k-mer, occurrences} table (4^K x 8 B) when K <= 16 and the device has room for it."""
     import torch
     import genie_smem_b200 as g
     n_rows = index.n_rows
@@ -768,6 +782,8 @@ def train_rmi(index, K, experts, dev, max_keys=8_000_000, probe_table=True):
     if probe_table:
         out.build_probe_table(index)
     out.build_none_rows(index)
+    if bounds_table and K <= 16 and torch.cuda.mem_get_info(index.device)[0] > (8 << (2 * K)) + (24 << 30):
+        out.build_bounds_table(index)
     return out
 
 

@@ -42,7 +42,8 @@ namespace gsm {
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr int SELECT_THREADS = 128;
 constexpr int SELECT_DEFAULT_BLOCKS = 7;     // k_select_seeded: resident blocks per SM / variant when the environment says nothing
-constexpr int SELECT_DEFAULT_OPT = 0;
+constexpr int SELECT_DEFAULT_OPT_LUT = 1;    // measured per method (tools/sweep_ab.py, profiles/r02_notes.md)
+constexpr int SELECT_DEFAULT_OPT_RMI = 3;
 constexpr uint32_t SELECT_STAGE = 64;   // staged records per selection thread; reads emitting more are run twice (see DevSelCtx::close)
 
 // ===================================================================================== select
@@ -1131,7 +1132,7 @@ int launch_seeded1(const SelectArgs& se, int cap, cudaStream_t stream) {
 template <int METHOD, int ARITH>
 int launch_seeded(const SelectArgs& se, int cap, cudaStream_t stream) {
     static const int mb = getenv("GSM_SELECT_BLOCKS") ? atoi(getenv("GSM_SELECT_BLOCKS")) : SELECT_DEFAULT_BLOCKS;
-    static const int opt = getenv("GSM_SELECT_OPT") ? atoi(getenv("GSM_SELECT_OPT")) : SELECT_DEFAULT_OPT;
+    static const int opt = getenv("GSM_SELECT_OPT") ? atoi(getenv("GSM_SELECT_OPT")) : (METHOD == GSM_METHOD_LUT ? SELECT_DEFAULT_OPT_LUT : SELECT_DEFAULT_OPT_RMI);
 #define GSM_SEL_CASE(M, O) if (mb == M && opt == O) return launch_seeded1<METHOD, ARITH, M, O>(se, cap, stream);
     GSM_SEL_CASE(6, 0) GSM_SEL_CASE(6, 1) GSM_SEL_CASE(6, 2) GSM_SEL_CASE(6, 3)
     GSM_SEL_CASE(7, 0) GSM_SEL_CASE(7, 1) GSM_SEL_CASE(7, 2) GSM_SEL_CASE(7, 3)

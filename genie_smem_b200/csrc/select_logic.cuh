@@ -514,23 +514,58 @@ GSM_HD bool rmi_none_in_range(const RmiModel& m, uint32_t a, uint32_t b) {
 // bracket end stays at its default, both binary searches of the literal algorithm return the exact bounds (see
 // RmiGallop): lo = A, hi = B - 1 (hi = lo - 1 <=> absent).  Otherwise: hazard, the caller runs the literal search.
 // row0 = RmiGallop::predicted_row.  Returns false on a hazard.
+// The two gallops have closed forms: going up from `start` the probes are start + 1, 2, 4, ..., the first one at or beyond
+// B ends the phase (or the table does: default upper end, hazard), and a probe fell below A iff the first one did; going
+// down likewise with the first power of two that exceeds start - A.
+GSM_HD uint32_t clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__clz((int)x);
+#else
+    return x ? (uint32_t)__builtin_clz(x) : 32u;
+#endif
+}
 GSM_HD bool rmi_arith_lookup(const RmiModel& m, int64_t row0, uint32_t A, uint32_t cnt, uint32_t n_rows, int64_t& lo, int64_t& hi) {
     if (row0 < 0) return false;                                   // prediction outside the table
     const uint32_t start = (uint32_t)row0, B = A + cnt;
+    bool have_lower = start < A;
+    uint32_t rmin = start, rmax = start;
+    if (start < B) {                                              // RMI_LUT.py:151-163: first w = 2^t with start + w >= B
+        const uint32_t d = B - start;
+        const uint64_t w = 1ull << (d == 1u ? 0u : 32u - clz32(d - 1u));
+        if (w >= (uint64_t)n_rows - start) return false;          // the table ends first: the upper end stays at its default
+        rmax = start + (uint32_t)w;
+        have_lower |= start + 1u < A;                             // the first (lowest) probe of the phase
+    }
+    if (!have_lower) {                                            // RMI_LUT.py:166-178: first w = 2^t with start - w < A
+        const uint32_t g = start - A;
+        const uint64_t w = 1ull << (g == 0u ? 0u : 32u - clz32(g));
+        if (w > start) return false;                              // row 0 comes first: the lower end stays at its default
+        rmin = start - (uint32_t)w;
+    }
+    if (rmi_none_in_range(m, rmin, rmax)) return false;           // a None row probed or inside the bracket
+    lo = (int64_t)A;
+    hi = (int64_t)B - 1;
+    return true;
+}
+
+// the same replay probe by probe (the loops of RMI_LUT.exponential_search on row numbers): what the closed form is tested against
+GSM_HD bool rmi_arith_lookup_loops(const RmiModel& m, int64_t row0, uint32_t A, uint32_t cnt, uint32_t n_rows, int64_t& lo, int64_t& hi) {
+    if (row0 < 0) return false;
+    const uint32_t start = (uint32_t)row0, B = A + cnt;
     bool have_lower = start < A, have_upper = start >= B;
     uint32_t rmin = start, rmax = start;
-    for (uint32_t w = 1; !have_upper && (uint64_t)start + w < n_rows && w != 0u; w <<= 1) {      // RMI_LUT.py:151-163
+    for (uint32_t w = 1; !have_upper && (uint64_t)start + w < n_rows && w != 0u; w <<= 1) {
         rmax = start + w;
         have_upper = rmax >= B;
         have_lower |= rmax < A;
     }
-    for (uint32_t w = 1; !have_lower && start >= w && w != 0u; w <<= 1) {                         // RMI_LUT.py:166-178
+    for (uint32_t w = 1; !have_lower && start >= w && w != 0u; w <<= 1) {
         rmin = start - w;
         have_lower = rmin < A;
         have_upper |= rmin >= B;
     }
-    if (!have_lower || !have_upper) return false;                 // a default bracket end
-    if (rmi_none_in_range(m, rmin, rmax)) return false;           // a None row probed or inside the bracket
+    if (!have_lower || !have_upper) return false;
+    if (rmi_none_in_range(m, rmin, rmax)) return false;
     lo = (int64_t)A;
     hi = (int64_t)B - 1;
     return true;

@@ -282,6 +282,38 @@ __device__ __forceinline__ bool lane_step(const uint4* __restrict__ fwd, const u
 // LONG = true : the bases are read from the packed batch in global memory (L1 / L2 hits: 4 bases per byte), shared
 //               memory only holds the candidate slots, so any length up to 65535 runs; the grid is sized so that the
 //               per-lane match / candidate staging (2 x max_len x 16 bytes) fits a fixed budget.
+// flush_finished for a list of 33..64 matches (one read in a dozen at 1 % substitutions): same ordered, field-by-field
+// hand-over with two entries per lane -- entry x sits in lane x & 31 (x < 32: v0, else v1).  Out of line: its registers
+// are not the sweep loop's.
+__device__ __noinline__ void hand_over_long(const uint4* sp, uint32_t n, uint4* dst) {
+    constexpr uint32_t FULLM = 0xFFFFFFFFu;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+    if (lane < n) v0 = __ldcg(sp + lane);
+    if (lane + 32u < n) v1 = __ldcg(sp + lane + 32u);
+    const uint32_t prev0 = __shfl_up_sync(FULLM, v0.w, 1);
+    const uint32_t last0 = __shfl_sync(FULLM, v0.w, 31);
+    uint32_t prev1 = __shfl_up_sync(FULLM, v1.w, 1);
+    if (lane == 0u) prev1 = last0;
+    const unsigned long long heads =
+        (unsigned long long)__ballot_sync(FULLM, lane < n && (lane == 0u || v0.w != prev0)) |
+        ((unsigned long long)__ballot_sync(FULLM, lane + 32u < n && v1.w != prev1) << 32);
+    uint32_t* seg = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t x = lane + 32u * half;
+        if (x < n) {
+            const uint4 v = half ? v1 : v0;
+            const unsigned long long upto = heads & (~0ull >> (63u - x));              // heads at or below this entry
+            const uint32_t s0 = 63u - (uint32_t)__clzll((long long)upto);
+            const unsigned long long above = x == 63u ? 0ull : heads & (~0ull << (x + 1u));
+            const uint32_t s1 = above ? (uint32_t)__ffsll((long long)above) - 1u : n;
+            const uint32_t d = s0 + (s1 - 1u - x);
+            seg[d] = v.x; seg[n + d] = v.y; seg[2u * n + d] = v.z; seg[3u * n + d] = v.w;
+        }
+    }
+}
+
 template <bool LONG, bool UNIQ>
 struct DevSweepCtx1 {
     const SweepArgs& a;
@@ -388,35 +420,26 @@ struct DevSweepCtx1 {
             const unsigned long long off = __shfl_sync(FULLM, my_off, src);
             const uint4* sp = reinterpret_cast<const uint4*>((uintptr_t)__shfl_sync(FULLM, st, src));
             if (!fits) continue;
-            if (n <= SOA_MAX) {
-                // entry x of the list sits in lane x & 31 (x < 32: v0, else v1).  A segment = run of equal sweep ordinals
-                // (.w), emitted in descending order of the end: reverse each run.  Short lists are stored field by field
-                // (n start|end words, then n lo, n count, n sweep ordinals): the selection kernels look starts and ends up
-                // over and over, and this way those lookups share one or two sectors
-                uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
-                if (lane < n) v0 = __ldcg(sp + lane);
-                if (lane + 32u < n) v1 = __ldcg(sp + lane + 32u);
-                const uint32_t prev0 = __shfl_up_sync(FULLM, v0.w, 1);
-                const uint32_t last0 = __shfl_sync(FULLM, v0.w, 31);
-                uint32_t prev1 = __shfl_up_sync(FULLM, v1.w, 1);
-                if (lane == 0u) prev1 = last0;
-                const unsigned long long heads =
-                    (unsigned long long)__ballot_sync(FULLM, lane < n && (lane == 0u || v0.w != prev0)) |
-                    ((unsigned long long)__ballot_sync(FULLM, lane + 32u < n && v1.w != prev1) << 32);
-                uint32_t* seg = reinterpret_cast<uint32_t*>(a.mem_pool + off);
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t x = lane + 32u * half;
-                    if (x < n) {
-                        const uint4 v = half ? v1 : v0;
-                        const unsigned long long upto = heads & (~0ull >> (63u - x));              // heads at or below this entry
-                        const uint32_t s0 = 63u - (uint32_t)__clzll((long long)upto);
-                        const unsigned long long above = x == 63u ? 0ull : heads & (~0ull << (x + 1u));
-                        const uint32_t s1 = above ? (uint32_t)__ffsll((long long)above) - 1u : n;
-                        const uint32_t d = s0 + (s1 - 1u - x);
-                        seg[d] = v.x; seg[n + d] = v.y; seg[2u * n + d] = v.z; seg[3u * n + d] = v.w;
-                    }
+            // Short lists are handed over in ascending order and stored field by field (n start|end words, then n lo, n count,
+            // n sweep ordinals): the selection kernels look starts and ends up over and over, and this way those lookups
+            // share one or two sectors.  A segment = run of equal sweep ordinals (.w), emitted in descending order of the
+            // end: each run is reversed on the way.
+            if (n <= 32u) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (lane < n) v = __ldcg(sp + lane);
+                const uint32_t prev = __shfl_up_sync(FULLM, v.w, 1);
+                const uint32_t heads = __ballot_sync(FULLM, lane < n && (lane == 0u || v.w != prev));
+                if (lane < n) {
+                    const uint32_t upto = heads & (0xFFFFFFFFu >> (31u - lane));          // heads at or below this lane
+                    const uint32_t s0 = 31u - (uint32_t)__clz((int)upto);
+                    const uint32_t above = lane == 31u ? 0u : heads & (0xFFFFFFFFu << (lane + 1u));
+                    const uint32_t s1 = above ? (uint32_t)__ffs((int)above) - 1u : n;
+                    uint32_t* seg = reinterpret_cast<uint32_t*>(a.mem_pool + off);
+                    const uint32_t d = s0 + (s1 - 1u - lane);
+                    seg[d] = v.x; seg[n + d] = v.y; seg[2u * n + d] = v.z; seg[3u * n + d] = v.w;
                 }
+            } else if (n <= SOA_MAX) {
+                hand_over_long(sp, n, a.mem_pool + off);
             } else {
                 for (uint32_t k = lane; k < n; k += 32u) a.mem_pool[off + k] = __ldcg(sp + k);
             }

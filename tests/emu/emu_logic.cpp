@@ -437,4 +437,31 @@ int emu_rmi_arith(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint3
     return 0;
 }
 
+// closed-form rmi_arith_lookup against the probe-by-probe loops on n random (start, A, cnt) triples of a table of n_rows
+// rows with the given None rows; returns the number of disagreements (outcome, bounds)
+uint64_t emu_rmi_arith_fuzz(uint32_t n_rows, uint32_t n_none, const uint32_t* none_rows, uint64_t n, uint64_t seed) {
+    RmiModel m; memset(&m, 0, sizeof(m));
+    rmi_set_none_rows(m, none_rows, n_none, n_rows);
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1, bad = 0;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    for (uint64_t t = 0; t < n; ++t) {
+        const uint32_t mode = (uint32_t)(rnd() % 6);
+        uint32_t A = (uint32_t)(rnd() % ((uint64_t)n_rows + 1));
+        uint32_t cnt = (uint32_t)(rnd() % 5 == 0 ? 0 : rnd() % ((uint64_t)n_rows - A + 1));
+        if (mode == 1) cnt = (uint32_t)(rnd() % 4) < n_rows - A ? (uint32_t)(rnd() % 4) : 0;
+        int64_t start = (int64_t)(rnd() % n_rows);
+        if (mode == 2) start = (int64_t)A + (int64_t)(rnd() % 9) - 4;                 // near the lower bound
+        if (mode == 3) start = (int64_t)A + cnt + (int64_t)(rnd() % 9) - 4;           // near the upper bound
+        if (mode == 4) start = (int64_t)(rnd() % 3);                                  // table start
+        if (mode == 5) start = (int64_t)n_rows - 1 - (int64_t)(rnd() % 3);            // table end
+        if (start < 0) start = 0;
+        if (start >= (int64_t)n_rows) start = -1;                                     // also: prediction outside the table
+        int64_t l1 = 7, h1 = 7, l2 = 7, h2 = 7;
+        const bool a = rmi_arith_lookup(m, start, A, cnt, n_rows, l1, h1);
+        const bool b = rmi_arith_lookup_loops(m, start, A, cnt, n_rows, l2, h2);
+        if (a != b || l1 != l2 || h1 != h2) ++bad;
+    }
+    return bad;
+}
+
 }  // extern "C"

@@ -44,6 +44,8 @@ class Emu:
                                           C.POINTER(u32), C.POINTER(u32)]
         self.lib.emu_rmi_arith.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u32, P, u64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                            C.POINTER(u32)]
+        self.lib.emu_rmi_arith_fuzz.argtypes = [u32, u32, P, u64, u64]
+        self.lib.emu_rmi_arith_fuzz.restype = u64
         self.lib.emu_rmi_search.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                             C.POINTER(u32)]
         self.lib.emu_locate.argtypes = [C.POINTER(EmuIndex), u32, u64, P, P]

@@ -58,6 +58,17 @@ def test_rmi_lookup_logic(emus, tag, name):
     assert n_arith > 0.8 * len(gu.load_json(f"rmi_lookups_{tag}.json.gz")[::3])
 
 
+def test_closed_form_gallops_equal_the_probe_loops(emus):
+    """rmi_arith_lookup computes the two exponential phases of RMI_LUT.exponential_search (RMI_LUT.py:151-178) in closed
+    form; against the probe-by-probe loops on 6 M random and edge-case (start, bounds) triples: tiny and 2^31-row tables,
+    None rows at both table ends, starts around both bounds, prediction outside the table."""
+    _, em = emus["small_data"]
+    for n_rows, none in ((1, [0]), (2, [1]), (7, [0, 3]), (1000, [0, 1, 999]), (100_001, [5, 50_000, 100_000]),
+                         (2_147_483_648, [0, 17, 2_147_483_647]), (4_294_967_295, [1, 4_294_967_294])):
+        nr = np.asarray(none, np.uint32)
+        assert em.lib.emu_rmi_arith_fuzz(n_rows, len(nr), nr.ctypes.data, 1_000_000 if n_rows > 7 else 200_000, n_rows) == 0, n_rows
+
+
 def test_rmi_search_machine_equals_literal_search_on_bad_models(emus):
     """Differential test of RmiSearch against the literal RmiTable on deliberately poor models: predictions far off,
     negative, beyond the table -- the paths where the reference wraps (negative rows), skips None rows or raises."""
