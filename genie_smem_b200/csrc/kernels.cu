@@ -243,18 +243,22 @@ __device__ __forceinline__ void order_segments(uint4* mems, uint32_t n_mems) {
     }
 }
 
+// BWA-SMEM selection, one thread per read: over all reads, or (queue != nullptr) over the reads k_select_bwa_picked left.
 template <int METHOD>
-__global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
+__global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a, const uint32_t* queue) {
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     uint4* const stage = a.stage + gtid * a.stage_stride;
-    for (size_t rid = gtid; rid < a.n_reads; rid += nthreads) {
+    const size_t n_work = queue ? (size_t)a.counters[4] : (size_t)a.n_reads;
+    for (size_t w = gtid; w < n_work; w += nthreads) {
+        const size_t rid = queue ? queue[w] : w;
+        const uint32_t mc = a.mem_cnt[rid];
         DevSelCtx<METHOD> c{a,
                             a.reads + (size_t)__ldg(a.chunk_off + rid) * 4,
                             a.mem_pool + a.mem_off[rid],
                             stage, a.stage_stride,
-                            __ldg(a.len + rid), a.K, a.mem_cnt[rid] & 0x7FFFFFFFu, a.min_len, (uint32_t)rid, 0u, false, false, (a.mem_cnt[rid] >> 31) != 0u};
-        if (!c.soa) order_segments(c.mems, c.n_mems);        // bit 31: the sweep already ordered the list
+                            __ldg(a.len + rid), a.K, mc & MEMS_COUNT, a.min_len, (uint32_t)rid, 0u, false, false, (mc & MEMS_ORDERED) != 0u};
+        if (!c.soa) order_segments(c.mems, c.n_mems);        // MEMS_ORDERED: the sweep already ordered the list
         bool direct = false;
         do {
             static_assert(METHOD == GSM_METHOD_BWA, "LUT- and RMI-SMEM run in k_select_seeded");
@@ -263,6 +267,46 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a) {
         } while (true);
     }
 }
+
+// BWA-SMEM selection where the sweep has already made the picks (MEMS_PICKED: lists of 1..32 matches, nine reads in ten):
+// the read's records ARE the picked entries of its match list, so "selecting" is the min_len filter and a count --
+// rec_cnt[read] = records, rec_tmp_off[read] = the picks (k_gather_records writes the records from the list).  Reads
+// without picks are queued for k_select<BWA>; counters[6] += records counted here.
+__global__ void __launch_bounds__(256) k_select_bwa_picked(const SelectArgs a, uint32_t* queue) {
+    const size_t rid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n_rec = 0;
+    bool later = false;
+    if (rid < a.n_reads) {
+        const uint32_t mc = a.mem_cnt[rid];
+        if (mc & MEMS_PICKED) {
+            const uint32_t n = mc & MEMS_COUNT;
+            const uint32_t* seg = reinterpret_cast<const uint32_t*>(a.mem_pool + a.mem_off[rid]);
+            uint32_t picks = seg[3u * n];
+            if (a.min_len > 1u)
+                for (uint32_t m = picks; m != 0u; m &= m - 1u) {
+                    const uint32_t k = (uint32_t)__ffs((int)m) - 1u, w = seg[k];
+                    if ((w >> 16) - (w & 0xFFFFu) < a.min_len) picks &= ~(1u << k);
+                }
+            n_rec = (uint32_t)__popc(picks);
+            a.rec_cnt[rid] = n_rec; a.rec_tmp_off[rid] = picks; a.read_status[rid] = GSM_READ_OK;
+        } else {
+            later = true;
+        }
+    }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lm = __ballot_sync(FULL, later);
+    if (lm) {
+        unsigned long long slot = 0;
+        if (lane == (uint32_t)__ffs((int)lm) - 1u) slot = atomicAdd(&a.counters[4], (unsigned long long)__popc(lm));
+        slot = __shfl_sync(FULL, slot, __ffs((int)lm) - 1);
+        if (later) queue[slot + __popc(lm & ((1u << lane) - 1u))] = (uint32_t)rid;
+    }
+    const uint32_t total = __reduce_add_sync(FULL, n_rec);
+    if (lane == 0 && total) atomicAdd(&a.counters[6], (unsigned long long)total);
+}
+
+// after the two BWA kernels: counters[1] (records of the batch; so far the pool cursor of k_select<BWA>) += counters[6]
+__global__ void k_select_bwa_finish(unsigned long long* counters) { counters[1] += counters[6]; }
 
 // The lookup results of one round (Selector::round_decide's `win`) in shared memory: two planes (lo, hi) of K windows x
 // WIN_STRIDE words, window i of a thread at word i * WIN_STRIDE + threadIdx.x -- nothing of it lives in local memory (as
@@ -422,9 +466,9 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __gr
             c.words = a.reads + (size_t)__ldg(a.chunk_off + rid) * 4;
             c.mems = a.mem_pool + a.mem_off[rid];
             const uint32_t mc = a.mem_cnt[rid];
-            c.L = __ldg(a.len + rid); c.n_mems = mc & 0x7FFFFFFFu; c.rid = (uint32_t)rid; c.n_rec = 0; c.raised = false; c.overflow = false;
+            c.L = __ldg(a.len + rid); c.n_mems = mc & MEMS_COUNT; c.rid = (uint32_t)rid; c.n_rec = 0; c.raised = false; c.overflow = false;
             c.out = stage; c.cap = a.stage_stride;
-            c.soa = (mc >> 31) != 0u;
+            c.soa = (mc & MEMS_ORDERED) != 0u;
             if (!c.soa) order_segments(c.mems, c.n_mems);                      // bit 31: the sweep already ordered the list
             st = typename Sel::Seeded();
             if (PREFETCH && rid + nthreads < a.n_reads) {
@@ -774,7 +818,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(unsigned long long* o
 // memory, either may be NULL = 0), so no host round trip sits between the selection and the write.
 __global__ void k_gather_records(const uint4* rec_tmp, const uint32_t* tmp_off, const uint32_t* cnt, const unsigned long long* off,
                                  uint64_t n_reads, uint4* out, unsigned long long out_cap, unsigned long long* counters,
-                                 const unsigned long long* rank_counts, uint32_t rank, const unsigned long long* base) {
+                                 const unsigned long long* rank_counts, uint32_t rank, const unsigned long long* base,
+                                 const uint4* mem_pool, const uint32_t* mem_off, const uint32_t* mem_cnt, uint32_t read_id_base) {
     // four lanes per read: records are 16 bytes, a read has a handful of them
     const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const uint32_t ql = threadIdx.x & 3u;
@@ -785,6 +830,17 @@ __global__ void k_gather_records(const uint4* rec_tmp, const uint32_t* tmp_off, 
     const unsigned long long dst = first + off[q];
     if (dst + n > out_cap) { if (ql == 0 && n) atomicOr(&counters[2], 4ull); return; }
     const uint32_t src = tmp_off[q];
+    if (counters[5] != 0ull && (mem_cnt[q] & MEMS_PICKED)) {
+        // BWA-SMEM on a list the sweep picked from (k_select_bwa_picked): src = the picks; record k = the k-th picked entry
+        const uint32_t nm = mem_cnt[q] & MEMS_COUNT;
+        const uint32_t* seg = reinterpret_cast<const uint32_t*>(mem_pool + mem_off[q]);
+        for (uint32_t k = ql; k < n; k += 4) {
+            const uint32_t b = __fns(src, 0u, (int)k + 1);
+            const uint32_t lo = seg[nm + b];
+            out[dst + k] = make_uint4(read_id_base + (uint32_t)q, seg[b], lo, lo + seg[2u * nm + b] - 1u);
+        }
+        return;
+    }
     for (uint32_t k = ql; k < n; k += 4) out[dst + k] = rec_tmp[(size_t)src + k];
 }
 
@@ -1434,8 +1490,24 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
     int grid = lb;
     if (method == GSM_METHOD_BWA) {
         if ((st = resident_grid(k_select<GSM_METHOD_BWA>, SELECT_THREADS, 0, lb, &grid))) return st;
-        k_select<GSM_METHOD_BWA><<<grid, SELECT_THREADS, 0, stream>>>(se);
+        // reads whose picks the sweep made need no pass over their lists; the others queue up (4 read numbers per 16-byte
+        // slot of the record pool's last eighth) for the one-thread-per-read kernel
+        const uint64_t reserve = ws->rec_cap / 8;
+        static const bool use_picks = !(getenv("GSM_BWA_PICKS") && atoi(getenv("GSM_BWA_PICKS")) == 0);
+        if (use_picks && reserve * 4 >= rd->n_reads) {
+            se.rec_cap = ws->rec_cap - reserve;
+            uint32_t* queue = (uint32_t*)((uint4*)ws->rec_tmp + se.rec_cap);
+            GSM_CUDA(cudaMemsetAsync((unsigned long long*)ws->counters + 4, 0, 3 * sizeof(uint64_t), stream));    // queue length, mode, records
+            k_select_bwa_picked<<<(unsigned)((rd->n_reads + 255) / 256), 256, 0, stream>>>(se, queue);
+            k_select<GSM_METHOD_BWA><<<grid, SELECT_THREADS, 0, stream>>>(se, queue);
+            k_select_bwa_finish<<<1, 1, 0, stream>>>((unsigned long long*)ws->counters);
+            GSM_CUDA(cudaMemsetAsync((unsigned long long*)ws->counters + 5, 1, 1, stream));                        // mode: picked reads' records come from their lists
+        } else {
+            GSM_CUDA(cudaMemsetAsync((unsigned long long*)ws->counters + 5, 0, sizeof(uint64_t), stream));
+            k_select<GSM_METHOD_BWA><<<grid, SELECT_THREADS, 0, stream>>>(se, nullptr);
+        }
     } else {
+        GSM_CUDA(cudaMemsetAsync((unsigned long long*)ws->counters + 5, 0, sizeof(uint64_t), stream));
         const bool arith = rm.n_none != 0u && se.seed_K != 0u && se.seed_K <= K;       // lookups from the seed table: no probes
         if (method == GSM_METHOD_LUT) st = launch_seeded<GSM_METHOD_LUT, 0>(se, lb, stream);
         else if (se.rmi_bounds) st = launch_seeded<GSM_METHOD_RMI, 2>(se, lb, stream);
@@ -1473,7 +1545,8 @@ int gsm_smem_collect(const gsm_dev_reads* rd, gsm_workspace* ws, gsm_record* out
     const uint64_t threads = rd->n_reads * 4;
     k_gather_records<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)ws->rec_tmp, ws->rec_tmp_off, ws->rec_cnt, (const unsigned long long*)ws->rec_off, rd->n_reads, (uint4*)out, out_cap,
-        (unsigned long long*)ws->counters, nullptr, 0u, nullptr);
+        (unsigned long long*)ws->counters, nullptr, 0u, nullptr,
+        (const uint4*)ws->mem_pool, ws->mem_off, ws->mem_cnt, rd->read_id_base);
     GSM_CUDA(cudaGetLastError());
     return GSM_OK;
 }
@@ -1487,7 +1560,8 @@ int gsm_smem_collect_gathered(const gsm_dev_reads* rd, gsm_workspace* ws, gsm_re
     const uint64_t threads = rd->n_reads * 4;
     k_gather_records<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)ws->rec_tmp, ws->rec_tmp_off, ws->rec_cnt, (const unsigned long long*)ws->rec_off, rd->n_reads, (uint4*)out, out_cap,
-        (unsigned long long*)ws->counters, (const unsigned long long*)counts_dev, rank, (const unsigned long long*)base_dev);
+        (unsigned long long*)ws->counters, (const unsigned long long*)counts_dev, rank, (const unsigned long long*)base_dev,
+        (const uint4*)ws->mem_pool, ws->mem_off, ws->mem_cnt, rd->read_id_base);
     GSM_CUDA(cudaGetLastError());
     return GSM_OK;
 }

@@ -19,6 +19,11 @@ constexpr int SWEEP_GROUPS = SWEEP_THREADS / SWEEP_LPR;   // reads in flight per
 constexpr int SWEEP_CAP = 12;                             // candidates kept in shared memory per read
 constexpr int SWEEP_MIN_BLOCKS = 8;
 
+// mem_cnt[read]: number of maximal matches in the low 30 bits, and how the sweep left the list
+constexpr uint32_t MEMS_ORDERED = 0x80000000u;   // ascending and field by field (n start|end words, n lo, n count, n sweep ordinals)
+constexpr uint32_t MEMS_PICKED = 0x40000000u;    // ... and the first sweep ordinal replaced by the BWA-SMEM picks (bit = position)
+constexpr uint32_t MEMS_COUNT = 0x3FFFFFFFu;
+
 struct SweepArgs {
     const uint4* fwd;
     const uint4* rev;
@@ -429,14 +434,32 @@ struct DevSweepCtx1 {
                 if (lane < n) v = __ldcg(sp + lane);
                 const uint32_t prev = __shfl_up_sync(FULLM, v.w, 1);
                 const uint32_t heads = __ballot_sync(FULLM, lane < n && (lane == 0u || v.w != prev));
+                uint32_t d = 64u;                                                         // this lane's entry goes to position d of the ordered list
                 if (lane < n) {
                     const uint32_t upto = heads & (0xFFFFFFFFu >> (31u - lane));          // heads at or below this lane
                     const uint32_t s0 = 31u - (uint32_t)__clz((int)upto);
                     const uint32_t above = lane == 31u ? 0u : heads & (0xFFFFFFFFu << (lane + 1u));
                     const uint32_t s1 = above ? (uint32_t)__ffs((int)above) - 1u : n;
+                    d = s0 + (s1 - 1u - lane);
+                }
+                // While the list is in registers: the BWA-SMEM selection over it (get_SMEMS, SMEM.py:456-467 = Selector::run_bwa:
+                // from position p take the longest match covering p among those ending beyond it -- ties: the first --, jump to
+                // its end), the warp working on one read: two reductions and a ballot per pick.  The picks (bit = position in
+                // the ordered list) take the place of the first sweep ordinal, which nobody reads once the list is in order:
+                // gsm_smem_select(BWA) needs no pass over the list, and the records are written straight from it.
+                const uint32_t ms = v.x & 0xFFFFu, me = v.x >> 16;
+                uint32_t picks = 0u;
+                for (uint32_t p = 0u, from = 0u;;) {
+                    from = __reduce_min_sync(FULLM, (d < 64u && d >= from && me > p) ? d : 64u);      // first match ending beyond p
+                    if (from >= n) break;
+                    const uint32_t best = __reduce_max_sync(FULLM, (d < 64u && d >= from && ms <= p) ? (((me - ms) << 6) | (63u - d)) : 0u);
+                    const uint32_t b = best ? 63u - (best & 63u) : from;                    // nothing covers p: the first match beyond it
+                    picks |= 1u << b;
+                    p = __shfl_sync(FULLM, me, __ffs((int)__ballot_sync(FULLM, d == b)) - 1);
+                }
+                if (lane < n) {
                     uint32_t* seg = reinterpret_cast<uint32_t*>(a.mem_pool + off);
-                    const uint32_t d = s0 + (s1 - 1u - lane);
-                    seg[d] = v.x; seg[n + d] = v.y; seg[2u * n + d] = v.z; seg[3u * n + d] = v.w;
+                    seg[d] = v.x; seg[n + d] = v.y; seg[2u * n + d] = v.z; seg[3u * n + d] = d == 0u ? picks : v.w;
                 }
             } else if (n <= SOA_MAX) {
                 hand_over_long(sp, n, a.mem_pool + off);
@@ -446,7 +469,7 @@ struct DevSweepCtx1 {
         }
         if (fin_n != NO_FIN) {
             a.mem_off[fin_rid] = fits ? (uint32_t)my_off : 0u;
-            a.mem_cnt[fin_rid] = fits ? (fin_n | (fin_n <= SOA_MAX ? 0x80000000u : 0u)) : 0u;
+            a.mem_cnt[fin_rid] = fits ? (fin_n | (fin_n <= SOA_MAX ? MEMS_ORDERED : 0u) | (fin_n >= 1u && fin_n <= 32u ? MEMS_PICKED : 0u)) : 0u;
             fin_n = NO_FIN;
         }
     }

@@ -730,11 +730,11 @@ class Engine:
                                             C.byref(rmi.c) if rmi is not None else None, C.byref(self.ws), _stream()))
         if gatherer is not None:
             gatherer.collect(self, r)
-            self.kernel_launches += ((6 if method == capi.METHOD_BWA else 7) if reads.n else 1)
+            self.kernel_launches += (8 if method == capi.METHOD_BWA else 7) if reads.n else 1
             return
         capi.check(capi.lib.gsm_smem_collect(C.byref(r), C.byref(self.ws), _ptr(self.records), self.rec_cap, _stream()))
-        # select (LUT / RMI: + the deferred explicit searches), 3 scan kernels, ordered write
-        self.kernel_launches += (5 if method == capi.METHOD_BWA else 6) if reads.n else 0
+        # BWA: picked / queued / finish; LUT, RMI: select + the deferred explicit searches; then 3 scan kernels, ordered write
+        self.kernel_launches += (7 if method == capi.METHOD_BWA else 6) if reads.n else 0
 
     def collect_local(self, reads: ReadBatch):
         """(Re)write the records of the batch just selected into this engine's own `records` buffer."""

@@ -226,14 +226,15 @@ typedef struct {
     void* quad_scratch;    /* per-resident-quad staging */
     uint64_t quad_scratch_bytes;
     uint32_t* mem_off;     /* n_reads */
-    uint32_t* mem_cnt;     /* n_reads: matches per read; bit 31 set = the list is in ascending order and stored field by field */
+    uint32_t* mem_cnt;     /* n_reads: matches per read (low 30 bits); bit 31 = the list is in ascending order and stored field by
+                              field, bit 30 = ... and carries the BWA-SMEM picks in place of its first sweep ordinal */
     gsm_record* rec_tmp;   /* unordered record pool, rec_cap entries */
     uint64_t rec_cap;
     uint32_t* rec_tmp_off; /* n_reads */
     uint32_t* rec_cnt;     /* n_reads: records per read (phase-1 result) */
     uint64_t* rec_off;     /* n_reads + 1: exclusive scan of rec_cnt */
     uint8_t* read_status;  /* n_reads: GSM_READ_* */
-    uint64_t* counters;    /* 8 x uint64: [0] mems used, [1] records, [2] status bits, [3] next read */
+    uint64_t* counters;    /* 8 x uint64: [0] mems used, [1] records, [2] status bits, [3] next read, [4..7] scratch of the kernels */
     void* scan_tmp;        /* scan scratch */
     uint64_t scan_tmp_bytes;
 } gsm_workspace;
