@@ -443,19 +443,20 @@ struct DevSweepCtx1 {
                     d = s0 + (s1 - 1u - lane);
                 }
                 // While the list is in registers: the BWA-SMEM selection over it (get_SMEMS, SMEM.py:456-467 = Selector::run_bwa:
-                // from position p take the longest match covering p among those ending beyond it -- ties: the first --, jump to
-                // its end), the warp working on one read: two reductions and a ballot per pick.  The picks (bit = position in
-                // the ordered list) take the place of the first sweep ordinal, which nobody reads once the list is in order:
-                // gsm_smem_select(BWA) needs no pass over the list, and the records are written straight from it.
-                const uint32_t ms = v.x & 0xFFFFu, me = v.x >> 16;
+                // from position p take the longest match covering p -- ties: the first; nothing covers p: the first match
+                // ending beyond it --, jump to its end), the warp working on one read: one reduction and one shuffle per pick.
+                // The picks (bit = position in the ordered list) take the place of the first sweep ordinal, which nobody
+                // reads once the list is in order: gsm_smem_select(BWA) needs no pass over the list, and the records are
+                // written straight from it.
+                const uint32_t ox = __shfl_sync(FULLM, v.x, d & 31u);      // entry at position `lane`: lane d holds it (reversing is an involution)
+                const uint32_t os = ox & 0xFFFFu, oe = ox >> 16;
+                const uint32_t pmax = __shfl_sync(FULLM, oe, (n - 1u) & 31u);
                 uint32_t picks = 0u;
-                for (uint32_t p = 0u, from = 0u;;) {
-                    from = __reduce_min_sync(FULLM, (d < 64u && d >= from && me > p) ? d : 64u);      // first match ending beyond p
-                    if (from >= n) break;
-                    const uint32_t best = __reduce_max_sync(FULLM, (d < 64u && d >= from && ms <= p) ? (((me - ms) << 6) | (63u - d)) : 0u);
-                    const uint32_t b = best ? 63u - (best & 63u) : from;                    // nothing covers p: the first match beyond it
+                for (uint32_t p = 0u; p < pmax;) {
+                    const uint32_t key = (lane < n && oe > p) ? ((os <= p ? 0x80000000u | ((oe - os) << 6) : 0u) | (63u - lane)) : 0u;
+                    const uint32_t b = 63u - (__reduce_max_sync(FULLM, key) & 63u);
                     picks |= 1u << b;
-                    p = __shfl_sync(FULLM, me, __ffs((int)__ballot_sync(FULLM, d == b)) - 1);
+                    p = __shfl_sync(FULLM, oe, b);
                 }
                 if (lane < n) {
                     uint32_t* seg = reinterpret_cast<uint32_t*>(a.mem_pool + off);

@@ -10,4 +10,4 @@ print({k:d[k] for k in d if k.startswith('ms_select') or k.startswith('sha') or 
 PY
 tail -2 gpurun_out/${T}_ab_$n.err | cut -c1-300; }
 ab def GSM_X=0
-ab nopicks GSM_BWA_PICKS=0
+
