@@ -74,7 +74,17 @@ def main():
     if rmi is not None:
         legs.append(("rmi", g.METHOD_RMI, {"rmi": rmi}))
         legs.append(("rmi_bounds", g.METHOD_RMI, {"rmi": rmi}))
+    persist = os.environ.get("AB_PERSIST")               # A/B: pin the LUT / the RMI parameters in the persisting L2
     for name, method, kw in legs:
+        if persist:
+            import ctypes as C
+            from genie_smem_b200 import _capi as capi
+            t = lut if name == "lut" else (rmi.params if name.startswith("rmi") else None)
+            st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if t is None:
+                capi.check(capi.lib.gsm_l2_persist(None, 0, st))
+            else:
+                capi.check(capi.lib.gsm_l2_persist(C.c_void_p(t.data_ptr()), t.numel() * t.element_size(), st))
         if name == "rmi_bounds":                      # same lookups from the dense bounds table (gsm_rmi_bounds_build)
             out["ms_bounds_build"] = round(timed(lambda: rmi.build_bounds_table(index), 1), 1)
         out[f"ms_select_{name}"] = round(timed(lambda: eng.select(method, batch, **kw), a.steps), 3)
