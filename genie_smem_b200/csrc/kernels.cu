@@ -41,7 +41,7 @@ namespace gsm {
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr int SELECT_THREADS = 128;
-constexpr int SELECT_DEFAULT_BLOCKS = 7;     // k_select_seeded: resident blocks per SM / variant when the environment says nothing
+constexpr int SELECT_BLOCKS = 7;             // k_select_seeded: resident blocks per SM the registers are allocated for
 constexpr int SELECT_DEFAULT_OPT_LUT = 1;    // measured per method (tools/sweep_ab.py, profiles/r02_notes.md)
 constexpr int SELECT_DEFAULT_OPT_RMI = 3;
 constexpr uint32_t SELECT_STAGE = 64;   // staged records per selection thread; reads emitting more are run twice (see DevSelCtx::close)
@@ -431,7 +431,8 @@ __device__ __noinline__ LiteralOut literal_lookups(const SelectArgs& a, const ui
 // ARITH (RMI only): 1 = the launch has a usable seed table (seed_K <= K) and the None rows, so every lookup is the probe-free
 // rmi_arith_lookup and the probe-based phases are compiled out (fewer registers for the path that always runs);
 // 2 = as 1, the k-mer's true bounds read from the dense table of gsm_rmi_bounds_build (one fetch, no backward steps).
-// MB: resident blocks per SM the register allocation aims at (8: 64 registers with spills, 6: 80); GSM_SELECT_BLOCKS=6 for A/B
+// MB: resident blocks per SM the register allocation aims at (7: 72 registers; 8: 64 with spills and 6: 80 measured slower)
+// OPT: bit 0 = two (thread, window) pairs per lane and trip of pass 1, bit 1 = prefetch of the thread's next read
 template <int METHOD, int ARITH = 0, int MB = 8, int OPT = 0>
 __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __grid_constant__ SelectArgs a) {
     using CtxT = DevSelCtx<METHOD>;
@@ -1183,18 +1184,18 @@ int launch_seeded1(const SelectArgs& se, int cap, cudaStream_t stream) {
     k_select_seeded<METHOD, ARITH, MB, OPT><<<grid, SELECT_THREADS, smem, stream>>>(se);
     return GSM_OK;
 }
-// A/B switches (tools/sweep_ab.py): GSM_SELECT_BLOCKS = 6 | 7 | 8 resident blocks per SM the registers are allocated for,
-// GSM_SELECT_OPT bit 0 = two (thread, window) pairs per lane and trip of pass 1, bit 1 = prefetch of the thread's next read
+// A/B switch (tools/sweep_ab.py): GSM_SELECT_OPT bit 0 = two (thread, window) pairs per lane and trip of pass 1, bit 1 = prefetch
+// of the thread's next read.  Resident blocks per SM: 7 (72 registers; 6 and 8 measured slower for both methods).
 template <int METHOD, int ARITH>
 int launch_seeded(const SelectArgs& se, int cap, cudaStream_t stream) {
-    static const int mb = getenv("GSM_SELECT_BLOCKS") ? atoi(getenv("GSM_SELECT_BLOCKS")) : SELECT_DEFAULT_BLOCKS;
     static const int opt = getenv("GSM_SELECT_OPT") ? atoi(getenv("GSM_SELECT_OPT")) : (METHOD == GSM_METHOD_LUT ? SELECT_DEFAULT_OPT_LUT : SELECT_DEFAULT_OPT_RMI);
-#define GSM_SEL_CASE(M, O) if (mb == M && opt == O) return launch_seeded1<METHOD, ARITH, M, O>(se, cap, stream);
-    GSM_SEL_CASE(6, 0) GSM_SEL_CASE(6, 1) GSM_SEL_CASE(6, 2) GSM_SEL_CASE(6, 3)
-    GSM_SEL_CASE(7, 0) GSM_SEL_CASE(7, 1) GSM_SEL_CASE(7, 2) GSM_SEL_CASE(7, 3)
-    GSM_SEL_CASE(8, 0) GSM_SEL_CASE(8, 1) GSM_SEL_CASE(8, 2) GSM_SEL_CASE(8, 3)
-#undef GSM_SEL_CASE
-    return fail(GSM_E_INVALID, "GSM_SELECT_BLOCKS must be 6..8 and GSM_SELECT_OPT 0..3");
+    switch (opt) {
+        case 0: return launch_seeded1<METHOD, ARITH, SELECT_BLOCKS, 0>(se, cap, stream);
+        case 1: return launch_seeded1<METHOD, ARITH, SELECT_BLOCKS, 1>(se, cap, stream);
+        case 2: return launch_seeded1<METHOD, ARITH, SELECT_BLOCKS, 2>(se, cap, stream);
+        case 3: return launch_seeded1<METHOD, ARITH, SELECT_BLOCKS, 3>(se, cap, stream);
+    }
+    return fail(GSM_E_INVALID, "GSM_SELECT_OPT must be 0..3");
 }
 
 }  // namespace
@@ -1512,7 +1513,7 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
         if (method == GSM_METHOD_LUT) st = launch_seeded<GSM_METHOD_LUT, 0>(se, lb, stream);
         else if (se.rmi_bounds) st = launch_seeded<GSM_METHOD_RMI, 2>(se, lb, stream);
         else if (arith) st = launch_seeded<GSM_METHOD_RMI, 1>(se, lb, stream);
-        else st = launch_seeded1<GSM_METHOD_RMI, 0, 8, 0>(se, lb, stream);
+        else st = launch_seeded1<GSM_METHOD_RMI, 0, SELECT_BLOCKS, 0>(se, lb, stream);
         if (st) return st;
         int dev = 0, sms = 148;
         GSM_CUDA(cudaGetDevice(&dev));

@@ -1,13 +1,21 @@
 #!/bin/bash
-# A/B of the sweep variants + GPU tests under the variant + ncu captures of the LUT step's kernels
-T=${1:-r2c}
+# One GPU session of A/B runs: (optionally) the GPU tests first, then tools/sweep_ab.py once per variant.  A variant is a
+# quoted list of environment assignments; record checksums (sha_*) must be identical across variants.
+#   usage: tools/gpu_ab.sh TAG [--tests] "GSM_SELECT_OPT=0" "GSM_SELECT_OPT=3" "GSM_SWEEP_BLOCKS=6 GSM_BWA_PICKS=0" ...
+T=$1; shift
 mkdir -p gpurun_out
-ab() { env "$@" python tools/sweep_ab.py --tag "$*" > gpurun_out/${T}_ab_$N.json 2> gpurun_out/${T}_ab_$N.err; echo "[$*] exit=$?"; cat gpurun_out/${T}_ab_$N.json; tail -2 gpurun_out/${T}_ab_$N.err | cut -c1-300; }
-N=pair ab GSM_SWEEP_LPR=2
-N=lane ab GSM_SWEEP_LPR=1 GSM_SWEEP_UNIQ=0
-N=lane_uniq ab GSM_SWEEP_LPR=1 GSM_SWEEP_UNIQ=1
-GSM_SWEEP_LPR=1 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest_lpr1.log 2>&1; echo "pytest lpr1 uniq exit=$?"; tail -4 gpurun_out/${T}_pytest_lpr1.log
-export GSM_SWEEP_LPR=1
-python tools/profile_step.py --method lut --reads 1000000 --steps 1 > gpurun_out/${T}_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"k_select_seeded|k_sweep" -c 2 -o gpurun_out/${T}_lut python tools/profile_step.py --method lut --reads 1000000 --steps 1 > gpurun_out/${T}_ncu.log 2>&1; echo "ncu exit=$?"
-tail -3 gpurun_out/${T}_ncu.log
+if [ "$1" == "--tests" ]; then
+  shift
+  python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest exit=$?"; tail -4 gpurun_out/${T}_pytest.log
+fi
+i=0
+for v in "$@"; do
+  i=$((i+1))
+  env $v python tools/sweep_ab.py --tag "$v" > gpurun_out/${T}_ab_$i.json 2> gpurun_out/${T}_ab_$i.err; echo "[$v] exit=$?"
+  python - gpurun_out/${T}_ab_$i.json <<'PY'
+import json, sys
+d = json.load(open(sys.argv[1]))
+print({k: d[k] for k in d if k.startswith(("ms_select", "sha", "records")) or k == "ms_sweep"})
+PY
+  tail -2 gpurun_out/${T}_ab_$i.err | cut -c1-300
+done
