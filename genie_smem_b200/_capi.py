@@ -26,7 +26,7 @@ class IndexInfo(C.Structure):
 class DevIndex(C.Structure):
     _fields_ = [("n_rows", C.c_uint64), ("n_buckets", C.c_uint64), ("fwd_buckets", C.c_void_p), ("rev_buckets", C.c_void_p),
                 ("sa", C.c_void_p), ("text2bit", C.c_void_p), ("C", C.c_uint32 * 5), ("primary_fwd", C.c_uint32),
-                ("primary_rev", C.c_uint32), ("seed_K", C.c_uint32), ("seed_table", C.c_void_p), ("isa", C.c_void_p)]
+                ("primary_rev", C.c_uint32), ("seed_K", C.c_uint32), ("seed_table", C.c_void_p)]
 
 
 class DevReads(C.Structure):
@@ -88,7 +88,6 @@ EXPORTS = {
     "gsm_smem_collect": (C.c_int, [C.POINTER(DevReads), C.POINTER(Workspace), C.c_void_p, C.c_uint64, C.c_void_p]),
     "gsm_rmi_probe_build": (C.c_int, [C.POINTER(DevIndex), C.c_void_p, C.c_void_p]),
     "gsm_rmi_bounds_build": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p]),
-    "gsm_isa_build": (C.c_int, [C.POINTER(DevIndex), C.c_void_p, C.c_void_p]),
     "gsm_rmi_none_rows": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_rmi_lookup_batch": (C.c_int, [C.POINTER(DevIndex), C.POINTER(DevRmi), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -989,12 +989,6 @@ __global__ void k_rmi_lookup(const uint32_t* sa, const uint32_t* text, uint64_t 
     status[i] = t.raised ? GSM_READ_REF_RAISES : GSM_READ_OK;
 }
 
-// inverse suffix array: isa[text index] = row of the suffix starting there (suffix-array values are 1-based, ExactMatch.py:66)
-__global__ void k_isa_build(const uint32_t* sa, uint64_t n_rows, uint32_t* isa) {
-    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row < n_rows) isa[__ldg(sa + row) - 1u] = (uint32_t)row;
-}
-
 // rows whose suffix is shorter than K (RMI_LUT.get_ref_seq returns None there): out[0] = count, out[1..] = rows
 __global__ void k_none_rows(const uint32_t* sa, uint64_t n_rows, uint32_t K, uint32_t* out) {
     const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1366,15 +1360,6 @@ int gsm_rmi_none_rows(const gsm_dev_index* ix, uint32_t K, uint32_t* rows_host, 
     return GSM_OK;
 }
 
-int gsm_isa_build(const gsm_dev_index* ix, uint32_t* isa, void* stream) {
-    if (!ix || !ix->sa || !isa) return fail(GSM_E_INVALID, "gsm_isa_build needs the suffix array on the device");
-    int st = device_ready();
-    if (st) return st;
-    k_isa_build<<<(unsigned)((ix->n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ix->sa, ix->n_rows, isa);
-    GSM_CUDA(cudaGetLastError());
-    return GSM_OK;
-}
-
 int gsm_rmi_bounds_build(const gsm_dev_index* ix, uint32_t K, void* bounds, void* stream) {
     if (!ix || !ix->fwd_buckets || !bounds || K < 1 || K > 16) return fail(GSM_E_INVALID, "gsm_rmi_bounds_build: needs the rank buckets and K in 1..16");
     int st = device_ready();
@@ -1443,29 +1428,23 @@ int gsm_smem_sweep(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_workspa
     if (sa.seed_tab && (sa.seed_K < 1 || sa.seed_K > 16)) return fail(GSM_E_INVALID, "seed table K must be in 1..16");
     sa.mem_pool = (uint4*)ws->mem_pool; sa.mem_cap = ws->mem_cap; sa.mem_off = ws->mem_off; sa.mem_cnt = ws->mem_cnt;
     sa.scratch = (uint4*)ws->quad_scratch; sa.counters = (unsigned long long*)ws->counters;
-    // unique-match shortcut of the lane kernels: needs the suffix array and the packed text on the device, and the inverse
-    // suffix array to run to the left as well (GSM_SWEEP_UNIQ = 0 / 1 restricts it)
-    static const int uniq_env = getenv("GSM_SWEEP_UNIQ") ? atoi(getenv("GSM_SWEEP_UNIQ")) : 2;
-    sa.sa = ix->sa; sa.text = ix->text2bit; sa.n_bases = (uint32_t)(ix->n_rows - 1); sa.isa = ix->isa;
-    const int uniq = (uniq_env == 0 || !ix->sa || !ix->text2bit) ? 0 : ((uniq_env >= 2 && ix->isa) ? 2 : 1);
+    // unique-match shortcut of the lane kernels: needs the suffix array and the packed text on the device (GSM_SWEEP_UNIQ=0 disables)
+    static const int uniq_env = getenv("GSM_SWEEP_UNIQ") ? atoi(getenv("GSM_SWEEP_UNIQ")) : 1;
+    sa.sa = ix->sa; sa.text = ix->text2bit; sa.n_bases = (uint32_t)(ix->n_rows - 1);
+    const bool uniq = uniq_env != 0 && ix->sa && ix->text2bit;
     const int kind = sweep_kind(rd->max_len);
     if (kind == SWEEP_LANE) {
         static const int stats = getenv("GSM_SWEEP_STATS") ? atoi(getenv("GSM_SWEEP_STATS")) : 0;
         static const int paired = getenv("GSM_SWEEP_PAIRED") ? atoi(getenv("GSM_SWEEP_PAIRED")) : 0;      // A/B: buckets as one 64-byte request per lane pair
-        const size_t smem = sweep1_smem_bytes(rd->max_len, false);
-        if (uniq == 2 && stats) k_sweep1<false, 2, SWEEP1_MIN_BLOCKS, true><<<sb, SWEEP1_THREADS, smem, stream>>>(sa);
-        else if (uniq == 2) k_sweep1<false, 2><<<sb, SWEEP1_THREADS, smem, stream>>>(sa);
-        else if (uniq && paired) k_sweep1<false, 1, SWEEP1_MIN_BLOCKS, false, true><<<sb, SWEEP1_THREADS, smem, stream>>>(sa);
-        else if (uniq && stats) k_sweep1<false, 1, SWEEP1_MIN_BLOCKS, true><<<sb, SWEEP1_THREADS, smem, stream>>>(sa);
-        else if (uniq && sweep_blocks_env() == 6) k_sweep1<false, 1, 6><<<sb, SWEEP1_THREADS, smem, stream>>>(sa);
-        else if (uniq && sweep_blocks_env() == 8) k_sweep1<false, 1, 8><<<sb, SWEEP1_THREADS, smem, stream>>>(sa);
-        else if (uniq) k_sweep1<false, 1><<<sb, SWEEP1_THREADS, smem, stream>>>(sa);
-        else k_sweep1<false, 0><<<sb, SWEEP1_THREADS, smem, stream>>>(sa);
+        if (uniq && paired) { k_sweep1<false, true, SWEEP1_MIN_BLOCKS, false, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa); GSM_CUDA(cudaGetLastError()); return GSM_OK; }
+        if (uniq && stats) k_sweep1<false, true, SWEEP1_MIN_BLOCKS, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
+        else if (uniq && sweep_blocks_env() == 6) k_sweep1<false, true, 6><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
+        else if (uniq && sweep_blocks_env() == 8) k_sweep1<false, true, 8><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
+        else if (uniq) k_sweep1<false, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
+        else k_sweep1<false, false><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, false), stream>>>(sa);
     } else if (kind == SWEEP_LANE_LONG) {
-        const size_t smem = sweep1_smem_bytes(rd->max_len, true);
-        if (uniq == 2) k_sweep1<true, 2><<<sb, SWEEP1_THREADS, smem, stream>>>(sa);
-        else if (uniq) k_sweep1<true, 1><<<sb, SWEEP1_THREADS, smem, stream>>>(sa);
-        else k_sweep1<true, 0><<<sb, SWEEP1_THREADS, smem, stream>>>(sa);
+        if (uniq) k_sweep1<true, true><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, true), stream>>>(sa);
+        else k_sweep1<true, false><<<sb, SWEEP1_THREADS, sweep1_smem_bytes(rd->max_len, true), stream>>>(sa);
     } else {
         k_sweep<<<sb, SWEEP_THREADS, sweep_smem_bytes(rd->max_len), stream>>>(sa);
     }

@@ -45,7 +45,6 @@ struct SweepArgs {
     unsigned long long* counters;
     const uint32_t* sa;      // unique-match shortcut of the lane kernels (k_sweep1<.., true>): suffix array (1-based values) ...
     const uint32_t* text;    // ... and the 2-bit packed text (MSB-first, readable 2 words past its end)
-    const uint32_t* isa;     // optional inverse suffix array (row of the suffix at each text index): the shortcut also to the left
     uint32_t n_bases;
 };
 
@@ -320,9 +319,7 @@ __device__ __noinline__ void hand_over_long(const uint4* sp, uint32_t n, uint4* 
     }
 }
 
-// UNIQ: unique-match shortcut of the sweep logic -- 0 off, 1 forward (suffix array + text), 2 forward and backward (+ the
-// inverse suffix array: SweepArgs::isa)
-template <bool LONG, int UNIQ>
+template <bool LONG, bool UNIQ>
 struct DevSweepCtx1 {
     const SweepArgs& a;
     uint32_t cand0;       // index (uint4) of this lane's candidate slots
@@ -353,38 +350,31 @@ struct DevSweepCtx1 {
     __device__ __forceinline__ uint32_t base(uint32_t pos) const { return (word(pos >> 4) >> (30u - 2u * (pos & 15u))) & 3u; }
     __device__ __forceinline__ uint32_t seed_k() const { return a.seed_K; }
     // unique-match shortcut, forward direction: once q[x:pos) occurs once, its extent is read off the text (sweep_logic.cuh)
-    __device__ __forceinline__ constexpr bool uniq() const { return UNIQ != 0; }
-    __device__ __forceinline__ constexpr bool uniq_back() const { return UNIQ == 2; }
+    __device__ __forceinline__ constexpr bool uniq() const { return UNIQ; }
+    __device__ __forceinline__ constexpr bool uniq_back() const { return false; }
     __device__ __forceinline__ uint32_t kmer(uint32_t pos) const {
         return __funnelshift_l(word((pos >> 4) + 1u), word(pos >> 4), 2u * (pos & 15u)) >> (32u - 2u * a.seed_K);
     }
-    // Number of bases (at most 64) on which the text and the read agree, forward from text[t] / q[p], or (back) backward
-    // from text[t - 1] / q[p - 1].  Both sides are MSB-first 2-bit words: the 64 bases behind (in front of) each position
-    // are brought to a common phase with one funnel shift per word, and a mismatch is the first (last) set bit of the XOR.
-    // Words outside the arrays are replaced by the nearest one inside (the text is readable 2 words past its end); what
-    // they compare as is cut off by the caller (Sweeper::cmp_max: the bases that really exist on both sides).
-    __device__ __forceinline__ uint32_t match_text(uint32_t t, uint32_t p, bool back) const {
-        const int tb = (int)t - (back ? 64 : 0), qb = (int)p - (back ? 64 : 0);
-        const int tw = tb >> 4, qw = qb >> 4;
-        const uint32_t ts = 2u * ((uint32_t)tb & 15u), qs = 2u * ((uint32_t)qb & 15u);
-        const int tlast = (int)(((a.n_bases + 15u) >> 4) + 1u);
+    // Number of leading bases (at most 64) on which text[t..) and q[p..) agree: both sides are MSB-first 2-bit words, so
+    // after one funnel shift per word to a common phase a mismatch is the first set bit of the XOR.  Callers cap the
+    // result by the bases that really exist on both sides (Sweeper::cmp_max).
+    __device__ __forceinline__ uint32_t match_forward(uint32_t t, uint32_t p) const {
+        const uint32_t tw = t >> 4, ts = 2u * (t & 15u), qw = p >> 4, qs = 2u * (p & 15u);
+        const uint32_t tlast = ((a.n_bases + 15u) >> 4) + 1u;           // the text is readable 2 words past its end
         uint32_t T[5], Q[5];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const int w = tw + i;
-            T[i] = __ldg(a.text + (w < 0 ? 0 : (w < tlast ? w : tlast)));
-            Q[i] = word((uint32_t)(qw + i > 0 ? qw + i : 0));
+        for (uint32_t i = 0; i < 5u; ++i) {
+            const uint32_t w = tw + i;
+            T[i] = __ldg(a.text + (w < tlast ? w : tlast));
+            Q[i] = word(qw + i);
         }
-        uint32_t fwd = 64u, bwd = 64u;
+        uint32_t matched = 64u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 3; i >= 0; --i) {
             const uint32_t x = __funnelshift_l(T[i + 1], T[i], ts) ^ __funnelshift_l(Q[i + 1], Q[i], qs);
-            if (x != 0u) {
-                if (fwd == 64u) fwd = 16u * (uint32_t)i + ((uint32_t)__clz((int)x) >> 1);
-                bwd = 16u * (uint32_t)(3 - i) + (((uint32_t)__ffs((int)x) - 1u) >> 1);
-            }
+            if (x != 0u) matched = 16u * (uint32_t)i + ((uint32_t)__clz((int)x) >> 1);
         }
-        return back ? bwd : fwd;
+        return matched;
     }
     __device__ __forceinline__ void cand_put(uint32_t i, uint32_t j, uint32_t lo, uint32_t cnt) {
         if (i < (uint32_t)SWEEP1_CAP) g_sweep_smem[cand0 + i] = make_uint4(j, lo, cnt, 0u);
@@ -502,7 +492,7 @@ inline size_t sweep1_smem_bytes(uint32_t max_len, bool long_reads) {
 // STATS: count lane-slots / FM passes / seed fetches / text operations into counters[4..7] (measurement builds only)
 // PAIRED: buckets fetched as one 64-byte request by lane pairs (lane_step); measured slower than two requests per lane
 // (54.7 vs 44.3 ms per 10 M reads at C4: the shuffles sit between the loads and their use), kept as GSM_SWEEP_PAIRED=1
-template <bool LONG, int UNIQ, int MB = SWEEP1_MIN_BLOCKS, bool STATS = false, bool PAIRED = false>
+template <bool LONG, bool UNIQ, int MB = SWEEP1_MIN_BLOCKS, bool STATS = false, bool PAIRED = false>
 __global__ void __launch_bounds__(SWEEP1_THREADS, MB) k_sweep1(const SweepArgs a) {
     using Ctx = DevSweepCtx1<LONG, UNIQ>;
     const uint32_t lane_u4 = sweep1_lane_u4(a.max_len, LONG);
@@ -521,16 +511,16 @@ __global__ void __launch_bounds__(SWEEP1_THREADS, MB) k_sweep1(const SweepArgs a
         // (at most two) buckets of an FM step, a suffix-array value or the text words of a comparison -- so all 32 chains'
         // loads are in flight together.
         const bool is_seed = need && sw.pending_seed();
-        const bool is_word = UNIQ != 0 && need && sw.pending_word();
-        const bool is_cmp = UNIQ != 0 && need && sw.pending_cmp();
+        const bool is_word = UNIQ && need && sw.pending_word();
+        const bool is_cmp = UNIQ && need && sw.pending_cmp();
         const bool is_step = need && !is_seed && !is_word && !is_cmp;
         if (STATS) { n_it++; n_step += is_step; n_seed += is_seed; n_text += is_word || is_cmp; }
         uint4 se = make_uint4(0u, 0u, 0u, 0u);
         if (is_seed) se = ldg_seed(a.seed_tab + sw.P0);
         uint32_t wv = 0u, matched = 0u;
-        if (UNIQ != 0 && is_word) wv = __ldg((UNIQ == 2 && sw.mode == M_ISA ? a.isa : a.sa) + sw.aux);
-        if (UNIQ != 0 && is_cmp) {
-            matched = ctx.match_text(sw.cmp_text(), sw.cmp_read(), UNIQ == 2 && sw.mode == M_CMPB);
+        if (UNIQ && is_word) wv = __ldg(a.sa + sw.aux);
+        if (UNIQ && is_cmp) {
+            matched = ctx.match_forward(sw.cmp_text(), sw.cmp_read());
             const uint32_t mx = sw.cmp_max(a.n_bases);
             matched = matched < mx ? matched : mx;
         }
@@ -540,8 +530,8 @@ __global__ void __launch_bounds__(SWEEP1_THREADS, MB) k_sweep1(const SweepArgs a
                                                rev ? a.meta.prim_r : a.meta.prim_f, is_step, part, r);
         if (stepped) sw.consume(ctx, a.meta, r);
         else if (is_seed) sw.consume_seed(ctx, a.meta, SeedEntry{se.x, se.y, se.z, se.w});
-        else if (UNIQ != 0 && is_word) sw.consume_word(ctx, a.meta, wv);
-        else if (UNIQ != 0 && is_cmp) sw.consume_cmp(ctx, a.meta, matched);
+        else if (UNIQ && is_word) sw.consume_word(ctx, a.meta, wv);
+        else if (UNIQ && is_cmp) sw.consume_cmp(ctx, a.meta, matched);
     }
     if (STATS) {
         atomicAdd(&a.counters[4], (unsigned long long)n_it);

@@ -337,8 +337,6 @@ class DeviceIndex:
         seed = getattr(self, "seed_table", None)
         d.seed_K = getattr(self, "seed_K", 0) if seed is not None else 0
         d.seed_table = seed.data_ptr() if seed is not None else None
-        isa = getattr(self, "isa", None)
-        d.isa = isa.data_ptr() if isa is not None and self.sa is not None else None
         self.c = d
         self.n_rows = int(info.n_rows)
         self.n_bases = int(info.n_bases)
@@ -416,19 +414,6 @@ class DeviceIndex:
         with torch.cuda.device(self.device):
             capi.check(capi.lib.gsm_seed_table_build(C.byref(self.c), K, _ptr(t), _stream()))
         self.seed_table, self.seed_K = t, K
-        self._bind()
-        return self
-
-    def build_isa(self):
-        """Inverse suffix array (gsm_isa_build, 4 bytes per row): with it the sweep extends a match that occurs once
-        to the LEFT along the text as well (64 bases per fetch instead of one rank query per base).  Results never
-        depend on it."""
-        if self.sa is None:
-            raise ValueError("the inverse suffix array needs the full suffix array on the device")
-        isa = torch.empty(self.n_rows, dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
-            capi.check(capi.lib.gsm_isa_build(C.byref(self.c), _ptr(isa), _stream()))
-        self.isa = isa
         self._bind()
         return self
 

@@ -181,8 +181,6 @@ typedef struct {
     uint32_t seed_K;          /* K of seed_table (1..14), ignored when seed_table is NULL */
     const void* seed_table;   /* device, optional: gsm_seed_table_build output (4^K x 16 bytes); lets the sweep
                                  kernel replace the first K steps of every extension by one fetch */
-    const uint32_t* isa;      /* device, optional: gsm_isa_build output (n_rows x 4 bytes); lets the sweep kernel extend a
-                                 unique match to the left along the text as well */
 } gsm_dev_index;
 
 typedef struct {
@@ -342,12 +340,6 @@ int gsm_gather_advance(uint64_t* base_dev, const uint64_t* counts_dev, uint32_t 
  * bases at that suffix} (16 bytes), so RMI_LUT.get_ref_seq (RMI_LUT.py:89-92) is ONE fetch instead of
  * a suffix-array read followed by a text read.  probe: n_rows * 16 bytes of device memory. */
 int gsm_rmi_probe_build(const gsm_dev_index* idx, void* probe, void* stream);
-
-/* Optional accelerator for gsm_smem_sweep: the inverse suffix array, isa[text index] = row of the suffix starting there
- * (n_rows uint32 of device memory).  With the suffix array, the text and this array on the device a match that occurs
- * exactly once is extended in BOTH directions by comparing the read with the text, 64 bases per fetch, instead of one
- * rank query per base; its row after a left extension is one fetch from this array.  Results never depend on it. */
-int gsm_isa_build(const gsm_dev_index* idx, uint32_t* isa, void* stream);
 
 /* Optional accelerator for the RMI lookups of gsm_smem_select: bounds[code] = {first row whose K-mer >= code, occurrences of
  * the K-mer} (two uint32) for all 4^K codes, K = the model's prediction size (K <= 16; 8.6 GB for K = 15).  The error-bounded

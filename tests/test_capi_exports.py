@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from genie_smem_b200 import _capi as capi
     assert C.sizeof(capi.IndexInfo) == 96      # 92 bytes of fields, 8-byte aligned
-    assert C.sizeof(capi.DevIndex) == 2 * 8 + 4 * 8 + 5 * 4 + 3 * 4 + 8 + 8  # + seed_table and isa pointers
+    assert C.sizeof(capi.DevIndex) == 2 * 8 + 4 * 8 + 5 * 4 + 3 * 4 + 8      # + seed_table pointer
     assert C.sizeof(capi.DevReads) == 8 + 3 * 8 + 2 * 4
     assert C.sizeof(capi.Workspace) == 15 * 8
     from genie_smem_b200.engine import RECORD_DTYPE

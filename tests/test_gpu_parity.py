@@ -472,7 +472,7 @@ def test_all_methods_vs_oracle_on_synthetic_reference(gs, seed_table):
     text = np.frombuffer(b"ACGT", np.uint8)[ref].tobytes()
     idx = gs.DeviceIndex.build_on_device(ref)
     if seed_table:
-        idx.build_seed_table().build_isa()              # + the unique-match shortcut of the sweep in both directions
+        idx.build_seed_table()
     sa = idx.suffix_array_host()
     reads_s = _codes_to_strings(reads)
     batch = gs.ReadBatch.from_codes(reads, L)
@@ -567,11 +567,5 @@ def test_reads_longer_than_the_shared_memory_path_vs_oracle(gs, matchers):
     exp = _oracle_dicts(text, gidx["suffix_array"], 0, reads, min_len=1)
     assert _dicts(reads, s.get_SMEMS_batch(reads, 1)) == exp
     assert _dicts(reads, s.get_smems_lut_batch(reads)) == _oracle_dicts(text, gidx["suffix_array"], 1, reads, K=10)
-    m.device_index.build_isa()                                              # long exact stretches: the shortcut to the left runs for thousands of bases
-    try:
-        assert _dicts(reads, s.get_SMEMS_batch(reads, 1)) == exp
-    finally:
-        m.device_index.isa = None
-        m.device_index._bind()
     with pytest.raises(ValueError):
         s.get_SMEMS_batch(["A" * 65536], 1)

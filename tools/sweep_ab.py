@@ -35,8 +35,6 @@ def main():
     index = g.DeviceIndex.build_on_device(ref_dev, "cuda")
     if a.seed_k != 0:
         index.build_seed_table(None if a.seed_k < 0 else a.seed_k)
-    if os.environ.get("AB_ISA"):                          # A/B: inverse suffix array -> unique matches also extended to the left along the text
-        index.build_isa()
     codes = torch.empty((a.reads, bench.READ_LEN), dtype=torch.uint8, device="cuda")
     if a.random_reads:
         gen = torch.Generator(device="cuda")
