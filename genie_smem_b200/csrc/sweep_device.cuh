@@ -453,8 +453,7 @@ struct DevSweepCtx1 {
                 const uint32_t pmax = __shfl_sync(FULLM, oe, (n - 1u) & 31u);
                 uint32_t picks = 0u;
                 for (uint32_t p = 0u; p < pmax;) {
-                    const uint32_t key = (lane < n && oe > p) ? ((os <= p ? 0x80000000u | ((oe - os) << 6) : 0u) | (63u - lane)) : 0u;
-                    const uint32_t b = 63u - (__reduce_max_sync(FULLM, key) & 63u);
+                    const uint32_t b = bwa_pick_of(__reduce_max_sync(FULLM, lane < n ? bwa_pick_key(os, oe, lane, p) : 0u));
                     picks |= 1u << b;
                     p = __shfl_sync(FULLM, oe, b);
                 }

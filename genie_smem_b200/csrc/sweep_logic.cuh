@@ -84,6 +84,18 @@ constexpr uint32_t SWEEP_CMP_CHUNK = 64;   // bases compared per text fetch
 //   void     cand_sync()                                make candidate writes visible to the pair
 //   void     emit(uint32_t idx, MemEntry e)             stage maximal match #idx of this read
 //   void     finish(uint32_t rid, uint32_t n_mems)      read complete
+// BWA-SMEM selection (get_SMEMS, SMEM.py:456-467 = Selector::run_bwa) as a MAXIMUM over the ordered match list: standing at
+// read position p the pick is the entry with the largest key -- entries ending at or before p are out (key 0); an entry
+// covering p beats every entry that starts beyond it, the longer one wins, ties go to the earlier entry; if nothing covers
+// p the first entry beyond it is taken (what covering_best returns then).  k = position in the ordered list (< 64),
+// lengths < 2^16.  The sweep's hand-over reduces these keys over the lanes of a warp (flush_finished), one pick per
+// reduction, then continues from the pick's end; tests/emu compares the same loop with Selector::run_bwa.
+GSM_HD uint32_t bwa_pick_key(uint32_t start, uint32_t end, uint32_t k, uint32_t p) {
+    if (end <= p) return 0u;
+    return (start <= p ? 0x80000000u | ((end - start) << 6) : 0u) | (63u - k);
+}
+GSM_HD uint32_t bwa_pick_of(uint32_t key) { return 63u - (key & 63u); }
+
 template <typename Ctx>
 struct Sweeper {
     int mode = M_FETCH;

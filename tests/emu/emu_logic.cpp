@@ -437,6 +437,21 @@ int emu_rmi_arith(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint3
     return 0;
 }
 
+// The BWA-SMEM picks as the sweep's hand-over makes them (maximum of bwa_pick_key over the ordered list, continue from the
+// pick's end) on a list of n <= 32 (start, end) pairs: the pick mask, bit = position in the list.
+uint32_t emu_bwa_picks(uint32_t n, const uint32_t* starts, const uint32_t* ends) {
+    uint32_t picks = 0;
+    if (n == 0 || n > 32) return 0;
+    for (uint32_t p = 0; p < ends[n - 1];) {
+        uint32_t best = 0;
+        for (uint32_t k = 0; k < n; ++k) { const uint32_t key = bwa_pick_key(starts[k], ends[k], k, p); if (key > best) best = key; }
+        const uint32_t b = bwa_pick_of(best);
+        picks |= 1u << b;
+        p = ends[b];
+    }
+    return picks;
+}
+
 // closed-form rmi_arith_lookup against the probe-by-probe loops on n random (start, A, cnt) triples of a table of n_rows
 // rows with the given None rows; returns the number of disagreements (outcome, bounds)
 uint64_t emu_rmi_arith_fuzz(uint32_t n_rows, uint32_t n_none, const uint32_t* none_rows, uint64_t n, uint64_t seed) {

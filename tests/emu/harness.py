@@ -44,6 +44,8 @@ class Emu:
                                           C.POINTER(u32), C.POINTER(u32)]
         self.lib.emu_rmi_arith.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u32, P, u64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                            C.POINTER(u32)]
+        self.lib.emu_bwa_picks.argtypes = [u32, P, P]
+        self.lib.emu_bwa_picks.restype = u32
         self.lib.emu_rmi_arith_fuzz.argtypes = [u32, u32, P, u64, u64]
         self.lib.emu_rmi_arith_fuzz.restype = u64
         self.lib.emu_rmi_search.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
@@ -140,6 +142,12 @@ class Emu:
         sk, st = self._seed_args()
         n = self.lib.emu_sweep(C.byref(self.e), w.ctypes.data, len(q), out.ctypes.data, len(q) + 1, C.byref(steps), sk, st)
         return [tuple(int(x) for x in out[4 * k:4 * k + 4]) for k in range(n)], steps.value
+
+    def bwa_picks(self, mems):
+        """Pick mask of the sweep's hand-over (bwa_pick_key) for an ordered match list [(start, end, ...), ...] of <= 32 entries."""
+        st = np.asarray([m[0] for m in mems], np.uint32)
+        en = np.asarray([m[1] for m in mems], np.uint32)
+        return int(self.lib.emu_bwa_picks(len(mems), st.ctypes.data, en.ctypes.data))
 
     def lut(self, K):
         if K not in self._lut:

@@ -58,6 +58,59 @@ def test_rmi_lookup_logic(emus, tag, name):
     assert n_arith > 0.8 * len(gu.load_json(f"rmi_lookups_{tag}.json.gz")[::3])
 
 
+def test_hand_over_picks_equal_run_bwa(emus):
+    """The BWA-SMEM picks the sweep's hand-over makes (one maximum of bwa_pick_key per pick) select exactly the records of
+    Selector::run_bwa (get_SMEMS, SMEM.py:456-467) -- on the golden reads of the three references, on low-complexity reads,
+    and on random lists with gaps (positions no match covers: outside the reference's domain, still the same picks)."""
+    n_checked = 0
+    for name, (g, em) in emus.items():
+        text = g["text"]
+        rng = random.Random(len(text))
+        reads = []
+        for _ in range(250):
+            L = rng.choice((30, 60, 101, 151))
+            p = rng.randrange(0, max(1, len(text) - L))
+            q = list(text[p:p + L])
+            for k in range(len(q)):
+                if rng.random() < 0.03:
+                    q[k] = rng.choice("ACGT")
+            reads.append("".join(q))
+        reads += ["A" * 40 + "C" + "A" * 30, "ACGT" * 20, "".join(rng.choice("ACGT") for _ in range(120))]
+        for q in reads:
+            mems, _ = em.sweep(q)
+            if not 1 <= len(mems) <= 32:
+                continue
+            mask = em.bwa_picks(mems)
+            picked = [(m[0], m[1], m[2], m[2] + m[3] - 1) for k, m in enumerate(mems) if (mask >> k) & 1]
+            assert picked == em.smem(0, q, min_len=1), (name, q)
+            n_checked += 1
+    assert n_checked > 600
+    _, em = emus["small_data"]
+    rng = random.Random(5)
+    for _ in range(20000):                                  # lists with gaps, against the literal loop of Selector::run_bwa
+        L = rng.randint(1, 60)
+        n = rng.randint(1, min(12, L))
+        ss, es = sorted(rng.sample(range(0, L), n)), sorted(rng.sample(range(1, L + 1), n))
+        mems = [(s, e) for s, e in zip(ss, es) if e > s]
+        if not mems:
+            continue
+        exp, p, frm = 0, 0, 0
+        while p < L and frm < len(mems):
+            while frm < len(mems) and mems[frm][1] <= p:
+                frm += 1
+            if frm >= len(mems):
+                break
+            best, bl = frm, 0
+            for k in range(frm, len(mems)):
+                if mems[k][0] > p:
+                    break
+                if mems[k][1] - mems[k][0] > bl:
+                    bl, best = mems[k][1] - mems[k][0], k
+            exp |= 1 << best
+            p = mems[best][1]
+        assert em.bwa_picks(mems) == exp, mems
+
+
 def test_closed_form_gallops_equal_the_probe_loops(emus):
     """rmi_arith_lookup computes the two exponential phases of RMI_LUT.exponential_search (RMI_LUT.py:151-178) in closed
     form; against the probe-by-probe loops on 6 M random and edge-case (start, bounds) triples: tiny and 2^31-row tables,
