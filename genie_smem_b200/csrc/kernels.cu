@@ -1,19 +1,23 @@
 // sm_100a kernels + C ABI of the SMEM-seeding engine.
 //
-// Work decomposition (B200: 148 SMs, 126 MB L2, HBM3e):
-//   * a rank query is one aligned 64-byte bucket = two 32-byte halves; a lane PAIR fetches it with one 256-bit load per
-//     lane (LDG.E.ENL2.256), so one warp-wide load instruction moves 16 buckets = 16 independent FM chains.  The path
-//     is random-access and latency-bound: no TMA, no tensor cores.
-//   * k_sweep (sweep_device.cuh): persistent grid, one lane pair per read (16 reads in flight per warp, dynamic read
-//     queue), bidirectional FM extension enumerating every maximal exact match of the read.  All pairs of a warp
-//     execute ONE uniform load/popcount section per iteration, so the 16 chains' fetches are in flight together.
-//   * k_select<BWA>: one thread per read, the reference's get_SMEMS selection over the match list.
+// Work decomposition (B200: 148 SMs, 126 MB L2, HBM3e).  The path is random access of 16..64 bytes behind dependent
+// addresses: no TMA, no tensor cores; what matters is how many independent fetches a warp keeps in flight.
+//   * a rank query is one aligned 64-byte bucket = two 32-byte halves, each one 256-bit load (LDG.E.ENL2.256).
+//   * k_sweep1 (sweep_device.cuh; the dominant kernel): persistent grid, ONE LANE PER READ (32 reads in flight per warp,
+//     dynamic read queue), bidirectional FM extension enumerating every maximal exact match of the read; per iteration
+//     every lane runs its control and the warp executes ONE uniform memory section (seed-table entry / bucket / suffix-array
+//     value / text words).  Finished reads hand their match lists over cooperatively (flush_finished): ordered, field by
+//     field, and with the BWA-SMEM picks already made.  k_sweep (lane pairs, round 1) is kept behind GSM_SWEEP_LPR=2.
+//   * BWA-SMEM selection: k_select_bwa_picked (count + min_len filter where the sweep made the picks), k_select<BWA> (one
+//     thread per read, Selector::run_bwa) for the reads it queues, k_select_bwa_finish.
 //   * k_select_seeded<LUT|RMI>: persistent threads, one read per thread, the reference's frame machine one ROUND at a
-//     time with the warp in lock step: pass 1 = all table lookups of the round (LUT gather; RMI predict + seed-table
-//     bounds + arithmetic replay of the error-bounded search, literal probe search only on a hazard), pass 2 = the
-//     integer machine, pass 3 = the (rare) explicit backward search of the round's winner.
-//   * k_scan_* / k_gather_records: counts -> offsets -> records in (read, emission) order; the destination may be a
-//     peer GPU's memory (gsm_peer_*), which makes the ordered write the NVLink gather of the multi-GPU path.
+//     time with the warp in lock step: pass 1 = all table lookups of the round, spread evenly over the warp's lanes, results
+//     in shared memory (LUT gather; RMI predict + true bounds from the k-mer bounds table or the seed table + the
+//     error-bounded search replayed on row numbers, literal probe search only on a hazard), pass 2 = the integer
+//     machine, pass 3 = the winner's interval; explicit backward searches are queued for k_resolve_lazy.
+//   * k_scan_* / k_gather_records: counts -> offsets -> records in (read, emission) order, from the record pool or
+//     straight from the picked match lists; the destination may be a peer GPU's memory (gsm_peer_*), which makes the
+//     ordered write the NVLink gather of the multi-GPU path.
 #include <cuda_runtime.h>
 
 #include <algorithm>

@@ -1,11 +1,14 @@
-// Device side of the sweep kernel.  Two lanes ("a pair") cooperate on every 64-byte rank bucket
-// of one read: each issues ONE 256-bit load for its half, popcounts up to 96 symbols and the two
-// halves are summed with one shuffle.  16 reads are in flight per warp, and the whole warp executes
-// ONE uniform load/popcount section per iteration (pair_step) so that all 16 chains' bucket fetches
-// are in flight together; the per-read control (sweep_logic.cuh) only touches registers and shared
-// memory.  (A 4-lane variant with 128-bit loads was measured first: 78 M reads/s against 103 M for
-// pairs on the same bench, because the kernel is instruction-issue bound, not bandwidth bound --
-// profiles/r01_notes.md.)
+// Device side of the sweep kernels.
+//   k_sweep1 (default): ONE LANE PER READ, 32 reads in flight per warp.  Every iteration each lane runs its per-read control
+//   (sweep_logic.cuh: registers and shared memory only) and then the whole warp executes ONE uniform memory section -- a
+//   predicated seed-table fetch, a predicated suffix-array / text fetch, and the two 256-bit loads of one rank bucket with
+//   the bit-plane masks built once and popcounted below both offsets (lane_step) -- so all 32 chains' fetches are in flight
+//   together.  Finished reads hand their matches to the pool cooperatively (flush_finished): one atomic per warp,
+//   coalesced copies, lists of up to 64 matches ordered and stored field by field, the BWA-SMEM picks of lists of up to 32
+//   made on the way.
+//   k_sweep (GSM_SWEEP_LPR=2, round 1): two lanes ("a pair") per read, one bucket half each, halves summed with one shuffle
+//   (pair_step); 16 reads per warp.  (A 4-lane variant with 128-bit loads was measured first: 78 M reads/s against 103 M for
+//   pairs, 187 M for one lane per read on the same bench -- profiles/r01_notes.md, r02_notes.md.)
 #pragma once
 #include <cuda_runtime.h>
 
