@@ -439,7 +439,7 @@ def main():
             gathered = {"records": int(tot.item()), "bytes": int(tot.item()) * 16, "per_rank": [int(x) for x in totals]}
     snaps["bwa"] = snapshot(n_par)
 
-    # ---- per-kernel split of the step + algorithmic bytes (roofline of the dominant kernel, k_sweep)
+    # ---- per-kernel split of the step + algorithmic bytes (roofline of the dominant kernel, k_sweep1)
     ms_sweep = timed(lambda: engine.sweep(batch), args.steps, 1)
     engine.sweep(batch)
     ms_sel_bwa = timed(lambda: engine.select(g.METHOD_BWA, batch, min_len=1), args.steps, 1)

@@ -400,7 +400,7 @@ class DeviceIndex:
     def build_seed_table(self, K=None):
         """Seed table of the sweep kernel (gsm_seed_table_build): 4^K x 16 bytes; K defaults to the largest value that
         still leaves 2+ expected occurrences per k-mer (14 at 1-3 Gbp: 4.3 GB, 12 at 100 Mbp; measured on B200 at 1 Gbp:
-        k_sweep 127 / 88 / 82 / 77 / 76 ms per 10 M reads for K = none / 11 / 12 / 13 / 14).  Results never depend on it."""
+        round-1 k_sweep 127 / 88 / 82 / 77 / 76 ms per 10 M reads for K = none / 11 / 12 / 13 / 14).  Results never depend on it."""
         if K is None:
             K = 1
             while K < 14 and self.n_rows / 4.0 ** (K + 1) >= 2.0:
@@ -717,7 +717,7 @@ class Engine:
         return self._reads_c
 
     def sweep(self, reads: ReadBatch):
-        """k_sweep: every maximal exact match of every read (method-independent FM walk)."""
+        """k_sweep1: every maximal exact match of every read (method-independent FM walk; also leaves the BWA-SMEM picks)."""
         r = self._check_batch(reads)
         capi.check(capi.lib.gsm_smem_sweep(C.byref(self.index.c), C.byref(r), C.byref(self.ws), _stream()))
         self.kernel_launches += 1 if reads.n else 0
