@@ -488,7 +488,22 @@ def main():
                                   "dominant_kernel": "k_sweep1" if ms_sweep >= ms_sel else f"k_select_seeded<{name.upper()}>"}
         return ms
 
-    method_leg("lut", g.METHOD_LUT, max(2, args.steps // 2), {"K": LUT_K, "lut": lut}, LUT_K, 32, {})
+    g.set_lut_frame_machine(False)
+    method_leg("lut", g.METHOD_LUT, max(2, args.steps // 2), {"K": LUT_K, "lut": lut}, LUT_K, 32,
+               {"selection": "the sweep's picks: get_smems_lut emits exactly get_SMEMS's records with min_len 1 for reads of >= K bases "
+                             "(DESIGN.md section 3); K flags reads that are too short"})
+    if extras and world == 1:
+        # the reference's frame machine itself (k_select_seeded<LUT>): same records, the cross-check of the identity above
+        g.set_lut_frame_machine(True)
+        try:
+            ms_m = timed(lambda: step(g.METHOD_LUT, K=LUT_K, lut=lut), 2, 1)
+            engine.check_overflow()
+            snaps["lut_frame_machine"] = snapshot(n_par)
+            engine.sweep(batch)
+            methods["lut"]["frame_machine_reads_per_s"] = job_reads / (ms_m * 1e-3)
+            methods["lut"]["frame_machine_select_ms"] = round(timed(lambda: engine.select(g.METHOD_LUT, batch, K=LUT_K, lut=lut), 2, 1), 3)
+        finally:
+            g.set_lut_frame_machine(False)
     if rmi is not None:
         P = 2 * int(np.ceil(np.log2(2 * rmi.max_err + 2)))
         method_leg("rmi", g.METHOD_RMI, max(2, args.steps // 2), {"rmi": rmi}, RMI_K, 64 * P,
@@ -640,6 +655,8 @@ def main():
                                       f"O(L^2) restarts included) on {thr} pthreads"}
         v2, _, _, out, counts = cpu_arm(o, reads_head, 1, 0, budget / 2, K=LUT_K, n_min=n_par)
         parity["lut"], _ = compare_with_oracle(reads_head, snaps["lut"], out, counts, n_par)
+        if "lut_frame_machine" in snaps:
+            parity["lut_frame_machine"], _ = compare_with_oracle(reads_head, snaps["lut_frame_machine"], out, counts, n_par)
         if cpu_baseline:
             cpu_baseline["lut_reads_per_s"] = round(v2, 1)
         if rmi is not None:
@@ -669,7 +686,7 @@ def main():
             out["gather_transport"] = ("peer mapping (CUDA IPC): each rank's ordered-write kernel stores into rank 0's buffer" if gat.fused else
                                        f"NCCL send/recv per batch (peer mapping unavailable: {gat.fallback_reason})")
         emit_result(out)
-    bad = rank == 0 and parity is not None and any(parity.get(k, 0) for k in ("bwa", "lut", "rmi", "rmi_probe_search", "rmi_seed_table_lookup"))
+    bad = rank == 0 and parity is not None and any(parity.get(k, 0) for k in ("bwa", "lut", "lut_frame_machine", "rmi", "rmi_probe_search", "rmi_seed_table_lookup"))
     if world > 1:
         dist.destroy_process_group()
     if bad:

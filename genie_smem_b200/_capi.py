@@ -88,6 +88,7 @@ EXPORTS = {
     "gsm_smem_collect": (C.c_int, [C.POINTER(DevReads), C.POINTER(Workspace), C.c_void_p, C.c_uint64, C.c_void_p]),
     "gsm_rmi_probe_build": (C.c_int, [C.POINTER(DevIndex), C.c_void_p, C.c_void_p]),
     "gsm_rmi_bounds_build": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p]),
+    "gsm_option_lut_frame_machine": (C.c_int, [C.c_int]),
     "gsm_rmi_none_rows": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_rmi_lookup_batch": (C.c_int, [C.POINTER(DevIndex), C.POINTER(DevRmi), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),

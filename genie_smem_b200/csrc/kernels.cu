@@ -44,6 +44,8 @@ namespace gsm {
     } while (0)
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
+// gsm_option_lut_frame_machine: 0 = LUT-SMEM records are taken from the sweep's picks (see gsm_smem_select), 1 = k_select_seeded<LUT>
+static int g_lut_frame_machine = getenv("GSM_LUT_MACHINE") ? atoi(getenv("GSM_LUT_MACHINE")) : 0;
 constexpr int SELECT_THREADS = 128;
 constexpr int SELECT_BLOCKS = 7;             // k_select_seeded: resident blocks per SM the registers are allocated for
 constexpr int SELECT_DEFAULT_OPT_LUT = 1;    // measured per method (tools/sweep_ab.py, profiles/r02_notes.md)
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(SELECT_THREADS) k_select(const SelectArgs a, c
                             __ldg(a.len + rid), a.K, mc & MEMS_COUNT, a.min_len, (uint32_t)rid, 0u, false, false, (mc & MEMS_ORDERED) != 0u};
         if (!c.soa) order_segments(c.mems, c.n_mems);        // MEMS_ORDERED: the sweep already ordered the list
         bool direct = false;
+        if (a.K != 0u && c.L < a.K) { c.close(GSM_READ_TOO_SHORT, direct); continue; }       // LUT-SMEM through this kernel: K = the table's k
         do {
             static_assert(METHOD == GSM_METHOD_BWA, "LUT- and RMI-SMEM run in k_select_seeded");
             Selector<DevSelCtx<METHOD>>::run_bwa(c);
@@ -282,7 +285,9 @@ __global__ void __launch_bounds__(256) k_select_bwa_picked(const SelectArgs a, u
     bool later = false;
     if (rid < a.n_reads) {
         const uint32_t mc = a.mem_cnt[rid];
-        if (mc & MEMS_PICKED) {
+        if (a.K != 0u && __ldg(a.len + rid) < a.K) {                  // LUT-SMEM through this kernel: reads shorter than the table's k
+            a.rec_cnt[rid] = 0u; a.rec_tmp_off[rid] = 0u; a.read_status[rid] = GSM_READ_TOO_SHORT;
+        } else if (mc & MEMS_PICKED) {
             const uint32_t n = mc & MEMS_COUNT;
             const uint32_t* seg = reinterpret_cast<const uint32_t*>(a.mem_pool + a.mem_off[rid]);
             uint32_t picks = seg[3u * n];
@@ -1456,6 +1461,12 @@ int gsm_smem_sweep(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_workspa
     return GSM_OK;
 }
 
+int gsm_option_lut_frame_machine(int on) {
+    const int before = g_lut_frame_machine;
+    if (on >= 0) g_lut_frame_machine = on ? 1 : 0;
+    return before;
+}
+
 int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd, uint32_t min_len, uint32_t K, const uint32_t* lut,
                     const gsm_dev_rmi* rmi, gsm_workspace* ws, void* stream_) {
     int sb = 0, lb = 0;
@@ -1478,6 +1489,13 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
     SelectArgs se;
     se.fwd = (const uint4*)ix->fwd_buckets; se.meta = make_meta(ix); se.n_bases = ix->n_rows - 1; se.sa = ix->sa; se.text = ix->text2bit; se.probe = (method == GSM_METHOD_RMI && rmi) ? (const uint4*)rmi->probe : nullptr;
     se.reads = (const uint32_t*)rd->packed; se.chunk_off = rd->chunk_off; se.len = rd->len; se.n_reads = (uint32_t)rd->n_reads;
+    // LUT-SMEM emits exactly the records of BWA-SMEM with min_len 1 for every read of at least K bases (DESIGN.md section 3:
+    // each round of get_smems_lut returns the longest maximal match covering the previous SMEM's end, ties to the smaller end,
+    // which is get_SMEMS's pick): unless the frame machine is asked for (gsm_option_lut_frame_machine) the records are the
+    // sweep's picks, and K only decides which reads are too short.
+    const bool lut_as_picks = method == GSM_METHOD_LUT && g_lut_frame_machine == 0;
+    if (lut_as_picks) { method = GSM_METHOD_BWA; min_len = 1; }
+    else if (method == GSM_METHOD_BWA) K = 0;
     se.max_len = rd->max_len; se.read_id_base = rd->read_id_base; se.min_len = min_len; se.K = K; se.lut = (const uint2*)lut; se.rmi = rm;
     se.rmi_bounds = (method == GSM_METHOD_RMI && rmi && rm.n_none != 0u && K <= 16) ? (const uint2*)rmi->bounds : nullptr;
     se.seed_tab = (const uint4*)ix->seed_table; se.seed_K = ix->seed_table ? ix->seed_K : 0u;

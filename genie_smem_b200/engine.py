@@ -730,11 +730,16 @@ class Engine:
                                             C.byref(rmi.c) if rmi is not None else None, C.byref(self.ws), _stream()))
         if gatherer is not None:
             gatherer.collect(self, r)
-            self.kernel_launches += (8 if method == capi.METHOD_BWA else 7) if reads.n else 1
+            self.kernel_launches += (8 if self._picks_path(method) else 7) if reads.n else 1
             return
         capi.check(capi.lib.gsm_smem_collect(C.byref(r), C.byref(self.ws), _ptr(self.records), self.rec_cap, _stream()))
         # BWA: picked / queued / finish; LUT, RMI: select + the deferred explicit searches; then 3 scan kernels, ordered write
-        self.kernel_launches += (7 if method == capi.METHOD_BWA else 6) if reads.n else 0
+        self.kernel_launches += (7 if self._picks_path(method) else 6) if reads.n else 0
+
+    @staticmethod
+    def _picks_path(method):
+        """BWA-SMEM, and LUT-SMEM unless the frame machine is asked for: picked / queued / finish kernels."""
+        return method == capi.METHOD_BWA or (method == capi.METHOD_LUT and capi.lib.gsm_option_lut_frame_machine(-1) == 0)
 
     def collect_local(self, reads: ReadBatch):
         """(Re)write the records of the batch just selected into this engine's own `records` buffer."""
@@ -829,6 +834,14 @@ def sa_lookup(index: DeviceIndex, rows):
     out = torch.empty_like(r)
     capi.check(capi.lib.gsm_sa_lookup_batch(C.byref(index.c), rows.size, _ptr(r), _ptr(out), _stream()))
     return out.cpu().numpy().view(np.uint32)
+
+
+def set_lut_frame_machine(on=True):
+    """LUT-SMEM selection: False (default) = the records are the sweep's picks (get_smems_lut emits exactly get_SMEMS's
+    records with min_len 1 for reads of at least K bases); True = run the reference's frame machine itself
+    (k_select_seeded<LUT>, the cross-check: same records).  Process-wide (gsm_option_lut_frame_machine); returns the
+    previous setting."""
+    return bool(capi.lib.gsm_option_lut_frame_machine(1 if on else 0))
 
 
 def lut_build(index: DeviceIndex, K):

@@ -290,6 +290,14 @@ int gsm_smem_batch(int method, const gsm_dev_index* idx, const gsm_dev_reads* re
                    uint32_t K, const uint32_t* lut, const gsm_dev_rmi* rmi, gsm_workspace* ws,
                    void* stream);
 
+/* get_smems_lut (SMEM.py:20-192) emits exactly the records of get_SMEMS (SMEM.py:456-467) with min_len 1 for every read of at
+ * least K bases: each round of its frame machine returns the longest maximal match covering the previous SMEM's end, ties to
+ * the smaller end (checked on 11.5 M adversarial cases of the literal restatement).  By default
+ * gsm_smem_select(GSM_METHOD_LUT) therefore takes the records from the sweep's picks and uses K only to flag reads that are too
+ * short; on = 1 runs the frame machine itself (k_select_seeded<LUT>: same records, the cross-check), on < 0 only queries.
+ * Returns the previous setting.  Process-wide; GSM_LUT_MACHINE=1 in the environment sets the initial value. */
+int gsm_option_lut_frame_machine(int on);
+
 /* The two halves of gsm_smem_batch, callable separately (bench.py times them separately).
  * gsm_smem_sweep: every maximal exact match of every read (the FM-index walk, method-independent)
  * into ws->mem_pool / mem_off / mem_cnt.  gsm_smem_select: the reference's record selection for

