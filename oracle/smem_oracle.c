@@ -527,8 +527,12 @@ static void* worker(void* arg) {
             rec_t* recs = (rec_t*)malloc(sizeof(rec_t) * ((size_t)L + 2));
             int ok = 1;
             for (int t = 0; t < L; ++t) { int c = code_of(j->reads[j->off[r] + t]); if (c < 0) ok = 0; q[t] = (uint8_t)c; }
-            int n = 0;
+            int n = 0, absent = 0;
+            /* a base that does not occur in the text: count_dic[char] raises KeyError (ExactMatch.py:140) the first time it is
+             * queried, and every base of a read is queried (without this the walk below would not advance past it) */
+            for (int t = 0; ok && t < L; ++t) if (j->ix->cnt[q[t]] == 0) absent = 1;
             if (!ok) { j->bad = 1; n = 0; }
+            else if (absent) n = -1;
             else if (j->method == 0) n = smems_bwa(j->ix, q, L, j->min_len, recs, val, has);
             else if (L < j->K) n = -2;
             else {

@@ -67,3 +67,34 @@ def test_smem_sets(orcs, fname):
                 assert got[k] == "raises"
             else:
                 assert got[k] == exp[i]
+
+
+def test_lut_identity_exhaustive_slice():
+    """get_smems_lut == get_SMEMS(min_len 1) record for record on reads of at least K bases -- the identity
+    gsm_smem_select(LUT) relies on -- exhaustively on a small world: every reference over ACGT of 4..5
+    bases that contains all four, every read of 1..5 bases, K = 1..3 (tools/lut_identity_exhaustive.py ran 4..7 x 1..7 x 1..4)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "lut_identity_exhaustive", os.path.join(os.path.dirname(__file__), "..", "tools", "lut_identity_exhaustive.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    reads = tool.all_reads(5)
+    lens = np.asarray([len(r) for r in reads], np.uint32)
+    joined = "".join(reads).encode()
+    n = sum(tool.check_text(t, reads, joined, lens, 3) for t in tool.texts(4, 5))
+    assert n > 1_000_000
+
+
+def test_base_absent_from_the_reference_raises():
+    """count_dic[char] raises KeyError for a base the reference does not contain (ExactMatch.py:140): the oracle reports the
+    read as 'raises' (and terminates) instead of walking a position it can never pass."""
+    import genie_smem_b200 as gs
+    text = "AAGTAGGTTA"
+    sa, _ = gs.HostIndex.build(text).export()
+    o = COracle(text, sa)
+    reads = ["AAGT", "ACGT", "C", "GGTT", "TTAC"]
+    for method, kw in ((0, {"min_len": 1}), (1, {"K": 2})):
+        got = o.smem_dicts(method, reads, **kw)
+        assert [g == "raises" for g in got] == [False, True, True, False, True]
+        assert got[0][0][0] == "AAGT" and got[3][0][0] == "GGTT"

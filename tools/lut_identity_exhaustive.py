@@ -8,6 +8,8 @@ ACGT of length 4..n_max that contains all four bases x every read over ACGT of l
 infrastructure only (imports oracle/); tests/test_logic_emu.py runs a bounded slice of it.
 
     python tools/lut_identity_exhaustive.py [n_max=6] [l_max=7] [k_max=4]
+    python tools/lut_identity_exhaustive.py ac [n_max=12] [l_max=10] [k_max=6]   # repetitive worlds: references = every string
+                                                                                 # over AC of 2..n_max bases + "GT", reads over AC
 """
 import itertools
 import os
@@ -18,10 +20,10 @@ import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
 
-def all_reads(l_max):
+def all_reads(l_max, alphabet="ACGT"):
     reads = []
     for L in range(1, l_max + 1):
-        reads += ["".join(t) for t in itertools.product("ACGT", repeat=L)]
+        reads += ["".join(t) for t in itertools.product(alphabet, repeat=L)]
     return reads
 
 
@@ -51,25 +53,38 @@ def texts(n_min, n_max):
                 yield "".join(t)
 
 
+def texts_ac(n_min, n_max):
+    for n in range(n_min, n_max + 1):
+        for t in itertools.product("AC", repeat=n):
+            if len(set(t)) == 2:                 # all four bases present, as above
+                yield "".join(t) + "GT"
+
+
 def _work(args):
-    text, l_max, k_max = args
-    reads = _work.reads if getattr(_work, "l_max", None) == l_max else None
+    text, l_max, k_max, alphabet = args
+    reads = _work.reads if getattr(_work, "key", None) == (l_max, alphabet) else None
     if reads is None:
-        _work.reads, _work.l_max = all_reads(l_max), l_max
+        _work.reads, _work.key = all_reads(l_max, alphabet), (l_max, alphabet)
         _work.lens = np.asarray([len(r) for r in _work.reads], np.uint32)
         _work.joined = "".join(_work.reads).encode()
     return check_text(text, _work.reads, _work.joined, _work.lens, k_max)
 
 
 def main():
-    n_max = int(sys.argv[1]) if len(sys.argv) > 1 else 6
-    l_max = int(sys.argv[2]) if len(sys.argv) > 2 else 7
-    k_max = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+    argv = sys.argv[1:]
+    ac = bool(argv) and argv[0] == "ac"
+    if ac:
+        argv = argv[1:]
+    n_max = int(argv[0]) if len(argv) > 0 else (12 if ac else 6)
+    l_max = int(argv[1]) if len(argv) > 1 else (10 if ac else 7)
+    k_max = int(argv[2]) if len(argv) > 2 else (6 if ac else 4)
     from multiprocessing import Pool
-    jobs = [(t, l_max, k_max) for t in texts(4, n_max)]
+    jobs = [(t, l_max, k_max, "AC" if ac else "ACGT") for t in (texts_ac(2, n_max) if ac else texts(4, n_max))]
     with Pool(os.cpu_count()) as pool:
         total = sum(pool.imap_unordered(_work, jobs, chunksize=8))
-    print(f"{len(jobs)} references (length 4..{n_max}, all four bases) x every read of length 1..{l_max} x K = 1..{k_max}: "
+    world = (f"every string over AC of 2..{n_max} bases + 'GT', reads over AC" if ac else
+             f"length 4..{n_max} over ACGT, all four bases present, reads over ACGT")
+    print(f"{len(jobs)} references ({world}) x every read of length 1..{l_max} x K = 1..{k_max}: "
           f"{total} cases, get_smems_lut == get_SMEMS(min_len 1) in every one")
 
 
