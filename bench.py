@@ -513,6 +513,22 @@ def main():
                               " + arithmetic replay of the error-bounded search (no probes); literal search on hazards"})
         st = engine.read_status[:n_reads]
         methods["rmi"]["reads_where_reference_raises"] = int((st == g.READ_REF_RAISES).sum().item())
+        methods["rmi"]["prefilter"] = {
+            "hazard_codes": rmi.n_hazards, "codes": 4 ** RMI_K, "active": rmi.hazard_slots is not None,
+            "what": "reads without a hazard window (a k-mer code whose last-mile search is not certified exact) take the BWA-SMEM "
+                    "records with min_len 1 (k_rmi_prefilter + k_select<BWA>); only the others run the frame machine"}
+        if extras and world == 1 and rmi.hazard_slots is not None:
+            # the reference's frame machine on every read (k_select_seeded<RMI> alone): same records, the cross-check
+            g.set_rmi_prefilter(False)
+            try:
+                ms_m = timed(lambda: step(g.METHOD_RMI, rmi=rmi), 2, 1)
+                engine.check_overflow()
+                snaps["rmi_frame_machine"] = snapshot(n_par)
+                engine.sweep(batch)
+                methods["rmi"]["frame_machine_reads_per_s"] = job_reads / (ms_m * 1e-3)
+                methods["rmi"]["frame_machine_select_ms"] = round(timed(lambda: engine.select(g.METHOD_RMI, batch, rmi=rmi), 2, 1), 3)
+            finally:
+                g.set_rmi_prefilter(True)
         if extras and world == 1:
             if rmi.bounds is not None:
                 # the same lookups with the true bounds taken from the sweep's seed table + K - seed_K backward steps
@@ -664,6 +680,8 @@ def main():
             parity["rmi"], parity["ref_raises"] = compare_with_oracle(reads_head, snaps["rmi"], out, counts, n_par)
             if "rmi_probe" in snaps:
                 parity["rmi_probe_search"], _ = compare_with_oracle(reads_head, snaps["rmi_probe"], out, counts, n_par)
+            if "rmi_frame_machine" in snaps:
+                parity["rmi_frame_machine"], _ = compare_with_oracle(reads_head, snaps["rmi_frame_machine"], out, counts, n_par)
             if "rmi_seed_table" in snaps:
                 parity["rmi_seed_table_lookup"], _ = compare_with_oracle(reads_head, snaps["rmi_seed_table"], out, counts, n_par)
             if cpu_baseline:
@@ -686,7 +704,7 @@ def main():
             out["gather_transport"] = ("peer mapping (CUDA IPC): each rank's ordered-write kernel stores into rank 0's buffer" if gat.fused else
                                        f"NCCL send/recv per batch (peer mapping unavailable: {gat.fallback_reason})")
         emit_result(out)
-    bad = rank == 0 and parity is not None and any(parity.get(k, 0) for k in ("bwa", "lut", "lut_frame_machine", "rmi", "rmi_probe_search", "rmi_seed_table_lookup"))
+    bad = rank == 0 and parity is not None and any(parity.get(k, 0) for k in ("bwa", "lut", "lut_frame_machine", "rmi", "rmi_frame_machine", "rmi_probe_search", "rmi_seed_table_lookup"))
     if world > 1:
         dist.destroy_process_group()
     if bad:

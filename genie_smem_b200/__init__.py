@@ -6,7 +6,7 @@ GPU every search call raises.
 """
 from . import _capi  # noqa: F401  (fails loudly when the CUDA library is missing)
 from .engine import (BaseError, DeviceIndex, Engine, HostIndex, IndexFile, PackedIndex, PipelinedEngine, ReadBatch, RmiParams, RECORD_DTYPE, SmemResult,  # noqa: F401
-                     add_one_batch, backsearch_batch, gather_probe, gather_probe2, l2_fetch_granularity, lut_build, rmi_lookup_batch, sa_lookup, set_lut_frame_machine)
+                     add_one_batch, backsearch_batch, gather_probe, gather_probe2, l2_fetch_granularity, lut_build, rmi_lookup_batch, sa_lookup, set_lut_frame_machine, set_rmi_prefilter)
 from .ingest import read_fasta, read_fastq, write_fastq  # noqa: F401
 from .surface import (ExactMatch, LUT, RMI, RMI_LUT, SMEM, create_query_from_ref, create_random_query)  # noqa: F401
 from ._capi import METHOD_BWA, METHOD_LUT, METHOD_RMI, READ_OK, READ_REF_RAISES, READ_TOO_SHORT, GsmError  # noqa: F401

@@ -36,7 +36,8 @@ class DevReads(C.Structure):
 
 class DevRmi(C.Structure):
     _fields_ = [("K", C.c_uint32), ("n_levels", C.c_uint32), ("level_sizes", u32p), ("coef", C.c_void_p), ("intercept", C.c_void_p), ("probe", C.c_void_p),
-                ("none_rows", u32p), ("n_none_rows", C.c_uint32), ("param_stride", C.c_uint32), ("bounds", C.c_void_p)]
+                ("none_rows", u32p), ("n_none_rows", C.c_uint32), ("param_stride", C.c_uint32), ("bounds", C.c_void_p),
+                ("hazard_slots", C.c_void_p), ("hazard_n_slots", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 class Workspace(C.Structure):
@@ -89,6 +90,9 @@ EXPORTS = {
     "gsm_rmi_probe_build": (C.c_int, [C.POINTER(DevIndex), C.c_void_p, C.c_void_p]),
     "gsm_rmi_bounds_build": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p]),
     "gsm_option_lut_frame_machine": (C.c_int, [C.c_int]),
+    "gsm_option_rmi_prefilter": (C.c_int, [C.c_int]),
+    "gsm_rmi_hazard_scan": (C.c_int, [C.POINTER(DevIndex), C.POINTER(DevRmi), C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
+    "gsm_rmi_hazard_hash": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]),
     "gsm_rmi_none_rows": (C.c_int, [C.POINTER(DevIndex), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsm_rmi_lookup_batch": (C.c_int, [C.POINTER(DevIndex), C.POINTER(DevRmi), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -46,6 +46,10 @@ namespace gsm {
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 // gsm_option_lut_frame_machine: 0 = LUT-SMEM records are taken from the sweep's picks (see gsm_smem_select), 1 = k_select_seeded<LUT>
 static int g_lut_frame_machine = getenv("GSM_LUT_MACHINE") ? atoi(getenv("GSM_LUT_MACHINE")) : 0;
+// gsm_option_rmi_prefilter: 1 = RMI-SMEM reads without a hazard window take their records from the BWA-SMEM selection
+// (k_rmi_prefilter, see gsm_smem_select), 0 = every read runs the frame machine (k_select_seeded<RMI>)
+static int g_rmi_prefilter = getenv("GSM_RMI_PREFILTER") ? atoi(getenv("GSM_RMI_PREFILTER")) : 1;
+constexpr uint8_t READ_PENDING = 0xFFu;      // read_status while a pre-filtered RMI batch waits for the frame machine (never survives a select)
 constexpr int SELECT_THREADS = 128;
 constexpr int SELECT_BLOCKS = 7;             // k_select_seeded: resident blocks per SM the registers are allocated for
 constexpr int SELECT_DEFAULT_OPT_LUT = 1;    // measured per method (tools/sweep_ab.py, profiles/r02_notes.md)
@@ -86,6 +90,9 @@ struct SelectArgs {
     unsigned long long* counters;
     uint4* fix;                 // deferred explicit searches {read, record ordinal, start | end << 16, 0} (k_resolve_lazy): the tail of the record pool
     unsigned long long fix_cap;
+    const uint32_t* hz_slots;   // RMI pre-filter: hash set of the model's hazard codes (gsm_rmi_hazard_scan / gsm_rmi_hazard_hash), else NULL
+    uint32_t hz_mask;           // slots - 1
+    uint32_t only_pending;      // k_select_seeded: run only the reads k_rmi_prefilter left at READ_PENDING
 };
 
 // 16-byte probe record {s, code64 hi, code64 lo, 0}: one fetch per get_ref_seq (RMI_LUT.py:89-92)
@@ -317,6 +324,52 @@ __global__ void __launch_bounds__(256) k_select_bwa_picked(const SelectArgs a, u
 // after the two BWA kernels: counters[1] (records of the batch; so far the pool cursor of k_select<BWA>) += counters[6]
 __global__ void k_select_bwa_finish(unsigned long long* counters) { counters[1] += counters[6]; }
 
+// RMI-SMEM pre-filter, one thread per read: a read none of whose K-mer windows is a hazard code of the model (select_logic.cuh,
+// "hazard codes of a model") emits exactly the BWA-SMEM records with min_len 1, so it is queued for k_select<BWA> (which also
+// flags reads shorter than K); a read with a hazard window is left at READ_PENDING for the frame machine (k_select_seeded<RMI>
+// with only_pending).  Queue: 4 read numbers per 16-byte slot of the record pool's last eighth, length in counters[4].
+__global__ void __launch_bounds__(256) k_rmi_prefilter(const SelectArgs a, uint32_t* queue) {
+    const size_t rid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool picks = false;
+    if (rid < a.n_reads) {
+        const uint32_t* w = a.reads + (size_t)__ldg(a.chunk_off + rid) * 4;
+        const uint32_t* slots = a.hz_slots;
+        picks = rmi_read_hazard_free([w](uint32_t x) { return __ldg(w + x); }, __ldg(a.len + rid), a.K,
+                                     [slots](uint32_t h) { return __ldg(slots + h); }, a.hz_mask);
+        if (!picks) a.read_status[rid] = READ_PENDING;
+    }
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t pm = __ballot_sync(FULL, picks);
+    if (pm) {
+        unsigned long long slot = 0;
+        if (lane == (uint32_t)__ffs((int)pm) - 1u) slot = atomicAdd(&a.counters[4], (unsigned long long)__popc(pm));
+        slot = __shfl_sync(FULL, slot, __ffs((int)pm) - 1);
+        if (picks) queue[slot + __popc(pm & ((1u << lane) - 1u))] = (uint32_t)rid;
+    }
+}
+
+// Every K-mer code whose lookup the arithmetic replay cannot certify (rmi_code_is_hazard) is appended to out[] (at most cap
+// codes are stored; *count keeps counting, so the caller sees an overflow).  bounds = gsm_rmi_bounds_build's table.
+__global__ void __launch_bounds__(256) k_rmi_hazard_scan(RmiModel m, const uint2* bounds, uint64_t n_codes, uint32_t n_rows, uint32_t* out,
+                                                         unsigned long long cap, unsigned long long* count) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint64_t code = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; code - lane < n_codes; code += stride) {     // whole warps take a trip
+        bool hz = false;
+        if (code < n_codes) {
+            const uint2 b = __ldg(bounds + code);
+            hz = rmi_code_is_hazard(m, code, b.x, b.y, n_rows);
+        }
+        const uint32_t hm = __ballot_sync(FULL, hz);                   // a poor model has hazards everywhere: one atomic per warp
+        if (hm) {
+            unsigned long long k = 0;
+            if (lane == (uint32_t)__ffs((int)hm) - 1u) k = atomicAdd(count, (unsigned long long)__popc(hm));
+            k = __shfl_sync(FULL, k, __ffs((int)hm) - 1) + __popc(hm & ((1u << lane) - 1u));
+            if (hz && k < cap) out[k] = (uint32_t)code;
+        }
+    }
+}
+
 // The lookup results of one round (Selector::round_decide's `win`) in shared memory: two planes (lo, hi) of K windows x
 // WIN_STRIDE words, window i of a thread at word i * WIN_STRIDE + threadIdx.x -- nothing of it lives in local memory (as
 // per-thread arrays the two planes were 512 bytes of stack per thread: with 151,552 resident threads more than the L2
@@ -473,6 +526,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, MB) k_select_seeded(const __gr
     // open reads until one needs a round (reads shorter than K are closed at once)
     auto open_reads = [&]() {
         while (!have && rid < a.n_reads) {
+            if (a.only_pending && a.read_status[rid] != READ_PENDING) { rid += nthreads; continue; }     // k_rmi_prefilter gave it to k_select<BWA>
             c.words = a.reads + (size_t)__ldg(a.chunk_off + rid) * 4;
             c.mems = a.mem_pool + a.mem_off[rid];
             const uint32_t mc = a.mem_cnt[rid];
@@ -1382,6 +1436,39 @@ int gsm_rmi_bounds_build(const gsm_dev_index* ix, uint32_t K, void* bounds, void
     return GSM_OK;
 }
 
+int gsm_rmi_hazard_scan(const gsm_dev_index* ix, const gsm_dev_rmi* rmi, uint32_t* codes, uint64_t cap, uint64_t* count_dev,
+                        uint64_t* n_found, void* stream) {
+    if (!ix || !rmi || !rmi->bounds || !codes || !count_dev || !n_found || cap == 0)
+        return fail(GSM_E_INVALID, "gsm_rmi_hazard_scan: needs the bounds table, a code buffer and a device counter");
+    if (rmi->K < 1 || rmi->K > 15) return fail(GSM_E_INVALID, "gsm_rmi_hazard_scan: K in 1..15 (32-bit codes)");
+    int st = device_ready();
+    if (st) return st;
+    RmiModel m;
+    if ((st = fill_rmi(rmi, &m, ix->n_rows))) return st;
+    if (m.n_none == 0u) return fail(GSM_E_INVALID, "gsm_rmi_hazard_scan: needs none_rows (gsm_rmi_none_rows)");
+    cudaStream_t s_ = (cudaStream_t)stream;
+    const uint64_t n_codes = 1ull << (2 * rmi->K);
+    int dev = 0, sms = 148;
+    GSM_CUDA(cudaGetDevice(&dev));
+    GSM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    uint64_t blocks = (n_codes + 255) / 256;
+    if (blocks > (uint64_t)sms * 64) blocks = (uint64_t)sms * 64;
+    GSM_CUDA(cudaMemsetAsync(count_dev, 0, sizeof(uint64_t), s_));
+    k_rmi_hazard_scan<<<(unsigned)blocks, 256, 0, s_>>>(m, (const uint2*)rmi->bounds, n_codes, (uint32_t)ix->n_rows, codes, cap,
+                                                       (unsigned long long*)count_dev);
+    GSM_CUDA(cudaGetLastError());
+    GSM_CUDA(cudaMemcpyAsync(n_found, count_dev, sizeof(uint64_t), cudaMemcpyDeviceToHost, s_));
+    GSM_CUDA(cudaStreamSynchronize(s_));
+    return GSM_OK;
+}
+
+int gsm_rmi_hazard_hash(const uint32_t* codes, uint64_t n, uint32_t* slots, uint32_t n_slots) {
+    if ((!codes && n) || !slots) return fail(GSM_E_INVALID, "gsm_rmi_hazard_hash: null");
+    if (!hz_build(codes, n, slots, n_slots))
+        return fail(GSM_E_INVALID, "gsm_rmi_hazard_hash: n_slots must be a power of two in [2 n + 2, 2^24] and no code may be 0xFFFFFFFF");
+    return GSM_OK;
+}
+
 int gsm_rmi_probe_build(const gsm_dev_index* ix, void* probe, void* stream) {
     if (!ix || !ix->sa || !ix->text2bit || !probe) return fail(GSM_E_INVALID, "gsm_rmi_probe_build needs sa + text on the device");
     int st = device_ready();
@@ -1461,6 +1548,12 @@ int gsm_smem_sweep(const gsm_dev_index* ix, const gsm_dev_reads* rd, gsm_workspa
     return GSM_OK;
 }
 
+int gsm_option_rmi_prefilter(int on) {
+    const int before = g_rmi_prefilter;
+    if (on >= 0) g_rmi_prefilter = on ? 1 : 0;
+    return before;
+}
+
 int gsm_option_lut_frame_machine(int on) {
     const int before = g_lut_frame_machine;
     if (on >= 0) g_lut_frame_machine = on ? 1 : 0;
@@ -1503,6 +1596,7 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
     se.rec_tmp = (uint4*)ws->rec_tmp; se.rec_cap = ws->rec_cap; se.rec_tmp_off = ws->rec_tmp_off; se.rec_cnt = ws->rec_cnt;
     se.read_status = ws->read_status; se.counters = (unsigned long long*)ws->counters;
     se.fix = nullptr; se.fix_cap = 0;
+    se.hz_slots = nullptr; se.hz_mask = 0u; se.only_pending = 0u;
     if (method != GSM_METHOD_BWA) {           // deferred explicit searches queue in the last eighth of the record pool (at most one per read)
         const uint64_t reserve = ws->rec_cap / 8 < rd->n_reads ? ws->rec_cap / 8 : rd->n_reads;
         se.rec_cap = ws->rec_cap - reserve;
@@ -1532,6 +1626,24 @@ int gsm_smem_select(int method, const gsm_dev_index* ix, const gsm_dev_reads* rd
     } else {
         GSM_CUDA(cudaMemsetAsync((unsigned long long*)ws->counters + 5, 0, sizeof(uint64_t), stream));
         const bool arith = rm.n_none != 0u && se.seed_K != 0u && se.seed_K <= K;       // lookups from the seed table: no probes
+        // RMI-SMEM pre-filter (with the bounds table and the model's hazard set): reads without a hazard window emit the
+        // BWA-SMEM records with min_len 1 (select_logic.cuh, "hazard codes of a model"), so they go through k_select<BWA>;
+        // the frame machine then runs only the reads left at READ_PENDING.  The read queue borrows the deferred-search queue's
+        // place (4 read numbers per 16-byte slot) and is consumed before k_select_seeded starts filling that one.
+        if (method == GSM_METHOD_RMI && g_rmi_prefilter != 0 && se.rmi_bounds && rmi->hazard_slots && rmi->hazard_n_slots >= 2u &&
+            (rmi->hazard_n_slots & (rmi->hazard_n_slots - 1u)) == 0u && K <= 15u && se.fix_cap * 4ull >= rd->n_reads) {
+            se.hz_slots = rmi->hazard_slots; se.hz_mask = rmi->hazard_n_slots - 1u;
+            SelectArgs sb_ = se;                       // the BWA-SMEM selection of the queued reads: min_len 1, K flags reads shorter than K
+            sb_.min_len = 1u;
+            int grid_b = lb;
+            if ((st = resident_grid(k_select<GSM_METHOD_BWA>, SELECT_THREADS, 0, lb, &grid_b))) return st;
+            uint32_t* queue = (uint32_t*)se.fix;
+            k_rmi_prefilter<<<(unsigned)((rd->n_reads + 255) / 256), 256, 0, stream>>>(se, queue);
+            k_select<GSM_METHOD_BWA><<<grid_b, SELECT_THREADS, 0, stream>>>(sb_, queue);
+            GSM_CUDA(cudaGetLastError());
+            GSM_CUDA(cudaMemsetAsync((unsigned long long*)ws->counters + 4, 0, sizeof(uint64_t), stream));       // the queue is consumed
+            se.only_pending = 1u;
+        }
         if (method == GSM_METHOD_LUT) st = launch_seeded<GSM_METHOD_LUT, 0>(se, lb, stream);
         else if (se.rmi_bounds) st = launch_seeded<GSM_METHOD_RMI, 2>(se, lb, stream);
         else if (arith) st = launch_seeded<GSM_METHOD_RMI, 1>(se, lb, stream);

@@ -571,6 +571,64 @@ GSM_HD bool rmi_arith_lookup_loops(const RmiModel& m, int64_t row0, uint32_t A, 
     return true;
 }
 
+// ------------------------------------------------------------------------------------ hazard codes of a model
+// The result of RMI_LUT.get_suffix_rmi for a k-mer (RMI_LUT.py:67-78) is a function of the k-mer's CODE alone: the model's
+// prediction, the k-mer's true bounds and the K None rows are all fixed per (model, reference).  A code is a HAZARD iff
+// rmi_arith_lookup cannot certify that the literal search returns the true interval; every other code looks up exactly.
+// On a read none of whose windows is a hazard, get_smems_rmi (SMEM.py:206-384) sees at every lookup what get_smems_lut
+// (SMEM.py:20-192) with the same K sees -- hit iff the k-mer occurs, its true interval, and check_sequential over the same
+// positions (get_positions of the true rows = the table's position list) -- and the two routines are the same text line for
+// line apart from the lookup; get_smems_lut in turn emits get_SMEMS's records with min_len 1.  Such a
+// read therefore takes its RMI-SMEM records from the BWA-SMEM selection, and only reads with a hazard window run the frame
+// machine.  The hazard codes (a few thousand of 4^15 for a model worth using) are kept in an open-addressing hash set of
+// 32-bit codes (K <= 15: a code never equals HZ_EMPTY), at most half full, so a probe sequence always ends at an empty slot.
+constexpr uint32_t HZ_EMPTY = 0xFFFFFFFFu;
+
+GSM_HD bool rmi_code_is_hazard(const RmiModel& m, uint64_t code, uint32_t A, uint32_t cnt, uint32_t n_rows) {
+    int64_t lo, hi;
+    return !rmi_arith_lookup(m, RmiGallop::predicted_row(m, code, n_rows), A, cnt, n_rows, lo, hi);
+}
+
+GSM_HD uint32_t hz_slot(uint32_t code, uint32_t mask) { return ((code * 0x9E3779B1u) >> 8) & mask; }
+
+// slot(h) = h-th word of the table; mask = slots - 1 (a power of two)
+template <typename LoadSlot>
+GSM_HD bool hz_contains(LoadSlot slot, uint32_t mask, uint32_t code) {
+    for (uint32_t h = hz_slot(code, mask);; h = (h + 1u) & mask) {
+        const uint32_t v = slot(h);
+        if (v == code) return true;
+        if (v == HZ_EMPTY) return false;
+    }
+}
+
+// host: fill `slots` (n_slots words, a power of two >= 2 n + 2, at most 2^24) with the n codes; false if the table cannot take them
+inline bool hz_build(const uint32_t* codes, uint64_t n, uint32_t* slots, uint32_t n_slots) {
+    if (n_slots < 2u || (n_slots & (n_slots - 1u)) != 0u || n_slots > (1u << 24) || 2u * n + 2u > (uint64_t)n_slots) return false;
+    const uint32_t mask = n_slots - 1u;
+    for (uint32_t h = 0; h < n_slots; ++h) slots[h] = HZ_EMPTY;
+    for (uint64_t k = 0; k < n; ++k) {
+        if (codes[k] == HZ_EMPTY) return false;
+        uint32_t h = hz_slot(codes[k], mask);
+        while (slots[h] != HZ_EMPTY && slots[h] != codes[k]) h = (h + 1u) & mask;
+        slots[h] = codes[k];
+    }
+    return true;
+}
+
+// No window q[i:i+K), 0 <= i <= L-K, of the read is a hazard code (a read shorter than K has no window).  rd(w) = packed read
+// word w (2 bits per base, MSB first); the code of the window ending at base i is rolled from the one ending at i-1.  K <= 15.
+template <typename ReadW, typename LoadSlot>
+GSM_HD bool rmi_read_hazard_free(ReadW rd, uint32_t L, uint32_t K, LoadSlot slot, uint32_t mask) {
+    const uint32_t kmask = (1u << (2u * K)) - 1u;
+    uint32_t code = 0, w = 0;
+    for (uint32_t i = 0; i < L; ++i) {
+        if ((i & 15u) == 0u) w = rd(i >> 4);
+        code = ((code << 2) | ((w >> (30u - 2u * (i & 15u))) & 3u)) & kmask;
+        if (i + 1u >= K && hz_contains(slot, mask, code)) return false;
+    }
+    return true;
+}
+
 // True bounds (A, occurrences) of the K-mer q[cpos:cpos+K) from the sweep's seed table: entry of its last seed_K bases,
 // then K - seed_K backward steps.  The table stores the insertion point in fwd_lo for absent k-mers (cnt == 0) and a
 // backward step on an empty interval keeps tracking it, so (A, 0) is exact for absent k-mers too.

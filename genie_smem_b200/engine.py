@@ -599,10 +599,13 @@ class RmiParams:
         s.probe = None
         s.bounds = None
         s.none_rows, s.n_none_rows = None, 0
+        s.hazard_slots, s.hazard_n_slots, s.reserved0 = None, 0, 0
         self.c = s
         self.probe = None
         self.bounds = None
         self.none_rows = None
+        self.hazard_slots = None
+        self.n_hazards = None
 
     def persist_in_l2(self, on=True):
         """Pin the model parameters in the persisting L2 for kernels of the current stream (gsm_l2_persist): every
@@ -636,11 +639,50 @@ class RmiParams:
         with torch.cuda.device(index.device):
             capi.check(capi.lib.gsm_rmi_bounds_build(C.byref(index.c), self.K, _ptr(self.bounds), _stream()))
         self.c.bounds = self.bounds.data_ptr()
+        if self.none_rows is not None and self.K <= 15:
+            self.build_hazard_filter(index)
         return self
 
     def drop_bounds_table(self):
         self.bounds = None
         self.c.bounds = None
+        return self.drop_hazard_filter()
+
+    def build_hazard_filter(self, index, max_codes=1 << 18):
+        """The model's HAZARD codes -- the K-mers whose last-mile search is not certified to return the true interval, a few
+        per million for a model worth using -- as a hash set on the device (gsm_rmi_hazard_scan over all 4^K codes, then
+        gsm_rmi_hazard_hash on the host).  With it gsm_smem_select(RMI) hands every read without a hazard window to the
+        BWA-SMEM selection (same records, include/genie_smem.h) and runs the frame machine on the others only.  Needs the
+        None rows and the bounds table (build_bounds_table calls this).  A model with more than max_codes hazards gets no
+        filter (self.n_hazards says how many there were).  Results never depend on it."""
+        if self.bounds is None or self.none_rows is None:
+            raise ValueError("hazard filter: build_none_rows and build_bounds_table first")
+        if self.K > 15:
+            raise ValueError("hazard filter: K must be <= 15")
+        self.drop_hazard_filter()
+        codes = torch.empty(max_codes, dtype=torch.int32, device=index.device)
+        count = torch.zeros(1, dtype=torch.int64, device=index.device)
+        found = C.c_uint64(0)
+        with torch.cuda.device(index.device):
+            capi.check(capi.lib.gsm_rmi_hazard_scan(C.byref(index.c), C.byref(self.c), _ptr(codes), max_codes, _ptr(count), C.byref(found), _stream()))
+        self.n_hazards = int(found.value)
+        if self.n_hazards > max_codes:
+            return self
+        host = codes[:self.n_hazards].cpu().numpy().view(np.uint32)
+        n_slots = 1024
+        while n_slots < 4 * self.n_hazards + 4:
+            n_slots *= 2
+        slots = np.empty(n_slots, np.uint32)
+        capi.check(capi.lib.gsm_rmi_hazard_hash(host.ctypes.data, self.n_hazards, slots.ctypes.data, n_slots))
+        self.hazard_slots = torch.from_numpy(slots.view(np.int32)).to(index.device)
+        self.c.hazard_slots = self.hazard_slots.data_ptr()
+        self.c.hazard_n_slots = n_slots
+        return self
+
+    def drop_hazard_filter(self):
+        self.hazard_slots = None
+        self.c.hazard_slots = None
+        self.c.hazard_n_slots = 0
         return self
 
     def build_probe_table(self, index):
@@ -728,13 +770,17 @@ class Engine:
         r = self._check_batch(reads)
         capi.check(capi.lib.gsm_smem_select(method, C.byref(self.index.c), C.byref(r), int(min_len), int(K), _ptr(lut),
                                             C.byref(rmi.c) if rmi is not None else None, C.byref(self.ws), _stream()))
+        # RMI with a hazard filter: + k_rmi_prefilter and k_select<BWA> for the reads without a hazard window (the library
+        # applies the same conditions; a workspace too small for the read queue only makes this count two too high)
+        pre = 2 if (reads.n and method == capi.METHOD_RMI and rmi is not None and rmi.hazard_slots is not None and rmi.bounds is not None
+                    and capi.lib.gsm_option_rmi_prefilter(-1) != 0) else 0
         if gatherer is not None:
             gatherer.collect(self, r)
-            self.kernel_launches += (8 if self._picks_path(method) else 7) if reads.n else 1
+            self.kernel_launches += ((8 if self._picks_path(method) else 7) + pre) if reads.n else 1
             return
         capi.check(capi.lib.gsm_smem_collect(C.byref(r), C.byref(self.ws), _ptr(self.records), self.rec_cap, _stream()))
         # BWA: picked / queued / finish; LUT, RMI: select + the deferred explicit searches; then 3 scan kernels, ordered write
-        self.kernel_launches += (7 if self._picks_path(method) else 6) if reads.n else 0
+        self.kernel_launches += ((7 if self._picks_path(method) else 6) + pre) if reads.n else 0
 
     @staticmethod
     def _picks_path(method):
@@ -834,6 +880,14 @@ def sa_lookup(index: DeviceIndex, rows):
     out = torch.empty_like(r)
     capi.check(capi.lib.gsm_sa_lookup_batch(C.byref(index.c), rows.size, _ptr(r), _ptr(out), _stream()))
     return out.cpu().numpy().view(np.uint32)
+
+
+def set_rmi_prefilter(on=True):
+    """RMI-SMEM selection: True (default) = reads without a hazard window take their records from the BWA-SMEM selection when
+    the model carries a hazard filter (RmiParams.build_hazard_filter); False = every read runs the reference's frame machine
+    (k_select_seeded<RMI>, the cross-check: same records).  Process-wide (gsm_option_rmi_prefilter); returns the previous
+    setting."""
+    return bool(capi.lib.gsm_option_rmi_prefilter(1 if on else 0))
 
 
 def set_lut_frame_machine(on=True):

@@ -216,6 +216,10 @@ typedef struct {
     uint32_t param_stride;       /* elements between consecutive models in coef[] / intercept[]: 0 or 1 = two dense arrays;
                                     2 = one interleaved {coef, intercept} array (intercept == coef + 1): one line per model */
     const void* bounds;          /* device, optional: 4^K x 8 B from gsm_rmi_bounds_build (used with none_rows), else NULL */
+    const uint32_t* hazard_slots; /* device, optional: hash set of the model's hazard codes (gsm_rmi_hazard_scan +
+                                    gsm_rmi_hazard_hash; used with bounds), else NULL */
+    uint32_t hazard_n_slots;     /* words in hazard_slots (a power of two), or 0 */
+    uint32_t reserved0;
 } gsm_dev_rmi;
 
 /* Scratch + output buffers for one SMEM batch; all device memory, all caller-allocated.
@@ -361,6 +365,25 @@ int gsm_rmi_bounds_build(const gsm_dev_index* idx, uint32_t K, void* bounds, voi
  * selection kernel can prove, per lookup, that the literal exponential + binary search equals a plain error-bounded
  * binary search, and runs that instead; the literal search remains the path for every lookup it cannot prove. */
 int gsm_rmi_none_rows(const gsm_dev_index* idx, uint32_t K, uint32_t* rows_host, uint32_t* scratch, void* stream);
+
+/* RMI-SMEM pre-filter.  What RMI_LUT.get_suffix_rmi (RMI_LUT.py:67-78) returns for a K-mer is a function of its code alone
+ * (prediction, true bounds, None rows), and for all but a few codes per million -- the model's HAZARD codes -- it is the
+ * k-mer's true interval.  On a read none of whose windows is a hazard, get_smems_rmi (SMEM.py:206-384) makes the very lookups
+ * of get_smems_lut (SMEM.py:20-192; the two routines are the same text apart from the lookup) and so emits the records of
+ * get_SMEMS with min_len 1: gsm_smem_select(GSM_METHOD_RMI) hands such reads to the BWA-SMEM selection
+ * and runs the frame machine on the others only.  Results never depend on it.
+ *   gsm_rmi_hazard_scan: every hazard code of `rmi` (needs bounds + none_rows, K <= 15) appended to codes[] (device, cap
+ *     entries); *n_found (HOST) = how many there are -- more than cap: not all were stored, do not build the set.
+ *     count_dev: 8 bytes of device scratch.  Synchronises the stream.
+ *   gsm_rmi_hazard_hash (host only, no GPU needed): open-addressing set of n 32-bit codes in slots[n_slots], n_slots a power
+ *     of two in [2 n + 2, 2^24]; upload it and name it in gsm_dev_rmi.hazard_slots / hazard_n_slots.
+ *   gsm_option_rmi_prefilter: 1 (default) = use the set when present, 0 = frame machine for every read (the cross-check:
+ *     same records), < 0 = query; returns the previous setting.  Process-wide; GSM_RMI_PREFILTER in the environment sets the
+ *     initial value. */
+int gsm_rmi_hazard_scan(const gsm_dev_index* idx, const gsm_dev_rmi* rmi, uint32_t* codes, uint64_t cap, uint64_t* count_dev,
+                        uint64_t* n_found, void* stream);
+int gsm_rmi_hazard_hash(const uint32_t* codes, uint64_t n, uint32_t* slots, uint32_t n_slots);
+int gsm_option_rmi_prefilter(int on);
 
 /* RMI_LUT.get_suffix_rmi (RMI_LUT.py:67-78) for a batch of K-mer codes: predict + exponential
  * + binary last-mile search.  pred receives the float64 prediction, lo/hi the returned pair

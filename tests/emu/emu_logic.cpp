@@ -479,4 +479,44 @@ uint64_t emu_rmi_arith_fuzz(uint32_t n_rows, uint32_t n_none, const uint32_t* no
     return bad;
 }
 
+// The hazard codes of a model (rmi_code_is_hazard over every K-mer code, true bounds by a plain backward search continued
+// through empty intervals, as emu_rmi_arith): writes up to cap codes, returns how many there are.  What k_rmi_hazard_scan computes.
+uint64_t emu_rmi_hazards(const EmuIndex* ei, uint32_t K, uint32_t n_levels, const uint32_t* level_sizes, const double* coef,
+                         const double* intercept, uint32_t n_none, const uint32_t* none_rows, uint32_t* out, uint64_t cap) {
+    RmiModel m; memset(&m, 0, sizeof(m));
+    m.K = K; m.n_levels = n_levels; m.coef = coef; m.intercept = intercept; m.stride = 1;
+    uint32_t off = 0;
+    for (uint32_t l = 0; l < n_levels; ++l) { m.level_size[l] = level_sizes[l]; m.level_off[l] = off; off += level_sizes[l]; }
+    rmi_set_none_rows(m, none_rows, n_none, ei->n_rows);
+    const Half* fwd = (const Half*)ei->fwd;
+    auto load = [&](uint64_t idx) { return fwd[idx]; };
+    uint64_t n = 0;
+    for (uint64_t code = 0; code < (1ull << (2 * K)); ++code) {
+        uint32_t A = 0, cnt = ei->n_rows;
+        for (uint32_t t = 0; t < K; ++t) {
+            const uint32_t c = (uint32_t)(code >> (2 * t)) & 3u;
+            const StepOut r = step_single(load, A, A + cnt, c, ei->C[c], ei->prim_f);
+            A = r.lo_new; cnt = r.cnt_new;
+        }
+        if (rmi_code_is_hazard(m, code, A, cnt, ei->n_rows)) { if (n < cap) out[n] = (uint32_t)code; ++n; }
+    }
+    return n;
+}
+
+int emu_hz_build(const uint32_t* codes, uint64_t n, uint32_t* slots, uint32_t n_slots) { return hz_build(codes, n, slots, n_slots) ? 1 : 0; }
+
+int emu_hz_contains(const uint32_t* slots, uint32_t n_slots, uint32_t code) {
+    return hz_contains([slots](uint32_t h) { return slots[h]; }, n_slots - 1u, code) ? 1 : 0;
+}
+
+// rmi_read_hazard_free on a packed read, as k_rmi_prefilter calls it
+int emu_read_hazard_free(const uint32_t* words, uint32_t L, uint32_t K, const uint32_t* slots, uint32_t n_slots) {
+    return rmi_read_hazard_free([words](uint32_t w) { return words[w]; }, L, K, [slots](uint32_t h) { return slots[h]; }, n_slots - 1u) ? 1 : 0;
+}
+
+// kmer_code of the window at base p (what the selection kernels look up), for the cross-check of the rolled codes
+uint64_t emu_kmer_code(const uint32_t* words, uint32_t p, uint32_t K) {
+    return kmer_code([words](uint64_t w) { return words[w]; }, p, K);
+}
+
 }  // extern "C"

@@ -50,6 +50,13 @@ class Emu:
         self.lib.emu_rmi_arith_fuzz.restype = u64
         self.lib.emu_rmi_search.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                             C.POINTER(u32)]
+        self.lib.emu_rmi_hazards.argtypes = [C.POINTER(EmuIndex), u32, u32, P, P, P, u32, P, P, u64]
+        self.lib.emu_rmi_hazards.restype = u64
+        self.lib.emu_hz_build.argtypes = [P, u64, P, u32]
+        self.lib.emu_hz_contains.argtypes = [P, u32, u32]
+        self.lib.emu_read_hazard_free.argtypes = [P, u32, u32, P, u32]
+        self.lib.emu_kmer_code.argtypes = [P, u32, u32]
+        self.lib.emu_kmer_code.restype = u64
         self.lib.emu_locate.argtypes = [C.POINTER(EmuIndex), u32, u64, P, P]
         self.lib.emu_seed_build.argtypes = [C.POINTER(EmuIndex), u32, P]
         self.lib.emu_counters.argtypes = [P, C.c_int]
@@ -235,6 +242,32 @@ def _rmi_arith(self, rmi, code):
 
 
 Emu.rmi_arith_lookup = _rmi_arith
+
+
+def _rmi_hazards(self, rmi):
+    """Sorted hazard codes of a model on this index (rmi_code_is_hazard over all 4^K codes): the set k_rmi_hazard_scan finds."""
+    ls = np.asarray(rmi["level_sizes"], np.uint32)
+    coef = np.ascontiguousarray(rmi["coef"], np.float64)
+    icpt = np.ascontiguousarray(rmi["intercept"], np.float64)
+    nr = self.none_rows(rmi["K"])
+    cap = 1 << (2 * rmi["K"])
+    out = np.zeros(cap, np.uint32)
+    n = self.lib.emu_rmi_hazards(C.byref(self.e), rmi["K"], len(ls), ls.ctypes.data, coef.ctypes.data, icpt.ctypes.data, len(nr), nr.ctypes.data,
+                                 out.ctypes.data, cap)
+    return np.sort(out[:n])
+
+
+Emu.rmi_hazards = _rmi_hazards
+
+
+def hazard_table(lib, codes):
+    """Open-addressing table of the codes (hz_build), sized as RmiParams.build_hazard_filter sizes it; None if it refuses."""
+    codes = np.ascontiguousarray(codes, np.uint32)
+    n_slots = 1024
+    while n_slots < 4 * len(codes) + 4:
+        n_slots *= 2
+    slots = np.zeros(n_slots, np.uint32)
+    return slots if lib.emu_hz_build(codes.ctypes.data, len(codes), slots.ctypes.data, n_slots) else None
 
 
 def records_to_dict(q, recs):

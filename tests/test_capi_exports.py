@@ -35,6 +35,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(capi.DevIndex) == 2 * 8 + 4 * 8 + 5 * 4 + 3 * 4 + 8      # + seed_table pointer
     assert C.sizeof(capi.DevReads) == 8 + 3 * 8 + 2 * 4
     assert C.sizeof(capi.Workspace) == 15 * 8
+    assert C.sizeof(capi.DevRmi) == 2 * 4 + 5 * 8 + 2 * 4 + 8 + 8 + 2 * 4      # ... bounds, hazard_slots, hazard_n_slots, reserved0
     from genie_smem_b200.engine import RECORD_DTYPE
     assert RECORD_DTYPE.itemsize == 16
 
@@ -118,3 +119,33 @@ def test_device_entry_points_refuse_without_gpu():
     wi = capi.WorkspaceInfo()
     assert capi.lib.gsm_smem_workspace_info(10, 100, C.byref(wi)) == capi.E_NODEVICE
     assert b"no CPU fallback" in capi.lib.gsm_last_error()
+
+
+def test_hazard_hash_is_an_exact_set():
+    """gsm_rmi_hazard_hash (host only): the open-addressing table holds exactly the given codes, stays at most half full, and
+    refuses sizes that could not terminate a probe sequence."""
+    from genie_smem_b200 import _capi as capi
+    from tests.emu.harness import build as build_emu
+    emu = C.CDLL(build_emu())
+    emu.emu_hz_contains.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 7, 511, 5000):
+        codes = np.unique(rng.integers(0, 1 << 30, n).astype(np.uint32))
+        if n >= 7:
+            codes[:3] = (0, 1, (1 << 30) - 1)
+            codes = np.unique(codes)
+        n_slots = 1024
+        while n_slots < 4 * len(codes) + 4:
+            n_slots *= 2
+        slots = np.zeros(n_slots, np.uint32)
+        capi.check(capi.lib.gsm_rmi_hazard_hash(codes.ctypes.data, len(codes), slots.ctypes.data, n_slots))
+        assert sorted(slots[slots != 0xFFFFFFFF].tolist()) == codes.tolist()
+        inside = set(codes.tolist())
+        for c in list(codes[:200]) + rng.integers(0, 1 << 30, 300).tolist():
+            assert bool(emu.emu_hz_contains(slots.ctypes.data, n_slots, int(c))) == (int(c) in inside)
+    codes = np.arange(600, dtype=np.uint32)
+    slots = np.zeros(1024, np.uint32)
+    assert capi.lib.gsm_rmi_hazard_hash(codes.ctypes.data, 600, slots.ctypes.data, 1024) == capi.E_INVALID      # more than half full
+    assert capi.lib.gsm_rmi_hazard_hash(codes.ctypes.data, 10, slots.ctypes.data, 1000) == capi.E_INVALID       # not a power of two
+    bad = np.asarray([5, 0xFFFFFFFF], np.uint32)
+    assert capi.lib.gsm_rmi_hazard_hash(bad.ctypes.data, 2, slots.ctypes.data, 1024) == capi.E_INVALID          # the empty marker

@@ -425,17 +425,28 @@ def test_rmi_fast_search_changes_nothing(gs):
     idx = gs.DeviceIndex.build_on_device(ref).build_seed_table()
     batch = gs.ReadBatch.from_codes(reads, L)
     e = gs.Engine(idx, len(reads), L, mems_per_read=64, recs_per_read=64)
+    n_filters = 0
     for K, experts in ((9, (16, 512)), (11, (64, 4096)), (8, (1, 1))):
         rmi = bench.train_rmi(idx, K, experts, idx.device)                # probe table + None rows
         assert rmi.c.n_none_rows == K
         fast = e.run(gs.METHOD_RMI, batch, rmi=rmi)
         fr, fo, fs = fast.records.copy(), fast.offsets.copy(), fast.status.copy()
-        bnd = e.run(gs.METHOD_RMI, batch, rmi=rmi.build_bounds_table(idx))   # true bounds from the dense table
-        assert np.array_equal(fo, bnd.offsets) and np.array_equal(fr, bnd.records) and np.array_equal(fs, bnd.status)
+        bnd = e.run(gs.METHOD_RMI, batch, rmi=rmi.build_bounds_table(idx))   # true bounds from the dense table; with the hazard
+        assert np.array_equal(fo, bnd.offsets) and np.array_equal(fr, bnd.records) and np.array_equal(fs, bnd.status)   # filter: pre-filtered
+        n_filters += rmi.hazard_slots is not None
+        assert rmi.n_hazards is not None and (rmi.hazard_slots is not None) == (rmi.n_hazards <= 1 << 18)
+        try:
+            gs.set_rmi_prefilter(False)                                       # bounds table, frame machine on every read
+            bnd = e.run(gs.METHOD_RMI, batch, rmi=rmi)
+            assert np.array_equal(fo, bnd.offsets) and np.array_equal(fr, bnd.records) and np.array_equal(fs, bnd.status)
+        finally:
+            gs.set_rmi_prefilter(True)
         rmi.drop_bounds_table()
+        assert rmi.hazard_slots is None and rmi.c.hazard_n_slots == 0
         rmi.c.none_rows, rmi.c.n_none_rows = None, 0                      # literal search only
         lit = e.run(gs.METHOD_RMI, batch, rmi=rmi)
         assert np.array_equal(fo, lit.offsets) and np.array_equal(fr, lit.records) and np.array_equal(fs, lit.status)
+    assert n_filters >= 2                                                 # the pre-filter ran (K = 8, 9: at most 4^K <= 2^18 hazard codes)
 
 
 def _codes_to_strings(reads):
@@ -501,17 +512,25 @@ def test_all_methods_vs_oracle_on_synthetic_reference(gs, seed_table):
             assert np.array_equal(picks[0], res.records) and np.array_equal(picks[1], res.offsets) and np.array_equal(picks[2], res.status)
     finally:
         gs.set_lut_frame_machine(False)
-    n_raise = 0
+    n_raise = n_filters = 0
     for K, experts in ((11, (64, 4096)), (15, (256, 16384)), (9, (4, 64))):
         rmi = bench.train_rmi(idx, K, experts, idx.device)
         res = e.run(gs.METHOD_RMI, batch, rmi=rmi)
         exp = o.smem_dicts(2, reads_s, rmi=bench.rmi_dict(rmi))
         n_raise += _check_against_oracle(gs, res, reads_s, exp, f"rmi K={K}")
-        rmi.build_bounds_table(idx)                                       # lookups from the dense k-mer bounds table
-        res = e.run(gs.METHOD_RMI, batch, rmi=rmi)
-        _check_against_oracle(gs, res, reads_s, exp, f"rmi K={K}, bounds table")
+        rmi.build_bounds_table(idx)                                       # lookups from the dense k-mer bounds table; reads without a
+        res = e.run(gs.METHOD_RMI, batch, rmi=rmi)                        # hazard window pre-filtered to the BWA-SMEM selection
+        _check_against_oracle(gs, res, reads_s, exp, f"rmi K={K}, bounds table, pre-filter {rmi.hazard_slots is not None} ({rmi.n_hazards} hazard codes)")
+        n_filters += rmi.hazard_slots is not None
+        try:
+            gs.set_rmi_prefilter(False)                                   # the frame machine on every read
+            res = e.run(gs.METHOD_RMI, batch, rmi=rmi)
+            _check_against_oracle(gs, res, reads_s, exp, f"rmi K={K}, bounds table, frame machine")
+        finally:
+            gs.set_rmi_prefilter(True)
         rmi.drop_bounds_table()
     assert n_raise < 200
+    assert n_filters >= 1
 
 
 def test_add_one_vs_oracle_on_many_pairs(gs, matchers, oracles):

@@ -363,3 +363,80 @@ def test_lf_walk_to_sampled_rows_recovers_the_suffix_array(emus, name):
     rows = np.arange(len(sa), dtype=np.uint32) if len(sa) < 5000 else np.random.default_rng(1).integers(0, len(sa), 4000).astype(np.uint32)
     for sample in (1, 2, 7, 32, 1 << 30):
         assert np.array_equal(em.locate(rows, sample), sa[rows]), sample
+
+
+def _bad_model(p, rng):
+    """The golden model with its leaf intercepts shifted by up to a few hundred rows: predictions far off, many hazards."""
+    q = dict(p)
+    icpt = np.array(p["intercept"], np.float64)
+    n_root = int(p["level_sizes"][0])
+    icpt[n_root:] += rng.integers(-300, 300, len(icpt) - n_root)
+    q["intercept"] = icpt
+    return q
+
+
+@pytest.mark.parametrize("tag,name,bad", [("medium_data_k6", "medium_data", False), ("medium_data_k6", "medium_data", True)])
+def test_rmi_hazard_free_reads_take_the_picks(emus, tag, name, bad):
+    """The RMI-SMEM pre-filter (k_rmi_hazard_scan / k_rmi_prefilter): (1) a code outside the hazard set looks up exactly -- the
+    literal search returns the k-mer's true interval; (2) rmi_read_hazard_free on rolled window codes == membership of every
+    kmer_code window in the set; (3) a read without a hazard window emits, through the frame machine (Selector::run_seeded<RMI>),
+    exactly the records of BWA-SMEM with min_len 1 (Selector::run_bwa) -- what lets gsm_smem_select(RMI) hand such reads to
+    k_select<BWA>."""
+    from tests.emu.harness import hazard_table
+    g, em = emus[name]
+    text = g["text"]
+    rng = np.random.default_rng(11)
+    p = gu.load_rmi(tag)
+    if bad:
+        p = _bad_model(p, rng)
+    K = p["K"]
+    hz = em.rmi_hazards(p)
+    hz_set = set(int(c) for c in hz)
+    slots = hazard_table(em.lib, hz)
+    assert slots is not None and (slots != 0xFFFFFFFF).sum() == len(hz_set)
+    assert 0 < len(hz_set) < 4 ** K
+    # (1) exact lookups outside the set; inside the set the table says so
+    codes = np.arange(4 ** K) if K <= 6 else rng.integers(0, 4 ** K, 4000)
+    for code in codes:
+        code = int(code)
+        inside = bool(em.lib.emu_hz_contains(slots.ctypes.data, len(slots), code))
+        assert inside == (code in hz_set)
+        hazard, lo, hi = em.rmi_arith_lookup(p, code)
+        assert hazard == inside
+        if not inside:
+            s, _, glo, ghi = em.rmi_lookup(p, code)           # the literal RMI_LUT search
+            assert s == 0 and (glo, ghi) == (lo, hi), code
+            kmer = "".join("ACGT"[(code >> (2 * (K - 1 - t))) & 3] for t in range(K))
+            assert (hi - lo + 1) == sum(1 for i in range(len(text) - K + 1) if text.startswith(kmer, i)) or K > 6
+    # (2), (3)
+    reads = []
+    rnd = random.Random(5)
+    for _ in range(220):
+        L = rnd.choice((K, K + 1, 25, 60, 101, 151))
+        L = min(L, len(text) - 1)
+        s0 = rnd.randrange(0, len(text) - L)
+        q = list(text[s0:s0 + L])
+        pm = rnd.choice((0.0, 0.01, 0.05, 0.3))
+        for k in range(L):
+            if rnd.random() < pm:
+                q[k] = rnd.choice("ACGT")
+        reads.append("".join(q))
+    reads += ["".join(rnd.choice("ACGT") for _ in range(rnd.choice((K, 40, 101)))) for _ in range(40)]
+    reads += ["A" * 40, "AC" * 25, text[-60:], text[:50], text[-(K + 3):]]
+    n_free = n_hazard = 0
+    em.rmi_fast = True
+    try:
+        for q in reads:
+            w = em.pack_read(q)
+            window_codes = [int(em.lib.emu_kmer_code(w.ctypes.data, i, K)) for i in range(len(q) - K + 1)]
+            want = not any(c in hz_set for c in window_codes)
+            got = bool(em.lib.emu_read_hazard_free(w.ctypes.data, len(q), K, slots.ctypes.data, len(slots)))
+            assert got == want, q
+            if got:
+                n_free += 1
+                assert em.smem(2, q, rmi=p) == em.smem(0, q, min_len=1), q
+            else:
+                n_hazard += 1
+    finally:
+        em.rmi_fast = False
+    assert n_free >= 20 and n_hazard >= 1, (n_free, n_hazard)
