@@ -124,3 +124,13 @@ def test_smems_sub151(indexes):
 
 def test_smems_medium_fuzz(indexes):
     _check_set(indexes, "smems_medium_fuzz.json.gz", stride=5)
+
+
+def test_python_baseline_tool_reports_every_method():
+    """bench.py's cpu_baseline.python_port: one process and a pool, three methods, core count stated."""
+    import bench
+    out = bench.python_port_baseline(0.2)
+    assert "unavailable" not in out, out
+    assert out["cores"] >= 1
+    for m in ("bwa", "lut", "rmi"):
+        assert out[f"{m}_reads_per_s_one_process"] > 0 and out[f"{m}_reads_per_s_pool"] > 0
