@@ -440,3 +440,53 @@ def test_rmi_hazard_free_reads_take_the_picks(emus, tag, name, bad):
     finally:
         em.rmi_fast = False
     assert n_free >= 20 and n_hazard >= 1, (n_free, n_hazard)
+
+
+@pytest.mark.parametrize("tag,name", [("medium_data_k6", "medium_data"), ("big_data_k12", "big_data"), ("big_data_k15", "big_data")])
+def test_get_smems_rmi_equals_get_SMEMS_when_every_window_looks_up_exactly(tag, name):
+    """The identity behind the RMI-SMEM pre-filter, on the literal Python restatement (oracle/ref_port.py, pinned to the golden
+    vectors): if get_suffix_rmi returns the true interval for every K-mer window of a read (hit <=> the k-mer occurs),
+    get_smems_rmi(q) == get_SMEMS(q, 1) as ordered dicts -- with the reference-trained models and with perturbed ones."""
+    g = gu.load_index(name)
+    text = g["text"]
+    idx = rp.RefIndex(text, g["suffix_array"])
+    p = gu.load_rmi(tag)
+    K = p["K"]
+    rnd = random.Random(len(text) + K)
+    n_same = n_skipped = 0
+    for bad in (False, True):
+        icpt = np.array(p["intercept"], np.float64)
+        if bad:
+            n_root = int(p["level_sizes"][0])
+            icpt[n_root:] += np.random.default_rng(3).integers(-40, 40, len(icpt) - n_root)
+        rmi = rp.RefRMI(idx, K, p["level_sizes"], p["coef"], icpt)
+        o = rp.RefSMEM(idx, rmi=rmi)
+        for _ in range(60 if K > 6 else 120):
+            L = rnd.choice((K, K + 2, 30, 60, 101))
+            s0 = rnd.randrange(0, len(text) - L)
+            q = list(text[s0:s0 + L])
+            pm = rnd.choice((0.0, 0.02, 0.1))
+            for k in range(L):
+                if rnd.random() < pm:
+                    q[k] = rnd.choice("ACGT")
+            q = "".join(q)
+            exact = True
+            for i in range(L - K + 1):
+                kmer = q[i:i + K]
+                true = idx.exact_match_back_prop(kmer)
+                try:
+                    got = rmi.get_suffix_rmi(kmer)
+                except (IndexError, RecursionError, TypeError):
+                    exact = False
+                    break
+                if (true == -1 and got[1] >= got[0]) or (true != -1 and tuple(got) != tuple(true)):
+                    exact = False
+                    break
+            if not exact:
+                n_skipped += 1
+                continue
+            a = o.get_SMEMS(q, 1)
+            b = {k: tuple(v) for k, v in o.get_smems_rmi(q).items()}
+            assert a == b and list(a) == list(b), (bad, q)
+            n_same += 1
+    assert n_same >= 40, (n_same, n_skipped)
