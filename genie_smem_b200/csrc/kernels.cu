@@ -9,7 +9,10 @@
 //     value / text words).  Finished reads hand their match lists over cooperatively (flush_finished): ordered, field by
 //     field, and with the BWA-SMEM picks already made.  k_sweep (lane pairs, round 1) is kept behind GSM_SWEEP_LPR=2.
 //   * BWA-SMEM selection: k_select_bwa_picked (count + min_len filter where the sweep made the picks), k_select<BWA> (one
-//     thread per read, Selector::run_bwa) for the reads it queues, k_select_bwa_finish.
+//     thread per read, Selector::run_bwa) for the reads it queues, k_select_bwa_finish.  LUT-SMEM takes the same records
+//     (get_smems_lut == get_SMEMS with min_len 1 on reads of >= K bases) unless the frame machine is
+//     asked for.  RMI-SMEM: k_rmi_prefilter sends every read without a hazard window (k_rmi_hazard_scan: the K-mer codes
+//     whose last-mile search is not certified exact) through k_select<BWA> as well; only the others run the frame machine.
 //   * k_select_seeded<LUT|RMI>: persistent threads, one read per thread, the reference's frame machine one ROUND at a
 //     time with the warp in lock step: pass 1 = all table lookups of the round, spread evenly over the warp's lanes, results
 //     in shared memory (LUT gather; RMI predict + true bounds from the k-mer bounds table or the seed table + the
