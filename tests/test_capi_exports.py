@@ -149,3 +149,22 @@ def test_hazard_hash_is_an_exact_set():
     assert capi.lib.gsm_rmi_hazard_hash(codes.ctypes.data, 10, slots.ctypes.data, 1000) == capi.E_INVALID       # not a power of two
     bad = np.asarray([5, 0xFFFFFFFF], np.uint32)
     assert capi.lib.gsm_rmi_hazard_hash(bad.ctypes.data, 2, slots.ctypes.data, 1024) == capi.E_INVALID          # the empty marker
+
+
+def test_header_is_plain_c_and_agrees_with_the_bindings(tmp_path):
+    """include/genie_smem.h compiles as C99 (no C++ or torch types in the boundary), links against the library, and its struct
+    sizes are the ones the ctypes bindings assume."""
+    import subprocess
+    from genie_smem_b200 import _capi as capi
+    src = tmp_path / "abi.c"
+    src.write_text('#include "genie_smem.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %d\\n", sizeof(gsm_dev_index), sizeof(gsm_dev_reads), sizeof(gsm_record),\n'
+                   '    sizeof(gsm_dev_rmi), sizeof(gsm_workspace), sizeof(gsm_workspace_info), (int)gsm_version()); return 0; }\n')
+    exe = tmp_path / "abi"
+    lib_dir = os.path.dirname(capi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", lib_dir, "-lgenie_smem", f"-Wl,-rpath,{lib_dir}"])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    sizes = [int(x) for x in out[:6]]
+    assert sizes == [C.sizeof(capi.DevIndex), C.sizeof(capi.DevReads), 16, C.sizeof(capi.DevRmi), C.sizeof(capi.Workspace), C.sizeof(capi.WorkspaceInfo)]
+    assert int(out[6]) == capi.lib.gsm_version()
