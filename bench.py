@@ -699,6 +699,7 @@ def main():
                "maximal_matches_per_read": round(n_mems / n_reads, 3), "gathered": gathered, "record_gather": record_gather, "locate": locate,
                "index_build": index.build_stats}
         out["sweep_seed_table_K"] = int(index.c.seed_K)
+        out["limiter"] = name_limiter(ms_bwa, ms_sweep, ms_sel_bwa, e2e, job_reads, world)
         if world > 1:
             out["value_includes"] = "sweep + select + scan + ordered write of every rank, the write being the gather into rank 0's HBM (NVLink), + completion fence"
             out["gather_transport"] = ("peer mapping (CUDA IPC): each rank's ordered-write kernel stores into rank 0's buffer" if gat.fused else
@@ -710,6 +711,30 @@ def main():
     if bad:
         log(f"PARITY FAILURE: {parity}")
         sys.exit(3)
+
+
+def name_limiter(ms_step, ms_sweep, ms_select, e2e, job_reads, world):
+    """What bounds the step at this N, from the numbers measured above (never raises: the record matters more)."""
+    try:
+        other = max(ms_step - ms_sweep - ms_select, 0.0)
+        rest = ("NVLink ingest of the other ranks' records into rank 0 + completion fence + kernel tails" if world > 1
+                else "launch gaps between the kernels")
+        parts = {"k_sweep1 (request-rate bound random 16..64-byte fetches, see roofline)": ms_sweep,
+                 "selection + scan + ordered write": ms_select, rest: other}
+        top = max(parts, key=parts.get)
+        out = {"device": {"limiter": top, "share_of_step": round(parts[top] / ms_step, 3), "ms_step": round(ms_step, 3),
+                          "ms_sweep": round(ms_sweep, 3), "ms_select_scan_write_local": round(ms_select, 3), "ms_rest": round(other, 3)}}
+        e2e_ms = job_reads / e2e["value"] * 1e3
+        gb = (e2e.get("h2d_bytes_per_step", 0) + e2e.get("d2h_bytes_per_step", 0)) / 1e9
+        if e2e_ms <= 1.1 * ms_step:
+            why = "the device kernels (copies and chunk launches hidden behind them)"
+        else:
+            why = (f"the host side: {e2e_ms - ms_step:.1f} ms per step beyond the kernels -- first-chunk H2D / last-chunk D2H that cannot overlap, "
+                   f"per-chunk launches and the Python loop around them ({gb:.2f} GB cross PCIe per rank and step)")
+        out["e2e"] = {"limiter": why, "ms_step": round(e2e_ms, 3), "over_device_step": round(e2e_ms / ms_step, 3)}
+        return out
+    except Exception as e:          # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
 
 
 def fastq_leg(g, pipe, reads_head, n_rec_expected):

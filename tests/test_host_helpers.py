@@ -110,3 +110,19 @@ def test_host_read_packer_multithreaded_equals_bitwise_definition():
     bad[start + 3] = ord("N")
     with pytest.raises(ValueError, match="read 7000"):
         capi.check(capi.lib.gsm_pack_reads(bytes(bad), lens.ctypes.data, len(lens), off.ctypes.data, packed.ctypes.data))
+
+
+def test_bench_names_the_limiter_from_its_own_numbers():
+    """bench.py's `limiter` object on the committed 1- and 8-GPU records: the sweep kernel bounds the device step; end to end the
+    host side shows up once the per-rank batch is small.  Never raises on a malformed record."""
+    import json
+    import os
+    import bench
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name, world in (("r02_bench_c4_1gpu.json", 1), ("r02_bench_c4_8gpu.json", 8)):
+        d = json.load(open(os.path.join(root, "profiles", name)))
+        lim = bench.name_limiter(d["ms_per_step"], d["roofline"]["ms_sweep"], d["roofline"]["ms_select_scan_write"], d["e2e"], 50_000_000, world)
+        assert lim["device"]["limiter"].startswith("k_sweep1") and 0.7 < lim["device"]["share_of_step"] <= 1.0
+        assert abs(lim["device"]["ms_sweep"] + lim["device"]["ms_select_scan_write_local"] + lim["device"]["ms_rest"] - d["ms_per_step"]) < 0.01
+        assert lim["e2e"]["over_device_step"] >= 1.0
+    assert "unavailable" in bench.name_limiter(1.0, 0.5, 0.2, None, 10, 1)
