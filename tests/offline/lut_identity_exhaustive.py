@@ -5,10 +5,10 @@
 
 Both sides are the C restatement of the reference (oracle/smem_oracle.c, pinned to tests/golden): every reference text over
 ACGT of length 4..n_max that contains all four bases x every read over ACGT of length 1..l_max x K = 1..k_max.  Test
-infrastructure only (imports oracle/); tests/test_logic_emu.py runs a bounded slice of it.
+infrastructure only (imports oracle/; lives under tests/ for that reason); tests/test_oracle_c.py runs a bounded slice of it.
 
-    python tools/lut_identity_exhaustive.py [n_max=6] [l_max=7] [k_max=4]
-    python tools/lut_identity_exhaustive.py ac [n_max=12] [l_max=10] [k_max=6]   # repetitive worlds: references = every string
+    python tests/offline/lut_identity_exhaustive.py [n_max=6] [l_max=7] [k_max=4]
+    python tests/offline/lut_identity_exhaustive.py ac [n_max=12] [l_max=10] [k_max=6]   # repetitive worlds: references = every string
                                                                                  # over AC of 2..n_max bases + "GT", reads over AC
 """
 import itertools
@@ -17,7 +17,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 
 
 def all_reads(l_max, alphabet="ACGT"):

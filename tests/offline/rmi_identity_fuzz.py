@@ -4,7 +4,7 @@
 whose K-mer windows ALL look up exactly through get_suffix_rmi (hit <=> the k-mer occurs, true interval) must satisfy
 get_smems_rmi(q) == get_SMEMS(q, 1) as ordered dicts.  Test infrastructure (imports oracle/).
 
-    python tools/rmi_identity_fuzz.py [seed] [seconds]        (round 2: 6 seeds x 420 s = 4.79 M identical cases, 0 differences)
+    python tests/offline/rmi_identity_fuzz.py [seed] [seconds]        (round 2: 6 seeds x 420 s = 4.79 M identical cases, 0 differences)
 """
 import os
 import random
@@ -13,7 +13,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
 import genie_smem_b200 as gs
 from oracle import ref_port as rp
 from __graft_entry__ import _rmi_keys

@@ -72,11 +72,11 @@ def test_smem_sets(orcs, fname):
 def test_lut_identity_exhaustive_slice():
     """get_smems_lut == get_SMEMS(min_len 1) record for record on reads of at least K bases -- the identity
     gsm_smem_select(LUT) relies on -- exhaustively on a small world: every reference over ACGT of 4..5
-    bases that contains all four, every read of 1..5 bases, K = 1..3 (tools/lut_identity_exhaustive.py ran 4..7 x 1..7 x 1..4)."""
+    bases that contains all four, every read of 1..5 bases, K = 1..3 (tests/offline/lut_identity_exhaustive.py ran 4..7 x 1..7 x 1..4)."""
     import importlib.util
     import os
     spec = importlib.util.spec_from_file_location(
-        "lut_identity_exhaustive", os.path.join(os.path.dirname(__file__), "..", "tools", "lut_identity_exhaustive.py"))
+        "lut_identity_exhaustive", os.path.join(os.path.dirname(__file__), "offline", "lut_identity_exhaustive.py"))
     tool = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(tool)
     reads = tool.all_reads(5)
