@@ -490,3 +490,34 @@ def test_get_smems_rmi_equals_get_SMEMS_when_every_window_looks_up_exactly(tag, 
             assert a == b and list(a) == list(b), (bad, q)
             n_same += 1
     assert n_same >= 40, (n_same, n_skipped)
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.text(alphabet="ACGT", min_size=0, max_size=200), st.integers(1, 15), st.integers(0, 2 ** 32 - 1))
+def test_read_hazard_free_is_window_membership(q, K, seed):
+    """rmi_read_hazard_free (rolled 2-bit window codes + open-addressing probes) == "no window's kmer_code is in the set", for
+    any read length (also shorter than K, also ending exactly at a 16-base word boundary), any K <= 15 and sets that hold some
+    of the read's own windows."""
+    from tests.emu.harness import build, hazard_table
+    import ctypes as C
+    lib = C.CDLL(build())
+    lib.emu_read_hazard_free.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+    lib.emu_hz_build.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
+    rnd = random.Random(seed)
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    windows = []
+    for i in range(len(q) - K + 1):
+        v = 0
+        for ch in q[i:i + K]:
+            v = v * 4 + code[ch]
+        windows.append(v)
+    members = set(rnd.randrange(0, 4 ** K) for _ in range(rnd.choice((0, 1, 5, 300))))
+    if windows and rnd.random() < 0.5:
+        members |= set(rnd.sample(windows, min(len(windows), rnd.choice((1, 2)))))
+    slots = hazard_table(lib, np.asarray(sorted(members), np.uint32))
+    assert slots is not None
+    words = np.zeros(len(q) // 16 + 3, np.uint32)
+    for i, ch in enumerate(q):
+        words[i >> 4] |= np.uint32(code[ch] << (30 - 2 * (i & 15)))
+    got = bool(lib.emu_read_hazard_free(words.ctypes.data, len(q), K, slots.ctypes.data, len(slots)))
+    assert got == (not any(w in members for w in windows))
