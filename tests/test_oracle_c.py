@@ -98,3 +98,24 @@ def test_base_absent_from_the_reference_raises():
         got = o.smem_dicts(method, reads, **kw)
         assert [g == "raises" for g in got] == [False, True, True, False, True]
         assert got[0][0][0] == "AAGT" and got[3][0][0] == "GGTT"
+
+
+def test_rmi_identity_exhaustive_slice():
+    """get_smems_rmi == get_SMEMS(min_len 1) for every read whose windows all look up exactly -- the identity behind the RMI-SMEM
+    pre-filter -- exhaustively on a small world: every reference over ACGT of 4..5 bases with all four
+    bases, a trained and a perturbed model, K = 1..3, every read of K..5 bases (tests/offline/rmi_identity_exhaustive.py ran
+    larger worlds)."""
+    import importlib.util
+    import itertools
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "rmi_identity_exhaustive", os.path.join(os.path.dirname(__file__), "offline", "rmi_identity_exhaustive.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    texts = ["".join(t) for n in (4, 5) for t in itertools.product("ACGT", repeat=n) if len(set(t)) == 4]
+    n_same = n_skip = 0
+    for i, t in enumerate(texts[::3]):
+        a, b = tool.check_text(t, 5, 3, i)
+        n_same += a
+        n_skip += b
+    assert n_same > 50_000 and n_skip > 0
